@@ -1,0 +1,87 @@
+"""The oracle restatement (oracle/swinv2_oracle.py) against outputs of the REAL reference.
+
+The golden files were produced by tests/golden/make_golden.py, which imports stockeh/swift from
+/root/reference and runs its own SwinV2 / PassPrecond / DiffusionSampler on the seeded fixtures.
+Both sides are fp32 on CPU, so agreement is to rounding (different op order only).
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import swinv2_oracle as orc
+from swift_b200 import synthetic as syn
+
+TAP_STRIDE = 8
+
+
+def _net(params, cfg):
+    return lambda x, t, cond, aux: orc.pass_precond(params, cfg, x, t, cond, aux)
+
+
+def _close(a, b, tol=2e-5):
+    a = torch.as_tensor(a)
+    b = torch.as_tensor(b)
+    err = (a - b).norm() / b.norm().clamp_min(1e-30)
+    assert err < tol, f"rel L2 {err:.3e}"
+    assert torch.allclose(a, b, rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("name,cfgname", [("tiny", "SWIFT_TINY"), ("small", "SWIFT_SMALL")])
+def test_forward_and_taps(golden, name, cfgname):
+    g = golden(name)
+    c = getattr(syn, cfgname)
+    cfg = orc.make_cfg(**c)
+    p = syn.random_state_dict(c, seed=1)
+    lat, cond = syn.synthetic_fields(c, 2, seed=3)
+    taps = {}
+    y = orc.swinv2_forward(p, cfg, torch.cat([lat, cond], 1), torch.from_numpy(g["fwd_t"]),
+                           torch.from_numpy(g["fwd_aux"]), taps=taps)
+    _close(y, g["fwd_y"])
+    _close(taps["cond"], g["tap_cond"])
+    for i in range(c["depth"]):
+        _close(taps[f"block{i}"][:, ::TAP_STRIDE], g[f"tap_block{i}"])
+    # the reference's patch_embed tap is taken before +pos_embed
+    _close(taps["embed"][:, ::TAP_STRIDE] - p["pos_embed"][:, ::TAP_STRIDE], g["tap_patch_embed"], tol=1e-4)
+
+
+@pytest.mark.parametrize("name,cfgname", [("tiny", "SWIFT_TINY"), ("small", "SWIFT_SMALL")])
+def test_samplers(golden, name, cfgname):
+    g = golden(name)
+    c = getattr(syn, cfgname)
+    cfg = orc.make_cfg(**c)
+    p = syn.random_state_dict(c, seed=1)
+    lat, cond = syn.synthetic_fields(c, 2, seed=3)
+    net = _net(p, cfg)
+    z = torch.from_numpy(g["scm2_noise"])
+    _close(orc.scm_solver(net, lat, cond, 0.6, num_steps=1), g["scm1"])
+    _close(orc.scm_solver(net, lat, cond, 0.6, num_steps=2, noise_fn=lambda x: z), g["scm2"])
+    _close(orc.scm_solver(net, lat, cond, 0.6, num_steps=3, noise_fn=lambda x: z), g["scm3"])
+    _close(orc.dpm_solver_2s(net, lat, cond, 0.6, num_steps=3), g["dpm2s_3"], tol=1e-4)
+
+
+def test_swift_b_digest(golden):
+    """Full Swift-B (226 M parameters), one sCM step, against the reference digest (about 10 s on 8 cores)."""
+    g = golden("swift_b")
+    c = syn.SWIFT_B
+    cfg = orc.make_cfg(**c)
+    p = syn.random_state_dict(c, seed=1)
+    assert sum(v.numel() for v in p.values()) == 225_980_976       # SURVEY.md section 6 [probe]
+    lat, cond = syn.synthetic_fields(c, 1, seed=0)
+    with torch.no_grad():
+        y = orc.scm_solver(_net(p, cfg), lat, cond, 0.6, num_steps=1)
+    _close(y.flatten(2).norm(dim=-1), g["scm1_channel_l2"], tol=1e-5)
+    _close(y[:, :, ::8, ::8], g["scm1_sub"], tol=5e-5)
+    _close(y[0, ::17, 37, :], g["scm1_row"], tol=5e-5)
+
+
+def test_time_grid_and_embedding():
+    ts = orc.scm_time_grid(1, 0.02, 200.0, 1.0)
+    assert ts.tolist() == [pytest.approx(math.pi / 2), 0.0]
+    ts = orc.scm_time_grid(2, 0.02, 200.0, 1.0)
+    assert ts[1].item() == pytest.approx(1.1) and ts[2].item() == 0.0
+    e = orc.timestep_embedding(torch.tensor([0.7]), 8)
+    f = torch.exp(-math.log(10000.0) * torch.arange(4) / 4)
+    np.testing.assert_allclose(e[0, :4].numpy(), torch.sin(0.7 * f).numpy(), rtol=1e-6)
+    np.testing.assert_allclose(e[0, 4:].numpy(), torch.cos(0.7 * f).numpy(), rtol=1e-6)
