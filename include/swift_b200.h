@@ -1,0 +1,149 @@
+/* swift_b200 -- C ABI of the B200 (sm_100a) implementation of the Swift forecast hot path.
+ *
+ * The reference (stockeh/swift) is pure Python/PyTorch and has no FFI of its own; its
+ * plugin boundary for this path is the hydra `_target_` class `swift.models.swinv2.SwinV2`
+ * (src/swift/configs/model/swinv2.yaml:1, instantiated at src/swift/models/precond.py:123-131) whose
+ * `forward(x, t, auxiliary)` (src/swift/models/swinv2.py:305-330) is called by
+ * `DiffusionSampler.scm_solver` / `dpm_solver_2s` (src/swift/generating/diffusion.py:417-461 / :355-415).
+ * The entry points below are what a binding for that boundary needs: plain pointers and sizes, an opaque
+ * cudaStream_t passed as void*, int return codes (0 = ok), no torch types.  The Python host layer
+ * (swift_b200/swinv2.py, loaded through ctypes) is the binding used in this repo; INTEGRATION.md shows the
+ * stub a maintainer of the reference would add.
+ *
+ * Ownership: the caller owns every buffer.  All pointers are DEVICE pointers unless stated otherwise and are
+ * only borrowed for the duration of the call (the work is enqueued on `stream`; buffers must stay alive until
+ * the stream reaches that point).  No function synchronises the device or allocates memory, so every call is
+ * legal inside CUDA-graph stream capture.
+ */
+#ifndef SWIFT_B200_H_
+#define SWIFT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWB200_ABI_VERSION 1
+#if defined(__GNUC__)
+#define SWB200_API __attribute__((visibility("default")))
+#else
+#define SWB200_API
+#endif
+
+/* Geometry + packed parameters of one SwinV2 denoiser (constructor arguments of swinv2.py:255-270).
+ * Packed layouts are produced by swift_b200/packing.py (documented in DESIGN.md section 3):
+ *   w_embed : bf16 [dim, k_embed * (1 + split_embed)]   columns in "(c p1 p2)" order, zero padded to k_embed,
+ *             duplicated when split_embed (the A operand is then [hi | lo], see swb200_forward)
+ *   w_qkv   : bf16 [depth][3*dim, dim]   rows reordered to  part*dim + head*88 + d   (part = q,k,v)
+ *   w_o     : bf16 [depth][dim, dim]
+ *   w_1     : bf16 [depth][2*dff, dim]   rows reordered so that every 176-row tile is [88 gate | 88 up]
+ *   w_2     : bf16 [depth][dim, dff]
+ *   w_head  : bf16 [out_channels*p1*p2, dim * (1 + split_head)]   rows in the reference "(c p1 p2)" order
+ *   mod_w/b : fp32 [2*depth*2*dim, dim] / [2*depth*2*dim]   ModulatedNorm.modulation of layer l attention
+ *             (index 2l) and feed-forward (index 2l+1), each [scale(dim) | shift(dim)]
+ *   ln_gamma/ln_beta : fp32 [2*depth, dim]   LayerNorm affine, same order
+ *   qscale  : fp32 [depth, heads]   exp(min(scale, ln 100))  (swinv2.py:125-126)                              */
+typedef struct swb200_model {
+  int32_t img_h, img_w, patch_h, patch_w, win_h, win_w, shift_h, shift_w;
+  int32_t in_channels, out_channels, depth, dim, heads, dff, aux_dim;
+  int32_t k_embed, split_embed, split_head;
+  float timestep_weight;
+  const void* w_embed;
+  const float* b_embed;
+  const float* pos_embed;     /* [tokens, dim] */
+  const float* aux_w;         /* [dim, aux_dim] or NULL */
+  const float* aux_b;
+  const float* l1_w;
+  const float* l1_b;
+  const float* l2_w;
+  const float* l2_b;
+  const float* mod_w;
+  const float* mod_b;
+  const float* ln_gamma;
+  const float* ln_beta;
+  const float* qscale;
+  const void* w_qkv;
+  const void* w_o;
+  const void* w_1;
+  const void* w_2;
+  const void* w_head;
+} swb200_model;
+
+/* Output combination applied in the head epilogue (all NCHW fp32 [B, out_channels, img_h, img_w]):
+ *     y = alpha * xt + beta * F + gamma * fprev          (terms with a NULL pointer are dropped)
+ * and, when out_f != NULL, the raw network output F is stored there as well.
+ *   module forward (swinv2.py:324):                  xt = NULL, beta = 1
+ *   sCM step (diffusion.py:459):                     alpha = cos t, beta = -sin t * sigma_d, xt = x_t
+ *   2S Euler (diffusion.py:402) / Heun (:410):       alpha = 1, beta = delta*sigma_d [*0.5], gamma = beta, fprev = F_s */
+typedef struct swb200_update {
+  const float* xt;
+  const float* fprev;
+  float* out_f;
+  float alpha, beta, gamma;
+} swb200_update;
+
+/* ---- library ------------------------------------------------------------------------------------------ */
+SWB200_API int swb200_abi_version(void);
+SWB200_API const char* swb200_last_error(void);          /* message for the last non-zero return code on this thread */
+
+/* Check that `m` is a configuration the kernels support (16x16 windows, head_dim 88, mlp dim % 88 == 0, ...).
+ * Returns 0 or SWB200 error with swb200_last_error() set.  Host only. */
+SWB200_API int swb200_validate(const swb200_model* m);
+
+/* Bytes of device workspace needed to push `chunk` samples through swb200_forward at once. Host only. */
+SWB200_API size_t swb200_workspace_bytes(const swb200_model* m, int chunk);
+/* Bytes of scratch for swb200_conditioning with batch B. Host only. */
+SWB200_API size_t swb200_conditioning_scratch_bytes(const swb200_model* m, int B);
+
+/* ---- the hot path ------------------------------------------------------------------------------------- */
+
+/* Conditioning vectors (swinv2.py:316-321 + every ModulatedNorm.modulation, :84):
+ *   t [B], aux [B, aux_dim] or NULL  ->  gain, bias : fp32 [2*depth, B, dim]  with
+ *   gain = gamma*(1+scale(t)), bias = beta*(1+scale(t)) + shift(t).  cond_out (optional) = latent_embed output
+ *   [B, dim].  For the 1-step sCM sampler (t = pi/2, aux = 0.6 fixed) this is computed once per rollout. */
+SWB200_API int swb200_conditioning(const swb200_model* m, const float* t, const float* aux, int B, float* gain, float* bias,
+                        float* cond_out, void* scratch, size_t scratch_bytes, void* stream);
+
+/* One denoiser forward, SwinV2.forward (swinv2.py:305-330) with PassPrecond's channel concat
+ * (precond.py:139-141) and the sampler update fused:
+ *   network input = cat([x0 * scale0 (c0 channels), x1 (c1 channels)], dim=1), c0 + c1 == in_channels
+ *   (x1 may be NULL when c1 == 0); gain/bias from swb200_conditioning with the same B;
+ *   y = upd-combination of F (see swb200_update).  Samples are processed in chunks that fit `workspace`. */
+SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, float scale0, const float* x1, int c1, int B,
+                   const float* gain, const float* bias, const swb200_update* upd, float* y, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* ---- individual kernels (unit tests, profiling) -------------------------------------------------------- */
+
+/* D[M,N] = A[M,K] (bf16, row pitch lda) * W[N,K]^T (bf16, row pitch ldw), fp32 accumulate on tcgen05.
+ * epi: 0 store fp32 out[M,ldo], 1 store bf16 out[M,ldo].  cta_group: 2 = paired-CTA UMMA (default), 1 = single. */
+SWB200_API int swb200_gemm(int epi, int cta_group, const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M,
+                int N, int K, void* stream);
+/* qkv projection with fused scaled-cosine normalisation: out = bf16 [3][heads][M][96]; W packed as w_qkv. */
+SWB200_API int swb200_gemm_qkv(int cta_group, const void* A, int lda, const void* W, const float* qscale, void* out, int M,
+                    int dim, int heads, void* stream);
+/* SwiGLU up-projection: out[M, dff] = silu(gate) * up; W packed as w_1. */
+SWB200_API int swb200_gemm_swiglu(int cta_group, const void* A, int lda, const void* W, void* out, int M, int dim, int dff,
+                       void* stream);
+/* Patch-embed: x[M,dim] = A*W^T + bias + pos[row % tokens]; xb = bf16(x). */
+SWB200_API int swb200_gemm_embed(int cta_group, const void* A, int lda, const void* W, int K, const float* bias,
+                      const float* pos, int tokens, float* x, void* xb, int M, int dim, void* stream);
+/* Output head with pixel-shuffle + update; A is [M, K] with K = dim*(1+split). */
+SWB200_API int swb200_gemm_head(int cta_group, const swb200_model* m, const void* A, int lda, int K, int B,
+                     const swb200_update* upd, float* y, void* stream);
+/* cat + patchify + bf16 cast (+ hi/lo split): A[B*tokens, lda] */
+SWB200_API int swb200_patch_gather(const swb200_model* m, const float* x0, int c0, float scale0, const float* x1, int c1, int B,
+                        void* A, int lda, void* stream);
+/* x += LN(branch)*gain[b] + bias[b]; xb = bf16(x) (pitch ldxb); xlo optional (same pitch). */
+SWB200_API int swb200_ln_mod_residual(const float* branch, float* x, void* xb, int ldxb, void* xlo, const float* gain,
+                           const float* bias, int M, int dim, int tokens, void* stream);
+/* shifted-window cosine attention on the packed qkv buffer; out bf16 [M, heads*88]. */
+SWB200_API int swb200_window_attention(const void* qkv, void* out, int B, int grid_h, int grid_w, int heads, int shift_h,
+                            int shift_w, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWIFT_B200_H_ */

@@ -1,0 +1,103 @@
+"""ctypes binding of ``libswift_b200.so`` (the C ABI declared in ``include/swift_b200.h``).
+
+There is deliberately no fallback: if the library is missing or a call fails, a ``RuntimeError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libswift_b200.so")
+
+ABI_VERSION = 1
+
+# Every symbol ``include/swift_b200.h`` declares; tests check the library exports exactly these.
+EXPORTS = (
+    "swb200_abi_version", "swb200_last_error", "swb200_validate", "swb200_workspace_bytes",
+    "swb200_conditioning_scratch_bytes", "swb200_conditioning", "swb200_forward", "swb200_gemm",
+    "swb200_gemm_qkv", "swb200_gemm_swiglu", "swb200_gemm_embed", "swb200_gemm_head", "swb200_patch_gather",
+    "swb200_ln_mod_residual", "swb200_window_attention",
+)
+
+_i32, _f32, _vp, _sz = C.c_int32, C.c_float, C.c_void_p, C.c_size_t
+
+
+class Model(C.Structure):
+    """``struct swb200_model`` (field order must match include/swift_b200.h)."""
+    _fields_ = (
+        [(n, _i32) for n in ("img_h", "img_w", "patch_h", "patch_w", "win_h", "win_w", "shift_h", "shift_w",
+                             "in_channels", "out_channels", "depth", "dim", "heads", "dff", "aux_dim",
+                             "k_embed", "split_embed", "split_head")]
+        + [("timestep_weight", _f32)]
+        + [(n, _vp) for n in ("w_embed", "b_embed", "pos_embed", "aux_w", "aux_b", "l1_w", "l1_b", "l2_w", "l2_b",
+                              "mod_w", "mod_b", "ln_gamma", "ln_beta", "qscale", "w_qkv", "w_o", "w_1", "w_2",
+                              "w_head")]
+    )
+
+
+class Update(C.Structure):
+    """``struct swb200_update``: y = alpha*xt + beta*F + gamma*fprev; optional raw F output."""
+    _fields_ = [("xt", _vp), ("fprev", _vp), ("out_f", _vp), ("alpha", _f32), ("beta", _f32), ("gamma", _f32)]
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+def _declare(lib):
+    MP, UP = C.POINTER(Model), C.POINTER(Update)
+    sig = {
+        "swb200_abi_version": (C.c_int, []),
+        "swb200_last_error": (C.c_char_p, []),
+        "swb200_validate": (C.c_int, [MP]),
+        "swb200_workspace_bytes": (_sz, [MP, C.c_int]),
+        "swb200_conditioning_scratch_bytes": (_sz, [MP, C.c_int]),
+        "swb200_conditioning": (C.c_int, [MP, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _sz, _vp]),
+        "swb200_forward": (C.c_int, [MP, _vp, C.c_int, _f32, _vp, C.c_int, C.c_int, _vp, _vp, UP, _vp, _vp, _sz, _vp]),
+        "swb200_gemm": (C.c_int, [C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int,
+                                  C.c_int, _vp]),
+        "swb200_gemm_qkv": (C.c_int, [C.c_int, _vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+        "swb200_gemm_swiglu": (C.c_int, [C.c_int, _vp, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+        "swb200_gemm_embed": (C.c_int, [C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, C.c_int,
+                                        C.c_int, _vp]),
+        "swb200_gemm_head": (C.c_int, [C.c_int, MP, _vp, C.c_int, C.c_int, C.c_int, UP, _vp, _vp]),
+        "swb200_patch_gather": (C.c_int, [MP, _vp, C.c_int, _f32, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp]),
+        "swb200_ln_mod_residual": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+        "swb200_window_attention": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    }
+    assert set(sig) == set(EXPORTS)
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+
+
+def lib():
+    """Load (once) and return the CUDA library.  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} is missing: the swift_b200 CUDA library has not been built "
+                        "(run `python -m swift_b200.build`); there is no CPU or PyTorch fallback")
+                l = C.CDLL(LIB_PATH)
+                _declare(l)
+                if l.swb200_abi_version() != ABI_VERSION:
+                    raise RuntimeError("libswift_b200.so ABI version mismatch; rebuild with `python -m swift_b200.build`")
+                _lib = l
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().swb200_last_error()
+        raise RuntimeError(f"swift_b200 {what} failed (code {rc}): {msg.decode() if msg else '?'}")
+
+
+def ptr(t) -> int | None:
+    """Raw device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()

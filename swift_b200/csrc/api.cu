@@ -1,0 +1,334 @@
+// extern "C" layer: argument validation, workspace carving and the kernel sequence of one denoiser forward.
+#include "../../include/swift_b200.h"
+
+#include "common.h"
+#include "gemm_sm100.cuh"
+#include "kernels.h"
+
+using namespace swb;
+
+namespace {
+
+constexpr int kDefaultCG = 2;
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Geom {
+  int gh, gw, tokens, pp, k_embed_total, k_head_total;
+};
+Geom geom(const swb200_model* m) {
+  Geom g;
+  g.gh = m->img_h / m->patch_h;
+  g.gw = m->img_w / m->patch_w;
+  g.tokens = g.gh * g.gw;
+  g.pp = m->patch_h * m->patch_w;
+  g.k_embed_total = m->k_embed * (1 + (m->split_embed ? 1 : 0));
+  g.k_head_total = m->dim * (1 + (m->split_head ? 1 : 0));
+  return g;
+}
+
+// per-sample workspace layout (offsets in bytes, every buffer 1024-byte aligned per chunk)
+struct Workspace {
+  size_t x, xb, qkv, attn, branch, h, total;   // sizes for `chunk` samples; a_embed aliases qkv, x_final aliases h
+};
+Workspace carve(const swb200_model* m, int chunk) {
+  const Geom g = geom(m);
+  const size_t M = static_cast<size_t>(chunk) * g.tokens;
+  Workspace w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 1024);
+    return o;
+  };
+  w.x = take(M * m->dim * 4);
+  w.xb = take(M * m->dim * 2);
+  size_t qkv_bytes = static_cast<size_t>(3) * m->heads * M * kHeadDimPad * 2;
+  size_t emb_bytes = M * g.k_embed_total * 2;
+  w.qkv = take(qkv_bytes > emb_bytes ? qkv_bytes : emb_bytes);
+  w.attn = take(M * m->dim * 2);
+  w.branch = take(M * m->dim * 4);
+  size_t h_cols = static_cast<size_t>(m->dff) > static_cast<size_t>(g.k_head_total) ? m->dff : g.k_head_total;
+  w.h = take(M * h_cols * 2);
+  w.total = off;
+  return w;
+}
+
+int validate(const swb200_model* m) {
+  SWB_REQUIRE(m != nullptr, "model is NULL");
+  SWB_REQUIRE(m->patch_h > 0 && m->patch_w > 0 && m->img_h % m->patch_h == 0 && m->img_w % m->patch_w == 0,
+              "image %dx%d not divisible by patch %dx%d", m->img_h, m->img_w, m->patch_h, m->patch_w);
+  const Geom g = geom(m);
+  SWB_REQUIRE(m->win_h == 16 && m->win_w == 16,
+              "only 16x16 windows are implemented (got %dx%d); Swift-B uses 16x16", m->win_h, m->win_w);
+  SWB_REQUIRE(g.gh % 16 == 0 && g.gw % 16 == 0, "token grid %dx%d is not a multiple of the 16x16 window", g.gh, g.gw);
+  SWB_REQUIRE(m->heads > 0 && m->dim == m->heads * kHeadDim,
+              "only head_dim 88 is implemented (dim=%d heads=%d); Swift-B uses 1056/12", m->dim, m->heads);
+  SWB_REQUIRE(m->dim % 8 == 0 && m->dff > 0 && m->dff % kHeadDim == 0, "mlp dim %d must be a multiple of 88", m->dff);
+  SWB_REQUIRE(m->k_embed % 8 == 0 && m->k_embed >= m->in_channels * g.pp, "k_embed=%d invalid for %d input features",
+              m->k_embed, m->in_channels * g.pp);
+  SWB_REQUIRE(m->shift_h >= 0 && m->shift_w >= 0 && m->shift_h < 16 && m->shift_w < 16, "bad shift %d,%d", m->shift_h,
+              m->shift_w);
+  SWB_REQUIRE(m->depth > 0 && m->aux_dim >= 0, "bad depth/aux_dim");
+  return SWB_OK;
+}
+
+GemmParams base_params(int M, int N, int K) {
+  GemmParams p = {};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+SWB200_API int swb200_abi_version(void) { return SWB200_ABI_VERSION; }
+SWB200_API const char* swb200_last_error(void) { return get_error(); }
+SWB200_API int swb200_validate(const swb200_model* m) { return validate(m); }
+
+SWB200_API size_t swb200_workspace_bytes(const swb200_model* m, int chunk) {
+  if (validate(m) != SWB_OK || chunk <= 0) return 0;
+  return carve(m, chunk).total;
+}
+
+SWB200_API size_t swb200_conditioning_scratch_bytes(const swb200_model* m, int B) {
+  if (m == nullptr || B <= 0) return 0;
+  const size_t L = 2 * static_cast<size_t>(m->depth);
+  return static_cast<size_t>(B) * (3 * m->dim + L * 2 * m->dim) * sizeof(float);
+}
+
+SWB200_API int swb200_conditioning(const swb200_model* m, const float* t, const float* aux, int B, float* gain, float* bias,
+                        float* cond_out, void* scratch, size_t scratch_bytes, void* stream) {
+  int rc = validate(m);
+  if (rc) return rc;
+  SWB_REQUIRE(B > 0 && t && gain && bias && scratch, "conditioning: NULL argument or B=%d", B);
+  SWB_REQUIRE(scratch_bytes >= swb200_conditioning_scratch_bytes(m, B), "conditioning: scratch too small");
+  CondWeights w;
+  w.aux_w = m->aux_w;
+  w.aux_b = m->aux_b;
+  w.aux_dim = m->aux_dim;
+  w.l1_w = m->l1_w;
+  w.l1_b = m->l1_b;
+  w.l2_w = m->l2_w;
+  w.l2_b = m->l2_b;
+  w.mod_w = m->mod_w;
+  w.mod_b = m->mod_b;
+  w.ln_gamma = m->ln_gamma;
+  w.ln_beta = m->ln_beta;
+  const float* aux_eff = (m->aux_dim > 0 && m->aux_w != nullptr) ? aux : nullptr;
+  return launch_conditioning(w, t, aux_eff, B, m->dim, 2 * m->depth, m->timestep_weight,
+                             static_cast<float*>(scratch), gain, bias, cond_out, static_cast<cudaStream_t>(stream));
+}
+
+SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, float scale0, const float* x1, int c1, int B,
+                   const float* gain, const float* bias, const swb200_update* upd, float* y, void* workspace,
+                   size_t workspace_bytes, void* stream_) {
+  int rc = validate(m);
+  if (rc) return rc;
+  SWB_REQUIRE(B > 0 && x0 && gain && bias && upd && y && workspace, "forward: NULL argument or B=%d", B);
+  SWB_REQUIRE(c0 + c1 == m->in_channels && (c1 == 0 || x1 != nullptr), "forward: c0+c1=%d != in_channels=%d", c0 + c1,
+              m->in_channels);
+  SWB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "forward: workspace must be 1024-byte aligned");
+  const size_t per1 = carve(m, 1).total;
+  int chunk = static_cast<int>(workspace_bytes / per1);
+  SWB_REQUIRE(chunk >= 1, "forward: workspace of %zu bytes cannot hold one sample (%zu bytes)", workspace_bytes, per1);
+  if (chunk > B) chunk = B;
+  while (carve(m, chunk).total > workspace_bytes) --chunk;   // alignment slack
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const Geom g = geom(m);
+  const int D = m->dim, H = m->heads, Dff = m->dff;
+  const size_t img_in0 = static_cast<size_t>(c0) * m->img_h * m->img_w;
+  const size_t img_in1 = static_cast<size_t>(c1) * m->img_h * m->img_w;
+  const size_t img_out = static_cast<size_t>(m->out_channels) * m->img_h * m->img_w;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int bc = (B - b0 < chunk) ? (B - b0) : chunk;
+    const int M = bc * g.tokens;
+    const Workspace w = carve(m, bc);
+    float* x = reinterpret_cast<float*>(ws + w.x);
+    void* xb = ws + w.xb;
+    void* qkv = ws + w.qkv;
+    void* a_emb = qkv;
+    void* attn = ws + w.attn;
+    float* branch = reinterpret_cast<float*>(ws + w.branch);
+    void* hbuf = ws + w.h;
+
+    // 1. concat + patchify + cast
+    rc = launch_patch_gather(x0 + b0 * img_in0, c0, scale0, x1 ? x1 + b0 * img_in1 : nullptr, c1, a_emb,
+                             g.k_embed_total, m->k_embed, m->split_embed, bc, m->img_h, m->img_w, m->patch_h,
+                             m->patch_w, stream);
+    if (rc) return rc;
+    // 2. patch-embed GEMM (+bias +pos_embed)
+    {
+      GemmParams p = base_params(M, D, g.k_embed_total);
+      p.out0 = x;
+      p.out1 = xb;
+      p.ldo = D;
+      p.bias = m->b_embed;
+      p.pos = m->pos_embed;
+      p.pos_rows = g.tokens;
+      rc = launch_gemm(EPI_EMBED, kDefaultCG, a_emb, g.k_embed_total, m->w_embed, g.k_embed_total, p, stream);
+      if (rc) return rc;
+    }
+    // 3. transformer blocks
+    for (int l = 0; l < m->depth; ++l) {
+      const bool shifted = (m->shift_h || m->shift_w) && (l & 1);
+      {
+        GemmParams p = base_params(M, 3 * D, D);
+        p.out0 = qkv;
+        p.qscale = m->qscale + static_cast<size_t>(l) * H;
+        p.heads = H;
+        p.dmodel = D;
+        const auto* wq = static_cast<const __nv_bfloat16*>(m->w_qkv) + static_cast<size_t>(l) * 3 * D * D;
+        rc = launch_gemm(EPI_QKV, kDefaultCG, xb, D, wq, D, p, stream);
+        if (rc) return rc;
+      }
+      rc = launch_window_attention(qkv, attn, bc, g.gh, g.gw, H, shifted ? m->shift_h : 0, shifted ? m->shift_w : 0,
+                                   stream);
+      if (rc) return rc;
+      {
+        GemmParams p = base_params(M, D, D);
+        p.out0 = branch;
+        p.ldo = D;
+        const auto* wo = static_cast<const __nv_bfloat16*>(m->w_o) + static_cast<size_t>(l) * D * D;
+        rc = launch_gemm(EPI_STORE_F32, kDefaultCG, attn, D, wo, D, p, stream);
+        if (rc) return rc;
+      }
+      rc = launch_ln_mod_residual(branch, x, xb, D, nullptr, gain + (static_cast<size_t>(2 * l) * B + b0) * D,
+                                  bias + (static_cast<size_t>(2 * l) * B + b0) * D, M, D, g.tokens, 1e-6f, stream);
+      if (rc) return rc;
+      {
+        GemmParams p = base_params(M, 2 * Dff, D);
+        p.out0 = hbuf;
+        p.ldo = Dff;
+        const auto* w1 = static_cast<const __nv_bfloat16*>(m->w_1) + static_cast<size_t>(l) * 2 * Dff * D;
+        rc = launch_gemm(EPI_SWIGLU, kDefaultCG, xb, D, w1, D, p, stream);
+        if (rc) return rc;
+      }
+      {
+        GemmParams p = base_params(M, D, Dff);
+        p.out0 = branch;
+        p.ldo = D;
+        const auto* w2 = static_cast<const __nv_bfloat16*>(m->w_2) + static_cast<size_t>(l) * D * Dff;
+        rc = launch_gemm(EPI_STORE_F32, kDefaultCG, hbuf, Dff, w2, Dff, p, stream);
+        if (rc) return rc;
+      }
+      const bool last = (l == m->depth - 1);
+      // the last LN writes the head operand: [hi | lo] with pitch k_head_total into the (dead) h buffer
+      void* xb_dst = last ? hbuf : xb;
+      const int ldxb = last ? g.k_head_total : D;
+      void* xlo = (last && m->split_head) ? static_cast<void*>(static_cast<__nv_bfloat16*>(hbuf) + D) : nullptr;
+      rc = launch_ln_mod_residual(branch, x, xb_dst, ldxb, xlo, gain + (static_cast<size_t>(2 * l + 1) * B + b0) * D,
+                                  bias + (static_cast<size_t>(2 * l + 1) * B + b0) * D, M, D, g.tokens, 1e-6f, stream);
+      if (rc) return rc;
+    }
+    // 4. head GEMM + pixel shuffle + sampler update
+    {
+      swb200_update u = *upd;
+      if (u.xt) u.xt += b0 * img_out;
+      if (u.fprev) u.fprev += b0 * img_out;
+      if (u.out_f) u.out_f += b0 * img_out;
+      rc = swb200_gemm_head(kDefaultCG, m, hbuf, g.k_head_total, g.k_head_total, bc, &u, y + b0 * img_out, stream_);
+      if (rc) return rc;
+    }
+  }
+  return SWB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ single kernels
+
+SWB200_API int swb200_gemm(int epi, int cta_group, const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M,
+                int N, int K, void* stream) {
+  SWB_REQUIRE(epi == EPI_STORE_F32 || epi == EPI_STORE_BF16, "swb200_gemm: epi must be 0 (fp32) or 1 (bf16)");
+  SWB_REQUIRE(A && W && out, "swb200_gemm: NULL pointer");
+  SWB_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "swb200_gemm: out must be 16-byte aligned");
+  GemmParams p = base_params(M, N, K);
+  p.out0 = out;
+  p.ldo = ldo;
+  return launch_gemm(epi, cta_group, A, lda, W, ldw, p, static_cast<cudaStream_t>(stream));
+}
+
+SWB200_API int swb200_gemm_qkv(int cta_group, const void* A, int lda, const void* W, const float* qscale, void* out, int M,
+                    int dim, int heads, void* stream) {
+  SWB_REQUIRE(A && W && qscale && out, "swb200_gemm_qkv: NULL pointer");
+  SWB_REQUIRE(dim == heads * kHeadDim, "swb200_gemm_qkv: need head_dim 88 (dim=%d heads=%d)", dim, heads);
+  GemmParams p = base_params(M, 3 * dim, dim);
+  p.out0 = out;
+  p.qscale = qscale;
+  p.heads = heads;
+  p.dmodel = dim;
+  return launch_gemm(EPI_QKV, cta_group, A, lda, W, dim, p, static_cast<cudaStream_t>(stream));
+}
+
+SWB200_API int swb200_gemm_swiglu(int cta_group, const void* A, int lda, const void* W, void* out, int M, int dim, int dff,
+                       void* stream) {
+  SWB_REQUIRE(A && W && out, "swb200_gemm_swiglu: NULL pointer");
+  SWB_REQUIRE(dff % kHeadDim == 0, "swb200_gemm_swiglu: dff must be a multiple of 88");
+  GemmParams p = base_params(M, 2 * dff, dim);
+  p.out0 = out;
+  p.ldo = dff;
+  return launch_gemm(EPI_SWIGLU, cta_group, A, lda, W, dim, p, static_cast<cudaStream_t>(stream));
+}
+
+SWB200_API int swb200_gemm_embed(int cta_group, const void* A, int lda, const void* W, int K, const float* bias,
+                      const float* pos, int tokens, float* x, void* xb, int M, int dim, void* stream) {
+  SWB_REQUIRE(A && W && bias && pos && x && xb, "swb200_gemm_embed: NULL pointer");
+  GemmParams p = base_params(M, dim, K);
+  p.out0 = x;
+  p.out1 = xb;
+  p.ldo = dim;
+  p.bias = bias;
+  p.pos = pos;
+  p.pos_rows = tokens;
+  return launch_gemm(EPI_EMBED, cta_group, A, lda, W, K, p, static_cast<cudaStream_t>(stream));
+}
+
+SWB200_API int swb200_gemm_head(int cta_group, const swb200_model* m, const void* A, int lda, int K, int B,
+                     const swb200_update* upd, float* y, void* stream) {
+  SWB_REQUIRE(m && A && upd && y, "swb200_gemm_head: NULL pointer");
+  const Geom g = geom(m);
+  GemmParams p = base_params(B * g.tokens, m->out_channels * g.pp, K);
+  p.out0 = y;
+  p.xt = upd->xt;
+  p.fprev = upd->fprev;
+  p.out_f = upd->out_f;
+  p.alpha = upd->alpha;
+  p.beta = upd->beta;
+  p.gamma = upd->gamma;
+  p.C = m->out_channels;
+  p.H = m->img_h;
+  p.W = m->img_w;
+  p.p1 = m->patch_h;
+  p.p2 = m->patch_w;
+  p.gw = g.gw;
+  p.tokens = g.tokens;
+  return launch_gemm(EPI_HEAD, cta_group, A, lda, m->w_head, K, p, static_cast<cudaStream_t>(stream));
+}
+
+SWB200_API int swb200_patch_gather(const swb200_model* m, const float* x0, int c0, float scale0, const float* x1, int c1, int B,
+                        void* A, int lda, void* stream) {
+  SWB_REQUIRE(m && x0 && A, "swb200_patch_gather: NULL pointer");
+  SWB_REQUIRE(c0 + c1 == m->in_channels, "swb200_patch_gather: c0+c1 != in_channels");
+  return launch_patch_gather(x0, c0, scale0, x1, c1, A, lda, m->k_embed, m->split_embed, B, m->img_h, m->img_w,
+                             m->patch_h, m->patch_w, static_cast<cudaStream_t>(stream));
+}
+
+SWB200_API int swb200_ln_mod_residual(const float* branch, float* x, void* xb, int ldxb, void* xlo, const float* gain,
+                           const float* bias, int M, int dim, int tokens, void* stream) {
+  SWB_REQUIRE(branch && x && xb && gain && bias, "swb200_ln_mod_residual: NULL pointer");
+  return launch_ln_mod_residual(branch, x, xb, ldxb, xlo, gain, bias, M, dim, tokens, 1e-6f,
+                                static_cast<cudaStream_t>(stream));
+}
+
+SWB200_API int swb200_window_attention(const void* qkv, void* out, int B, int grid_h, int grid_w, int heads, int shift_h,
+                            int shift_w, void* stream) {
+  SWB_REQUIRE(qkv && out, "swb200_window_attention: NULL pointer");
+  return launch_window_attention(qkv, out, B, grid_h, grid_w, heads, shift_h, shift_w,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,49 @@
+// Host-side shared declarations for the swift_b200 C-ABI library (no torch types anywhere).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace swb {
+
+// last error message of the calling thread (returned by swb200_last_error())
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define SWB_CHECK_CUDA(expr)                                                                         \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess) {                                                                         \
+      swb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));          \
+      return static_cast<int>(_e) ? static_cast<int>(_e) : -1;                                       \
+    }                                                                                                \
+  } while (0)
+
+#define SWB_REQUIRE(cond, ...)                                                                       \
+  do {                                                                                               \
+    if (!(cond)) {                                                                                   \
+      swb::set_error(__VA_ARGS__);                                                                   \
+      return SWB_ERR_INVALID;                                                                        \
+    }                                                                                                \
+  } while (0)
+
+constexpr int SWB_OK = 0;
+constexpr int SWB_ERR_INVALID = -2;     // bad argument / unsupported configuration
+constexpr int SWB_ERR_DRIVER = -3;      // driver entry point or tensor-map encode failure
+
+int num_sms();
+
+// bf16 row-major [rows, cols] -> 2-D TMA descriptor with a [box_rows x 64] SWIZZLE_128B box
+int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                      uint32_t box_cols);
+int make_tmap_bf16_2d_pitch(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+                            uint32_t box_rows, uint32_t box_cols);
+
+struct GemmParams;
+// D = A[M,K] * W[N,K]^T with a fused epilogue (gemm_sm100.cuh); cta_group 2 = paired-CTA UMMA (M=256 tiles)
+int launch_gemm(int epi, int cta_group, const void* A, int lda, const void* W, int ldw, const GemmParams& p,
+                cudaStream_t stream);
+
+}  // namespace swb

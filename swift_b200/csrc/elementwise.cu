@@ -1,0 +1,268 @@
+// HBM-bound glue kernels of the Swift denoiser: patch gather (fused concat + patchify + bf16 cast),
+// LayerNorm + TrigFlow-time modulation + residual add, and the conditioning micro-kernels
+// (sinusoidal embedding, fp32 GEMVs, modulation folding).
+#include "common.h"
+#include "kernels.h"
+
+#include <cuda_bf16.h>
+
+namespace swb {
+
+// =========================================================================================================
+// Patch gather: A[(b, gy, gx), k] with k = c*(p1*p2) + py*p2 + px  <-  cat([src0*scale0, src1], 1)[b, c, gy*p1+py, gx*p2+px]
+//
+// Replaces precond.py:139-141 (torch.cat) + swinv2.py:224-229 (einops rearrange) + the fp32->bf16 cast of the
+// GEMM operand.  The reference feature order is "(p1 p2 c)"; we use "(c p1 p2)" and permute the columns of the
+// patch-embed weight once at pack time, which makes the gather write 2*p1*p2-byte runs per channel.
+// SPLIT writes a second operand half lo = bf16(x - float(bf16(x))) at column offset Kp so that
+// [hi | lo] * [W | W]^T reproduces the fp32 input to ~2^-17 relative instead of 2^-9.
+constexpr int kGatherCh = 8;
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) patch_gather_kernel(const float* __restrict__ src0, int C0, float scale0,
+                                                           const float* __restrict__ src1, int C1,
+                                                           __nv_bfloat16* __restrict__ A, int lda, int Kp, int H,
+                                                           int W, int p1, int p2) {
+  extern __shared__ float tile[];   // [kGatherCh * p1][W + 2]
+  const int gy = blockIdx.x, b = blockIdx.y;
+  const int gh = H / p1, gw = W / p2;
+  const int pp = p1 * p2;
+  const int C = C0 + C1;
+  const int pitch = W + 2;
+  const int cvirt = (Kp + pp - 1) / pp;            // channels >= C are virtual zero padding up to Kp
+  const int nchunks = (cvirt + kGatherCh - 1) / kGatherCh;
+  const size_t row_base = (static_cast<size_t>(b) * gh + gy) * gw;
+  for (int chunk = 0; chunk < nchunks; ++chunk) {
+    const int c0 = chunk * kGatherCh;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < kGatherCh * p1 * W; idx += blockDim.x) {
+      const int xw = idx % W;
+      const int r = idx / W;            // c*p1 + py
+      const int c = c0 + r / p1, py = r % p1;
+      float v = 0.f;
+      if (c < C0)
+        v = __ldg(src0 + ((static_cast<size_t>(b) * C0 + c) * H + gy * p1 + py) * W + xw) * scale0;
+      else if (c < C)
+        v = __ldg(src1 + ((static_cast<size_t>(b) * C1 + (c - C0)) * H + gy * p1 + py) * W + xw);
+      tile[r * pitch + xw] = v;
+    }
+    __syncthreads();
+    const int kchunk = kGatherCh * pp;
+    for (int idx = threadIdx.x; idx < gw * kchunk; idx += blockDim.x) {
+      const int kl = idx % kchunk, gx = idx / kchunk;
+      const int c = kl / pp, r = kl % pp;
+      const int py = r / p2, px = r % p2;
+      const int k = (c0 + c) * pp + r;
+      if (k < Kp) {
+        const float v = tile[(c * p1 + py) * pitch + gx * p2 + px];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        __nv_bfloat16* dst = A + (row_base + gx) * lda + k;
+        *dst = hi;
+        if (SPLIT) dst[Kp] = __float2bfloat16_rn(v - __bfloat162float(hi));
+      }
+    }
+  }
+}
+
+int launch_patch_gather(const float* src0, int C0, float scale0, const float* src1, int C1, void* A, int lda, int Kp,
+                        int split, int B, int H, int W, int p1, int p2, cudaStream_t stream) {
+  SWB_REQUIRE(H % p1 == 0 && W % p2 == 0, "patch_gather: image %dx%d not divisible by patch %dx%d", H, W, p1, p2);
+  SWB_REQUIRE(Kp >= (C0 + C1) * p1 * p2, "patch_gather: Kp=%d < C*p1*p2=%d", Kp, (C0 + C1) * p1 * p2);
+  const size_t smem = static_cast<size_t>(kGatherCh) * p1 * (W + 2) * sizeof(float);
+  SWB_REQUIRE(smem <= 48 * 1024, "patch_gather: image width %d too large for the staging tile", W);
+  dim3 grid(H / p1, B);
+  if (split)
+    patch_gather_kernel<true><<<grid, 256, smem, stream>>>(src0, C0, scale0, src1, C1,
+                                                           static_cast<__nv_bfloat16*>(A), lda, Kp, H, W, p1, p2);
+  else
+    patch_gather_kernel<false><<<grid, 256, smem, stream>>>(src0, C0, scale0, src1, C1,
+                                                            static_cast<__nv_bfloat16*>(A), lda, Kp, H, W, p1, p2);
+  SWB_CHECK_CUDA(cudaGetLastError());
+  return SWB_OK;
+}
+
+// =========================================================================================================
+// x <- x + LN(branch) * gain[b] + bias[b];   xb <- bf16(x)   (optionally xlo <- bf16(x - xb))
+//
+// reference: ModulatedNorm (swinv2.py:77-86) applied to the branch output, then the residual add
+// (swinv2.py:211-212).  gain = gamma*(1+scale(t)), bias = beta*(1+scale(t)) + shift(t) are folded per sample
+// by mod_finalize_kernel.  One warp per token row, the row lives in registers (two-pass mean/variance in fp32),
+// all global accesses are lane-strided so every warp request is one full 128-byte line.
+template <int VPL>
+__global__ void __launch_bounds__(256) ln_mod_residual_kernel(const float* __restrict__ branch, float* __restrict__ x,
+                                                              __nv_bfloat16* __restrict__ xb, int ldxb,
+                                                              __nv_bfloat16* __restrict__ xlo,
+                                                              const float* __restrict__ gain,
+                                                              const float* __restrict__ bias, int M, int D,
+                                                              int tokens, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const float* br = branch + static_cast<size_t>(row) * D;
+  float v[VPL];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = i * 32 + lane;
+    v[i] = (c < D) ? __ldg(br + c) : 0.f;
+    sum += v[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / static_cast<float>(D);
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = i * 32 + lane;
+    const float d = (c < D) ? v[i] - mean : 0.f;
+    var = fmaf(d, d, var);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / static_cast<float>(D) + eps);
+  const int b = row / tokens;
+  const float* g = gain + static_cast<size_t>(b) * D;
+  const float* bs = bias + static_cast<size_t>(b) * D;
+  float* xr = x + static_cast<size_t>(row) * D;
+  __nv_bfloat16* xbr = xb + static_cast<size_t>(row) * ldxb;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = i * 32 + lane;
+    if (c < D) {
+      const float y = fmaf((v[i] - mean) * rstd, __ldg(g + c), __ldg(bs + c));
+      const float xn = xr[c] + y;
+      xr[c] = xn;
+      const __nv_bfloat16 hi = __float2bfloat16_rn(xn);
+      xbr[c] = hi;
+      if (xlo) xlo[static_cast<size_t>(row) * ldxb + c] = __float2bfloat16_rn(xn - __bfloat162float(hi));
+    }
+  }
+}
+
+int launch_ln_mod_residual(const float* branch, float* x, void* xb, int ldxb, void* xlo, const float* gain,
+                           const float* bias, int M, int D, int tokens, float eps, cudaStream_t stream) {
+  const int rows_per_block = 8;
+  dim3 grid((M + rows_per_block - 1) / rows_per_block);
+  auto xb_ = static_cast<__nv_bfloat16*>(xb);
+  auto xlo_ = static_cast<__nv_bfloat16*>(xlo);
+  if (D <= 32 * 9)
+    ln_mod_residual_kernel<9><<<grid, 256, 0, stream>>>(branch, x, xb_, ldxb, xlo_, gain, bias, M, D, tokens, eps);
+  else if (D <= 32 * 17)
+    ln_mod_residual_kernel<17><<<grid, 256, 0, stream>>>(branch, x, xb_, ldxb, xlo_, gain, bias, M, D, tokens, eps);
+  else if (D <= 32 * 33)
+    ln_mod_residual_kernel<33><<<grid, 256, 0, stream>>>(branch, x, xb_, ldxb, xlo_, gain, bias, M, D, tokens, eps);
+  else if (D <= 32 * 64)
+    ln_mod_residual_kernel<64><<<grid, 256, 0, stream>>>(branch, x, xb_, ldxb, xlo_, gain, bias, M, D, tokens, eps);
+  else {
+    set_error("ln_mod_residual: dim %d > 2048 unsupported", D);
+    return SWB_ERR_INVALID;
+  }
+  SWB_CHECK_CUDA(cudaGetLastError());
+  return SWB_OK;
+}
+
+// =========================================================================================================
+// Conditioning (swinv2.py:44-60, :316-321): emb = [sin(t f) | cos(t f)] + aux_embed(aux * sqrt(aux_dim))
+__global__ void cond_embed_kernel(const float* __restrict__ t, const float* __restrict__ aux,
+                                  const float* __restrict__ aux_w, const float* __restrict__ aux_b, int aux_dim,
+                                  float timestep_weight, int D, float* __restrict__ emb) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D) return;
+  const int half = D / 2;
+  float e = 0.f;
+  if (i < 2 * half) {
+    const int j = (i < half) ? i : i - half;
+    const float freq = expf(-9.210340371976184f * static_cast<float>(j) / static_cast<float>(half));
+    const float arg = (t[b] * timestep_weight) * freq;
+    e = (i < half) ? sinf(arg) : cosf(arg);
+  }
+  if (aux != nullptr && aux_dim > 0) {
+    const float s = sqrtf(static_cast<float>(aux_dim));
+    float a = aux_b[i];
+    for (int j = 0; j < aux_dim; ++j) a = fmaf(aux_w[i * aux_dim + j], aux[b * aux_dim + j] * s, a);
+    e += a;
+  }
+  emb[static_cast<size_t>(b) * D + i] = e;
+}
+
+// out[b, n] = act(bias[n] + W[n, :] . in[b, :]) in fp32; one warp per output row n, batch tiled by 8.
+template <int ACT>
+__global__ void __launch_bounds__(256) gemv_rows_kernel(const float* __restrict__ Wm, const float* __restrict__ bias,
+                                                        const float* __restrict__ in, float* __restrict__ out, int N,
+                                                        int K, int B) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const int lane = threadIdx.x & 31;
+  const float* w = Wm + static_cast<size_t>(n) * K;
+  for (int b0 = 0; b0 < B; b0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float wv = __ldg(w + k);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (b0 + j < B) acc[j] = fmaf(wv, __ldg(in + static_cast<size_t>(b0 + j) * K + k), acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (b0 + j < B) {
+          float v = acc[j] + (bias ? bias[n] : 0.f);
+          if (ACT == 1) v = v / (1.0f + expf(-v));
+          out[static_cast<size_t>(b0 + j) * N + n] = v;
+        }
+      }
+    }
+  }
+}
+
+// gain[l, b, i] = gamma[l, i] * (1 + scale),  bias[l, b, i] = beta[l, i] * (1 + scale) + shift,
+// with [scale | shift] = mod[b, l*2D : (l+1)*2D]   (ModulatedNorm, swinv2.py:83-86)
+__global__ void mod_finalize_kernel(const float* __restrict__ mod, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, float* __restrict__ gain,
+                                    float* __restrict__ bias, int L, int B, int D) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(L) * B * D;
+  if (idx >= total) return;
+  const int i = idx % D;
+  const int b = (idx / D) % B;
+  const int l = idx / (static_cast<size_t>(D) * B);
+  const float* m = mod + (static_cast<size_t>(b) * L + l) * 2 * D;
+  const float sc = 1.0f + m[i];
+  gain[idx] = gamma[l * D + i] * sc;
+  bias[idx] = fmaf(beta[l * D + i], sc, m[D + i]);
+}
+
+int launch_conditioning(const CondWeights& w, const float* t, const float* aux, int B, int D, int L,
+                        float timestep_weight, float* scratch, float* gain, float* bias, float* cond_out,
+                        cudaStream_t stream) {
+  // scratch: emb [B,D] | h1 [B,D] | c [B,D] | mod [B, L*2D]
+  float* emb = scratch;
+  float* h1 = emb + static_cast<size_t>(B) * D;
+  float* c = h1 + static_cast<size_t>(B) * D;
+  float* mod = c + static_cast<size_t>(B) * D;
+  cond_embed_kernel<<<dim3((D + 127) / 128, B), 128, 0, stream>>>(t, aux, w.aux_w, w.aux_b, w.aux_dim,
+                                                                  timestep_weight, D, emb);
+  const int wpb = 8;
+  gemv_rows_kernel<1><<<(D + wpb - 1) / wpb, 256, 0, stream>>>(w.l1_w, w.l1_b, emb, h1, D, D, B);
+  gemv_rows_kernel<1><<<(D + wpb - 1) / wpb, 256, 0, stream>>>(w.l2_w, w.l2_b, h1, c, D, D, B);
+  const int NM = L * 2 * D;
+  gemv_rows_kernel<0><<<(NM + wpb - 1) / wpb, 256, 0, stream>>>(w.mod_w, w.mod_b, c, mod, NM, D, B);
+  const size_t total = static_cast<size_t>(L) * B * D;
+  mod_finalize_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(mod, w.ln_gamma, w.ln_beta,
+                                                                                      gain, bias, L, B, D);
+  if (cond_out)
+    SWB_CHECK_CUDA(cudaMemcpyAsync(cond_out, c, static_cast<size_t>(B) * D * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, stream));
+  SWB_CHECK_CUDA(cudaGetLastError());
+  return SWB_OK;
+}
+
+}  // namespace swb

@@ -1,0 +1,144 @@
+// Host launcher for the tcgen05 GEMM (gemm_sm100.cuh): builds the TMA descriptors and dispatches the
+// (tile, cta_group, epilogue) instantiation.
+#include "common.h"
+#include "gemm_sm100.cuh"
+
+#include <mutex>
+
+namespace swb {
+
+// ----------------------------------------------------------------------------- error string
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+// ----------------------------------------------------------------------------- TMA descriptors
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled get_encode_fn() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+  });
+  return fn;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                      uint32_t box_cols) {
+  return make_tmap_bf16_2d_pitch(out, ptr, rows, cols, cols, box_rows, box_cols);
+}
+
+int make_tmap_bf16_2d_pitch(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+                            uint32_t box_rows, uint32_t box_cols) {
+  PFN_tmapEncodeTiled fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled driver entry point not available");
+    return SWB_ERR_DRIVER;
+  }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((pitch_elems * 2) & 15)) {
+    set_error("TMA operand must be 16-byte aligned with a 16-byte multiple row pitch (ptr=%p pitch=%llu elems)", ptr,
+              (unsigned long long)pitch_elems);
+    return SWB_ERR_INVALID;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu box=%ux%u", (int)r, (unsigned long long)rows,
+              (unsigned long long)cols, box_rows, box_cols);
+    return SWB_ERR_DRIVER;
+  }
+  return SWB_OK;
+}
+
+// ----------------------------------------------------------------------------- launch
+template <int BN, int CG, int EPI>
+static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  using S = GemmSmem<BN, CG>;
+  auto kern = gemm_tcgen05_kernel<BN, CG, EPI>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SWB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    attr_done = true;
+  }
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int tiles_m = (p.M + kBlockM * CG - 1) / (kBlockM * CG);
+  const int num_tiles = tiles_m * tiles_n;
+  int clusters = num_sms() / CG;
+  if (clusters > num_tiles) clusters = num_tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * CG);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SWB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+  return SWB_OK;
+}
+
+template <int BN, int CG>
+static int launch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                      cudaStream_t stream) {
+  switch (epi) {
+    case EPI_STORE_F32: return launch_inst<BN, CG, EPI_STORE_F32>(ta, tb, p, stream);
+    case EPI_STORE_BF16: return launch_inst<BN, CG, EPI_STORE_BF16>(ta, tb, p, stream);
+    case EPI_EMBED: return launch_inst<BN, CG, EPI_EMBED>(ta, tb, p, stream);
+    case EPI_QKV: return launch_inst<BN, CG, EPI_QKV>(ta, tb, p, stream);
+    case EPI_SWIGLU: return launch_inst<BN, CG, EPI_SWIGLU>(ta, tb, p, stream);
+    case EPI_HEAD: return launch_inst<BN, CG, EPI_HEAD>(ta, tb, p, stream);
+  }
+  set_error("unknown GEMM epilogue %d", epi);
+  return SWB_ERR_INVALID;
+}
+
+// A: bf16 [M, K] with row pitch lda; W: bf16 [N, K] with row pitch ldw (nn.Linear layout).
+int launch_gemm(int epi, int cta_group, const void* A, int lda, const void* W, int ldw, const GemmParams& p,
+                cudaStream_t stream) {
+  SWB_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
+  SWB_REQUIRE(p.K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm: K and row pitches must be multiples of 8 (K=%d)",
+              p.K);
+  SWB_REQUIRE(cta_group == 1 || cta_group == 2, "gemm: cta_group must be 1 or 2");
+  constexpr int BN = 176;
+  CUtensorMap ta, tb;
+  int rc = make_tmap_bf16_2d_pitch(&ta, A, p.M, p.K, lda, kBlockM, kBlockK);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d_pitch(&tb, W, p.N, p.K, ldw, BN / cta_group, kBlockK);
+  if (rc) return rc;
+  if (cta_group == 2) return launch_epi<BN, 2>(epi, ta, tb, p, stream);
+  return launch_epi<BN, 1>(epi, ta, tb, p, stream);
+}
+
+}  // namespace swb

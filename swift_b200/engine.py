@@ -1,0 +1,126 @@
+"""Host-side driver of the CUDA denoiser: owns packed weights and workspace, issues the C-ABI calls.
+
+PyTorch is used for device memory and streams only; every FLOP of the forward runs in ``libswift_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib, packing
+
+
+def _aligned_buffer(nbytes: int, device: torch.device, align: int = 1024) -> Tuple[torch.Tensor, int]:
+    buf = torch.empty(nbytes + align, dtype=torch.uint8, device=device)
+    base = (buf.data_ptr() + align - 1) // align * align
+    return buf, base
+
+
+class Engine:
+    """One packed SwinV2 denoiser on one GPU."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], geom: packing.Geometry, device: torch.device,
+                 split_embed: bool = True, split_head: bool = True, max_chunk: int = 8):
+        if device.type != "cuda":
+            raise RuntimeError("swift_b200 runs on CUDA devices only (no CPU fallback)")
+        self.lib = _lib.lib()
+        self.geom = geom
+        self.device = device
+        with torch.cuda.device(device):
+            self.model, self._keep = packing.pack(state_dict, geom, device, split_embed, split_head)
+        _lib.check(self.lib.swb200_validate(C.byref(self.model)), "validate")
+        self.max_chunk = max_chunk
+        self._ws: Optional[torch.Tensor] = None
+        self._ws_base = 0
+        self._ws_bytes = 0
+        self._cond_scratch: Optional[torch.Tensor] = None
+        self.launches = 0           # kernels enqueued by this engine (for bench.py's gpu_launches)
+
+    # ------------------------------------------------------------------ helpers
+    @property
+    def out_shape(self) -> Tuple[int, int, int]:
+        return (self.geom.out_channels, self.geom.img[0], self.geom.img[1])
+
+    def launches_per_forward(self, batch: int) -> int:
+        chunks = math.ceil(batch / max(1, min(batch, self.max_chunk)))
+        return chunks * (2 + 7 * self.geom.depth + 1)
+
+    def workspace(self, batch: int) -> Tuple[int, int]:
+        chunk = max(1, min(batch, self.max_chunk))
+        need = self.lib.swb200_workspace_bytes(C.byref(self.model), chunk)
+        if need == 0:
+            _lib.check(self.lib.swb200_validate(C.byref(self.model)), "workspace_bytes")
+        if self._ws is None or self._ws_bytes < need:
+            self._ws, self._ws_base = _aligned_buffer(need, self.device)
+            self._ws_bytes = need
+        return self._ws_base, self._ws_bytes
+
+    @staticmethod
+    def _stream() -> int:
+        return torch.cuda.current_stream().cuda_stream
+
+    @staticmethod
+    def _check_f32(t: torch.Tensor, name: str):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise RuntimeError(f"{name}: expected a contiguous float32 CUDA tensor, got {t.dtype} on {t.device} "
+                               f"(contiguous={t.is_contiguous()}); swift_b200 has no CPU fallback")
+
+    # ------------------------------------------------------------------ conditioning
+    def conditioning(self, t: torch.Tensor, aux: Optional[torch.Tensor], want_cond: bool = False):
+        """t [B] fp32, aux [B, aux_dim] fp32 or None -> (gain, bias) each [2*depth, B, dim] (+ cond [B, dim])."""
+        g = self.geom
+        B = t.shape[0]
+        self._check_f32(t, "t")
+        if aux is not None:
+            self._check_f32(aux, "auxiliary")
+            if aux.shape != (B, g.aux_dim):
+                raise RuntimeError(f"auxiliary must be [{B}, {g.aux_dim}], got {tuple(aux.shape)}")
+        gain = torch.empty(2 * g.depth, B, g.dim, device=self.device, dtype=torch.float32)
+        bias = torch.empty_like(gain)
+        cond = torch.empty(B, g.dim, device=self.device, dtype=torch.float32) if want_cond else None
+        need = self.lib.swb200_conditioning_scratch_bytes(C.byref(self.model), B)
+        if self._cond_scratch is None or self._cond_scratch.numel() < need:
+            self._cond_scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.swb200_conditioning(C.byref(self.model), t.data_ptr(), _lib.ptr(aux), B, gain.data_ptr(),
+                                                bias.data_ptr(), _lib.ptr(cond), self._cond_scratch.data_ptr(),
+                                                self._cond_scratch.numel(), self._stream()), "conditioning")
+        self.launches += 5
+        return (gain, bias, cond) if want_cond else (gain, bias)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x0: torch.Tensor, x1: Optional[torch.Tensor], gain: torch.Tensor, bias: torch.Tensor,
+                out: Optional[torch.Tensor] = None, scale0: float = 1.0, xt: Optional[torch.Tensor] = None,
+                fprev: Optional[torch.Tensor] = None, out_f: Optional[torch.Tensor] = None, alpha: float = 0.0,
+                beta: float = 1.0, gamma: float = 0.0) -> torch.Tensor:
+        """F = SwinV2(cat([x0*scale0, x1], 1));  returns  alpha*xt + beta*F + gamma*fprev  (NCHW fp32)."""
+        g = self.geom
+        self._check_f32(x0, "x0")
+        B, c0 = x0.shape[0], x0.shape[1]
+        c1 = 0
+        if x1 is not None:
+            self._check_f32(x1, "x1")
+            c1 = x1.shape[1]
+            if x1.shape[0] != B or tuple(x1.shape[2:]) != g.img:
+                raise RuntimeError(f"condition shape {tuple(x1.shape)} does not match {B} x * x {g.img}")
+        if tuple(x0.shape[2:]) != g.img or c0 + c1 != g.in_channels:
+            raise RuntimeError(f"input channels {c0}+{c1} / resolution {tuple(x0.shape[2:])} do not match the model "
+                               f"({g.in_channels} channels at {g.img})")
+        if gain.shape != (2 * g.depth, B, g.dim):
+            raise RuntimeError("conditioning vectors were computed for a different batch size")
+        for nm, tns in (("xt", xt), ("fprev", fprev), ("out_f", out_f), ("out", out)):
+            if tns is not None:
+                self._check_f32(tns, nm)
+                if tuple(tns.shape) != (B, *self.out_shape):
+                    raise RuntimeError(f"{nm} must be {(B, *self.out_shape)}, got {tuple(tns.shape)}")
+        if out is None:
+            out = torch.empty(B, *self.out_shape, device=self.device, dtype=torch.float32)
+        upd = _lib.Update(_lib.ptr(xt), _lib.ptr(fprev), _lib.ptr(out_f), alpha, beta, gamma)
+        ws, ws_bytes = self.workspace(B)
+        _lib.check(self.lib.swb200_forward(C.byref(self.model), x0.data_ptr(), c0, scale0, _lib.ptr(x1), c1, B,
+                                           gain.data_ptr(), bias.data_ptr(), C.byref(upd), out.data_ptr(), ws,
+                                           ws_bytes, self._stream()), "forward")
+        self.launches += self.launches_per_forward(B)
+        return out

@@ -1,0 +1,174 @@
+"""Drop-in ``SwinV2`` denoiser: the reference's constructor, ``forward`` signature and state-dict schema
+(stockeh/swift ``src/swift/models/swinv2.py:254-330``), with the compute done by hand-written sm_100a kernels.
+
+Selecting it: point hydra's ``model._target_`` at ``swift_b200.swinv2.SwinV2`` (the reference names
+``swift.models.swinv2.SwinV2`` in ``configs/model/swinv2.yaml:1``); ``PassPrecond`` then instantiates it with the
+same keyword arguments (``models/precond.py:123-131``) and ``load_state_dict(state["ema"])`` succeeds strictly.
+
+The sub-modules below only *hold parameters* under the reference's names; none of them has a ``forward``.
+``SwinV2.forward`` packs the parameters once per checkpoint (bf16 GEMM weights, reordered rows -- see
+``packing.py``) and calls ``libswift_b200.so``.  Inference only: there is no autograd graph and no CPU path.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Union
+
+import torch
+import torch.nn as nn
+
+from . import packing
+from .engine import Engine
+
+try:  # when the reference package is importable, be an ``AbstractNetwork`` so isinstance checks keep working
+    from swift.models.abstract import AbstractNetwork as _Base  # type: ignore
+except Exception:  # pragma: no cover - the normal case on the GPU box
+    class _Base(nn.Module):
+        """Same attributes as swift.models.abstract.AbstractNetwork (models/abstract.py:12-35)."""
+
+        def __init__(self, img_resolution, in_channels: int, out_channels: int):
+            super().__init__()
+            self.img_resolution = img_resolution
+            self.in_channels = in_channels
+            self.out_channels = out_channels
+
+
+# ---------------------------------------------------------------------------- parameter containers
+class _ModulatedNorm(nn.Module):            # models/swinv2.py:77-86
+    def __init__(self, dim: int, eps: float = 1e-6):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim, eps)
+        self.modulation = nn.Linear(dim, dim * 2, bias=True)
+
+
+class _Attention(nn.Module):                # models/swinv2.py:105-116
+    def __init__(self, dim: int, heads: int):
+        super().__init__()
+        self.norm = _ModulatedNorm(dim)
+        self.to_qkv = nn.Linear(dim, dim * 3, bias=False)
+        self.wo = nn.Linear(dim, dim, bias=False)
+        self.scale = nn.Parameter(torch.log(10 * torch.ones(1, heads, 1, 1)))
+
+
+class _FeedForward(nn.Module):              # models/swinv2.py:89-96
+    def __init__(self, dim: int, hidden: int):
+        super().__init__()
+        self.norm = _ModulatedNorm(dim)
+        self.w1 = nn.Linear(dim, 2 * hidden, bias=False)
+        self.w2 = nn.Linear(hidden, dim, bias=False)
+
+
+class _Transformer(nn.Module):              # models/swinv2.py:142-172
+    def __init__(self, depth: int, dim: int, heads: int):
+        super().__init__()
+        hidden = int(8 / 3.0 * dim)
+        self.layers = nn.Sequential(*[nn.ModuleList([_Attention(dim, heads), _FeedForward(dim, hidden)])
+                                      for _ in range(depth)])
+
+
+class _PatchEmbedding(nn.Module):           # models/swinv2.py:217-222
+    def __init__(self, in_features: int, dim: int):
+        super().__init__()
+        self.emb = nn.Linear(in_features, dim)
+
+
+class _LatentEmbedding(nn.Module):          # models/swinv2.py:67-71
+    def __init__(self, dim: int):
+        super().__init__()
+        self.l1 = nn.Linear(dim, dim, bias=True)
+        self.l2 = nn.Linear(dim, dim, bias=True)
+
+
+class _OutputHead(nn.Module):               # models/swinv2.py:233-244 (the Rearrange holds no parameters)
+    def __init__(self, dim: int, out_features: int):
+        super().__init__()
+        self.head = nn.Sequential(nn.Linear(dim, out_features, bias=False))
+
+
+# ---------------------------------------------------------------------------- the module
+class SwinV2(_Base):
+    def __init__(self, img_resolution, in_channels: int, out_channels: int, window_size, shift_size, patch_size,
+                 depth: int = 6, dim: int = 512, heads: int = 12, auxiliary_dim: int = 0, flash: bool = True,
+                 logvar: bool = False, timestep_weight: float = 1.0):
+        super().__init__(img_resolution, in_channels, out_channels)
+        img, patch = packing._pair(img_resolution), packing._pair(patch_size)
+        self.geometry = packing.Geometry(img=img, patch=patch, window=packing._pair(window_size),
+                                         shift=packing._pair(shift_size), in_channels=in_channels,
+                                         out_channels=out_channels, depth=depth, dim=dim, heads=heads,
+                                         aux_dim=auxiliary_dim, timestep_weight=float(timestep_weight))
+        packing.check_supported(self.geometry)      # fail at construction, not at the first forward
+        gh, gw = self.geometry.grid
+        self.auxiliary_dim = auxiliary_dim
+        self.timestep_weight = timestep_weight
+        self.flash = flash                           # accepted for signature parity; attention is always fused
+
+        self.pos_embed = nn.Parameter(torch.randn(1, gh * gw, dim) * 0.02)
+        self.patch_embed = _PatchEmbedding(in_channels * patch[0] * patch[1], dim)
+        self.latent_embed = _LatentEmbedding(dim)
+        self.logvar_embed = nn.Linear(dim, 1) if logvar else None
+        self.auxiliary_embed = nn.Linear(auxiliary_dim, dim) if auxiliary_dim else None
+        self.transformer = _Transformer(depth, dim, heads)
+        self.head = _OutputHead(dim, out_channels * patch[0] * patch[1])
+        self._init_weights()
+        self._engine: Optional[Engine] = None
+        self._engine_key = None
+        self.split_embed = True      # [hi|lo] bf16 operands for the two small end GEMMs (accuracy, <1% of FLOPs)
+        self.split_head = True
+        self.max_chunk = 8           # samples pushed through the kernels per launch sequence
+
+    def _init_weights(self):
+        """Same policy as models/swinv2.py:295-303: trunc_normal(0.02), zeros for modulation/head, zero biases."""
+        for name, m in self.named_modules():
+            if isinstance(m, nn.Linear):
+                if "modulation" in name or "head" in name:
+                    nn.init.zeros_(m.weight)
+                else:
+                    nn.init.trunc_normal_(m.weight, std=0.02)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+
+    # ------------------------------------------------------------------ engine management
+    def _params_key(self):
+        return tuple((p.data_ptr(), p._version, p.device) for p in self.parameters())
+
+    def engine(self) -> Engine:
+        """The packed CUDA engine for the current parameter values (re-packed when parameters change)."""
+        key = (self._params_key(), self.split_embed, self.split_head, self.max_chunk)
+        if self._engine is None or self._engine_key != key:
+            dev = self.pos_embed.device
+            if dev.type != "cuda":
+                raise RuntimeError("swift_b200.SwinV2 runs on CUDA only: move the module to a B200 with .cuda(); "
+                                   "there is no CPU fallback")
+            sd = {k: v for k, v in self.state_dict().items()}
+            self._engine = Engine(sd, self.geometry, dev, self.split_embed, self.split_head, self.max_chunk)
+            self._engine_key = key
+        return self._engine
+
+    # ------------------------------------------------------------------ reference-compatible forward
+    def forward(self, x: torch.Tensor, t: torch.Tensor, auxiliary: Optional[torch.Tensor] = None, jvp: bool = False,
+                return_logvar: bool = False) -> Union[torch.Tensor, tuple]:
+        """models/swinv2.py:305-330.  x [B, in_channels, H, W]; t scalar, [1] or [B]; auxiliary [B, aux_dim] or None."""
+        if jvp:
+            raise NotImplementedError("the forward-mode tangent (sCM training) path is not part of the forecast hot "
+                                      "path implemented by swift_b200 (SURVEY.md section 8f)")
+        if self.training and torch.is_grad_enabled():
+            raise RuntimeError("swift_b200.SwinV2 is inference-only: call .eval() / use torch.no_grad()")
+        eng = self.engine()
+        B = x.shape[0]
+        x = x.detach().to(torch.float32).contiguous()
+        t = t.detach().to(device=x.device, dtype=torch.float32)
+        if t.dim() == 0 or (t.dim() == 1 and t.shape[0] == 1):     # models/swinv2.py:316-317
+            t = t.reshape(-1).repeat(B)
+        t = t.contiguous()
+        aux = None
+        if self.auxiliary_embed is not None and auxiliary is not None:
+            aux = auxiliary.detach().to(device=x.device, dtype=torch.float32).reshape(-1, self.auxiliary_dim)
+            if aux.shape[0] == 1 and B > 1:                        # broadcast like the reference's `t + aux_embed(.)`
+                aux = aux.expand(B, -1)
+            aux = aux.contiguous()
+        want_lv = self.logvar_embed is not None and return_logvar
+        cond = eng.conditioning(t, aux, want_cond=want_lv)
+        y = eng.forward(x, None, cond[0], cond[1])
+        if want_lv:                                                # models/swinv2.py:326-328
+            return y, torch.nn.functional.linear(cond[2], self.logvar_embed.weight, self.logvar_embed.bias).squeeze(-1)
+        return y

@@ -1,0 +1,161 @@
+"""End-to-end parity of the CUDA denoiser / samplers with the reference (golden files) and the oracle.
+
+Tolerance (BASELINE.json north_star): per-field relative L2 <= 1e-2 after one step, fields = output channels,
+norms over (H, W).  Weights of the GEMM families are bf16-representable (swift_b200.synthetic), activations are
+rounded to bf16 at GEMM inputs, everything else is fp32.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-2
+
+
+def per_field_rel_l2(y, ref):
+    y, ref = torch.as_tensor(y).double().cpu(), torch.as_tensor(ref).double().cpu()
+    num = (y - ref).flatten(2).norm(dim=-1)
+    den = ref.flatten(2).norm(dim=-1).clamp_min(1e-30)
+    return num / den          # [B, C]
+
+
+def build_net(cfg, seed=1, img_channels=None):
+    from swift_b200 import synthetic as syn
+    from swift_b200.precond import PassPrecond
+    img_channels = cfg["out_channels"] if img_channels is None else img_channels
+    model_cfg = dict(_target_="swift_b200.swinv2.SwinV2", window_size=cfg["window_size"],
+                     shift_size=cfg["shift_size"], patch_size=cfg["patch_size"], depth=cfg["depth"], dim=cfg["dim"],
+                     heads=cfg["heads"], logvar=False, timestep_weight=1.0)
+    net = PassPrecond(model_cfg, img_resolution=cfg["img_resolution"], img_channels=img_channels,
+                      condition_channels=cfg["in_channels"] - img_channels, auxiliary_dim=cfg["auxiliary_dim"],
+                      sigma_min=0.0, sigma_max=float("inf"), sigma_data=1.0)
+    sd = syn.random_state_dict(cfg, seed=seed, prefix="model.")
+    missing = net.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return net.cuda().eval(), {k[len("model."):]: v for k, v in sd.items()}
+
+
+@pytest.mark.parametrize("name,cfgname", [("tiny", "SWIFT_TINY"), ("small", "SWIFT_SMALL")])
+def test_module_forward_vs_reference_golden(golden, name, cfgname):
+    from swift_b200 import synthetic as syn
+    g = golden(name)
+    cfg = getattr(syn, cfgname)
+    net, _ = build_net(cfg)
+    lat, cond = syn.synthetic_fields(cfg, 2, seed=3)
+    with torch.no_grad():
+        y = net(lat.cuda(), torch.from_numpy(g["fwd_t"]).cuda(), cond.cuda(), torch.from_numpy(g["fwd_aux"]).cuda())
+    err = per_field_rel_l2(y, g["fwd_y"])
+    print(f"{name}: forward per-field rel-L2 max {err.max():.4e} mean {err.mean():.4e}")
+    assert err.max() < TOL
+
+
+@pytest.mark.parametrize("name,cfgname", [("tiny", "SWIFT_TINY"), ("small", "SWIFT_SMALL")])
+def test_samplers_vs_reference_golden(golden, name, cfgname):
+    from swift_b200 import synthetic as syn
+    from swift_b200.sampler import DiffusionSampler
+    g = golden(name)
+    cfg = getattr(syn, cfgname)
+    net, _ = build_net(cfg)
+    lat, cond = syn.synthetic_fields(cfg, 2, seed=3)
+    lat, cond = lat.cuda(), cond.cuda()
+    z = torch.from_numpy(g["scm2_noise"]).cuda()
+    S = DiffusionSampler(net)
+    kw = dict(condition=cond, auxiliary=0.6, sigma_min=0.02, sigma_max=200.0)
+    res = {
+        "scm1": S.scm_solver(latents=lat, num_steps=1, **kw),
+        "scm2": S.scm_solver(latents=lat, num_steps=2, randn_like=lambda x: z, **kw),
+        "scm3": S.scm_solver(latents=lat, num_steps=3, randn_like=lambda x: z, **kw),
+        "dpm2s_3": S.dpm_solver_2s(latents=lat, num_steps=3, **kw),
+    }
+    for k, v in res.items():
+        err = per_field_rel_l2(v, g[k])
+        print(f"{name}/{k}: per-field rel-L2 max {err.max():.4e}")
+        # multi-step solvers chain 2..5 denoiser calls; the stated bar is for one step
+        assert err.max() < (TOL if k == "scm1" else 3 * TOL), (k, err.max())
+
+
+def test_fused_sampler_equals_generic_path():
+    """sampler fast path (fused concat/update) == calling the module through PassPrecond.forward like the reference."""
+    from swift_b200 import synthetic as syn
+    from swift_b200.sampler import DiffusionSampler
+    cfg = syn.SWIFT_TINY
+    net, _ = build_net(cfg)
+    lat, cond = syn.synthetic_fields(cfg, 2, seed=5)
+    lat, cond = lat.cuda(), cond.cuda()
+    fused = DiffusionSampler(net).scm_solver(latents=lat, condition=cond, auxiliary=0.6, num_steps=1,
+                                              sigma_min=0.02, sigma_max=200.0)
+    t = torch.tensor([math.pi / 2], device="cuda")
+    with torch.no_grad():
+        F = net(lat, t.expand(2), cond, 0.6)
+    generic = torch.cos(t) * lat - torch.sin(t) * F
+    assert torch.allclose(fused, generic, rtol=1e-5, atol=1e-6)
+
+
+def test_swift_b_one_step_vs_oracle_and_golden(golden):
+    """BASELINE.json configs[0]: Swift-B, single 6 h sCM step, batch 1, 128x256, vs fp32 reference."""
+    from oracle import swinv2_oracle as orc
+    from swift_b200 import synthetic as syn
+    from swift_b200.sampler import DiffusionSampler
+    cfg = syn.SWIFT_B
+    net, sd = build_net(cfg, img_channels=syn.IMG_CHANNELS)
+    lat, cond = syn.synthetic_fields(cfg, 1, seed=0)
+    y = DiffusionSampler(net).scm_solver(latents=lat.cuda(), condition=cond.cuda(), auxiliary=0.6, num_steps=1,
+                                         sigma_min=0.02, sigma_max=200.0)
+    torch.cuda.synchronize()
+    # oracle in fp32 on the GPU (TF32 off) for speed; pinned to the reference by the digest below
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    ocfg = orc.make_cfg(**cfg)
+    sd_gpu = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        ref = orc.scm_solver(lambda x, t, c, a: orc.pass_precond(sd_gpu, ocfg, x, t, c, a), lat.cuda(), cond.cuda(),
+                             0.6, num_steps=1)
+    g = golden("swift_b")
+    assert np.allclose(ref[:, :, ::8, ::8].cpu().numpy(), g["scm1_sub"], rtol=2e-3, atol=2e-4), \
+        "GPU fp32 oracle drifted from the reference digest"
+    err = per_field_rel_l2(y, ref)
+    print(f"swift_b scm1: per-field rel-L2 max {err.max():.4e} mean {err.mean():.4e}")
+    assert err.max() < TOL
+    sub = per_field_rel_l2(y[:, :, ::8, ::8], torch.from_numpy(g["scm1_sub"]))
+    assert sub.max() < 1.5 * TOL            # sub-sampled norm (512 points per field) is noisier
+
+
+def test_module_contract():
+    from swift_b200 import synthetic as syn
+    from swift_b200.swinv2 import SwinV2
+    cfg = syn.SWIFT_TINY
+    m = SwinV2(**cfg)
+    ref_shapes = syn.state_dict_shapes(cfg)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == ref_shapes
+    # default init zeroes modulation/head like the reference -> output identically 0
+    m = m.cuda().eval()
+    x = torch.randn(1, cfg["in_channels"], 32, 64, device="cuda")
+    with torch.no_grad():
+        y = m(x, torch.tensor(0.5, device="cuda"), torch.tensor([[0.6]], device="cuda"))
+    assert y.shape == (1, cfg["out_channels"], 32, 64) and float(y.abs().max()) == 0.0
+    with pytest.raises(RuntimeError):
+        m.cpu()(x.cpu(), torch.tensor(0.5))
+    with pytest.raises(NotImplementedError):
+        m.cuda()(x, torch.tensor(0.5, device="cuda"), jvp=True)
+    with pytest.raises(NotImplementedError):
+        SwinV2(**{**cfg, "window_size": [8, 8]})
+    m.train()
+    with pytest.raises(RuntimeError):
+        m(x, torch.tensor(0.5, device="cuda"))
+
+
+def test_chunked_batch_matches_single():
+    from swift_b200 import synthetic as syn
+    cfg = syn.SWIFT_TINY
+    net, _ = build_net(cfg)
+    lat, cond = syn.synthetic_fields(cfg, 5, seed=9)
+    t = torch.full((5,), 0.9, device="cuda")
+    with torch.no_grad():
+        net.model.max_chunk = 8
+        y_all = net(lat.cuda(), t, cond.cuda(), 0.6).clone()
+        net.model.max_chunk = 2
+        y_chunk = net(lat.cuda(), t, cond.cuda(), 0.6)
+    assert torch.equal(y_all, y_chunk)

@@ -1,0 +1,147 @@
+"""Glue kernels and window attention through the C ABI vs PyTorch / oracle references."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+HD, HDP = 88, 96
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from swift_b200 import _lib
+    return _lib.lib()
+
+
+def _check(rc):
+    from swift_b200 import _lib
+    _lib.check(rc, "test call")
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("split", [0, 1])
+@pytest.mark.parametrize("p1,p2,C0,C1,H,W", [(2, 2, 5, 8, 32, 64), (2, 2, 69, 72, 128, 256), (1, 1, 3, 4, 16, 32),
+                                             (2, 4, 3, 0, 16, 64)])
+def test_patch_gather(lib, split, p1, p2, C0, C1, H, W):
+    from swift_b200 import _lib
+    B = 2
+    x0 = torch.randn(B, C0, H, W, device="cuda")
+    x1 = torch.randn(B, C1, H, W, device="cuda") if C1 else None
+    m = _lib.Model()
+    m.img_h, m.img_w, m.patch_h, m.patch_w, m.in_channels = H, W, p1, p2, C0 + C1
+    Cin = C0 + C1
+    kp = (Cin * p1 * p2 + 7) // 8 * 8
+    m.k_embed, m.split_embed = kp, split
+    lda = kp * (1 + split)
+    T = (H // p1) * (W // p2)
+    A = torch.full((B * T, lda), float("nan"), device="cuda", dtype=torch.bfloat16)
+    scale0 = 0.5
+    _check(lib.swb200_patch_gather(C.byref(m), x0.data_ptr(), C0, scale0, _lib.ptr(x1), C1, B, A.data_ptr(), lda,
+                                   _stream()))
+    torch.cuda.synchronize()
+    full = torch.cat([x0 * scale0] + ([x1] if C1 else []), 1)
+    # ours: k = c*pp + py*p2 + px
+    ref = full.reshape(B, Cin, H // p1, p1, W // p2, p2).permute(0, 2, 4, 1, 3, 5).reshape(B * T, Cin * p1 * p2)
+    hi = ref.to(torch.bfloat16)
+    assert torch.equal(A[:, :Cin * p1 * p2], hi)
+    assert (A[:, Cin * p1 * p2:kp] == 0).all()
+    if split:
+        lo = (ref - hi.float()).to(torch.bfloat16)
+        assert torch.equal(A[:, kp:kp + Cin * p1 * p2], lo)
+        assert _rel(A[:, :kp].float()[:, :Cin * p1 * p2] + A[:, kp:].float()[:, :Cin * p1 * p2], ref) < 2e-5
+
+
+@pytest.mark.parametrize("D", [264, 528, 1056])
+@pytest.mark.parametrize("with_lo", [False, True])
+def test_ln_mod_residual(lib, D, with_lo):
+    B, T = 3, 256
+    M = B * T
+    branch = torch.randn(M, D, device="cuda") * 3 + 0.7
+    x = torch.randn(M, D, device="cuda")
+    gain = torch.randn(B, D, device="cuda")
+    bias = torch.randn(B, D, device="cuda")
+    ldxb = 2 * D if with_lo else D
+    xb = torch.zeros(M, ldxb, device="cuda", dtype=torch.bfloat16)
+    x_ref = x + torch.nn.functional.layer_norm(branch, (D,), eps=1e-6).reshape(B, T, D).mul(gain[:, None]).add(
+        bias[:, None]).reshape(M, D)
+    xlo_ptr = xb.data_ptr() + 2 * D if with_lo else None
+    _check(lib.swb200_ln_mod_residual(branch.data_ptr(), x.data_ptr(), xb.data_ptr(), ldxb, xlo_ptr, gain.data_ptr(),
+                                      bias.data_ptr(), M, D, T, _stream()))
+    torch.cuda.synchronize()
+    assert _rel(x, x_ref) < 2e-6, f"{_rel(x, x_ref):.3e}"
+    assert torch.equal(xb[:, :D], x.to(torch.bfloat16))
+    if with_lo:
+        assert torch.equal(xb[:, D:], (x - xb[:, :D].float()).to(torch.bfloat16))
+
+
+def _window_attention_ref(qkv, B, gh, gw, H, shift):
+    """Reference on the same packed bf16 q/k/v: roll, partition, softmax(q k^T) v, reverse, roll back."""
+    M = B * gh * gw
+    q, k, v = [qkv[i, :, :, :HD].float().reshape(H, B, gh, gw, HD) for i in range(3)]
+
+    def win(t):
+        t = torch.roll(t, shifts=(-shift[0], -shift[1]), dims=(2, 3))
+        t = t.reshape(H, B, gh // 16, 16, gw // 16, 16, HD).permute(0, 1, 2, 4, 3, 5, 6)
+        return t.reshape(H, B, (gh // 16) * (gw // 16), 256, HD)
+
+    qw, kw, vw = win(q), win(k), win(v)
+    o = torch.softmax(qw @ kw.transpose(-1, -2), dim=-1) @ vw
+    o = o.reshape(H, B, gh // 16, gw // 16, 16, 16, HD).permute(0, 1, 2, 4, 3, 5, 6).reshape(H, B, gh, gw, HD)
+    o = torch.roll(o, shifts=(shift[0], shift[1]), dims=(2, 3))
+    return o.permute(1, 2, 3, 0, 4).reshape(M, H * HD)
+
+
+@pytest.mark.parametrize("shift", [(0, 0), (8, 8), (8, 0), (3, 5)])
+@pytest.mark.parametrize("B,gh,gw,H", [(1, 16, 32, 3), (2, 32, 32, 2), (1, 64, 128, 12)])
+def test_window_attention(lib, shift, B, gh, gw, H):
+    M = B * gh * gw
+    g = torch.Generator(device="cuda").manual_seed(5)
+    raw = torch.randn(3, H, M, HDP, generator=g, device="cuda")
+    raw[..., HD:] = 0
+    qs = torch.linspace(4.0, 30.0, H, device="cuda")[:, None, None]
+    raw[0] = torch.nn.functional.normalize(raw[0], dim=-1) * qs
+    raw[1] = torch.nn.functional.normalize(raw[1], dim=-1)
+    qkv = raw.to(torch.bfloat16).contiguous()
+    out = torch.full((M, H * HD), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _check(lib.swb200_window_attention(qkv.data_ptr(), out.data_ptr(), B, gh, gw, H, shift[0], shift[1], _stream()))
+    torch.cuda.synchronize()
+    ref = _window_attention_ref(qkv, B, gh, gw, H, shift)
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out.float(), ref) < 8e-3, f"{_rel(out.float(), ref):.3e}"   # P and output are rounded to bf16
+
+
+def test_conditioning_matches_oracle(lib):
+    from oracle import swinv2_oracle as orc
+    from swift_b200 import packing, synthetic as syn
+    from swift_b200.engine import Engine
+    c = syn.SWIFT_SMALL
+    sd = syn.random_state_dict(c, seed=1)
+    g = packing.Geometry(img=(64, 64), patch=(2, 2), window=(16, 16), shift=(8, 8), in_channels=c["in_channels"],
+                         out_channels=c["out_channels"], depth=c["depth"], dim=c["dim"], heads=c["heads"], aux_dim=1,
+                         timestep_weight=1.0)
+    eng = Engine(sd, g, torch.device("cuda"))
+    t = torch.tensor([0.3, math.pi / 2, 1.1], device="cuda")
+    aux = torch.tensor([[0.6], [1.2], [2.4]], device="cuda")
+    gain, bias, cond = eng.conditioning(t, aux, want_cond=True)
+    torch.cuda.synchronize()
+    cref = orc.conditioning_vector(sd, t.cpu(), aux.cpu(), c["dim"], 1, 1.0, 3)
+    assert _rel(cond.cpu(), cref) < 1e-5
+    D = c["dim"]
+    for l in range(c["depth"]):
+        for j, blk in enumerate(("0", "1")):
+            pre = f"transformer.layers.{l}.{blk}.norm"
+            mod = torch.nn.functional.linear(cref, sd[pre + ".modulation.weight"], sd[pre + ".modulation.bias"])
+            g_ref = sd[pre + ".norm.weight"] * (1 + mod[:, :D])
+            b_ref = sd[pre + ".norm.bias"] * (1 + mod[:, :D]) + mod[:, D:]
+            assert _rel(gain[2 * l + j].cpu(), g_ref) < 1e-5
+            assert _rel(bias[2 * l + j].cpu(), b_ref) < 1e-5
