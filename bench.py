@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""Benchmark of the Swift forecast hot path (BASELINE.json: forecast member-steps/sec).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path (one rank per GPU under torchrun)
+  python bench.py --impl reference [...]                         the reference algorithm on the host CPU cores
+
+Workload (BASELINE.json configs[1]; configs[2] when launched on 8 GPUs): Swift-B (era5-swinv2-1.4-scm) sCM 1-step
+autoregressive rollout, 12 members x 8 initial conditions = 96 resident trajectories PER GPU (weak scaling: at
+N = 8 this is the 12 x 64 workload of configs[2]), synthetic 128x256 ERA5-shaped fields, random-init weights.
+One bench "step" = one 6 h advance of every resident trajectory = 96 member-steps per GPU (96 denoiser forwards).
+K = 60 steps is the full 15-day rollout.
+
+  value  member-steps/s with initial conditions, forcings and weights already resident in HBM (device-timed with
+         CUDA events, max over ranks).
+  e2e    the same rollout through the public sampler API with HOST buffers: every step copies that step's forcings
+         from pinned host memory and reads the new physical state back to pinned host memory (what
+         generate.py:100-131 does with `.to(device)` / `.cpu()`).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOP_PER_MEMBER_STEP = 2.75177e12     # un-padded 2*M*N*K of one Swift-B denoiser call
+MEMBERS, ICS_PER_GPU = 12, 8
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            p = [v.strip() for v in ln.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[1]))
+                smax = float(p[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference / CPU arm
+def cpu_member_steps_per_sec(n_timed: int, warmup: int = 1):
+    """The reference algorithm (oracle port: plain PyTorch fp32, all host threads) on one Swift-B sCM step, B = 1."""
+    import torch
+    from oracle import swinv2_oracle as orc
+    from swift_b200 import synthetic as syn
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = syn.SWIFT_B
+    sd = syn.random_state_dict(cfg, seed=1)
+    ocfg = orc.make_cfg(**cfg)
+    lat, cond = syn.synthetic_fields(cfg, 1, seed=0)
+    net = lambda x, t, c, a: orc.pass_precond(sd, ocfg, x, t, c, a)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + n_timed):
+            t0 = time.perf_counter()
+            orc.scm_solver(net, lat, cond, 0.6, num_steps=1)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    per = sum(times) / len(times)
+    return 1.0 / per, per, cores, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = max(1, min(args.steps, 20))          # bounded: one member-step is seconds of CPU work
+    v, per, cores, threads = cpu_member_steps_per_sec(n, max(1, min(args.warmup, 1)))
+    sample = (f"{n} sCM member-steps of Swift-B at batch 1 (of the 96/step workload), fp32, "
+              f"oracle port of swift.models.swinv2 + scm_solver, {threads} torch threads")
+    line = {
+        "impl": "reference", "metric": "forecast member-steps/sec", "value": v, "unit": "member-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus, "cpu"),
+        "cpu_baseline": {"value": v, "unit": "member-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "member-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_tflops": v * FLOP_PER_MEMBER_STEP / 1e12,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus: int, where: str):
+    return {"workload": "Swift-B (era5-swinv2-1.4-scm) sCM 1-step autoregressive rollout, 12 members x 8 ICs per GPU "
+                        "x K 6h steps (K=60: 15 days), 128x256 synthetic ERA5 fields, random-init weights",
+            "members": MEMBERS, "initial_conditions": ICS_PER_GPU * n_gpus, "trajectories_per_gpu": MEMBERS * ICS_PER_GPU,
+            "member_steps_per_bench_step": MEMBERS * ICS_PER_GPU * n_gpus,
+            "sharding": f"(member, IC) over {n_gpus} GPU(s), no collective on the forecast path",
+            "l2_policy": "inputs larger than L2 (96 trajectories x 18.5 MB inputs, 216 MB workspace per sample)",
+            "device": where}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from swift_b200 import synthetic as syn
+    from swift_b200.precond import PassPrecond
+    from swift_b200.rollout import EnsembleRollout, Normalizers, shard_trajectories
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    n_gpus = world
+
+    cfg = syn.SWIFT_B
+    model_cfg = dict(_target_="swift_b200.swinv2.SwinV2", window_size=cfg["window_size"], shift_size=cfg["shift_size"],
+                     patch_size=cfg["patch_size"], depth=cfg["depth"], dim=cfg["dim"], heads=cfg["heads"])
+    net = PassPrecond(model_cfg, img_resolution=cfg["img_resolution"], img_channels=syn.IMG_CHANNELS,
+                      condition_channels=syn.COND_CHANNELS, auxiliary_dim=1, sigma_min=0.0, sigma_max=float("inf"))
+    net.load_state_dict(syn.random_state_dict(cfg, seed=1, prefix="model."), strict=True)
+    net = net.to(dev).eval()
+    net.model.max_chunk = args.chunk
+    eng = net.model.engine()
+
+    n_ic = ICS_PER_GPU * n_gpus
+    traj = shard_trajectories(MEMBERS, n_ic, rank, world)
+    B = len(traj)
+    total_steps = args.warmup + args.steps
+    forc_host = syn.synthetic_forcings(cfg, total_steps, seed=0).pin_memory()
+    forc_dev = forc_host.to(dev)
+    norm = Normalizers.synthetic(syn.IMG_CHANNELS, dev, diff=0.1)
+    ro = EnsembleRollout(net, norm, forc_dev, traj, solver="scm")
+    ics = {}
+    x0 = torch.empty(B, syn.IMG_CHANNELS, *cfg["img_resolution"])
+    for b, (m, j) in enumerate(traj):
+        if j not in ics:
+            ics[j] = syn.synthetic_fields(cfg, 1, seed=j)[1][0, :syn.IMG_CHANNELS]
+        x0[b] = ics[j]
+    x0 = x0.pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident leg
+    ro.set_state(x0.to(dev))
+    for i in range(args.warmup):
+        ro.step(i)
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    launches0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        ro.step(args.warmup + i)
+    e1.record()
+    barrier()
+    clock_info = clocks.stop()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = eng.launches - launches0
+    member_steps = B * world * args.steps
+    value = member_steps / (ms / 1e3)
+
+    # ---------------- end-to-end leg: host buffers in, host buffers out, every step
+    out_host = torch.empty(B, syn.IMG_CHANNELS, *cfg["img_resolution"]).pin_memory()
+    ro.set_state(x0.to(dev, non_blocking=True))
+    forc_step = torch.empty_like(forc_dev[0])
+    e2e_steps = args.steps if args.e2e_steps <= 0 else min(args.e2e_steps, args.steps)
+    for i in range(min(args.warmup, 1)):
+        forc_step.copy_(forc_host[i], non_blocking=True)
+        out_host.copy_(ro.step(i, forc_step), non_blocking=True)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    e2.record()
+    for i in range(e2e_steps):
+        forc_step.copy_(forc_host[args.warmup + i], non_blocking=True)            # H2D: this step's forcings
+        x_phys = ro.step(args.warmup + i, forc_step)
+        out_host.copy_(x_phys, non_blocking=True)                                  # D2H: new physical state
+        torch.cuda.current_stream().synchronize()                                  # host consumes it (generate.py:129)
+    e3.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    e2e_ms = max_over_ranks(max(e2.elapsed_time(e3), wall_ms))
+    e2e_value = B * world * e2e_steps / (e2e_ms / 1e3)
+    h2d = forc_step.numel() * 4
+    d2h = out_host.numel() * 4
+
+    # ---------------- roofline of the dominant kernel (SwiGLU up-projection GEMM: 42.5 % of the FLOPs), timed alone
+    roof = dominant_kernel_roofline(eng, dev, args.chunk)
+    peaks, which = measured_peaks()
+    step_tflops = value / world * FLOP_PER_MEMBER_STEP / 1e12
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        v, per, cores, threads = cpu_member_steps_per_sec(2, 1)
+        cpu = {"value": v, "unit": "member-steps/s", "cores": cores, "kind": "port",
+               "sample": f"2 Swift-B sCM member-steps at batch 1 after 1 warm-up ({per:.2f} s each), fp32 oracle port, "
+                         f"{threads} torch threads"}
+    line = {
+        "metric": "forecast member-steps/sec", "value": value, "unit": "member-steps/s", "n_gpus": n_gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 tensor-core GEMMs, fp32 accumulate / residual / LayerNorm / softmax",
+        "data": "synthetic", "config": workload_config(n_gpus, torch.cuda.get_device_name(dev)),
+        "clocks": clock_info,
+        "e2e": {"value": e2e_value, "unit": "member-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps},
+        "gpu_launches": launches,
+        "roofline": roof,
+        "step_tflops_per_gpu": step_tflops,
+        "step_frac_of_sustained_bf16": step_tflops / peaks["bf16_tflops_sustained"],
+        "peaks": which,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def dominant_kernel_roofline(eng, dev, chunk: int):
+    """w1 (SwiGLU) GEMM at the shapes of the rollout: M = chunk*8192, N = 5632, K = 1056, timed alone with CUDA
+    events on the launch stream (inputs + outputs of one launch exceed L2 for chunk >= 4)."""
+    import ctypes as C
+    import torch
+    from swift_b200 import _lib
+
+    g = eng.geom
+    M, D, Dff = chunk * g.tokens, g.dim, g.dff
+    A = (torch.randn(M, D, device=dev) * 0.5).to(torch.bfloat16)
+    out = torch.empty(M, Dff, device=dev, dtype=torch.bfloat16)
+    W = eng._keep["w_1"][0]
+    stream = torch.cuda.current_stream().cuda_stream
+    lib = eng.lib
+    for _ in range(3):
+        _lib.check(lib.swb200_gemm_swiglu(2, A.data_ptr(), D, W.data_ptr(), out.data_ptr(), M, D, Dff, stream))
+    torch.cuda.synchronize()
+    n = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        _lib.check(lib.swb200_gemm_swiglu(2, A.data_ptr(), D, W.data_ptr(), out.data_ptr(), M, D, Dff, stream))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    flops = 2.0 * M * (2 * Dff) * D
+    peaks, which = measured_peaks()
+    achieved = flops / (ms / 1e3) / 1e12
+    return {"kernel": "gemm_tcgen05_kernel<176,2,EPI_SWIGLU> (w1 up-projection, 42.5% of FLOPs)", "bound": "tensor",
+            "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
+            "traffic": None, "launch_ms": ms, "flops_per_launch": flops, "peak_source": f"{which} burst bf16"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chunk", type=int, default=8, help="trajectories per kernel launch sequence")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end leg (0 = same as --steps)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
