@@ -264,7 +264,7 @@ def run_ours(args):
         "metric": "forecast member-steps/sec", "value": value, "unit": "member-steps/s", "n_gpus": n_gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16 tensor-core GEMMs, fp32 accumulate / residual / LayerNorm / softmax",
+        "dtype": ("fp16 activations x bf16 weights" if eng.act_fp16 else "bf16") + " on tcgen05 kind::f16, fp32 accumulate / residual / LayerNorm / softmax",
         "data": "synthetic", "config": workload_config(n_gpus, torch.cuda.get_device_name(dev)),
         "clocks": clock_info,
         "e2e": {"value": e2e_value, "unit": "member-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -290,19 +290,21 @@ def dominant_kernel_roofline(eng, dev, chunk: int):
 
     g = eng.geom
     M, D, Dff = chunk * g.tokens, g.dim, g.dff
-    A = (torch.randn(M, D, device=dev) * 0.5).to(torch.bfloat16)
-    out = torch.empty(M, Dff, device=dev, dtype=torch.bfloat16)
+    adt = torch.float16 if eng.act_fp16 else torch.bfloat16
+    f16 = int(eng.act_fp16)
+    A = (torch.randn(M, D, device=dev) * 0.5).to(adt)
+    out = torch.empty(M, Dff, device=dev, dtype=adt)
     W = eng._keep["w_1"][0]
     stream = torch.cuda.current_stream().cuda_stream
     lib = eng.lib
     for _ in range(3):
-        _lib.check(lib.swb200_gemm_swiglu(2, A.data_ptr(), D, W.data_ptr(), out.data_ptr(), M, D, Dff, stream))
+        _lib.check(lib.swb200_gemm_swiglu(2, f16, A.data_ptr(), D, W.data_ptr(), out.data_ptr(), M, D, Dff, stream))
     torch.cuda.synchronize()
     n = 20
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(n):
-        _lib.check(lib.swb200_gemm_swiglu(2, A.data_ptr(), D, W.data_ptr(), out.data_ptr(), M, D, Dff, stream))
+        _lib.check(lib.swb200_gemm_swiglu(2, f16, A.data_ptr(), D, W.data_ptr(), out.data_ptr(), M, D, Dff, stream))
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n

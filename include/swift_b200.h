@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SWB200_ABI_VERSION 1
+#define SWB200_ABI_VERSION 2
 #if defined(__GNUC__)
 #define SWB200_API __attribute__((visibility("default")))
 #else
@@ -49,6 +49,7 @@ typedef struct swb200_model {
   int32_t img_h, img_w, patch_h, patch_w, win_h, win_w, shift_h, shift_w;
   int32_t in_channels, out_channels, depth, dim, heads, dff, aux_dim;
   int32_t k_embed, split_embed, split_head;
+  int32_t act_fp16;           /* 1: activations (GEMM A operands, q/k/v, P) are fp16; 0: bf16.  Weights are bf16. */
   float timestep_weight;
   const void* w_embed;
   const float* b_embed;
@@ -117,18 +118,18 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
 
 /* ---- individual kernels (unit tests, profiling) -------------------------------------------------------- */
 
-/* D[M,N] = A[M,K] (bf16, row pitch lda) * W[N,K]^T (bf16, row pitch ldw), fp32 accumulate on tcgen05.
- * epi: 0 store fp32 out[M,ldo], 1 store bf16 out[M,ldo].  cta_group: 2 = paired-CTA UMMA (default), 1 = single. */
-SWB200_API int swb200_gemm(int epi, int cta_group, const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M,
-                int N, int K, void* stream);
+/* D[M,N] = A[M,K] (fp16 if act_fp16 else bf16, row pitch lda) * W[N,K]^T (bf16, row pitch ldw), fp32 accumulate
+ * on tcgen05.  epi: 0 store fp32 out[M,ldo], 1 store out[M,ldo] in the activation format.  cta_group: 2 = paired-CTA UMMA (default), 1 = single. */
+SWB200_API int swb200_gemm(int epi, int cta_group, int act_fp16, const void* A, int lda, const void* W, int ldw, void* out,
+                int ldo, int M, int N, int K, void* stream);
 /* qkv projection with fused scaled-cosine normalisation: out = bf16 [3][heads][M][96]; W packed as w_qkv. */
-SWB200_API int swb200_gemm_qkv(int cta_group, const void* A, int lda, const void* W, const float* qscale, void* out, int M,
+SWB200_API int swb200_gemm_qkv(int cta_group, int act_fp16, const void* A, int lda, const void* W, const float* qscale, void* out, int M,
                     int dim, int heads, void* stream);
 /* SwiGLU up-projection: out[M, dff] = silu(gate) * up; W packed as w_1. */
-SWB200_API int swb200_gemm_swiglu(int cta_group, const void* A, int lda, const void* W, void* out, int M, int dim, int dff,
+SWB200_API int swb200_gemm_swiglu(int cta_group, int act_fp16, const void* A, int lda, const void* W, void* out, int M, int dim, int dff,
                        void* stream);
 /* Patch-embed: x[M,dim] = A*W^T + bias + pos[row % tokens]; xb = bf16(x). */
-SWB200_API int swb200_gemm_embed(int cta_group, const void* A, int lda, const void* W, int K, const float* bias,
+SWB200_API int swb200_gemm_embed(int cta_group, int act_fp16, const void* A, int lda, const void* W, int K, const float* bias,
                       const float* pos, int tokens, float* x, void* xb, int M, int dim, void* stream);
 /* Output head with pixel-shuffle + update; A is [M, K] with K = dim*(1+split). */
 SWB200_API int swb200_gemm_head(int cta_group, const swb200_model* m, const void* A, int lda, int K, int B,
@@ -138,10 +139,10 @@ SWB200_API int swb200_patch_gather(const swb200_model* m, const float* x0, int c
                         void* A, int lda, void* stream);
 /* x += LN(branch)*gain[b] + bias[b]; xb = bf16(x) (pitch ldxb); xlo optional (same pitch). */
 SWB200_API int swb200_ln_mod_residual(const float* branch, float* x, void* xb, int ldxb, void* xlo, const float* gain,
-                           const float* bias, int M, int dim, int tokens, void* stream);
+                           const float* bias, int M, int dim, int tokens, int act_fp16, void* stream);
 /* shifted-window cosine attention on the packed qkv buffer; out bf16 [M, heads*88]. */
 SWB200_API int swb200_window_attention(const void* qkv, void* out, int B, int grid_h, int grid_w, int heads, int shift_h,
-                            int shift_w, void* stream);
+                            int shift_w, int act_fp16, void* stream);
 
 #ifdef __cplusplus
 }

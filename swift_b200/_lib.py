@@ -11,7 +11,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libswift_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # Every symbol ``include/swift_b200.h`` declares; tests check the library exports exactly these.
 EXPORTS = (
@@ -29,7 +29,7 @@ class Model(C.Structure):
     _fields_ = (
         [(n, _i32) for n in ("img_h", "img_w", "patch_h", "patch_w", "win_h", "win_w", "shift_h", "shift_w",
                              "in_channels", "out_channels", "depth", "dim", "heads", "dff", "aux_dim",
-                             "k_embed", "split_embed", "split_head")]
+                             "k_embed", "split_embed", "split_head", "act_fp16")]
         + [("timestep_weight", _f32)]
         + [(n, _vp) for n in ("w_embed", "b_embed", "pos_embed", "aux_w", "aux_b", "l1_w", "l1_b", "l2_w", "l2_b",
                               "mod_w", "mod_b", "ln_gamma", "ln_beta", "qscale", "w_qkv", "w_o", "w_1", "w_2",
@@ -56,16 +56,18 @@ def _declare(lib):
         "swb200_conditioning_scratch_bytes": (_sz, [MP, C.c_int]),
         "swb200_conditioning": (C.c_int, [MP, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _sz, _vp]),
         "swb200_forward": (C.c_int, [MP, _vp, C.c_int, _f32, _vp, C.c_int, C.c_int, _vp, _vp, UP, _vp, _vp, _sz, _vp]),
-        "swb200_gemm": (C.c_int, [C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int,
-                                  C.c_int, _vp]),
-        "swb200_gemm_qkv": (C.c_int, [C.c_int, _vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
-        "swb200_gemm_swiglu": (C.c_int, [C.c_int, _vp, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
-        "swb200_gemm_embed": (C.c_int, [C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, C.c_int,
-                                        C.c_int, _vp]),
+        "swb200_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int,
+                                  C.c_int, C.c_int, _vp]),
+        "swb200_gemm_qkv": (C.c_int, [C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+        "swb200_gemm_swiglu": (C.c_int, [C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+        "swb200_gemm_embed": (C.c_int, [C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp,
+                                        C.c_int, C.c_int, _vp]),
         "swb200_gemm_head": (C.c_int, [C.c_int, MP, _vp, C.c_int, C.c_int, C.c_int, UP, _vp, _vp]),
         "swb200_patch_gather": (C.c_int, [MP, _vp, C.c_int, _f32, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp]),
-        "swb200_ln_mod_residual": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
-        "swb200_window_attention": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+        "swb200_ln_mod_residual": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             _vp]),
+        "swb200_window_attention": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                              _vp]),
     }
     assert set(sig) == set(EXPORTS)
     for name, (res, args) in sig.items():

@@ -140,6 +140,7 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const Geom g = geom(m);
   const int D = m->dim, H = m->heads, Dff = m->dff;
+  const int F16 = m->act_fp16 ? 1 : 0;
   const size_t img_in0 = static_cast<size_t>(c0) * m->img_h * m->img_w;
   const size_t img_in1 = static_cast<size_t>(c1) * m->img_h * m->img_w;
   const size_t img_out = static_cast<size_t>(m->out_channels) * m->img_h * m->img_w;
@@ -159,7 +160,7 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
 
     // 1. concat + patchify + cast
     rc = launch_patch_gather(x0 + b0 * img_in0, c0, scale0, x1 ? x1 + b0 * img_in1 : nullptr, c1, a_emb,
-                             g.k_embed_total, m->k_embed, m->split_embed, bc, m->img_h, m->img_w, m->patch_h,
+                             g.k_embed_total, m->k_embed, m->split_embed, F16, bc, m->img_h, m->img_w, m->patch_h,
                              m->patch_w, stream);
     if (rc) return rc;
     // 2. patch-embed GEMM (+bias +pos_embed)
@@ -171,7 +172,7 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
       p.bias = m->b_embed;
       p.pos = m->pos_embed;
       p.pos_rows = g.tokens;
-      rc = launch_gemm(EPI_EMBED, kDefaultCG, a_emb, g.k_embed_total, m->w_embed, g.k_embed_total, p, stream);
+      rc = launch_gemm(EPI_EMBED, kDefaultCG, F16, a_emb, g.k_embed_total, m->w_embed, g.k_embed_total, p, stream);
       if (rc) return rc;
     }
     // 3. transformer blocks
@@ -184,29 +185,29 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
         p.heads = H;
         p.dmodel = D;
         const auto* wq = static_cast<const __nv_bfloat16*>(m->w_qkv) + static_cast<size_t>(l) * 3 * D * D;
-        rc = launch_gemm(EPI_QKV, kDefaultCG, xb, D, wq, D, p, stream);
+        rc = launch_gemm(EPI_QKV, kDefaultCG, F16, xb, D, wq, D, p, stream);
         if (rc) return rc;
       }
       rc = launch_window_attention(qkv, attn, bc, g.gh, g.gw, H, shifted ? m->shift_h : 0, shifted ? m->shift_w : 0,
-                                   stream);
+                                   F16, stream);
       if (rc) return rc;
       {
         GemmParams p = base_params(M, D, D);
         p.out0 = branch;
         p.ldo = D;
         const auto* wo = static_cast<const __nv_bfloat16*>(m->w_o) + static_cast<size_t>(l) * D * D;
-        rc = launch_gemm(EPI_STORE_F32, kDefaultCG, attn, D, wo, D, p, stream);
+        rc = launch_gemm(EPI_STORE_F32, kDefaultCG, F16, attn, D, wo, D, p, stream);
         if (rc) return rc;
       }
       rc = launch_ln_mod_residual(branch, x, xb, D, nullptr, gain + (static_cast<size_t>(2 * l) * B + b0) * D,
-                                  bias + (static_cast<size_t>(2 * l) * B + b0) * D, M, D, g.tokens, 1e-6f, stream);
+                                  bias + (static_cast<size_t>(2 * l) * B + b0) * D, M, D, g.tokens, 1e-6f, F16, stream);
       if (rc) return rc;
       {
         GemmParams p = base_params(M, 2 * Dff, D);
         p.out0 = hbuf;
         p.ldo = Dff;
         const auto* w1 = static_cast<const __nv_bfloat16*>(m->w_1) + static_cast<size_t>(l) * 2 * Dff * D;
-        rc = launch_gemm(EPI_SWIGLU, kDefaultCG, xb, D, w1, D, p, stream);
+        rc = launch_gemm(EPI_SWIGLU, kDefaultCG, F16, xb, D, w1, D, p, stream);
         if (rc) return rc;
       }
       {
@@ -214,7 +215,7 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
         p.out0 = branch;
         p.ldo = D;
         const auto* w2 = static_cast<const __nv_bfloat16*>(m->w_2) + static_cast<size_t>(l) * D * Dff;
-        rc = launch_gemm(EPI_STORE_F32, kDefaultCG, hbuf, Dff, w2, Dff, p, stream);
+        rc = launch_gemm(EPI_STORE_F32, kDefaultCG, F16, hbuf, Dff, w2, Dff, p, stream);
         if (rc) return rc;
       }
       const bool last = (l == m->depth - 1);
@@ -223,7 +224,7 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
       const int ldxb = last ? g.k_head_total : D;
       void* xlo = (last && m->split_head) ? static_cast<void*>(static_cast<__nv_bfloat16*>(hbuf) + D) : nullptr;
       rc = launch_ln_mod_residual(branch, x, xb_dst, ldxb, xlo, gain + (static_cast<size_t>(2 * l + 1) * B + b0) * D,
-                                  bias + (static_cast<size_t>(2 * l + 1) * B + b0) * D, M, D, g.tokens, 1e-6f, stream);
+                                  bias + (static_cast<size_t>(2 * l + 1) * B + b0) * D, M, D, g.tokens, 1e-6f, F16, stream);
       if (rc) return rc;
     }
     // 4. head GEMM + pixel shuffle + sampler update
@@ -241,18 +242,18 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
 
 // ------------------------------------------------------------------------------------------------ single kernels
 
-SWB200_API int swb200_gemm(int epi, int cta_group, const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M,
-                int N, int K, void* stream) {
-  SWB_REQUIRE(epi == EPI_STORE_F32 || epi == EPI_STORE_BF16, "swb200_gemm: epi must be 0 (fp32) or 1 (bf16)");
+SWB200_API int swb200_gemm(int epi, int cta_group, int act_fp16, const void* A, int lda, const void* W, int ldw, void* out,
+                int ldo, int M, int N, int K, void* stream) {
+  SWB_REQUIRE(epi == EPI_STORE_F32 || epi == EPI_STORE_ACT, "swb200_gemm: epi must be 0 (fp32) or 1 (activation format)");
   SWB_REQUIRE(A && W && out, "swb200_gemm: NULL pointer");
   SWB_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "swb200_gemm: out must be 16-byte aligned");
   GemmParams p = base_params(M, N, K);
   p.out0 = out;
   p.ldo = ldo;
-  return launch_gemm(epi, cta_group, A, lda, W, ldw, p, static_cast<cudaStream_t>(stream));
+  return launch_gemm(epi, cta_group, act_fp16, A, lda, W, ldw, p, static_cast<cudaStream_t>(stream));
 }
 
-SWB200_API int swb200_gemm_qkv(int cta_group, const void* A, int lda, const void* W, const float* qscale, void* out, int M,
+SWB200_API int swb200_gemm_qkv(int cta_group, int act_fp16, const void* A, int lda, const void* W, const float* qscale, void* out, int M,
                     int dim, int heads, void* stream) {
   SWB_REQUIRE(A && W && qscale && out, "swb200_gemm_qkv: NULL pointer");
   SWB_REQUIRE(dim == heads * kHeadDim, "swb200_gemm_qkv: need head_dim 88 (dim=%d heads=%d)", dim, heads);
@@ -261,20 +262,20 @@ SWB200_API int swb200_gemm_qkv(int cta_group, const void* A, int lda, const void
   p.qscale = qscale;
   p.heads = heads;
   p.dmodel = dim;
-  return launch_gemm(EPI_QKV, cta_group, A, lda, W, dim, p, static_cast<cudaStream_t>(stream));
+  return launch_gemm(EPI_QKV, cta_group, act_fp16, A, lda, W, dim, p, static_cast<cudaStream_t>(stream));
 }
 
-SWB200_API int swb200_gemm_swiglu(int cta_group, const void* A, int lda, const void* W, void* out, int M, int dim, int dff,
+SWB200_API int swb200_gemm_swiglu(int cta_group, int act_fp16, const void* A, int lda, const void* W, void* out, int M, int dim, int dff,
                        void* stream) {
   SWB_REQUIRE(A && W && out, "swb200_gemm_swiglu: NULL pointer");
   SWB_REQUIRE(dff % kHeadDim == 0, "swb200_gemm_swiglu: dff must be a multiple of 88");
   GemmParams p = base_params(M, 2 * dff, dim);
   p.out0 = out;
   p.ldo = dff;
-  return launch_gemm(EPI_SWIGLU, cta_group, A, lda, W, dim, p, static_cast<cudaStream_t>(stream));
+  return launch_gemm(EPI_SWIGLU, cta_group, act_fp16, A, lda, W, dim, p, static_cast<cudaStream_t>(stream));
 }
 
-SWB200_API int swb200_gemm_embed(int cta_group, const void* A, int lda, const void* W, int K, const float* bias,
+SWB200_API int swb200_gemm_embed(int cta_group, int act_fp16, const void* A, int lda, const void* W, int K, const float* bias,
                       const float* pos, int tokens, float* x, void* xb, int M, int dim, void* stream) {
   SWB_REQUIRE(A && W && bias && pos && x && xb, "swb200_gemm_embed: NULL pointer");
   GemmParams p = base_params(M, dim, K);
@@ -284,7 +285,7 @@ SWB200_API int swb200_gemm_embed(int cta_group, const void* A, int lda, const vo
   p.bias = bias;
   p.pos = pos;
   p.pos_rows = tokens;
-  return launch_gemm(EPI_EMBED, cta_group, A, lda, W, K, p, static_cast<cudaStream_t>(stream));
+  return launch_gemm(EPI_EMBED, cta_group, act_fp16, A, lda, W, K, p, static_cast<cudaStream_t>(stream));
 }
 
 SWB200_API int swb200_gemm_head(int cta_group, const swb200_model* m, const void* A, int lda, int K, int B,
@@ -306,28 +307,28 @@ SWB200_API int swb200_gemm_head(int cta_group, const swb200_model* m, const void
   p.p2 = m->patch_w;
   p.gw = g.gw;
   p.tokens = g.tokens;
-  return launch_gemm(EPI_HEAD, cta_group, A, lda, m->w_head, K, p, static_cast<cudaStream_t>(stream));
+  return launch_gemm(EPI_HEAD, cta_group, m->act_fp16 ? 1 : 0, A, lda, m->w_head, K, p, static_cast<cudaStream_t>(stream));
 }
 
 SWB200_API int swb200_patch_gather(const swb200_model* m, const float* x0, int c0, float scale0, const float* x1, int c1, int B,
                         void* A, int lda, void* stream) {
   SWB_REQUIRE(m && x0 && A, "swb200_patch_gather: NULL pointer");
   SWB_REQUIRE(c0 + c1 == m->in_channels, "swb200_patch_gather: c0+c1 != in_channels");
-  return launch_patch_gather(x0, c0, scale0, x1, c1, A, lda, m->k_embed, m->split_embed, B, m->img_h, m->img_w,
+  return launch_patch_gather(x0, c0, scale0, x1, c1, A, lda, m->k_embed, m->split_embed, m->act_fp16 ? 1 : 0, B, m->img_h, m->img_w,
                              m->patch_h, m->patch_w, static_cast<cudaStream_t>(stream));
 }
 
 SWB200_API int swb200_ln_mod_residual(const float* branch, float* x, void* xb, int ldxb, void* xlo, const float* gain,
-                           const float* bias, int M, int dim, int tokens, void* stream) {
+                           const float* bias, int M, int dim, int tokens, int act_fp16, void* stream) {
   SWB_REQUIRE(branch && x && xb && gain && bias, "swb200_ln_mod_residual: NULL pointer");
-  return launch_ln_mod_residual(branch, x, xb, ldxb, xlo, gain, bias, M, dim, tokens, 1e-6f,
+  return launch_ln_mod_residual(branch, x, xb, ldxb, xlo, gain, bias, M, dim, tokens, 1e-6f, act_fp16,
                                 static_cast<cudaStream_t>(stream));
 }
 
 SWB200_API int swb200_window_attention(const void* qkv, void* out, int B, int grid_h, int grid_w, int heads, int shift_h,
-                            int shift_w, void* stream) {
+                            int shift_w, int act_fp16, void* stream) {
   SWB_REQUIRE(qkv && out, "swb200_window_attention: NULL pointer");
-  return launch_window_attention(qkv, out, B, grid_h, grid_w, heads, shift_h, shift_w,
+  return launch_window_attention(qkv, out, B, grid_h, grid_w, heads, shift_h, shift_w, act_fp16,
                                  static_cast<cudaStream_t>(stream));
 }
 

@@ -15,6 +15,7 @@
 #include "kernels.h"
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace swb {
 
@@ -38,18 +39,33 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint3
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
                : "r"(addr));
 }
-__device__ __forceinline__ void mma_bf16_16816(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, "
-      "%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+template <bool F16>
+__device__ __forceinline__ void mma_16816(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  if constexpr (F16)
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, "
+        "%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, "
+        "%2, %3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
+template <bool F16>
+__device__ __forceinline__ uint32_t pack2_act(float lo, float hi) {
+  if constexpr (F16) {
+    __half2 v = __floats2half2_rn(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
+    return *reinterpret_cast<uint32_t*>(&v);
+  } else {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(att::kThreads, 1)
 window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int M, int gh, int gw,
                         int heads, int shift_h, int shift_w) {
@@ -120,8 +136,8 @@ window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
       for (int kt = 0; kt < 6; kt += 2) {
         uint32_t b0, b1, b2, b3;
         ldsm_x4(sK_u + (key * kPitch + kt * 16 + c) * 2, b0, b1, b2, b3);
-        mma_bf16_16816(s[nt], qf[kt], b0, b1);
-        mma_bf16_16816(s[nt], qf[kt + 1], b2, b3);
+        mma_16816<F16>(s[nt], qf[kt], b0, b1);
+        mma_16816<F16>(s[nt], qf[kt + 1], b2, b3);
       }
     }
     // online softmax (logits already carry the learned scale; softmax scale = 1)
@@ -162,18 +178,18 @@ window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       uint32_t pf[4];
-      pf[0] = pack2_bf16(s[2 * kk][0], s[2 * kk][1]);
-      pf[1] = pack2_bf16(s[2 * kk][2], s[2 * kk][3]);
-      pf[2] = pack2_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-      pf[3] = pack2_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+      pf[0] = pack2_act<F16>(s[2 * kk][0], s[2 * kk][1]);
+      pf[1] = pack2_act<F16>(s[2 * kk][2], s[2 * kk][3]);
+      pf[2] = pack2_act<F16>(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pf[3] = pack2_act<F16>(s[2 * kk + 1][2], s[2 * kk + 1][3]);
       const int key = kc + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
       const int c = (lane >> 4) * 8;
 #pragma unroll
       for (int np = 0; np < 6; ++np) {
         uint32_t b0, b1, b2, b3;
         ldsm_x4_trans(sV_u + (key * kPitch + np * 16 + c) * 2, b0, b1, b2, b3);
-        mma_bf16_16816(o[2 * np], pf, b0, b1);
-        mma_bf16_16816(o[2 * np + 1], pf, b2, b3);
+        mma_16816<F16>(o[2 * np], pf, b0, b1);
+        mma_16816<F16>(o[2 * np + 1], pf, b2, b3);
       }
     }
   }
@@ -189,8 +205,8 @@ window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
 #pragma unroll
   for (int nt = 0; nt < 11; ++nt) {
     const int c = nt * 8 + 2 * t4;
-    *reinterpret_cast<uint32_t*>(sQ + (q0 + g) * kPitch + c) = pack2_bf16(o[nt][0] * inv0, o[nt][1] * inv0);
-    *reinterpret_cast<uint32_t*>(sQ + (q0 + g + 8) * kPitch + c) = pack2_bf16(o[nt][2] * inv1, o[nt][3] * inv1);
+    *reinterpret_cast<uint32_t*>(sQ + (q0 + g) * kPitch + c) = pack2_act<F16>(o[nt][0] * inv0, o[nt][1] * inv0);
+    *reinterpret_cast<uint32_t*>(sQ + (q0 + g + 8) * kPitch + c) = pack2_act<F16>(o[nt][2] * inv1, o[nt][3] * inv1);
   }
   __syncwarp();
   const int dmodel = heads * kHd;
@@ -202,21 +218,26 @@ window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
 }
 
 int launch_window_attention(const void* qkv, void* out, int B, int gh, int gw, int heads, int shift_h, int shift_w,
-                            cudaStream_t stream) {
+                            int act_f16, cudaStream_t stream) {
   using namespace att;
   SWB_REQUIRE(gh % kWin == 0 && gw % kWin == 0, "window_attention: token grid %dx%d not divisible by 16x16 windows",
               gh, gw);
   static bool attr_done = false;
   if (!attr_done) {
-    SWB_CHECK_CUDA(cudaFuncSetAttribute(window_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SWB_CHECK_CUDA(cudaFuncSetAttribute(window_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kSmemBytes));
+    SWB_CHECK_CUDA(cudaFuncSetAttribute(window_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         kSmemBytes));
     attr_done = true;
   }
   const int M = B * gh * gw;
   dim3 grid((gh / kWin) * (gw / kWin), heads, B);
-  window_attention_kernel<<<grid, kThreads, kSmemBytes, stream>>>(static_cast<const __nv_bfloat16*>(qkv),
-                                                                 static_cast<__nv_bfloat16*>(out), M, gh, gw, heads,
-                                                                 shift_h, shift_w);
+  auto q_ = static_cast<const __nv_bfloat16*>(qkv);
+  auto o_ = static_cast<__nv_bfloat16*>(out);
+  if (act_f16)
+    window_attention_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(q_, o_, M, gh, gw, heads, shift_h, shift_w);
+  else
+    window_attention_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(q_, o_, M, gh, gw, heads, shift_h, shift_w);
   SWB_CHECK_CUDA(cudaGetLastError());
   return SWB_OK;
 }

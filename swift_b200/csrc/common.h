@@ -35,15 +35,15 @@ constexpr int SWB_ERR_DRIVER = -3;      // driver entry point or tensor-map enco
 
 int num_sms();
 
-// bf16 row-major [rows, cols] -> 2-D TMA descriptor with a [box_rows x 64] SWIZZLE_128B box
-int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
-                      uint32_t box_cols);
-int make_tmap_bf16_2d_pitch(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
-                            uint32_t box_rows, uint32_t box_cols);
+// 16-bit (fp16 / bf16) row-major [rows, cols] with row pitch `pitch_elems` -> 2-D TMA descriptor with a
+// [box_rows x box_cols] SWIZZLE_128B box (box_cols * 2 bytes must be 128)
+int make_tmap_16bit_2d(CUtensorMap* out, const void* ptr, bool is_f16, uint64_t rows, uint64_t cols,
+                       uint64_t pitch_elems, uint32_t box_rows, uint32_t box_cols);
 
 struct GemmParams;
-// D = A[M,K] * W[N,K]^T with a fused epilogue (gemm_sm100.cuh); cta_group 2 = paired-CTA UMMA (M=256 tiles)
-int launch_gemm(int epi, int cta_group, const void* A, int lda, const void* W, int ldw, const GemmParams& p,
-                cudaStream_t stream);
+// D = A[M,K] * W[N,K]^T with a fused epilogue (gemm_sm100.cuh); cta_group 2 = paired-CTA UMMA (M=256 tiles);
+// act_f16: activations (A and 16-bit outputs) are fp16 instead of bf16.  W is always bf16.
+int launch_gemm(int epi, int cta_group, int act_f16, const void* A, int lda, const void* W, int ldw,
+                const GemmParams& p, cudaStream_t stream);
 
 }  // namespace swb

@@ -3,6 +3,7 @@
 // (sinusoidal embedding, fp32 GEMVs, modulation folding).
 #include "common.h"
 #include "kernels.h"
+#include "ptx.cuh"
 
 #include <cuda_bf16.h>
 
@@ -18,10 +19,10 @@ namespace swb {
 // [hi | lo] * [W | W]^T reproduces the fp32 input to ~2^-17 relative instead of 2^-9.
 constexpr int kGatherCh = 8;
 
-template <bool SPLIT>
+template <bool SPLIT, bool F16>
 __global__ void __launch_bounds__(256) patch_gather_kernel(const float* __restrict__ src0, int C0, float scale0,
                                                            const float* __restrict__ src1, int C1,
-                                                           __nv_bfloat16* __restrict__ A, int lda, int Kp, int H,
+                                                           uint16_t* __restrict__ A, int lda, int Kp, int H,
                                                            int W, int p1, int p2) {
   extern __shared__ float tile[];   // [kGatherCh * p1][W + 2]
   const int gy = blockIdx.x, b = blockIdx.y;
@@ -55,28 +56,31 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const float* __restri
       const int k = (c0 + c) * pp + r;
       if (k < Kp) {
         const float v = tile[(c * p1 + py) * pitch + gx * p2 + px];
-        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-        __nv_bfloat16* dst = A + (row_base + gx) * lda + k;
+        const uint16_t hi = pack_act1<F16>(v);
+        uint16_t* dst = A + (row_base + gx) * lda + k;
         *dst = hi;
-        if (SPLIT) dst[Kp] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        if (SPLIT) dst[Kp] = pack_act1<F16>(v - unpack_act1<F16>(hi));
       }
     }
   }
 }
 
 int launch_patch_gather(const float* src0, int C0, float scale0, const float* src1, int C1, void* A, int lda, int Kp,
-                        int split, int B, int H, int W, int p1, int p2, cudaStream_t stream) {
+                        int split, int act_f16, int B, int H, int W, int p1, int p2, cudaStream_t stream) {
   SWB_REQUIRE(H % p1 == 0 && W % p2 == 0, "patch_gather: image %dx%d not divisible by patch %dx%d", H, W, p1, p2);
   SWB_REQUIRE(Kp >= (C0 + C1) * p1 * p2, "patch_gather: Kp=%d < C*p1*p2=%d", Kp, (C0 + C1) * p1 * p2);
   const size_t smem = static_cast<size_t>(kGatherCh) * p1 * (W + 2) * sizeof(float);
   SWB_REQUIRE(smem <= 48 * 1024, "patch_gather: image width %d too large for the staging tile", W);
   dim3 grid(H / p1, B);
-  if (split)
-    patch_gather_kernel<true><<<grid, 256, smem, stream>>>(src0, C0, scale0, src1, C1,
-                                                           static_cast<__nv_bfloat16*>(A), lda, Kp, H, W, p1, p2);
-  else
-    patch_gather_kernel<false><<<grid, 256, smem, stream>>>(src0, C0, scale0, src1, C1,
-                                                            static_cast<__nv_bfloat16*>(A), lda, Kp, H, W, p1, p2);
+  uint16_t* A_ = static_cast<uint16_t*>(A);
+#define SWB_GATHER(SP, F) \
+  patch_gather_kernel<SP, F><<<grid, 256, smem, stream>>>(src0, C0, scale0, src1, C1, A_, lda, Kp, H, W, p1, p2)
+  if (split) {
+    if (act_f16) SWB_GATHER(true, true); else SWB_GATHER(true, false);
+  } else {
+    if (act_f16) SWB_GATHER(false, true); else SWB_GATHER(false, false);
+  }
+#undef SWB_GATHER
   SWB_CHECK_CUDA(cudaGetLastError());
   return SWB_OK;
 }
@@ -86,77 +90,110 @@ int launch_patch_gather(const float* src0, int C0, float scale0, const float* sr
 //
 // reference: ModulatedNorm (swinv2.py:77-86) applied to the branch output, then the residual add
 // (swinv2.py:211-212).  gain = gamma*(1+scale(t)), bias = beta*(1+scale(t)) + shift(t) are folded per sample
-// by mod_finalize_kernel.  One warp per token row, the row lives in registers (two-pass mean/variance in fp32),
-// all global accesses are lane-strided so every warp request is one full 128-byte line.
-template <int VPL>
-__global__ void __launch_bounds__(256) ln_mod_residual_kernel(const float* __restrict__ branch, float* __restrict__ x,
-                                                              __nv_bfloat16* __restrict__ xb, int ldxb,
-                                                              __nv_bfloat16* __restrict__ xlo,
+// by mod_finalize_kernel.  One warp per token row; the row lives in registers (two-pass mean/variance in fp32);
+// accesses are 16-byte per lane, lane-strided (512 contiguous bytes per warp request).
+template <int NV4, bool F16>
+__global__ void __launch_bounds__(128) ln_mod_residual_kernel(const float* __restrict__ branch, float* __restrict__ x,
+                                                              uint16_t* __restrict__ xb, int ldxb,
+                                                              uint16_t* __restrict__ xlo,
                                                               const float* __restrict__ gain,
                                                               const float* __restrict__ bias, int M, int D,
                                                               int tokens, float eps) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
-  const float* br = branch + static_cast<size_t>(row) * D;
-  float v[VPL];
+  const int nv = D >> 2;                                   // float4 per row
+  const float4* br = reinterpret_cast<const float4*>(branch + static_cast<size_t>(row) * D);
+  float4* xr = reinterpret_cast<float4*>(x + static_cast<size_t>(row) * D);
+  // every global load of the row (branch AND residual) is issued before the first use: 2*NV4 independent
+  // 512-byte warp requests in flight per warp
+  float4 v[NV4], xv[NV4];
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    const int c = i * 32 + lane;
+    v[i] = (c < nv) ? __ldg(br + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    const int c = i * 32 + lane;
+    xv[i] = (c < nv) ? xr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int c = i * 32 + lane;
-    v[i] = (c < D) ? __ldg(br + c) : 0.f;
-    sum += v[i];
-  }
+  for (int i = 0; i < NV4; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float mean = sum / static_cast<float>(D);
   float var = 0.f;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int c = i * 32 + lane;
-    const float d = (c < D) ? v[i] - mean : 0.f;
-    var = fmaf(d, d, var);
+  for (int i = 0; i < NV4; ++i) {
+    if (i * 32 + lane < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c2 = v[i].z - mean, d = v[i].w - mean;
+      var += (a * a + b * b) + (c2 * c2 + d * d);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
   const float rstd = rsqrtf(var / static_cast<float>(D) + eps);
   const int b = row / tokens;
-  const float* g = gain + static_cast<size_t>(b) * D;
-  const float* bs = bias + static_cast<size_t>(b) * D;
-  float* xr = x + static_cast<size_t>(row) * D;
-  __nv_bfloat16* xbr = xb + static_cast<size_t>(row) * ldxb;
+  const float4* g4 = reinterpret_cast<const float4*>(gain + static_cast<size_t>(b) * D);
+  const float4* b4 = reinterpret_cast<const float4*>(bias + static_cast<size_t>(b) * D);
+  uint2* xbr = reinterpret_cast<uint2*>(xb + static_cast<size_t>(row) * ldxb);
+  uint2* xlr = xlo ? reinterpret_cast<uint2*>(xlo + static_cast<size_t>(row) * ldxb) : nullptr;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
+  for (int i = 0; i < NV4; ++i) {
     const int c = i * 32 + lane;
-    if (c < D) {
-      const float y = fmaf((v[i] - mean) * rstd, __ldg(g + c), __ldg(bs + c));
-      const float xn = xr[c] + y;
-      xr[c] = xn;
-      const __nv_bfloat16 hi = __float2bfloat16_rn(xn);
-      xbr[c] = hi;
-      if (xlo) xlo[static_cast<size_t>(row) * ldxb + c] = __float2bfloat16_rn(xn - __bfloat162float(hi));
+    if (c < nv) {
+      const float4 g = __ldg(g4 + c), bb = __ldg(b4 + c);
+      float4 o;
+      o.x = xv[i].x + fmaf((v[i].x - mean) * rstd, g.x, bb.x);
+      o.y = xv[i].y + fmaf((v[i].y - mean) * rstd, g.y, bb.y);
+      o.z = xv[i].z + fmaf((v[i].z - mean) * rstd, g.z, bb.z);
+      o.w = xv[i].w + fmaf((v[i].w - mean) * rstd, g.w, bb.w);
+      xr[c] = o;
+      const uint32_t h0 = pack_act2<F16>(o.x, o.y), h1 = pack_act2<F16>(o.z, o.w);
+      xbr[c] = make_uint2(h0, h1);
+      if (xlr) {
+        const float l0 = o.x - unpack_act1<F16>(static_cast<uint16_t>(h0 & 0xffffu));
+        const float l1 = o.y - unpack_act1<F16>(static_cast<uint16_t>(h0 >> 16));
+        const float l2 = o.z - unpack_act1<F16>(static_cast<uint16_t>(h1 & 0xffffu));
+        const float l3 = o.w - unpack_act1<F16>(static_cast<uint16_t>(h1 >> 16));
+        xlr[c] = make_uint2(pack_act2<F16>(l0, l1), pack_act2<F16>(l2, l3));
+      }
     }
   }
 }
 
 int launch_ln_mod_residual(const float* branch, float* x, void* xb, int ldxb, void* xlo, const float* gain,
-                           const float* bias, int M, int D, int tokens, float eps, cudaStream_t stream) {
-  const int rows_per_block = 8;
+                           const float* bias, int M, int D, int tokens, float eps, int act_f16, cudaStream_t stream) {
+  SWB_REQUIRE(D % 4 == 0 && ldxb % 4 == 0, "ln_mod_residual: dim %d and pitch %d must be multiples of 4", D, ldxb);
+  SWB_REQUIRE(((reinterpret_cast<uintptr_t>(branch) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gain) |
+                reinterpret_cast<uintptr_t>(bias)) & 15) == 0 &&
+                  ((reinterpret_cast<uintptr_t>(xb) | reinterpret_cast<uintptr_t>(xlo)) & 7) == 0,
+              "ln_mod_residual: pointers must be 16-byte (fp32) / 8-byte (16-bit) aligned");
+  const int rows_per_block = 4;
   dim3 grid((M + rows_per_block - 1) / rows_per_block);
-  auto xb_ = static_cast<__nv_bfloat16*>(xb);
-  auto xlo_ = static_cast<__nv_bfloat16*>(xlo);
-  if (D <= 32 * 9)
-    ln_mod_residual_kernel<9><<<grid, 256, 0, stream>>>(branch, x, xb_, ldxb, xlo_, gain, bias, M, D, tokens, eps);
-  else if (D <= 32 * 17)
-    ln_mod_residual_kernel<17><<<grid, 256, 0, stream>>>(branch, x, xb_, ldxb, xlo_, gain, bias, M, D, tokens, eps);
-  else if (D <= 32 * 33)
-    ln_mod_residual_kernel<33><<<grid, 256, 0, stream>>>(branch, x, xb_, ldxb, xlo_, gain, bias, M, D, tokens, eps);
-  else if (D <= 32 * 64)
-    ln_mod_residual_kernel<64><<<grid, 256, 0, stream>>>(branch, x, xb_, ldxb, xlo_, gain, bias, M, D, tokens, eps);
+  auto xb_ = static_cast<uint16_t*>(xb);
+  auto xlo_ = static_cast<uint16_t*>(xlo);
+#define SWB_LN(V)                                                                                                  \
+  do {                                                                                                             \
+    if (act_f16)                                                                                                   \
+      ln_mod_residual_kernel<V, true><<<grid, 128, 0, stream>>>(branch, x, xb_, ldxb, xlo_, gain, bias, M, D, tokens, \
+                                                                eps);                                              \
+    else                                                                                                           \
+      ln_mod_residual_kernel<V, false><<<grid, 128, 0, stream>>>(branch, x, xb_, ldxb, xlo_, gain, bias, M, D,      \
+                                                                 tokens, eps);                                     \
+  } while (0)
+  const int nv4 = (D / 4 + 31) / 32;
+  if (nv4 <= 3) SWB_LN(3);
+  else if (nv4 <= 5) SWB_LN(5);
+  else if (nv4 <= 9) SWB_LN(9);
+  else if (nv4 <= 16) SWB_LN(16);
   else {
     set_error("ln_mod_residual: dim %d > 2048 unsupported", D);
     return SWB_ERR_INVALID;
   }
+#undef SWB_LN
   SWB_CHECK_CUDA(cudaGetLastError());
   return SWB_OK;
 }

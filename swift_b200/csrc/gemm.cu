@@ -46,13 +46,8 @@ static PFN_tmapEncodeTiled get_encode_fn() {
   return fn;
 }
 
-int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
-                      uint32_t box_cols) {
-  return make_tmap_bf16_2d_pitch(out, ptr, rows, cols, cols, box_rows, box_cols);
-}
-
-int make_tmap_bf16_2d_pitch(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
-                            uint32_t box_rows, uint32_t box_cols) {
+int make_tmap_16bit_2d(CUtensorMap* out, const void* ptr, bool is_f16, uint64_t rows, uint64_t cols,
+                       uint64_t pitch_elems, uint32_t box_rows, uint32_t box_cols) {
   PFN_tmapEncodeTiled fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled driver entry point not available");
@@ -67,7 +62,7 @@ int make_tmap_bf16_2d_pitch(CUtensorMap* out, const void* ptr, uint64_t rows, ui
   cuuint64_t gstride[1] = {pitch_elems * 2};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+  CUresult r = fn(out, is_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -79,10 +74,10 @@ int make_tmap_bf16_2d_pitch(CUtensorMap* out, const void* ptr, uint64_t rows, ui
 }
 
 // ----------------------------------------------------------------------------- launch
-template <int BN, int CG, int EPI>
+template <int BN, int CG, int EPI, bool F16>
 static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using S = GemmSmem<BN, CG>;
-  auto kern = gemm_tcgen05_kernel<BN, CG, EPI>;
+  auto kern = gemm_tcgen05_kernel<BN, CG, EPI, F16>;
   static bool attr_done = false;
   if (!attr_done) {
     SWB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
@@ -109,36 +104,37 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   return SWB_OK;
 }
 
-template <int BN, int CG>
+template <int BN, int CG, bool F16>
 static int launch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                       cudaStream_t stream) {
   switch (epi) {
-    case EPI_STORE_F32: return launch_inst<BN, CG, EPI_STORE_F32>(ta, tb, p, stream);
-    case EPI_STORE_BF16: return launch_inst<BN, CG, EPI_STORE_BF16>(ta, tb, p, stream);
-    case EPI_EMBED: return launch_inst<BN, CG, EPI_EMBED>(ta, tb, p, stream);
-    case EPI_QKV: return launch_inst<BN, CG, EPI_QKV>(ta, tb, p, stream);
-    case EPI_SWIGLU: return launch_inst<BN, CG, EPI_SWIGLU>(ta, tb, p, stream);
-    case EPI_HEAD: return launch_inst<BN, CG, EPI_HEAD>(ta, tb, p, stream);
+    case EPI_STORE_F32: return launch_inst<BN, CG, EPI_STORE_F32, F16>(ta, tb, p, stream);
+    case EPI_STORE_ACT: return launch_inst<BN, CG, EPI_STORE_ACT, F16>(ta, tb, p, stream);
+    case EPI_EMBED: return launch_inst<BN, CG, EPI_EMBED, F16>(ta, tb, p, stream);
+    case EPI_QKV: return launch_inst<BN, CG, EPI_QKV, F16>(ta, tb, p, stream);
+    case EPI_SWIGLU: return launch_inst<BN, CG, EPI_SWIGLU, F16>(ta, tb, p, stream);
+    case EPI_HEAD: return launch_inst<BN, CG, EPI_HEAD, F16>(ta, tb, p, stream);
   }
   set_error("unknown GEMM epilogue %d", epi);
   return SWB_ERR_INVALID;
 }
 
-// A: bf16 [M, K] with row pitch lda; W: bf16 [N, K] with row pitch ldw (nn.Linear layout).
-int launch_gemm(int epi, int cta_group, const void* A, int lda, const void* W, int ldw, const GemmParams& p,
-                cudaStream_t stream) {
+// A: fp16/bf16 [M, K] with row pitch lda; W: bf16 [N, K] with row pitch ldw (nn.Linear layout).
+int launch_gemm(int epi, int cta_group, int act_f16, const void* A, int lda, const void* W, int ldw,
+                const GemmParams& p, cudaStream_t stream) {
   SWB_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
   SWB_REQUIRE(p.K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm: K and row pitches must be multiples of 8 (K=%d)",
               p.K);
   SWB_REQUIRE(cta_group == 1 || cta_group == 2, "gemm: cta_group must be 1 or 2");
   constexpr int BN = 176;
   CUtensorMap ta, tb;
-  int rc = make_tmap_bf16_2d_pitch(&ta, A, p.M, p.K, lda, kBlockM, kBlockK);
+  int rc = make_tmap_16bit_2d(&ta, A, act_f16 != 0, p.M, p.K, lda, kBlockM, kBlockK);
   if (rc) return rc;
-  rc = make_tmap_bf16_2d_pitch(&tb, W, p.N, p.K, ldw, BN / cta_group, kBlockK);
+  rc = make_tmap_16bit_2d(&tb, W, false, p.N, p.K, ldw, BN / cta_group, kBlockK);
   if (rc) return rc;
-  if (cta_group == 2) return launch_epi<BN, 2>(epi, ta, tb, p, stream);
-  return launch_epi<BN, 1>(epi, ta, tb, p, stream);
+  if (cta_group == 2)
+    return act_f16 ? launch_epi<BN, 2, true>(epi, ta, tb, p, stream) : launch_epi<BN, 2, false>(epi, ta, tb, p, stream);
+  return act_f16 ? launch_epi<BN, 1, true>(epi, ta, tb, p, stream) : launch_epi<BN, 1, false>(epi, ta, tb, p, stream);
 }
 
 }  // namespace swb

@@ -1,4 +1,4 @@
-// Persistent, warp-specialised tcgen05 GEMM for sm_100a:  D[M,N] = A[M,K] * W[N,K]^T  (bf16 in, fp32 accumulate in TMEM)
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a:  D[M,N] = A[M,K] * W[N,K]^T  (A fp16 or bf16, W bf16, fp32 accumulate in TMEM)
 // with the epilogues the Swift denoiser needs fused in.  A and W are both K-major (row-major [rows, K]), which is
 // how activations and nn.Linear weights are stored, so neither is ever transposed in memory.
 //
@@ -20,7 +20,7 @@ namespace swb {
 
 enum GemmEpilogue : int {
   EPI_STORE_F32 = 0,   // out0[M, ldo] fp32
-  EPI_STORE_BF16 = 1,  // out0[M, ldo] bf16
+  EPI_STORE_ACT = 1,   // out0[M, ldo] in the activation format (bf16 / fp16)
   EPI_EMBED = 2,       // x = acc + bias[n] + pos[row % pos_rows, n];  out0 = x (fp32), out1 = bf16(x)
   EPI_QKV = 3,         // scaled-cosine q/k normalisation fused; out0 = [3][heads][M][HD_PAD] bf16
   EPI_SWIGLU = 4,      // tile = [gate(BN/2) | up(BN/2)];  out0[M, N/2] bf16 = silu(gate) * up
@@ -85,10 +85,10 @@ __device__ __forceinline__ void tmem_load_cols(uint32_t taddr, float* v) {
   tmem_ld_fence_regs<NCOL>(v);
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool F16>
 __device__ __forceinline__ void gemm_epilogue_row(const GemmParams& p, uint32_t tacc, int row, int n0) {
   const bool row_ok = row < p.M;
-  if constexpr (EPI == EPI_STORE_F32 || EPI == EPI_STORE_BF16 || EPI == EPI_EMBED) {
+  if constexpr (EPI == EPI_STORE_F32 || EPI == EPI_STORE_ACT || EPI == EPI_EMBED) {
 #pragma unroll 1
     for (int c = 0; c < BN; c += 16) {
       float v[16];
@@ -103,27 +103,27 @@ __device__ __forceinline__ void gemm_epilogue_row(const GemmParams& p, uint32_t 
       }
       const size_t off = static_cast<size_t>(row) * p.ldo + n;
       if (n + 16 <= p.N) {
-        if constexpr (EPI != EPI_STORE_BF16) {
+        if constexpr (EPI != EPI_STORE_ACT) {
           float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out0) + off);
 #pragma unroll
           for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
         if constexpr (EPI != EPI_STORE_F32) {
           void* dst = (EPI == EPI_EMBED) ? p.out1 : p.out0;
-          uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(dst) + off);
-          o[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                            pack_bf16x2(v[6], v[7]));
-          o[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
-                            pack_bf16x2(v[14], v[15]));
+          uint4* o = reinterpret_cast<uint4*>(static_cast<uint16_t*>(dst) + off);
+          o[0] = make_uint4(pack_act2<F16>(v[0], v[1]), pack_act2<F16>(v[2], v[3]), pack_act2<F16>(v[4], v[5]),
+                            pack_act2<F16>(v[6], v[7]));
+          o[1] = make_uint4(pack_act2<F16>(v[8], v[9]), pack_act2<F16>(v[10], v[11]), pack_act2<F16>(v[12], v[13]),
+                            pack_act2<F16>(v[14], v[15]));
         }
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           if (n + j < p.N) {
-            if constexpr (EPI != EPI_STORE_BF16) static_cast<float*>(p.out0)[off + j] = v[j];
+            if constexpr (EPI != EPI_STORE_ACT) static_cast<float*>(p.out0)[off + j] = v[j];
             if constexpr (EPI != EPI_STORE_F32) {
               void* dst = (EPI == EPI_EMBED) ? p.out1 : p.out0;
-              static_cast<__nv_bfloat16*>(dst)[off + j] = __float2bfloat16_rn(v[j]);
+              static_cast<uint16_t*>(dst)[off + j] = pack_act1<F16>(v[j]);
             }
           }
         }
@@ -152,13 +152,13 @@ __device__ __forceinline__ void gemm_epilogue_row(const GemmParams& p, uint32_t 
 #pragma unroll
         for (int j = 0; j < kHeadDim; ++j) v[j] *= inv;
       }
-      __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out0) +
+      uint16_t* dst = static_cast<uint16_t*>(p.out0) +
                            (static_cast<size_t>(part * p.heads + head) * p.M + row) * kHeadDimPad;
       uint4* o = reinterpret_cast<uint4*>(dst);
 #pragma unroll
       for (int j = 0; j < kHeadDim / 8; ++j)
-        o[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                          pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+        o[j] = make_uint4(pack_act2<F16>(v[8 * j], v[8 * j + 1]), pack_act2<F16>(v[8 * j + 2], v[8 * j + 3]),
+                          pack_act2<F16>(v[8 * j + 4], v[8 * j + 5]), pack_act2<F16>(v[8 * j + 6], v[8 * j + 7]));
       o[kHeadDim / 8] = make_uint4(0u, 0u, 0u, 0u);   // zero pad 88..95
     }
   } else if constexpr (EPI == EPI_SWIGLU) {
@@ -166,7 +166,7 @@ __device__ __forceinline__ void gemm_epilogue_row(const GemmParams& p, uint32_t 
     static_assert(BN == 2 * kHeadDim, "EPI_SWIGLU needs a 176-column tile");
     constexpr int HB = BN / 2;
     const int o0 = (n0 / BN) * HB;
-    __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out0) + static_cast<size_t>(row) * p.ldo + o0;
+    uint16_t* dst = static_cast<uint16_t*>(p.out0) + static_cast<size_t>(row) * p.ldo + o0;
 #pragma unroll 1
     for (int c = 0; c < HB; c += 16) {
       float g[16], u[16];
@@ -182,7 +182,7 @@ __device__ __forceinline__ void gemm_epilogue_row(const GemmParams& p, uint32_t 
           uint32_t w[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            w[j] = pack_bf16x2(silu_f(g[2 * j]) * u[2 * j], silu_f(g[2 * j + 1]) * u[2 * j + 1]);
+            w[j] = pack_act2<F16>(silu_f(g[2 * j]) * u[2 * j], silu_f(g[2 * j + 1]) * u[2 * j + 1]);
           o[0] = make_uint4(w[0], w[1], w[2], w[3]);
           o[1] = make_uint4(w[4], w[5], w[6], w[7]);
         }
@@ -196,7 +196,7 @@ __device__ __forceinline__ void gemm_epilogue_row(const GemmParams& p, uint32_t 
           uint32_t w[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            w[j] = pack_bf16x2(silu_f(g[2 * j]) * u[2 * j], silu_f(g[2 * j + 1]) * u[2 * j + 1]);
+            w[j] = pack_act2<F16>(silu_f(g[2 * j]) * u[2 * j], silu_f(g[2 * j + 1]) * u[2 * j + 1]);
           *reinterpret_cast<uint4*>(dst + c) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
@@ -233,7 +233,7 @@ __device__ __forceinline__ void gemm_epilogue_row(const GemmParams& p, uint32_t 
 
 // ---------------------------------------------------------------------------------------------------------
 
-template <int BN, int CG, int EPI>
+template <int BN, int CG, int EPI, bool F16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const GemmParams p) {
@@ -322,7 +322,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp == 1) {
     // ===================================== UMMA issuer (leader CTA) =====================================
     if (cta_rank == 0 && lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBlockM * CG, BN);
+      constexpr uint32_t idesc = make_idesc_f16(kBlockM * CG, BN, /*A=*/F16, /*B (weights)=*/false);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -364,7 +364,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tcgen05_fence_after();
       const int row = tm * (kBlockM * CG) + static_cast<int>(cta_rank) * kBlockM + quad * 32 + lane;
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccStride;
-      gemm_epilogue_row<BN, EPI>(p, tacc, row, tn * BN);
+      gemm_epilogue_row<BN, EPI, F16>(p, tacc, row, tn * BN);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {

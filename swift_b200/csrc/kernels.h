@@ -20,19 +20,19 @@ struct CondWeights {
 };
 
 int launch_patch_gather(const float* src0, int C0, float scale0, const float* src1, int C1, void* A, int lda, int Kp,
-                        int split, int B, int H, int W, int p1, int p2, cudaStream_t stream);
+                        int split, int act_f16, int B, int H, int W, int p1, int p2, cudaStream_t stream);
 
 int launch_ln_mod_residual(const float* branch, float* x, void* xb, int ldxb, void* xlo, const float* gain,
-                           const float* bias, int M, int D, int tokens, float eps, cudaStream_t stream);
+                           const float* bias, int M, int D, int tokens, float eps, int act_f16, cudaStream_t stream);
 
 // scratch needs B*(3*D + L*2*D) floats; gain/bias are [L, B, D]
 int launch_conditioning(const CondWeights& w, const float* t, const float* aux, int B, int D, int L,
                         float timestep_weight, float* scratch, float* gain, float* bias, float* cond_out,
                         cudaStream_t stream);
 
-// Shifted-window scaled-cosine attention on the packed qkv buffer [3][heads][M][96] (bf16, q/k already
-// normalised and q scaled by the GEMM epilogue); out is bf16 [M, heads*88] in un-shifted token order.
+// Shifted-window scaled-cosine attention on the packed qkv buffer [3][heads][M][96] (fp16/bf16, q/k already
+// normalised and q scaled by the GEMM epilogue); out is [M, heads*88] in the same 16-bit format in un-shifted token order.
 int launch_window_attention(const void* qkv, void* out, int B, int gh, int gw, int heads, int shift_h, int shift_w,
-                            cudaStream_t stream);
+                            int act_f16, cudaStream_t stream);
 
 }  // namespace swb

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -147,11 +148,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 }
 constexpr uint32_t SWZ_NONE = 0, SWZ_128B = 2, SWZ_64B = 4, SWZ_32B = 6;
 
-// Instruction descriptor for kind::f16 with bf16 A/B and fp32 accumulate.
-//   [4,6) D fmt (1 = f32)  [7,10) A fmt (1 = bf16)  [10,13) B fmt  [15] A major (0 = K)  [16] B major
+// Instruction descriptor for kind::f16 (A, B each fp16 or bf16) and fp32 accumulate.
+//   [4,6) D fmt (1 = f32)  [7,10) A fmt (0 = f16, 1 = bf16)  [10,13) B fmt  [15] A major (0 = K)  [16] B major
 //   [17,23) N >> 3   [24,29) M >> 4
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, int a_mn_major = 0, int b_mn_major = 0) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, bool a_is_f16, bool b_is_f16, int a_mn_major = 0,
+                                                      int b_mn_major = 0) {
+  return (1u << 4) | ((a_is_f16 ? 0u : 1u) << 7) | ((b_is_f16 ? 0u : 1u) << 10) |
+         (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);
 }
@@ -220,6 +223,36 @@ __device__ __forceinline__ void tmem_ld_fence_regs(float* v) {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+// Activations (every GEMM A operand, q/k/v, P) are stored in one 16-bit format chosen per model:
+//   F16 = true : IEEE half (11-bit significand; saturated to +-65504 so no inf is ever produced)
+//   F16 = false: bfloat16
+// Weights are always bf16; tcgen05 kind::f16 takes the A and B formats independently in the instruction descriptor.
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
+  if constexpr (F16) {
+    lo = fminf(fmaxf(lo, -65504.f), 65504.f);
+    hi = fminf(fmaxf(hi, -65504.f), 65504.f);
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  } else {
+    return pack_bf16x2(lo, hi);
+  }
+}
+template <bool F16>
+__device__ __forceinline__ uint16_t pack_act1(float x) {
+  if constexpr (F16) {
+    __half v = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
+    return *reinterpret_cast<uint16_t*>(&v);
+  } else {
+    __nv_bfloat16 v = __float2bfloat16_rn(x);
+    return *reinterpret_cast<uint16_t*>(&v);
+  }
+}
+template <bool F16>
+__device__ __forceinline__ float unpack_act1(uint16_t u) {
+  if constexpr (F16) return __half2float(*reinterpret_cast<__half*>(&u));
+  else return __bfloat162float(*reinterpret_cast<__nv_bfloat16*>(&u));
 }
 
 }  // namespace swb

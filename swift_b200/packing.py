@@ -75,7 +75,7 @@ def check_supported(g: Geometry) -> None:
 
 
 def pack(sd: Dict[str, torch.Tensor], g: Geometry, device: torch.device, split_embed: bool = True,
-         split_head: bool = True):
+         split_head: bool = True, act_fp16: bool = True):
     """Returns (``_lib.Model`` struct, dict of device tensors that must stay alive as long as the struct is used)."""
     check_supported(g)
     bf = torch.bfloat16
@@ -144,6 +144,7 @@ def pack(sd: Dict[str, torch.Tensor], g: Geometry, device: torch.device, split_e
     m.in_channels, m.out_channels, m.depth, m.dim, m.heads = g.in_channels, g.out_channels, L, D, H
     m.dff, m.aux_dim, m.k_embed = Dff, (g.aux_dim if "aux_w" in keep else 0), g.k_embed
     m.split_embed, m.split_head = int(split_embed), int(split_head)
+    m.act_fp16 = int(act_fp16)
     m.timestep_weight = float(g.timestep_weight)
     for name in ("w_embed", "b_embed", "pos_embed", "aux_w", "aux_b", "l1_w", "l1_b", "l2_w", "l2_b", "mod_w",
                  "mod_b", "ln_gamma", "ln_beta", "qscale", "w_qkv", "w_o", "w_1", "w_2", "w_head"):

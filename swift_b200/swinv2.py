@@ -114,6 +114,7 @@ class SwinV2(_Base):
         self._engine_key = None
         self.split_embed = True      # [hi|lo] bf16 operands for the two small end GEMMs (accuracy, <1% of FLOPs)
         self.split_head = True
+        self.act_fp16 = True         # activations fp16 (weights bf16): 8x smaller rounding error than bf16, same tcgen05 rate
         self.max_chunk = 8           # samples pushed through the kernels per launch sequence
 
     def _init_weights(self):
@@ -133,14 +134,15 @@ class SwinV2(_Base):
 
     def engine(self) -> Engine:
         """The packed CUDA engine for the current parameter values (re-packed when parameters change)."""
-        key = (self._params_key(), self.split_embed, self.split_head, self.max_chunk)
+        key = (self._params_key(), self.split_embed, self.split_head, self.max_chunk, self.act_fp16)
         if self._engine is None or self._engine_key != key:
             dev = self.pos_embed.device
             if dev.type != "cuda":
                 raise RuntimeError("swift_b200.SwinV2 runs on CUDA only: move the module to a B200 with .cuda(); "
                                    "there is no CPU fallback")
             sd = {k: v for k, v in self.state_dict().items()}
-            self._engine = Engine(sd, self.geometry, dev, self.split_embed, self.split_head, self.max_chunk)
+            self._engine = Engine(sd, self.geometry, dev, self.split_embed, self.split_head, self.max_chunk,
+                                  self.act_fp16)
             self._engine_key = key
         return self._engine
 

@@ -22,7 +22,7 @@ def per_field_rel_l2(y, ref):
     return num / den          # [B, C]
 
 
-def build_net(cfg, seed=1, img_channels=None):
+def build_net(cfg, seed=1, img_channels=None, act_fp16=True):
     from swift_b200 import synthetic as syn
     from swift_b200.precond import PassPrecond
     img_channels = cfg["out_channels"] if img_channels is None else img_channels
@@ -35,21 +35,23 @@ def build_net(cfg, seed=1, img_channels=None):
     sd = syn.random_state_dict(cfg, seed=seed, prefix="model.")
     missing = net.load_state_dict(sd, strict=True)
     assert not missing.missing_keys and not missing.unexpected_keys
+    net.model.act_fp16 = act_fp16
     return net.cuda().eval(), {k[len("model."):]: v for k, v in sd.items()}
 
 
+@pytest.mark.parametrize("act_fp16", [True, False], ids=["act_fp16", "act_bf16"])
 @pytest.mark.parametrize("name,cfgname", [("tiny", "SWIFT_TINY"), ("small", "SWIFT_SMALL")])
-def test_module_forward_vs_reference_golden(golden, name, cfgname):
+def test_module_forward_vs_reference_golden(golden, name, cfgname, act_fp16):
     from swift_b200 import synthetic as syn
     g = golden(name)
     cfg = getattr(syn, cfgname)
-    net, _ = build_net(cfg)
+    net, _ = build_net(cfg, act_fp16=act_fp16)
     lat, cond = syn.synthetic_fields(cfg, 2, seed=3)
     with torch.no_grad():
         y = net(lat.cuda(), torch.from_numpy(g["fwd_t"]).cuda(), cond.cuda(), torch.from_numpy(g["fwd_aux"]).cuda())
     err = per_field_rel_l2(y, g["fwd_y"])
-    print(f"{name}: forward per-field rel-L2 max {err.max():.4e} mean {err.mean():.4e}")
-    assert err.max() < TOL
+    print(f"{name} act_fp16={act_fp16}: forward per-field rel-L2 max {err.max():.4e} mean {err.mean():.4e}")
+    assert err.max() < (0.25 * TOL if act_fp16 else TOL)
 
 
 @pytest.mark.parametrize("name,cfgname", [("tiny", "SWIFT_TINY"), ("small", "SWIFT_SMALL")])
@@ -95,7 +97,10 @@ def test_fused_sampler_equals_generic_path():
 
 
 def test_swift_b_one_step_vs_oracle_and_golden(golden):
-    """BASELINE.json configs[0]: Swift-B, single 6 h sCM step, batch 1, 128x256, vs fp32 reference."""
+    """BASELINE.json configs[0]: Swift-B, single 6 h sCM step, batch 1, 128x256, vs fp32 reference.
+
+    Default numerics (fp16 activations x bf16 weights) must meet the 1e-2 per-field bar with margin; the all-bf16
+    mode is measured too and reported (SURVEY.md section 7.3 predicts ~0.8e-2 mean / ~1e-2 max for it)."""
     from oracle import swinv2_oracle as orc
     from swift_b200 import synthetic as syn
     from swift_b200.sampler import DiffusionSampler
@@ -117,10 +122,16 @@ def test_swift_b_one_step_vs_oracle_and_golden(golden):
     assert np.allclose(ref[:, :, ::8, ::8].cpu().numpy(), g["scm1_sub"], rtol=2e-3, atol=2e-4), \
         "GPU fp32 oracle drifted from the reference digest"
     err = per_field_rel_l2(y, ref)
-    print(f"swift_b scm1: per-field rel-L2 max {err.max():.4e} mean {err.mean():.4e}")
-    assert err.max() < TOL
+    print(f"swift_b scm1 (fp16 activations): per-field rel-L2 max {err.max():.4e} mean {err.mean():.4e}")
+    assert err.max() < 0.5 * TOL
     sub = per_field_rel_l2(y[:, :, ::8, ::8], torch.from_numpy(g["scm1_sub"]))
-    assert sub.max() < 1.5 * TOL            # sub-sampled norm (512 points per field) is noisier
+    assert sub.max() < TOL                  # vs the REAL reference's sub-sampled output (512 points per field)
+    net.model.act_fp16 = False
+    yb = DiffusionSampler(net).scm_solver(latents=lat.cuda(), condition=cond.cuda(), auxiliary=0.6, num_steps=1,
+                                          sigma_min=0.02, sigma_max=200.0)
+    errb = per_field_rel_l2(yb, ref)
+    print(f"swift_b scm1 (bf16 activations): per-field rel-L2 max {errb.max():.4e} mean {errb.mean():.4e}")
+    assert errb.max() < 1.5 * TOL
 
 
 def test_module_contract():

@@ -30,20 +30,29 @@ def _rel(a, b):
     return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
 
 
-def _rand_bf16(shape, seed, scale=1.0):
+def _rand_bf16(shape, seed, scale=1.0, dtype=torch.bfloat16):
     g = torch.Generator(device="cuda").manual_seed(seed)
-    return (torch.randn(shape, generator=g, device="cuda") * scale).to(torch.bfloat16)
+    return (torch.randn(shape, generator=g, device="cuda") * scale).to(dtype)
 
 
+ACT = pytest.mark.parametrize("f16", [1, 0], ids=["act_fp16", "act_bf16"])
+
+
+def _adt(f16):
+    return torch.float16 if f16 else torch.bfloat16
+
+
+@ACT
 @pytest.mark.parametrize("cg", [2, 1])
 @pytest.mark.parametrize("M,N,K", [(256, 176, 64), (256, 176, 128), (512, 352, 1056), (4096, 1056, 2816),
                                    (300, 276, 568), (8192, 1056, 1056)])
-def test_gemm_store_f32(lib, cg, M, N, K):
-    A = _rand_bf16((M, K), 1)
+def test_gemm_store_f32(lib, cg, M, N, K, f16):
+    """A in the activation format (fp16 or bf16) x W in bf16: the mixed-format kind::f16 UMMA."""
+    A = _rand_bf16((M, K), 1, dtype=_adt(f16))
     W = _rand_bf16((N, K), 2, 0.05)
     ldo = (N + 7) // 8 * 8
     out = torch.full((M, ldo), float("nan"), device="cuda")
-    _check(lib.swb200_gemm(0, cg, A.data_ptr(), K, W.data_ptr(), K, out.data_ptr(), ldo, M, N, K, _stream()))
+    _check(lib.swb200_gemm(0, cg, f16, A.data_ptr(), K, W.data_ptr(), K, out.data_ptr(), ldo, M, N, K, _stream()))
     torch.cuda.synchronize()
     ref = A.float() @ W.float().t()
     got = out[:, :N]
@@ -51,28 +60,30 @@ def test_gemm_store_f32(lib, cg, M, N, K):
     assert _rel(got, ref) < 2e-3, f"rel L2 {_rel(got, ref):.3e}"
 
 
+@ACT
 @pytest.mark.parametrize("cg", [2, 1])
-def test_gemm_store_bf16_strided_operands(lib, cg):
+def test_gemm_store_act_strided_operands(lib, cg, f16):
     M, N, K = 512, 528, 264
-    Abig = _rand_bf16((M, 2 * K), 3)          # A is the left half of a wider buffer (row pitch 2K)
+    Abig = _rand_bf16((M, 2 * K), 3, dtype=_adt(f16))          # A is the left half of a wider buffer (row pitch 2K)
     W = _rand_bf16((N, K), 4, 0.05)
-    out = torch.zeros((M, N), device="cuda", dtype=torch.bfloat16)
-    _check(lib.swb200_gemm(1, cg, Abig.data_ptr(), 2 * K, W.data_ptr(), K, out.data_ptr(), N, M, N, K, _stream()))
+    out = torch.zeros((M, N), device="cuda", dtype=_adt(f16))
+    _check(lib.swb200_gemm(1, cg, f16, Abig.data_ptr(), 2 * K, W.data_ptr(), K, out.data_ptr(), N, M, N, K, _stream()))
     torch.cuda.synchronize()
     ref = Abig[:, :K].float() @ W.float().t()
     assert _rel(out.float(), ref) < 6e-3
 
 
+@ACT
 @pytest.mark.parametrize("cg", [2, 1])
-def test_gemm_qkv_epilogue(lib, cg):
+def test_gemm_qkv_epilogue(lib, cg, f16):
     """EPI_QKV: rows packed part*D + h*88 + d; q,k L2-normalised in fp32 (eps 1e-12), q * qscale[h]; pad to 96."""
-    M, H = 512, 6
+    M, H = 512, 5
     D = H * HD
-    A = _rand_bf16((M, D), 5)
+    A = _rand_bf16((M, D), 5, dtype=_adt(f16))
     W = _rand_bf16((3 * D, D), 6, 0.03)
     qscale = torch.linspace(5.0, 20.0, H, device="cuda")
-    out = torch.full((3, H, M, HDP), float("nan"), device="cuda", dtype=torch.bfloat16)
-    _check(lib.swb200_gemm_qkv(cg, A.data_ptr(), D, W.data_ptr(), qscale.data_ptr(), out.data_ptr(), M, D, H, _stream()))
+    out = torch.full((3, H, M, HDP), float("nan"), device="cuda", dtype=_adt(f16))
+    _check(lib.swb200_gemm_qkv(cg, f16, A.data_ptr(), D, W.data_ptr(), qscale.data_ptr(), out.data_ptr(), M, D, H, _stream()))
     torch.cuda.synchronize()
     y = (A.float() @ W.float().t()).reshape(M, 3, H, HD).permute(1, 2, 0, 3)       # [3, H, M, 88]
     q = torch.nn.functional.normalize(y[0], dim=-1) * qscale[:, None, None]
@@ -83,49 +94,53 @@ def test_gemm_qkv_epilogue(lib, cg):
         assert _rel(out[part, ..., :HD].float(), ref[part]) < 4e-3, f"{name}: {_rel(out[part, ..., :HD].float(), ref[part]):.3e}"
 
 
+@ACT
 @pytest.mark.parametrize("cg", [2, 1])
-def test_gemm_swiglu_epilogue(lib, cg):
+def test_gemm_swiglu_epilogue(lib, cg, f16):
     M, D, Dff = 512, 264, 704
-    A = _rand_bf16((M, D), 7)
+    A = _rand_bf16((M, D), 7, dtype=_adt(f16))
     W1 = _rand_bf16((2 * Dff, D), 8, 0.06)        # reference layout: [gate | up]
     gate, up = W1[:Dff].reshape(Dff // HD, 1, HD, D), W1[Dff:].reshape(Dff // HD, 1, HD, D)
     Wp = torch.cat([gate, up], 1).reshape(2 * Dff, D).contiguous()
-    out = torch.full((M, Dff), float("nan"), device="cuda", dtype=torch.bfloat16)
-    _check(lib.swb200_gemm_swiglu(cg, A.data_ptr(), D, Wp.data_ptr(), out.data_ptr(), M, D, Dff, _stream()))
+    out = torch.full((M, Dff), float("nan"), device="cuda", dtype=_adt(f16))
+    _check(lib.swb200_gemm_swiglu(cg, f16, A.data_ptr(), D, Wp.data_ptr(), out.data_ptr(), M, D, Dff, _stream()))
     torch.cuda.synchronize()
     h = A.float() @ W1.float().t()
     ref = torch.nn.functional.silu(h[:, :Dff]) * h[:, Dff:]
     assert _rel(out.float(), ref) < 4e-3, f"{_rel(out.float(), ref):.3e}"
 
 
+@ACT
 @pytest.mark.parametrize("cg", [2, 1])
-def test_gemm_embed_epilogue(lib, cg):
+def test_gemm_embed_epilogue(lib, cg, f16):
     B, T, D, K = 2, 512, 264, 56
     M = B * T
-    A = _rand_bf16((M, K), 9)
+    A = _rand_bf16((M, K), 9, dtype=_adt(f16))
     W = _rand_bf16((D, K), 10, 0.1)
     bias = torch.randn(D, device="cuda")
     pos = torch.randn(T, D, device="cuda")
     x = torch.full((M, D), float("nan"), device="cuda")
-    xb = torch.zeros((M, D), device="cuda", dtype=torch.bfloat16)
-    _check(lib.swb200_gemm_embed(cg, A.data_ptr(), K, W.data_ptr(), K, bias.data_ptr(), pos.data_ptr(), T,
+    xb = torch.zeros((M, D), device="cuda", dtype=_adt(f16))
+    _check(lib.swb200_gemm_embed(cg, f16, A.data_ptr(), K, W.data_ptr(), K, bias.data_ptr(), pos.data_ptr(), T,
                                  x.data_ptr(), xb.data_ptr(), M, D, _stream()))
     torch.cuda.synchronize()
     ref = A.float() @ W.float().t() + bias + pos.repeat(B, 1)
     assert _rel(x, ref) < 1e-4, f"{_rel(x, ref):.3e}"
-    assert torch.equal(xb, x.to(torch.bfloat16))
+    assert torch.equal(xb, x.to(_adt(f16)))
 
 
+@ACT
 @pytest.mark.parametrize("cg", [2, 1])
 @pytest.mark.parametrize("mode", ["plain", "scm", "heun"])
-def test_gemm_head_epilogue(lib, cg, mode):
+def test_gemm_head_epilogue(lib, cg, mode, f16):
     from swift_b200 import _lib
     B, C_out, Himg, Wimg, p1, p2, D = 2, 5, 32, 64, 2, 2, 264
     gh, gw = Himg // p1, Wimg // p2
     M = B * gh * gw
-    A = _rand_bf16((M, D), 11)
+    A = _rand_bf16((M, D), 11, dtype=_adt(f16))
     W = _rand_bf16((C_out * p1 * p2, D), 12, 0.05)
     m = _lib.Model()
+    m.act_fp16 = f16
     m.img_h, m.img_w, m.patch_h, m.patch_w, m.out_channels, m.dim = Himg, Wimg, p1, p2, C_out, D
     m.w_head = W.data_ptr()
     xt = torch.randn(B, C_out, Himg, Wimg, device="cuda")
@@ -153,7 +168,7 @@ def test_gemm_rejects_bad_arguments(lib):
     from swift_b200 import _lib
     A = _rand_bf16((256, 64), 1)
     out = torch.zeros(256, 176, device="cuda")
-    rc = lib.swb200_gemm(0, 2, A.data_ptr(), 60, A.data_ptr(), 64, out.data_ptr(), 176, 256, 176, 60, _stream())
+    rc = lib.swb200_gemm(0, 2, 0, A.data_ptr(), 60, A.data_ptr(), 64, out.data_ptr(), 176, 256, 176, 60, _stream())
     assert rc != 0 and b"multiples of 8" in lib.swb200_last_error()
     with pytest.raises(RuntimeError):
-        _lib.check(lib.swb200_gemm(7, 2, A.data_ptr(), 64, A.data_ptr(), 64, out.data_ptr(), 176, 256, 176, 64, _stream()))
+        _lib.check(lib.swb200_gemm(7, 2, 0, A.data_ptr(), 64, A.data_ptr(), 64, out.data_ptr(), 176, 256, 176, 64, _stream()))

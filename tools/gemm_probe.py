@@ -21,7 +21,7 @@ def one(cg, M, N, K):
     W = (torch.randn(N, K, generator=g, device="cuda") * 0.05).to(torch.bfloat16)
     ldo = (N + 7) // 8 * 8
     out = torch.full((M, ldo), float("nan"), device="cuda")
-    rc = lib.swb200_gemm(0, cg, A.data_ptr(), K, W.data_ptr(), K, out.data_ptr(), ldo, M, N, K,
+    rc = lib.swb200_gemm(0, cg, 0, A.data_ptr(), K, W.data_ptr(), K, out.data_ptr(), ldo, M, N, K,
                          torch.cuda.current_stream().cuda_stream)
     print("rc", rc, lib.swb200_last_error())
     torch.cuda.synchronize()
