@@ -264,7 +264,7 @@ def run_ours(args):
         "metric": "forecast member-steps/sec", "value": value, "unit": "member-steps/s", "n_gpus": n_gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
-        "dtype": ("fp16 activations x bf16 weights" if eng.act_fp16 else "bf16") + " on tcgen05 kind::f16, fp32 accumulate / residual / LayerNorm / softmax",
+        "dtype": ("fp16" if eng.act_fp16 else "bf16") + " tensor-core operands (tcgen05 kind::f16), fp32 accumulate / residual / LayerNorm / softmax",
         "data": "synthetic", "config": workload_config(n_gpus, torch.cuda.get_device_name(dev)),
         "clocks": clock_info,
         "e2e": {"value": e2e_value, "unit": "member-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

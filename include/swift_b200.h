@@ -34,13 +34,14 @@ extern "C" {
 
 /* Geometry + packed parameters of one SwinV2 denoiser (constructor arguments of swinv2.py:255-270).
  * Packed layouts are produced by swift_b200/packing.py (documented in DESIGN.md section 3):
- *   w_embed : bf16 [dim, k_embed * (1 + split_embed)]   columns in "(c p1 p2)" order, zero padded to k_embed,
+ * ("h16" = fp16 when act_fp16 else bf16)
+ *   w_embed : h16 [dim, k_embed * (1 + split_embed)]   columns in "(c p1 p2)" order, zero padded to k_embed,
  *             duplicated when split_embed (the A operand is then [hi | lo], see swb200_forward)
- *   w_qkv   : bf16 [depth][3*dim, dim]   rows reordered to  part*dim + head*88 + d   (part = q,k,v)
- *   w_o     : bf16 [depth][dim, dim]
- *   w_1     : bf16 [depth][2*dff, dim]   rows reordered so that every 176-row tile is [88 gate | 88 up]
- *   w_2     : bf16 [depth][dim, dff]
- *   w_head  : bf16 [out_channels*p1*p2, dim * (1 + split_head)]   rows in the reference "(c p1 p2)" order
+ *   w_qkv   : h16  [depth][3*dim, dim]   rows reordered to  part*dim + head*88 + d   (part = q,k,v)
+ *   w_o     : h16  [depth][dim, dim]
+ *   w_1     : h16  [depth][2*dff, dim]   rows reordered so that every 176-row tile is [88 gate | 88 up]
+ *   w_2     : h16  [depth][dim, dff]
+ *   w_head  : h16  [out_channels*p1*p2, dim * (1 + split_head)]   rows in the reference "(c p1 p2)" order
  *   mod_w/b : fp32 [2*depth*2*dim, dim] / [2*depth*2*dim]   ModulatedNorm.modulation of layer l attention
  *             (index 2l) and feed-forward (index 2l+1), each [scale(dim) | shift(dim)]
  *   ln_gamma/ln_beta : fp32 [2*depth, dim]   LayerNorm affine, same order
@@ -49,7 +50,7 @@ typedef struct swb200_model {
   int32_t img_h, img_w, patch_h, patch_w, win_h, win_w, shift_h, shift_w;
   int32_t in_channels, out_channels, depth, dim, heads, dff, aux_dim;
   int32_t k_embed, split_embed, split_head;
-  int32_t act_fp16;           /* 1: activations (GEMM A operands, q/k/v, P) are fp16; 0: bf16.  Weights are bf16. */
+  int32_t act_fp16;           /* 16-bit tensor-core operand format of activations AND packed weights: 1 = fp16, 0 = bf16 */
   float timestep_weight;
   const void* w_embed;
   const float* b_embed;
@@ -118,7 +119,7 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
 
 /* ---- individual kernels (unit tests, profiling) -------------------------------------------------------- */
 
-/* D[M,N] = A[M,K] (fp16 if act_fp16 else bf16, row pitch lda) * W[N,K]^T (bf16, row pitch ldw), fp32 accumulate
+/* D[M,N] = A[M,K] (row pitch lda) * W[N,K]^T (row pitch ldw), both fp16 if act_fp16 else both bf16, fp32 accumulate
  * on tcgen05.  epi: 0 store fp32 out[M,ldo], 1 store out[M,ldo] in the activation format.  cta_group: 2 = paired-CTA UMMA (default), 1 = single. */
 SWB200_API int swb200_gemm(int epi, int cta_group, int act_fp16, const void* A, int lda, const void* W, int ldw, void* out,
                 int ldo, int M, int N, int K, void* stream);

@@ -42,7 +42,7 @@ int make_tmap_16bit_2d(CUtensorMap* out, const void* ptr, bool is_f16, uint64_t 
 
 struct GemmParams;
 // D = A[M,K] * W[N,K]^T with a fused epilogue (gemm_sm100.cuh); cta_group 2 = paired-CTA UMMA (M=256 tiles);
-// act_f16: activations (A and 16-bit outputs) are fp16 instead of bf16.  W is always bf16.
+// act_f16: the 16-bit operand format (A, W and 16-bit outputs) is fp16 instead of bf16.
 int launch_gemm(int epi, int cta_group, int act_f16, const void* A, int lda, const void* W, int ldw,
                 const GemmParams& p, cudaStream_t stream);
 

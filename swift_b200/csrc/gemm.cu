@@ -119,7 +119,7 @@ static int launch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, con
   return SWB_ERR_INVALID;
 }
 
-// A: fp16/bf16 [M, K] with row pitch lda; W: bf16 [N, K] with row pitch ldw (nn.Linear layout).
+// A: [M, K] with row pitch lda; W: [N, K] with row pitch ldw (nn.Linear layout); both fp16 (act_f16) or both bf16.
 int launch_gemm(int epi, int cta_group, int act_f16, const void* A, int lda, const void* W, int ldw,
                 const GemmParams& p, cudaStream_t stream) {
   SWB_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
@@ -130,7 +130,7 @@ int launch_gemm(int epi, int cta_group, int act_f16, const void* A, int lda, con
   CUtensorMap ta, tb;
   int rc = make_tmap_16bit_2d(&ta, A, act_f16 != 0, p.M, p.K, lda, kBlockM, kBlockK);
   if (rc) return rc;
-  rc = make_tmap_16bit_2d(&tb, W, false, p.N, p.K, ldw, BN / cta_group, kBlockK);
+  rc = make_tmap_16bit_2d(&tb, W, act_f16 != 0, p.N, p.K, ldw, BN / cta_group, kBlockK);
   if (rc) return rc;
   if (cta_group == 2)
     return act_f16 ? launch_epi<BN, 2, true>(epi, ta, tb, p, stream) : launch_epi<BN, 2, false>(epi, ta, tb, p, stream);

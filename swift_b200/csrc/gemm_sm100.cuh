@@ -1,4 +1,4 @@
-// Persistent, warp-specialised tcgen05 GEMM for sm_100a:  D[M,N] = A[M,K] * W[N,K]^T  (A fp16 or bf16, W bf16, fp32 accumulate in TMEM)
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a:  D[M,N] = A[M,K] * W[N,K]^T  (A and W both fp16 or both bf16, fp32 accumulate in TMEM)
 // with the epilogues the Swift denoiser needs fused in.  A and W are both K-major (row-major [rows, K]), which is
 // how activations and nn.Linear weights are stored, so neither is ever transposed in memory.
 //
@@ -322,7 +322,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp == 1) {
     // ===================================== UMMA issuer (leader CTA) =====================================
     if (cta_rank == 0 && lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(kBlockM * CG, BN, /*A=*/F16, /*B (weights)=*/false);
+      constexpr uint32_t idesc = make_idesc_f16(kBlockM * CG, BN, /*A=*/F16, /*B=*/F16);   // mixed A/B formats trap
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;

@@ -224,10 +224,11 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-// Activations (every GEMM A operand, q/k/v, P) are stored in one 16-bit format chosen per model:
-//   F16 = true : IEEE half (11-bit significand; saturated to +-65504 so no inf is ever produced)
+// Tensor-core operands (every GEMM A operand, the packed weights, q/k/v, P) use one 16-bit format chosen per model:
+//   F16 = true : IEEE half (11-bit significand; activations saturate to +-65504 so no inf is ever produced)
 //   F16 = false: bfloat16
-// Weights are always bf16; tcgen05 kind::f16 takes the A and B formats independently in the instruction descriptor.
+// tcgen05 kind::f16 encodes the A and B formats separately, but mixing them (fp16 x bf16) raises an illegal-instruction
+// trap on sm_100a (measured), so the weights are packed in the same format as the activations.
 template <bool F16>
 __device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
   if constexpr (F16) {

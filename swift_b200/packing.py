@@ -78,7 +78,7 @@ def pack(sd: Dict[str, torch.Tensor], g: Geometry, device: torch.device, split_e
          split_head: bool = True, act_fp16: bool = True):
     """Returns (``_lib.Model`` struct, dict of device tensors that must stay alive as long as the struct is used)."""
     check_supported(g)
-    bf = torch.bfloat16
+    bf = torch.float16 if act_fp16 else torch.bfloat16     # one 16-bit operand format for activations and weights
     D, H, L, Dff, pp = g.dim, g.heads, g.depth, g.dff, g.pp
     f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
     keep: Dict[str, torch.Tensor] = {}

@@ -114,7 +114,7 @@ class SwinV2(_Base):
         self._engine_key = None
         self.split_embed = True      # [hi|lo] bf16 operands for the two small end GEMMs (accuracy, <1% of FLOPs)
         self.split_head = True
-        self.act_fp16 = True         # activations fp16 (weights bf16): 8x smaller rounding error than bf16, same tcgen05 rate
+        self.act_fp16 = True         # tensor-core operands in fp16 (else bf16): 8x smaller rounding error, same tcgen05 rate
         self.max_chunk = 8           # samples pushed through the kernels per launch sequence
 
     def _init_weights(self):

@@ -99,7 +99,7 @@ def test_fused_sampler_equals_generic_path():
 def test_swift_b_one_step_vs_oracle_and_golden(golden):
     """BASELINE.json configs[0]: Swift-B, single 6 h sCM step, batch 1, 128x256, vs fp32 reference.
 
-    Default numerics (fp16 activations x bf16 weights) must meet the 1e-2 per-field bar with margin; the all-bf16
+    Default numerics (fp16 tensor-core operands, fp32 accumulate) must meet the 1e-2 per-field bar with margin; the all-bf16
     mode is measured too and reported (SURVEY.md section 7.3 predicts ~0.8e-2 mean / ~1e-2 max for it)."""
     from oracle import swinv2_oracle as orc
     from swift_b200 import synthetic as syn
@@ -122,7 +122,7 @@ def test_swift_b_one_step_vs_oracle_and_golden(golden):
     assert np.allclose(ref[:, :, ::8, ::8].cpu().numpy(), g["scm1_sub"], rtol=2e-3, atol=2e-4), \
         "GPU fp32 oracle drifted from the reference digest"
     err = per_field_rel_l2(y, ref)
-    print(f"swift_b scm1 (fp16 activations): per-field rel-L2 max {err.max():.4e} mean {err.mean():.4e}")
+    print(f"swift_b scm1 (fp16 operands): per-field rel-L2 max {err.max():.4e} mean {err.mean():.4e}")
     assert err.max() < 0.5 * TOL
     sub = per_field_rel_l2(y[:, :, ::8, ::8], torch.from_numpy(g["scm1_sub"]))
     assert sub.max() < TOL                  # vs the REAL reference's sub-sampled output (512 points per field)
@@ -130,7 +130,7 @@ def test_swift_b_one_step_vs_oracle_and_golden(golden):
     yb = DiffusionSampler(net).scm_solver(latents=lat.cuda(), condition=cond.cuda(), auxiliary=0.6, num_steps=1,
                                           sigma_min=0.02, sigma_max=200.0)
     errb = per_field_rel_l2(yb, ref)
-    print(f"swift_b scm1 (bf16 activations): per-field rel-L2 max {errb.max():.4e} mean {errb.mean():.4e}")
+    print(f"swift_b scm1 (bf16 operands): per-field rel-L2 max {errb.max():.4e} mean {errb.mean():.4e}")
     assert errb.max() < 1.5 * TOL
 
 

@@ -47,9 +47,9 @@ def _adt(f16):
 @pytest.mark.parametrize("M,N,K", [(256, 176, 64), (256, 176, 128), (512, 352, 1056), (4096, 1056, 2816),
                                    (300, 276, 568), (8192, 1056, 1056)])
 def test_gemm_store_f32(lib, cg, M, N, K, f16):
-    """A in the activation format (fp16 or bf16) x W in bf16: the mixed-format kind::f16 UMMA."""
+    """A and W in the model's 16-bit operand format (fp16 or bf16)."""
     A = _rand_bf16((M, K), 1, dtype=_adt(f16))
-    W = _rand_bf16((N, K), 2, 0.05)
+    W = _rand_bf16((N, K), 2, 0.05, dtype=_adt(f16))
     ldo = (N + 7) // 8 * 8
     out = torch.full((M, ldo), float("nan"), device="cuda")
     _check(lib.swb200_gemm(0, cg, f16, A.data_ptr(), K, W.data_ptr(), K, out.data_ptr(), ldo, M, N, K, _stream()))
@@ -65,7 +65,7 @@ def test_gemm_store_f32(lib, cg, M, N, K, f16):
 def test_gemm_store_act_strided_operands(lib, cg, f16):
     M, N, K = 512, 528, 264
     Abig = _rand_bf16((M, 2 * K), 3, dtype=_adt(f16))          # A is the left half of a wider buffer (row pitch 2K)
-    W = _rand_bf16((N, K), 4, 0.05)
+    W = _rand_bf16((N, K), 4, 0.05, dtype=_adt(f16))
     out = torch.zeros((M, N), device="cuda", dtype=_adt(f16))
     _check(lib.swb200_gemm(1, cg, f16, Abig.data_ptr(), 2 * K, W.data_ptr(), K, out.data_ptr(), N, M, N, K, _stream()))
     torch.cuda.synchronize()
@@ -80,7 +80,7 @@ def test_gemm_qkv_epilogue(lib, cg, f16):
     M, H = 512, 5
     D = H * HD
     A = _rand_bf16((M, D), 5, dtype=_adt(f16))
-    W = _rand_bf16((3 * D, D), 6, 0.03)
+    W = _rand_bf16((3 * D, D), 6, 0.03, dtype=_adt(f16))
     qscale = torch.linspace(5.0, 20.0, H, device="cuda")
     out = torch.full((3, H, M, HDP), float("nan"), device="cuda", dtype=_adt(f16))
     _check(lib.swb200_gemm_qkv(cg, f16, A.data_ptr(), D, W.data_ptr(), qscale.data_ptr(), out.data_ptr(), M, D, H, _stream()))
@@ -99,7 +99,7 @@ def test_gemm_qkv_epilogue(lib, cg, f16):
 def test_gemm_swiglu_epilogue(lib, cg, f16):
     M, D, Dff = 512, 264, 704
     A = _rand_bf16((M, D), 7, dtype=_adt(f16))
-    W1 = _rand_bf16((2 * Dff, D), 8, 0.06)        # reference layout: [gate | up]
+    W1 = _rand_bf16((2 * Dff, D), 8, 0.06, dtype=_adt(f16))        # reference layout: [gate | up]
     gate, up = W1[:Dff].reshape(Dff // HD, 1, HD, D), W1[Dff:].reshape(Dff // HD, 1, HD, D)
     Wp = torch.cat([gate, up], 1).reshape(2 * Dff, D).contiguous()
     out = torch.full((M, Dff), float("nan"), device="cuda", dtype=_adt(f16))
@@ -116,7 +116,7 @@ def test_gemm_embed_epilogue(lib, cg, f16):
     B, T, D, K = 2, 512, 264, 56
     M = B * T
     A = _rand_bf16((M, K), 9, dtype=_adt(f16))
-    W = _rand_bf16((D, K), 10, 0.1)
+    W = _rand_bf16((D, K), 10, 0.1, dtype=_adt(f16))
     bias = torch.randn(D, device="cuda")
     pos = torch.randn(T, D, device="cuda")
     x = torch.full((M, D), float("nan"), device="cuda")
@@ -138,7 +138,7 @@ def test_gemm_head_epilogue(lib, cg, mode, f16):
     gh, gw = Himg // p1, Wimg // p2
     M = B * gh * gw
     A = _rand_bf16((M, D), 11, dtype=_adt(f16))
-    W = _rand_bf16((C_out * p1 * p2, D), 12, 0.05)
+    W = _rand_bf16((C_out * p1 * p2, D), 12, 0.05, dtype=_adt(f16))
     m = _lib.Model()
     m.act_fp16 = f16
     m.img_h, m.img_w, m.patch_h, m.patch_w, m.out_channels, m.dim = Himg, Wimg, p1, p2, C_out, D
