@@ -298,20 +298,20 @@ def dominant_kernel_roofline(eng, dev, chunk: int):
     stream = torch.cuda.current_stream().cuda_stream
     lib = eng.lib
     for _ in range(3):
-        _lib.check(lib.swb200_gemm_swiglu(2, f16, A.data_ptr(), D, W.data_ptr(), out.data_ptr(), M, D, Dff, stream))
+        _lib.check(lib.swb200_gemm_swiglu(eng.model.gemm_tile, f16, A.data_ptr(), D, W.data_ptr(), out.data_ptr(), M, D, Dff, stream))
     torch.cuda.synchronize()
     n = 20
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(n):
-        _lib.check(lib.swb200_gemm_swiglu(2, f16, A.data_ptr(), D, W.data_ptr(), out.data_ptr(), M, D, Dff, stream))
+        _lib.check(lib.swb200_gemm_swiglu(eng.model.gemm_tile, f16, A.data_ptr(), D, W.data_ptr(), out.data_ptr(), M, D, Dff, stream))
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     flops = 2.0 * M * (2 * Dff) * D
     peaks, which = measured_peaks()
     achieved = flops / (ms / 1e3) / 1e12
-    return {"kernel": "gemm_tcgen05_kernel<176,2,EPI_SWIGLU> (w1 up-projection, 42.5% of FLOPs)", "bound": "tensor",
+    return {"kernel": "gemm_tcgen05_kernel<NSUB=%d,CG=2,EPI_SWIGLU> (w1 up-projection, 42.5%% of FLOPs)" % (2 if eng.model.gemm_tile == 3 else 1), "bound": "tensor",
             "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
             "traffic": None, "launch_ms": ms, "flops_per_launch": flops, "peak_source": f"{which} burst bf16"}
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SWB200_ABI_VERSION 2
+#define SWB200_ABI_VERSION 3
 #if defined(__GNUC__)
 #define SWB200_API __attribute__((visibility("default")))
 #else
@@ -39,7 +39,8 @@ extern "C" {
  *             duplicated when split_embed (the A operand is then [hi | lo], see swb200_forward)
  *   w_qkv   : h16  [depth][3*dim, dim]   rows reordered to  part*dim + head*88 + d   (part = q,k,v)
  *   w_o     : h16  [depth][dim, dim]
- *   w_1     : h16  [depth][2*dff, dim]   rows reordered so that every 176-row tile is [88 gate | 88 up]
+ *   w_1     : h16  [depth][2*dff, dim]   rows reordered per GEMM tile of T = 176 (gemm_tile 1, 2) or 352 (gemm_tile 3)
+ *             rows: [T/2 gate rows | T/2 up rows], so gate and up of an output column share an accumulator row
  *   w_2     : h16  [depth][dim, dff]
  *   w_head  : h16  [out_channels*p1*p2, dim * (1 + split_head)]   rows in the reference "(c p1 p2)" order
  *   mod_w/b : fp32 [2*depth*2*dim, dim] / [2*depth*2*dim]   ModulatedNorm.modulation of layer l attention
@@ -50,6 +51,7 @@ typedef struct swb200_model {
   int32_t img_h, img_w, patch_h, patch_w, win_h, win_w, shift_h, shift_w;
   int32_t in_channels, out_channels, depth, dim, heads, dff, aux_dim;
   int32_t k_embed, split_embed, split_head;
+  int32_t gemm_tile;          /* GEMM tile: 1 = 128x176 single CTA, 2 = 256x176 CTA pair, 3 = 256x352 CTA pair (default) */
   int32_t act_fp16;           /* 16-bit tensor-core operand format of activations AND packed weights: 1 = fp16, 0 = bf16 */
   float timestep_weight;
   const void* w_embed;
@@ -120,20 +122,21 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
 /* ---- individual kernels (unit tests, profiling) -------------------------------------------------------- */
 
 /* D[M,N] = A[M,K] (row pitch lda) * W[N,K]^T (row pitch ldw), both fp16 if act_fp16 else both bf16, fp32 accumulate
- * on tcgen05.  epi: 0 store fp32 out[M,ldo], 1 store out[M,ldo] in the activation format.  cta_group: 2 = paired-CTA UMMA (default), 1 = single. */
-SWB200_API int swb200_gemm(int epi, int cta_group, int act_fp16, const void* A, int lda, const void* W, int ldw, void* out,
+ * on tcgen05.  epi: 0 store fp32 out[M,ldo], 1 store out[M,ldo] in the 16-bit operand format.
+ * tile: 1 = 128x176 single CTA, 2 = 256x176 CTA pair (cta_group::2), 3 = 256x352 CTA pair. */
+SWB200_API int swb200_gemm(int epi, int tile, int act_fp16, const void* A, int lda, const void* W, int ldw, void* out,
                 int ldo, int M, int N, int K, void* stream);
 /* qkv projection with fused scaled-cosine normalisation: out = bf16 [3][heads][M][96]; W packed as w_qkv. */
-SWB200_API int swb200_gemm_qkv(int cta_group, int act_fp16, const void* A, int lda, const void* W, const float* qscale, void* out, int M,
+SWB200_API int swb200_gemm_qkv(int tile, int act_fp16, const void* A, int lda, const void* W, const float* qscale, void* out, int M,
                     int dim, int heads, void* stream);
 /* SwiGLU up-projection: out[M, dff] = silu(gate) * up; W packed as w_1. */
-SWB200_API int swb200_gemm_swiglu(int cta_group, int act_fp16, const void* A, int lda, const void* W, void* out, int M, int dim, int dff,
+SWB200_API int swb200_gemm_swiglu(int tile, int act_fp16, const void* A, int lda, const void* W, void* out, int M, int dim, int dff,
                        void* stream);
 /* Patch-embed: x[M,dim] = A*W^T + bias + pos[row % tokens]; xb = bf16(x). */
-SWB200_API int swb200_gemm_embed(int cta_group, int act_fp16, const void* A, int lda, const void* W, int K, const float* bias,
+SWB200_API int swb200_gemm_embed(int tile, int act_fp16, const void* A, int lda, const void* W, int K, const float* bias,
                       const float* pos, int tokens, float* x, void* xb, int M, int dim, void* stream);
 /* Output head with pixel-shuffle + update; A is [M, K] with K = dim*(1+split). */
-SWB200_API int swb200_gemm_head(int cta_group, const swb200_model* m, const void* A, int lda, int K, int B,
+SWB200_API int swb200_gemm_head(int tile, const swb200_model* m, const void* A, int lda, int K, int B,
                      const swb200_update* upd, float* y, void* stream);
 /* cat + patchify + bf16 cast (+ hi/lo split): A[B*tokens, lda] */
 SWB200_API int swb200_patch_gather(const swb200_model* m, const float* x0, int c0, float scale0, const float* x1, int c1, int B,

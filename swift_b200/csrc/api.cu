@@ -9,7 +9,6 @@ using namespace swb;
 
 namespace {
 
-constexpr int kDefaultCG = 2;
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -70,6 +69,9 @@ int validate(const swb200_model* m) {
   SWB_REQUIRE(m->shift_h >= 0 && m->shift_w >= 0 && m->shift_h < 16 && m->shift_w < 16, "bad shift %d,%d", m->shift_h,
               m->shift_w);
   SWB_REQUIRE(m->depth > 0 && m->aux_dim >= 0, "bad depth/aux_dim");
+  SWB_REQUIRE(m->gemm_tile >= 1 && m->gemm_tile <= 3, "gemm_tile must be 1, 2 or 3 (got %d)", m->gemm_tile);
+  SWB_REQUIRE(m->gemm_tile != 3 || m->dff % (2 * kHeadDim) == 0,
+              "gemm_tile 3 (256x352) needs mlp dim %d to be a multiple of 176", m->dff);
   return SWB_OK;
 }
 
@@ -141,6 +143,7 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
   const Geom g = geom(m);
   const int D = m->dim, H = m->heads, Dff = m->dff;
   const int F16 = m->act_fp16 ? 1 : 0;
+  const int kDefaultCG = m->gemm_tile;          // tile config of every GEMM (the w1 packing depends on it)
   const size_t img_in0 = static_cast<size_t>(c0) * m->img_h * m->img_w;
   const size_t img_in1 = static_cast<size_t>(c1) * m->img_h * m->img_w;
   const size_t img_out = static_cast<size_t>(m->out_channels) * m->img_h * m->img_w;
@@ -242,18 +245,19 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
 
 // ------------------------------------------------------------------------------------------------ single kernels
 
-SWB200_API int swb200_gemm(int epi, int cta_group, int act_fp16, const void* A, int lda, const void* W, int ldw, void* out,
+SWB200_API int swb200_gemm(int epi, int tile, int act_fp16, const void* A, int lda, const void* W, int ldw, void* out,
                 int ldo, int M, int N, int K, void* stream) {
   SWB_REQUIRE(epi == EPI_STORE_F32 || epi == EPI_STORE_ACT, "swb200_gemm: epi must be 0 (fp32) or 1 (activation format)");
   SWB_REQUIRE(A && W && out, "swb200_gemm: NULL pointer");
-  SWB_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "swb200_gemm: out must be 16-byte aligned");
+  SWB_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && N % (epi == EPI_STORE_F32 ? 4 : 8) == 0,
+              "swb200_gemm: out must be 16-byte aligned, ldo %% 8 == 0, N %% 4 (fp32) / 8 (16-bit) == 0");
   GemmParams p = base_params(M, N, K);
   p.out0 = out;
   p.ldo = ldo;
-  return launch_gemm(epi, cta_group, act_fp16, A, lda, W, ldw, p, static_cast<cudaStream_t>(stream));
+  return launch_gemm(epi, tile, act_fp16, A, lda, W, ldw, p, static_cast<cudaStream_t>(stream));
 }
 
-SWB200_API int swb200_gemm_qkv(int cta_group, int act_fp16, const void* A, int lda, const void* W, const float* qscale, void* out, int M,
+SWB200_API int swb200_gemm_qkv(int tile, int act_fp16, const void* A, int lda, const void* W, const float* qscale, void* out, int M,
                     int dim, int heads, void* stream) {
   SWB_REQUIRE(A && W && qscale && out, "swb200_gemm_qkv: NULL pointer");
   SWB_REQUIRE(dim == heads * kHeadDim, "swb200_gemm_qkv: need head_dim 88 (dim=%d heads=%d)", dim, heads);
@@ -262,20 +266,21 @@ SWB200_API int swb200_gemm_qkv(int cta_group, int act_fp16, const void* A, int l
   p.qscale = qscale;
   p.heads = heads;
   p.dmodel = dim;
-  return launch_gemm(EPI_QKV, cta_group, act_fp16, A, lda, W, dim, p, static_cast<cudaStream_t>(stream));
+  return launch_gemm(EPI_QKV, tile, act_fp16, A, lda, W, dim, p, static_cast<cudaStream_t>(stream));
 }
 
-SWB200_API int swb200_gemm_swiglu(int cta_group, int act_fp16, const void* A, int lda, const void* W, void* out, int M, int dim, int dff,
+SWB200_API int swb200_gemm_swiglu(int tile, int act_fp16, const void* A, int lda, const void* W, void* out, int M, int dim, int dff,
                        void* stream) {
   SWB_REQUIRE(A && W && out, "swb200_gemm_swiglu: NULL pointer");
-  SWB_REQUIRE(dff % kHeadDim == 0, "swb200_gemm_swiglu: dff must be a multiple of 88");
+  SWB_REQUIRE(dff % kHeadDim == 0 && (tile != 3 || dff % (2 * kHeadDim) == 0),
+              "swb200_gemm_swiglu: dff must be a multiple of 88 (176 for tile 3)");
   GemmParams p = base_params(M, 2 * dff, dim);
   p.out0 = out;
   p.ldo = dff;
-  return launch_gemm(EPI_SWIGLU, cta_group, act_fp16, A, lda, W, dim, p, static_cast<cudaStream_t>(stream));
+  return launch_gemm(EPI_SWIGLU, tile, act_fp16, A, lda, W, dim, p, static_cast<cudaStream_t>(stream));
 }
 
-SWB200_API int swb200_gemm_embed(int cta_group, int act_fp16, const void* A, int lda, const void* W, int K, const float* bias,
+SWB200_API int swb200_gemm_embed(int tile, int act_fp16, const void* A, int lda, const void* W, int K, const float* bias,
                       const float* pos, int tokens, float* x, void* xb, int M, int dim, void* stream) {
   SWB_REQUIRE(A && W && bias && pos && x && xb, "swb200_gemm_embed: NULL pointer");
   GemmParams p = base_params(M, dim, K);
@@ -285,10 +290,10 @@ SWB200_API int swb200_gemm_embed(int cta_group, int act_fp16, const void* A, int
   p.bias = bias;
   p.pos = pos;
   p.pos_rows = tokens;
-  return launch_gemm(EPI_EMBED, cta_group, act_fp16, A, lda, W, K, p, static_cast<cudaStream_t>(stream));
+  return launch_gemm(EPI_EMBED, tile, act_fp16, A, lda, W, K, p, static_cast<cudaStream_t>(stream));
 }
 
-SWB200_API int swb200_gemm_head(int cta_group, const swb200_model* m, const void* A, int lda, int K, int B,
+SWB200_API int swb200_gemm_head(int tile, const swb200_model* m, const void* A, int lda, int K, int B,
                      const swb200_update* upd, float* y, void* stream) {
   SWB_REQUIRE(m && A && upd && y, "swb200_gemm_head: NULL pointer");
   const Geom g = geom(m);
@@ -307,7 +312,7 @@ SWB200_API int swb200_gemm_head(int cta_group, const swb200_model* m, const void
   p.p2 = m->patch_w;
   p.gw = g.gw;
   p.tokens = g.tokens;
-  return launch_gemm(EPI_HEAD, cta_group, m->act_fp16 ? 1 : 0, A, lda, m->w_head, K, p, static_cast<cudaStream_t>(stream));
+  return launch_gemm(EPI_HEAD, tile, m->act_fp16 ? 1 : 0, A, lda, m->w_head, K, p, static_cast<cudaStream_t>(stream));
 }
 
 SWB200_API int swb200_patch_gather(const swb200_model* m, const float* x0, int c0, float scale0, const float* x1, int c1, int B,

@@ -41,9 +41,10 @@ int make_tmap_16bit_2d(CUtensorMap* out, const void* ptr, bool is_f16, uint64_t 
                        uint64_t pitch_elems, uint32_t box_rows, uint32_t box_cols);
 
 struct GemmParams;
-// D = A[M,K] * W[N,K]^T with a fused epilogue (gemm_sm100.cuh); cta_group 2 = paired-CTA UMMA (M=256 tiles);
+// D = A[M,K] * W[N,K]^T with a fused epilogue (gemm_sm100.cuh).
+// tile: 1 = single CTA 128x176, 2 = CTA pair 256x176, 3 = CTA pair 256x352 (the SwiGLU weight packing depends on it);
 // act_f16: the 16-bit operand format (A, W and 16-bit outputs) is fp16 instead of bf16.
-int launch_gemm(int epi, int cta_group, int act_f16, const void* A, int lda, const void* W, int ldw,
-                const GemmParams& p, cudaStream_t stream);
+int launch_gemm(int epi, int tile, int act_f16, const void* A, int lda, const void* W, int ldw, const GemmParams& p,
+                cudaStream_t stream);
 
 }  // namespace swb

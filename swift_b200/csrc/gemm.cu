@@ -74,23 +74,23 @@ int make_tmap_16bit_2d(CUtensorMap* out, const void* ptr, bool is_f16, uint64_t 
 }
 
 // ----------------------------------------------------------------------------- launch
-template <int BN, int CG, int EPI, bool F16>
+template <int NSUB, int CG, int EPI, bool F16>
 static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-  using S = GemmSmem<BN, CG>;
-  auto kern = gemm_tcgen05_kernel<BN, CG, EPI, F16>;
+  using S = GemmCfg<NSUB, CG>;
+  auto kern = gemm_tcgen05_kernel<NSUB, CG, EPI, F16>;
   static bool attr_done = false;
   if (!attr_done) {
     SWB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     attr_done = true;
   }
-  const int tiles_n = (p.N + BN - 1) / BN;
+  const int tiles_n = (p.N + S::kTileN - 1) / S::kTileN;
   const int tiles_m = (p.M + kBlockM * CG - 1) / (kBlockM * CG);
   const int num_tiles = tiles_m * tiles_n;
   int clusters = num_sms() / CG;
   if (clusters > num_tiles) clusters = num_tiles;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * CG);
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(S::kThreads);
   cfg.dynamicSmemBytes = S::kTotal;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -104,37 +104,41 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   return SWB_OK;
 }
 
-template <int BN, int CG, bool F16>
+template <int NSUB, int CG, bool F16>
 static int launch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                       cudaStream_t stream) {
   switch (epi) {
-    case EPI_STORE_F32: return launch_inst<BN, CG, EPI_STORE_F32, F16>(ta, tb, p, stream);
-    case EPI_STORE_ACT: return launch_inst<BN, CG, EPI_STORE_ACT, F16>(ta, tb, p, stream);
-    case EPI_EMBED: return launch_inst<BN, CG, EPI_EMBED, F16>(ta, tb, p, stream);
-    case EPI_QKV: return launch_inst<BN, CG, EPI_QKV, F16>(ta, tb, p, stream);
-    case EPI_SWIGLU: return launch_inst<BN, CG, EPI_SWIGLU, F16>(ta, tb, p, stream);
-    case EPI_HEAD: return launch_inst<BN, CG, EPI_HEAD, F16>(ta, tb, p, stream);
+    case EPI_STORE_F32: return launch_inst<NSUB, CG, EPI_STORE_F32, F16>(ta, tb, p, stream);
+    case EPI_STORE_ACT: return launch_inst<NSUB, CG, EPI_STORE_ACT, F16>(ta, tb, p, stream);
+    case EPI_EMBED: return launch_inst<NSUB, CG, EPI_EMBED, F16>(ta, tb, p, stream);
+    case EPI_QKV: return launch_inst<NSUB, CG, EPI_QKV, F16>(ta, tb, p, stream);
+    case EPI_SWIGLU: return launch_inst<NSUB, CG, EPI_SWIGLU, F16>(ta, tb, p, stream);
+    case EPI_HEAD: return launch_inst<NSUB, CG, EPI_HEAD, F16>(ta, tb, p, stream);
   }
   set_error("unknown GEMM epilogue %d", epi);
   return SWB_ERR_INVALID;
 }
 
 // A: [M, K] with row pitch lda; W: [N, K] with row pitch ldw (nn.Linear layout); both fp16 (act_f16) or both bf16.
-int launch_gemm(int epi, int cta_group, int act_f16, const void* A, int lda, const void* W, int ldw,
-                const GemmParams& p, cudaStream_t stream) {
+// tile: 1 = single CTA 128x176, 2 = CTA pair 256x176 (double-buffered accumulator), 3 = CTA pair 256x352.
+int launch_gemm(int epi, int tile, int act_f16, const void* A, int lda, const void* W, int ldw, const GemmParams& p,
+                cudaStream_t stream) {
   SWB_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
   SWB_REQUIRE(p.K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm: K and row pitches must be multiples of 8 (K=%d)",
               p.K);
-  SWB_REQUIRE(cta_group == 1 || cta_group == 2, "gemm: cta_group must be 1 or 2");
-  constexpr int BN = 176;
+  SWB_REQUIRE(tile >= 1 && tile <= 3, "gemm: tile config must be 1 (128x176), 2 (256x176) or 3 (256x352), got %d", tile);
+  const int cg = tile == 1 ? 1 : 2;
+  const int nsub = tile == 3 ? 2 : 1;
   CUtensorMap ta, tb;
   int rc = make_tmap_16bit_2d(&ta, A, act_f16 != 0, p.M, p.K, lda, kBlockM, kBlockK);
   if (rc) return rc;
-  rc = make_tmap_16bit_2d(&tb, W, act_f16 != 0, p.N, p.K, ldw, BN / cta_group, kBlockK);
+  rc = make_tmap_16bit_2d(&tb, W, act_f16 != 0, p.N, p.K, ldw, kUmmaN * nsub / cg, kBlockK);
   if (rc) return rc;
-  if (cta_group == 2)
-    return act_f16 ? launch_epi<BN, 2, true>(epi, ta, tb, p, stream) : launch_epi<BN, 2, false>(epi, ta, tb, p, stream);
-  return act_f16 ? launch_epi<BN, 1, true>(epi, ta, tb, p, stream) : launch_epi<BN, 1, false>(epi, ta, tb, p, stream);
+  if (tile == 3)
+    return act_f16 ? launch_epi<2, 2, true>(epi, ta, tb, p, stream) : launch_epi<2, 2, false>(epi, ta, tb, p, stream);
+  if (tile == 2)
+    return act_f16 ? launch_epi<1, 2, true>(epi, ta, tb, p, stream) : launch_epi<1, 2, false>(epi, ta, tb, p, stream);
+  return act_f16 ? launch_epi<1, 1, true>(epi, ta, tb, p, stream) : launch_epi<1, 1, false>(epi, ta, tb, p, stream);
 }
 
 }  // namespace swb

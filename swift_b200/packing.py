@@ -75,13 +75,16 @@ def check_supported(g: Geometry) -> None:
 
 
 def pack(sd: Dict[str, torch.Tensor], g: Geometry, device: torch.device, split_embed: bool = True,
-         split_head: bool = True, act_fp16: bool = True):
+         split_head: bool = True, act_fp16: bool = True, gemm_tile: int = 3):
     """Returns (``_lib.Model`` struct, dict of device tensors that must stay alive as long as the struct is used)."""
     check_supported(g)
     bf = torch.float16 if act_fp16 else torch.bfloat16     # one 16-bit operand format for activations and weights
     D, H, L, Dff, pp = g.dim, g.heads, g.depth, g.dff, g.pp
     f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
     keep: Dict[str, torch.Tensor] = {}
+    if gemm_tile == 3 and Dff % (2 * HEAD_DIM):
+        gemm_tile = 2                               # 352-wide tiles need whole gate/up slot pairs
+    half = HEAD_DIM * (2 if gemm_tile == 3 else 1)
 
     # patch-embed: reference feature order "(p1 p2 c)" -> ours "(c p1 p2)"; zero pad to k_embed; duplicate for [hi|lo]
     w = f32(sd["patch_embed.emb.weight"])
@@ -116,9 +119,10 @@ def pack(sd: Dict[str, torch.Tensor], g: Geometry, device: torch.device, split_e
         q = f32(sd[a + ".to_qkv.weight"]).reshape(H, 3, HEAD_DIM, D).permute(1, 0, 2, 3).reshape(3 * D, D)
         wq.append(q.to(bf))
         wo.append(f32(sd[a + ".wo.weight"]).to(bf))
-        # w1 rows: [gate(Dff) | up(Dff)] (chunk(2), models/swinv2.py:99) -> per 176-row tile [88 gate | 88 up]
+        # w1 rows: [gate(Dff) | up(Dff)] (chunk(2), models/swinv2.py:99) -> per GEMM tile of 2*half rows:
+        # [half gate rows | half up rows] (half = 88 for the 176-wide tiles, 176 for the 352-wide tile)
         w1_ = f32(sd[f + ".w1.weight"])
-        gate, up = w1_[:Dff].reshape(Dff // HEAD_DIM, 1, HEAD_DIM, D), w1_[Dff:].reshape(Dff // HEAD_DIM, 1, HEAD_DIM, D)
+        gate, up = w1_[:Dff].reshape(Dff // half, 1, half, D), w1_[Dff:].reshape(Dff // half, 1, half, D)
         w1.append(torch.cat([gate, up], dim=1).reshape(2 * Dff, D).to(bf))
         w2.append(f32(sd[f + ".w2.weight"]).to(bf))
     keep["mod_w"] = torch.cat(mod_w, 0).contiguous()
@@ -145,6 +149,7 @@ def pack(sd: Dict[str, torch.Tensor], g: Geometry, device: torch.device, split_e
     m.dff, m.aux_dim, m.k_embed = Dff, (g.aux_dim if "aux_w" in keep else 0), g.k_embed
     m.split_embed, m.split_head = int(split_embed), int(split_head)
     m.act_fp16 = int(act_fp16)
+    m.gemm_tile = int(gemm_tile)
     m.timestep_weight = float(g.timestep_weight)
     for name in ("w_embed", "b_embed", "pos_embed", "aux_w", "aux_b", "l1_w", "l1_b", "l2_w", "l2_b", "mod_w",
                  "mod_b", "ln_gamma", "ln_beta", "qscale", "w_qkv", "w_o", "w_1", "w_2", "w_head"):

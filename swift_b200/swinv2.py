@@ -115,6 +115,7 @@ class SwinV2(_Base):
         self.split_embed = True      # [hi|lo] bf16 operands for the two small end GEMMs (accuracy, <1% of FLOPs)
         self.split_head = True
         self.act_fp16 = True         # tensor-core operands in fp16 (else bf16): 8x smaller rounding error, same tcgen05 rate
+        self.gemm_tile = 3           # 1: 128x176 single CTA, 2: 256x176 CTA pair, 3: 256x352 CTA pair
         self.max_chunk = 8           # samples pushed through the kernels per launch sequence
 
     def _init_weights(self):
@@ -134,7 +135,7 @@ class SwinV2(_Base):
 
     def engine(self) -> Engine:
         """The packed CUDA engine for the current parameter values (re-packed when parameters change)."""
-        key = (self._params_key(), self.split_embed, self.split_head, self.max_chunk, self.act_fp16)
+        key = (self._params_key(), self.split_embed, self.split_head, self.max_chunk, self.act_fp16, self.gemm_tile)
         if self._engine is None or self._engine_key != key:
             dev = self.pos_embed.device
             if dev.type != "cuda":
@@ -142,7 +143,7 @@ class SwinV2(_Base):
                                    "there is no CPU fallback")
             sd = {k: v for k, v in self.state_dict().items()}
             self._engine = Engine(sd, self.geometry, dev, self.split_embed, self.split_head, self.max_chunk,
-                                  self.act_fp16)
+                                  self.act_fp16, self.gemm_tile)
             self._engine_key = key
         return self._engine
 

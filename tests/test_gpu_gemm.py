@@ -43,7 +43,7 @@ def _adt(f16):
 
 
 @ACT
-@pytest.mark.parametrize("cg", [2, 1])
+@pytest.mark.parametrize("cg", [3, 2, 1], ids=["tile256x352", "tile256x176", "tile128x176"])
 @pytest.mark.parametrize("M,N,K", [(256, 176, 64), (256, 176, 128), (512, 352, 1056), (4096, 1056, 2816),
                                    (300, 276, 568), (8192, 1056, 1056)])
 def test_gemm_store_f32(lib, cg, M, N, K, f16):
@@ -61,7 +61,7 @@ def test_gemm_store_f32(lib, cg, M, N, K, f16):
 
 
 @ACT
-@pytest.mark.parametrize("cg", [2, 1])
+@pytest.mark.parametrize("cg", [3, 2, 1], ids=["tile256x352", "tile256x176", "tile128x176"])
 def test_gemm_store_act_strided_operands(lib, cg, f16):
     M, N, K = 512, 528, 264
     Abig = _rand_bf16((M, 2 * K), 3, dtype=_adt(f16))          # A is the left half of a wider buffer (row pitch 2K)
@@ -74,9 +74,9 @@ def test_gemm_store_act_strided_operands(lib, cg, f16):
 
 
 @ACT
-@pytest.mark.parametrize("cg", [2, 1])
+@pytest.mark.parametrize("cg", [3, 2, 1], ids=["tile256x352", "tile256x176", "tile128x176"])
 def test_gemm_qkv_epilogue(lib, cg, f16):
-    """EPI_QKV: rows packed part*D + h*88 + d; q,k L2-normalised in fp32 (eps 1e-12), q * qscale[h]; pad to 96."""
+    """EPI_QKV (odd head count: slots straddle tiles): rows packed part*D + h*88 + d; q,k L2-normalised in fp32 (eps 1e-12), q * qscale[h]; pad to 96."""
     M, H = 512, 5
     D = H * HD
     A = _rand_bf16((M, D), 5, dtype=_adt(f16))
@@ -95,12 +95,13 @@ def test_gemm_qkv_epilogue(lib, cg, f16):
 
 
 @ACT
-@pytest.mark.parametrize("cg", [2, 1])
+@pytest.mark.parametrize("cg", [3, 2, 1], ids=["tile256x352", "tile256x176", "tile128x176"])
 def test_gemm_swiglu_epilogue(lib, cg, f16):
     M, D, Dff = 512, 264, 704
     A = _rand_bf16((M, D), 7, dtype=_adt(f16))
     W1 = _rand_bf16((2 * Dff, D), 8, 0.06, dtype=_adt(f16))        # reference layout: [gate | up]
-    gate, up = W1[:Dff].reshape(Dff // HD, 1, HD, D), W1[Dff:].reshape(Dff // HD, 1, HD, D)
+    half = 2 * HD if cg == 3 else HD              # rows per tile: [half gate | half up]
+    gate, up = W1[:Dff].reshape(Dff // half, 1, half, D), W1[Dff:].reshape(Dff // half, 1, half, D)
     Wp = torch.cat([gate, up], 1).reshape(2 * Dff, D).contiguous()
     out = torch.full((M, Dff), float("nan"), device="cuda", dtype=_adt(f16))
     _check(lib.swb200_gemm_swiglu(cg, f16, A.data_ptr(), D, Wp.data_ptr(), out.data_ptr(), M, D, Dff, _stream()))
@@ -111,7 +112,7 @@ def test_gemm_swiglu_epilogue(lib, cg, f16):
 
 
 @ACT
-@pytest.mark.parametrize("cg", [2, 1])
+@pytest.mark.parametrize("cg", [3, 2, 1], ids=["tile256x352", "tile256x176", "tile128x176"])
 def test_gemm_embed_epilogue(lib, cg, f16):
     B, T, D, K = 2, 512, 264, 56
     M = B * T
@@ -130,7 +131,7 @@ def test_gemm_embed_epilogue(lib, cg, f16):
 
 
 @ACT
-@pytest.mark.parametrize("cg", [2, 1])
+@pytest.mark.parametrize("cg", [3, 2, 1], ids=["tile256x352", "tile256x176", "tile128x176"])
 @pytest.mark.parametrize("mode", ["plain", "scm", "heun"])
 def test_gemm_head_epilogue(lib, cg, mode, f16):
     from swift_b200 import _lib

@@ -45,6 +45,7 @@ def test_validate_rejects_unsupported_geometry():
     m.dim, m.heads, m.dff, m.depth = 1056, 12, 2816, 12
     m.in_channels, m.out_channels, m.k_embed = 141, 69, 568
     m.shift_h = m.shift_w = 8
+    m.gemm_tile = 3
     assert lib.swb200_validate(ctypes.byref(m)) == 0
     assert lib.swb200_workspace_bytes(ctypes.byref(m), 1) > 200e6      # ~216 MB per Swift-B sample
 
@@ -64,7 +65,7 @@ def _geometry(c):
                             dim=c["dim"], heads=c["heads"], aux_dim=c["auxiliary_dim"], timestep_weight=1.0)
 
 
-def _emulate_packed_forward(keep, g, x, cond_vec_fn):
+def _emulate_packed_forward(keep, g, x, cond_vec_fn, gemm_tile):
     """What the CUDA kernels compute, written with PyTorch ops on the PACKED tensors (fp32 math): validates the
     layouts of packing.py and the gather-instead-of-roll window indexing of attention.cu."""
     B = x.shape[0]
@@ -96,7 +97,8 @@ def _emulate_packed_forward(keep, g, x, cond_vec_fn):
         branch = attn.reshape(B * T, D) @ keep["w_o"][l].float().t()
         ln = torch.nn.functional.layer_norm(branch, (D,), eps=1e-6).reshape(B, T, D)
         tok = tok + (ln * gain[2 * l][:, None] + bias[2 * l][:, None]).reshape(B * T, D)
-        h = (tok @ keep["w_1"][l].float().t()).reshape(B * T, Dff // HD, 2, HD)
+        half = HD * (2 if gemm_tile == 3 else 1)          # w1 is packed per GEMM tile: [half gate | half up]
+        h = (tok @ keep["w_1"][l].float().t()).reshape(B * T, Dff // half, 2, half)
         h = (torch.nn.functional.silu(h[:, :, 0]) * h[:, :, 1]).reshape(B * T, Dff)
         branch = h @ keep["w_2"][l].float().t()
         ln = torch.nn.functional.layer_norm(branch, (D,), eps=1e-6).reshape(B, T, D)
@@ -105,12 +107,14 @@ def _emulate_packed_forward(keep, g, x, cond_vec_fn):
     return y.reshape(B, gh, gw, g.out_channels, p1, p2).permute(0, 3, 1, 4, 2, 5).reshape(B, g.out_channels, *g.img)
 
 
+@pytest.mark.parametrize("gemm_tile", [3, 2])
 @pytest.mark.parametrize("cfgname", ["SWIFT_TINY", "SWIFT_SMALL"])
-def test_packed_layouts_reproduce_oracle(cfgname):
+def test_packed_layouts_reproduce_oracle(cfgname, gemm_tile):
     c = getattr(syn, cfgname)
     g = _geometry(c)
     sd = syn.random_state_dict(c, seed=1)
-    model, keep = packing.pack(sd, g, torch.device("cpu"))
+    model, keep = packing.pack(sd, g, torch.device("cpu"), gemm_tile=gemm_tile)
+    assert model.gemm_tile == gemm_tile
     assert model.k_embed == g.k_embed and model.dff == g.dff and model.split_embed == 1
     lat, cond = syn.synthetic_fields(c, 2, seed=3)
     x = torch.cat([lat, cond], 1)
@@ -124,7 +128,7 @@ def test_packed_layouts_reproduce_oracle(cfgname):
         bias = keep["ln_beta"][None] * (1 + mod[:, :, 0]) + mod[:, :, 1]
         return gain.transpose(0, 1), bias.transpose(0, 1)
 
-    y = _emulate_packed_forward(keep, g, x, cond_vecs)
+    y = _emulate_packed_forward(keep, g, x, cond_vecs, gemm_tile)
     ref = orc.swinv2_forward(sd, orc.make_cfg(**c), x, t, aux)
     err = (y - ref).norm() / ref.norm()
     assert err < 2e-5, err

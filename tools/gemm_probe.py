@@ -51,8 +51,8 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "one":
         one(*[int(v) for v in sys.argv[2:6]])
         return
-    cases = [(1, 128, 176, 64), (1, 256, 176, 256), (2, 256, 176, 64), (2, 256, 176, 256), (2, 512, 352, 1056),
-             (1, 512, 352, 1056), (2, 8192, 1056, 1056)]
+    cases = [(1, 128, 176, 64), (2, 256, 176, 64), (3, 256, 352, 64), (3, 256, 352, 256), (3, 512, 352, 1056),
+             (2, 512, 352, 1056), (3, 8192, 1056, 1056), (3, 300, 276, 568)]
     for c in cases:
         print("=" * 80)
         try:
