@@ -50,7 +50,7 @@ def main():
         }
         tot_ms, tot_fl = 0.0, 0.0
         for name, (fn, fl) in cases.items():
-            ms = timeit(fn)
+            ms = min(timeit(fn) for _ in range(3))
             tot_ms += ms
             tot_fl += fl
             print(f"tile={cg} {name:4s} M={M}: {ms*1e3:8.1f} us  {fl/ms/1e9:7.1f} TFLOP/s")
