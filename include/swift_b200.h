@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SWB200_ABI_VERSION 3
+#define SWB200_ABI_VERSION 4
 #if defined(__GNUC__)
 #define SWB200_API __attribute__((visibility("default")))
 #else
@@ -52,6 +52,7 @@ typedef struct swb200_model {
   int32_t in_channels, out_channels, depth, dim, heads, dff, aux_dim;
   int32_t k_embed, split_embed, split_head;
   int32_t gemm_tile;          /* GEMM tile: 1 = 128x176 single CTA, 2 = 256x176 CTA pair, 3 = 256x352 CTA pair (default) */
+  int32_t attn_impl;          /* window attention: 0 = auto (tcgen05 kernel for shifts that are multiples of 8), 1 = mma.sync, 2 = tcgen05 */
   int32_t act_fp16;           /* 16-bit tensor-core operand format of activations AND packed weights: 1 = fp16, 0 = bf16 */
   float timestep_weight;
   const void* w_embed;
@@ -144,9 +145,10 @@ SWB200_API int swb200_patch_gather(const swb200_model* m, const float* x0, int c
 /* x += LN(branch)*gain[b] + bias[b]; xb = bf16(x) (pitch ldxb); xlo optional (same pitch). */
 SWB200_API int swb200_ln_mod_residual(const float* branch, float* x, void* xb, int ldxb, void* xlo, const float* gain,
                            const float* bias, int M, int dim, int tokens, int act_fp16, void* stream);
-/* shifted-window cosine attention on the packed qkv buffer; out bf16 [M, heads*88]. */
+/* shifted-window cosine attention on the packed qkv buffer; out 16-bit [M, heads*88].
+ * impl: 0 auto, 1 general-shift mma.sync kernel, 2 tcgen05/TMEM/TMA kernel (shift must be a multiple of 8). */
 SWB200_API int swb200_window_attention(const void* qkv, void* out, int B, int grid_h, int grid_w, int heads, int shift_h,
-                            int shift_w, int act_fp16, void* stream);
+                            int shift_w, int act_fp16, int impl, void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libswift_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # Every symbol ``include/swift_b200.h`` declares; tests check the library exports exactly these.
 EXPORTS = (
@@ -29,7 +29,7 @@ class Model(C.Structure):
     _fields_ = (
         [(n, _i32) for n in ("img_h", "img_w", "patch_h", "patch_w", "win_h", "win_w", "shift_h", "shift_w",
                              "in_channels", "out_channels", "depth", "dim", "heads", "dff", "aux_dim",
-                             "k_embed", "split_embed", "split_head", "gemm_tile", "act_fp16")]
+                             "k_embed", "split_embed", "split_head", "gemm_tile", "attn_impl", "act_fp16")]
         + [("timestep_weight", _f32)]
         + [(n, _vp) for n in ("w_embed", "b_embed", "pos_embed", "aux_w", "aux_b", "l1_w", "l1_b", "l2_w", "l2_b",
                               "mod_w", "mod_b", "ln_gamma", "ln_beta", "qscale", "w_qkv", "w_o", "w_1", "w_2",
@@ -67,7 +67,7 @@ def _declare(lib):
         "swb200_ln_mod_residual": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                              _vp]),
         "swb200_window_attention": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                              _vp]),
+                                              C.c_int, _vp]),
     }
     assert set(sig) == set(EXPORTS)
     for name, (res, args) in sig.items():

@@ -70,6 +70,7 @@ int validate(const swb200_model* m) {
               m->shift_w);
   SWB_REQUIRE(m->depth > 0 && m->aux_dim >= 0, "bad depth/aux_dim");
   SWB_REQUIRE(m->gemm_tile >= 1 && m->gemm_tile <= 3, "gemm_tile must be 1, 2 or 3 (got %d)", m->gemm_tile);
+  SWB_REQUIRE(m->attn_impl >= 0 && m->attn_impl <= 2, "attn_impl must be 0, 1 or 2 (got %d)", m->attn_impl);
   SWB_REQUIRE(m->gemm_tile != 3 || m->dff % (2 * kHeadDim) == 0,
               "gemm_tile 3 (256x352) needs mlp dim %d to be a multiple of 176", m->dff);
   return SWB_OK;
@@ -192,7 +193,7 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
         if (rc) return rc;
       }
       rc = launch_window_attention(qkv, attn, bc, g.gh, g.gw, H, shifted ? m->shift_h : 0, shifted ? m->shift_w : 0,
-                                   F16, stream);
+                                   F16, m->attn_impl, stream);
       if (rc) return rc;
       {
         GemmParams p = base_params(M, D, D);
@@ -331,9 +332,9 @@ SWB200_API int swb200_ln_mod_residual(const float* branch, float* x, void* xb, i
 }
 
 SWB200_API int swb200_window_attention(const void* qkv, void* out, int B, int grid_h, int grid_w, int heads, int shift_h,
-                            int shift_w, int act_fp16, void* stream) {
+                            int shift_w, int act_fp16, int impl, void* stream) {
   SWB_REQUIRE(qkv && out, "swb200_window_attention: NULL pointer");
-  return launch_window_attention(qkv, out, B, grid_h, grid_w, heads, shift_h, shift_w, act_fp16,
+  return launch_window_attention(qkv, out, B, grid_h, grid_w, heads, shift_h, shift_w, act_fp16, impl,
                                  static_cast<cudaStream_t>(stream));
 }
 

@@ -9,8 +9,9 @@
 //     single bf16 rounding, so this kernel sees q_hat*scale and k_hat; softmax scale is 1.0.
 //   * "b h n d -> b n (h d)": the output is written as the [M, heads*88] bf16 operand of the wo GEMM.
 //
-// v1 data path: cp.async gather -> smem, mma.sync m16n8k16 (bf16, fp32 accumulate) with an online softmax over
-// 4 chunks of 64 keys, 16 warps x 16 query rows per (window, head) CTA.
+// This file: the general-shift kernel (any shift; used when the shift is not a multiple of 8 tokens): cp.async gather
+// -> smem, mma.sync m16n8k16 with an online softmax over 4 chunks of 64 keys, 16 warps x 16 query rows per
+// (window, head) CTA.  The production kernel for Swift's shift of 8 is attention_tc.cu (tcgen05 / TMEM / TMA).
 #include "common.h"
 #include "kernels.h"
 
@@ -218,8 +219,11 @@ window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
 }
 
 int launch_window_attention(const void* qkv, void* out, int B, int gh, int gw, int heads, int shift_h, int shift_w,
-                            int act_f16, cudaStream_t stream) {
+                            int act_f16, int impl, cudaStream_t stream) {
   using namespace att;
+  SWB_REQUIRE(impl >= 0 && impl <= 2, "window_attention: impl must be 0 (auto), 1 (mma.sync) or 2 (tcgen05)");
+  if (impl == 2 || (impl == 0 && shift_h % 8 == 0 && shift_w % 8 == 0))
+    return launch_window_attention_tc(qkv, out, B, gh, gw, heads, shift_h, shift_w, act_f16, stream);
   SWB_REQUIRE(gh % kWin == 0 && gw % kWin == 0, "window_attention: token grid %dx%d not divisible by 16x16 windows",
               gh, gw);
   static bool attr_done = false;

@@ -87,15 +87,6 @@ struct GemmCfg {
 
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-  return v;
-}
-
 // Each lane holds NCH 16-byte chunks of ITS OWN row (lane = row of a 32-row block).  Writing them straight to global
 // would touch 32 different 128-byte lines per instruction with 16 useful bytes each; instead the warp transposes
 // through a 4 KB XOR-swizzled smem buffer (4 wavefronts per instruction both ways = the minimum for 512 bytes) and

@@ -32,7 +32,10 @@ int launch_conditioning(const CondWeights& w, const float* t, const float* aux, 
 
 // Shifted-window scaled-cosine attention on the packed qkv buffer [3][heads][M][96] (fp16/bf16, q/k already
 // normalised and q scaled by the GEMM epilogue); out is [M, heads*88] in the same 16-bit format in un-shifted token order.
+// impl: 0 = auto (tcgen05 kernel when the shift is a multiple of 8, else the mma.sync kernel), 1 = mma.sync, 2 = tcgen05
 int launch_window_attention(const void* qkv, void* out, int B, int gh, int gw, int heads, int shift_h, int shift_w,
-                            int act_f16, cudaStream_t stream);
+                            int act_f16, int impl, cudaStream_t stream);
+int launch_window_attention_tc(const void* qkv, void* out, int B, int gh, int gw, int heads, int shift_h, int shift_w,
+                               int act_f16, cudaStream_t stream);
 
 }  // namespace swb

@@ -24,7 +24,7 @@ class Engine:
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], geom: packing.Geometry, device: torch.device,
                  split_embed: bool = True, split_head: bool = True, max_chunk: int = 8, act_fp16: bool = True,
-                 gemm_tile: int = 3):
+                 gemm_tile: int = 3, attn_impl: int = 0):
         if device.type != "cuda":
             raise RuntimeError("swift_b200 runs on CUDA devices only (no CPU fallback)")
         self.lib = _lib.lib()
@@ -32,7 +32,7 @@ class Engine:
         self.device = device
         with torch.cuda.device(device):
             self.model, self._keep = packing.pack(state_dict, geom, device, split_embed, split_head, act_fp16,
-                                                   gemm_tile)
+                                                   gemm_tile, attn_impl)
         self.act_fp16 = act_fp16
         _lib.check(self.lib.swb200_validate(C.byref(self.model)), "validate")
         self.max_chunk = max_chunk

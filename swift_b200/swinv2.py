@@ -116,6 +116,7 @@ class SwinV2(_Base):
         self.split_head = True
         self.act_fp16 = True         # tensor-core operands in fp16 (else bf16): 8x smaller rounding error, same tcgen05 rate
         self.gemm_tile = 3           # 1: 128x176 single CTA, 2: 256x176 CTA pair, 3: 256x352 CTA pair
+        self.attn_impl = 0           # 0: tcgen05 attention when the shift is a multiple of 8, 1: mma.sync kernel, 2: tcgen05
         self.max_chunk = 8           # samples pushed through the kernels per launch sequence
 
     def _init_weights(self):
@@ -135,7 +136,7 @@ class SwinV2(_Base):
 
     def engine(self) -> Engine:
         """The packed CUDA engine for the current parameter values (re-packed when parameters change)."""
-        key = (self._params_key(), self.split_embed, self.split_head, self.max_chunk, self.act_fp16, self.gemm_tile)
+        key = (self._params_key(), self.split_embed, self.split_head, self.max_chunk, self.act_fp16, self.gemm_tile, self.attn_impl)
         if self._engine is None or self._engine_key != key:
             dev = self.pos_embed.device
             if dev.type != "cuda":
@@ -143,7 +144,7 @@ class SwinV2(_Base):
                                    "there is no CPU fallback")
             sd = {k: v for k, v in self.state_dict().items()}
             self._engine = Engine(sd, self.geometry, dev, self.split_embed, self.split_head, self.max_chunk,
-                                  self.act_fp16, self.gemm_tile)
+                                  self.act_fp16, self.gemm_tile, self.attn_impl)
             self._engine_key = key
         return self._engine
 
