@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SWB200_ABI_VERSION 4
+#define SWB200_ABI_VERSION 5
 #if defined(__GNUC__)
 #define SWB200_API __attribute__((visibility("default")))
 #else
@@ -87,6 +87,18 @@ typedef struct swb200_update {
   const float* fprev;
   float* out_f;
   float alpha, beta, gamma;
+  /* Rollout mode (state != NULL): the per-step glue of generate.py:120-131 (residual branch) is applied to y in the
+   * same epilogue:  X_phys = X_std*x_std + x_mean + y*d_std;  X_std <- (X_phys - x_mean)/x_std  written IN PLACE into
+   * the first out_channels channels of `state` [B, state_channels, H, W] (the condition buffer of the next step);
+   * phys (optional) receives X_phys; channel `zero_channel` (>= 0) is forced to 0 (data/era5.py zero_field).
+   * In this mode `y` of swb200_forward may be NULL. */
+  float* state;
+  int32_t state_channels;
+  int32_t zero_channel;
+  const float* x_std;
+  const float* x_mean;
+  const float* d_std;
+  float* phys;
 } swb200_update;
 
 /* ---- library ------------------------------------------------------------------------------------------ */
@@ -149,6 +161,18 @@ SWB200_API int swb200_ln_mod_residual(const float* branch, float* x, void* xb, i
  * impl: 0 auto, 1 general-shift mma.sync kernel, 2 tcgen05/TMEM/TMA kernel (shift must be a multiple of 8). */
 SWB200_API int swb200_window_attention(const void* qkv, void* out, int B, int grid_h, int grid_w, int heads, int shift_h,
                             int shift_w, int act_fp16, int impl, void* stream);
+
+/* ---- rollout glue around the sampler (generate.py:97-118), graph-capturable ------------------------------ */
+
+/* latents[b, i] ~ N(0,1): Philox4x32-10 keyed by seeds[b], counter (i/4, *step), Box-Muller.  Replaces the per-member
+ * torch.Generator of generate.py:83 / factory.py:52-56 with a stream that depends only on (seed, step, element). */
+SWB200_API int swb200_rollout_noise(float* latents, const uint64_t* seeds, const int32_t* step, int B, int64_t n_per_sample,
+                         void* stream);
+/* cond[b, state_channels + f, :] = table[*step, f, :] for f < n_forcings (standardised forcings, generate.py:100-117) */
+SWB200_API int swb200_rollout_forcings(float* cond, int total_channels, int state_channels, const float* table, int n_forcings,
+                            const int32_t* step, int B, int hw, void* stream);
+/* *step += 1 (device-side, so a captured graph of one step can be replayed for the whole rollout) */
+SWB200_API int swb200_rollout_advance(int32_t* step, void* stream);
 
 #ifdef __cplusplus
 }

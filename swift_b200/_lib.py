@@ -11,14 +11,15 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libswift_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # Every symbol ``include/swift_b200.h`` declares; tests check the library exports exactly these.
 EXPORTS = (
     "swb200_abi_version", "swb200_last_error", "swb200_validate", "swb200_workspace_bytes",
     "swb200_conditioning_scratch_bytes", "swb200_conditioning", "swb200_forward", "swb200_gemm",
     "swb200_gemm_qkv", "swb200_gemm_swiglu", "swb200_gemm_embed", "swb200_gemm_head", "swb200_patch_gather",
-    "swb200_ln_mod_residual", "swb200_window_attention",
+    "swb200_ln_mod_residual", "swb200_window_attention", "swb200_rollout_noise", "swb200_rollout_forcings",
+    "swb200_rollout_advance",
 )
 
 _i32, _f32, _vp, _sz = C.c_int32, C.c_float, C.c_void_p, C.c_size_t
@@ -39,7 +40,9 @@ class Model(C.Structure):
 
 class Update(C.Structure):
     """``struct swb200_update``: y = alpha*xt + beta*F + gamma*fprev; optional raw F output."""
-    _fields_ = [("xt", _vp), ("fprev", _vp), ("out_f", _vp), ("alpha", _f32), ("beta", _f32), ("gamma", _f32)]
+    _fields_ = [("xt", _vp), ("fprev", _vp), ("out_f", _vp), ("alpha", _f32), ("beta", _f32), ("gamma", _f32),
+                ("state", _vp), ("state_channels", _i32), ("zero_channel", _i32), ("x_std", _vp), ("x_mean", _vp),
+                ("d_std", _vp), ("phys", _vp)]
 
 
 _lock = threading.Lock()
@@ -68,6 +71,9 @@ def _declare(lib):
                                              _vp]),
         "swb200_window_attention": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                               C.c_int, _vp]),
+        "swb200_rollout_noise": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int64, _vp]),
+        "swb200_rollout_forcings": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp]),
+        "swb200_rollout_advance": (C.c_int, [_vp, _vp]),
     }
     assert set(sig) == set(EXPORTS)
     for name, (res, args) in sig.items():

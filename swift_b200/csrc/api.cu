@@ -131,7 +131,10 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
                    size_t workspace_bytes, void* stream_) {
   int rc = validate(m);
   if (rc) return rc;
-  SWB_REQUIRE(B > 0 && x0 && gain && bias && upd && y && workspace, "forward: NULL argument or B=%d", B);
+  SWB_REQUIRE(B > 0 && x0 && gain && bias && upd && workspace, "forward: NULL argument or B=%d", B);
+  SWB_REQUIRE(y != nullptr || upd->state != nullptr, "forward: y may only be NULL in rollout mode (upd->state set)");
+  SWB_REQUIRE(upd->state == nullptr || (upd->x_std && upd->x_mean && upd->d_std && upd->state_channels >= m->out_channels),
+              "forward: rollout mode needs x_std / x_mean / d_std and state_channels >= out_channels");
   SWB_REQUIRE(c0 + c1 == m->in_channels && (c1 == 0 || x1 != nullptr), "forward: c0+c1=%d != in_channels=%d", c0 + c1,
               m->in_channels);
   SWB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "forward: workspace must be 1024-byte aligned");
@@ -237,7 +240,10 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
       if (u.xt) u.xt += b0 * img_out;
       if (u.fprev) u.fprev += b0 * img_out;
       if (u.out_f) u.out_f += b0 * img_out;
-      rc = swb200_gemm_head(kDefaultCG, m, hbuf, g.k_head_total, g.k_head_total, bc, &u, y + b0 * img_out, stream_);
+      if (u.state) u.state += b0 * static_cast<size_t>(u.state_channels) * m->img_h * m->img_w;
+      if (u.phys) u.phys += b0 * img_out;
+      rc = swb200_gemm_head(kDefaultCG, m, hbuf, g.k_head_total, g.k_head_total, bc, &u, y ? y + b0 * img_out : nullptr,
+                            stream_);
       if (rc) return rc;
     }
   }
@@ -296,7 +302,7 @@ SWB200_API int swb200_gemm_embed(int tile, int act_fp16, const void* A, int lda,
 
 SWB200_API int swb200_gemm_head(int tile, const swb200_model* m, const void* A, int lda, int K, int B,
                      const swb200_update* upd, float* y, void* stream) {
-  SWB_REQUIRE(m && A && upd && y, "swb200_gemm_head: NULL pointer");
+  SWB_REQUIRE(m && A && upd && (y || upd->state), "swb200_gemm_head: NULL pointer");
   const Geom g = geom(m);
   GemmParams p = base_params(B * g.tokens, m->out_channels * g.pp, K);
   p.out0 = y;
@@ -313,6 +319,13 @@ SWB200_API int swb200_gemm_head(int tile, const swb200_model* m, const void* A, 
   p.p2 = m->patch_w;
   p.gw = g.gw;
   p.tokens = g.tokens;
+  p.state = upd->state;
+  p.state_C = upd->state_channels;
+  p.x_std = upd->x_std;
+  p.x_mean = upd->x_mean;
+  p.d_std = upd->d_std;
+  p.phys = upd->phys;
+  p.zero_channel = upd->state ? upd->zero_channel : -1;
   return launch_gemm(EPI_HEAD, tile, m->act_fp16 ? 1 : 0, A, lda, m->w_head, K, p, static_cast<cudaStream_t>(stream));
 }
 
@@ -336,6 +349,27 @@ SWB200_API int swb200_window_attention(const void* qkv, void* out, int B, int gr
   SWB_REQUIRE(qkv && out, "swb200_window_attention: NULL pointer");
   return launch_window_attention(qkv, out, B, grid_h, grid_w, heads, shift_h, shift_w, act_fp16, impl,
                                  static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------------ rollout glue
+
+SWB200_API int swb200_rollout_noise(float* latents, const uint64_t* seeds, const int32_t* step, int B, int64_t n_per_sample,
+                         void* stream) {
+  SWB_REQUIRE(latents && seeds && step && B > 0, "swb200_rollout_noise: NULL pointer or B=%d", B);
+  return launch_rollout_noise(latents, reinterpret_cast<const unsigned long long*>(seeds), step, B, n_per_sample,
+                              static_cast<cudaStream_t>(stream));
+}
+
+SWB200_API int swb200_rollout_forcings(float* cond, int total_channels, int state_channels, const float* table, int n_forcings,
+                            const int32_t* step, int B, int hw, void* stream) {
+  SWB_REQUIRE(cond && table && step && B > 0, "swb200_rollout_forcings: NULL pointer or B=%d", B);
+  return launch_rollout_forcings(cond, total_channels, state_channels, table, n_forcings, step, B, hw,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+SWB200_API int swb200_rollout_advance(int32_t* step, void* stream) {
+  SWB_REQUIRE(step, "swb200_rollout_advance: NULL pointer");
+  return launch_rollout_advance(step, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

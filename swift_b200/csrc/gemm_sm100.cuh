@@ -50,6 +50,14 @@ struct GemmParams {
   float* out_f;            // raw network output F (optional)
   float alpha, beta, gamma;
   int C, H, W, p1, p2, gw, tokens;   // tokens = gh*gw per sample
+  // EPI_HEAD, rollout mode (generate.py:120-131 folded in): state != null
+  float* state;            // [B, state_C, H, W] standardised state (first C channels updated in place)
+  int state_C;
+  const float* x_std;      // [C] per-channel sigma_x, mu_x, sigma_diff
+  const float* x_mean;
+  const float* d_std;
+  float* phys;             // [B, C, H, W] physical-space state (optional)
+  int zero_channel;        // channel forced to 0 (era5.py zero_field) or -1
 };
 
 constexpr int kBlockM = 128;     // rows of A per CTA
@@ -108,6 +116,26 @@ __device__ __forceinline__ void warp_store_rows(uint8_t* g_row0, size_t pitch_by
   __syncwarp();
 }
 
+// Inverse of warp_store_rows: fetch NCH 16-byte chunks of 32 consecutive rows with full-line global loads and hand
+// every lane the chunks of its own row.
+template <int NCH>
+__device__ __forceinline__ void warp_load_rows(const uint8_t* g_row0, size_t pitch_bytes, uint4* v, uint32_t scratch,
+                                               int lane, int rows_valid, int chunks_valid) {
+  static_assert(NCH >= 1 && NCH <= 8, "one 128-byte smem row per lane");
+#pragma unroll
+  for (int it = 0; it < NCH; ++it) {
+    const int idx = it * 32 + lane;
+    const int r = idx / NCH, c = idx - r * NCH;
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    if (r < rows_valid && c < chunks_valid) q = __ldg(reinterpret_cast<const uint4*>(g_row0 + r * pitch_bytes + c * 16));
+    st_shared_v4(scratch + r * 128 + ((c ^ (r & 7)) << 4), q);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) v[c] = ld_shared_v4(scratch + lane * 128 + ((c ^ (lane & 7)) << 4));
+  __syncwarp();
+}
+
 template <int NCOL>
 __device__ __forceinline__ void tmem_load_cols(uint32_t taddr, float* v) {
   // NCOL multiple of 8: greedy x32, x16, x8 (tcgen05.ld is .sync.aligned: the warp must be converged)
@@ -157,13 +185,15 @@ __device__ __forceinline__ void epi_slot_store(const GemmParams& p, const EpiCtx
     cols_valid = cols_valid < 0 ? 0 : (cols_valid > ncol ? ncol : cols_valid);
     if (cols_valid == 0) continue;
     if constexpr (EPI == EPI_EMBED) {
-      const int row = e.row0 + e.lane;
-      if (row < p.M) {
-        const float* pr = p.pos + static_cast<size_t>(row % p.pos_rows) * p.N + n;
+      // + bias[n] + pos_embed[row % tokens, n]: 32-row blocks never straddle a sample (tokens % 32 == 0), so the
+      // warp's pos rows are contiguous and can be fetched with full-line loads
+      float pe[32];
+      const uint8_t* pg = reinterpret_cast<const uint8_t*>(p.pos + static_cast<size_t>(e.row0 % p.pos_rows) * p.N + n);
+      warp_load_rows<8>(pg, static_cast<size_t>(p.N) * 4, reinterpret_cast<uint4*>(pe), e.scratch, e.lane, e.rows_valid,
+                        cols_valid >> 2);
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < cols_valid) v[j] += __ldg(p.bias + n + j) + __ldg(pr + j);
-      }
+      for (int j = 0; j < 32; ++j)
+        if (j < cols_valid) v[j] += __ldg(p.bias + n + j) + pe[j];
     }
     if constexpr (EPI == EPI_STORE_F32 || EPI == EPI_EMBED) {
       uint8_t* g = reinterpret_cast<uint8_t*>(static_cast<float*>(p.out0) + static_cast<size_t>(e.row0) * p.ldo + n);
@@ -249,6 +279,26 @@ __device__ __forceinline__ void epi_slot_swiglu(const GemmParams& p, const EpiCt
 }
 
 // ---- output head: packed column order is the reference's "(c p1 p2)" (models/swinv2.py:242); write NCHW directly ----
+// One element of the output image.  F is the raw network output.
+__device__ __forceinline__ void head_apply(const GemmParams& p, int b, int ch, size_t pix, float F) {
+  const size_t a = (static_cast<size_t>(b) * p.C + ch) * (static_cast<size_t>(p.H) * p.W) + pix;
+  float y = p.beta * F;
+  if (p.xt) y = fmaf(p.alpha, __ldg(p.xt + a), y);
+  if (p.fprev) y = fmaf(p.gamma, __ldg(p.fprev + a), y);
+  if (p.out0) static_cast<float*>(p.out0)[a] = y;
+  if (p.out_f) p.out_f[a] = F;
+  if (p.state) {
+    // generate.py:120-131 (residual branch): X_phys = unstd_x(X) + Y*sigma_diff;  X <- std_x(X_phys)
+    float* sp = p.state + (static_cast<size_t>(b) * p.state_C + ch) * (static_cast<size_t>(p.H) * p.W) + pix;
+    const float xs = __ldg(p.x_std + ch), xm = __ldg(p.x_mean + ch);
+    float ph = fmaf(*sp, xs, xm) + y * __ldg(p.d_std + ch);
+    float sn = (ph - xm) / xs;
+    if (ch == p.zero_channel) ph = sn = 0.f;
+    *sp = sn;
+    if (p.phys) p.phys[a] = ph;
+  }
+}
+
 __device__ __forceinline__ void epi_slot_head(const GemmParams& p, const EpiCtx& e, uint32_t tslot, int n0) {
   const int row = e.row0 + e.lane;
   const bool row_ok = row < p.M;
@@ -261,18 +311,15 @@ __device__ __forceinline__ void epi_slot_head(const GemmParams& p, const EpiCtx&
     float v[8];
     tmem_load_cols<8>(tslot + c, v);
     if (!row_ok) continue;
+    // consecutive columns walk px fastest: lanes (consecutive gx) x px form contiguous runs along the image row,
+    // so every warp access below is one contiguous 32*p2-float segment per (channel, py)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int n = n0 + c + j;
       if (n < p.N) {
         const int ch = n / pp, r = n - ch * pp;
         const int py = r / p.p2, px = r - py * p.p2;
-        const size_t a = ((static_cast<size_t>(b) * p.C + ch) * p.H + (gy * p.p1 + py)) * p.W + (gx * p.p2 + px);
-        float y = p.beta * v[j];
-        if (p.xt) y = fmaf(p.alpha, __ldg(p.xt + a), y);
-        if (p.fprev) y = fmaf(p.gamma, __ldg(p.fprev + a), y);
-        static_cast<float*>(p.out0)[a] = y;
-        if (p.out_f) p.out_f[a] = v[j];
+        head_apply(p, b, ch, static_cast<size_t>(gy * p.p1 + py) * p.W + (gx * p.p2 + px), v[j]);
       }
     }
   }

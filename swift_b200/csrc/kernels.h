@@ -38,4 +38,11 @@ int launch_window_attention(const void* qkv, void* out, int B, int gh, int gw, i
 int launch_window_attention_tc(const void* qkv, void* out, int B, int gh, int gw, int heads, int shift_h, int shift_w,
                                int act_f16, cudaStream_t stream);
 
+// rollout glue (rollout.cu)
+int launch_rollout_noise(float* latents, const unsigned long long* seeds, const int* step, int B,
+                         long long n_per_sample, cudaStream_t stream);
+int launch_rollout_forcings(float* cond, int total_ch, int state_ch, const float* table, int n_forc, const int* step,
+                            int B, int hw, cudaStream_t stream);
+int launch_rollout_advance(int* step, cudaStream_t stream);
+
 }  // namespace swb

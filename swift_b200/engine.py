@@ -97,8 +97,11 @@ class Engine:
     def forward(self, x0: torch.Tensor, x1: Optional[torch.Tensor], gain: torch.Tensor, bias: torch.Tensor,
                 out: Optional[torch.Tensor] = None, scale0: float = 1.0, xt: Optional[torch.Tensor] = None,
                 fprev: Optional[torch.Tensor] = None, out_f: Optional[torch.Tensor] = None, alpha: float = 0.0,
-                beta: float = 1.0, gamma: float = 0.0) -> torch.Tensor:
-        """F = SwinV2(cat([x0*scale0, x1], 1));  returns  alpha*xt + beta*F + gamma*fprev  (NCHW fp32)."""
+                beta: float = 1.0, gamma: float = 0.0, rollout: Optional["RolloutGlue"] = None) -> Optional[torch.Tensor]:
+        """F = SwinV2(cat([x0*scale0, x1], 1));  returns  y = alpha*xt + beta*F + gamma*fprev  (NCHW fp32).
+
+        With ``rollout`` the per-step glue of generate.py:120-131 is applied to y in the head epilogue (state updated
+        in place, physical state written to ``rollout.phys``) and y itself is not materialised (returns None)."""
         g = self.geom
         self._check_f32(x0, "x0")
         B, c0 = x0.shape[0], x0.shape[1]
@@ -118,12 +121,44 @@ class Engine:
                 self._check_f32(tns, nm)
                 if tuple(tns.shape) != (B, *self.out_shape):
                     raise RuntimeError(f"{nm} must be {(B, *self.out_shape)}, got {tuple(tns.shape)}")
-        if out is None:
-            out = torch.empty(B, *self.out_shape, device=self.device, dtype=torch.float32)
         upd = _lib.Update(_lib.ptr(xt), _lib.ptr(fprev), _lib.ptr(out_f), alpha, beta, gamma)
+        if rollout is not None:
+            rollout.check(self, B)
+            upd.state, upd.state_channels = rollout.state.data_ptr(), rollout.state.shape[1]
+            upd.zero_channel = rollout.zero_channel
+            upd.x_std, upd.x_mean, upd.d_std = (rollout.x_std.data_ptr(), rollout.x_mean.data_ptr(),
+                                                rollout.d_std.data_ptr())
+            upd.phys = _lib.ptr(rollout.phys)
+        elif out is None:
+            out = torch.empty(B, *self.out_shape, device=self.device, dtype=torch.float32)
         ws, ws_bytes = self.workspace(B)
         _lib.check(self.lib.swb200_forward(C.byref(self.model), x0.data_ptr(), c0, scale0, _lib.ptr(x1), c1, B,
-                                           gain.data_ptr(), bias.data_ptr(), C.byref(upd), out.data_ptr(), ws,
+                                           gain.data_ptr(), bias.data_ptr(), C.byref(upd), _lib.ptr(out), ws,
                                            ws_bytes, self._stream()), "forward")
         self.launches += self.launches_per_forward(B)
         return out
+
+
+class RolloutGlue:
+    """Buffers of the fused rollout epilogue: ``state`` [B, C_state, H, W] (standardised condition buffer, first
+    out_channels channels updated in place), per-channel normalisers [C] and the optional physical output."""
+
+    def __init__(self, state: torch.Tensor, x_std: torch.Tensor, x_mean: torch.Tensor, d_std: torch.Tensor,
+                 phys: Optional[torch.Tensor] = None, zero_channel: int = -1):
+        self.state, self.phys, self.zero_channel = state, phys, int(zero_channel)
+        self.x_std, self.x_mean, self.d_std = (t.reshape(-1).to(torch.float32).contiguous() for t in (x_std, x_mean, d_std))
+
+    def check(self, eng: "Engine", B: int) -> None:
+        C_out = eng.geom.out_channels
+        Engine._check_f32(self.state, "rollout state")
+        if self.state.shape[0] != B or self.state.shape[1] < C_out or tuple(self.state.shape[2:]) != eng.geom.img:
+            raise RuntimeError(f"rollout state {tuple(self.state.shape)} does not match batch {B} / model output")
+        for nm in ("x_std", "x_mean", "d_std"):
+            t = getattr(self, nm)
+            Engine._check_f32(t, nm)
+            if t.numel() != C_out:
+                raise RuntimeError(f"{nm} must have {C_out} entries")
+        if self.phys is not None:
+            Engine._check_f32(self.phys, "phys")
+            if tuple(self.phys.shape) != (B, *eng.out_shape):
+                raise RuntimeError(f"phys must be {(B, *eng.out_shape)}")

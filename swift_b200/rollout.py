@@ -9,23 +9,30 @@ Per 6 h step and trajectory (member m, initial condition j) the reference does (
     rollout[:, i+1] = X_phys.cpu()                                :129
     X      <- standardize_x(X_phys)                               :131
 
-Differences, all documented in DESIGN.md:
+Here the whole step is six kinds of kernels and no PyTorch op: counter-based latents, forcings copy into the condition
+buffer, the denoiser (patch gather fuses the concat, the head epilogue fuses the sCM update AND the affine glue above,
+updating the state in place), and a device-side step counter -- so one captured CUDA graph is replayed for every step.
+
+Differences from the reference, all documented in DESIGN.md:
   * trajectories are sharded by flattened (IC, member) index over ranks (the reference shards by member only and
     leaves 4 of 8 ranks half idle for 12 members); no collective is needed on the forecast path;
-  * every trajectory owns its noise stream, ``torch.Generator(device).manual_seed(seed_of(m, j))``, so a
-    trajectory's result does not depend on world size or batching (the reference's per-member generator is consumed
-    in batch order);
+  * every trajectory owns its noise stream: Philox4x32-10 keyed by ``trajectory_seed(member, ic)`` with counter
+    (element, step), so a trajectory's result does not depend on world size or batching (the reference's per-member
+    ``torch.Generator`` is consumed in batch order);
   * forcings are pre-staged on the device as a [steps, n_forcings, H, W] table instead of one HDF5 read per sample
     per step on the main thread.
 """
 from __future__ import annotations
 
+import ctypes as C
 from dataclasses import dataclass
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
 
-from .sampler import DiffusionSampler
+from . import _lib
+from .engine import RolloutGlue
+from .sampler import DiffusionSampler, _fused_target
 
 
 def shard_trajectories(members: int, n_ic: int, rank: int, world: int) -> List[Tuple[int, int]]:
@@ -39,7 +46,7 @@ def shard_trajectories(members: int, n_ic: int, rank: int, world: int) -> List[T
 
 
 def trajectory_seed(member: int, ic: int) -> int:
-    """Seed of the (member, ic) noise stream; member m of every IC shares the reference's ``manual_seed(m)`` family."""
+    """Key of the (member, ic) noise stream (member m of every IC extends the reference's ``manual_seed(m)`` family)."""
     return member + 1_000_003 * ic
 
 
@@ -49,6 +56,7 @@ class Normalizers:
     x_mean: torch.Tensor      # variables only
     x_std: torch.Tensor
     diff_std: torch.Tensor    # t_stds[interval] (t_means are zero for residual targets)
+    zero_channel: int = -1    # index of sea_surface_temperature when delta != 24 (era5.py zero_field), else -1
 
     @staticmethod
     def synthetic(n_var: int, device, diff: float = 0.1) -> "Normalizers":
@@ -60,10 +68,10 @@ class EnsembleRollout:
     """Advances a batch of independent trajectories that live on one GPU."""
 
     def __init__(self, net, norm: Normalizers, forcings_std: torch.Tensor, trajectories: Sequence[Tuple[int, int]],
-                 solver: str = "scm", solver_kwargs: Optional[dict] = None):
+                 solver: str = "scm", solver_kwargs: Optional[dict] = None, use_graph: bool = True):
         self.net = net
         self.norm = norm
-        self.forcings = forcings_std              # [steps(+), n_forc, H, W] standardised, on device
+        self.forcings = forcings_std.contiguous()   # [steps(+), n_forc, H, W] standardised, on device
         self.traj = list(trajectories)
         self.device = forcings_std.device
         self.diffusion = DiffusionSampler(net)
@@ -76,41 +84,114 @@ class EnsembleRollout:
             self._solve = self.diffusion.dpm_solver_2s
         else:
             raise ValueError(f"Unknown solver mode: {solver}")
-        self.generators = [torch.Generator(device=self.device).manual_seed(trajectory_seed(m, j))
-                           for m, j in self.traj]
         inner = getattr(net, "module", net)
         self.n_var = inner.img_channels
         self.res = tuple(int(v) for v in inner.img_resolution)
+        self.sigma_data = float(inner.sigma_data)
         B = len(self.traj)
-        n_forc = forcings_std.shape[1]
-        self.cond = torch.empty(B, self.n_var + n_forc, *self.res, device=self.device)
+        n_forc = self.forcings.shape[1]
+        self.cond = torch.zeros(B, self.n_var + n_forc, *self.res, device=self.device)
         self.latents = torch.empty(B, self.n_var, *self.res, device=self.device)
+        self.phys = torch.empty(B, self.n_var, *self.res, device=self.device)
+        self.seeds = torch.tensor([trajectory_seed(m, j) for m, j in self.traj], dtype=torch.int64, device=self.device)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.lib = _lib.lib()
+        self.model = _fused_target(net)
+        # the single-kernel-sequence step: 1-step sCM through the fused CUDA entry point
+        self.fused = self.model is not None and solver == "scm" and kw["num_steps"] == 1
+        self.use_graph = use_graph and self.fused
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._glue = RolloutGlue(self.cond, norm.x_std, norm.x_mean, norm.diff_std, self.phys, norm.zero_channel)
+        self._cond_vecs = None
 
-    def set_state(self, x_std: torch.Tensor) -> None:
+    # ------------------------------------------------------------------ state
+    def set_state(self, x_std: torch.Tensor, step: int = 0) -> None:
         """x_std: [B, n_var, H, W] standardised initial conditions, one row per trajectory."""
         self.cond[:, : self.n_var].copy_(x_std)
+        self.step_dev.fill_(step)
+
+    # ------------------------------------------------------------------ pieces of one step
+    def _stream(self) -> int:
+        return torch.cuda.current_stream().cuda_stream
 
     def draw_latents(self) -> torch.Tensor:
-        for b, g in enumerate(self.generators):
-            self.latents[b].normal_(generator=g)          # == torch.randn(..., generator=g) (factory.py:52-56)
+        n = self.latents[0].numel()
+        _lib.check(self.lib.swb200_rollout_noise(self.latents.data_ptr(), self.seeds.data_ptr(),
+                                                 self.step_dev.data_ptr(), len(self.traj), n, self._stream()), "noise")
         return self.latents
 
+    def _load_forcings(self) -> None:
+        hw = self.res[0] * self.res[1]
+        _lib.check(self.lib.swb200_rollout_forcings(self.cond.data_ptr(), self.cond.shape[1], self.n_var,
+                                                    self.forcings.data_ptr(), self.forcings.shape[1],
+                                                    self.step_dev.data_ptr(), len(self.traj), hw, self._stream()),
+                   "forcings")
+
+    def _advance(self) -> None:
+        _lib.check(self.lib.swb200_rollout_advance(self.step_dev.data_ptr(), self._stream()), "advance")
+
+    def _fused_step(self) -> None:
+        """noise -> forcings -> denoiser (+ sCM update + affine glue in the head epilogue) -> step += 1."""
+        eng = self.model.engine()
+        t = torch.tensor([torch.pi / 2])                     # diffusion.py:435-436 (fp32 pi/2)
+        cos_t, sin_t = float(torch.cos(t)), float(torch.sin(t))
+        self.draw_latents()
+        self._load_forcings()
+        gain, bias = self._cond_vecs
+        sd = self.sigma_data
+        x_in = self.latents
+        if sd != 1.0:
+            x_in.mul_(sd)                                    # x_t = latents * sigma_d (diffusion.py:452)
+        eng.forward(x_in, self.cond, gain, bias, scale0=1.0 / sd, xt=x_in, alpha=cos_t, beta=-sin_t * sd,
+                    rollout=self._glue)
+        self._advance()
+        eng.launches += 3
+
     @torch.no_grad()
-    def step(self, i: int, forcings_i: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """One 6 h advance of every trajectory; returns the physical state [B, n_var, H, W]."""
-        f = self.forcings[i] if forcings_i is None else forcings_i
-        self.cond[:, self.n_var:].copy_(f.unsqueeze(0).expand(self.cond.shape[0], -1, -1, -1) if f.dim() == 3 else f)
-        y = self._solve(latents=self.draw_latents(), condition=self.cond, **self.solver_kwargs)
+    def step(self, forcings_i: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One 6 h advance of every trajectory; returns the physical state [B, n_var, H, W] (a view of a static
+        buffer that the next step overwrites)."""
+        if self.fused and forcings_i is None:
+            if self._cond_vecs is None:
+                self._cond_vecs = self.diffusion._conditioning(self.model, float(torch.tensor([torch.pi / 2])),
+                                                               self.solver_kwargs["auxiliary"], len(self.traj),
+                                                               self.device)
+            if not self.use_graph:
+                self._fused_step()
+            else:
+                if self._graph is None:
+                    self.model.engine().workspace(len(self.traj))        # allocate before capture
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._fused_step()
+                    self._graph = g          # capture does not execute: the replay below is the first real step
+                self._graph.replay()
+                self.model.engine().launches += self.model.engine().launches_per_forward(len(self.traj)) + 3
+            return self.phys
+        # generic path (multi-step sCM, 2S, non-fused nets, externally supplied forcings)
+        if forcings_i is None:
+            self._load_forcings()
+        else:
+            f = forcings_i
+            self.cond[:, self.n_var:].copy_(f.unsqueeze(0).expand(self.cond.shape[0], -1, -1, -1) if f.dim() == 3 else f)
+        kw = {k: v for k, v in self.solver_kwargs.items()}
+        y = self._solve(latents=self.draw_latents(), condition=self.cond, **kw)
         x_std = self.cond[:, : self.n_var]
         x_phys = torch.addcmul(x_std * self.norm.x_std + self.norm.x_mean, y, self.norm.diff_std)
-        x_std.copy_((x_phys - self.norm.x_mean) / self.norm.x_std)
-        return x_phys
+        x_new = (x_phys - self.norm.x_mean) / self.norm.x_std
+        if self.norm.zero_channel >= 0:
+            x_phys[:, self.norm.zero_channel] = 0
+            x_new[:, self.norm.zero_channel] = 0
+        x_std.copy_(x_new)
+        self.phys.copy_(x_phys)
+        self._advance()
+        return self.phys
 
     @torch.no_grad()
     def run(self, steps: int, on_step: Optional[Callable[[int, torch.Tensor], None]] = None) -> torch.Tensor:
-        x_phys = None
         for i in range(steps):
-            x_phys = self.step(i)
+            x_phys = self.step()
             if on_step is not None:
                 on_step(i, x_phys)
-        return x_phys
+        return self.phys

@@ -1,0 +1,56 @@
+"""Host-side multi-GPU logic on CPU: (member, IC) sharding and the gloo rendezvous / max-over-ranks pattern bench.py
+uses (world_size 2, backend gloo)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from swift_b200.rollout import shard_trajectories, trajectory_seed
+
+
+@pytest.mark.parametrize("members,n_ic,world", [(12, 8, 1), (12, 64, 8), (12, 16, 2), (5, 3, 4), (3, 1, 8)])
+def test_shards_partition_all_trajectories(members, n_ic, world):
+    shards = [shard_trajectories(members, n_ic, r, world) for r in range(world)]
+    flat = [t for s in shards for t in s]
+    assert sorted(flat) == sorted((m, j) for j in range(n_ic) for m in range(members))
+    assert len(set(flat)) == members * n_ic
+    assert max(len(s) for s in shards) - min(len(s) for s in shards) <= 1          # balanced (the reference: 2 vs 1 members)
+    if n_ic % world == 0:                                                           # members of an IC stay together
+        for s in shards:
+            assert all(sum(1 for m, j in s if j == jj) == members for jj in {j for _, j in s})
+    assert len({trajectory_seed(m, j) for m, j in flat}) == len(flat)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = shard_trajectories(12, 8, rank, world)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    t = torch.tensor([10.0 + 5.0 * rank], dtype=torch.float64)           # "elapsed ms" of this rank
+    dist.barrier()
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        q.put((gathered, float(t.item())))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_barrier_and_max_reduce():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    gathered, tmax = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert tmax == 15.0                                                   # max over ranks, as bench.py reports
+    assert sorted(gathered[0] + gathered[1]) == sorted((m, j) for j in range(8) for m in range(12))
+    assert len(gathered[0]) == len(gathered[1]) == 48
