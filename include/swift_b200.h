@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SWB200_ABI_VERSION 5
+#define SWB200_ABI_VERSION 6
 #if defined(__GNUC__)
 #define SWB200_API __attribute__((visibility("default")))
 #else
@@ -154,9 +154,10 @@ SWB200_API int swb200_gemm_head(int tile, const swb200_model* m, const void* A, 
 /* cat + patchify + bf16 cast (+ hi/lo split): A[B*tokens, lda] */
 SWB200_API int swb200_patch_gather(const swb200_model* m, const float* x0, int c0, float scale0, const float* x1, int c1, int B,
                         void* A, int lda, void* stream);
-/* x += LN(branch)*gain[b] + bias[b]; xb = bf16(x) (pitch ldxb); xlo optional (same pitch). */
-SWB200_API int swb200_ln_mod_residual(const float* branch, float* x, void* xb, int ldxb, void* xlo, const float* gain,
-                           const float* bias, int M, int dim, int tokens, int act_fp16, void* stream);
+/* x += LN(branch)*gain[b] + bias[b]; xb = 16-bit copy of x (pitch ldxb); xlo optional (same pitch).
+ * branch is fp32 [M, dim], or the 16-bit operand format when branch_16bit. */
+SWB200_API int swb200_ln_mod_residual(const void* branch, int branch_16bit, float* x, void* xb, int ldxb, void* xlo,
+                           const float* gain, const float* bias, int M, int dim, int tokens, int act_fp16, void* stream);
 /* shifted-window cosine attention on the packed qkv buffer; out 16-bit [M, heads*88].
  * impl: 0 auto, 1 general-shift mma.sync kernel, 2 tcgen05/TMEM/TMA kernel (shift must be a multiple of 8). */
 SWB200_API int swb200_window_attention(const void* qkv, void* out, int B, int grid_h, int grid_w, int heads, int shift_h,

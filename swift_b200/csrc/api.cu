@@ -162,7 +162,11 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
     void* qkv = ws + w.qkv;
     void* a_emb = qkv;
     void* attn = ws + w.attn;
-    float* branch = reinterpret_cast<float*>(ws + w.branch);
+    void* branch = ws + w.branch;
+    // fp16 mode: the wo / w2 branch outputs are stored in fp16 (saturated); bf16 mode keeps them in fp32 because the
+    // extra bf16 rounding in front of the LayerNorm costs ~10 % accuracy
+    const int BR16 = F16;
+    const int epi_branch = BR16 ? EPI_STORE_ACT : EPI_STORE_F32;
     void* hbuf = ws + w.h;
 
     // 1. concat + patchify + cast
@@ -203,10 +207,10 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
         p.out0 = branch;
         p.ldo = D;
         const auto* wo = static_cast<const __nv_bfloat16*>(m->w_o) + static_cast<size_t>(l) * D * D;
-        rc = launch_gemm(EPI_STORE_F32, kDefaultCG, F16, attn, D, wo, D, p, stream);
+        rc = launch_gemm(epi_branch, kDefaultCG, F16, attn, D, wo, D, p, stream);
         if (rc) return rc;
       }
-      rc = launch_ln_mod_residual(branch, x, xb, D, nullptr, gain + (static_cast<size_t>(2 * l) * B + b0) * D,
+      rc = launch_ln_mod_residual(branch, BR16, x, xb, D, nullptr, gain + (static_cast<size_t>(2 * l) * B + b0) * D,
                                   bias + (static_cast<size_t>(2 * l) * B + b0) * D, M, D, g.tokens, 1e-6f, F16, stream);
       if (rc) return rc;
       {
@@ -222,7 +226,7 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
         p.out0 = branch;
         p.ldo = D;
         const auto* w2 = static_cast<const __nv_bfloat16*>(m->w_2) + static_cast<size_t>(l) * D * Dff;
-        rc = launch_gemm(EPI_STORE_F32, kDefaultCG, F16, hbuf, Dff, w2, Dff, p, stream);
+        rc = launch_gemm(epi_branch, kDefaultCG, F16, hbuf, Dff, w2, Dff, p, stream);
         if (rc) return rc;
       }
       const bool last = (l == m->depth - 1);
@@ -230,7 +234,7 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
       void* xb_dst = last ? hbuf : xb;
       const int ldxb = last ? g.k_head_total : D;
       void* xlo = (last && m->split_head) ? static_cast<void*>(static_cast<__nv_bfloat16*>(hbuf) + D) : nullptr;
-      rc = launch_ln_mod_residual(branch, x, xb_dst, ldxb, xlo, gain + (static_cast<size_t>(2 * l + 1) * B + b0) * D,
+      rc = launch_ln_mod_residual(branch, BR16, x, xb_dst, ldxb, xlo, gain + (static_cast<size_t>(2 * l + 1) * B + b0) * D,
                                   bias + (static_cast<size_t>(2 * l + 1) * B + b0) * D, M, D, g.tokens, 1e-6f, F16, stream);
       if (rc) return rc;
     }
@@ -242,7 +246,9 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
       if (u.out_f) u.out_f += b0 * img_out;
       if (u.state) u.state += b0 * static_cast<size_t>(u.state_channels) * m->img_h * m->img_w;
       if (u.phys) u.phys += b0 * img_out;
-      rc = swb200_gemm_head(kDefaultCG, m, hbuf, g.k_head_total, g.k_head_total, bc, &u, y ? y + b0 * img_out : nullptr,
+      // few output columns (276 for Swift-B): the 176-wide tile gives twice as many tiles to spread over the SMs
+      rc = swb200_gemm_head(kDefaultCG == 3 ? 2 : kDefaultCG, m, hbuf, g.k_head_total, g.k_head_total, bc, &u,
+                            y ? y + b0 * img_out : nullptr,
                             stream_);
       if (rc) return rc;
     }
@@ -337,10 +343,10 @@ SWB200_API int swb200_patch_gather(const swb200_model* m, const float* x0, int c
                              m->patch_h, m->patch_w, static_cast<cudaStream_t>(stream));
 }
 
-SWB200_API int swb200_ln_mod_residual(const float* branch, float* x, void* xb, int ldxb, void* xlo, const float* gain,
-                           const float* bias, int M, int dim, int tokens, int act_fp16, void* stream) {
+SWB200_API int swb200_ln_mod_residual(const void* branch, int branch_16bit, float* x, void* xb, int ldxb, void* xlo,
+                           const float* gain, const float* bias, int M, int dim, int tokens, int act_fp16, void* stream) {
   SWB_REQUIRE(branch && x && xb && gain && bias, "swb200_ln_mod_residual: NULL pointer");
-  return launch_ln_mod_residual(branch, x, xb, ldxb, xlo, gain, bias, M, dim, tokens, 1e-6f, act_fp16,
+  return launch_ln_mod_residual(branch, branch_16bit, x, xb, ldxb, xlo, gain, bias, M, dim, tokens, 1e-6f, act_fp16,
                                 static_cast<cudaStream_t>(stream));
 }
 

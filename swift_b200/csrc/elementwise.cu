@@ -17,7 +17,7 @@ namespace swb {
 // patch-embed weight once at pack time, which makes the gather write 2*p1*p2-byte runs per channel.
 // SPLIT writes a second operand half lo = bf16(x - float(bf16(x))) at column offset Kp so that
 // [hi | lo] * [W | W]^T reproduces the fp32 input to ~2^-17 relative instead of 2^-9.
-constexpr int kGatherCh = 8;
+constexpr int kGatherCh = 16;   // channels staged per pass: 16 * p1*p2 output elements (128 B for 2x2 patches) per token
 
 template <bool SPLIT, bool F16>
 __global__ void __launch_bounds__(256) patch_gather_kernel(const float* __restrict__ src0, int C0, float scale0,
@@ -33,6 +33,8 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const float* __restri
   const int cvirt = (Kp + pp - 1) / pp;            // channels >= C are virtual zero padding up to Kp
   const int nchunks = (cvirt + kGatherCh - 1) / kGatherCh;
   const size_t row_base = (static_cast<size_t>(b) * gh + gy) * gw;
+  const int kchunk = kGatherCh * pp;               // output elements per token per pass (multiple of 8)
+  const int groups = kchunk / 8;                   // 16-byte groups per token per pass
   for (int chunk = 0; chunk < nchunks; ++chunk) {
     const int c0 = chunk * kGatherCh;
     __syncthreads();
@@ -48,19 +50,30 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const float* __restri
       tile[r * pitch + xw] = v;
     }
     __syncthreads();
-    const int kchunk = kGatherCh * pp;
-    for (int idx = threadIdx.x; idx < gw * kchunk; idx += blockDim.x) {
-      const int kl = idx % kchunk, gx = idx / kchunk;
-      const int c = kl / pp, r = kl % pp;
-      const int py = r / p2, px = r % p2;
-      const int k = (c0 + c) * pp + r;
-      if (k < Kp) {
-        const float v = tile[(c * p1 + py) * pitch + gx * p2 + px];
-        const uint16_t hi = pack_act1<F16>(v);
-        uint16_t* dst = A + (row_base + gx) * lda + k;
-        *dst = hi;
-        if (SPLIT) dst[Kp] = pack_act1<F16>(v - unpack_act1<F16>(hi));
+    // one 16-byte store (8 consecutive k) per thread: consecutive threads cover consecutive groups of one token
+    for (int idx = threadIdx.x; idx < gw * groups; idx += blockDim.x) {
+      const int q = idx % groups, gx = idx / groups;
+      const int k0 = c0 * pp + q * 8;
+      if (k0 >= Kp) continue;                       // Kp is a multiple of 8
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int kl = q * 8 + j;
+        const int c = kl / pp, r = kl - c * pp;
+        const int py = r / p2, px = r - py * p2;
+        v[j] = tile[(c * p1 + py) * pitch + gx * p2 + px];
       }
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        hi[j] = pack_act2<F16>(v[2 * j], v[2 * j + 1]);
+        if (SPLIT)
+          lo[j] = pack_act2<F16>(v[2 * j] - unpack_act1<F16>(static_cast<uint16_t>(hi[j] & 0xffffu)),
+                                 v[2 * j + 1] - unpack_act1<F16>(static_cast<uint16_t>(hi[j] >> 16)));
+      }
+      uint16_t* dst = A + (row_base + gx) * lda + k0;
+      *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      if (SPLIT) *reinterpret_cast<uint4*>(dst + Kp) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
   }
 }
@@ -68,7 +81,10 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const float* __restri
 int launch_patch_gather(const float* src0, int C0, float scale0, const float* src1, int C1, void* A, int lda, int Kp,
                         int split, int act_f16, int B, int H, int W, int p1, int p2, cudaStream_t stream) {
   SWB_REQUIRE(H % p1 == 0 && W % p2 == 0, "patch_gather: image %dx%d not divisible by patch %dx%d", H, W, p1, p2);
-  SWB_REQUIRE(Kp >= (C0 + C1) * p1 * p2, "patch_gather: Kp=%d < C*p1*p2=%d", Kp, (C0 + C1) * p1 * p2);
+  SWB_REQUIRE(Kp >= (C0 + C1) * p1 * p2 && Kp % 8 == 0 && lda % 8 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0,
+              "patch_gather: need Kp=%d >= C*p1*p2=%d, Kp and lda multiples of 8, A 16-byte aligned", Kp,
+              (C0 + C1) * p1 * p2);
+  SWB_REQUIRE((kGatherCh * p1 * p2) % 8 == 0, "patch_gather: patch %dx%d unsupported", p1, p2);
   const size_t smem = static_cast<size_t>(kGatherCh) * p1 * (W + 2) * sizeof(float);
   SWB_REQUIRE(smem <= 48 * 1024, "patch_gather: image width %d too large for the staging tile", W);
   dim3 grid(H / p1, B);
@@ -92,8 +108,10 @@ int launch_patch_gather(const float* src0, int C0, float scale0, const float* sr
 // (swinv2.py:211-212).  gain = gamma*(1+scale(t)), bias = beta*(1+scale(t)) + shift(t) are folded per sample
 // by mod_finalize_kernel.  One warp per token row; the row lives in registers (two-pass mean/variance in fp32);
 // accesses are 16-byte per lane, lane-strided (512 contiguous bytes per warp request).
-template <int NV4, bool F16>
-__global__ void __launch_bounds__(128) ln_mod_residual_kernel(const float* __restrict__ branch, float* __restrict__ x,
+// BR16: the branch is stored in the 16-bit operand format (fp16 mode: halves the epilogue store of the wo / w2 GEMMs
+// and this kernel's branch read) instead of fp32.
+template <int NV4, bool F16, bool BR16>
+__global__ void __launch_bounds__(128) ln_mod_residual_kernel(const void* __restrict__ branch_, float* __restrict__ x,
                                                               uint16_t* __restrict__ xb, int ldxb,
                                                               uint16_t* __restrict__ xlo,
                                                               const float* __restrict__ gain,
@@ -103,15 +121,31 @@ __global__ void __launch_bounds__(128) ln_mod_residual_kernel(const float* __res
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
   const int nv = D >> 2;                                   // float4 per row
-  const float4* br = reinterpret_cast<const float4*>(branch + static_cast<size_t>(row) * D);
   float4* xr = reinterpret_cast<float4*>(x + static_cast<size_t>(row) * D);
   // every global load of the row (branch AND residual) is issued before the first use: 2*NV4 independent
-  // 512-byte warp requests in flight per warp
+  // warp requests in flight per warp
   float4 v[NV4], xv[NV4];
+  if constexpr (BR16) {
+    const uint2* br = reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(branch_) + static_cast<size_t>(row) * D);
+    uint2 raw[NV4];
 #pragma unroll
-  for (int i = 0; i < NV4; ++i) {
-    const int c = i * 32 + lane;
-    v[i] = (c < nv) ? __ldg(br + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < NV4; ++i) {
+      const int c = i * 32 + lane;
+      raw[i] = (c < nv) ? __ldg(br + c) : make_uint2(0u, 0u);
+    }
+#pragma unroll
+    for (int i = 0; i < NV4; ++i)
+      v[i] = make_float4(unpack_act1<F16>(static_cast<uint16_t>(raw[i].x & 0xffffu)),
+                         unpack_act1<F16>(static_cast<uint16_t>(raw[i].x >> 16)),
+                         unpack_act1<F16>(static_cast<uint16_t>(raw[i].y & 0xffffu)),
+                         unpack_act1<F16>(static_cast<uint16_t>(raw[i].y >> 16)));
+  } else {
+    const float4* br = reinterpret_cast<const float4*>(static_cast<const float*>(branch_) + static_cast<size_t>(row) * D);
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int c = i * 32 + lane;
+      v[i] = (c < nv) ? __ldg(br + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
 #pragma unroll
   for (int i = 0; i < NV4; ++i) {
@@ -164,8 +198,9 @@ __global__ void __launch_bounds__(128) ln_mod_residual_kernel(const float* __res
   }
 }
 
-int launch_ln_mod_residual(const float* branch, float* x, void* xb, int ldxb, void* xlo, const float* gain,
-                           const float* bias, int M, int D, int tokens, float eps, int act_f16, cudaStream_t stream) {
+int launch_ln_mod_residual(const void* branch, int branch_16bit, float* x, void* xb, int ldxb, void* xlo,
+                           const float* gain, const float* bias, int M, int D, int tokens, float eps, int act_f16,
+                           cudaStream_t stream) {
   SWB_REQUIRE(D % 4 == 0 && ldxb % 4 == 0, "ln_mod_residual: dim %d and pitch %d must be multiples of 4", D, ldxb);
   SWB_REQUIRE(((reinterpret_cast<uintptr_t>(branch) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gain) |
                 reinterpret_cast<uintptr_t>(bias)) & 15) == 0 &&
@@ -175,14 +210,15 @@ int launch_ln_mod_residual(const float* branch, float* x, void* xb, int ldxb, vo
   dim3 grid((M + rows_per_block - 1) / rows_per_block);
   auto xb_ = static_cast<uint16_t*>(xb);
   auto xlo_ = static_cast<uint16_t*>(xlo);
-#define SWB_LN(V)                                                                                                  \
-  do {                                                                                                             \
-    if (act_f16)                                                                                                   \
-      ln_mod_residual_kernel<V, true><<<grid, 128, 0, stream>>>(branch, x, xb_, ldxb, xlo_, gain, bias, M, D, tokens, \
-                                                                eps);                                              \
-    else                                                                                                           \
-      ln_mod_residual_kernel<V, false><<<grid, 128, 0, stream>>>(branch, x, xb_, ldxb, xlo_, gain, bias, M, D,      \
-                                                                 tokens, eps);                                     \
+#define SWB_LN3(V, F, R) \
+  ln_mod_residual_kernel<V, F, R><<<grid, 128, 0, stream>>>(branch, x, xb_, ldxb, xlo_, gain, bias, M, D, tokens, eps)
+#define SWB_LN(V)                                                   \
+  do {                                                              \
+    if (act_f16) {                                                  \
+      if (branch_16bit) SWB_LN3(V, true, true); else SWB_LN3(V, true, false);   \
+    } else {                                                        \
+      if (branch_16bit) SWB_LN3(V, false, true); else SWB_LN3(V, false, false); \
+    }                                                               \
   } while (0)
   const int nv4 = (D / 4 + 31) / 32;
   if (nv4 <= 3) SWB_LN(3);
@@ -194,6 +230,7 @@ int launch_ln_mod_residual(const float* branch, float* x, void* xb, int ldxb, vo
     return SWB_ERR_INVALID;
   }
 #undef SWB_LN
+#undef SWB_LN3
   SWB_CHECK_CUDA(cudaGetLastError());
   return SWB_OK;
 }

@@ -71,22 +71,25 @@ def test_patch_gather(lib, split, p1, p2, C0, C1, H, W, f16):
 
 
 @ACT
+@pytest.mark.parametrize("br16", [0, 1], ids=["branch_fp32", "branch_16bit"])
 @pytest.mark.parametrize("D", [264, 528, 1056])
 @pytest.mark.parametrize("with_lo", [False, True])
-def test_ln_mod_residual(lib, D, with_lo, f16):
+def test_ln_mod_residual(lib, D, with_lo, f16, br16):
     dt = _adt(f16)
     B, T = 3, 256
     M = B * T
     branch = torch.randn(M, D, device="cuda") * 3 + 0.7
+    if br16:
+        branch = branch.to(dt)
     x = torch.randn(M, D, device="cuda")
     gain = torch.randn(B, D, device="cuda")
     bias = torch.randn(B, D, device="cuda")
     ldxb = 2 * D if with_lo else D
     xb = torch.zeros(M, ldxb, device="cuda", dtype=dt)
-    x_ref = x + torch.nn.functional.layer_norm(branch, (D,), eps=1e-6).reshape(B, T, D).mul(gain[:, None]).add(
+    x_ref = x + torch.nn.functional.layer_norm(branch.float(), (D,), eps=1e-6).reshape(B, T, D).mul(gain[:, None]).add(
         bias[:, None]).reshape(M, D)
     xlo_ptr = xb.data_ptr() + 2 * D if with_lo else None
-    _check(lib.swb200_ln_mod_residual(branch.data_ptr(), x.data_ptr(), xb.data_ptr(), ldxb, xlo_ptr, gain.data_ptr(),
+    _check(lib.swb200_ln_mod_residual(branch.data_ptr(), br16, x.data_ptr(), xb.data_ptr(), ldxb, xlo_ptr, gain.data_ptr(),
                                       bias.data_ptr(), M, D, T, f16, _stream()))
     torch.cuda.synchronize()
     assert _rel(x, x_ref) < 2e-6, f"{_rel(x, x_ref):.3e}"
