@@ -246,9 +246,7 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
       if (u.out_f) u.out_f += b0 * img_out;
       if (u.state) u.state += b0 * static_cast<size_t>(u.state_channels) * m->img_h * m->img_w;
       if (u.phys) u.phys += b0 * img_out;
-      // few output columns (276 for Swift-B): the 176-wide tile gives twice as many tiles to spread over the SMs
-      rc = swb200_gemm_head(kDefaultCG == 3 ? 2 : kDefaultCG, m, hbuf, g.k_head_total, g.k_head_total, bc, &u,
-                            y ? y + b0 * img_out : nullptr,
+      rc = swb200_gemm_head(kDefaultCG, m, hbuf, g.k_head_total, g.k_head_total, bc, &u, y ? y + b0 * img_out : nullptr,
                             stream_);
       if (rc) return rc;
     }

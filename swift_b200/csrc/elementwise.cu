@@ -35,9 +35,10 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const float* __restri
   const size_t row_base = (static_cast<size_t>(b) * gh + gy) * gw;
   const int kchunk = kGatherCh * pp;               // output elements per token per pass (multiple of 8)
   const int groups = kchunk / 8;                   // 16-byte groups per token per pass
-  for (int chunk = 0; chunk < nchunks; ++chunk) {
+  (void)nchunks;
+  {
+    const int chunk = blockIdx.z;                    // one channel chunk per block: gh * B * nchunks independent blocks
     const int c0 = chunk * kGatherCh;
-    __syncthreads();
     for (int idx = threadIdx.x; idx < kGatherCh * p1 * W; idx += blockDim.x) {
       const int xw = idx % W;
       const int r = idx / W;            // c*p1 + py
@@ -87,7 +88,8 @@ int launch_patch_gather(const float* src0, int C0, float scale0, const float* sr
   SWB_REQUIRE((kGatherCh * p1 * p2) % 8 == 0, "patch_gather: patch %dx%d unsupported", p1, p2);
   const size_t smem = static_cast<size_t>(kGatherCh) * p1 * (W + 2) * sizeof(float);
   SWB_REQUIRE(smem <= 48 * 1024, "patch_gather: image width %d too large for the staging tile", W);
-  dim3 grid(H / p1, B);
+  const int cvirt = (Kp + p1 * p2 - 1) / (p1 * p2);
+  dim3 grid(H / p1, B, (cvirt + kGatherCh - 1) / kGatherCh);
   uint16_t* A_ = static_cast<uint16_t*>(A);
 #define SWB_GATHER(SP, F) \
   patch_gather_kernel<SP, F><<<grid, 256, smem, stream>>>(src0, C0, scale0, src1, C1, A_, lda, Kp, H, W, p1, p2)

@@ -279,23 +279,58 @@ __device__ __forceinline__ void epi_slot_swiglu(const GemmParams& p, const EpiCt
 }
 
 // ---- output head: packed column order is the reference's "(c p1 p2)" (models/swinv2.py:242); write NCHW directly ----
-// One element of the output image.  F is the raw network output.
-__device__ __forceinline__ void head_apply(const GemmParams& p, int b, int ch, size_t pix, float F) {
-  const size_t a = (static_cast<size_t>(b) * p.C + ch) * (static_cast<size_t>(p.H) * p.W) + pix;
-  float y = p.beta * F;
-  if (p.xt) y = fmaf(p.alpha, __ldg(p.xt + a), y);
-  if (p.fprev) y = fmaf(p.gamma, __ldg(p.fprev + a), y);
-  if (p.out0) static_cast<float*>(p.out0)[a] = y;
-  if (p.out_f) p.out_f[a] = F;
+// NV (1 or 2) horizontally adjacent pixels of one output channel.  F is the raw network output.
+template <int NV>
+__device__ __forceinline__ void head_apply(const GemmParams& p, int b, int ch, size_t pix, const float* F) {
+  const size_t hw = static_cast<size_t>(p.H) * p.W;
+  const size_t a = (static_cast<size_t>(b) * p.C + ch) * hw + pix;
+  float y[NV], t[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) y[i] = p.beta * F[i];
+  auto load = [&](const float* src, size_t off) {
+    if constexpr (NV == 2) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(src + off));
+      t[0] = v.x; t[1] = v.y;
+    } else {
+      t[0] = __ldg(src + off);
+    }
+  };
+  auto store = [&](float* dst, size_t off, const float* v) {
+    if constexpr (NV == 2) *reinterpret_cast<float2*>(dst + off) = make_float2(v[0], v[1]);
+    else dst[off] = v[0];
+  };
+  if (p.xt) {
+    load(p.xt, a);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) y[i] = fmaf(p.alpha, t[i], y[i]);
+  }
+  if (p.fprev) {
+    load(p.fprev, a);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) y[i] = fmaf(p.gamma, t[i], y[i]);
+  }
+  if (p.out0) store(static_cast<float*>(p.out0), a, y);
+  if (p.out_f) store(p.out_f, a, F);
   if (p.state) {
     // generate.py:120-131 (residual branch): X_phys = unstd_x(X) + Y*sigma_diff;  X <- std_x(X_phys)
-    float* sp = p.state + (static_cast<size_t>(b) * p.state_C + ch) * (static_cast<size_t>(p.H) * p.W) + pix;
-    const float xs = __ldg(p.x_std + ch), xm = __ldg(p.x_mean + ch);
-    float ph = fmaf(*sp, xs, xm) + y * __ldg(p.d_std + ch);
-    float sn = (ph - xm) / xs;
-    if (ch == p.zero_channel) ph = sn = 0.f;
-    *sp = sn;
-    if (p.phys) p.phys[a] = ph;
+    const size_t sa = (static_cast<size_t>(b) * p.state_C + ch) * hw + pix;
+    const float xs = __ldg(p.x_std + ch), xm = __ldg(p.x_mean + ch), ds = __ldg(p.d_std + ch);
+    const float rxs = 1.0f / xs;
+    float ph[NV], sn[NV];
+    if constexpr (NV == 2) {
+      const float2 v = *reinterpret_cast<const float2*>(p.state + sa);
+      t[0] = v.x; t[1] = v.y;
+    } else {
+      t[0] = p.state[sa];
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      ph[i] = fmaf(t[i], xs, xm) + y[i] * ds;
+      sn[i] = (ph[i] - xm) * rxs;
+      if (ch == p.zero_channel) ph[i] = sn[i] = 0.f;
+    }
+    store(p.state, sa, sn);
+    if (p.phys) store(p.phys, a, ph);
   }
 }
 
@@ -306,20 +341,32 @@ __device__ __forceinline__ void epi_slot_head(const GemmParams& p, const EpiCtx&
   const int tok = row - b * p.tokens;
   const int gy = tok / p.gw, gx = tok - gy * p.gw;
   const int pp = p.p1 * p.p2;
+  const bool pairs = (p.p2 & 1) == 0;      // px runs fastest: even p2 -> columns (n, n+1) are horizontally adjacent pixels
 #pragma unroll 1
   for (int c = 0; c < kSlot; c += 8) {
     float v[8];
     tmem_load_cols<8>(tslot + c, v);
     if (!row_ok) continue;
-    // consecutive columns walk px fastest: lanes (consecutive gx) x px form contiguous runs along the image row,
-    // so every warp access below is one contiguous 32*p2-float segment per (channel, py)
+    // lanes are consecutive gx: every warp access below is one contiguous run of 32*p2 floats per (channel, py)
+    if (pairs) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int n = n0 + c + j;
-      if (n < p.N) {
-        const int ch = n / pp, r = n - ch * pp;
-        const int py = r / p.p2, px = r - py * p.p2;
-        head_apply(p, b, ch, static_cast<size_t>(gy * p.p1 + py) * p.W + (gx * p.p2 + px), v[j]);
+      for (int j = 0; j < 8; j += 2) {
+        const int n = n0 + c + j;
+        if (n < p.N) {
+          const int ch = n / pp, r = n - ch * pp;
+          const int py = r / p.p2, px = r - py * p.p2;
+          head_apply<2>(p, b, ch, static_cast<size_t>(gy * p.p1 + py) * p.W + (gx * p.p2 + px), v + j);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int n = n0 + c + j;
+        if (n < p.N) {
+          const int ch = n / pp, r = n - ch * pp;
+          const int py = r / p.p2, px = r - py * p.p2;
+          head_apply<1>(p, b, ch, static_cast<size_t>(gy * p.p1 + py) * p.W + (gx * p.p2 + px), v + j);
+        }
       }
     }
   }
