@@ -373,6 +373,105 @@ __device__ __forceinline__ void epi_slot_head(const GemmParams& p, const EpiCtx&
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// "Drain first" epilogues.  With the 352-wide tile there is a single accumulator set, so the UMMA issuer cannot start the
+// next tile on a sub-accumulator until its epilogue group has read it.  These handlers pull both 88-column slots of
+// the group out of TMEM (packing the first one to 16 bits on the way so that everything fits in registers), hand the
+// accumulator back (`release`) and only then do the math / transposes / global stores, which thereby overlap with the
+// next tile's main loop.
+
+// 88 packed 16-bit values of one row -> out[row, n0 .. n0+87] through the coalescing transpose
+__device__ __forceinline__ void store_slot16(void* out, int ldo, int N, const EpiCtx& e, int n0, const uint32_t* w) {
+  int cv = N - n0;
+  cv = cv < 0 ? 0 : (cv > kSlot ? kSlot : cv);
+  const int ch = cv >> 3;                                   // valid 16-byte chunks (N % 8 == 0)
+  if (ch == 0) return;
+  uint8_t* g = reinterpret_cast<uint8_t*>(static_cast<uint16_t*>(out) + static_cast<size_t>(e.row0) * ldo + n0);
+  const size_t pitch = static_cast<size_t>(ldo) * 2;
+  warp_store_rows<8>(g, pitch, reinterpret_cast<const uint4*>(w), e.scratch, e.lane, e.rows_valid, ch);
+  if (ch > 8) warp_store_rows<3>(g + 128, pitch, reinterpret_cast<const uint4*>(w + 32), e.scratch, e.lane, e.rows_valid, ch - 8);
+}
+
+template <bool F16, typename Release>
+__device__ __forceinline__ void epi_group_store16(const GemmParams& p, const EpiCtx& e, uint32_t tacc, int n_lo, int n_hi,
+                                                  Release&& release) {
+  float v[kSlot];
+  uint32_t wa[44], wb[44];
+  tmem_load_cols<kSlot>(tacc, v);
+  pack_row16<F16, 44>(v, wa);
+  tmem_load_cols<kSlot>(tacc + kSlot, v);
+  release();
+  pack_row16<F16, 44>(v, wb);
+  store_slot16(p.out0, p.ldo, p.N, e, n_lo, wa);
+  store_slot16(p.out0, p.ldo, p.N, e, n_hi, wb);
+}
+
+// normalise (q, k) / scale (q) one (part, head) slot held in v[88] and pack it to 96 halfs (zero padded)
+template <bool F16>
+__device__ __forceinline__ bool qkv_slot_pack(const GemmParams& p, int n0, float* v, uint32_t* w, int* dst_slot) {
+  const int slot = n0 / kHeadDim;
+  const int part = slot / p.heads;
+  const int head = slot - part * p.heads;
+  *dst_slot = slot;
+  if (part >= 3) return false;                               // padded tail slot (warp-uniform)
+  if (part < 2) {
+    // F.normalize(x, dim=-1, eps=1e-12) (reference models/swinv2.py:123-127); q additionally * exp(min(scale, ln100))
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < kHeadDim; ++j) ss = fmaf(v[j], v[j], ss);
+    float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    if (part == 0) inv *= __ldg(p.qscale + head);
+#pragma unroll
+    for (int j = 0; j < kHeadDim; ++j) v[j] *= inv;
+  }
+  pack_row16<F16, 44>(v, w);
+  w[44] = w[45] = w[46] = w[47] = 0u;
+  return true;
+}
+
+__device__ __forceinline__ void qkv_slot_store(const GemmParams& p, const EpiCtx& e, int slot, const uint32_t* w) {
+  uint8_t* g = reinterpret_cast<uint8_t*>(static_cast<uint16_t*>(p.out0) +
+                                          (static_cast<size_t>(slot) * p.M + e.row0) * kHeadDimPad);
+  const size_t pitch = kHeadDimPad * 2;
+  warp_store_rows<8>(g, pitch, reinterpret_cast<const uint4*>(w), e.scratch, e.lane, e.rows_valid, 8);
+  warp_store_rows<4>(g + 128, pitch, reinterpret_cast<const uint4*>(w + 32), e.scratch, e.lane, e.rows_valid, 4);
+}
+
+template <bool F16, typename Release>
+__device__ __forceinline__ void epi_group_qkv(const GemmParams& p, const EpiCtx& e, uint32_t tacc, int n_lo, int n_hi,
+                                              Release&& release) {
+  float v[kSlot];
+  uint32_t wa[48], wb[48];
+  int sa, sb;
+  tmem_load_cols<kSlot>(tacc, v);
+  const bool oka = qkv_slot_pack<F16>(p, n_lo, v, wa, &sa);
+  tmem_load_cols<kSlot>(tacc + kSlot, v);
+  release();
+  const bool okb = qkv_slot_pack<F16>(p, n_hi, v, wb, &sb);
+  if (oka) qkv_slot_store(p, e, sa, wa);
+  if (okb) qkv_slot_store(p, e, sb, wb);
+}
+
+template <bool F16, typename Release>
+__device__ __forceinline__ void epi_group_swiglu(const GemmParams& p, const EpiCtx& e, uint32_t tacc, int out_col0,
+                                                 bool valid, Release&& release) {
+  // gate slot at columns [0,88), up slot at [88,176) of this group's accumulator.  The gate is parked in registers as
+  // 16-bit pairs (one extra 2^-12 rounding in front of a result that is itself stored in 16 bits).
+  float v[kSlot];
+  uint32_t g16[44], w[44];
+  tmem_load_cols<kSlot>(tacc, v);
+  pack_row16<F16, 44>(v, g16);
+  tmem_load_cols<kSlot>(tacc + kSlot, v);
+  release();
+#pragma unroll
+  for (int j = 0; j < 44; ++j) {
+    const float g0 = unpack_act1<F16>(static_cast<uint16_t>(g16[j] & 0xffffu));
+    const float g1 = unpack_act1<F16>(static_cast<uint16_t>(g16[j] >> 16));
+    w[j] = pack_act2<F16>(silu_f(g0) * v[2 * j], silu_f(g1) * v[2 * j + 1]);
+  }
+  if (valid) store_slot16(p.out0, p.ldo, p.ldo, e, out_col0, w);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 
 template <int NSUB, int CG, int EPI, bool F16>
 __global__ void __launch_bounds__(GemmCfg<NSUB, CG>::kThreads, 1)
@@ -561,26 +660,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       //   CG == 1:  s = 0 and s = 1
       const int s_lo = (NSUB == 1) ? 0 : grp;
       const int s_hi = (NSUB == 1) ? 1 : NSUB + grp;
+      auto release = [&]() {
+        // every TMEM read of this warp for this tile has completed (tcgen05.wait::ld): hand the accumulator back
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          const int bar_idx = (NSUB == 1) ? static_cast<int>(par) : grp;
+          if constexpr (CG == 2) mbar_arrive_cluster(tempty_leader0 + 8u * bar_idx);
+          else mbar_arrive(tempty_bar(bar_idx));
+        }
+      };
+      const int n_lo = n_tile + s_lo * kSlot, n_hi = n_tile + s_hi * kSlot;
       if constexpr (EPI == EPI_SWIGLU) {
         // packed w1 rows per tile: [NSUB gate slots | NSUB up slots]
-        const int out_col0 = (tn * NSUB + s_lo) * kSlot;
-        if (n_tile < p.N) epi_slot_swiglu<F16>(p, e, tacc, tacc + kSlot, out_col0);
+        epi_group_swiglu<F16>(p, e, tacc, (tn * NSUB + s_lo) * kSlot, n_tile < p.N, release);
+      } else if constexpr (EPI == EPI_QKV) {
+        epi_group_qkv<F16>(p, e, tacc, n_lo, n_hi, release);
+      } else if constexpr (EPI == EPI_STORE_ACT) {
+        epi_group_store16<F16>(p, e, tacc, n_lo, n_hi, release);
       } else {
 #pragma unroll 1
         for (int hf = 0; hf < 2; ++hf) {
-          const int n0 = n_tile + (hf ? s_hi : s_lo) * kSlot;
+          const int n0 = hf ? n_hi : n_lo;
           const uint32_t tslot = tacc + hf * kSlot;
-          if constexpr (EPI == EPI_QKV) epi_slot_qkv<F16>(p, e, tslot, n0);
-          else if constexpr (EPI == EPI_HEAD) epi_slot_head(p, e, tslot, n0);
+          if constexpr (EPI == EPI_HEAD) epi_slot_head(p, e, tslot, n0);
           else epi_slot_store<EPI, F16>(p, e, tslot, n0);
         }
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        const int bar_idx = (NSUB == 1) ? static_cast<int>(par) : grp;
-        if constexpr (CG == 2) mbar_arrive_cluster(tempty_leader0 + 8u * bar_idx);
-        else mbar_arrive(tempty_bar(bar_idx));
+        release();
       }
     }
   }

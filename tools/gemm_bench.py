@@ -39,14 +39,15 @@ def main():
     w2 = (torch.randn(D, Dff, device="cuda") * 0.02).to(dt)
     qs = torch.full((H,), 10.0, device="cuda")
     qkv = torch.empty(3, H, M, 96, device="cuda", dtype=dt)
-    br = torch.empty(M, D, device="cuda")
+    br = torch.empty(M, D, device="cuda", dtype=dt if f16 else torch.float32)
+    epi_br = 1 if f16 else 0        # the forward stores the wo / w2 branch in fp16 in fp16 mode
     hb = torch.empty(M, Dff, device="cuda", dtype=dt)
     for cg in cgs:
         cases = {
             "qkv": (lambda: lib.swb200_gemm_qkv(cg, f16, x.data_ptr(), D, wq.data_ptr(), qs.data_ptr(), qkv.data_ptr(), M, D, H, st), 2.0 * M * 3 * D * D),
-            "wo": (lambda: lib.swb200_gemm(0, cg, f16, x.data_ptr(), D, wo.data_ptr(), D, br.data_ptr(), D, M, D, D, st), 2.0 * M * D * D),
+            "wo": (lambda: lib.swb200_gemm(epi_br, cg, f16, x.data_ptr(), D, wo.data_ptr(), D, br.data_ptr(), D, M, D, D, st), 2.0 * M * D * D),
             "w1": (lambda: lib.swb200_gemm_swiglu(cg, f16, x.data_ptr(), D, w1.data_ptr(), hb.data_ptr(), M, D, Dff, st), 2.0 * M * 2 * Dff * D),
-            "w2": (lambda: lib.swb200_gemm(0, cg, f16, h.data_ptr(), Dff, w2.data_ptr(), Dff, br.data_ptr(), D, M, D, Dff, st), 2.0 * M * D * Dff),
+            "w2": (lambda: lib.swb200_gemm(epi_br, cg, f16, h.data_ptr(), Dff, w2.data_ptr(), Dff, br.data_ptr(), D, M, D, Dff, st), 2.0 * M * D * Dff),
         }
         tot_ms, tot_fl = 0.0, 0.0
         for name, (fn, fl) in cases.items():
