@@ -134,8 +134,10 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def workload_config(n_gpus: int, where: str):
-    return {"workload": "Swift-B (era5-swinv2-1.4-scm) sCM 1-step autoregressive rollout, 12 members x 8 ICs per GPU "
+def workload_config(n_gpus: int, where: str, solver: str = "scm"):
+    name = ("Swift-B (era5-swinv2-1.4-scm) sCM 1-step" if solver == "scm" else
+            "Swift-B (era5-swinv2-1.4-trigflow) TrigFlow 2S 20-step (39 denoiser calls per member-step)")
+    return {"workload": name + " autoregressive rollout, 12 members x 8 ICs per GPU "
                         "x K 6h steps (K=60: 15 days), 128x256 synthetic ERA5 fields, random-init weights",
             "members": MEMBERS, "initial_conditions": ICS_PER_GPU * n_gpus, "trajectories_per_gpu": MEMBERS * ICS_PER_GPU,
             "member_steps_per_bench_step": MEMBERS * ICS_PER_GPU * n_gpus,
@@ -182,7 +184,8 @@ def run_ours(args):
     forc_host = syn.synthetic_forcings(cfg, total_steps, seed=0).pin_memory()
     forc_dev = forc_host.to(dev)
     norm = Normalizers.synthetic(syn.IMG_CHANNELS, dev, diff=0.1)
-    ro = EnsembleRollout(net, norm, forc_dev, traj, solver="scm", use_graph=not args.no_graph)
+    skw = dict(num_steps=20, sigma_min=0.02, sigma_max=200.0, auxiliary=0.6) if args.solver == "2s" else None
+    ro = EnsembleRollout(net, norm, forc_dev, traj, solver=args.solver, solver_kwargs=skw, use_graph=not args.no_graph)
     ics = {}
     x0 = torch.empty(B, syn.IMG_CHANNELS, *cfg["img_resolution"])
     for b, (m, j) in enumerate(traj):
@@ -247,9 +250,10 @@ def run_ours(args):
     d2h = out_host.numel() * 4
 
     # ---------------- roofline of the dominant kernel (SwiGLU up-projection GEMM: 42.5 % of the FLOPs), timed alone
-    roof = dominant_kernel_roofline(eng, dev, args.chunk)
+    roof = dominant_kernel_roofline(eng, dev, min(args.chunk, 8))
     peaks, which = measured_peaks()
-    step_tflops = value / world * FLOP_PER_MEMBER_STEP / 1e12
+    calls = 39 if args.solver == "2s" else 1
+    step_tflops = value / world * FLOP_PER_MEMBER_STEP * calls / 1e12
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -265,7 +269,7 @@ def run_ours(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
         "dtype": ("fp16" if eng.act_fp16 else "bf16") + " tensor-core operands (tcgen05 kind::f16), fp32 accumulate / residual / LayerNorm / softmax",
-        "data": "synthetic", "config": workload_config(n_gpus, torch.cuda.get_device_name(dev)),
+        "data": "synthetic", "config": workload_config(n_gpus, torch.cuda.get_device_name(dev), args.solver),
         "clocks": clock_info,
         "e2e": {"value": e2e_value, "unit": "member-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps},
@@ -322,7 +326,10 @@ def main():
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--chunk", type=int, default=8, help="trajectories per kernel launch sequence")
+    ap.add_argument("--chunk", type=int, default=24, help="trajectories per kernel launch sequence")
+    ap.add_argument("--solver", default="scm", choices=["scm", "2s"],
+                    help="scm: Swift 1-step consistency sampler (headline); 2s: TrigFlow diffusion baseline, 20 Heun steps = "
+                         "39 denoiser calls per 6 h step (BASELINE.json configs[3])")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end leg (0 = same as --steps)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SWB200_ABI_VERSION 6
+#define SWB200_ABI_VERSION 7
 #if defined(__GNUC__)
 #define SWB200_API __attribute__((visibility("default")))
 #else
@@ -145,19 +145,20 @@ SWB200_API int swb200_gemm_qkv(int tile, int act_fp16, const void* A, int lda, c
 /* SwiGLU up-projection: out[M, dff] = silu(gate) * up; W packed as w_1. */
 SWB200_API int swb200_gemm_swiglu(int tile, int act_fp16, const void* A, int lda, const void* W, void* out, int M, int dim, int dff,
                        void* stream);
-/* Patch-embed: x[M,dim] = A*W^T + bias + pos[row % tokens]; xb = bf16(x). */
+/* Patch-embed: x[M,dim] = A*W^T + bias + pos[row % tokens], written as the 16-bit residual pair xhl[M, 2*dim] =
+ * [hi | lo] with x = hi + lo (hi is the A operand of the next GEMM, row pitch 2*dim). */
 SWB200_API int swb200_gemm_embed(int tile, int act_fp16, const void* A, int lda, const void* W, int K, const float* bias,
-                      const float* pos, int tokens, float* x, void* xb, int M, int dim, void* stream);
+                      const float* pos, int tokens, void* xhl, int M, int dim, void* stream);
 /* Output head with pixel-shuffle + update; A is [M, K] with K = dim*(1+split). */
 SWB200_API int swb200_gemm_head(int tile, const swb200_model* m, const void* A, int lda, int K, int B,
                      const swb200_update* upd, float* y, void* stream);
 /* cat + patchify + bf16 cast (+ hi/lo split): A[B*tokens, lda] */
 SWB200_API int swb200_patch_gather(const swb200_model* m, const float* x0, int c0, float scale0, const float* x1, int c1, int B,
                         void* A, int lda, void* stream);
-/* x += LN(branch)*gain[b] + bias[b]; xb = 16-bit copy of x (pitch ldxb); xlo optional (same pitch).
+/* x += LN(branch)*gain[b] + bias[b] on the residual pair xhl[M, 2*dim] = [hi | lo] (in place).
  * branch is fp32 [M, dim], or the 16-bit operand format when branch_16bit. */
-SWB200_API int swb200_ln_mod_residual(const void* branch, int branch_16bit, float* x, void* xb, int ldxb, void* xlo,
-                           const float* gain, const float* bias, int M, int dim, int tokens, int act_fp16, void* stream);
+SWB200_API int swb200_ln_mod_residual(const void* branch, int branch_16bit, void* xhl, const float* gain, const float* bias,
+                           int M, int dim, int tokens, int act_fp16, void* stream);
 /* shifted-window cosine attention on the packed qkv buffer; out 16-bit [M, heads*88].
  * impl: 0 auto, 1 general-shift mma.sync kernel, 2 tcgen05/TMEM/TMA kernel (shift must be a multiple of 8). */
 SWB200_API int swb200_window_attention(const void* qkv, void* out, int B, int grid_h, int grid_w, int heads, int shift_h,

@@ -11,7 +11,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libswift_b200.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 # Every symbol ``include/swift_b200.h`` declares; tests check the library exports exactly these.
 EXPORTS = (
@@ -63,12 +63,11 @@ def _declare(lib):
                                   C.c_int, C.c_int, _vp]),
         "swb200_gemm_qkv": (C.c_int, [C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
         "swb200_gemm_swiglu": (C.c_int, [C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
-        "swb200_gemm_embed": (C.c_int, [C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp,
+        "swb200_gemm_embed": (C.c_int, [C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp, C.c_int, _vp,
                                         C.c_int, C.c_int, _vp]),
         "swb200_gemm_head": (C.c_int, [C.c_int, MP, _vp, C.c_int, C.c_int, C.c_int, UP, _vp, _vp]),
         "swb200_patch_gather": (C.c_int, [MP, _vp, C.c_int, _f32, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp]),
-        "swb200_ln_mod_residual": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int,
-                                             C.c_int, _vp]),
+        "swb200_ln_mod_residual": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
         "swb200_window_attention": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                               C.c_int, _vp]),
         "swb200_rollout_noise": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int64, _vp]),

@@ -28,7 +28,7 @@ Geom geom(const swb200_model* m) {
 
 // per-sample workspace layout (offsets in bytes, every buffer 1024-byte aligned per chunk)
 struct Workspace {
-  size_t x, xb, qkv, attn, branch, h, total;   // sizes for `chunk` samples; a_embed aliases qkv, x_final aliases h
+  size_t xhl, qkv, attn, branch, h, total;   // sizes for `chunk` samples; a_embed aliases qkv
 };
 Workspace carve(const swb200_model* m, int chunk) {
   const Geom g = geom(m);
@@ -40,15 +40,13 @@ Workspace carve(const swb200_model* m, int chunk) {
     off = align_up(off + bytes, 1024);
     return o;
   };
-  w.x = take(M * m->dim * 4);
-  w.xb = take(M * m->dim * 2);
+  w.xhl = take(M * m->dim * 2 * 2);          // residual stream as a 16-bit [hi | lo] pair
   size_t qkv_bytes = static_cast<size_t>(3) * m->heads * M * kHeadDimPad * 2;
   size_t emb_bytes = M * g.k_embed_total * 2;
   w.qkv = take(qkv_bytes > emb_bytes ? qkv_bytes : emb_bytes);
   w.attn = take(M * m->dim * 2);
   w.branch = take(M * m->dim * 4);
-  size_t h_cols = static_cast<size_t>(m->dff) > static_cast<size_t>(g.k_head_total) ? m->dff : g.k_head_total;
-  w.h = take(M * h_cols * 2);
+  w.h = take(M * static_cast<size_t>(m->dff) * 2);
   w.total = off;
   return w;
 }
@@ -157,8 +155,7 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
     const int bc = (B - b0 < chunk) ? (B - b0) : chunk;
     const int M = bc * g.tokens;
     const Workspace w = carve(m, bc);
-    float* x = reinterpret_cast<float*>(ws + w.x);
-    void* xb = ws + w.xb;
+    void* xhl = ws + w.xhl;                    // [M, 2D]: hi (= GEMM A operand, row pitch 2D) | lo
     void* qkv = ws + w.qkv;
     void* a_emb = qkv;
     void* attn = ws + w.attn;
@@ -177,9 +174,8 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
     // 2. patch-embed GEMM (+bias +pos_embed)
     {
       GemmParams p = base_params(M, D, g.k_embed_total);
-      p.out0 = x;
-      p.out1 = xb;
-      p.ldo = D;
+      p.out0 = xhl;
+      p.ldo = 2 * D;
       p.bias = m->b_embed;
       p.pos = m->pos_embed;
       p.pos_rows = g.tokens;
@@ -196,7 +192,7 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
         p.heads = H;
         p.dmodel = D;
         const auto* wq = static_cast<const __nv_bfloat16*>(m->w_qkv) + static_cast<size_t>(l) * 3 * D * D;
-        rc = launch_gemm(EPI_QKV, kDefaultCG, F16, xb, D, wq, D, p, stream);
+        rc = launch_gemm(EPI_QKV, kDefaultCG, F16, xhl, 2 * D, wq, D, p, stream);
         if (rc) return rc;
       }
       rc = launch_window_attention(qkv, attn, bc, g.gh, g.gw, H, shifted ? m->shift_h : 0, shifted ? m->shift_w : 0,
@@ -210,7 +206,7 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
         rc = launch_gemm(epi_branch, kDefaultCG, F16, attn, D, wo, D, p, stream);
         if (rc) return rc;
       }
-      rc = launch_ln_mod_residual(branch, BR16, x, xb, D, nullptr, gain + (static_cast<size_t>(2 * l) * B + b0) * D,
+      rc = launch_ln_mod_residual(branch, BR16, xhl, gain + (static_cast<size_t>(2 * l) * B + b0) * D,
                                   bias + (static_cast<size_t>(2 * l) * B + b0) * D, M, D, g.tokens, 1e-6f, F16, stream);
       if (rc) return rc;
       {
@@ -218,7 +214,7 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
         p.out0 = hbuf;
         p.ldo = Dff;
         const auto* w1 = static_cast<const __nv_bfloat16*>(m->w_1) + static_cast<size_t>(l) * 2 * Dff * D;
-        rc = launch_gemm(EPI_SWIGLU, kDefaultCG, F16, xb, D, w1, D, p, stream);
+        rc = launch_gemm(EPI_SWIGLU, kDefaultCG, F16, xhl, 2 * D, w1, D, p, stream);
         if (rc) return rc;
       }
       {
@@ -229,12 +225,7 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
         rc = launch_gemm(epi_branch, kDefaultCG, F16, hbuf, Dff, w2, Dff, p, stream);
         if (rc) return rc;
       }
-      const bool last = (l == m->depth - 1);
-      // the last LN writes the head operand: [hi | lo] with pitch k_head_total into the (dead) h buffer
-      void* xb_dst = last ? hbuf : xb;
-      const int ldxb = last ? g.k_head_total : D;
-      void* xlo = (last && m->split_head) ? static_cast<void*>(static_cast<__nv_bfloat16*>(hbuf) + D) : nullptr;
-      rc = launch_ln_mod_residual(branch, BR16, x, xb_dst, ldxb, xlo, gain + (static_cast<size_t>(2 * l + 1) * B + b0) * D,
+      rc = launch_ln_mod_residual(branch, BR16, xhl, gain + (static_cast<size_t>(2 * l + 1) * B + b0) * D,
                                   bias + (static_cast<size_t>(2 * l + 1) * B + b0) * D, M, D, g.tokens, 1e-6f, F16, stream);
       if (rc) return rc;
     }
@@ -246,7 +237,8 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
       if (u.out_f) u.out_f += b0 * img_out;
       if (u.state) u.state += b0 * static_cast<size_t>(u.state_channels) * m->img_h * m->img_w;
       if (u.phys) u.phys += b0 * img_out;
-      rc = swb200_gemm_head(kDefaultCG, m, hbuf, g.k_head_total, g.k_head_total, bc, &u, y ? y + b0 * img_out : nullptr,
+      // the head reads the residual pair directly: K = 2D ([hi | lo] x [W | W]) or K = D (hi only), row pitch 2D
+      rc = swb200_gemm_head(kDefaultCG, m, xhl, 2 * D, g.k_head_total, bc, &u, y ? y + b0 * img_out : nullptr,
                             stream_);
       if (rc) return rc;
     }
@@ -292,12 +284,11 @@ SWB200_API int swb200_gemm_swiglu(int tile, int act_fp16, const void* A, int lda
 }
 
 SWB200_API int swb200_gemm_embed(int tile, int act_fp16, const void* A, int lda, const void* W, int K, const float* bias,
-                      const float* pos, int tokens, float* x, void* xb, int M, int dim, void* stream) {
-  SWB_REQUIRE(A && W && bias && pos && x && xb, "swb200_gemm_embed: NULL pointer");
+                      const float* pos, int tokens, void* xhl, int M, int dim, void* stream) {
+  SWB_REQUIRE(A && W && bias && pos && xhl, "swb200_gemm_embed: NULL pointer");
   GemmParams p = base_params(M, dim, K);
-  p.out0 = x;
-  p.out1 = xb;
-  p.ldo = dim;
+  p.out0 = xhl;
+  p.ldo = 2 * dim;
   p.bias = bias;
   p.pos = pos;
   p.pos_rows = tokens;
@@ -341,10 +332,10 @@ SWB200_API int swb200_patch_gather(const swb200_model* m, const float* x0, int c
                              m->patch_h, m->patch_w, static_cast<cudaStream_t>(stream));
 }
 
-SWB200_API int swb200_ln_mod_residual(const void* branch, int branch_16bit, float* x, void* xb, int ldxb, void* xlo,
-                           const float* gain, const float* bias, int M, int dim, int tokens, int act_fp16, void* stream) {
-  SWB_REQUIRE(branch && x && xb && gain && bias, "swb200_ln_mod_residual: NULL pointer");
-  return launch_ln_mod_residual(branch, branch_16bit, x, xb, ldxb, xlo, gain, bias, M, dim, tokens, 1e-6f, act_fp16,
+SWB200_API int swb200_ln_mod_residual(const void* branch, int branch_16bit, void* xhl, const float* gain, const float* bias,
+                           int M, int dim, int tokens, int act_fp16, void* stream) {
+  SWB_REQUIRE(branch && xhl && gain && bias, "swb200_ln_mod_residual: NULL pointer");
+  return launch_ln_mod_residual(branch, branch_16bit, xhl, gain, bias, M, dim, tokens, 1e-6f, act_fp16,
                                 static_cast<cudaStream_t>(stream));
 }
 

@@ -104,29 +104,33 @@ int launch_patch_gather(const float* src0, int C0, float scale0, const float* sr
 }
 
 // =========================================================================================================
-// x <- x + LN(branch) * gain[b] + bias[b];   xb <- bf16(x)   (optionally xlo <- bf16(x - xb))
+// x <- x + LN(branch) * gain[b] + bias[b]
 //
 // reference: ModulatedNorm (swinv2.py:77-86) applied to the branch output, then the residual add
 // (swinv2.py:211-212).  gain = gamma*(1+scale(t)), bias = beta*(1+scale(t)) + shift(t) are folded per sample
-// by mod_finalize_kernel.  One warp per token row; the row lives in registers (two-pass mean/variance in fp32);
-// accesses are 16-byte per lane, lane-strided (512 contiguous bytes per warp request).
-// BR16: the branch is stored in the 16-bit operand format (fp16 mode: halves the epilogue store of the wo / w2 GEMMs
-// and this kernel's branch read) instead of fp32.
+// by mod_finalize_kernel.  The residual stream x lives in HBM as a 16-bit pair xhl[M, 2D] = [hi | lo] with
+// x = hi + lo (about 22 significant bits in fp16 mode); hi is at the same time the A operand of the next GEMM, so no
+// separate 16-bit copy is written and the row costs 2 (branch) + 4 (read) + 4 (write) bytes per element.
+// One warp per token row; the row lives in registers (two-pass mean/variance in fp32); every global load is issued
+// before the first use; accesses are 8 / 16 bytes per lane, lane-strided.
+// BR16: the branch is stored in the 16-bit operand format (fp16 mode) instead of fp32.
 template <int NV4, bool F16, bool BR16>
-__global__ void __launch_bounds__(128) ln_mod_residual_kernel(const void* __restrict__ branch_, float* __restrict__ x,
-                                                              uint16_t* __restrict__ xb, int ldxb,
-                                                              uint16_t* __restrict__ xlo,
+__global__ void __launch_bounds__(128) ln_mod_residual_kernel(const void* __restrict__ branch_, uint16_t* __restrict__ xhl,
                                                               const float* __restrict__ gain,
                                                               const float* __restrict__ bias, int M, int D,
                                                               int tokens, float eps) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
-  const int nv = D >> 2;                                   // float4 per row
-  float4* xr = reinterpret_cast<float4*>(x + static_cast<size_t>(row) * D);
-  // every global load of the row (branch AND residual) is issued before the first use: 2*NV4 independent
-  // warp requests in flight per warp
-  float4 v[NV4], xv[NV4];
+  const int nv = D >> 2;                                   // groups of 4 elements per row
+  uint2* xh = reinterpret_cast<uint2*>(xhl + static_cast<size_t>(row) * 2 * D);
+  uint2* xl = xh + nv;
+  float4 v[NV4];
+  uint2 rh[NV4], rl[NV4];
+  auto unpack4 = [](uint2 r) {
+    return make_float4(unpack_act1<F16>(static_cast<uint16_t>(r.x & 0xffffu)), unpack_act1<F16>(static_cast<uint16_t>(r.x >> 16)),
+                       unpack_act1<F16>(static_cast<uint16_t>(r.y & 0xffffu)), unpack_act1<F16>(static_cast<uint16_t>(r.y >> 16)));
+  };
   if constexpr (BR16) {
     const uint2* br = reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(branch_) + static_cast<size_t>(row) * D);
     uint2 raw[NV4];
@@ -136,11 +140,13 @@ __global__ void __launch_bounds__(128) ln_mod_residual_kernel(const void* __rest
       raw[i] = (c < nv) ? __ldg(br + c) : make_uint2(0u, 0u);
     }
 #pragma unroll
-    for (int i = 0; i < NV4; ++i)
-      v[i] = make_float4(unpack_act1<F16>(static_cast<uint16_t>(raw[i].x & 0xffffu)),
-                         unpack_act1<F16>(static_cast<uint16_t>(raw[i].x >> 16)),
-                         unpack_act1<F16>(static_cast<uint16_t>(raw[i].y & 0xffffu)),
-                         unpack_act1<F16>(static_cast<uint16_t>(raw[i].y >> 16)));
+    for (int i = 0; i < NV4; ++i) {
+      const int c = i * 32 + lane;
+      rh[i] = (c < nv) ? xh[c] : make_uint2(0u, 0u);
+      rl[i] = (c < nv) ? xl[c] : make_uint2(0u, 0u);
+    }
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) v[i] = unpack4(raw[i]);
   } else {
     const float4* br = reinterpret_cast<const float4*>(static_cast<const float*>(branch_) + static_cast<size_t>(row) * D);
 #pragma unroll
@@ -148,11 +154,12 @@ __global__ void __launch_bounds__(128) ln_mod_residual_kernel(const void* __rest
       const int c = i * 32 + lane;
       v[i] = (c < nv) ? __ldg(br + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-  }
 #pragma unroll
-  for (int i = 0; i < NV4; ++i) {
-    const int c = i * 32 + lane;
-    xv[i] = (c < nv) ? xr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < NV4; ++i) {
+      const int c = i * 32 + lane;
+      rh[i] = (c < nv) ? xh[c] : make_uint2(0u, 0u);
+      rl[i] = (c < nv) ? xl[c] : make_uint2(0u, 0u);
+    }
   }
   float sum = 0.f;
 #pragma unroll
@@ -174,46 +181,38 @@ __global__ void __launch_bounds__(128) ln_mod_residual_kernel(const void* __rest
   const int b = row / tokens;
   const float4* g4 = reinterpret_cast<const float4*>(gain + static_cast<size_t>(b) * D);
   const float4* b4 = reinterpret_cast<const float4*>(bias + static_cast<size_t>(b) * D);
-  uint2* xbr = reinterpret_cast<uint2*>(xb + static_cast<size_t>(row) * ldxb);
-  uint2* xlr = xlo ? reinterpret_cast<uint2*>(xlo + static_cast<size_t>(row) * ldxb) : nullptr;
 #pragma unroll
   for (int i = 0; i < NV4; ++i) {
     const int c = i * 32 + lane;
     if (c < nv) {
       const float4 g = __ldg(g4 + c), bb = __ldg(b4 + c);
-      float4 o;
-      o.x = xv[i].x + fmaf((v[i].x - mean) * rstd, g.x, bb.x);
-      o.y = xv[i].y + fmaf((v[i].y - mean) * rstd, g.y, bb.y);
-      o.z = xv[i].z + fmaf((v[i].z - mean) * rstd, g.z, bb.z);
-      o.w = xv[i].w + fmaf((v[i].w - mean) * rstd, g.w, bb.w);
-      xr[c] = o;
-      const uint32_t h0 = pack_act2<F16>(o.x, o.y), h1 = pack_act2<F16>(o.z, o.w);
-      xbr[c] = make_uint2(h0, h1);
-      if (xlr) {
-        const float l0 = o.x - unpack_act1<F16>(static_cast<uint16_t>(h0 & 0xffffu));
-        const float l1 = o.y - unpack_act1<F16>(static_cast<uint16_t>(h0 >> 16));
-        const float l2 = o.z - unpack_act1<F16>(static_cast<uint16_t>(h1 & 0xffffu));
-        const float l3 = o.w - unpack_act1<F16>(static_cast<uint16_t>(h1 >> 16));
-        xlr[c] = make_uint2(pack_act2<F16>(l0, l1), pack_act2<F16>(l2, l3));
-      }
+      const float4 xh4 = unpack4(rh[i]), xl4 = unpack4(rl[i]);
+      float o[4];
+      o[0] = (xh4.x + xl4.x) + fmaf((v[i].x - mean) * rstd, g.x, bb.x);
+      o[1] = (xh4.y + xl4.y) + fmaf((v[i].y - mean) * rstd, g.y, bb.y);
+      o[2] = (xh4.z + xl4.z) + fmaf((v[i].z - mean) * rstd, g.z, bb.z);
+      o[3] = (xh4.w + xl4.w) + fmaf((v[i].w - mean) * rstd, g.w, bb.w);
+      const uint32_t h0 = pack_act2<F16>(o[0], o[1]), h1 = pack_act2<F16>(o[2], o[3]);
+      xh[c] = make_uint2(h0, h1);
+      const float l0 = o[0] - unpack_act1<F16>(static_cast<uint16_t>(h0 & 0xffffu));
+      const float l1 = o[1] - unpack_act1<F16>(static_cast<uint16_t>(h0 >> 16));
+      const float l2 = o[2] - unpack_act1<F16>(static_cast<uint16_t>(h1 & 0xffffu));
+      const float l3 = o[3] - unpack_act1<F16>(static_cast<uint16_t>(h1 >> 16));
+      xl[c] = make_uint2(pack_act2<F16>(l0, l1), pack_act2<F16>(l2, l3));
     }
   }
 }
 
-int launch_ln_mod_residual(const void* branch, int branch_16bit, float* x, void* xb, int ldxb, void* xlo,
-                           const float* gain, const float* bias, int M, int D, int tokens, float eps, int act_f16,
-                           cudaStream_t stream) {
-  SWB_REQUIRE(D % 4 == 0 && ldxb % 4 == 0, "ln_mod_residual: dim %d and pitch %d must be multiples of 4", D, ldxb);
-  SWB_REQUIRE(((reinterpret_cast<uintptr_t>(branch) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gain) |
-                reinterpret_cast<uintptr_t>(bias)) & 15) == 0 &&
-                  ((reinterpret_cast<uintptr_t>(xb) | reinterpret_cast<uintptr_t>(xlo)) & 7) == 0,
+int launch_ln_mod_residual(const void* branch, int branch_16bit, void* xhl, const float* gain, const float* bias, int M,
+                           int D, int tokens, float eps, int act_f16, cudaStream_t stream) {
+  SWB_REQUIRE(D % 4 == 0, "ln_mod_residual: dim %d must be a multiple of 4", D);
+  SWB_REQUIRE(((reinterpret_cast<uintptr_t>(branch) | reinterpret_cast<uintptr_t>(gain) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(xhl) & 7) == 0,
               "ln_mod_residual: pointers must be 16-byte (fp32) / 8-byte (16-bit) aligned");
   const int rows_per_block = 4;
   dim3 grid((M + rows_per_block - 1) / rows_per_block);
-  auto xb_ = static_cast<uint16_t*>(xb);
-  auto xlo_ = static_cast<uint16_t*>(xlo);
-#define SWB_LN3(V, F, R) \
-  ln_mod_residual_kernel<V, F, R><<<grid, 128, 0, stream>>>(branch, x, xb_, ldxb, xlo_, gain, bias, M, D, tokens, eps)
+  auto x_ = static_cast<uint16_t*>(xhl);
+#define SWB_LN3(V, F, R) ln_mod_residual_kernel<V, F, R><<<grid, 128, 0, stream>>>(branch, x_, gain, bias, M, D, tokens, eps)
 #define SWB_LN(V)                                                   \
   do {                                                              \
     if (act_f16) {                                                  \

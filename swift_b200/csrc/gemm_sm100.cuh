@@ -26,7 +26,7 @@ namespace swb {
 enum GemmEpilogue : int {
   EPI_STORE_F32 = 0,   // out0[M, ldo] fp32
   EPI_STORE_ACT = 1,   // out0[M, ldo] in the 16-bit operand format (fp16 / bf16)
-  EPI_EMBED = 2,       // x = acc + bias[n] + pos[row % pos_rows, n];  out0 = x (fp32), out1 = 16-bit copy
+  EPI_EMBED = 2,       // x = acc + bias[n] + pos[row % pos_rows, n];  out0[M, 2N] = [hi | lo] 16-bit pair of x
   EPI_QKV = 3,         // scaled-cosine q/k normalisation fused; out0 = [3][heads][M][96] 16-bit
   EPI_SWIGLU = 4,      // tile = [gate slots | up slots];  out0[M, N/2] 16-bit = silu(gate) * up
   EPI_HEAD = 5,        // pixel-shuffle to NCHW + sampler update: y = alpha*xt + beta*F + gamma*fprev
@@ -195,20 +195,30 @@ __device__ __forceinline__ void epi_slot_store(const GemmParams& p, const EpiCtx
       for (int j = 0; j < 32; ++j)
         if (j < cols_valid) v[j] += __ldg(p.bias + n + j) + pe[j];
     }
-    if constexpr (EPI == EPI_STORE_F32 || EPI == EPI_EMBED) {
+    if constexpr (EPI == EPI_STORE_F32) {
       uint8_t* g = reinterpret_cast<uint8_t*>(static_cast<float*>(p.out0) + static_cast<size_t>(e.row0) * p.ldo + n);
       const size_t pitch = static_cast<size_t>(p.ldo) * 4;
       if (blk < 2) warp_store_rows<8>(g, pitch, reinterpret_cast<const uint4*>(v), e.scratch, e.lane, e.rows_valid, cols_valid >> 2);
       else warp_store_rows<6>(g, pitch, reinterpret_cast<const uint4*>(v), e.scratch, e.lane, e.rows_valid, cols_valid >> 2);
     }
     if constexpr (EPI == EPI_STORE_ACT || EPI == EPI_EMBED) {
-      void* dst = (EPI == EPI_EMBED) ? p.out1 : p.out0;
       uint32_t w[16];
       pack_row16<F16, 16>(v, w);
-      uint8_t* g = reinterpret_cast<uint8_t*>(static_cast<uint16_t*>(dst) + static_cast<size_t>(e.row0) * p.ldo + n);
+      uint8_t* g = reinterpret_cast<uint8_t*>(static_cast<uint16_t*>(p.out0) + static_cast<size_t>(e.row0) * p.ldo + n);
       const size_t pitch = static_cast<size_t>(p.ldo) * 2;
       if (blk < 2) warp_store_rows<4>(g, pitch, reinterpret_cast<const uint4*>(w), e.scratch, e.lane, e.rows_valid, cols_valid >> 3);
       else warp_store_rows<3>(g, pitch, reinterpret_cast<const uint4*>(w), e.scratch, e.lane, e.rows_valid, cols_valid >> 3);
+      if constexpr (EPI == EPI_EMBED) {
+        // residual stream is kept as a 16-bit [hi | lo] pair (hi doubles as the next GEMM's A operand): lo at column N + n
+        uint32_t wl[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          wl[j] = pack_act2<F16>(v[2 * j] - unpack_act1<F16>(static_cast<uint16_t>(w[j] & 0xffffu)),
+                                 v[2 * j + 1] - unpack_act1<F16>(static_cast<uint16_t>(w[j] >> 16)));
+        uint8_t* gl = g + static_cast<size_t>(p.N) * 2;
+        if (blk < 2) warp_store_rows<4>(gl, pitch, reinterpret_cast<const uint4*>(wl), e.scratch, e.lane, e.rows_valid, cols_valid >> 3);
+        else warp_store_rows<3>(gl, pitch, reinterpret_cast<const uint4*>(wl), e.scratch, e.lane, e.rows_valid, cols_valid >> 3);
+      }
     }
   }
 }

@@ -22,9 +22,9 @@ struct CondWeights {
 int launch_patch_gather(const float* src0, int C0, float scale0, const float* src1, int C1, void* A, int lda, int Kp,
                         int split, int act_f16, int B, int H, int W, int p1, int p2, cudaStream_t stream);
 
-int launch_ln_mod_residual(const void* branch, int branch_16bit, float* x, void* xb, int ldxb, void* xlo,
-                           const float* gain, const float* bias, int M, int D, int tokens, float eps, int act_f16,
-                           cudaStream_t stream);
+// xhl: residual stream as a 16-bit [hi | lo] pair, [M, 2*D]; branch: fp32 or 16-bit [M, D]
+int launch_ln_mod_residual(const void* branch, int branch_16bit, void* xhl, const float* gain, const float* bias, int M,
+                           int D, int tokens, float eps, int act_f16, cudaStream_t stream);
 
 // scratch needs B*(3*D + L*2*D) floats; gain/bias are [L, B, D]
 int launch_conditioning(const CondWeights& w, const float* t, const float* aux, int B, int D, int L,

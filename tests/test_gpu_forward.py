@@ -134,6 +134,28 @@ def test_swift_b_one_step_vs_oracle_and_golden(golden):
     assert errb.max() < 1.5 * TOL
 
 
+def test_swift_b_trigflow_2s_vs_oracle():
+    """BASELINE.json configs[3] (TrigFlow 2S diffusion baseline) at Swift-B scale, 3 Heun steps = 5 denoiser calls with
+    time-dependent conditioning, vs the fp32 oracle; multi-call drift is reported."""
+    from oracle import swinv2_oracle as orc
+    from swift_b200 import synthetic as syn
+    from swift_b200.sampler import DiffusionSampler
+    cfg = syn.SWIFT_B
+    net, sd = build_net(cfg, img_channels=syn.IMG_CHANNELS)
+    lat, cond = syn.synthetic_fields(cfg, 1, seed=2)
+    y = DiffusionSampler(net).dpm_solver_2s(latents=lat.cuda(), condition=cond.cuda(), auxiliary=0.6, num_steps=3,
+                                            sigma_min=0.02, sigma_max=200.0)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ocfg = orc.make_cfg(**cfg)
+    sd_gpu = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        ref = orc.dpm_solver_2s(lambda x, t, c, a: orc.pass_precond(sd_gpu, ocfg, x, t, c, a), lat.cuda(), cond.cuda(),
+                                0.6, num_steps=3)
+    err = per_field_rel_l2(y, ref)
+    print(f"swift_b 2S (5 calls): per-field rel-L2 max {err.max():.4e} mean {err.mean():.4e}")
+    assert err.max() < TOL
+
+
 def test_module_contract():
     from swift_b200 import synthetic as syn
     from swift_b200.swinv2 import SwinV2

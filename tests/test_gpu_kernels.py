@@ -73,8 +73,8 @@ def test_patch_gather(lib, split, p1, p2, C0, C1, H, W, f16):
 @ACT
 @pytest.mark.parametrize("br16", [0, 1], ids=["branch_fp32", "branch_16bit"])
 @pytest.mark.parametrize("D", [264, 528, 1056])
-@pytest.mark.parametrize("with_lo", [False, True])
-def test_ln_mod_residual(lib, D, with_lo, f16, br16):
+def test_ln_mod_residual(lib, D, f16, br16):
+    """x += LN(branch)*gain + bias on the residual pair [hi | lo]."""
     dt = _adt(f16)
     B, T = 3, 256
     M = B * T
@@ -82,20 +82,20 @@ def test_ln_mod_residual(lib, D, with_lo, f16, br16):
     if br16:
         branch = branch.to(dt)
     x = torch.randn(M, D, device="cuda")
+    hi = x.to(dt)
+    lo = (x - hi.float()).to(dt)
+    x0 = hi.float() + lo.float()                       # what the pair actually represents
+    xhl = torch.cat([hi, lo], 1).contiguous()
     gain = torch.randn(B, D, device="cuda")
     bias = torch.randn(B, D, device="cuda")
-    ldxb = 2 * D if with_lo else D
-    xb = torch.zeros(M, ldxb, device="cuda", dtype=dt)
-    x_ref = x + torch.nn.functional.layer_norm(branch.float(), (D,), eps=1e-6).reshape(B, T, D).mul(gain[:, None]).add(
+    x_ref = x0 + torch.nn.functional.layer_norm(branch.float(), (D,), eps=1e-6).reshape(B, T, D).mul(gain[:, None]).add(
         bias[:, None]).reshape(M, D)
-    xlo_ptr = xb.data_ptr() + 2 * D if with_lo else None
-    _check(lib.swb200_ln_mod_residual(branch.data_ptr(), br16, x.data_ptr(), xb.data_ptr(), ldxb, xlo_ptr, gain.data_ptr(),
-                                      bias.data_ptr(), M, D, T, f16, _stream()))
+    _check(lib.swb200_ln_mod_residual(branch.data_ptr(), br16, xhl.data_ptr(), gain.data_ptr(), bias.data_ptr(), M, D, T,
+                                      f16, _stream()))
     torch.cuda.synchronize()
-    assert _rel(x, x_ref) < 2e-6, f"{_rel(x, x_ref):.3e}"
-    assert torch.equal(xb[:, :D], x.to(dt))
-    if with_lo:
-        assert torch.equal(xb[:, D:], (x - xb[:, :D].float()).to(dt))
+    got = xhl[:, :D].float() + xhl[:, D:].float()
+    assert _rel(got, x_ref) < (3e-6 if f16 else 3e-5), f"{_rel(got, x_ref):.3e}"
+    assert _rel(xhl[:, :D].float(), x_ref) < (6e-4 if f16 else 5e-3)
 
 
 def _window_attention_ref(qkv, B, gh, gw, H, shift):

@@ -47,7 +47,7 @@ def test_validate_rejects_unsupported_geometry():
     m.shift_h = m.shift_w = 8
     m.gemm_tile = 3
     assert lib.swb200_validate(ctypes.byref(m)) == 0
-    assert lib.swb200_workspace_bytes(ctypes.byref(m), 1) > 200e6      # ~216 MB per Swift-B sample
+    assert 150e6 < lib.swb200_workspace_bytes(ctypes.byref(m), 1) < 250e6      # ~190 MB per Swift-B sample
 
 
 def test_missing_library_fails_loudly(monkeypatch):
