@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SWB200_ABI_VERSION 7
+#define SWB200_ABI_VERSION 8
 #if defined(__GNUC__)
 #define SWB200_API __attribute__((visibility("default")))
 #else
@@ -163,6 +163,15 @@ SWB200_API int swb200_ln_mod_residual(const void* branch, int branch_16bit, void
  * impl: 0 auto, 1 general-shift mma.sync kernel, 2 tcgen05/TMEM/TMA kernel (shift must be a multiple of 8). */
 SWB200_API int swb200_window_attention(const void* qkv, void* out, int B, int grid_h, int grid_w, int heads, int shift_h,
                             int shift_w, int act_fp16, int impl, void* stream);
+
+/* ---- tracing ---------------------------------------------------------------------------------------------- */
+
+/* In-situ per-kernel timing of swb200_forward (CUDA events around every launch; not usable during graph capture).
+ * The reference's counterpart is the optional torch.profiler block of training/trainer.py:155-177.
+ * swb200_trace_enable(1) resets and starts; swb200_trace_report synchronises the device and writes a JSON object
+ * {"kernel": {"ms": total, "launches": n}, ...} into buf. */
+SWB200_API int swb200_trace_enable(int on);
+SWB200_API int swb200_trace_report(char* buf, size_t buf_bytes);
 
 /* ---- rollout glue around the sampler (generate.py:97-118), graph-capturable ------------------------------ */
 

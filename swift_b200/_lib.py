@@ -11,7 +11,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libswift_b200.so")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 # Every symbol ``include/swift_b200.h`` declares; tests check the library exports exactly these.
 EXPORTS = (
@@ -19,7 +19,7 @@ EXPORTS = (
     "swb200_conditioning_scratch_bytes", "swb200_conditioning", "swb200_forward", "swb200_gemm",
     "swb200_gemm_qkv", "swb200_gemm_swiglu", "swb200_gemm_embed", "swb200_gemm_head", "swb200_patch_gather",
     "swb200_ln_mod_residual", "swb200_window_attention", "swb200_rollout_noise", "swb200_rollout_forcings",
-    "swb200_rollout_advance",
+    "swb200_rollout_advance", "swb200_trace_enable", "swb200_trace_report",
 )
 
 _i32, _f32, _vp, _sz = C.c_int32, C.c_float, C.c_void_p, C.c_size_t
@@ -73,6 +73,8 @@ def _declare(lib):
         "swb200_rollout_noise": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int64, _vp]),
         "swb200_rollout_forcings": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp]),
         "swb200_rollout_advance": (C.c_int, [_vp, _vp]),
+        "swb200_trace_enable": (C.c_int, [C.c_int]),
+        "swb200_trace_report": (C.c_int, [C.c_char_p, _sz]),
     }
     assert set(sig) == set(EXPORTS)
     for name, (res, args) in sig.items():

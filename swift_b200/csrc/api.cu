@@ -5,10 +5,47 @@
 #include "gemm_sm100.cuh"
 #include "kernels.h"
 
+#include <string.h>
+#include <string>
+#include <utility>
+#include <vector>
+
 using namespace swb;
 
 namespace {
 
+// ------------------------------------------------------------------------------------------------
+// Optional in-situ tracing (swb200_trace_enable): CUDA events around every kernel of swb200_forward, so per-kernel
+// durations can be read at the clocks of the real, power-capped step instead of under a profiler.  Off by default
+// (and illegal during graph capture).
+enum TraceSlot { T_GATHER = 0, T_EMBED, T_QKV, T_ATTN, T_WO, T_LN, T_W1, T_W2, T_HEAD, T_NSLOTS };
+const char* const kTraceNames[T_NSLOTS] = {"patch_gather", "gemm_embed", "gemm_qkv", "window_attention", "gemm_wo",
+                                           "ln_mod_residual", "gemm_w1_swiglu", "gemm_w2", "gemm_head"};
+struct Trace {
+  bool on = false;
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev;
+  double ms[T_NSLOTS] = {0};
+  long n[T_NSLOTS] = {0};
+} g_trace;
+
+struct TraceScope {
+  int slot;
+  cudaStream_t st;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  TraceScope(int s, cudaStream_t stream) : slot(s), st(stream) {
+    if (g_trace.on) {
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      cudaEventRecord(e0, st);
+    }
+  }
+  ~TraceScope() {
+    if (e0) {
+      cudaEventRecord(e1, st);
+      g_trace.ev.push_back({slot, {e0, e1}});
+    }
+  }
+};
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -167,9 +204,10 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
     void* hbuf = ws + w.h;
 
     // 1. concat + patchify + cast
+    { TraceScope ts_(T_GATHER, stream);
     rc = launch_patch_gather(x0 + b0 * img_in0, c0, scale0, x1 ? x1 + b0 * img_in1 : nullptr, c1, a_emb,
                              g.k_embed_total, m->k_embed, m->split_embed, F16, bc, m->img_h, m->img_w, m->patch_h,
-                             m->patch_w, stream);
+                             m->patch_w, stream); }
     if (rc) return rc;
     // 2. patch-embed GEMM (+bias +pos_embed)
     {
@@ -179,7 +217,8 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
       p.bias = m->b_embed;
       p.pos = m->pos_embed;
       p.pos_rows = g.tokens;
-      rc = launch_gemm(EPI_EMBED, kDefaultCG, F16, a_emb, g.k_embed_total, m->w_embed, g.k_embed_total, p, stream);
+      { TraceScope ts_(T_EMBED, stream);
+      rc = launch_gemm(EPI_EMBED, kDefaultCG, F16, a_emb, g.k_embed_total, m->w_embed, g.k_embed_total, p, stream); }
       if (rc) return rc;
     }
     // 3. transformer blocks
@@ -192,29 +231,34 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
         p.heads = H;
         p.dmodel = D;
         const auto* wq = static_cast<const __nv_bfloat16*>(m->w_qkv) + static_cast<size_t>(l) * 3 * D * D;
-        rc = launch_gemm(EPI_QKV, kDefaultCG, F16, xhl, 2 * D, wq, D, p, stream);
+        { TraceScope ts_(T_QKV, stream);
+        rc = launch_gemm(EPI_QKV, kDefaultCG, F16, xhl, 2 * D, wq, D, p, stream); }
         if (rc) return rc;
       }
+      { TraceScope ts_(T_ATTN, stream);
       rc = launch_window_attention(qkv, attn, bc, g.gh, g.gw, H, shifted ? m->shift_h : 0, shifted ? m->shift_w : 0,
-                                   F16, m->attn_impl, stream);
+                                   F16, m->attn_impl, stream); }
       if (rc) return rc;
       {
         GemmParams p = base_params(M, D, D);
         p.out0 = branch;
         p.ldo = D;
         const auto* wo = static_cast<const __nv_bfloat16*>(m->w_o) + static_cast<size_t>(l) * D * D;
-        rc = launch_gemm(epi_branch, kDefaultCG, F16, attn, D, wo, D, p, stream);
+        { TraceScope ts_(T_WO, stream);
+        rc = launch_gemm(epi_branch, kDefaultCG, F16, attn, D, wo, D, p, stream); }
         if (rc) return rc;
       }
+      { TraceScope ts_(T_LN, stream);
       rc = launch_ln_mod_residual(branch, BR16, xhl, gain + (static_cast<size_t>(2 * l) * B + b0) * D,
-                                  bias + (static_cast<size_t>(2 * l) * B + b0) * D, M, D, g.tokens, 1e-6f, F16, stream);
+                                  bias + (static_cast<size_t>(2 * l) * B + b0) * D, M, D, g.tokens, 1e-6f, F16, stream); }
       if (rc) return rc;
       {
         GemmParams p = base_params(M, 2 * Dff, D);
         p.out0 = hbuf;
         p.ldo = Dff;
         const auto* w1 = static_cast<const __nv_bfloat16*>(m->w_1) + static_cast<size_t>(l) * 2 * Dff * D;
-        rc = launch_gemm(EPI_SWIGLU, kDefaultCG, F16, xhl, 2 * D, w1, D, p, stream);
+        { TraceScope ts_(T_W1, stream);
+        rc = launch_gemm(EPI_SWIGLU, kDefaultCG, F16, xhl, 2 * D, w1, D, p, stream); }
         if (rc) return rc;
       }
       {
@@ -222,11 +266,13 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
         p.out0 = branch;
         p.ldo = D;
         const auto* w2 = static_cast<const __nv_bfloat16*>(m->w_2) + static_cast<size_t>(l) * D * Dff;
-        rc = launch_gemm(epi_branch, kDefaultCG, F16, hbuf, Dff, w2, Dff, p, stream);
+        { TraceScope ts_(T_W2, stream);
+        rc = launch_gemm(epi_branch, kDefaultCG, F16, hbuf, Dff, w2, Dff, p, stream); }
         if (rc) return rc;
       }
+      { TraceScope ts_(T_LN, stream);
       rc = launch_ln_mod_residual(branch, BR16, xhl, gain + (static_cast<size_t>(2 * l + 1) * B + b0) * D,
-                                  bias + (static_cast<size_t>(2 * l + 1) * B + b0) * D, M, D, g.tokens, 1e-6f, F16, stream);
+                                  bias + (static_cast<size_t>(2 * l + 1) * B + b0) * D, M, D, g.tokens, 1e-6f, F16, stream); }
       if (rc) return rc;
     }
     // 4. head GEMM + pixel shuffle + sampler update
@@ -238,8 +284,9 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
       if (u.state) u.state += b0 * static_cast<size_t>(u.state_channels) * m->img_h * m->img_w;
       if (u.phys) u.phys += b0 * img_out;
       // the head reads the residual pair directly: K = 2D ([hi | lo] x [W | W]) or K = D (hi only), row pitch 2D
+      { TraceScope ts_(T_HEAD, stream);
       rc = swb200_gemm_head(kDefaultCG, m, xhl, 2 * D, g.k_head_total, bc, &u, y ? y + b0 * img_out : nullptr,
-                            stream_);
+                            stream_); }
       if (rc) return rc;
     }
   }
@@ -344,6 +391,41 @@ SWB200_API int swb200_window_attention(const void* qkv, void* out, int B, int gr
   SWB_REQUIRE(qkv && out, "swb200_window_attention: NULL pointer");
   return launch_window_attention(qkv, out, B, grid_h, grid_w, heads, shift_h, shift_w, act_fp16, impl,
                                  static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------------ tracing
+
+SWB200_API int swb200_trace_enable(int on) {
+  g_trace.on = on != 0;
+  if (!on) return SWB_OK;
+  for (int i = 0; i < T_NSLOTS; ++i) { g_trace.ms[i] = 0; g_trace.n[i] = 0; }
+  return SWB_OK;
+}
+
+SWB200_API int swb200_trace_report(char* buf, size_t buf_bytes) {
+  SWB_REQUIRE(buf && buf_bytes > 0, "swb200_trace_report: NULL buffer");
+  SWB_CHECK_CUDA(cudaDeviceSynchronize());
+  for (auto& e : g_trace.ev) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e.second.first, e.second.second) == cudaSuccess) {
+      g_trace.ms[e.first] += ms;
+      g_trace.n[e.first] += 1;
+    }
+    cudaEventDestroy(e.second.first);
+    cudaEventDestroy(e.second.second);
+  }
+  g_trace.ev.clear();
+  std::string out = "{";
+  char tmp[160];
+  for (int i = 0; i < T_NSLOTS; ++i) {
+    snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"ms\": %.4f, \"launches\": %ld}", i ? ", " : "", kTraceNames[i],
+             g_trace.ms[i], g_trace.n[i]);
+    out += tmp;
+  }
+  out += "}";
+  SWB_REQUIRE(out.size() + 1 <= buf_bytes, "swb200_trace_report: buffer too small (%zu needed)", out.size() + 1);
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return SWB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ rollout glue
