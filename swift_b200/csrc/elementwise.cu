@@ -112,9 +112,9 @@ int launch_patch_gather(const float* src0, int C0, float scale0, const float* sr
 // x = hi + lo (about 22 significant bits in fp16 mode); hi is at the same time the A operand of the next GEMM, so no
 // separate 16-bit copy is written and the row costs 2 (branch) + 4 (read) + 4 (write) bytes per element.
 // One warp per token row; the row lives in registers (two-pass mean/variance in fp32); every global load is issued
-// before the first use; accesses are 8 / 16 bytes per lane, lane-strided.
+// before the first use; accesses are 16 bytes per lane, lane-strided (512 contiguous bytes per warp request).
 // BR16: the branch is stored in the 16-bit operand format (fp16 mode) instead of fp32.
-template <int NV4, bool F16, bool BR16>
+template <int NV8, bool F16, bool BR16>
 __global__ void __launch_bounds__(128) ln_mod_residual_kernel(const void* __restrict__ branch_, uint16_t* __restrict__ xhl,
                                                               const float* __restrict__ gain,
                                                               const float* __restrict__ bias, int M, int D,
@@ -122,57 +122,73 @@ __global__ void __launch_bounds__(128) ln_mod_residual_kernel(const void* __rest
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
-  const int nv = D >> 2;                                   // groups of 4 elements per row
-  uint2* xh = reinterpret_cast<uint2*>(xhl + static_cast<size_t>(row) * 2 * D);
-  uint2* xl = xh + nv;
-  float4 v[NV4];
-  uint2 rh[NV4], rl[NV4];
-  auto unpack4 = [](uint2 r) {
-    return make_float4(unpack_act1<F16>(static_cast<uint16_t>(r.x & 0xffffu)), unpack_act1<F16>(static_cast<uint16_t>(r.x >> 16)),
-                       unpack_act1<F16>(static_cast<uint16_t>(r.y & 0xffffu)), unpack_act1<F16>(static_cast<uint16_t>(r.y >> 16)));
+  const int ng = D >> 3;                                   // groups of 8 elements (16 bytes of 16-bit data) per row
+  uint4* xh = reinterpret_cast<uint4*>(xhl + static_cast<size_t>(row) * 2 * D);
+  uint4* xl = xh + ng;
+  float v[NV8][8];
+  uint4 rh[NV8], rl[NV8];
+  auto unpack8 = [](uint4 r, float* o) {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      o[2 * j] = unpack_act1<F16>(static_cast<uint16_t>(w[j] & 0xffffu));
+      o[2 * j + 1] = unpack_act1<F16>(static_cast<uint16_t>(w[j] >> 16));
+    }
   };
+  // all global loads of the row (branch, hi, lo) are issued before the first use
   if constexpr (BR16) {
-    const uint2* br = reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(branch_) + static_cast<size_t>(row) * D);
-    uint2 raw[NV4];
+    const uint4* br = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(branch_) + static_cast<size_t>(row) * D);
+    uint4 raw[NV8];
 #pragma unroll
-    for (int i = 0; i < NV4; ++i) {
+    for (int i = 0; i < NV8; ++i) {
       const int c = i * 32 + lane;
-      raw[i] = (c < nv) ? __ldg(br + c) : make_uint2(0u, 0u);
+      raw[i] = (c < ng) ? __ldg(br + c) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
-    for (int i = 0; i < NV4; ++i) {
+    for (int i = 0; i < NV8; ++i) {
       const int c = i * 32 + lane;
-      rh[i] = (c < nv) ? xh[c] : make_uint2(0u, 0u);
-      rl[i] = (c < nv) ? xl[c] : make_uint2(0u, 0u);
+      rh[i] = (c < ng) ? xh[c] : make_uint4(0u, 0u, 0u, 0u);
+      rl[i] = (c < ng) ? xl[c] : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
-    for (int i = 0; i < NV4; ++i) v[i] = unpack4(raw[i]);
+    for (int i = 0; i < NV8; ++i) unpack8(raw[i], v[i]);
   } else {
     const float4* br = reinterpret_cast<const float4*>(static_cast<const float*>(branch_) + static_cast<size_t>(row) * D);
 #pragma unroll
-    for (int i = 0; i < NV4; ++i) {
+    for (int i = 0; i < NV8; ++i) {
       const int c = i * 32 + lane;
-      v[i] = (c < nv) ? __ldg(br + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+      if (c < ng) {
+        a = __ldg(br + 2 * c);
+        b = __ldg(br + 2 * c + 1);
+      }
+      v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w;
+      v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
     }
 #pragma unroll
-    for (int i = 0; i < NV4; ++i) {
+    for (int i = 0; i < NV8; ++i) {
       const int c = i * 32 + lane;
-      rh[i] = (c < nv) ? xh[c] : make_uint2(0u, 0u);
-      rl[i] = (c < nv) ? xl[c] : make_uint2(0u, 0u);
+      rh[i] = (c < ng) ? xh[c] : make_uint4(0u, 0u, 0u, 0u);
+      rl[i] = (c < ng) ? xl[c] : make_uint4(0u, 0u, 0u, 0u);
     }
   }
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV4; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  for (int i = 0; i < NV8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum += v[i][j];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float mean = sum / static_cast<float>(D);
   float var = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV4; ++i) {
-    if (i * 32 + lane < nv) {
-      const float a = v[i].x - mean, b = v[i].y - mean, c2 = v[i].z - mean, d = v[i].w - mean;
-      var += (a * a + b * b) + (c2 * c2 + d * d);
+  for (int i = 0; i < NV8; ++i) {
+    if (i * 32 + lane < ng) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mean;
+        var = fmaf(d, d, var);
+      }
     }
   }
 #pragma unroll
@@ -182,33 +198,36 @@ __global__ void __launch_bounds__(128) ln_mod_residual_kernel(const void* __rest
   const float4* g4 = reinterpret_cast<const float4*>(gain + static_cast<size_t>(b) * D);
   const float4* b4 = reinterpret_cast<const float4*>(bias + static_cast<size_t>(b) * D);
 #pragma unroll
-  for (int i = 0; i < NV4; ++i) {
+  for (int i = 0; i < NV8; ++i) {
     const int c = i * 32 + lane;
-    if (c < nv) {
-      const float4 g = __ldg(g4 + c), bb = __ldg(b4 + c);
-      const float4 xh4 = unpack4(rh[i]), xl4 = unpack4(rl[i]);
-      float o[4];
-      o[0] = (xh4.x + xl4.x) + fmaf((v[i].x - mean) * rstd, g.x, bb.x);
-      o[1] = (xh4.y + xl4.y) + fmaf((v[i].y - mean) * rstd, g.y, bb.y);
-      o[2] = (xh4.z + xl4.z) + fmaf((v[i].z - mean) * rstd, g.z, bb.z);
-      o[3] = (xh4.w + xl4.w) + fmaf((v[i].w - mean) * rstd, g.w, bb.w);
-      const uint32_t h0 = pack_act2<F16>(o[0], o[1]), h1 = pack_act2<F16>(o[2], o[3]);
-      xh[c] = make_uint2(h0, h1);
-      const float l0 = o[0] - unpack_act1<F16>(static_cast<uint16_t>(h0 & 0xffffu));
-      const float l1 = o[1] - unpack_act1<F16>(static_cast<uint16_t>(h0 >> 16));
-      const float l2 = o[2] - unpack_act1<F16>(static_cast<uint16_t>(h1 & 0xffffu));
-      const float l3 = o[3] - unpack_act1<F16>(static_cast<uint16_t>(h1 >> 16));
-      xl[c] = make_uint2(pack_act2<F16>(l0, l1), pack_act2<F16>(l2, l3));
+    if (c < ng) {
+      const float4 ga = __ldg(g4 + 2 * c), gb = __ldg(g4 + 2 * c + 1), ba = __ldg(b4 + 2 * c), bb = __ldg(b4 + 2 * c + 1);
+      const float g[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+      const float be[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+      float xhv[8], xlv[8], o[8];
+      unpack8(rh[i], xhv);
+      unpack8(rl[i], xlv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (xhv[j] + xlv[j]) + fmaf((v[i][j] - mean) * rstd, g[j], be[j]);
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        h[j] = pack_act2<F16>(o[2 * j], o[2 * j + 1]);
+        l[j] = pack_act2<F16>(o[2 * j] - unpack_act1<F16>(static_cast<uint16_t>(h[j] & 0xffffu)),
+                              o[2 * j + 1] - unpack_act1<F16>(static_cast<uint16_t>(h[j] >> 16)));
+      }
+      xh[c] = make_uint4(h[0], h[1], h[2], h[3]);
+      xl[c] = make_uint4(l[0], l[1], l[2], l[3]);
     }
   }
 }
 
 int launch_ln_mod_residual(const void* branch, int branch_16bit, void* xhl, const float* gain, const float* bias, int M,
                            int D, int tokens, float eps, int act_f16, cudaStream_t stream) {
-  SWB_REQUIRE(D % 4 == 0, "ln_mod_residual: dim %d must be a multiple of 4", D);
+  SWB_REQUIRE(D % 8 == 0, "ln_mod_residual: dim %d must be a multiple of 8", D);
   SWB_REQUIRE(((reinterpret_cast<uintptr_t>(branch) | reinterpret_cast<uintptr_t>(gain) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0 &&
-                  (reinterpret_cast<uintptr_t>(xhl) & 7) == 0,
-              "ln_mod_residual: pointers must be 16-byte (fp32) / 8-byte (16-bit) aligned");
+                  (reinterpret_cast<uintptr_t>(xhl) & 15) == 0,
+              "ln_mod_residual: pointers must be 16-byte aligned");
   const int rows_per_block = 4;
   dim3 grid((M + rows_per_block - 1) / rows_per_block);
   auto x_ = static_cast<uint16_t*>(xhl);
@@ -221,11 +240,11 @@ int launch_ln_mod_residual(const void* branch, int branch_16bit, void* xhl, cons
       if (branch_16bit) SWB_LN3(V, false, true); else SWB_LN3(V, false, false); \
     }                                                               \
   } while (0)
-  const int nv4 = (D / 4 + 31) / 32;
-  if (nv4 <= 3) SWB_LN(3);
-  else if (nv4 <= 5) SWB_LN(5);
-  else if (nv4 <= 9) SWB_LN(9);
-  else if (nv4 <= 16) SWB_LN(16);
+  const int nv8 = (D / 8 + 31) / 32;
+  if (nv8 <= 2) SWB_LN(2);
+  else if (nv8 <= 3) SWB_LN(3);
+  else if (nv8 <= 5) SWB_LN(5);
+  else if (nv8 <= 8) SWB_LN(8);
   else {
     set_error("ln_mod_residual: dim %d > 2048 unsupported", D);
     return SWB_ERR_INVALID;
