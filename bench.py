@@ -175,6 +175,8 @@ def run_ours(args):
     net.load_state_dict(syn.random_state_dict(cfg, seed=1, prefix="model."), strict=True)
     net = net.to(dev).eval()
     net.model.max_chunk = args.chunk
+    if args.fuse_ln >= 0:
+        net.model.fuse_ln = args.fuse_ln
     eng = net.model.engine()
 
     n_ic = ICS_PER_GPU * n_gpus
@@ -331,6 +333,7 @@ def main():
                     help="scm: Swift 1-step consistency sampler (headline); 2s: TrigFlow diffusion baseline, 20 Heun steps = "
                          "39 denoiser calls per 6 h step (BASELINE.json configs[3])")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end leg (0 = same as --steps)")
+    ap.add_argument("--fuse-ln", type=int, default=-1, help="override SwinV2.fuse_ln (bit 0: wo, bit 1: w2; 0 = separate LN kernel)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SWB200_ABI_VERSION 8
+#define SWB200_ABI_VERSION 9
 #if defined(__GNUC__)
 #define SWB200_API __attribute__((visibility("default")))
 #else
@@ -54,6 +54,7 @@ typedef struct swb200_model {
   int32_t gemm_tile;          /* GEMM tile: 1 = 128x176 single CTA, 2 = 256x176 CTA pair, 3 = 256x352 CTA pair (default) */
   int32_t attn_impl;          /* window attention: 0 = auto (tcgen05 kernel for shifts that are multiples of 8), 1 = mma.sync, 2 = tcgen05 */
   int32_t act_fp16;           /* 16-bit tensor-core operand format of activations AND packed weights: 1 = fp16, 0 = bf16 */
+  int32_t fuse_ln;            /* LayerNorm + modulation + residual add in the GEMM epilogue: bit 0 = wo, bit 1 = w2 (host default 2); 0 = separate kernel */
   float timestep_weight;
   const void* w_embed;
   const float* b_embed;
@@ -135,7 +136,9 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
 /* ---- individual kernels (unit tests, profiling) -------------------------------------------------------- */
 
 /* D[M,N] = A[M,K] (row pitch lda) * W[N,K]^T (row pitch ldw), both fp16 if act_fp16 else both bf16, fp32 accumulate
- * on tcgen05.  epi: 0 store fp32 out[M,ldo], 1 store out[M,ldo] in the 16-bit operand format.
+ * on tcgen05.  epi: 0 store fp32 out[M,ldo], 1 store out[M,ldo] in the 16-bit operand format; profiling only:
+ * 6 = accumulators discarded (main-loop rate), 7 = accumulators read out of TMEM but not stored, 8 = epilogue 1 without
+ * its global stores, 9 = epilogue 1 with per-thread stores instead of the shared-memory transpose.
  * tile: 1 = 128x176 single CTA, 2 = 256x176 CTA pair (cta_group::2), 3 = 256x352 CTA pair. */
 SWB200_API int swb200_gemm(int epi, int tile, int act_fp16, const void* A, int lda, const void* W, int ldw, void* out,
                 int ldo, int M, int N, int K, void* stream);
@@ -149,6 +152,18 @@ SWB200_API int swb200_gemm_swiglu(int tile, int act_fp16, const void* A, int lda
  * [hi | lo] with x = hi + lo (hi is the A operand of the next GEMM, row pitch 2*dim). */
 SWB200_API int swb200_gemm_embed(int tile, int act_fp16, const void* A, int lda, const void* W, int K, const float* bias,
                       const float* pos, int tokens, void* xhl, int M, int dim, void* stream);
+/* Fused post-norm residual update (swinv2.py:83-86, :137-138, :100-101, :211-212):
+ *     x <- x + LayerNorm(A W^T) * gain[b] + bias[b]     on the residual pair xhl[M, 2*dim] (in place), b = row / tokens,
+ * A [M, K] (row pitch lda), W [dim, K]; gain / bias fp32 [B, dim].  The row statistics are exchanged between the CTAs
+ * that hold the column tiles of a row through `ln_ws` (swb200_ln_workspace_bytes(M, dim) bytes, 256-byte aligned,
+ * private to the stream).  `gen` numbers the launches that share ln_ws since its counters were last cleared:
+ * launch 0 clears them (a memset node on `stream`), launch g expects the g launches before it to have completed.
+ * Every CTA of the grid must be resident (the launcher checks the occupancy; do not run other kernels on the device
+ * concurrently). */
+SWB200_API size_t swb200_ln_workspace_bytes(int M, int dim);
+SWB200_API int swb200_gemm_ln_residual(int tile, int act_fp16, const void* A, int lda, const void* W, int K, void* xhl,
+                            const float* gain, const float* bias, int M, int dim, int tokens, void* ln_ws, int gen,
+                            void* stream);
 /* Output head with pixel-shuffle + update; A is [M, K] with K = dim*(1+split). */
 SWB200_API int swb200_gemm_head(int tile, const swb200_model* m, const void* A, int lda, int K, int B,
                      const swb200_update* upd, float* y, void* stream);

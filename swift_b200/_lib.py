@@ -11,7 +11,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libswift_b200.so")
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 # Every symbol ``include/swift_b200.h`` declares; tests check the library exports exactly these.
 EXPORTS = (
@@ -19,7 +19,8 @@ EXPORTS = (
     "swb200_conditioning_scratch_bytes", "swb200_conditioning", "swb200_forward", "swb200_gemm",
     "swb200_gemm_qkv", "swb200_gemm_swiglu", "swb200_gemm_embed", "swb200_gemm_head", "swb200_patch_gather",
     "swb200_ln_mod_residual", "swb200_window_attention", "swb200_rollout_noise", "swb200_rollout_forcings",
-    "swb200_rollout_advance", "swb200_trace_enable", "swb200_trace_report",
+    "swb200_rollout_advance", "swb200_trace_enable", "swb200_trace_report", "swb200_ln_workspace_bytes",
+    "swb200_gemm_ln_residual",
 )
 
 _i32, _f32, _vp, _sz = C.c_int32, C.c_float, C.c_void_p, C.c_size_t
@@ -30,7 +31,8 @@ class Model(C.Structure):
     _fields_ = (
         [(n, _i32) for n in ("img_h", "img_w", "patch_h", "patch_w", "win_h", "win_w", "shift_h", "shift_w",
                              "in_channels", "out_channels", "depth", "dim", "heads", "dff", "aux_dim",
-                             "k_embed", "split_embed", "split_head", "gemm_tile", "attn_impl", "act_fp16")]
+                             "k_embed", "split_embed", "split_head", "gemm_tile", "attn_impl", "act_fp16",
+                             "fuse_ln")]
         + [("timestep_weight", _f32)]
         + [(n, _vp) for n in ("w_embed", "b_embed", "pos_embed", "aux_w", "aux_b", "l1_w", "l1_b", "l2_w", "l2_b",
                               "mod_w", "mod_b", "ln_gamma", "ln_beta", "qscale", "w_qkv", "w_o", "w_1", "w_2",
@@ -73,6 +75,9 @@ def _declare(lib):
         "swb200_rollout_noise": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int64, _vp]),
         "swb200_rollout_forcings": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp]),
         "swb200_rollout_advance": (C.c_int, [_vp, _vp]),
+        "swb200_ln_workspace_bytes": (_sz, [C.c_int, C.c_int]),
+        "swb200_gemm_ln_residual": (C.c_int, [C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int,
+                                              C.c_int, _vp, C.c_int, _vp]),
         "swb200_trace_enable": (C.c_int, [C.c_int]),
         "swb200_trace_report": (C.c_int, [C.c_char_p, _sz]),
     }

@@ -5,6 +5,7 @@
 #include "gemm_sm100.cuh"
 #include "kernels.h"
 
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <utility>
@@ -65,8 +66,22 @@ Geom geom(const swb200_model* m) {
 
 // per-sample workspace layout (offsets in bytes, every buffer 1024-byte aligned per chunk)
 struct Workspace {
-  size_t xhl, qkv, attn, branch, h, total;   // sizes for `chunk` samples; a_embed aliases qkv
+  size_t xhl, qkv, attn, branch, h, lnws, total;   // sizes for `chunk` samples; a_embed aliases qkv
 };
+
+// LayerNorm statistics exchange of the fused wo / w2 epilogue: [counters: Mpad/32 u32, padded to 1 KB][stats: groups x Mpad float2]
+struct LnWs {
+  size_t counters_bytes, total;
+  int stride, groups;
+};
+LnWs ln_ws_layout(int M, int dim) {
+  LnWs l;
+  l.stride = (M + 255) / 256 * 256;
+  l.groups = (dim + kUmmaN - 1) / kUmmaN + 1;             // enough for every tile configuration
+  l.counters_bytes = align_up(static_cast<size_t>(l.stride / 32) * sizeof(unsigned), 1024);
+  l.total = l.counters_bytes + static_cast<size_t>(l.groups) * l.stride * sizeof(float2);
+  return l;
+}
 Workspace carve(const swb200_model* m, int chunk) {
   const Geom g = geom(m);
   const size_t M = static_cast<size_t>(chunk) * g.tokens;
@@ -84,6 +99,7 @@ Workspace carve(const swb200_model* m, int chunk) {
   w.attn = take(M * m->dim * 2);
   w.branch = take(M * m->dim * 4);
   w.h = take(M * static_cast<size_t>(m->dff) * 2);
+  w.lnws = take(ln_ws_layout(static_cast<int>(M), m->dim).total);
   w.total = off;
   return w;
 }
@@ -106,6 +122,8 @@ int validate(const swb200_model* m) {
   SWB_REQUIRE(m->depth > 0 && m->aux_dim >= 0, "bad depth/aux_dim");
   SWB_REQUIRE(m->gemm_tile >= 1 && m->gemm_tile <= 3, "gemm_tile must be 1, 2 or 3 (got %d)", m->gemm_tile);
   SWB_REQUIRE(m->attn_impl >= 0 && m->attn_impl <= 2, "attn_impl must be 0, 1 or 2 (got %d)", m->attn_impl);
+  SWB_REQUIRE(m->fuse_ln >= 0 && m->fuse_ln <= 3 && (m->fuse_ln == 0 || m->dim <= 12 * kUmmaN),
+              "fuse_ln must be 0..3 (bit 0: wo, bit 1: w2) and needs dim <= 2112 (got %d, dim %d)", m->fuse_ln, m->dim);
   SWB_REQUIRE(m->gemm_tile != 3 || m->dff % (2 * kHeadDim) == 0,
               "gemm_tile 3 (256x352) needs mlp dim %d to be a multiple of 176", m->dff);
   return SWB_OK;
@@ -202,6 +220,9 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
     const int BR16 = F16;
     const int epi_branch = BR16 ? EPI_STORE_ACT : EPI_STORE_F32;
     void* hbuf = ws + w.h;
+    const bool fuse_wo = (m->fuse_ln & 1) != 0, fuse_w2 = (m->fuse_ln & 2) != 0;
+    void* lnws = ws + w.lnws;
+    int ln_gen = 0;                             // fused launches of this chunk so far (the first one clears the counters)
 
     // 1. concat + patchify + cast
     { TraceScope ts_(T_GATHER, stream);
@@ -239,19 +260,26 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
       rc = launch_window_attention(qkv, attn, bc, g.gh, g.gw, H, shifted ? m->shift_h : 0, shifted ? m->shift_w : 0,
                                    F16, m->attn_impl, stream); }
       if (rc) return rc;
-      {
+      const auto* wo = static_cast<const __nv_bfloat16*>(m->w_o) + static_cast<size_t>(l) * D * D;
+      const float* gain_a = gain + (static_cast<size_t>(2 * l) * B + b0) * D;
+      const float* bias_a = bias + (static_cast<size_t>(2 * l) * B + b0) * D;
+      if (fuse_wo) {
+        // wo projection + LayerNorm + modulation + residual add in one kernel (no branch buffer)
+        { TraceScope ts_(T_WO, stream);
+        rc = swb200_gemm_ln_residual(kDefaultCG, F16, attn, D, wo, D, xhl, gain_a, bias_a, M, D, g.tokens, lnws, ln_gen++,
+                                     stream_); }
+        if (rc) return rc;
+      } else {
         GemmParams p = base_params(M, D, D);
         p.out0 = branch;
         p.ldo = D;
-        const auto* wo = static_cast<const __nv_bfloat16*>(m->w_o) + static_cast<size_t>(l) * D * D;
         { TraceScope ts_(T_WO, stream);
         rc = launch_gemm(epi_branch, kDefaultCG, F16, attn, D, wo, D, p, stream); }
         if (rc) return rc;
+        { TraceScope ts_(T_LN, stream);
+        rc = launch_ln_mod_residual(branch, BR16, xhl, gain_a, bias_a, M, D, g.tokens, 1e-6f, F16, stream); }
+        if (rc) return rc;
       }
-      { TraceScope ts_(T_LN, stream);
-      rc = launch_ln_mod_residual(branch, BR16, xhl, gain + (static_cast<size_t>(2 * l) * B + b0) * D,
-                                  bias + (static_cast<size_t>(2 * l) * B + b0) * D, M, D, g.tokens, 1e-6f, F16, stream); }
-      if (rc) return rc;
       {
         GemmParams p = base_params(M, 2 * Dff, D);
         p.out0 = hbuf;
@@ -261,19 +289,25 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
         rc = launch_gemm(EPI_SWIGLU, kDefaultCG, F16, xhl, 2 * D, w1, D, p, stream); }
         if (rc) return rc;
       }
-      {
+      const auto* w2 = static_cast<const __nv_bfloat16*>(m->w_2) + static_cast<size_t>(l) * D * Dff;
+      const float* gain_f = gain + (static_cast<size_t>(2 * l + 1) * B + b0) * D;
+      const float* bias_f = bias + (static_cast<size_t>(2 * l + 1) * B + b0) * D;
+      if (fuse_w2) {
+        { TraceScope ts_(T_W2, stream);
+        rc = swb200_gemm_ln_residual(kDefaultCG, F16, hbuf, Dff, w2, Dff, xhl, gain_f, bias_f, M, D, g.tokens, lnws,
+                                     ln_gen++, stream_); }
+        if (rc) return rc;
+      } else {
         GemmParams p = base_params(M, D, Dff);
         p.out0 = branch;
         p.ldo = D;
-        const auto* w2 = static_cast<const __nv_bfloat16*>(m->w_2) + static_cast<size_t>(l) * D * Dff;
         { TraceScope ts_(T_W2, stream);
         rc = launch_gemm(epi_branch, kDefaultCG, F16, hbuf, Dff, w2, Dff, p, stream); }
         if (rc) return rc;
+        { TraceScope ts_(T_LN, stream);
+        rc = launch_ln_mod_residual(branch, BR16, xhl, gain_f, bias_f, M, D, g.tokens, 1e-6f, F16, stream); }
+        if (rc) return rc;
       }
-      { TraceScope ts_(T_LN, stream);
-      rc = launch_ln_mod_residual(branch, BR16, xhl, gain + (static_cast<size_t>(2 * l + 1) * B + b0) * D,
-                                  bias + (static_cast<size_t>(2 * l + 1) * B + b0) * D, M, D, g.tokens, 1e-6f, F16, stream); }
-      if (rc) return rc;
     }
     // 4. head GEMM + pixel shuffle + sampler update
     {
@@ -297,7 +331,8 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
 
 SWB200_API int swb200_gemm(int epi, int tile, int act_fp16, const void* A, int lda, const void* W, int ldw, void* out,
                 int ldo, int M, int N, int K, void* stream) {
-  SWB_REQUIRE(epi == EPI_STORE_F32 || epi == EPI_STORE_ACT, "swb200_gemm: epi must be 0 (fp32) or 1 (activation format)");
+  SWB_REQUIRE(epi == EPI_STORE_F32 || epi == EPI_STORE_ACT || (epi >= EPI_DISCARD && epi <= EPI_DIRECT),
+              "swb200_gemm: epi must be 0 (fp32), 1 (activation format), 6..9 (profiling variants)");
   SWB_REQUIRE(A && W && out, "swb200_gemm: NULL pointer");
   SWB_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && N % (epi == EPI_STORE_F32 ? 4 : 8) == 0,
               "swb200_gemm: out must be 16-byte aligned, ldo %% 8 == 0, N %% 4 (fp32) / 8 (16-bit) == 0");
@@ -340,6 +375,42 @@ SWB200_API int swb200_gemm_embed(int tile, int act_fp16, const void* A, int lda,
   p.pos = pos;
   p.pos_rows = tokens;
   return launch_gemm(EPI_EMBED, tile, act_fp16, A, lda, W, K, p, static_cast<cudaStream_t>(stream));
+}
+
+SWB200_API size_t swb200_ln_workspace_bytes(int M, int dim) {
+  if (M <= 0 || dim <= 0) return 0;
+  return ln_ws_layout(M, dim).total;
+}
+
+SWB200_API int swb200_gemm_ln_residual(int tile, int act_fp16, const void* A, int lda, const void* W, int K, void* xhl,
+                                       const float* gain, const float* bias, int M, int dim, int tokens, void* ln_ws, int gen,
+                                       void* stream_) {
+  SWB_REQUIRE(A && W && xhl && gain && bias && ln_ws, "swb200_gemm_ln_residual: NULL pointer");
+  SWB_REQUIRE(dim % kSlot == 0 && tokens > 0 && tokens % 32 == 0 && gen >= 0,
+              "swb200_gemm_ln_residual: dim %d must be a multiple of 88, tokens %d a multiple of 32, gen >= 0", dim, tokens);
+  SWB_REQUIRE(((reinterpret_cast<uintptr_t>(xhl) | reinterpret_cast<uintptr_t>(gain) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(ln_ws) & 255) == 0,
+              "swb200_gemm_ln_residual: xhl / gain / bias must be 16-byte aligned, ln_ws 256-byte aligned");
+  SWB_REQUIRE(tile >= 1 && tile <= 3, "swb200_gemm_ln_residual: tile config must be 1, 2 or 3 (got %d)", tile);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const LnWs l = ln_ws_layout(M, dim);
+  if (gen == 0) SWB_CHECK_CUDA(cudaMemsetAsync(ln_ws, 0, l.counters_bytes, stream));
+  const int tile_n = tile == 3 ? 2 * kUmmaN : kUmmaN;
+  const int groups = (dim + tile_n - 1) / tile_n * (tile == 3 ? 2 : 1);
+  SWB_REQUIRE(groups <= 12, "swb200_gemm_ln_residual: dim %d needs %d statistics groups (at most 12 are supported)", dim, groups);
+  GemmParams p = base_params(M, dim, K);
+  p.xhl = static_cast<uint16_t*>(xhl);
+  p.gain = gain;
+  p.lnbias = bias;
+  p.tokens = tokens;
+  p.ln_counter = static_cast<unsigned*>(ln_ws);
+  p.ln_stats = reinterpret_cast<float2*>(static_cast<uint8_t*>(ln_ws) + l.counters_bytes);
+  p.ln_stride = l.stride;
+  p.ln_target = static_cast<unsigned>(groups) * static_cast<unsigned>(gen + 1);
+  p.ln_eps = 1e-6f;
+  static const int dbg = getenv("SWB_LN_DEBUG") ? atoi(getenv("SWB_LN_DEBUG")) : 0;   // profiling knob, see GemmParams
+  p.ln_debug = dbg;
+  return launch_gemm(EPI_LN_RES, tile, act_fp16, A, lda, W, K, p, stream);
 }
 
 SWB200_API int swb200_gemm_head(int tile, const swb200_model* m, const void* A, int lda, int K, int B,

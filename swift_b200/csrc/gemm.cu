@@ -88,6 +88,13 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   const int num_tiles = tiles_m * tiles_n;
   int clusters = num_sms() / CG;
   if (clusters > num_tiles) clusters = num_tiles;
+  if constexpr (EPI == EPI_LN_RES) {
+    // the groups that exchange LayerNorm statistics (the tiles_n column tiles of one row block) must run at the same
+    // time: keep the cluster count a multiple of tiles_n so that they sit on neighbouring clusters in every wave
+    SWB_REQUIRE(clusters >= tiles_n, "gemm_ln_residual: %d column tiles need at least as many CTA clusters (%d)", tiles_n,
+                clusters);
+    clusters = clusters / tiles_n * tiles_n;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * CG);
   cfg.blockDim = dim3(S::kThreads);
@@ -100,6 +107,13 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if constexpr (EPI == EPI_LN_RES) {
+    // the statistics exchange spins on other CTAs of this grid: every cluster has to be resident
+    static int max_clusters = -1;
+    if (max_clusters < 0) SWB_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+    SWB_REQUIRE(max_clusters >= clusters, "gemm_ln_residual: only %d of %d CTA clusters can be co-resident", max_clusters,
+                clusters);
+  }
   SWB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
   return SWB_OK;
 }
@@ -114,6 +128,11 @@ static int launch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, con
     case EPI_QKV: return launch_inst<NSUB, CG, EPI_QKV, F16>(ta, tb, p, stream);
     case EPI_SWIGLU: return launch_inst<NSUB, CG, EPI_SWIGLU, F16>(ta, tb, p, stream);
     case EPI_HEAD: return launch_inst<NSUB, CG, EPI_HEAD, F16>(ta, tb, p, stream);
+    case EPI_LN_RES: return launch_inst<NSUB, CG, EPI_LN_RES, F16>(ta, tb, p, stream);
+    case EPI_DISCARD: return launch_inst<NSUB, CG, EPI_DISCARD, F16>(ta, tb, p, stream);
+    case EPI_DRAIN: return launch_inst<NSUB, CG, EPI_DRAIN, F16>(ta, tb, p, stream);
+    case EPI_SMEM_ONLY: return launch_inst<NSUB, CG, EPI_SMEM_ONLY, F16>(ta, tb, p, stream);
+    case EPI_DIRECT: return launch_inst<NSUB, CG, EPI_DIRECT, F16>(ta, tb, p, stream);
   }
   set_error("unknown GEMM epilogue %d", epi);
   return SWB_ERR_INVALID;

@@ -30,6 +30,12 @@ enum GemmEpilogue : int {
   EPI_QKV = 3,         // scaled-cosine q/k normalisation fused; out0 = [3][heads][M][96] 16-bit
   EPI_SWIGLU = 4,      // tile = [gate slots | up slots];  out0[M, N/2] 16-bit = silu(gate) * up
   EPI_HEAD = 5,        // pixel-shuffle to NCHW + sampler update: y = alpha*xt + beta*F + gamma*fprev
+  EPI_LN_RES = 10,     // x += LayerNorm(acc) * gain[b] + bias[b] on the residual pair xhl (row statistics exchanged between
+                       // the CTAs that hold the other column tiles of the same rows)
+  EPI_DISCARD = 6,     // profiling: accumulators handed back unread (main-loop rate)
+  EPI_DRAIN = 7,       // profiling: accumulators read out of TMEM, nothing stored (main loop + drain)
+  EPI_SMEM_ONLY = 8,   // profiling: EPI_STORE_ACT without its global stores (drain + pack + smem transposes)
+  EPI_DIRECT = 9,      // profiling: EPI_STORE_ACT with per-thread 16-byte global stores (no smem transpose)
 };
 
 struct GemmParams {
@@ -58,6 +64,16 @@ struct GemmParams {
   const float* d_std;
   float* phys;             // [B, C, H, W] physical-space state (optional)
   int zero_channel;        // channel forced to 0 (era5.py zero_field) or -1
+  // EPI_LN_RES (N == model dim; `tokens` rows per sample)
+  uint16_t* xhl;           // [M, 2N] residual stream as a 16-bit [hi | lo] pair, updated in place
+  const float* gain;       // [B, N]  gamma * (1 + scale(t))
+  const float* lnbias;     // [B, N]  beta * (1 + scale(t)) + shift(t)
+  float2* ln_stats;        // [tiles_n * NSUB][ln_stride]  per-row partial (sum, M2) of each 176-column group
+  unsigned* ln_counter;    // [ceil(M / 32)]  groups that have published their partials (monotonic over launches)
+  unsigned ln_target;      // counter value that completes this launch
+  int ln_stride;
+  float ln_eps;
+  int ln_debug;            // profiling only (SWB_LN_DEBUG): bit 0 = do not wait for the other groups, bit 1 = skip the x update
 };
 
 constexpr int kBlockM = 128;     // rows of A per CTA
@@ -80,7 +96,7 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kEpiWarps = 4 * NSUB;
   static constexpr int kThreads = 128 + 32 * kEpiWarps;
-  static constexpr int kScratchBytes = kEpiWarps * 4096;       // per-warp 32 x 128 B transpose buffer
+  static constexpr int kScratchBytes = kEpiWarps * (4096 + 256);   // per-warp 32 x 128 B transpose buffer + 32 x (rstd, shift)
   static constexpr int kBarBytes = 1024;
   static constexpr int kMaxSmem = 227 * 1024;
   static constexpr int kStagesRaw = (kMaxSmem - kScratchBytes - kBarBytes - 1024) / kStageBytes;
@@ -401,6 +417,53 @@ __device__ __forceinline__ void store_slot16(void* out, int ldo, int N, const Ep
   if (ch > 8) warp_store_rows<3>(g + 128, pitch, reinterpret_cast<const uint4*>(w + 32), e.scratch, e.lane, e.rows_valid, ch - 8);
 }
 
+// profiling variants of warp_store_rows: MODE 1 = transposes only (the global store is predicated off at run time),
+// MODE 2 = every lane stores the chunks of its own row directly
+template <int NCH, int MODE>
+__device__ __forceinline__ void warp_store_rows_prof(uint8_t* g_row0, size_t pitch_bytes, const uint4* v, uint32_t scratch,
+                                                     int lane, int rows_valid, int chunks_valid, int never) {
+  if constexpr (MODE == 2) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+      if (lane < rows_valid && c < chunks_valid) *reinterpret_cast<uint4*>(g_row0 + lane * pitch_bytes + c * 16) = v[c];
+  } else {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) st_shared_v4(scratch + lane * 128 + ((c ^ (lane & 7)) << 4), v[c]);
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < NCH; ++it) {
+      const int idx = it * 32 + lane;
+      const int r = idx / NCH, c = idx - r * NCH;
+      const uint4 q = ld_shared_v4(scratch + r * 128 + ((c ^ (r & 7)) << 4));
+      if (r < rows_valid && c < chunks_valid && q.x == static_cast<uint32_t>(never))
+        *reinterpret_cast<uint4*>(g_row0 + r * pitch_bytes + c * 16) = q;
+    }
+    __syncwarp();
+  }
+}
+
+template <bool F16, int MODE, typename Release>
+__device__ __forceinline__ void epi_group_store16_prof(const GemmParams& p, const EpiCtx& e, uint32_t tacc, int n_lo, int n_hi,
+                                                       Release&& release) {
+  float v[kSlot];
+  uint32_t wa[44], wb[44];
+  tmem_load_cols<kSlot>(tacc, v);
+  pack_row16<F16, 44>(v, wa);
+  tmem_load_cols<kSlot>(tacc + kSlot, v);
+  release();
+  pack_row16<F16, 44>(v, wb);
+  const size_t pitch = static_cast<size_t>(p.ldo) * 2;
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    const int n0 = hf ? n_hi : n_lo;
+    const uint32_t* w = hf ? wb : wa;
+    if (n0 >= p.N) continue;
+    uint8_t* g = reinterpret_cast<uint8_t*>(static_cast<uint16_t*>(p.out0) + static_cast<size_t>(e.row0) * p.ldo + n0);
+    warp_store_rows_prof<8, MODE>(g, pitch, reinterpret_cast<const uint4*>(w), e.scratch, e.lane, e.rows_valid, 8, p.heads + 0x7fc00000);
+    warp_store_rows_prof<3, MODE>(g + 128, pitch, reinterpret_cast<const uint4*>(w + 32), e.scratch, e.lane, e.rows_valid, 3, p.heads + 0x7fc00000);
+  }
+}
+
 template <bool F16, typename Release>
 __device__ __forceinline__ void epi_group_store16(const GemmParams& p, const EpiCtx& e, uint32_t tacc, int n_lo, int n_hi,
                                                   Release&& release) {
@@ -482,6 +545,252 @@ __device__ __forceinline__ void epi_group_swiglu(const GemmParams& p, const EpiC
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// EPI_LN_RES: the post-norm residual update of the reference (models/swinv2.py:83-86, :137-138, :100-101, :211-212)
+//     x <- x + LayerNorm(branch) * gain[b] + bias[b],     branch = A W^T  (wo or w2 projection)
+// done in the GEMM epilogue, so the branch never exists in HBM.  A LayerNorm row spans every column tile, while one
+// epilogue warp only sees its 176 columns of 32 rows: each warp publishes the (sum, M2) of its part of the rows to
+// global memory, bumps a per-32-row counter and spins until all tiles_n * NSUB groups of those rows have arrived (they
+// run at the same time on neighbouring clusters of this persistent kernel: the launcher keeps the number of clusters a
+// multiple of tiles_n, every CTA is resident, and the accumulator has already been handed back, so main loops never
+// wait on this exchange).  The partials are merged with Chan's formula; the branch is held in registers as fp16 pairs
+// (the same rounding the stand-alone LN kernel sees in fp16 mode) and goes through the coalescing transpose, x hi / lo
+// are read and written in place with full-line accesses.
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned ld_relaxed_gpu_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ float2 ld_shared_f2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_shared_f2(uint32_t addr, float2 v) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ float2 h2_to_f2(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
+
+// 8 consecutive columns of one row: x (hi + lo) += fma(branch * rstd + shift, gain, bias); re-split into hi / lo
+template <bool F16>
+__device__ __forceinline__ void ln_apply8(uint4 br, float2 st, const float* g, const float* b, uint4& xh, uint4& xl) {
+  const uint32_t bw[4] = {br.x, br.y, br.z, br.w};
+  uint32_t hw[4] = {xh.x, xh.y, xh.z, xh.w};
+  uint32_t lw[4] = {xl.x, xl.y, xl.z, xl.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 v = h2_to_f2(bw[j]);
+    const float o0 = (unpack_act1<F16>(static_cast<uint16_t>(hw[j] & 0xffffu)) + unpack_act1<F16>(static_cast<uint16_t>(lw[j] & 0xffffu))) +
+                     fmaf(fmaf(v.x, st.x, st.y), g[2 * j], b[2 * j]);
+    const float o1 = (unpack_act1<F16>(static_cast<uint16_t>(hw[j] >> 16)) + unpack_act1<F16>(static_cast<uint16_t>(lw[j] >> 16))) +
+                     fmaf(fmaf(v.y, st.x, st.y), g[2 * j + 1], b[2 * j + 1]);
+    hw[j] = pack_act2<F16>(o0, o1);
+    lw[j] = pack_act2<F16>(o0 - unpack_act1<F16>(static_cast<uint16_t>(hw[j] & 0xffffu)),
+                           o1 - unpack_act1<F16>(static_cast<uint16_t>(hw[j] >> 16)));
+  }
+  xh = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+  xl = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+}
+
+// NCH 16-byte chunks (8 columns each) of this warp's 32 rows, starting at column n0.  In the coalesced orientation lane
+// `lane` handles (row r, chunk c) = divmod(it * 32 + lane, NCH) in iteration it: full-line accesses to x hi / lo.
+template <int NCH>
+__device__ __forceinline__ void ln_part_rc(int it, int lane, int& r, int& c) {
+  const int idx = it * 32 + lane;
+  r = idx / NCH;
+  c = idx - r * NCH;
+}
+// issue every x load of the part (they do not depend on the statistics: called as early as registers allow)
+template <int NCH>
+__device__ __forceinline__ void ln_part_load(const GemmParams& p, const EpiCtx& e, int n0, uint4* xh, uint4* xl) {
+  const size_t pitch = static_cast<size_t>(p.N) * 2;                    // elements per xhl row
+  const uint16_t* x0 = p.xhl + static_cast<size_t>(e.row0) * pitch + n0;
+#pragma unroll
+  for (int it = 0; it < NCH; ++it) {
+    int r, c;
+    ln_part_rc<NCH>(it, e.lane, r, c);
+    xh[it] = xl[it] = make_uint4(0u, 0u, 0u, 0u);
+    if (r < e.rows_valid) {
+      const uint4* px = reinterpret_cast<const uint4*>(x0 + r * pitch + c * 8);
+      xh[it] = *px;
+      xl[it] = *(px + (p.N >> 3));
+    }
+  }
+}
+// transpose the fp16 branch values of the part through smem and update x
+template <bool F16, int NCH>
+__device__ __forceinline__ void ln_part_apply(const GemmParams& p, const EpiCtx& e, uint32_t stat_smem, const uint32_t* w,
+                                              int n0, const float* gn, const float* bs, uint4* xh, uint4* xl) {
+  const uint4* w4 = reinterpret_cast<const uint4*>(w);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) st_shared_v4(e.scratch + e.lane * 128 + ((c ^ (e.lane & 7)) << 4), w4[c]);
+  __syncwarp();
+  const size_t pitch = static_cast<size_t>(p.N) * 2;
+  uint16_t* x0 = p.xhl + static_cast<size_t>(e.row0) * pitch + n0;
+  float g[8], b[8];
+  auto load_gb = [&](int c) {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gn + n0 + c * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gn + n0 + c * 8 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bs + n0 + c * 8)), b1 = __ldg(reinterpret_cast<const float4*>(bs + n0 + c * 8 + 4));
+    g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+    b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+  };
+  if constexpr (NCH == 8) load_gb(e.lane & 7);                          // the chunk index is the same in every iteration
+#pragma unroll
+  for (int it = 0; it < NCH; ++it) {
+    int r, c;
+    ln_part_rc<NCH>(it, e.lane, r, c);
+    const uint4 q = ld_shared_v4(e.scratch + r * 128 + ((c ^ (r & 7)) << 4));
+    const float2 st = ld_shared_f2(stat_smem + r * 8);
+    if constexpr (NCH != 8) load_gb(c);
+    ln_apply8<F16>(q, st, g, b, xh[it], xl[it]);
+    if (r < e.rows_valid) {
+      uint4* px = reinterpret_cast<uint4*>(x0 + r * pitch + c * 8);
+      *px = xh[it];
+      *(px + (p.N >> 3)) = xl[it];
+    }
+  }
+  __syncwarp();
+}
+
+// L2 prefetch of the x hi / lo segments this warp will update (issued before the warp waits for the accumulator, a whole
+// main loop ahead of their use)
+__device__ __forceinline__ void ln_prefetch_x(const GemmParams& p, int row0, int rows_valid, int lane, int n_lo, int n_hi) {
+  if (lane >= rows_valid) return;
+  const uint16_t* xr = p.xhl + static_cast<size_t>(row0 + lane) * (2 * p.N);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int n0 = (k & 1) ? n_hi : n_lo;
+    if (n0 < p.N) {
+      const uint16_t* a = xr + n0 + ((k & 2) ? p.N : 0);
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(kSlot * 2) : "memory");
+    }
+  }
+}
+
+// columns [lo, lo + 88) and [hi, hi + 88) held by statistics group s (s = tile_n * NSUB + epilogue group)
+template <int NSUB, int CG>
+__device__ __forceinline__ void ln_group_cols(int s, int& lo, int& hi) {
+  if constexpr (NSUB == 2) {
+    lo = (s >> 1) * (2 * kUmmaN) + (s & 1) * kSlot;
+    hi = lo + 2 * kSlot;
+  } else {
+    lo = s * kUmmaN;
+    hi = lo + kSlot;
+  }
+}
+
+template <int NSUB, int CG, bool F16, typename Release>
+__device__ __forceinline__ void epi_group_lnres(const GemmParams& p, const EpiCtx& e, uint32_t stat_smem, uint32_t tacc, int sgrp,
+                                                int nslots, Release&& release) {
+  int n_lo, n_hi;
+  ln_group_cols<NSUB, CG>(sgrp, n_lo, n_hi);
+  const bool va = n_lo < p.N, vb = n_hi < p.N;               // N % 88 == 0: a slot is entirely inside or outside
+  // The branch is parked in registers as fp16 pairs (whatever the operand format).  Row statistics of the ROUNDED values
+  // in one pass: sums of (x - K) and (x - K)^2 about a pivot K taken from the row itself (no cancellation problem).
+  float v[kSlot];
+  uint32_t wa[44], wb[44];
+  float s1 = 0.f, s2 = 0.f, K;
+  tmem_load_cols<kSlot>(tacc, v);
+  wa[0] = pack_act2<true>(v[0], v[1]);
+  K = h2_to_f2(wa[0]).x;
+#pragma unroll
+  for (int j = 0; j < 44; ++j) {
+    wa[j] = pack_act2<true>(v[2 * j], v[2 * j + 1]);
+    const float2 f = h2_to_f2(wa[j]);
+    s1 += (f.x - K) + (f.y - K);
+    s2 = fmaf(f.x - K, f.x - K, fmaf(f.y - K, f.y - K, s2));
+  }
+  tmem_load_cols<kSlot>(tacc + kSlot, v);
+  release();
+  if (!va) { s1 = s2 = 0.f; }
+  {
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 44; ++j) {
+      wb[j] = pack_act2<true>(v[2 * j], v[2 * j + 1]);
+      const float2 f = h2_to_f2(wb[j]);
+      t1 += (f.x - K) + (f.y - K);
+      t2 = fmaf(f.x - K, f.x - K, fmaf(f.y - K, f.y - K, t2));
+    }
+    if (vb) { s1 += t1; s2 += t2; }
+  }
+  if (e.rows_valid <= 0) return;                             // warp-uniform: none of the groups of these rows takes part
+  const int cnt = kSlot * (static_cast<int>(va) + static_cast<int>(vb));
+  const float fc = static_cast<float>(cnt);
+  const float sum = cnt ? fmaf(fc, K, s1) : 0.f;             // sum x      = s1 + n K
+  const float m2 = cnt ? fmaxf(s2 - s1 * s1 / fc, 0.f) : 0.f;   // sum (x - mean_p)^2
+  // publish, then wait for the other groups of these 32 rows
+  const int row = e.row0 + e.lane;
+  __stcg(p.ln_stats + static_cast<size_t>(sgrp) * p.ln_stride + row, make_float2(sum, m2));
+  __syncwarp();
+  unsigned* counter = p.ln_counter + (e.row0 >> 5);
+  if (e.lane == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+  }
+  // the x loads of the first part go out before the wait
+  uint4 xhA[8], xlA[8], xhB[3], xlB[3];
+  ln_part_load<8>(p, e, va ? n_lo : n_hi, xhA, xlA);
+  if (!(p.ln_debug & 1) && ld_relaxed_gpu_u32(counter) < p.ln_target) {
+    const long long t0 = clock64();
+    while (ld_relaxed_gpu_u32(counter) < p.ln_target) {
+      __nanosleep(32);
+      if (clock64() - t0 > SWB_WATCHDOG_CYCLES) {
+        printf("[swift_b200] LayerNorm statistics watchdog: block %d warp %d rows %d.. (%u of %u)\n", (int)blockIdx.x,
+               (int)(threadIdx.x >> 5), e.row0, ld_acquire_gpu_u32(counter), p.ln_target);
+        __trap();
+      }
+    }
+  }
+  fence_acq_rel_gpu();                                       // pairs with the publishers' __threadfence + atomicAdd
+  // merge the partials (Chan et al.): mean, M2 over all N columns
+  constexpr int kMaxGroups = 12;
+  float2 part[kMaxGroups];
+#pragma unroll
+  for (int s = 0; s < kMaxGroups; ++s)
+    part[s] = s < nslots ? __ldcg(p.ln_stats + static_cast<size_t>(s) * p.ln_stride + row) : make_float2(0.f, 0.f);
+  float tot = 0.f;
+#pragma unroll
+  for (int s = 0; s < kMaxGroups; ++s) tot += part[s].x;
+  const float mean = tot / static_cast<float>(p.N);
+  float M2 = 0.f;
+#pragma unroll
+  for (int s = 0; s < kMaxGroups; ++s) {
+    int lo, hi;
+    ln_group_cols<NSUB, CG>(s, lo, hi);
+    const int c = kSlot * (static_cast<int>(lo < p.N) + static_cast<int>(hi < p.N));
+    if (s < nslots && c) {
+      const float d = part[s].x / static_cast<float>(c) - mean;
+      M2 += part[s].y + static_cast<float>(c) * d * d;
+    }
+  }
+  const float rstd = rsqrtf(M2 / static_cast<float>(p.N) + p.ln_eps);
+  st_shared_f2(stat_smem + e.lane * 8, make_float2(rstd, -mean * rstd));
+  __syncwarp();
+  const int b = e.row0 / p.tokens;                           // tokens % 32 == 0: the 32 rows belong to one sample
+  const float* gn = p.gain + static_cast<size_t>(b) * p.N;
+  const float* bs = p.lnbias + static_cast<size_t>(b) * p.N;
+  if (p.ln_debug & 2) return;
+  // parts: (lo, 64 columns) (lo, 24) (hi, 64) (hi, 24); the loads of the next part are in flight while one is applied
+  if (va) {
+    ln_part_load<3>(p, e, n_lo + 64, xhB, xlB);
+    ln_part_apply<F16, 8>(p, e, stat_smem, wa, n_lo, gn, bs, xhA, xlA);
+    if (vb) ln_part_load<8>(p, e, n_hi, xhA, xlA);
+    ln_part_apply<F16, 3>(p, e, stat_smem, wa + 32, n_lo + 64, gn, bs, xhB, xlB);
+  }
+  if (vb) {
+    ln_part_load<3>(p, e, n_hi + 64, xhB, xlB);
+    ln_part_apply<F16, 8>(p, e, stat_smem, wb, n_hi, gn, bs, xhA, xlA);
+    ln_part_apply<F16, 3>(p, e, stat_smem, wb + 32, n_hi + 64, gn, bs, xhB, xlB);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 
 template <int NSUB, int CG, int EPI, bool F16>
 __global__ void __launch_bounds__(GemmCfg<NSUB, CG>::kThreads, 1)
@@ -543,6 +852,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // 384 threads x 168 registers at launch: warps 0-3 keep 64, the two epilogue warpgroups grow to 216 (64*128 + 216*256 = 384*168: setmaxnreg.inc blocks for ever if the CTA pool is exceeded) (the
+  // re-allocation sits at the top of each warpgroup's own branch: ptxas budgets the code it dominates)
+  if (warp < 4) {
+  if constexpr (S::kEpiWarps == 8) setmaxnreg_dec<64>();
   if (warp == 0) {
     // ===================================== TMA producer (whole warp converged, one elected lane issues) ==========
     const uint32_t full_leader0 = (CG == 2) ? mapa_u32(full_bar(0), 0) : full_bar(0);
@@ -639,19 +952,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         umma_commit_elect<CG>(tfull_bar(NSUB == 1 ? par : 0));   // accumulator(s) complete -> epilogue (both CTAs)
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
     // ===================================== epilogue =====================================
+    if constexpr (S::kEpiWarps == 8) setmaxnreg_inc<216>();
     const int quad = warp & 3;                              // TMEM lane quadrant this warp may access
     const int grp = (warp - 4) >> 2;                        // NSUB == 2: epilogue group = sub-tile it drains
     const uint32_t tempty_leader0 = (CG == 2) ? mapa_u32(tempty_bar(0), 0) : tempty_bar(0);
     EpiCtx e;
     e.lane = lane;
     e.scratch = scratch0 + (warp - 4) * 4096;
+    const uint32_t stat_smem = scratch0 + S::kEpiWarps * 4096 + (warp - 4) * 256;
     int it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const uint32_t par = static_cast<uint32_t>(it) & 1u;
       const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
       const int n_tile = tn * kTileN;
+      if constexpr (EPI == EPI_LN_RES) {
+        const int r0 = tm * (kBlockM * CG) + static_cast<int>(cta_rank) * kBlockM + quad * 32;
+        int lo, hi;
+        ln_group_cols<NSUB, CG>(tn * NSUB + grp, lo, hi);
+        ln_prefetch_x(p, r0, p.M - r0, lane, lo, hi);
+      }
       uint32_t tacc;                                        // column 0 of the accumulator this warp drains
       if constexpr (NSUB == 1) {
         mbar_wait(tfull_bar(par), (static_cast<uint32_t>(it) >> 1) & 1u, 4);
@@ -688,6 +1010,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         epi_group_qkv<F16>(p, e, tacc, n_lo, n_hi, release);
       } else if constexpr (EPI == EPI_STORE_ACT) {
         epi_group_store16<F16>(p, e, tacc, n_lo, n_hi, release);
+      } else if constexpr (EPI == EPI_LN_RES) {
+        epi_group_lnres<NSUB, CG, F16>(p, e, stat_smem, tacc, tn * NSUB + grp, tiles_n * NSUB, release);
+      } else if constexpr (EPI == EPI_SMEM_ONLY) {
+        epi_group_store16_prof<F16, 1>(p, e, tacc, n_lo, n_hi, release);
+      } else if constexpr (EPI == EPI_DIRECT) {
+        epi_group_store16_prof<F16, 2>(p, e, tacc, n_lo, n_hi, release);
+      } else if constexpr (EPI == EPI_DISCARD) {
+        release();
+      } else if constexpr (EPI == EPI_DRAIN) {
+        float v[kSlot];
+        tmem_load_cols<kSlot>(tacc, v);
+        tmem_load_cols<kSlot>(tacc + kSlot, v);
+        release();
       } else {
 #pragma unroll 1
         for (int hf = 0; hf < 2; ++hf) {

@@ -24,7 +24,7 @@ class Engine:
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], geom: packing.Geometry, device: torch.device,
                  split_embed: bool = True, split_head: bool = True, max_chunk: int = 8, act_fp16: bool = True,
-                 gemm_tile: int = 3, attn_impl: int = 0):
+                 gemm_tile: int = 3, attn_impl: int = 0, fuse_ln: int = 2):
         if device.type != "cuda":
             raise RuntimeError("swift_b200 runs on CUDA devices only (no CPU fallback)")
         self.lib = _lib.lib()
@@ -32,7 +32,8 @@ class Engine:
         self.device = device
         with torch.cuda.device(device):
             self.model, self._keep = packing.pack(state_dict, geom, device, split_embed, split_head, act_fp16,
-                                                   gemm_tile, attn_impl)
+                                                   gemm_tile, attn_impl, fuse_ln)
+        self.fuse_ln = int(fuse_ln)
         self.act_fp16 = act_fp16
         _lib.check(self.lib.swb200_validate(C.byref(self.model)), "validate")
         self.max_chunk = max_chunk
@@ -49,7 +50,8 @@ class Engine:
 
     def launches_per_forward(self, batch: int) -> int:
         chunks = math.ceil(batch / max(1, min(batch, self.max_chunk)))
-        return chunks * (2 + 7 * self.geom.depth + 1)
+        per_layer = 7 - bin(self.fuse_ln).count("1")     # qkv, attention, wo, w1, w2 + one LN kernel per un-fused projection
+        return chunks * (2 + per_layer * self.geom.depth + 1)
 
     def workspace(self, batch: int) -> Tuple[int, int]:
         chunk = max(1, min(batch, self.max_chunk))

@@ -117,6 +117,8 @@ class SwinV2(_Base):
         self.act_fp16 = True         # tensor-core operands in fp16 (else bf16): 8x smaller rounding error, same tcgen05 rate
         self.gemm_tile = 3           # 1: 128x176 single CTA, 2: 256x176 CTA pair, 3: 256x352 CTA pair
         self.attn_impl = 0           # 0: tcgen05 attention when the shift is a multiple of 8, 1: mma.sync kernel, 2: tcgen05
+        self.fuse_ln = 2             # LayerNorm + modulation + residual add in the GEMM epilogue: bit 0 = wo, bit 1 = w2; 0 = separate kernel
+                                     # (measured: w2 only is fastest; the short-K wo GEMM becomes epilogue-bound when fused)
         self.max_chunk = 8           # samples pushed through the kernels per launch sequence
 
     def _init_weights(self):
@@ -136,7 +138,8 @@ class SwinV2(_Base):
 
     def engine(self) -> Engine:
         """The packed CUDA engine for the current parameter values (re-packed when parameters change)."""
-        key = (self._params_key(), self.split_embed, self.split_head, self.max_chunk, self.act_fp16, self.gemm_tile, self.attn_impl)
+        key = (self._params_key(), self.split_embed, self.split_head, self.max_chunk, self.act_fp16, self.gemm_tile, self.attn_impl,
+               self.fuse_ln)
         if self._engine is None or self._engine_key != key:
             dev = self.pos_embed.device
             if dev.type != "cuda":
@@ -144,7 +147,7 @@ class SwinV2(_Base):
                                    "there is no CPU fallback")
             sd = {k: v for k, v in self.state_dict().items()}
             self._engine = Engine(sd, self.geometry, dev, self.split_embed, self.split_head, self.max_chunk,
-                                  self.act_fp16, self.gemm_tile, self.attn_impl)
+                                  self.act_fp16, self.gemm_tile, self.attn_impl, self.fuse_ln)
             self._engine_key = key
         return self._engine
 

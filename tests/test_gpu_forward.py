@@ -22,7 +22,7 @@ def per_field_rel_l2(y, ref):
     return num / den          # [B, C]
 
 
-def build_net(cfg, seed=1, img_channels=None, act_fp16=True):
+def build_net(cfg, seed=1, img_channels=None, act_fp16=True, fuse_ln=None):
     from swift_b200 import synthetic as syn
     from swift_b200.precond import PassPrecond
     img_channels = cfg["out_channels"] if img_channels is None else img_channels
@@ -36,16 +36,20 @@ def build_net(cfg, seed=1, img_channels=None, act_fp16=True):
     missing = net.load_state_dict(sd, strict=True)
     assert not missing.missing_keys and not missing.unexpected_keys
     net.model.act_fp16 = act_fp16
+    if fuse_ln is not None:
+        net.model.fuse_ln = fuse_ln
     return net.cuda().eval(), {k[len("model."):]: v for k, v in sd.items()}
 
 
+@pytest.mark.parametrize("fuse_ln", [0, 1, 2, 3], ids=["ln_kernel", "ln_in_wo", "ln_in_w2", "ln_in_wo_w2"])
 @pytest.mark.parametrize("act_fp16", [True, False], ids=["act_fp16", "act_bf16"])
 @pytest.mark.parametrize("name,cfgname", [("tiny", "SWIFT_TINY"), ("small", "SWIFT_SMALL")])
-def test_module_forward_vs_reference_golden(golden, name, cfgname, act_fp16):
+def test_module_forward_vs_reference_golden(golden, name, cfgname, act_fp16, fuse_ln):
+    """fuse_ln: LayerNorm + modulation + residual add as its own kernel or in the wo / w2 GEMM epilogue."""
     from swift_b200 import synthetic as syn
     g = golden(name)
     cfg = getattr(syn, cfgname)
-    net, _ = build_net(cfg, act_fp16=act_fp16)
+    net, _ = build_net(cfg, act_fp16=act_fp16, fuse_ln=fuse_ln)
     lat, cond = syn.synthetic_fields(cfg, 2, seed=3)
     with torch.no_grad():
         y = net(lat.cuda(), torch.from_numpy(g["fwd_t"]).cuda(), cond.cuda(), torch.from_numpy(g["fwd_aux"]).cuda())

@@ -173,4 +173,42 @@ def test_gemm_rejects_bad_arguments(lib):
     rc = lib.swb200_gemm(0, 2, 0, A.data_ptr(), 60, A.data_ptr(), 64, out.data_ptr(), 176, 256, 176, 60, _stream())
     assert rc != 0 and b"multiples of 8" in lib.swb200_last_error()
     with pytest.raises(RuntimeError):
-        _lib.check(lib.swb200_gemm(7, 2, 0, A.data_ptr(), 64, A.data_ptr(), 64, out.data_ptr(), 176, 256, 176, 64, _stream()))
+        _lib.check(lib.swb200_gemm(42, 2, 0, A.data_ptr(), 64, A.data_ptr(), 64, out.data_ptr(), 176, 256, 176, 64, _stream()))
+
+
+@ACT
+@pytest.mark.parametrize("cg", [3, 2, 1], ids=["tile256x352", "tile256x176", "tile128x176"])
+@pytest.mark.parametrize("B,T,D,K", [(3, 256, 264, 264), (5, 160, 528, 704), (3, 256, 1056, 1056), (2, 512, 1056, 2816),
+                                     (6, 8192, 1056, 264)])
+def test_gemm_ln_residual_epilogue(lib, cg, B, T, D, K, f16):
+    """EPI_LN_RES: x += LayerNorm(A W^T) * gain[b] + bias[b] on the [hi | lo] residual pair, row statistics exchanged
+    between the CTAs that own the column tiles of a row; two launches share the exchange workspace (gen 0, 1).
+    (6, 8192, ...) spans several waves of the persistent grid."""
+    dt = _adt(f16)
+    M = B * T
+    A = _rand_bf16((M, K), 21, dtype=dt)
+    W = _rand_bf16((D, K), 22, 0.05, dtype=dt)
+    g = torch.Generator(device="cuda").manual_seed(23)
+    x = torch.randn(M, D, device="cuda", generator=g)
+    hi = x.to(dt)
+    lo = (x - hi.float()).to(dt)
+    xhl = torch.cat([hi, lo], 1).contiguous()
+    x_ref = hi.float() + lo.float()
+    ws = torch.empty(lib.swb200_ln_workspace_bytes(M, D) + 256, dtype=torch.uint8, device="cuda")
+    ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+    branch = (A.float() @ W.float().t()).half().float()             # fp16 rounding of the accumulator, as in the kernel
+    for gen in range(2):
+        gain = torch.randn(B, D, device="cuda", generator=g)
+        bias = torch.randn(B, D, device="cuda", generator=g)
+        _check(lib.swb200_gemm_ln_residual(cg, f16, A.data_ptr(), K, W.data_ptr(), K, xhl.data_ptr(), gain.data_ptr(),
+                                           bias.data_ptr(), M, D, T, ws_ptr, gen, _stream()))
+        torch.cuda.synchronize()
+        ln = torch.nn.functional.layer_norm(branch, (D,), eps=1e-6).reshape(B, T, D)
+        x_ref = x_ref + (ln * gain[:, None] + bias[:, None]).reshape(M, D)
+        got = xhl[:, :D].float() + xhl[:, D:].float()
+        assert torch.isfinite(got).all()
+        # the pair represents x to ~2^-22 (fp16) / 2^-16 (bf16); the fp16 rounding of the branch flips for the few elements
+        # whose fp32 accumulation order differs from the reference's (more of them at large K)
+        assert _rel(got, x_ref) < (8e-5 if f16 else 2e-4), f"gen {gen}: {_rel(got, x_ref):.3e}"
+        assert _rel(xhl[:, :D].float(), x_ref) < (6e-4 if f16 else 5e-3)
+        x_ref = got.clone()

@@ -24,6 +24,8 @@ def main():
     net.load_state_dict(syn.random_state_dict(cfg, seed=1, prefix="model."), strict=True)
     net = net.cuda().eval()
     net.model.max_chunk = chunk
+    if len(sys.argv) > 3:
+        net.model.fuse_ln = int(sys.argv[3])
     traj = shard_trajectories(12, 8, 0, 1)
     forc = syn.synthetic_forcings(cfg, steps + 8, seed=0).cuda()
     ro = EnsembleRollout(net, Normalizers.synthetic(69, "cuda"), forc, traj, use_graph=False)
