@@ -166,6 +166,26 @@ __device__ __forceinline__ void tmem_load_cols(uint32_t taddr, float* v) {
   tmem_ld_fence_regs<NCOL>(v);
 }
 
+// two NCOL-column blocks with a single tcgen05.wait::ld
+template <int NCOL>
+__device__ __forceinline__ void tmem_load_cols2(uint32_t ta, float* a, uint32_t tb, float* b) {
+  __syncwarp();
+  constexpr int n32 = NCOL / 32;
+  constexpr int r32 = NCOL - 32 * n32;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const uint32_t t = h ? tb : ta;
+    float* v = h ? b : a;
+#pragma unroll
+    for (int i = 0; i < n32; ++i) tmem_ld_x32(t + 32 * i, v + 32 * i);
+    if constexpr (r32 >= 16) tmem_ld_x16(t + 32 * n32, v + 32 * n32);
+    if constexpr (r32 % 16 == 8) tmem_ld_x8(t + 32 * n32 + (r32 / 16) * 16, v + 32 * n32 + (r32 / 16) * 16);
+  }
+  tmem_ld_wait();
+  tmem_ld_fence_regs<NCOL>(a);
+  tmem_ld_fence_regs<NCOL>(b);
+}
+
 template <bool F16, int NW>
 __device__ __forceinline__ void pack_row16(const float* v, uint32_t* w) {   // 2*NW floats -> NW packed words
 #pragma unroll
@@ -467,13 +487,12 @@ __device__ __forceinline__ void epi_group_store16_prof(const GemmParams& p, cons
 template <bool F16, typename Release>
 __device__ __forceinline__ void epi_group_store16(const GemmParams& p, const EpiCtx& e, uint32_t tacc, int n_lo, int n_hi,
                                                   Release&& release) {
-  float v[kSlot];
+  float va[kSlot], vb[kSlot];
   uint32_t wa[44], wb[44];
-  tmem_load_cols<kSlot>(tacc, v);
-  pack_row16<F16, 44>(v, wa);
-  tmem_load_cols<kSlot>(tacc + kSlot, v);
+  tmem_load_cols2<kSlot>(tacc, va, tacc + kSlot, vb);       // both slots leave TMEM before anything else happens
   release();
-  pack_row16<F16, 44>(v, wb);
+  pack_row16<F16, 44>(va, wa);
+  pack_row16<F16, 44>(vb, wb);
   store_slot16(p.out0, p.ldo, p.N, e, n_lo, wa);
   store_slot16(p.out0, p.ldo, p.N, e, n_hi, wb);
 }
@@ -512,35 +531,25 @@ __device__ __forceinline__ void qkv_slot_store(const GemmParams& p, const EpiCtx
 template <bool F16, typename Release>
 __device__ __forceinline__ void epi_group_qkv(const GemmParams& p, const EpiCtx& e, uint32_t tacc, int n_lo, int n_hi,
                                               Release&& release) {
-  float v[kSlot];
-  uint32_t wa[48], wb[48];
+  float va[kSlot], vb[kSlot];
+  uint32_t w[48];
   int sa, sb;
-  tmem_load_cols<kSlot>(tacc, v);
-  const bool oka = qkv_slot_pack<F16>(p, n_lo, v, wa, &sa);
-  tmem_load_cols<kSlot>(tacc + kSlot, v);
+  tmem_load_cols2<kSlot>(tacc, va, tacc + kSlot, vb);
   release();
-  const bool okb = qkv_slot_pack<F16>(p, n_hi, v, wb, &sb);
-  if (oka) qkv_slot_store(p, e, sa, wa);
-  if (okb) qkv_slot_store(p, e, sb, wb);
+  if (qkv_slot_pack<F16>(p, n_lo, va, w, &sa)) qkv_slot_store(p, e, sa, w);
+  if (qkv_slot_pack<F16>(p, n_hi, vb, w, &sb)) qkv_slot_store(p, e, sb, w);
 }
 
 template <bool F16, typename Release>
 __device__ __forceinline__ void epi_group_swiglu(const GemmParams& p, const EpiCtx& e, uint32_t tacc, int out_col0,
                                                  bool valid, Release&& release) {
-  // gate slot at columns [0,88), up slot at [88,176) of this group's accumulator.  The gate is parked in registers as
-  // 16-bit pairs (one extra 2^-12 rounding in front of a result that is itself stored in 16 bits).
-  float v[kSlot];
-  uint32_t g16[44], w[44];
-  tmem_load_cols<kSlot>(tacc, v);
-  pack_row16<F16, 44>(v, g16);
-  tmem_load_cols<kSlot>(tacc + kSlot, v);
+  // gate slot at columns [0,88), up slot at [88,176) of this group's accumulator
+  float g[kSlot], v[kSlot];
+  uint32_t w[44];
+  tmem_load_cols2<kSlot>(tacc, g, tacc + kSlot, v);
   release();
 #pragma unroll
-  for (int j = 0; j < 44; ++j) {
-    const float g0 = unpack_act1<F16>(static_cast<uint16_t>(g16[j] & 0xffffu));
-    const float g1 = unpack_act1<F16>(static_cast<uint16_t>(g16[j] >> 16));
-    w[j] = pack_act2<F16>(silu_f(g0) * v[2 * j], silu_f(g1) * v[2 * j + 1]);
-  }
+  for (int j = 0; j < 44; ++j) w[j] = pack_act2<F16>(silu_f(g[2 * j]) * v[2 * j], silu_f(g[2 * j + 1]) * v[2 * j + 1]);
   if (valid) store_slot16(p.out0, p.ldo, p.ldo, e, out_col0, w);
 }
 
