@@ -9,7 +9,7 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libswift_b200.so")
+LIB_PATH = os.environ.get("SWB_LIB", os.path.join(HERE, "libswift_b200.so"))   # SWB_LIB: A/B builds (tools only)
 
 ABI_VERSION = 9
 

@@ -19,6 +19,8 @@ LIB = os.path.join(HERE, "libswift_b200.so")
 SOURCES = ["gemm.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "rollout.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+NVCC_FLAGS += os.environ.get("SWB_NVCC_DEFINES", "").split()      # e.g. "-DSWB_A_TMEM=1" for A/B builds of one kernel choice
+LIB = os.environ.get("SWB_LIB_OUT", LIB)
 
 
 def _nvcc() -> str:

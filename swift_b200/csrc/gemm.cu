@@ -4,6 +4,7 @@
 #include "gemm_sm100.cuh"
 
 #include <mutex>
+#include <stdlib.h>
 
 namespace swb {
 
@@ -46,8 +47,8 @@ static PFN_tmapEncodeTiled get_encode_fn() {
   return fn;
 }
 
-int make_tmap_16bit_2d(CUtensorMap* out, const void* ptr, bool is_f16, uint64_t rows, uint64_t cols,
-                       uint64_t pitch_elems, uint32_t box_rows, uint32_t box_cols) {
+static int make_tmap_16bit_2d_swz(CUtensorMap* out, const void* ptr, bool is_f16, uint64_t rows, uint64_t cols,
+                                  uint64_t pitch_elems, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz) {
   PFN_tmapEncodeTiled fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled driver entry point not available");
@@ -63,7 +64,7 @@ int make_tmap_16bit_2d(CUtensorMap* out, const void* ptr, bool is_f16, uint64_t 
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, is_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu box=%ux%u", (int)r, (unsigned long long)rows,
@@ -73,9 +74,15 @@ int make_tmap_16bit_2d(CUtensorMap* out, const void* ptr, bool is_f16, uint64_t 
   return SWB_OK;
 }
 
+int make_tmap_16bit_2d(CUtensorMap* out, const void* ptr, bool is_f16, uint64_t rows, uint64_t cols,
+                       uint64_t pitch_elems, uint32_t box_rows, uint32_t box_cols) {
+  return make_tmap_16bit_2d_swz(out, ptr, is_f16, rows, cols, pitch_elems, box_rows, box_cols, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 // ----------------------------------------------------------------------------- launch
 template <int NSUB, int CG, int EPI, bool F16>
-static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to0, const CUtensorMap& to1,
+                       const GemmParams& p, cudaStream_t stream) {
   using S = GemmCfg<NSUB, CG>;
   auto kern = gemm_tcgen05_kernel<NSUB, CG, EPI, F16>;
   static bool attr_done = false;
@@ -114,25 +121,25 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     SWB_REQUIRE(max_clusters >= clusters, "gemm_ln_residual: only %d of %d CTA clusters can be co-resident", max_clusters,
                 clusters);
   }
-  SWB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+  SWB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to0, to1, p));
   return SWB_OK;
 }
 
 template <int NSUB, int CG, bool F16>
-static int launch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                      cudaStream_t stream) {
+static int launch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to0,
+                      const CUtensorMap& to1, const GemmParams& p, cudaStream_t stream) {
   switch (epi) {
-    case EPI_STORE_F32: return launch_inst<NSUB, CG, EPI_STORE_F32, F16>(ta, tb, p, stream);
-    case EPI_STORE_ACT: return launch_inst<NSUB, CG, EPI_STORE_ACT, F16>(ta, tb, p, stream);
-    case EPI_EMBED: return launch_inst<NSUB, CG, EPI_EMBED, F16>(ta, tb, p, stream);
-    case EPI_QKV: return launch_inst<NSUB, CG, EPI_QKV, F16>(ta, tb, p, stream);
-    case EPI_SWIGLU: return launch_inst<NSUB, CG, EPI_SWIGLU, F16>(ta, tb, p, stream);
-    case EPI_HEAD: return launch_inst<NSUB, CG, EPI_HEAD, F16>(ta, tb, p, stream);
-    case EPI_LN_RES: return launch_inst<NSUB, CG, EPI_LN_RES, F16>(ta, tb, p, stream);
-    case EPI_DISCARD: return launch_inst<NSUB, CG, EPI_DISCARD, F16>(ta, tb, p, stream);
-    case EPI_DRAIN: return launch_inst<NSUB, CG, EPI_DRAIN, F16>(ta, tb, p, stream);
-    case EPI_SMEM_ONLY: return launch_inst<NSUB, CG, EPI_SMEM_ONLY, F16>(ta, tb, p, stream);
-    case EPI_DIRECT: return launch_inst<NSUB, CG, EPI_DIRECT, F16>(ta, tb, p, stream);
+    case EPI_STORE_F32: return launch_inst<NSUB, CG, EPI_STORE_F32, F16>(ta, tb, to0, to1, p, stream);
+    case EPI_STORE_ACT: return launch_inst<NSUB, CG, EPI_STORE_ACT, F16>(ta, tb, to0, to1, p, stream);
+    case EPI_EMBED: return launch_inst<NSUB, CG, EPI_EMBED, F16>(ta, tb, to0, to1, p, stream);
+    case EPI_QKV: return launch_inst<NSUB, CG, EPI_QKV, F16>(ta, tb, to0, to1, p, stream);
+    case EPI_SWIGLU: return launch_inst<NSUB, CG, EPI_SWIGLU, F16>(ta, tb, to0, to1, p, stream);
+    case EPI_HEAD: return launch_inst<NSUB, CG, EPI_HEAD, F16>(ta, tb, to0, to1, p, stream);
+    case EPI_LN_RES: return launch_inst<NSUB, CG, EPI_LN_RES, F16>(ta, tb, to0, to1, p, stream);
+    case EPI_DISCARD: return launch_inst<NSUB, CG, EPI_DISCARD, F16>(ta, tb, to0, to1, p, stream);
+    case EPI_DRAIN: return launch_inst<NSUB, CG, EPI_DRAIN, F16>(ta, tb, to0, to1, p, stream);
+    case EPI_SMEM_ONLY: return launch_inst<NSUB, CG, EPI_SMEM_ONLY, F16>(ta, tb, to0, to1, p, stream);
+    case EPI_DIRECT: return launch_inst<NSUB, CG, EPI_DIRECT, F16>(ta, tb, to0, to1, p, stream);
   }
   set_error("unknown GEMM epilogue %d", epi);
   return SWB_ERR_INVALID;
@@ -140,24 +147,47 @@ static int launch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, con
 
 // A: [M, K] with row pitch lda; W: [N, K] with row pitch ldw (nn.Linear layout); both fp16 (act_f16) or both bf16.
 // tile: 1 = single CTA 128x176, 2 = CTA pair 256x176 (double-buffered accumulator), 3 = CTA pair 256x352.
-int launch_gemm(int epi, int tile, int act_f16, const void* A, int lda, const void* W, int ldw, const GemmParams& p,
+int launch_gemm(int epi, int tile, int act_f16, const void* A, int lda, const void* W, int ldw, const GemmParams& p_in,
                 cudaStream_t stream) {
+  GemmParams p = p_in;
   SWB_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
   SWB_REQUIRE(p.K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm: K and row pitches must be multiples of 8 (K=%d)",
               p.K);
   SWB_REQUIRE(tile >= 1 && tile <= 3, "gemm: tile config must be 1 (128x176), 2 (256x176) or 3 (256x352), got %d", tile);
   const int cg = tile == 1 ? 1 : 2;
   const int nsub = tile == 3 ? 2 : 1;
-  CUtensorMap ta, tb;
-  int rc = make_tmap_16bit_2d(&ta, A, act_f16 != 0, p.M, p.K, lda, kBlockM, kBlockK);
+  const bool f16 = act_f16 != 0;
+  CUtensorMap ta, tb, to0, to1;
+  int rc = make_tmap_16bit_2d(&ta, A, f16, p.M, p.K, lda, kBlockM, kBlockK);
   if (rc) return rc;
-  rc = make_tmap_16bit_2d(&tb, W, act_f16 != 0, p.N, p.K, ldw, kUmmaN * nsub / cg, kBlockK);
+  rc = make_tmap_16bit_2d(&tb, W, f16, p.N, p.K, ldw, kUmmaN * nsub / cg, kBlockK);
   if (rc) return rc;
+  // 16-bit outputs leave through TMA tile stores: a 64-column box (SWIZZLE_128B image) plus the 24-column rest of an
+  // 88-column slot (plain image), or the 32-column rest of a padded 96-column q/k/v row (SWIZZLE_64B image)
+  static const bool no_tma_store = getenv("SWB_NO_TMA_STORE") != nullptr;      // profiling knob: LDS + STG path
+  p.tma_store = 0;
+  to0 = ta;
+  to1 = ta;
+  if (!no_tma_store && (epi == EPI_STORE_ACT || epi == EPI_SWIGLU)) {
+    const uint64_t cols = epi == EPI_SWIGLU ? static_cast<uint64_t>(p.N / 2) : static_cast<uint64_t>(p.N);
+    rc = make_tmap_16bit_2d_swz(&to0, p.out0, f16, p.M, cols, p.ldo, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_tmap_16bit_2d_swz(&to1, p.out0, f16, p.M, cols, p.ldo, 32, 24, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+    p.tma_store = 1;
+  } else if (!no_tma_store && epi == EPI_QKV && p.M % 32 == 0) {
+    const uint64_t rows = static_cast<uint64_t>(3) * p.heads * p.M;
+    rc = make_tmap_16bit_2d_swz(&to0, p.out0, f16, rows, kHeadDimPad, kHeadDimPad, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_tmap_16bit_2d_swz(&to1, p.out0, f16, rows, kHeadDimPad, kHeadDimPad, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    p.tma_store = 1;
+  }
   if (tile == 3)
-    return act_f16 ? launch_epi<2, 2, true>(epi, ta, tb, p, stream) : launch_epi<2, 2, false>(epi, ta, tb, p, stream);
+    return f16 ? launch_epi<2, 2, true>(epi, ta, tb, to0, to1, p, stream) : launch_epi<2, 2, false>(epi, ta, tb, to0, to1, p, stream);
   if (tile == 2)
-    return act_f16 ? launch_epi<1, 2, true>(epi, ta, tb, p, stream) : launch_epi<1, 2, false>(epi, ta, tb, p, stream);
-  return act_f16 ? launch_epi<1, 1, true>(epi, ta, tb, p, stream) : launch_epi<1, 1, false>(epi, ta, tb, p, stream);
+    return f16 ? launch_epi<1, 2, true>(epi, ta, tb, to0, to1, p, stream) : launch_epi<1, 2, false>(epi, ta, tb, to0, to1, p, stream);
+  return f16 ? launch_epi<1, 1, true>(epi, ta, tb, to0, to1, p, stream) : launch_epi<1, 1, false>(epi, ta, tb, to0, to1, p, stream);
 }
 
 }  // namespace swb

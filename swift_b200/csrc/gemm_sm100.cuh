@@ -21,6 +21,10 @@
 #pragma once
 #include "ptx.cuh"
 
+#ifndef SWB_A_TMEM
+#define SWB_A_TMEM 0     // 1: the 256x352 tile stages its A operand in tensor memory (tcgen05.cp + TMEM-A UMMA)
+#endif
+
 namespace swb {
 
 enum GemmEpilogue : int {
@@ -43,6 +47,7 @@ struct GemmParams {
   void* out0;
   void* out1;
   int ldo;                 // row pitch (elements) of out0/out1 for the plain / embed / swiglu epilogues
+  int tma_store;           // EPI_STORE_ACT / EPI_QKV / EPI_SWIGLU: write the 16-bit output with TMA tile stores (tmap_o0/o1)
   // EPI_EMBED
   const float* bias;       // [N]
   const float* pos;        // [pos_rows, N]
@@ -198,7 +203,57 @@ struct EpiCtx {
   int rows_valid;    // rows of it inside M
   int lane;
   uint32_t scratch;  // this warp's 4 KB transpose buffer
+  const CUtensorMap* to0;   // output tensor maps of the TMA-store epilogues: 64-column box (SWIZZLE_128B) ...
+  const CUtensorMap* to1;   // ... and the tail box (24 columns un-swizzled, or 32 columns SWIZZLE_64B for qkv)
+  bool pending;      // a TMA store issued by lane 0 may still be reading the scratch buffer
 };
+
+// ---- TMA-store epilogue pieces.  Every lane owns one row of the warp's 32-row block and writes its 16-byte chunks
+// into the scratch buffer in exactly the swizzled image a TMA tile store expects (bank-conflict free), then one
+// elected lane issues the store: no LDS, no STG, full-line writes generated by the copy engine.
+__device__ __forceinline__ void epi_scratch_acquire(EpiCtx& e) {
+  if (e.pending) {
+    if (e.lane == 0) bulk_wait_read_all();
+    __syncwarp();
+    e.pending = false;
+  }
+}
+// 64 columns (8 chunks) of 32 rows -> global (column c0, row r0)
+__device__ __forceinline__ void tma_store_part64(EpiCtx& e, const uint32_t* w, int c0, int r0) {
+  const uint4* w4 = reinterpret_cast<const uint4*>(w);
+  epi_scratch_acquire(e);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) st_shared_v4(e.scratch + e.lane * 128 + ((c ^ (e.lane & 7)) << 4), w4[c]);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (e.lane == 0) {
+    tma_store_2d(e.to0, e.scratch, c0, r0);
+    bulk_commit_group();
+  }
+  e.pending = true;
+}
+// tails of up to two slots: NT chunks per row (NT = 3: 24 columns, plain image; NT = 4: 32 columns, SWIZZLE_64B image)
+template <int NT>
+__device__ __forceinline__ void tma_store_tails(EpiCtx& e, const uint32_t* wa, bool va, int ca, int ra, const uint32_t* wb,
+                                                bool vb, int cb, int rb) {
+  if (!va && !vb) return;
+  epi_scratch_acquire(e);
+  const uint32_t sa = e.scratch, sb = e.scratch + 2048;
+  const int swz = NT == 4 ? ((e.lane >> 1) & 3) : 0;
+#pragma unroll
+  for (int c = 0; c < NT; ++c) {
+    if (va) st_shared_v4(sa + e.lane * (NT * 16) + ((c ^ swz) << 4), reinterpret_cast<const uint4*>(wa)[c]);
+    if (vb) st_shared_v4(sb + e.lane * (NT * 16) + ((c ^ swz) << 4), reinterpret_cast<const uint4*>(wb)[c]);
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (e.lane == 0) {
+    if (va) tma_store_2d(e.to1, sa, ca, ra);
+    if (vb) tma_store_2d(e.to1, sb, cb, rb);
+    bulk_commit_group();
+  }
+  e.pending = true;
+}
 
 // ---- one 88-column slot, fp32 / 16-bit / embed outputs ---------------------------------------------------
 template <int EPI, bool F16>
@@ -485,7 +540,7 @@ __device__ __forceinline__ void epi_group_store16_prof(const GemmParams& p, cons
 }
 
 template <bool F16, typename Release>
-__device__ __forceinline__ void epi_group_store16(const GemmParams& p, const EpiCtx& e, uint32_t tacc, int n_lo, int n_hi,
+__device__ __forceinline__ void epi_group_store16(const GemmParams& p, EpiCtx& e, uint32_t tacc, int n_lo, int n_hi,
                                                   Release&& release) {
   float va[kSlot], vb[kSlot];
   uint32_t wa[44], wb[44];
@@ -493,6 +548,13 @@ __device__ __forceinline__ void epi_group_store16(const GemmParams& p, const Epi
   release();
   pack_row16<F16, 44>(va, wa);
   pack_row16<F16, 44>(vb, wb);
+  if (p.tma_store) {
+    if (e.rows_valid <= 0) return;                          // rows and columns outside the tensor are clipped by TMA
+    if (n_lo < p.N) tma_store_part64(e, wa, n_lo, e.row0);
+    if (n_hi < p.N) tma_store_part64(e, wb, n_hi, e.row0);
+    tma_store_tails<3>(e, wa + 32, n_lo + 64 < p.N, n_lo + 64, e.row0, wb + 32, n_hi + 64 < p.N, n_hi + 64, e.row0);
+    return;
+  }
   store_slot16(p.out0, p.ldo, p.N, e, n_lo, wa);
   store_slot16(p.out0, p.ldo, p.N, e, n_hi, wb);
 }
@@ -529,19 +591,30 @@ __device__ __forceinline__ void qkv_slot_store(const GemmParams& p, const EpiCtx
 }
 
 template <bool F16, typename Release>
-__device__ __forceinline__ void epi_group_qkv(const GemmParams& p, const EpiCtx& e, uint32_t tacc, int n_lo, int n_hi,
+__device__ __forceinline__ void epi_group_qkv(const GemmParams& p, EpiCtx& e, uint32_t tacc, int n_lo, int n_hi,
                                               Release&& release) {
   float va[kSlot], vb[kSlot];
-  uint32_t w[48];
   int sa, sb;
   tmem_load_cols2<kSlot>(tacc, va, tacc + kSlot, vb);
   release();
+  if (p.tma_store) {
+    // output viewed as [3 * heads * M, 96]: slot s, row r -> row s * M + r (M % 32 == 0: a box never leaves its slot)
+    uint32_t wa[48], wb[48];
+    const bool oka = qkv_slot_pack<F16>(p, n_lo, va, wa, &sa) && e.rows_valid > 0;
+    if (oka) tma_store_part64(e, wa, 0, sa * p.M + e.row0);
+    tmem_ld_fence_regs<kSlot>(vb);                          // keeps slot B's math behind slot A's stores (register pressure)
+    const bool okb = qkv_slot_pack<F16>(p, n_hi, vb, wb, &sb) && e.rows_valid > 0;
+    if (okb) tma_store_part64(e, wb, 0, sb * p.M + e.row0);
+    tma_store_tails<4>(e, wa + 32, oka, 64, sa * p.M + e.row0, wb + 32, okb, 64, sb * p.M + e.row0);
+    return;
+  }
+  uint32_t w[48];
   if (qkv_slot_pack<F16>(p, n_lo, va, w, &sa)) qkv_slot_store(p, e, sa, w);
   if (qkv_slot_pack<F16>(p, n_hi, vb, w, &sb)) qkv_slot_store(p, e, sb, w);
 }
 
 template <bool F16, typename Release>
-__device__ __forceinline__ void epi_group_swiglu(const GemmParams& p, const EpiCtx& e, uint32_t tacc, int out_col0,
+__device__ __forceinline__ void epi_group_swiglu(const GemmParams& p, EpiCtx& e, uint32_t tacc, int out_col0,
                                                  bool valid, Release&& release) {
   // gate slot at columns [0,88), up slot at [88,176) of this group's accumulator
   float g[kSlot], v[kSlot];
@@ -550,6 +623,13 @@ __device__ __forceinline__ void epi_group_swiglu(const GemmParams& p, const EpiC
   release();
 #pragma unroll
   for (int j = 0; j < 44; ++j) w[j] = pack_act2<F16>(silu_f(g[2 * j]) * v[2 * j], silu_f(g[2 * j + 1]) * v[2 * j + 1]);
+  if (p.tma_store) {
+    if (valid && e.rows_valid > 0) {
+      tma_store_part64(e, w, out_col0, e.row0);
+      tma_store_tails<3>(e, w + 32, true, out_col0 + 64, e.row0, w, false, 0, 0);
+    }
+    return;
+  }
   if (valid) store_slot16(p.out0, p.ldo, p.ldo, e, out_col0, w);
 }
 
@@ -804,6 +884,7 @@ __device__ __forceinline__ void epi_group_lnres(const GemmParams& p, const EpiCt
 template <int NSUB, int CG, int EPI, bool F16>
 __global__ void __launch_bounds__(GemmCfg<NSUB, CG>::kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_o0, const __grid_constant__ CUtensorMap tmap_o1,
                     const GemmParams p) {
   using S = GemmCfg<NSUB, CG>;
   constexpr int kStages = S::kStages;
@@ -840,6 +921,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (p.tma_store) {
+      tma_prefetch_desc(&tmap_o0);
+      tma_prefetch_desc(&tmap_o1);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -928,31 +1013,44 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 umma_f16_ss_elect<CG>(tmem_d, adesc0 + 2u * k, bdesc0 + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
             }
           } else {
+            // A operand of this k-block: straight from shared memory (read once per sub-tile: SWB_A_TMEM 0), or copied once
+            // into one of two 32-column TMEM slots (columns 176..239, free between the accumulators) and read from there
+            // by both sub-tiles: shared-memory bandwidth, not the tensor pipe, is what limits this kernel.
+            const int nk = full_block ? kKSteps : tail_ksteps;
+#if SWB_A_TMEM
+            const uint32_t a_t = tmem_base + kUmmaN + (static_cast<uint32_t>(kb) & 1u) * 32u;
+            if (full_block) {
+#pragma unroll
+              for (int k = 0; k < kKSteps; ++k) utccp_128x256b_pair_elect(a_t + 8u * k, adesc0 + 2u * k);
+            } else {
+              for (int k = 0; k < tail_ksteps; ++k) utccp_128x256b_pair_elect(a_t + 8u * k, adesc0 + 2u * k);
+            }
+            auto mma = [&](int j, int k, uint32_t acc) {
+              umma_f16_ts_pair_elect(tmem_d + j * kSubStride, a_t + 8u * k, bdesc0 + j * kSubDescStep + 2u * k, idesc, acc);
+            };
+#else
+            auto mma = [&](int j, int k, uint32_t acc) {
+              umma_f16_ss_elect<CG>(tmem_d + j * kSubStride, adesc0 + 2u * k, bdesc0 + j * kSubDescStep + 2u * k, idesc, acc);
+            };
+#endif
             if (kb == 0) {
               // first k-block of a tile: each sub-accumulator becomes writable as soon as its own epilogue group
               // of the previous tile has drained it, so start on sub 0 while sub 1 may still be read
-              const int nk = full_block ? kKSteps : tail_ksteps;
 #pragma unroll 1
               for (int j = 0; j < NSUB; ++j) {
                 mbar_wait(tempty_bar(j), par ^ 1u, 2);
                 tcgen05_fence_after();
-                for (int k = 0; k < nk; ++k)
-                  umma_f16_ss_elect<CG>(tmem_d + j * kSubStride, adesc0 + 2u * k, bdesc0 + j * kSubDescStep + 2u * k,
-                                        idesc, k != 0 ? 1u : 0u);
+                for (int k = 0; k < nk; ++k) mma(j, k, k != 0 ? 1u : 0u);
               }
             } else if (full_block) {
 #pragma unroll
               for (int k = 0; k < kKSteps; ++k) {
 #pragma unroll
-                for (int j = 0; j < NSUB; ++j)
-                  umma_f16_ss_elect<CG>(tmem_d + j * kSubStride, adesc0 + 2u * k, bdesc0 + j * kSubDescStep + 2u * k,
-                                        idesc, 1u);
+                for (int j = 0; j < NSUB; ++j) mma(j, k, 1u);
               }
             } else {
               for (int k = 0; k < tail_ksteps; ++k)
-                for (int j = 0; j < NSUB; ++j)
-                  umma_f16_ss_elect<CG>(tmem_d + j * kSubStride, adesc0 + 2u * k, bdesc0 + j * kSubDescStep + 2u * k,
-                                        idesc, 1u);
+                for (int j = 0; j < NSUB; ++j) mma(j, k, 1u);
             }
           }
           umma_commit_elect<CG>(empty_bar(stage));          // smem stage reusable once these MMAs retire
@@ -971,6 +1069,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     EpiCtx e;
     e.lane = lane;
     e.scratch = scratch0 + (warp - 4) * 4096;
+    e.to0 = &tmap_o0;
+    e.to1 = &tmap_o1;
+    e.pending = false;
     const uint32_t stat_smem = scratch0 + S::kEpiWarps * 4096 + (warp - 4) * 256;
     int it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
@@ -1043,6 +1144,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         release();
       }
     }
+    epi_scratch_acquire(e);     // outstanding TMA stores have finished reading this warp's smem
   }
 
   // teardown: nobody may exit (or free TMEM) while the peer can still signal our barriers / read our smem

@@ -114,6 +114,17 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* tmap,
       : "memory");
 }
 
+// 2-D tile store smem -> global (bulk async group of the issuing thread); the smem image uses the tensor map's swizzle
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk stores committed by this thread have finished READING shared memory (the buffer may be overwritten)
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- tcgen05 / TMEM
 template <int CG>
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
@@ -278,6 +289,25 @@ __device__ __forceinline__ void umma_f16_ts_elect(uint32_t tmem_d, uint32_t tmem
       "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
       :
       : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// CTA-pair form (M = 256: every CTA reads its 128 rows of A from its own tensor memory)
+__device__ __forceinline__ void umma_f16_ts_pair_elect(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// smem -> TMEM copy of 128 rows x 32 bytes (one K-step of a K-major 16-bit operand) in both CTAs of the pair; executes in
+// issue order with the tcgen05.mma instructions of the same thread
+__device__ __forceinline__ void utccp_128x256b_pair_elect(uint32_t taddr, uint64_t sdesc) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.cp.cta_group::2.128x256b [%0], %1;\n\t}" ::"r"(taddr),
+      "l"(sdesc)
       : "memory");
 }
 // registers -> TMEM: each lane writes 16 consecutive 32-bit columns of its own TMEM lane
