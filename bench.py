@@ -143,7 +143,7 @@ def workload_config(n_gpus: int, where: str, solver: str = "scm"):
             "member_steps_per_bench_step": MEMBERS * ICS_PER_GPU * n_gpus,
             "sharding": f"(member, IC) over {n_gpus} GPU(s), no collective on the forecast path",
             "l2_policy": "inputs larger than L2 (96 trajectories x 18.5 MB inputs, 216 MB workspace per sample)",
-            "step": "one CUDA graph per 6h step: Philox latents, forcings, 88 denoiser kernels per 8-trajectory chunk with the sCM update and the std/unstd glue fused in the head epilogue",
+            "step": "one CUDA graph per 6h step: Philox latents, forcings, the denoiser kernels per trajectory chunk (LayerNorm fused into the w2 GEMM, sCM update and std/unstd glue fused in the head epilogue), ensemble statistics",
             "device": where}
 
 
@@ -188,6 +188,16 @@ def run_ours(args):
     norm = Normalizers.synthetic(syn.IMG_CHANNELS, dev, diff=0.1)
     skw = dict(num_steps=20, sigma_min=0.02, sigma_max=200.0, auxiliary=0.6) if args.solver == "2s" else None
     ro = EnsembleRollout(net, norm, forc_dev, traj, solver=args.solver, solver_kwargs=skw, use_graph=not args.no_graph)
+    stats = None
+    if not args.no_stats and len(traj) % MEMBERS == 0:
+        # eval/metrics.py on the device: per-step sufficient statistics inside the step's CUDA graph, one NCCL all_gather
+        # of the sums after the rollout (synthetic verification fields: zeros)
+        import numpy as np
+        from swift_b200.ensemble import EnsembleStatistics
+        H_, W_ = cfg["img_resolution"]
+        stats = EnsembleStatistics(MEMBERS, len(traj) // MEMBERS, syn.IMG_CHANNELS, (H_, W_), np.linspace(-89.3, 89.3, H_),
+                                   total_steps + args.steps + 4, dev)
+        ro.attach_statistics(stats, torch.zeros(len(traj) // MEMBERS, syn.IMG_CHANNELS, H_, W_, device=dev))
     ics = {}
     x0 = torch.empty(B, syn.IMG_CHANNELS, *cfg["img_resolution"])
     for b, (m, j) in enumerate(traj):
@@ -251,6 +261,22 @@ def run_ours(args):
     h2d = forc_host[0].numel() * 4
     d2h = out_host.numel() * 4
 
+    # ---------------- ensemble scores: the one collective of the forecast path (all_gather of the per-step sums)
+    stats_info = None
+    if stats is not None:
+        e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e4.record()
+        allsums = stats.gather()
+        sc = stats.scores(allsums)
+        e5.record()
+        torch.cuda.synchronize()
+        k = args.warmup + args.steps - 1                 # last step of the device-resident leg
+        stats_info = {"gather_ms": max_over_ranks(e4.elapsed_time(e5)), "ics_scored": int(allsums.shape[1]),
+                      "bytes_per_rank": int(stats.sums.numel() * 8),
+                      "collective": "all_gather over NCCL" if world > 1 else "none (1 GPU)",
+                      "last_step": {m: float(sc[m][k].mean()) for m in ("rmse", "crps", "ssr")}}
+
     # ---------------- roofline of the dominant kernel (SwiGLU up-projection GEMM: 42.5 % of the FLOPs), timed alone
     roof = dominant_kernel_roofline(eng, dev, min(args.chunk, 8))
     peaks, which = measured_peaks()
@@ -281,6 +307,7 @@ def run_ours(args):
         "step_frac_of_sustained_bf16": step_tflops / peaks["bf16_tflops_sustained"],
         "peaks": which,
         "cpu_baseline": cpu,
+        "ensemble_statistics": stats_info,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -334,6 +361,7 @@ def main():
                          "39 denoiser calls per 6 h step (BASELINE.json configs[3])")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end leg (0 = same as --steps)")
     ap.add_argument("--fuse-ln", type=int, default=-1, help="override SwinV2.fuse_ln (bit 0: wo, bit 1: w2; 0 = separate LN kernel)")
+    ap.add_argument("--no-stats", action="store_true", help="do not accumulate the on-device ensemble scores")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SWB200_ABI_VERSION 9
+#define SWB200_ABI_VERSION 10
 #if defined(__GNUC__)
 #define SWB200_API __attribute__((visibility("default")))
 #else
@@ -199,6 +199,18 @@ SWB200_API int swb200_rollout_forcings(float* cond, int total_channels, int stat
                             const int32_t* step, int B, int hw, void* stream);
 /* *step += 1 (device-side, so a captured graph of one step can be replayed for the whole rollout) */
 SWB200_API int swb200_rollout_advance(int32_t* step, void* stream);
+
+/* ---- ensemble verification statistics on resident trajectories (eval/metrics.py:39-134) ------------------ */
+
+/* phys [n_ic * members, n_var, H, W] physical-space forecasts, member m of initial condition j at row j*members + m
+ * (the IC-major trajectory order of the rollout); truth [n_ic, n_var, H, W]; w_lat [H] = cos(lat) / mean(cos(lat)).
+ * Writes, per (ic, var), the four latitude-weighted sums from which the reference's scores follow
+ *   [0] sum w (mean_n p - y)^2   [1] sum_n sum w |p_n - y|   [2] sum_{i<j} sum w |p_i - p_j|   [3] sum w var_n(p)
+ * as fp64 at out[(step ? *step : 0) * out_stride + (ic * n_var + var) * 4 + k]; `step` is a DEVICE pointer (the
+ * rollout's step counter) so the call can sit inside the replayed CUDA graph of a 6 h step.
+ *   rmse = mean_ic sqrt([0] / HW)    crps = mean_ic([1] / (N HW) - [2] / (N (N-1) HW))    ssr = mean_ic sqrt([3] / HW) / rmse */
+SWB200_API int swb200_ensemble_stats(const float* phys, const float* truth, const float* w_lat, int n_ic, int members,
+                          int n_var, int H, int W, const int32_t* step, int out_stride, double* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -515,6 +515,14 @@ SWB200_API int swb200_rollout_forcings(float* cond, int total_channels, int stat
                                  static_cast<cudaStream_t>(stream));
 }
 
+SWB200_API int swb200_ensemble_stats(const float* phys, const float* truth, const float* w_lat, int n_ic, int members,
+                                     int n_var, int H, int W, const int32_t* step, int out_stride, double* out, void* stream) {
+  SWB_REQUIRE(phys && truth && w_lat && out, "swb200_ensemble_stats: NULL pointer");
+  SWB_REQUIRE(step == nullptr || out_stride >= n_ic * n_var * 4, "swb200_ensemble_stats: out_stride %d < n_ic*n_var*4", out_stride);
+  return launch_ensemble_stats(phys, truth, w_lat, n_ic, members, n_var, H, W, step, out_stride, out,
+                               static_cast<cudaStream_t>(stream));
+}
+
 SWB200_API int swb200_rollout_advance(int32_t* step, void* stream) {
   SWB_REQUIRE(step, "swb200_rollout_advance: NULL pointer");
   return launch_rollout_advance(step, static_cast<cudaStream_t>(stream));

@@ -46,4 +46,8 @@ int launch_rollout_forcings(float* cond, int total_ch, int state_ch, const float
                             int B, int hw, cudaStream_t stream);
 int launch_rollout_advance(int* step, cudaStream_t stream);
 
+// ensemble verification statistics (ensemble.cu): out[(*step) * out_stride + (ic * V + v) * 4 + k]
+int launch_ensemble_stats(const float* phys, const float* truth, const float* w_lat, int n_ic, int members, int V, int H,
+                          int W, const int* step, int out_stride, double* out, cudaStream_t stream);
+
 }  // namespace swb

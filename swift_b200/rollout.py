@@ -103,6 +103,23 @@ class EnsembleRollout:
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._glue = RolloutGlue(self.cond, norm.x_std, norm.x_mean, norm.diff_std, self.phys, norm.zero_channel)
         self._cond_vecs = None
+        self._stats = None
+        self._truth: Optional[torch.Tensor] = None
+
+    # ------------------------------------------------------------------ ensemble statistics (eval/metrics.py on device)
+    def attach_statistics(self, stats, truth: torch.Tensor) -> None:
+        """Score every step on the device: ``stats`` (swift_b200.ensemble.EnsembleStatistics) receives the physical state of
+        each step, compared with ``truth`` [n_ic, n_var, H, W] -- a static device buffer the caller refreshes with the
+        verifying analysis of the coming step before calling step().  Needs whole ensembles on this GPU in IC-major order
+        (what shard_trajectories produces when the ICs divide evenly over the ranks)."""
+        n = stats.members
+        ok = len(self.traj) == stats.n_ic * n and all(m == k % n and j == self.traj[0][1] + k // n
+                                                       for k, (m, j) in enumerate(self.traj))
+        if not ok:
+            raise ValueError("attach_statistics needs the trajectories of this rank to be whole ensembles in IC-major order "
+                             f"({stats.n_ic} ICs x {n} members); got {len(self.traj)} trajectories starting at {self.traj[:2]}")
+        self._stats, self._truth = stats, truth
+        self._graph = None                       # the statistics kernel becomes part of the captured step
 
     # ------------------------------------------------------------------ state
     def set_state(self, x_std: torch.Tensor, step: int = 0) -> None:
@@ -144,8 +161,12 @@ class EnsembleRollout:
             x_in.mul_(sd)                                    # x_t = latents * sigma_d (diffusion.py:452)
         eng.forward(x_in, self.cond, gain, bias, scale0=1.0 / sd, xt=x_in, alpha=cos_t, beta=-sin_t * sd,
                     rollout=self._glue)
+        n_extra = 3
+        if self._stats is not None:
+            self._stats.accumulate(self.phys, self._truth, step_dev=self.step_dev)
+            n_extra += 1
         self._advance()
-        eng.launches += 3
+        eng.launches += n_extra
 
     @torch.no_grad()
     def step(self, forcings_i: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -167,7 +188,8 @@ class EnsembleRollout:
                         self._fused_step()
                     self._graph = g          # capture does not execute: the replay below is the first real step
                 self._graph.replay()
-                self.model.engine().launches += self.model.engine().launches_per_forward(len(self.traj)) + 3
+                self.model.engine().launches += (self.model.engine().launches_per_forward(len(self.traj)) + 3 +
+                                                 (1 if self._stats is not None else 0))
             return self.phys
         # generic path (multi-step sCM, 2S, non-fused nets, externally supplied forcings)
         if forcings_i is None:
@@ -185,6 +207,8 @@ class EnsembleRollout:
             x_new[:, self.norm.zero_channel] = 0
         x_std.copy_(x_new)
         self.phys.copy_(x_phys)
+        if self._stats is not None:
+            self._stats.accumulate(self.phys, self._truth, step_dev=self.step_dev)
         self._advance()
         return self.phys
 
