@@ -617,12 +617,28 @@ template <bool F16, typename Release>
 __device__ __forceinline__ void epi_group_swiglu(const GemmParams& p, EpiCtx& e, uint32_t tacc, int out_col0,
                                                  bool valid, Release&& release) {
   // gate slot at columns [0,88), up slot at [88,176) of this group's accumulator
+#ifdef SWB_SWIGLU_PACKED_GATE
+  // gate parked as 16-bit pairs between the two TMEM loads (one extra 2^-12 rounding in front of a 16-bit result)
+  float v[kSlot];
+  uint32_t g16[44], w[44];
+  tmem_load_cols<kSlot>(tacc, v);
+  pack_row16<F16, 44>(v, g16);
+  tmem_load_cols<kSlot>(tacc + kSlot, v);
+  release();
+#pragma unroll
+  for (int j = 0; j < 44; ++j) {
+    const float g0 = unpack_act1<F16>(static_cast<uint16_t>(g16[j] & 0xffffu));
+    const float g1 = unpack_act1<F16>(static_cast<uint16_t>(g16[j] >> 16));
+    w[j] = pack_act2<F16>(silu_f(g0) * v[2 * j], silu_f(g1) * v[2 * j + 1]);
+  }
+#else
   float g[kSlot], v[kSlot];
   uint32_t w[44];
   tmem_load_cols2<kSlot>(tacc, g, tacc + kSlot, v);
   release();
 #pragma unroll
   for (int j = 0; j < 44; ++j) w[j] = pack_act2<F16>(silu_f(g[2 * j]) * v[2 * j], silu_f(g[2 * j + 1]) * v[2 * j + 1]);
+#endif
   if (p.tma_store) {
     if (valid && e.rows_valid > 0) {
       tma_store_part64(e, w, out_col0, e.row0);
@@ -949,7 +965,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   // 384 threads x 168 registers at launch: warps 0-3 keep 64, the two epilogue warpgroups grow to 216 (64*128 + 216*256 = 384*168: setmaxnreg.inc blocks for ever if the CTA pool is exceeded) (the
   // re-allocation sits at the top of each warpgroup's own branch: ptxas budgets the code it dominates)
   if (warp < 4) {
+#ifndef SWB_NO_SETMAXNREG
   if constexpr (S::kEpiWarps == 8) setmaxnreg_dec<64>();
+#endif
   if (warp == 0) {
     // ===================================== TMA producer (whole warp converged, one elected lane issues) ==========
     const uint32_t full_leader0 = (CG == 2) ? mapa_u32(full_bar(0), 0) : full_bar(0);
@@ -1062,7 +1080,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
   } else {
     // ===================================== epilogue =====================================
+#ifndef SWB_NO_SETMAXNREG
     if constexpr (S::kEpiWarps == 8) setmaxnreg_inc<216>();
+#endif
     const int quad = warp & 3;                              // TMEM lane quadrant this warp may access
     const int grp = (warp - 4) >> 2;                        // NSUB == 2: epilogue group = sub-tile it drains
     const uint32_t tempty_leader0 = (CG == 2) ? mapa_u32(tempty_bar(0), 0) : tempty_bar(0);

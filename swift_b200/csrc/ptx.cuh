@@ -391,10 +391,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 template <bool F16>
 __device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
   if constexpr (F16) {
-    lo = fminf(fmaxf(lo, -65504.f), 65504.f);
-    hi = fminf(fmaxf(hi, -65504.f), 65504.f);
-    __half2 v = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
+    uint32_t r;                                   // one F2FP.SATFINITE: |x| > 65504 (and inf) -> +-65504
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
   } else {
     return pack_bf16x2(lo, hi);
   }
@@ -402,8 +401,9 @@ __device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
 template <bool F16>
 __device__ __forceinline__ uint16_t pack_act1(float x) {
   if constexpr (F16) {
-    __half v = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
-    return *reinterpret_cast<uint16_t*>(&v);
+    uint16_t r;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(x));
+    return r;
   } else {
     __nv_bfloat16 v = __float2bfloat16_rn(x);
     return *reinterpret_cast<uint16_t*>(&v);

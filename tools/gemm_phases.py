@@ -46,7 +46,10 @@ def main():
         W = (torch.randn(N, K, device="cuda") * 0.05).half()
         out = torch.empty(M, N, device="cuda", dtype=torch.float16)
         res = {}
-        for epi, label in ((6, "mainloop"), (7, "+drain"), (8, "+smem"), (9, "direct"), (1, "store16")):
+        variants = ((6, "mainloop"), (7, "+drain"), (8, "+smem"), (9, "direct"), (1, "store16"))
+        if os.environ.get("SWB_LIB_ANYABI"):
+            variants = ((1, "store16"),)                 # older builds do not have the profiling epilogues
+        for epi, label in variants:
             for _ in range(3):
                 _lib.check(lib.swb200_gemm(epi, tile, 1, A.data_ptr(), K, W.data_ptr(), K, out.data_ptr(), N, M, N, K, st))
             torch.cuda.synchronize()
@@ -59,6 +62,27 @@ def main():
                 e1.record()
                 torch.cuda.synchronize()
             res[label] = (e0.elapsed_time(e1) / reps, smi.mhz, smi.watt)
+        if name in ("qkv", "w1"):                       # the real fused epilogue of this shape
+            if name == "qkv":
+                qs = torch.full((12,), 10.0, device="cuda")
+                o2 = torch.empty(3 * 12 * M * 96, device="cuda", dtype=torch.float16)
+                fn = lambda: _lib.check(lib.swb200_gemm_qkv(tile, 1, A.data_ptr(), K, W.data_ptr(), qs.data_ptr(), o2.data_ptr(), M, 1056, 12, st))
+            else:
+                o2 = torch.empty(M, N // 2, device="cuda", dtype=torch.float16)
+                fn = lambda: _lib.check(lib.swb200_gemm_swiglu(tile, 1, A.data_ptr(), K, W.data_ptr(), o2.data_ptr(), M, 1056, N // 2, st))
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            reps = max(10, int(secs * 1e3 / max(1e-3, 2.0 * M * N * K / 1.3e12)))
+            with Smi() as smi:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+            res["fused_epi"] = (e0.elapsed_time(e1) / reps, smi.mhz, smi.watt)
+            del o2
         fl = 2.0 * M * N * K
         print(f"  {name:4s} N={N:5d} K={K:5d}: " + "\n        " + "\n        ".join(
             f"{k:9s} {v[0] * 1e3:7.1f} us ({fl / v[0] / 1e9:6.0f} TF/s, {v[1]:4.0f} MHz, {v[2]:4.0f} W, "
