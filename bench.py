@@ -240,27 +240,32 @@ def run_ours(args):
     value = member_steps / (ms / 1e3)
 
     # ---------------- end-to-end leg: host buffers in, host buffers out, every step
-    out_host = torch.empty(B, syn.IMG_CHANNELS, *cfg["img_resolution"]).pin_memory()
+    # (EnsembleRollout.run_to_host: per step the forcings come from pinned host memory and the new physical state of every
+    #  trajectory lands in pinned host memory; the D2H copy of step i overlaps the compute of step i+1.  The timed region
+    #  ends when the last step's state is complete on the host: wall clock, max over ranks.)
+    out_host = torch.empty(2, B, syn.IMG_CHANNELS, *cfg["img_resolution"]).pin_memory()
     e2e_steps = args.steps if args.e2e_steps <= 0 else min(args.e2e_steps, args.steps)
+    checksum = [0.0]
+
+    def consume(i, view):                                                          # the host reads every step's result
+        checksum[0] += float(view[0, 0, 0, 0]) + float(view[-1, -1, -1, -1])
+
     ro.set_state(x0.to(dev, non_blocking=True))                                    # H2D: initial conditions
-    ro.forcings[0].copy_(forc_host[0], non_blocking=True)
-    out_host.copy_(ro.step(), non_blocking=True)                                   # one untimed step
+    ro.run_to_host(1, out_host, forc_host, first_forcing=0, on_host=consume)       # one untimed step
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
     e2.record()
-    for i in range(e2e_steps):
-        ro.forcings[1 + i].copy_(forc_host[1 + i], non_blocking=True)              # H2D: this step's forcings
-        x_phys = ro.step()
-        out_host.copy_(x_phys, non_blocking=True)                                  # D2H: new physical state
-        torch.cuda.current_stream().synchronize()                                  # host consumes it (generate.py:129)
+    ro.run_to_host(e2e_steps, out_host, forc_host, first_forcing=1, on_host=consume)
     e3.record()
-    barrier()
     wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    barrier()
     e2e_ms = max_over_ranks(max(e2.elapsed_time(e3), wall_ms))
     e2e_value = B * world * e2e_steps / (e2e_ms / 1e3)
     h2d = forc_host[0].numel() * 4
-    d2h = out_host.numel() * 4
+    d2h = out_host[0].numel() * 4
+    if not math.isfinite(checksum[0]):
+        raise RuntimeError("end-to-end leg produced non-finite output")
 
     # ---------------- ensemble scores: the one collective of the forecast path (all_gather of the per-step sums)
     stats_info = None

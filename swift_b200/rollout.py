@@ -213,6 +213,45 @@ class EnsembleRollout:
         return self.phys
 
     @torch.no_grad()
+    def run_to_host(self, steps: int, out_host: torch.Tensor, forcings_host: Optional[torch.Tensor] = None,
+                    first_forcing: int = 0, on_host: Optional[Callable[[int, torch.Tensor], None]] = None) -> None:
+        """The loop of generate.py:97-136 with HOST buffers: per step the standardised forcings of that step come from
+        ``forcings_host`` [>= first_forcing + steps, n_forc, H, W] (pinned) and the new physical state of every trajectory
+        lands in ``out_host`` [steps or 2, B, n_var, H, W] (pinned; with 2 slots they are used alternately).
+        The reference blocks on ``.cpu()`` every step (generate.py:129); here the device->host copy of step i runs on a
+        copy stream while step i+1 computes (the state is first parked in a device staging buffer, because the next
+        step overwrites ``phys``).  ``on_host(i, view)`` is called once step i's data is complete in host memory."""
+        if out_host.dim() != 5 or tuple(out_host.shape[1:]) != tuple(self.phys.shape) or not out_host.is_pinned():
+            raise RuntimeError(f"out_host must be a pinned [slots, {', '.join(map(str, self.phys.shape))}] tensor")
+        slots = out_host.shape[0]
+        if slots < min(2, steps):
+            raise RuntimeError("out_host needs at least 2 slots (one is written while the other is consumed)")
+        main = torch.cuda.current_stream()
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._staging = torch.empty_like(self.phys)
+        staged = torch.cuda.Event()
+        drained = [torch.cuda.Event() for _ in range(2)]
+        for i in range(steps):
+            if forcings_host is not None:
+                self.forcings[first_forcing + i].copy_(forcings_host[first_forcing + i], non_blocking=True)
+            x_phys = self.step()
+            if i > 0:
+                main.wait_event(drained[(i - 1) & 1])          # the copy stream has finished reading the staging buffer
+            self._staging.copy_(x_phys, non_blocking=True)
+            staged.record(main)
+            self._copy_stream.wait_event(staged)
+            with torch.cuda.stream(self._copy_stream):
+                out_host[i % slots].copy_(self._staging, non_blocking=True)
+                drained[i & 1].record(self._copy_stream)
+            if on_host is not None and i > 0:
+                drained[(i - 1) & 1].synchronize()
+                on_host(i - 1, out_host[(i - 1) % slots])
+        self._copy_stream.synchronize()
+        if on_host is not None and steps > 0:
+            on_host(steps - 1, out_host[(steps - 1) % slots])
+
+    @torch.no_grad()
     def run(self, steps: int, on_step: Optional[Callable[[int, torch.Tensor], None]] = None) -> torch.Tensor:
         for i in range(steps):
             x_phys = self.step()
