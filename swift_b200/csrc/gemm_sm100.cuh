@@ -1149,10 +1149,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       } else if constexpr (EPI == EPI_DISCARD) {
         release();
       } else if constexpr (EPI == EPI_DRAIN) {
-        float v[kSlot];
-        tmem_load_cols<kSlot>(tacc, v);
-        tmem_load_cols<kSlot>(tacc + kSlot, v);
+        float va[kSlot], vb[kSlot];
+        tmem_load_cols2<kSlot>(tacc, va, tacc + kSlot, vb);
         release();
+        float acc = 0.f;                                    // consume the values (ptxas drops tcgen05.ld with dead results)
+#pragma unroll
+        for (int j = 0; j < kSlot; ++j) acc += va[j] * vb[j];
+        if (acc == 1.2345e-33f && p.out0) static_cast<float*>(p.out0)[0] = acc;
       } else {
 #pragma unroll 1
         for (int hf = 0; hf < 2; ++hf) {
