@@ -161,8 +161,11 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # rank 0 prints ONE JSON line on stdout: NCCL's version banner / debug lines go to a file instead
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/swift_b200_nccl.%h.%p.log")
+        # rank 0 prints ONE JSON line on stdout: anything native code writes to fd 1 meanwhile (NCCL's version banner,
+        # NCCL_DEBUG output) is sent to stderr; the descriptor is restored just before the line is printed
+        sys.stdout.flush()
+        stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -315,8 +318,12 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "ensemble_statistics": stats_info,
     }
+    if world > 1:
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
+        os.dup2(2, 1)
         dist.destroy_process_group()
 
 
