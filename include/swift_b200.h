@@ -158,8 +158,9 @@ SWB200_API int swb200_gemm_embed(int tile, int act_fp16, const void* A, int lda,
  * that hold the column tiles of a row through `ln_ws` (swb200_ln_workspace_bytes(M, dim) bytes, 256-byte aligned,
  * private to the stream).  `gen` numbers the launches that share ln_ws since its counters were last cleared:
  * launch 0 clears them (a memset node on `stream`), launch g expects the g launches before it to have completed.
- * Every CTA of the grid must be resident (the launcher checks the occupancy; do not run other kernels on the device
- * concurrently). */
+ * Every CTA of the grid must be resident: the launcher checks the occupancy and returns -4 (nothing launched) when the
+ * device cannot hold the grid -- swb200_forward then runs the same update as GEMM + swb200_ln_mod_residual; do not run
+ * other kernels on the device concurrently. */
 SWB200_API size_t swb200_ln_workspace_bytes(int M, int dim);
 SWB200_API int swb200_gemm_ln_residual(int tile, int act_fp16, const void* A, int lda, const void* W, int K, void* xhl,
                             const float* gain, const float* bias, int M, int dim, int tokens, void* ln_ws, int gen,

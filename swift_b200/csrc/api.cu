@@ -220,7 +220,9 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
     const int BR16 = F16;
     const int epi_branch = BR16 ? EPI_STORE_ACT : EPI_STORE_F32;
     void* hbuf = ws + w.h;
-    const bool fuse_wo = (m->fuse_ln & 1) != 0, fuse_w2 = (m->fuse_ln & 2) != 0;
+    // the fused epilogue spins on statistics published by other CTAs of its grid: if the device cannot keep the whole grid
+    // resident (reported before anything is launched) the same update runs as GEMM + LayerNorm kernel instead
+    bool fuse_wo = (m->fuse_ln & 1) != 0, fuse_w2 = (m->fuse_ln & 2) != 0;
     void* lnws = ws + w.lnws;
     int ln_gen = 0;                             // fused launches of this chunk so far (the first one clears the counters)
 
@@ -266,10 +268,13 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
       if (fuse_wo) {
         // wo projection + LayerNorm + modulation + residual add in one kernel (no branch buffer)
         { TraceScope ts_(T_WO, stream);
-        rc = swb200_gemm_ln_residual(kDefaultCG, F16, attn, D, wo, D, xhl, gain_a, bias_a, M, D, g.tokens, lnws, ln_gen++,
+        rc = swb200_gemm_ln_residual(kDefaultCG, F16, attn, D, wo, D, xhl, gain_a, bias_a, M, D, g.tokens, lnws, ln_gen,
                                      stream_); }
-        if (rc) return rc;
-      } else {
+        if (rc == SWB_ERR_RESIDENCY) fuse_wo = fuse_w2 = false;
+        else if (rc) return rc;
+        else ++ln_gen;
+      }
+      if (!fuse_wo) {
         GemmParams p = base_params(M, D, D);
         p.out0 = branch;
         p.ldo = D;
@@ -295,9 +300,12 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
       if (fuse_w2) {
         { TraceScope ts_(T_W2, stream);
         rc = swb200_gemm_ln_residual(kDefaultCG, F16, hbuf, Dff, w2, Dff, xhl, gain_f, bias_f, M, D, g.tokens, lnws,
-                                     ln_gen++, stream_); }
-        if (rc) return rc;
-      } else {
+                                     ln_gen, stream_); }
+        if (rc == SWB_ERR_RESIDENCY) fuse_wo = fuse_w2 = false;
+        else if (rc) return rc;
+        else ++ln_gen;
+      }
+      if (!fuse_w2) {
         GemmParams p = base_params(M, D, Dff);
         p.out0 = branch;
         p.ldo = D;

@@ -32,6 +32,7 @@ const char* get_error();
 constexpr int SWB_OK = 0;
 constexpr int SWB_ERR_INVALID = -2;     // bad argument / unsupported configuration
 constexpr int SWB_ERR_DRIVER = -3;      // driver entry point or tensor-map encode failure
+constexpr int SWB_ERR_RESIDENCY = -4;   // the fused LayerNorm GEMM needs every CTA of its grid resident and the device cannot hold them
 
 int num_sms();
 

@@ -118,8 +118,10 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     // the statistics exchange spins on other CTAs of this grid: every cluster has to be resident
     static int max_clusters = -1;
     if (max_clusters < 0) SWB_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
-    SWB_REQUIRE(max_clusters >= clusters, "gemm_ln_residual: only %d of %d CTA clusters can be co-resident", max_clusters,
-                clusters);
+    if (max_clusters < clusters) {
+      set_error("gemm_ln_residual: only %d of %d CTA clusters can be co-resident", max_clusters, clusters);
+      return SWB_ERR_RESIDENCY;
+    }
   }
   SWB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to0, to1, p));
   return SWB_OK;
