@@ -35,6 +35,7 @@ extern "C" {
 /* Geometry + packed parameters of one SwinV2 denoiser (constructor arguments of swinv2.py:255-270).
  * Packed layouts are produced by swift_b200/packing.py (documented in DESIGN.md section 3):
  * ("h16" = fp16 when act_fp16 else bf16)
+ *   b_embed : fp32 [dim] or NULL when the bias has been folded into pos_embed (what packing.py does)
  *   w_embed : h16 [dim, k_embed * (1 + split_embed)]   columns in "(c p1 p2)" order, zero padded to k_embed,
  *             duplicated when split_embed (the A operand is then [hi | lo], see swb200_forward)
  *   w_qkv   : h16  [depth][3*dim, dim]   rows reordered to  part*dim + head*88 + d   (part = q,k,v)
@@ -148,7 +149,7 @@ SWB200_API int swb200_gemm_qkv(int tile, int act_fp16, const void* A, int lda, c
 /* SwiGLU up-projection: out[M, dff] = silu(gate) * up; W packed as w_1. */
 SWB200_API int swb200_gemm_swiglu(int tile, int act_fp16, const void* A, int lda, const void* W, void* out, int M, int dim, int dff,
                        void* stream);
-/* Patch-embed: x[M,dim] = A*W^T + bias + pos[row % tokens], written as the 16-bit residual pair xhl[M, 2*dim] =
+/* Patch-embed: x[M,dim] = A*W^T + bias + pos[row % tokens] (bias may be NULL), written as the 16-bit residual pair xhl[M, 2*dim] =
  * [hi | lo] with x = hi + lo (hi is the A operand of the next GEMM, row pitch 2*dim). */
 SWB200_API int swb200_gemm_embed(int tile, int act_fp16, const void* A, int lda, const void* W, int K, const float* bias,
                       const float* pos, int tokens, void* xhl, int M, int dim, void* stream);

@@ -375,7 +375,7 @@ SWB200_API int swb200_gemm_swiglu(int tile, int act_fp16, const void* A, int lda
 
 SWB200_API int swb200_gemm_embed(int tile, int act_fp16, const void* A, int lda, const void* W, int K, const float* bias,
                       const float* pos, int tokens, void* xhl, int M, int dim, void* stream) {
-  SWB_REQUIRE(A && W && bias && pos && xhl, "swb200_gemm_embed: NULL pointer");
+  SWB_REQUIRE(A && W && pos && xhl, "swb200_gemm_embed: NULL pointer");
   GemmParams p = base_params(M, dim, K);
   p.out0 = xhl;
   p.ldo = 2 * dim;

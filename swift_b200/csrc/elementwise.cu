@@ -39,16 +39,21 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const float* __restri
   {
     const int chunk = blockIdx.z;                    // one channel chunk per block: gh * B * nchunks independent blocks
     const int c0 = chunk * kGatherCh;
-    for (int idx = threadIdx.x; idx < kGatherCh * p1 * W; idx += blockDim.x) {
-      const int xw = idx % W;
-      const int r = idx / W;            // c*p1 + py
+    // image rows of this channel chunk -> smem, 16 bytes per load (W % 4 == 0 and 16-byte aligned rows: checked by the launcher)
+    const int w4 = W >> 2;
+    for (int idx = threadIdx.x; idx < kGatherCh * p1 * w4; idx += blockDim.x) {
+      const int x4 = idx % w4;
+      const int r = idx / w4;           // c*p1 + py
       const int c = c0 + r / p1, py = r % p1;
-      float v = 0.f;
-      if (c < C0)
-        v = __ldg(src0 + ((static_cast<size_t>(b) * C0 + c) * H + gy * p1 + py) * W + xw) * scale0;
-      else if (c < C)
-        v = __ldg(src1 + ((static_cast<size_t>(b) * C1 + (c - C0)) * H + gy * p1 + py) * W + xw);
-      tile[r * pitch + xw] = v;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < C0) {
+        v = __ldg(reinterpret_cast<const float4*>(src0 + ((static_cast<size_t>(b) * C0 + c) * H + gy * p1 + py) * W) + x4);
+        v.x *= scale0; v.y *= scale0; v.z *= scale0; v.w *= scale0;
+      } else if (c < C) {
+        v = __ldg(reinterpret_cast<const float4*>(src1 + ((static_cast<size_t>(b) * C1 + (c - C0)) * H + gy * p1 + py) * W) + x4);
+      }
+      float* t = tile + r * pitch + 4 * x4;
+      t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
     }
     __syncthreads();
     // one 16-byte store (8 consecutive k) per thread: consecutive threads cover consecutive groups of one token
@@ -86,6 +91,8 @@ int launch_patch_gather(const float* src0, int C0, float scale0, const float* sr
               "patch_gather: need Kp=%d >= C*p1*p2=%d, Kp and lda multiples of 8, A 16-byte aligned", Kp,
               (C0 + C1) * p1 * p2);
   SWB_REQUIRE((kGatherCh * p1 * p2) % 8 == 0, "patch_gather: patch %dx%d unsupported", p1, p2);
+  SWB_REQUIRE(W % 4 == 0 && (reinterpret_cast<uintptr_t>(src0) & 15) == 0 && (reinterpret_cast<uintptr_t>(src1) & 15) == 0,
+              "patch_gather: image width %d must be a multiple of 4 and the inputs 16-byte aligned", W);
   const size_t smem = static_cast<size_t>(kGatherCh) * p1 * (W + 2) * sizeof(float);
   SWB_REQUIRE(smem <= 48 * 1024, "patch_gather: image width %d too large for the staging tile", W);
   const int cvirt = (Kp + p1 * p2 - 1) / (p1 * p2);

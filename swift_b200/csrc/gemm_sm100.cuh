@@ -143,13 +143,19 @@ template <int NCH>
 __device__ __forceinline__ void warp_load_rows(const uint8_t* g_row0, size_t pitch_bytes, uint4* v, uint32_t scratch,
                                                int lane, int rows_valid, int chunks_valid) {
   static_assert(NCH >= 1 && NCH <= 8, "one 128-byte smem row per lane");
+  uint4 q[NCH];                                             // every global load is issued before the first smem store
 #pragma unroll
   for (int it = 0; it < NCH; ++it) {
     const int idx = it * 32 + lane;
     const int r = idx / NCH, c = idx - r * NCH;
-    uint4 q = make_uint4(0u, 0u, 0u, 0u);
-    if (r < rows_valid && c < chunks_valid) q = __ldg(reinterpret_cast<const uint4*>(g_row0 + r * pitch_bytes + c * 16));
-    st_shared_v4(scratch + r * 128 + ((c ^ (r & 7)) << 4), q);
+    q[it] = make_uint4(0u, 0u, 0u, 0u);
+    if (r < rows_valid && c < chunks_valid) q[it] = __ldg(reinterpret_cast<const uint4*>(g_row0 + r * pitch_bytes + c * 16));
+  }
+#pragma unroll
+  for (int it = 0; it < NCH; ++it) {
+    const int idx = it * 32 + lane;
+    const int r = idx / NCH, c = idx - r * NCH;
+    st_shared_v4(scratch + r * 128 + ((c ^ (r & 7)) << 4), q[it]);
   }
   __syncwarp();
 #pragma unroll
@@ -256,15 +262,20 @@ __device__ __forceinline__ void tma_store_tails(EpiCtx& e, const uint32_t* wa, b
 }
 
 // ---- one 88-column slot, fp32 / 16-bit / embed outputs ---------------------------------------------------
-template <int EPI, bool F16>
-__device__ __forceinline__ void epi_slot_store(const GemmParams& p, const EpiCtx& e, uint32_t tslot, int n0) {
+// vreg == nullptr: the slot is read from TMEM block by block (accumulator still held); else its 88 values are in registers
+template <int EPI, bool F16, bool FROM_REGS = false>
+__device__ __forceinline__ void epi_slot_store(const GemmParams& p, const EpiCtx& e, uint32_t tslot, int n0,
+                                               const float* vreg = nullptr) {
   // blocks of 32, 32, 24 columns
-#pragma unroll 1
+#pragma unroll(FROM_REGS ? 3 : 1)
   for (int blk = 0; blk < 3; ++blk) {
     const int c0 = blk * 32;
     const int n = n0 + c0;
     float v[32];
-    if (blk < 2) {
+    if constexpr (FROM_REGS) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = (c0 + j < kSlot) ? vreg[(c0 + j < kSlot) ? c0 + j : 0] : 0.f;
+    } else if (blk < 2) {
       tmem_load_cols<32>(tslot + c0, v);
     } else {
       tmem_load_cols<24>(tslot + c0, v);
@@ -282,9 +293,14 @@ __device__ __forceinline__ void epi_slot_store(const GemmParams& p, const EpiCtx
       const uint8_t* pg = reinterpret_cast<const uint8_t*>(p.pos + static_cast<size_t>(e.row0 % p.pos_rows) * p.N + n);
       warp_load_rows<8>(pg, static_cast<size_t>(p.N) * 4, reinterpret_cast<uint4*>(pe), e.scratch, e.lane, e.rows_valid,
                         cols_valid >> 2);
+      if (p.bias) {                                       // (the model path folds the bias into pos_embed at pack time)
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < cols_valid) v[j] += __ldg(p.bias + n + j);
+      }
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (j < cols_valid) v[j] += __ldg(p.bias + n + j) + pe[j];
+        if (j < cols_valid) v[j] += pe[j];
     }
     if constexpr (EPI == EPI_STORE_F32) {
       uint8_t* g = reinterpret_cast<uint8_t*>(static_cast<float*>(p.out0) + static_cast<size_t>(e.row0) * p.ldo + n);
@@ -463,6 +479,103 @@ __device__ __forceinline__ void epi_slot_head(const GemmParams& p, const EpiCtx&
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int n = n0 + c + j;
+        if (n < p.N) {
+          const int ch = n / pp, r = n - ch * pp;
+          const int py = r / p.p2, px = r - py * p.p2;
+          head_apply<1>(p, b, ch, static_cast<size_t>(gy * p.p1 + py) * p.W + (gx * p.p2 + px), v + j);
+        }
+      }
+    }
+  }
+}
+
+// NB horizontally adjacent pixel pairs (columns n0, n0 + 2, ...) of one token: same arithmetic as head_apply<2>, but every
+// load of the batch is issued before the first store (the state is updated in place, so the compiler may not hoist a
+// load above an earlier store by itself: un-batched, the epilogue pays one DRAM round trip per pair).
+template <int NB>
+__device__ __forceinline__ void head_apply_pairs(const GemmParams& p, int b, int gy, int gx, int n0, const float* F) {
+  const size_t hw = static_cast<size_t>(p.H) * p.W;
+  const int pp = p.p1 * p.p2;
+  size_t a[NB], sa[NB];
+  int ch[NB];
+  bool ok[NB];
+  float2 xt[NB], fp[NB], st[NB];
+  float xs[NB], xm[NB], ds[NB];
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    const int n = n0 + 2 * i;
+    ok[i] = n < p.N;
+    ch[i] = n / pp;
+    const int r = n - ch[i] * pp;
+    const int py = r / p.p2, px = r - py * p.p2;
+    const size_t pix = static_cast<size_t>(gy * p.p1 + py) * p.W + (gx * p.p2 + px);
+    a[i] = (static_cast<size_t>(b) * p.C + ch[i]) * hw + pix;
+    sa[i] = (static_cast<size_t>(b) * p.state_C + ch[i]) * hw + pix;
+  }
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    xt[i] = fp[i] = st[i] = make_float2(0.f, 0.f);
+    xs[i] = 1.f;
+    xm[i] = ds[i] = 0.f;
+    if (ok[i]) {
+      if (p.xt) xt[i] = __ldg(reinterpret_cast<const float2*>(p.xt + a[i]));
+      if (p.fprev) fp[i] = __ldg(reinterpret_cast<const float2*>(p.fprev + a[i]));
+      if (p.state) {
+        st[i] = *reinterpret_cast<const float2*>(p.state + sa[i]);
+        xs[i] = __ldg(p.x_std + ch[i]);
+        xm[i] = __ldg(p.x_mean + ch[i]);
+        ds[i] = __ldg(p.d_std + ch[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    if (!ok[i]) continue;
+    float y0 = p.beta * F[2 * i], y1 = p.beta * F[2 * i + 1];
+    if (p.xt) { y0 = fmaf(p.alpha, xt[i].x, y0); y1 = fmaf(p.alpha, xt[i].y, y1); }
+    if (p.fprev) { y0 = fmaf(p.gamma, fp[i].x, y0); y1 = fmaf(p.gamma, fp[i].y, y1); }
+    if (p.out0) *reinterpret_cast<float2*>(static_cast<float*>(p.out0) + a[i]) = make_float2(y0, y1);
+    if (p.out_f) *reinterpret_cast<float2*>(p.out_f + a[i]) = make_float2(F[2 * i], F[2 * i + 1]);
+    if (p.state) {
+      // generate.py:120-131 (residual branch): X_phys = unstd_x(X) + Y*sigma_diff;  X <- std_x(X_phys)
+      const float rxs = 1.0f / xs[i];
+      float ph0 = fmaf(st[i].x, xs[i], xm[i]) + y0 * ds[i], ph1 = fmaf(st[i].y, xs[i], xm[i]) + y1 * ds[i];
+      float sn0 = (ph0 - xm[i]) * rxs, sn1 = (ph1 - xm[i]) * rxs;
+      if (ch[i] == p.zero_channel) ph0 = ph1 = sn0 = sn1 = 0.f;
+      *reinterpret_cast<float2*>(p.state + sa[i]) = make_float2(sn0, sn1);
+      if (p.phys) *reinterpret_cast<float2*>(p.phys + a[i]) = make_float2(ph0, ph1);
+    }
+  }
+}
+
+// head epilogue of one epilogue group: both slots leave TMEM, the accumulator is handed back, then the scatter runs
+template <typename Release>
+__device__ __forceinline__ void epi_group_head(const GemmParams& p, const EpiCtx& e, uint32_t tacc, int n_lo, int n_hi,
+                                               Release&& release) {
+  // (the fp32 values of both slots plus a batch of scatter operands do not fit in registers: slot A is scattered while
+  // slot B still sits in TMEM; the head GEMM's main loop is K = 2112 long, the hand-over is late by one slot's scatter)
+  const int row = e.row0 + e.lane;
+  const bool row_ok = row < p.M;
+  const int b = row / p.tokens;
+  const int tok = row - b * p.tokens;
+  const int gy = tok / p.gw, gx = tok - gy * p.gw;
+  const int pp = p.p1 * p.p2;
+  const bool pairs = (p.p2 & 1) == 0;     // px runs fastest: columns (n, n+1) are horizontally adjacent pixels
+#pragma unroll 1
+  for (int hf = 0; hf < 2; ++hf) {
+    const int n0 = hf ? n_hi : n_lo;
+    float v[kSlot];
+    tmem_load_cols<kSlot>(tacc + hf * kSlot, v);
+    if (hf) release();
+    if (!row_ok) continue;
+    if (pairs) {
+#pragma unroll
+      for (int c = 0; c < kSlot; c += 8)
+        if (n0 + c < p.N) head_apply_pairs<4>(p, b, gy, gx, n0 + c, v + c);
+    } else {
+#pragma unroll
+      for (int j = 0; j < kSlot; ++j) {
+        const int n = n0 + j;
         if (n < p.N) {
           const int ch = n / pp, r = n - ch * pp;
           const int py = r / p.p2, px = r - py * p.p2;
@@ -1140,6 +1253,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         epi_group_qkv<F16>(p, e, tacc, n_lo, n_hi, release);
       } else if constexpr (EPI == EPI_STORE_ACT) {
         epi_group_store16<F16>(p, e, tacc, n_lo, n_hi, release);
+      } else if constexpr (EPI == EPI_HEAD) {
+        epi_group_head(p, e, tacc, n_lo, n_hi, release);
+      } else if constexpr (EPI == EPI_EMBED && NSUB == 2) {
+        float va[kSlot], vb[kSlot];
+        tmem_load_cols2<kSlot>(tacc, va, tacc + kSlot, vb);
+        release();
+        epi_slot_store<EPI, F16, true>(p, e, 0u, n_lo, va);
+        epi_slot_store<EPI, F16, true>(p, e, 0u, n_hi, vb);
       } else if constexpr (EPI == EPI_LN_RES) {
         epi_group_lnres<NSUB, CG, F16>(p, e, stat_smem, tacc, tn * NSUB + grp, tiles_n * NSUB, release);
       } else if constexpr (EPI == EPI_SMEM_ONLY) {

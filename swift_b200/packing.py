@@ -95,8 +95,8 @@ def pack(sd: Dict[str, torch.Tensor], g: Geometry, device: torch.device, split_e
     if split_embed:
         w = torch.cat([w, w], dim=1)
     keep["w_embed"] = w.to(bf).contiguous()
-    keep["b_embed"] = f32(sd["patch_embed.emb.bias"])
-    keep["pos_embed"] = f32(sd["pos_embed"]).reshape(g.tokens, D).contiguous()
+    # the patch-embed bias is folded into the position table: x = A W^T + (pos + bias) costs one operand in the epilogue
+    keep["pos_embed"] = (f32(sd["pos_embed"]).reshape(g.tokens, D) + f32(sd["patch_embed.emb.bias"])[None, :]).contiguous()
 
     if g.aux_dim and "auxiliary_embed.weight" in sd:
         keep["aux_w"] = f32(sd["auxiliary_embed.weight"])

@@ -77,7 +77,7 @@ def _emulate_packed_forward(keep, g, x, cond_vec_fn, gemm_tile):
     A = x.reshape(B, g.in_channels, gh, p1, gw, p2).permute(0, 2, 4, 1, 3, 5).reshape(B * T, g.in_channels * pp)
     A = torch.nn.functional.pad(A, (0, g.k_embed - A.shape[1]))
     w_embed = keep["w_embed"].float()[:, :g.k_embed]
-    tok = A @ w_embed.t() + keep["b_embed"] + keep["pos_embed"].repeat(B, 1)
+    tok = A @ w_embed.t() + keep["pos_embed"].repeat(B, 1)           # the bias is folded into the position table
     gain, bias = cond_vec_fn()
     for l in range(L):
         qkv = (tok @ keep["w_qkv"][l].float().t()).reshape(B * T, 3, H, HD)
