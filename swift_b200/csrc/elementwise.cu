@@ -121,8 +121,11 @@ int launch_patch_gather(const float* src0, int C0, float scale0, const float* sr
 // One warp per token row; the row lives in registers (two-pass mean/variance in fp32); every global load is issued
 // before the first use; accesses are 16 bytes per lane, lane-strided (512 contiguous bytes per warp request).
 // BR16: the branch is stored in the 16-bit operand format (fp16 mode) instead of fp32.
+#ifndef SWB_LN_MIN_BLOCKS
+#define SWB_LN_MIN_BLOCKS 4
+#endif
 template <int NV8, bool F16, bool BR16>
-__global__ void __launch_bounds__(128) ln_mod_residual_kernel(const void* __restrict__ branch_, uint16_t* __restrict__ xhl,
+__global__ void __launch_bounds__(128, SWB_LN_MIN_BLOCKS) ln_mod_residual_kernel(const void* __restrict__ branch_, uint16_t* __restrict__ xhl,
                                                               const float* __restrict__ gain,
                                                               const float* __restrict__ bias, int M, int D,
                                                               int tokens, float eps) {
