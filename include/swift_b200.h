@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SWB200_ABI_VERSION 10
+#define SWB200_ABI_VERSION 11
 #if defined(__GNUC__)
 #define SWB200_API __attribute__((visibility("default")))
 #else
@@ -201,6 +201,22 @@ SWB200_API int swb200_rollout_forcings(float* cond, int total_channels, int stat
                             const int32_t* step, int B, int hw, void* stream);
 /* *step += 1 (device-side, so a captured graph of one step can be replayed for the whole rollout) */
 SWB200_API int swb200_rollout_advance(int32_t* step, void* stream);
+
+/* ---- forward-mode tangent of the denoiser (sCM training loss, training/loss.py:216-225) ------------------- */
+
+/* (F, dF) = jvp(SwinV2.forward, (x, t), (dx, dt)) with x = cat([x0*scale0, x1]) and dx = cat([dx0*scale0, 0]): what
+ * `torch.func.jvp(lambda x, t: net(x, t, condition, auxiliary, jvp=True), (x_t/sigma_d, t), (v_x, v_t))` evaluates.  Every
+ * Linear is the tcgen05 GEMM of the forecast path run over the row-stacked operand [x ; dx]; the derivative rules of
+ * LayerNorm-modulation, q/k normalisation, windowed softmax attention and SwiGLU run in swift_b200/csrc/tangent.cu.
+ * One sample at a time; workspace: swb200_jvp_workspace_bytes(m) bytes, 1024-byte aligned.
+ * gain / bias / dgain / dbias: fp32 [2*depth, B, dim] from swb200_conditioning_jvp (t [B], dt [B] tangent of t). */
+SWB200_API size_t swb200_jvp_workspace_bytes(const swb200_model* m);
+SWB200_API size_t swb200_conditioning_jvp_scratch_bytes(const swb200_model* m, int B);
+SWB200_API int swb200_conditioning_jvp(const swb200_model* m, const float* t, const float* dt, const float* aux, int B, float* gain,
+                            float* bias, float* dgain, float* dbias, void* scratch, size_t scratch_bytes, void* stream);
+SWB200_API int swb200_forward_jvp(const swb200_model* m, const float* x0, int c0, float scale0, const float* x1, int c1,
+                       const float* dx0, int B, const float* gain, const float* bias, const float* dgain, const float* dbias,
+                       float* y, float* dy, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- ensemble verification statistics on resident trajectories (eval/metrics.py:39-134) ------------------ */
 

@@ -11,7 +11,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SWB_LIB", os.path.join(HERE, "libswift_b200.so"))   # SWB_LIB: A/B builds (tools only)
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 # Every symbol ``include/swift_b200.h`` declares; tests check the library exports exactly these.
 EXPORTS = (
@@ -20,7 +20,8 @@ EXPORTS = (
     "swb200_gemm_qkv", "swb200_gemm_swiglu", "swb200_gemm_embed", "swb200_gemm_head", "swb200_patch_gather",
     "swb200_ln_mod_residual", "swb200_window_attention", "swb200_rollout_noise", "swb200_rollout_forcings",
     "swb200_rollout_advance", "swb200_trace_enable", "swb200_trace_report", "swb200_ln_workspace_bytes",
-    "swb200_gemm_ln_residual", "swb200_ensemble_stats",
+    "swb200_gemm_ln_residual", "swb200_ensemble_stats", "swb200_jvp_workspace_bytes",
+    "swb200_conditioning_jvp_scratch_bytes", "swb200_conditioning_jvp", "swb200_forward_jvp",
 )
 
 _i32, _f32, _vp, _sz = C.c_int32, C.c_float, C.c_void_p, C.c_size_t
@@ -80,6 +81,11 @@ def _declare(lib):
         "swb200_gemm_ln_residual": (C.c_int, [C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int,
                                               C.c_int, _vp, C.c_int, _vp]),
         "swb200_ensemble_stats": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp]),
+        "swb200_jvp_workspace_bytes": (_sz, [MP]),
+        "swb200_conditioning_jvp_scratch_bytes": (_sz, [MP, C.c_int]),
+        "swb200_conditioning_jvp": (C.c_int, [MP, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+        "swb200_forward_jvp": (C.c_int, [MP, _vp, C.c_int, _f32, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp,
+                                         _vp, _sz, _vp]),
         "swb200_trace_enable": (C.c_int, [C.c_int]),
         "swb200_trace_report": (C.c_int, [C.c_char_p, _sz]),
     }

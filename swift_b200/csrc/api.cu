@@ -7,6 +7,7 @@
 
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <string>
 #include <utility>
 #include <vector>
@@ -471,6 +472,184 @@ SWB200_API int swb200_window_attention(const void* qkv, void* out, int B, int gr
   return launch_window_attention(qkv, out, B, grid_h, grid_w, heads, shift_h, shift_w, act_fp16, impl,
                                  static_cast<cudaStream_t>(stream));
 }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ forward-mode tangent
+
+namespace {
+struct JvpWs {
+  size_t a2, xhl2, raw, qkvp, dqkvp, S, dS, attn2, branch2, h2, poszero, total;
+};
+JvpWs carve_jvp(const swb200_model* m) {
+  const Geom g = geom(m);
+  const size_t M = g.tokens;                                 // one sample at a time
+  JvpWs w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 1024);
+    return o;
+  };
+  const size_t nraw = static_cast<size_t>(std::max(3 * m->dim, 2 * m->dff));
+  const size_t items = static_cast<size_t>(g.gh / 16) * (g.gw / 16) * m->heads;
+  w.a2 = take(2 * M * g.k_embed_total * 2);
+  w.xhl2 = take(2 * M * m->dim * 2 * 2);
+  w.raw = take(2 * M * nraw * 4);
+  w.qkvp = take(static_cast<size_t>(3) * m->heads * M * kHeadDimPad * 2);
+  w.dqkvp = take(static_cast<size_t>(3) * m->heads * M * kHeadDimPad * 2);
+  w.S = take(items * 65536 * 4);
+  w.dS = take(items * 65536 * 4);
+  w.attn2 = take(2 * M * m->dim * 2);
+  w.branch2 = take(2 * M * m->dim * 4);
+  w.h2 = take(2 * M * static_cast<size_t>(m->dff) * 2);
+  w.poszero = take(M * m->dim * 4);
+  w.total = off;
+  return w;
+}
+}  // namespace
+
+extern "C" {
+
+SWB200_API size_t swb200_jvp_workspace_bytes(const swb200_model* m) {
+  if (validate(m) != SWB_OK) return 0;
+  return carve_jvp(m).total;
+}
+
+SWB200_API size_t swb200_conditioning_jvp_scratch_bytes(const swb200_model* m, int B) {
+  return 2 * swb200_conditioning_scratch_bytes(m, B);
+}
+
+SWB200_API int swb200_conditioning_jvp(const swb200_model* m, const float* t, const float* dt, const float* aux, int B, float* gain,
+                            float* bias, float* dgain, float* dbias, void* scratch, size_t scratch_bytes, void* stream) {
+  int rc = validate(m);
+  if (rc) return rc;
+  SWB_REQUIRE(B > 0 && t && dt && gain && bias && dgain && dbias && scratch, "conditioning_jvp: NULL argument or B=%d", B);
+  SWB_REQUIRE(scratch_bytes >= swb200_conditioning_jvp_scratch_bytes(m, B), "conditioning_jvp: scratch too small");
+  CondWeights w;
+  w.aux_w = m->aux_w; w.aux_b = m->aux_b; w.aux_dim = m->aux_dim;
+  w.l1_w = m->l1_w; w.l1_b = m->l1_b; w.l2_w = m->l2_w; w.l2_b = m->l2_b;
+  w.mod_w = m->mod_w; w.mod_b = m->mod_b; w.ln_gamma = m->ln_gamma; w.ln_beta = m->ln_beta;
+  const float* aux_eff = (m->aux_dim > 0 && m->aux_w != nullptr) ? aux : nullptr;
+  return launch_conditioning_dual(w, t, dt, aux_eff, B, m->dim, 2 * m->depth, m->timestep_weight, static_cast<float*>(scratch),
+                                  gain, bias, dgain, dbias, static_cast<cudaStream_t>(stream));
+}
+
+SWB200_API int swb200_forward_jvp(const swb200_model* m, const float* x0, int c0, float scale0, const float* x1, int c1,
+                       const float* dx0, int B, const float* gain, const float* bias, const float* dgain, const float* dbias,
+                       float* y, float* dy, void* workspace, size_t workspace_bytes, void* stream_) {
+  int rc = validate(m);
+  if (rc) return rc;
+  SWB_REQUIRE(B > 0 && x0 && dx0 && gain && bias && dgain && dbias && y && dy && workspace, "forward_jvp: NULL argument or B=%d", B);
+  SWB_REQUIRE(c0 + c1 == m->in_channels && (c1 == 0 || x1 != nullptr), "forward_jvp: c0+c1=%d != in_channels=%d", c0 + c1,
+              m->in_channels);
+  SWB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "forward_jvp: workspace must be 1024-byte aligned");
+  const JvpWs w = carve_jvp(m);
+  SWB_REQUIRE(workspace_bytes >= w.total, "forward_jvp: workspace of %zu bytes < %zu needed", workspace_bytes, w.total);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const Geom g = geom(m);
+  const int D = m->dim, H = m->heads, Dff = m->dff, M = g.tokens;
+  const int F16 = m->act_fp16 ? 1 : 0;
+  const int tile = m->gemm_tile;
+  const size_t img_in0 = static_cast<size_t>(c0) * m->img_h * m->img_w;
+  const size_t img_in1 = static_cast<size_t>(c1) * m->img_h * m->img_w;
+  const size_t img_out = static_cast<size_t>(m->out_channels) * m->img_h * m->img_w;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  uint16_t* a2 = reinterpret_cast<uint16_t*>(ws + w.a2);
+  uint16_t* xhl2 = reinterpret_cast<uint16_t*>(ws + w.xhl2);
+  float* raw = reinterpret_cast<float*>(ws + w.raw);
+  void* qkvp = ws + w.qkvp;
+  void* dqkvp = ws + w.dqkvp;
+  float* S = reinterpret_cast<float*>(ws + w.S);
+  float* dS = reinterpret_cast<float*>(ws + w.dS);
+  uint16_t* attn2 = reinterpret_cast<uint16_t*>(ws + w.attn2);
+  float* branch2 = reinterpret_cast<float*>(ws + w.branch2);
+  uint16_t* h2 = reinterpret_cast<uint16_t*>(ws + w.h2);
+  float* poszero = reinterpret_cast<float*>(ws + w.poszero);
+  SWB_CHECK_CUDA(cudaMemsetAsync(poszero, 0, static_cast<size_t>(M) * D * 4, stream));
+  const int KE = g.k_embed_total;
+
+  for (int b = 0; b < B; ++b) {
+    // 1. patch operands of the primal input cat([x0*scale0, x1]) and of its tangent cat([dx0*scale0, 0])
+    rc = launch_patch_gather(x0 + b * img_in0, c0, scale0, x1 ? x1 + b * img_in1 : nullptr, c1, a2, KE, m->k_embed,
+                             m->split_embed, F16, 1, m->img_h, m->img_w, m->patch_h, m->patch_w, stream);
+    if (rc) return rc;
+    rc = launch_patch_gather(dx0 + b * img_in0, c0, scale0, nullptr, 0, a2 + static_cast<size_t>(M) * KE, KE, m->k_embed,
+                             m->split_embed, F16, 1, m->img_h, m->img_w, m->patch_h, m->patch_w, stream);
+    if (rc) return rc;
+    // 2. patch embed: the primal rows get bias + pos_embed, the tangent rows nothing
+    for (int half = 0; half < 2; ++half) {
+      GemmParams p = base_params(M, D, KE);
+      p.out0 = xhl2 + static_cast<size_t>(half) * M * 2 * D;
+      p.ldo = 2 * D;
+      p.bias = half ? nullptr : m->b_embed;
+      p.pos = half ? poszero : m->pos_embed;
+      p.pos_rows = g.tokens;
+      rc = launch_gemm(EPI_EMBED, tile, F16, a2 + static_cast<size_t>(half) * M * KE, KE, m->w_embed, KE, p, stream);
+      if (rc) return rc;
+    }
+    // 3. transformer blocks on the row-stacked operand [x ; dx]
+    for (int l = 0; l < m->depth; ++l) {
+      const bool shifted = (m->shift_h || m->shift_w) && (l & 1);
+      const size_t ca = (static_cast<size_t>(2 * l) * B + b) * D, cf = (static_cast<size_t>(2 * l + 1) * B + b) * D;
+      {
+        GemmParams p = base_params(2 * M, 3 * D, D);
+        p.out0 = raw;
+        p.ldo = 3 * D;
+        const auto* wq = static_cast<const __nv_bfloat16*>(m->w_qkv) + static_cast<size_t>(l) * 3 * D * D;
+        rc = launch_gemm(EPI_STORE_F32, tile, F16, xhl2, 2 * D, wq, D, p, stream);
+        if (rc) return rc;
+      }
+      rc = launch_qkv_dual_pack(raw, m->qscale + static_cast<size_t>(l) * H, qkvp, dqkvp, M, D, H, kHeadDim, kHeadDimPad, F16, stream);
+      if (rc) return rc;
+      rc = launch_attention_dual(qkvp, dqkvp, S, dS, attn2, 1, g.gh, g.gw, H, kHeadDim, kHeadDimPad, shifted ? m->shift_h : 0,
+                                 shifted ? m->shift_w : 0, F16, stream);
+      if (rc) return rc;
+      {
+        GemmParams p = base_params(2 * M, D, D);
+        p.out0 = branch2;
+        p.ldo = D;
+        const auto* wo = static_cast<const __nv_bfloat16*>(m->w_o) + static_cast<size_t>(l) * D * D;
+        rc = launch_gemm(EPI_STORE_F32, tile, F16, attn2, D, wo, D, p, stream);
+        if (rc) return rc;
+      }
+      rc = launch_ln_dual(branch2, xhl2, gain + ca, bias + ca, dgain + ca, dbias + ca, M, D, M, 1e-6f, F16, stream);
+      if (rc) return rc;
+      {
+        GemmParams p = base_params(2 * M, 2 * Dff, D);
+        p.out0 = raw;
+        p.ldo = 2 * Dff;
+        const auto* w1 = static_cast<const __nv_bfloat16*>(m->w_1) + static_cast<size_t>(l) * 2 * Dff * D;
+        rc = launch_gemm(EPI_STORE_F32, tile, F16, xhl2, 2 * D, w1, D, p, stream);
+        if (rc) return rc;
+      }
+      rc = launch_swiglu_dual(raw, h2, M, Dff, tile == 3 ? 2 * kUmmaN : kUmmaN, F16, stream);
+      if (rc) return rc;
+      {
+        GemmParams p = base_params(2 * M, D, Dff);
+        p.out0 = branch2;
+        p.ldo = D;
+        const auto* w2 = static_cast<const __nv_bfloat16*>(m->w_2) + static_cast<size_t>(l) * D * Dff;
+        rc = launch_gemm(EPI_STORE_F32, tile, F16, h2, Dff, w2, Dff, p, stream);
+        if (rc) return rc;
+      }
+      rc = launch_ln_dual(branch2, xhl2, gain + cf, bias + cf, dgain + cf, dbias + cf, M, D, M, 1e-6f, F16, stream);
+      if (rc) return rc;
+    }
+    // 4. output head on the primal and on the tangent rows (plain F, no sampler update)
+    swb200_update u = {};
+    u.beta = 1.0f;
+    rc = swb200_gemm_head(tile, m, xhl2, 2 * D, g.k_head_total, 1, &u, y + b * img_out, stream_);
+    if (rc) return rc;
+    rc = swb200_gemm_head(tile, m, xhl2 + static_cast<size_t>(M) * 2 * D, 2 * D, g.k_head_total, 1, &u, dy + b * img_out, stream_);
+    if (rc) return rc;
+  }
+  return SWB_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
 
 // ------------------------------------------------------------------------------------------------ tracing
 

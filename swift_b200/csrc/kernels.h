@@ -46,6 +46,18 @@ int launch_rollout_forcings(float* cond, int total_ch, int state_ch, const float
                             int B, int hw, cudaStream_t stream);
 int launch_rollout_advance(int* step, cudaStream_t stream);
 
+// forward-mode tangent companions (tangent.cu); "2" buffers hold primal rows 0..M-1 followed by tangent rows M..2M-1
+int launch_ln_dual(const float* branch2, void* xhl2, const float* gain, const float* bias, const float* dgain,
+                   const float* dbias, int M, int D, int tokens, float eps, int act_f16, cudaStream_t stream);
+int launch_qkv_dual_pack(const float* raw2, const float* qscale, void* qkv, void* dqkv, int M, int D, int heads, int hd,
+                         int pad, int act_f16, cudaStream_t stream);
+int launch_attention_dual(const void* qkv, const void* dqkv, float* S, float* dS, void* attn2, int B, int gh, int gw,
+                          int heads, int hd, int pad, int shift_h, int shift_w, int act_f16, cudaStream_t stream);
+int launch_swiglu_dual(const float* raw2, void* h2, int M, int Dff, int tile, int act_f16, cudaStream_t stream);
+int launch_conditioning_dual(const CondWeights& w, const float* t, const float* dt, const float* aux, int B, int D, int L,
+                             float timestep_weight, float* scratch, float* gain, float* bias, float* dgain, float* dbias,
+                             cudaStream_t stream);
+
 // ensemble verification statistics (ensemble.cu): out[(*step) * out_stride + (ic * V + v) * 4 + k]
 int launch_ensemble_stats(const float* phys, const float* truth, const float* w_lat, int n_ic, int members, int V, int H,
                           int W, const int* step, int out_stride, double* out, cudaStream_t stream);

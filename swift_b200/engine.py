@@ -141,6 +141,37 @@ class Engine:
         return out
 
 
+    # ------------------------------------------------------------------ forward-mode tangent (sCM training loss)
+    def forward_jvp(self, x: torch.Tensor, t: torch.Tensor, aux: Optional[torch.Tensor], dx: torch.Tensor,
+                    dt: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(F, dF) = jvp(SwinV2.forward, (x, t), (dx, dt)): x, dx [B, in_channels, H, W]; t, dt [B]."""
+        g = self.geom
+        for nm, v in (("x", x), ("dx", dx), ("t", t), ("dt", dt)):
+            self._check_f32(v, nm)
+        B = x.shape[0]
+        if tuple(x.shape[1:]) != (g.in_channels, *g.img) or dx.shape != x.shape or t.shape != (B,) or dt.shape != (B,):
+            raise RuntimeError(f"forward_jvp: x/dx must be [B, {g.in_channels}, {g.img[0]}, {g.img[1]}] and t/dt [B]")
+        if aux is not None:
+            self._check_f32(aux, "auxiliary")
+        vecs = [torch.empty(2 * g.depth, B, g.dim, device=self.device, dtype=torch.float32) for _ in range(4)]
+        need = self.lib.swb200_conditioning_jvp_scratch_bytes(C.byref(self.model), B)
+        scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.swb200_conditioning_jvp(C.byref(self.model), t.data_ptr(), dt.data_ptr(), _lib.ptr(aux), B,
+                                                    *[v.data_ptr() for v in vecs], scratch.data_ptr(), need,
+                                                    self._stream()), "conditioning_jvp")
+        need = self.lib.swb200_jvp_workspace_bytes(C.byref(self.model))
+        if getattr(self, "_jvp_ws", None) is None or self._jvp_ws[2] < need:
+            buf, base = _aligned_buffer(need, self.device)
+            self._jvp_ws = (buf, base, need)
+        y = torch.empty(B, *self.out_shape, device=self.device, dtype=torch.float32)
+        dy = torch.empty_like(y)
+        _lib.check(self.lib.swb200_forward_jvp(C.byref(self.model), x.data_ptr(), g.in_channels, 1.0, None, 0,
+                                               dx.data_ptr(), B, *[v.data_ptr() for v in vecs], y.data_ptr(),
+                                               dy.data_ptr(), self._jvp_ws[1], self._jvp_ws[2], self._stream()),
+                   "forward_jvp")
+        return y, dy
+
+
 class RolloutGlue:
     """Buffers of the fused rollout epilogue: ``state`` [B, C_state, H, W] (standardised condition buffer, first
     out_channels channels updated in place), per-channel normalisers [C] and the optional physical output."""

@@ -85,6 +85,62 @@ class _OutputHead(nn.Module):               # models/swinv2.py:233-244 (the Rear
         self.head = nn.Sequential(nn.Linear(dim, out_features, bias=False))
 
 
+# ---------------------------------------------------------------------------- forward-mode AD hook
+class _TangentEval(torch.autograd.Function):
+    """dF for given (x, t, aux, dx, dt).  A node of its own so that, when called from ``_DenoiserFn.jvp`` under a
+    ``torch.func`` transform, its ``forward`` receives plain tensors (raw device pointers are needed for the C ABI)."""
+
+    @staticmethod
+    def forward(x, t, aux, dx, dt, module):
+        return module.engine().forward_jvp(x, t, aux, dx, dt)[1]
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        pass
+
+    @staticmethod
+    def jvp(ctx, *tangents):
+        raise NotImplementedError("second-order forward-mode derivatives of swift_b200.SwinV2 are not implemented")
+
+    @staticmethod
+    def backward(ctx, *grads):
+        raise NotImplementedError("swift_b200.SwinV2 has no reverse-mode backward (SURVEY.md section 8f-3)")
+
+
+class _DenoiserFn(torch.autograd.Function):
+    """The CUDA denoiser as an autograd node that supports forward-mode AD: ``torch.func.jvp`` through
+    ``net(x, t, condition, auxiliary, jvp=True)`` (training/loss.py:216-225) lands in ``jvp`` below, which evaluates primal
+    and tangent together with ``swb200_forward_jvp``.  No ``backward``: the tangent is used detached by the sCM loss."""
+
+    @staticmethod
+    def forward(x, t, aux, module):
+        eng = module.engine()
+        cond = eng.conditioning(t, aux)
+        return eng.forward(x, None, cond[0], cond[1])
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        x, t, aux, module = inputs
+        ctx.module = module
+        ctx.save_for_forward(x, t) if aux is None else ctx.save_for_forward(x, t, aux)
+        ctx.has_aux = aux is not None
+
+    @staticmethod
+    def jvp(ctx, dx, dt, daux, _):
+        saved = ctx.saved_tensors
+        x, t = saved[0], saved[1]
+        aux = saved[2] if ctx.has_aux else None
+        dx = torch.zeros_like(x) if dx is None else dx.to(torch.float32).contiguous()
+        dt = torch.zeros_like(t) if dt is None else dt.to(torch.float32).reshape(-1).expand_as(t).contiguous()
+        if daux is not None and bool((daux != 0).any()):
+            raise NotImplementedError("tangents with respect to `auxiliary` are not implemented")
+        return _TangentEval.apply(x, t, aux, dx, dt, ctx.module)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        raise NotImplementedError("swift_b200.SwinV2 has no reverse-mode backward (SURVEY.md section 8f-3)")
+
+
 # ---------------------------------------------------------------------------- the module
 class SwinV2(_Base):
     def __init__(self, img_resolution, in_channels: int, out_channels: int, window_size, shift_size, patch_size,
@@ -155,15 +211,13 @@ class SwinV2(_Base):
     def forward(self, x: torch.Tensor, t: torch.Tensor, auxiliary: Optional[torch.Tensor] = None, jvp: bool = False,
                 return_logvar: bool = False) -> Union[torch.Tensor, tuple]:
         """models/swinv2.py:305-330.  x [B, in_channels, H, W]; t scalar, [1] or [B]; auxiliary [B, aux_dim] or None."""
-        if jvp:
-            raise NotImplementedError("the forward-mode tangent (sCM training) path is not part of the forecast hot "
-                                      "path implemented by swift_b200 (SURVEY.md section 8f)")
-        if self.training and torch.is_grad_enabled():
+        if self.training and torch.is_grad_enabled() and not jvp:
             raise RuntimeError("swift_b200.SwinV2 is inference-only: call .eval() / use torch.no_grad()")
-        eng = self.engine()
         B = x.shape[0]
-        x = x.detach().to(torch.float32).contiguous()
-        t = t.detach().to(device=x.device, dtype=torch.float32)
+        if not jvp:                                                # (a detach would drop the forward-mode tangents)
+            x, t = x.detach(), t.detach()
+        x = x.to(torch.float32).contiguous()
+        t = t.to(device=x.device, dtype=torch.float32)
         if t.dim() == 0 or (t.dim() == 1 and t.shape[0] == 1):     # models/swinv2.py:316-317
             t = t.reshape(-1).repeat(B)
         t = t.contiguous()
@@ -173,6 +227,13 @@ class SwinV2(_Base):
             if aux.shape[0] == 1 and B > 1:                        # broadcast like the reference's `t + aux_embed(.)`
                 aux = aux.expand(B, -1)
             aux = aux.contiguous()
+        if jvp:
+            # forward-mode tangent path (the reference switches its attention to explicit softmax here, models/swinv2.py:
+            # 129-134, so that torch.func.jvp can differentiate it): an autograd node with a jvp rule
+            if return_logvar:
+                raise NotImplementedError("return_logvar together with jvp=True is not implemented")
+            return _DenoiserFn.apply(x, t, aux, self)        # (the engine is built inside the node, below any transform)
+        eng = self.engine()
         want_lv = self.logvar_embed is not None and return_logvar
         cond = eng.conditioning(t, aux, want_cond=want_lv)
         y = eng.forward(x, None, cond[0], cond[1])

@@ -1,0 +1,79 @@
+"""Forward-mode tangent path (first part): (F, dF) = jvp(net, (x, t), (v_x, v_t)) as the sCM
+training loss evaluates it (reference training/loss.py:216-225), against torch.func.jvp of the fp32 oracle."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def _per_field(y, ref):
+    num = (y.double() - ref.double()).flatten(2).norm(dim=-1)
+    return (num / ref.double().flatten(2).norm(dim=-1).clamp_min(1e-30)).max().item()
+
+
+@pytest.mark.parametrize("cfgname", ["SWIFT_TINY", "SWIFT_SMALL"])
+def test_engine_forward_jvp_vs_oracle(cfgname):
+    from oracle import swinv2_oracle as orc
+    from swift_b200 import synthetic as syn
+    from test_gpu_forward import build_net
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = getattr(syn, cfgname)
+    net, sd = build_net(cfg)
+    B = 2
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, cfg["in_channels"], *cfg["img_resolution"], generator=g).cuda()
+    dx = torch.randn(x.shape, generator=g).cuda()
+    dx[:, cfg["out_channels"]:] = 0                       # the condition channels carry no tangent (loss.py:213-215)
+    t = torch.tensor([0.3, 1.2]).cuda()
+    dt = torch.tensor([0.25, -0.4]).cuda()
+    aux = torch.full((B, 1), 0.6).cuda()
+    y, dy = net.model.engine().forward_jvp(x, t, aux, dx, dt)
+    ocfg = orc.make_cfg(**cfg)
+    sd_gpu = {k: v.cuda() for k, v in sd.items()}
+    f = lambda xx, tt: orc.swinv2_forward(sd_gpu, ocfg, xx, tt, aux)
+    ref, dref = torch.func.jvp(f, (x, t), (dx, dt))
+    print(f"{cfgname}: F per-field rel-L2 {_per_field(y, ref):.3e}, dF per-field rel-L2 {_per_field(dy, dref):.3e}")
+    assert _per_field(y, ref) < 5e-3
+    assert _per_field(dy, dref) < 1e-2
+    # each tangent direction separately (x only / t only): catches a missing term that the sum could hide
+    for dxx, dtt in ((dx, torch.zeros_like(dt)), (torch.zeros_like(dx), dt)):
+        _, d1 = net.model.engine().forward_jvp(x, t, aux, dxx, dtt)
+        _, r1 = torch.func.jvp(f, (x, t), (dxx, dtt))
+        assert _per_field(d1, r1) < 1e-2
+
+
+def test_torch_func_jvp_through_the_module_as_the_scm_loss_does():
+    """training/loss.py:216-225: torch.func.jvp(lambda x, t: net(x, t, condition, auxiliary, jvp=True), ...)."""
+    from oracle import swinv2_oracle as orc
+    from swift_b200 import synthetic as syn
+    from test_gpu_forward import build_net
+    cfg = syn.SWIFT_TINY
+    n_img = cfg["out_channels"]
+    net, sd = build_net(cfg, img_channels=n_img)
+    B = 2
+    g = torch.Generator().manual_seed(12)
+    x_t = torch.randn(B, n_img, *cfg["img_resolution"], generator=g).cuda()
+    cond = torch.randn(B, cfg["in_channels"] - n_img, *cfg["img_resolution"], generator=g).cuda()
+    t = torch.tensor([0.7, 1.4]).cuda()
+    cos_t, sin_t = torch.cos(t).view(-1, 1, 1, 1), torch.sin(t).view(-1, 1, 1, 1)
+    v_x = cos_t * sin_t * torch.randn(x_t.shape, generator=g).cuda()
+    v_t = (torch.cos(t) * torch.sin(t))
+
+    def wrapper(x, tt):
+        return net(x, tt, cond, 0.6, jvp=True)
+
+    F, dF = torch.func.jvp(wrapper, (x_t, t), (v_x, v_t))
+    ocfg = orc.make_cfg(**cfg)
+    sd_gpu = {k: v.cuda() for k, v in sd.items()}
+    ref, dref = torch.func.jvp(lambda x, tt: orc.pass_precond(sd_gpu, ocfg, x, tt, cond, 0.6), (x_t, t), (v_x, v_t))
+    assert _per_field(F, ref) < 5e-3
+    assert _per_field(dF, dref) < 1e-2
+    with torch.no_grad():                                   # jvp=True without a transform is just the forward
+        assert torch.equal(net(x_t, t, cond, 0.6, jvp=True), net(x_t, t, cond, 0.6))
