@@ -175,8 +175,11 @@ def test_module_contract():
     assert y.shape == (1, cfg["out_channels"], 32, 64) and float(y.abs().max()) == 0.0
     with pytest.raises(RuntimeError):
         m.cpu()(x.cpu(), torch.tensor(0.5))
-    with pytest.raises(NotImplementedError):
-        m.cuda()(x, torch.tensor(0.5, device="cuda"), jvp=True)
+    with torch.no_grad():                                   # jvp=True alone is the plain forward (explicit-softmax flag)
+        assert torch.equal(m.cuda()(x, torch.tensor(0.5, device="cuda"), torch.tensor([[0.6]], device="cuda"), jvp=True), y)
+    with pytest.raises(NotImplementedError):                # no reverse mode: the backward pass is not part of this library
+        xg = x.clone().requires_grad_(True)
+        m(xg, torch.tensor(0.5, device="cuda"), torch.tensor([[0.6]], device="cuda"), jvp=True).sum().backward()
     with pytest.raises(NotImplementedError):
         SwinV2(**{**cfg, "window_size": [8, 8]})
     m.train()

@@ -77,3 +77,51 @@ def test_torch_func_jvp_through_the_module_as_the_scm_loss_does():
     assert _per_field(dF, dref) < 1e-2
     with torch.no_grad():                                   # jvp=True without a transform is just the forward
         assert torch.equal(net(x_t, t, cond, 0.6, jvp=True), net(x_t, t, cond, 0.6))
+
+
+def test_swift_b_tangent_forward_vs_oracle_and_rate():
+    """Swift-B (config 5's network), batch 1: tangent forward vs torch.func.jvp of the fp32 oracle on the same GPU, and
+    its rate next to the plain forward (reported, not asserted: the dual kernels are plain CUDA-core code)."""
+    import time
+    from oracle import swinv2_oracle as orc
+    from swift_b200 import synthetic as syn
+    from test_gpu_forward import build_net
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = syn.SWIFT_B
+    net, sd = build_net(cfg, img_channels=syn.IMG_CHANNELS)
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(1, cfg["in_channels"], *cfg["img_resolution"], generator=g).cuda()
+    dx = torch.randn(x.shape, generator=g).cuda()
+    dx[:, syn.IMG_CHANNELS:] = 0
+    t = torch.tensor([0.9]).cuda()
+    dt = torch.tensor([0.45]).cuda()
+    aux = torch.full((1, 1), 0.6).cuda()
+    eng = net.model.engine()
+    y, dy = eng.forward_jvp(x, t, aux, dx, dt)
+    torch.cuda.synchronize()
+    ocfg = orc.make_cfg(**cfg)
+    sd_gpu = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        ref, dref = torch.func.jvp(lambda xx, tt: orc.swinv2_forward(sd_gpu, ocfg, xx, tt, aux), (x, t), (dx, dt))
+    e_f, e_df = _per_field(y, ref), _per_field(dy, dref)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        eng.forward_jvp(x, t, aux, dx, dt)
+    torch.cuda.synchronize()
+    ms_jvp = (time.perf_counter() - t0) / 3 * 1e3
+    cond = eng.conditioning(t, aux)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        eng.forward(x, None, cond[0], cond[1])
+    torch.cuda.synchronize()
+    ms_fwd = (time.perf_counter() - t0) / 3 * 1e3
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for _ in range(2):
+            torch.func.jvp(lambda xx, tt: orc.swinv2_forward(sd_gpu, ocfg, xx, tt, aux), (x, t), (dx, dt))
+    torch.cuda.synchronize()
+    ms_ref = (time.perf_counter() - t0) / 2 * 1e3
+    print(f"Swift-B tangent forward: F per-field rel-L2 {e_f:.3e}, dF {e_df:.3e}; {ms_jvp:.1f} ms per sample "
+          f"(plain forward at batch 1: {ms_fwd:.1f} ms; torch.func.jvp of the fp32 PyTorch restatement on the same GPU: "
+          f"{ms_ref:.1f} ms)")
+    assert e_f < 5e-3 and e_df < 1e-2
