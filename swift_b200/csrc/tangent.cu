@@ -11,8 +11,9 @@
 //                          O = P v, dO = dP v + P dv   (explicit-softmax path the reference selects with jvp=True)
 //   swiglu_dual_kernel     silu(gate) * up (:99-100)
 //   cond_* dual kernels    timestep embedding + latent MLP + modulation Linears (:44-60, :67-74, :84) w.r.t. t
-// Straightforward fp32 CUDA-core kernels: this path is about coverage and parity first (it runs once per training step
-// next to a backward pass that is not part of this library yet); the GEMMs, 97 % of its FLOPs, are on the tensor cores.
+// The score / output products of the dual attention run on the tensor cores (mma.sync m16n8k16); the other kernels are
+// straightforward fp32 CUDA-core code: this path is about coverage and parity first (it runs once per training step next
+// to a backward pass that is not part of this library yet).
 #include "common.h"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -154,61 +155,98 @@ __device__ __forceinline__ int window_token_row(const AttnDualGeom& g, int b, in
   return (b * g.gh + y) * g.gw + x;
 }
 
-// S[i, j] = q_i . k_j ;  dS[i, j] = dq_i . k_j + q_i . dk_j      one block per (item, 64 x 64 tile), 16 x 16 threads
+// ---- mma.sync m16n8k16 helpers (16-bit operands, fp32 accumulate)
+__device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
 template <bool F16>
-__global__ void __launch_bounds__(256) attn_scores_dual_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ dqkv,
+__device__ __forceinline__ void mma16816(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  if constexpr (F16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+constexpr int kDPitch = 104;          // 16-bit elements per smem row of a 96-wide operand (208 B: conflict-free ldmatrix)
+constexpr int kPPitch = 264;          // ... of a 256-wide P / dP row (528 B)
+
+// gather `rows` token rows (96 halfs = 12 x 16 B each) of one (part, head) slot into smem with cp.async
+__device__ __forceinline__ void gather_rows_async(const uint16_t* src_slot, uint16_t* dst, const AttnDualGeom& g, int b, int win,
+                                                  int n0, int rows, int tid, int nthreads) {
+  for (int idx = tid; idx < rows * 12; idx += nthreads) {
+    const int r = idx / 12, ch = idx - r * 12;
+    const uint16_t* src = src_slot + static_cast<size_t>(window_token_row(g, b, win, n0 + r)) * g.pad + ch * 8;
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst + r * kDPitch + ch * 8));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+  }
+}
+
+// S[i, j] = q_i . k_j ;  dS[i, j] = dq_i . k_j + q_i . dk_j      one block per (item, 64 x 64 tile); 4 warps x 16 rows,
+// tensor cores (mma.sync), q / dq / k / dk rows gathered by window index arithmetic
+template <bool F16>
+__global__ void __launch_bounds__(128) attn_scores_dual_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ dqkv,
                                                                float* __restrict__ S, float* __restrict__ dS, AttnDualGeom g) {
-  __shared__ float sq[64][33], sdq[64][33], sk[64][33], sdk[64][33];
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  uint16_t* sq = reinterpret_cast<uint16_t*>(smem_dyn);
+  uint16_t* sdq = sq + 64 * kDPitch;
+  uint16_t* sk = sdq + 64 * kDPitch;
+  uint16_t* sdk = sk + 64 * kDPitch;
   const int item = blockIdx.y;
   const int head = item % g.heads;
   const int bw = item / g.heads;
   const int nwin = (g.gh / 16) * (g.gw / 16);
   const int win = bw % nwin, b = bw / nwin;
   const int ti = (blockIdx.x >> 2) * 64, tj = (blockIdx.x & 3) * 64;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const size_t slot_q = static_cast<size_t>(head) * g.M, slot_k = static_cast<size_t>(g.heads + head) * g.M;
-  float acc[4][4] = {}, dacc[4][4] = {};
-  for (int k0 = 0; k0 < g.hd; k0 += 32) {
-    for (int idx = threadIdx.x; idx < 64 * 32; idx += 256) {
-      const int r = idx >> 5, c = idx & 31;
-      const int d = k0 + c;
-      const int rq = window_token_row(g, b, win, ti + r), rk = window_token_row(g, b, win, tj + r);
-      const bool ok = d < g.hd;
-      sq[r][c] = ok ? unpack_act1<F16>(qkv[(slot_q + rq) * g.pad + d]) : 0.f;
-      sdq[r][c] = ok ? unpack_act1<F16>(dqkv[(slot_q + rq) * g.pad + d]) : 0.f;
-      sk[r][c] = ok ? unpack_act1<F16>(qkv[(slot_k + rk) * g.pad + d]) : 0.f;
-      sdk[r][c] = ok ? unpack_act1<F16>(dqkv[(slot_k + rk) * g.pad + d]) : 0.f;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const size_t slot_q = static_cast<size_t>(head) * g.M * g.pad, slot_k = static_cast<size_t>(g.heads + head) * g.M * g.pad;
+  gather_rows_async(qkv + slot_q, sq, g, b, win, ti, 64, tid, 128);
+  gather_rows_async(dqkv + slot_q, sdq, g, b, win, ti, 64, tid, 128);
+  gather_rows_async(qkv + slot_k, sk, g, b, win, tj, 64, tid, 128);
+  gather_rows_async(dqkv + slot_k, sdk, g, b, win, tj, 64, tid, 128);
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const uint32_t uq = static_cast<uint32_t>(__cvta_generic_to_shared(sq)), udq = static_cast<uint32_t>(__cvta_generic_to_shared(sdq));
+  const uint32_t uk = static_cast<uint32_t>(__cvta_generic_to_shared(sk)), udk = static_cast<uint32_t>(__cvta_generic_to_shared(sdk));
+  float s[8][4] = {}, ds[8][4] = {};
+  const int ar = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, ac = (lane >> 4) * 8;
+#pragma unroll
+  for (int kt = 0; kt < 6; kt += 2) {
+    uint32_t qa[2][4], dqa[2][4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      ldsm4(uq + (ar * kDPitch + (kt + h) * 16 + ac) * 2, qa[h][0], qa[h][1], qa[h][2], qa[h][3]);
+      ldsm4(udq + (ar * kDPitch + (kt + h) * 16 + ac) * 2, dqa[h][0], dqa[h][1], dqa[h][2], dqa[h][3]);
     }
-    __syncthreads();
-#pragma unroll 8
-    for (int c = 0; c < 32; ++c) {
-      float q[4], dq[4], k[4], dk[4];
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        q[a] = sq[ty * 4 + a][c];
-        dq[a] = sdq[ty * 4 + a][c];
-        k[a] = sk[tx * 4 + a][c];
-        dk[a] = sdk[tx * 4 + a][c];
-      }
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          acc[a][e] = fmaf(q[a], k[e], acc[a][e]);
-          dacc[a][e] = fmaf(dq[a], k[e], fmaf(q[a], dk[e], dacc[a][e]));
-        }
+    for (int nt = 0; nt < 8; ++nt) {
+      const int key = nt * 8 + (lane & 7), c = (lane >> 3) * 8;
+      uint32_t b0, b1, b2, b3, d0, d1, d2, d3;
+      ldsm4(uk + (key * kDPitch + kt * 16 + c) * 2, b0, b1, b2, b3);
+      ldsm4(udk + (key * kDPitch + kt * 16 + c) * 2, d0, d1, d2, d3);
+      mma16816<F16>(s[nt], qa[0], b0, b1);
+      mma16816<F16>(s[nt], qa[1], b2, b3);
+      mma16816<F16>(ds[nt], dqa[0], b0, b1);
+      mma16816<F16>(ds[nt], dqa[1], b2, b3);
+      mma16816<F16>(ds[nt], qa[0], d0, d1);
+      mma16816<F16>(ds[nt], qa[1], d2, d3);
     }
-    __syncthreads();
   }
   float* So = S + static_cast<size_t>(item) * 65536;
   float* dSo = dS + static_cast<size_t>(item) * 65536;
+  const int gq = lane >> 2, t4 = lane & 3;
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      So[(ti + ty * 4 + a) * 256 + tj + tx * 4 + e] = acc[a][e];
-      dSo[(ti + ty * 4 + a) * 256 + tj + tx * 4 + e] = dacc[a][e];
-    }
+  for (int nt = 0; nt < 8; ++nt) {
+    const int col = tj + nt * 8 + 2 * t4;
+    const int r0 = ti + warp * 16 + gq;
+    *reinterpret_cast<float2*>(So + r0 * 256 + col) = make_float2(s[nt][0], s[nt][1]);
+    *reinterpret_cast<float2*>(So + (r0 + 8) * 256 + col) = make_float2(s[nt][2], s[nt][3]);
+    *reinterpret_cast<float2*>(dSo + r0 * 256 + col) = make_float2(ds[nt][0], ds[nt][1]);
+    *reinterpret_cast<float2*>(dSo + (r0 + 8) * 256 + col) = make_float2(ds[nt][2], ds[nt][3]);
+  }
 }
 
 // rows of 256: P = softmax(S), dP = P (dS - sum_j P dS), in place     (one warp per row)
@@ -249,72 +287,71 @@ __global__ void __launch_bounds__(256) attn_softmax_dual_kernel(float* __restric
 }
 
 // O = P v ; dO = dP v + P dv   -> attn2 [2M, D] 16-bit at the tokens' own rows, column head*hd + d.
-// one block per (item, 64-row tile); 16 x 16 threads, thread = 4 rows x 6 d-columns (covers 96 >= hd)
+// one block per (item, 64-row tile); 4 warps x 16 rows on the tensor cores; P / dP rounded to the 16-bit operand format
 template <bool F16>
-__global__ void __launch_bounds__(256) attn_out_dual_kernel(const float* __restrict__ P, const float* __restrict__ dP,
+__global__ void __launch_bounds__(128) attn_out_dual_kernel(const float* __restrict__ P, const float* __restrict__ dP,
                                                             const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ dqkv,
                                                             uint16_t* __restrict__ attn2, AttnDualGeom g) {
-  __shared__ float sp[64][33], sdp[64][33], sv[32][97], sdv[32][97];
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  uint16_t* sp = reinterpret_cast<uint16_t*>(smem_dyn);
+  uint16_t* sdp = sp + 64 * kPPitch;
+  uint16_t* sv = sdp + 64 * kPPitch;
+  uint16_t* sdv = sv + 256 * kDPitch;
   const int item = blockIdx.y;
   const int head = item % g.heads;
   const int bw = item / g.heads;
   const int nwin = (g.gh / 16) * (g.gw / 16);
   const int win = bw % nwin, b = bw / nwin;
   const int ti = blockIdx.x * 64;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const size_t slot_v = static_cast<size_t>(2 * g.heads + head) * g.M;
-  const float* Pi = P + static_cast<size_t>(item) * 65536;
-  const float* dPi = dP + static_cast<size_t>(item) * 65536;
-  float acc[4][6] = {}, dacc[4][6] = {};
-  for (int j0 = 0; j0 < 256; j0 += 32) {
-    for (int idx = threadIdx.x; idx < 64 * 32; idx += 256) {
-      const int r = idx >> 5, c = idx & 31;
-      sp[r][c] = Pi[(ti + r) * 256 + j0 + c];
-      sdp[r][c] = dPi[(ti + r) * 256 + j0 + c];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const size_t slot_v = static_cast<size_t>(2 * g.heads + head) * g.M * g.pad;
+  gather_rows_async(qkv + slot_v, sv, g, b, win, 0, 256, tid, 128);
+  gather_rows_async(dqkv + slot_v, sdv, g, b, win, 0, 256, tid, 128);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  const float* Pi = P + static_cast<size_t>(item) * 65536 + static_cast<size_t>(ti) * 256;
+  const float* dPi = dP + static_cast<size_t>(item) * 65536 + static_cast<size_t>(ti) * 256;
+  for (int idx = tid; idx < 64 * 64; idx += 128) {                    // 64 rows x 64 float4
+    const int r = idx >> 6, c4 = idx & 63;
+    const float4 a = *reinterpret_cast<const float4*>(Pi + r * 256 + c4 * 4);
+    const float4 d = *reinterpret_cast<const float4*>(dPi + r * 256 + c4 * 4);
+    *reinterpret_cast<uint2*>(sp + r * kPPitch + c4 * 4) = make_uint2(pack_act2<F16>(a.x, a.y), pack_act2<F16>(a.z, a.w));
+    *reinterpret_cast<uint2*>(sdp + r * kPPitch + c4 * 4) = make_uint2(pack_act2<F16>(d.x, d.y), pack_act2<F16>(d.z, d.w));
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const uint32_t up = static_cast<uint32_t>(__cvta_generic_to_shared(sp)), udp = static_cast<uint32_t>(__cvta_generic_to_shared(sdp));
+  const uint32_t uv = static_cast<uint32_t>(__cvta_generic_to_shared(sv)), udv = static_cast<uint32_t>(__cvta_generic_to_shared(sdv));
+  float o[12][4] = {}, dout[12][4] = {};
+  const int ar = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, ac = (lane >> 4) * 8;
+#pragma unroll 2
+  for (int kk = 0; kk < 16; ++kk) {                                   // 16 keys per step
+    uint32_t pa[4], dpa[4];
+    ldsm4(up + (ar * kPPitch + kk * 16 + ac) * 2, pa[0], pa[1], pa[2], pa[3]);
+    ldsm4(udp + (ar * kPPitch + kk * 16 + ac) * 2, dpa[0], dpa[1], dpa[2], dpa[3]);
+    const int key = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, c = (lane >> 4) * 8;
+#pragma unroll
+    for (int np = 0; np < 6; ++np) {
+      uint32_t b0, b1, b2, b3, d0, d1, d2, d3;
+      ldsm4_trans(uv + (key * kDPitch + np * 16 + c) * 2, b0, b1, b2, b3);
+      ldsm4_trans(udv + (key * kDPitch + np * 16 + c) * 2, d0, d1, d2, d3);
+      mma16816<F16>(o[2 * np], pa, b0, b1);
+      mma16816<F16>(o[2 * np + 1], pa, b2, b3);
+      mma16816<F16>(dout[2 * np], dpa, b0, b1);
+      mma16816<F16>(dout[2 * np + 1], dpa, b2, b3);
+      mma16816<F16>(dout[2 * np], pa, d0, d1);
+      mma16816<F16>(dout[2 * np + 1], pa, d2, d3);
     }
-    for (int idx = threadIdx.x; idx < 32 * 96; idx += 256) {
-      const int r = idx / 96, d = idx - r * 96;
-      const int rv = window_token_row(g, b, win, j0 + r);
-      const bool ok = d < g.hd;
-      sv[r][d] = ok ? unpack_act1<F16>(qkv[(slot_v + rv) * g.pad + d]) : 0.f;
-      sdv[r][d] = ok ? unpack_act1<F16>(dqkv[(slot_v + rv) * g.pad + d]) : 0.f;
-    }
-    __syncthreads();
-#pragma unroll 4
-    for (int c = 0; c < 32; ++c) {
-      float p[4], dp[4], v[6], dv[6];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        p[a] = sp[ty * 4 + a][c];
-        dp[a] = sdp[ty * 4 + a][c];
-      }
-#pragma unroll
-      for (int e = 0; e < 6; ++e) {
-        v[e] = sv[c][tx * 6 + e];
-        dv[e] = sdv[c][tx * 6 + e];
-      }
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int e = 0; e < 6; ++e) {
-          acc[a][e] = fmaf(p[a], v[e], acc[a][e]);
-          dacc[a][e] = fmaf(dp[a], v[e], fmaf(p[a], dv[e], dacc[a][e]));
-        }
-    }
-    __syncthreads();
   }
   const int D = g.heads * g.hd;
+  const int gq = lane >> 2, t4 = lane & 3;
+  const int row0 = window_token_row(g, b, win, ti + warp * 16 + gq), row1 = window_token_row(g, b, win, ti + warp * 16 + gq + 8);
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int row = window_token_row(g, b, win, ti + ty * 4 + a);
-#pragma unroll
-    for (int e = 0; e < 6; ++e) {
-      const int d = tx * 6 + e;
-      if (d < g.hd) {
-        attn2[static_cast<size_t>(row) * D + head * g.hd + d] = pack_act1<F16>(acc[a][e]);
-        attn2[static_cast<size_t>(g.M + row) * D + head * g.hd + d] = pack_act1<F16>(dacc[a][e]);
-      }
-    }
+  for (int nt = 0; nt < 11; ++nt) {                                   // 11 x 8 = 88 real head-dim columns
+    const int col = head * g.hd + nt * 8 + 2 * t4;
+    *reinterpret_cast<uint32_t*>(attn2 + static_cast<size_t>(row0) * D + col) = pack_act2<F16>(o[nt][0], o[nt][1]);
+    *reinterpret_cast<uint32_t*>(attn2 + static_cast<size_t>(row1) * D + col) = pack_act2<F16>(o[nt][2], o[nt][3]);
+    *reinterpret_cast<uint32_t*>(attn2 + static_cast<size_t>(g.M + row0) * D + col) = pack_act2<F16>(dout[nt][0], dout[nt][1]);
+    *reinterpret_cast<uint32_t*>(attn2 + static_cast<size_t>(g.M + row1) * D + col) = pack_act2<F16>(dout[nt][2], dout[nt][3]);
   }
 }
 
@@ -327,12 +364,23 @@ int launch_attention_dual(const void* qkv, const void* dqkv, float* S, float* dS
   const int items = B * (gh / 16) * (gw / 16) * heads;
   const auto* q = static_cast<const uint16_t*>(qkv);
   const auto* dq = static_cast<const uint16_t*>(dqkv);
-  if (act_f16) attn_scores_dual_kernel<true><<<dim3(16, items), 256, 0, stream>>>(q, dq, S, dS, g);
-  else attn_scores_dual_kernel<false><<<dim3(16, items), 256, 0, stream>>>(q, dq, S, dS, g);
+  constexpr int kScoresSmem = 4 * 64 * kDPitch * 2;                          // 53 KB
+  constexpr int kOutSmem = 2 * 64 * kPPitch * 2 + 2 * 256 * kDPitch * 2;     // 174 KB
+  static bool attr_done = false;
+  if (!attr_done) {
+    SWB_CHECK_CUDA(cudaFuncSetAttribute(attn_scores_dual_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScoresSmem));
+    SWB_CHECK_CUDA(cudaFuncSetAttribute(attn_scores_dual_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScoresSmem));
+    SWB_CHECK_CUDA(cudaFuncSetAttribute(attn_out_dual_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kOutSmem));
+    SWB_CHECK_CUDA(cudaFuncSetAttribute(attn_out_dual_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kOutSmem));
+    attr_done = true;
+  }
+  SWB_REQUIRE(hd == 88 && pad == 96, "attention_dual: the tensor-core kernels are specialised for head_dim 88 padded to 96");
+  if (act_f16) attn_scores_dual_kernel<true><<<dim3(16, items), 128, kScoresSmem, stream>>>(q, dq, S, dS, g);
+  else attn_scores_dual_kernel<false><<<dim3(16, items), 128, kScoresSmem, stream>>>(q, dq, S, dS, g);
   const size_t rows = static_cast<size_t>(items) * 256;
   attn_softmax_dual_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(S, dS, rows);
-  if (act_f16) attn_out_dual_kernel<true><<<dim3(4, items), 256, 0, stream>>>(S, dS, q, dq, static_cast<uint16_t*>(attn2), g);
-  else attn_out_dual_kernel<false><<<dim3(4, items), 256, 0, stream>>>(S, dS, q, dq, static_cast<uint16_t*>(attn2), g);
+  if (act_f16) attn_out_dual_kernel<true><<<dim3(4, items), 128, kOutSmem, stream>>>(S, dS, q, dq, static_cast<uint16_t*>(attn2), g);
+  else attn_out_dual_kernel<false><<<dim3(4, items), 128, kOutSmem, stream>>>(S, dS, q, dq, static_cast<uint16_t*>(attn2), g);
   SWB_CHECK_CUDA(cudaGetLastError());
   return SWB_OK;
 }
