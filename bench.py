@@ -365,6 +365,45 @@ def dominant_kernel_roofline(eng, dev, chunk: int):
             "launch_ms": ms, "flops_per_launch": flops, "peak_source": f"{which} burst bf16"}
 
 
+def run_tangent(args):
+    """Not the headline metric: the forward-mode tangent forward of the sCM training loss (BASELINE.json configs[4], first
+    part), Swift-B, batch 1 per call: (F, dF) = jvp(net, (x, t), (v_x, v_t)) through the C ABI."""
+    import torch
+
+    from swift_b200 import synthetic as syn
+    from swift_b200.precond import PassPrecond
+
+    dev = torch.device("cuda", 0)
+    cfg = syn.SWIFT_B
+    model_cfg = dict(_target_="swift_b200.swinv2.SwinV2", window_size=cfg["window_size"], shift_size=cfg["shift_size"],
+                     patch_size=cfg["patch_size"], depth=cfg["depth"], dim=cfg["dim"], heads=cfg["heads"])
+    net = PassPrecond(model_cfg, img_resolution=cfg["img_resolution"], img_channels=syn.IMG_CHANNELS,
+                      condition_channels=syn.COND_CHANNELS, auxiliary_dim=1, sigma_min=0.0, sigma_max=float("inf"))
+    net.load_state_dict(syn.random_state_dict(cfg, seed=1, prefix="model."), strict=True)
+    eng = net.to(dev).eval().model.engine()
+    x = torch.randn(1, cfg["in_channels"], *cfg["img_resolution"], device=dev)
+    dx = torch.randn_like(x)
+    dx[:, syn.IMG_CHANNELS:] = 0
+    t, dt = torch.tensor([0.9], device=dev), torch.tensor([0.45], device=dev)
+    aux = torch.full((1, 1), 0.6, device=dev)
+    for _ in range(max(3, args.warmup)):
+        eng.forward_jvp(x, t, aux, dx, dt)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        eng.forward_jvp(x, t, aux, dx, dt)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    flops = 2 * 2.72e12 + 0.5 * 5 * 8.86e9 * 12        # stacked GEMMs (2x) + five window products per layer instead of two
+    print(json.dumps({"metric": "tangent-forward samples/sec (Swift-B, batch 1)", "value": 1e3 / ms, "unit": "samples/s",
+                      "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms,
+                      "higher_is_better": True, "dtype": "fp16 tensor-core operands, fp32 accumulate / dual kernels",
+                      "data": "synthetic", "tflops": flops / ms / 1e9,
+                      "config": {"workload": "Swift-B forward-mode tangent forward (jvp of the denoiser w.r.t. x and t)"}}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -375,6 +414,8 @@ def main():
     ap.add_argument("--solver", default="scm", choices=["scm", "2s"],
                     help="scm: Swift 1-step consistency sampler (headline); 2s: TrigFlow diffusion baseline, 20 Heun steps = "
                          "39 denoiser calls per 6 h step (BASELINE.json configs[3])")
+    ap.add_argument("--mode", default="rollout", choices=["rollout", "tangent"],
+                    help="rollout: the headline forecast benchmark; tangent: the forward-mode tangent forward of the sCM loss")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end leg (0 = same as --steps)")
     ap.add_argument("--fuse-ln", type=int, default=-1, help="override SwinV2.fuse_ln (bit 0: wo, bit 1: w2; 0 = separate LN kernel)")
     ap.add_argument("--no-stats", action="store_true", help="do not accumulate the on-device ensemble scores")
@@ -383,6 +424,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "tangent":
+        run_tangent(args)
     else:
         run_ours(args)
 
