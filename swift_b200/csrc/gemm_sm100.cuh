@@ -1255,7 +1255,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         epi_group_store16<F16>(p, e, tacc, n_lo, n_hi, release);
       } else if constexpr (EPI == EPI_HEAD) {
         epi_group_head(p, e, tacc, n_lo, n_hi, release);
-      } else if constexpr (EPI == EPI_EMBED && NSUB == 2) {
+      } else if constexpr ((EPI == EPI_EMBED || EPI == EPI_STORE_F32) && NSUB == 2) {
         float va[kSlot], vb[kSlot];
         tmem_load_cols2<kSlot>(tacc, va, tacc + kSlot, vb);
         release();
