@@ -340,7 +340,7 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
 
 SWB200_API int swb200_gemm(int epi, int tile, int act_fp16, const void* A, int lda, const void* W, int ldw, void* out,
                 int ldo, int M, int N, int K, void* stream) {
-  SWB_REQUIRE(epi == EPI_STORE_F32 || epi == EPI_STORE_ACT || (epi >= EPI_DISCARD && epi <= EPI_DIRECT),
+  SWB_REQUIRE(epi == EPI_STORE_F32 || epi == EPI_STORE_ACT || (epi >= EPI_DISCARD && epi <= EPI_DIRECT) || epi >= 1000,
               "swb200_gemm: epi must be 0 (fp32), 1 (activation format), 6..9 (profiling variants)");
   SWB_REQUIRE(A && W && out, "swb200_gemm: NULL pointer");
   SWB_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && N % (epi == EPI_STORE_F32 ? 4 : 8) == 0,
@@ -348,6 +348,11 @@ SWB200_API int swb200_gemm(int epi, int tile, int act_fp16, const void* A, int l
   GemmParams p = base_params(M, N, K);
   p.out0 = out;
   p.ldo = ldo;
+  if (epi >= 1000) {                          // profiling: EPI_BUSY with (epi - 1000) x 64 FMAs per epilogue thread and tile
+    p.heads = (epi - 1000) % 1000;
+    p.dmodel = (epi - 1000) / 1000;             // 1: independent FMA chains (full issue rate)
+    epi = EPI_BUSY;
+  }
   return launch_gemm(epi, tile, act_fp16, A, lda, W, ldw, p, static_cast<cudaStream_t>(stream));
 }
 

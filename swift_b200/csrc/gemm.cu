@@ -138,6 +138,7 @@ static int launch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, con
     case EPI_SWIGLU: return launch_inst<NSUB, CG, EPI_SWIGLU, F16>(ta, tb, to0, to1, p, stream);
     case EPI_HEAD: return launch_inst<NSUB, CG, EPI_HEAD, F16>(ta, tb, to0, to1, p, stream);
     case EPI_LN_RES: return launch_inst<NSUB, CG, EPI_LN_RES, F16>(ta, tb, to0, to1, p, stream);
+    case EPI_BUSY: return launch_inst<NSUB, CG, EPI_BUSY, F16>(ta, tb, to0, to1, p, stream);
     case EPI_DISCARD: return launch_inst<NSUB, CG, EPI_DISCARD, F16>(ta, tb, to0, to1, p, stream);
     case EPI_DRAIN: return launch_inst<NSUB, CG, EPI_DRAIN, F16>(ta, tb, to0, to1, p, stream);
     case EPI_SMEM_ONLY: return launch_inst<NSUB, CG, EPI_SMEM_ONLY, F16>(ta, tb, to0, to1, p, stream);

@@ -40,6 +40,8 @@ enum GemmEpilogue : int {
   EPI_DRAIN = 7,       // profiling: accumulators read out of TMEM, nothing stored (main loop + drain)
   EPI_SMEM_ONLY = 8,   // profiling: EPI_STORE_ACT without its global stores (drain + pack + smem transposes)
   EPI_DIRECT = 9,      // profiling: EPI_STORE_ACT with per-thread 16-byte global stores (no smem transpose)
+  EPI_BUSY = 11,       // profiling: accumulators discarded, then `heads` x 64 dependent FMAs per epilogue thread and tile
+                       // (no memory traffic at all: does ALU work of the epilogue warps slow the UMMA issuer down?)
 };
 
 struct GemmParams {
@@ -1174,11 +1176,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 for (int k = 0; k < nk; ++k) mma(j, k, k != 0 ? 1u : 0u);
               }
             } else if (full_block) {
+#if SWB_A_TMEM
 #pragma unroll
               for (int k = 0; k < kKSteps; ++k) {
 #pragma unroll
                 for (int j = 0; j < NSUB; ++j) mma(j, k, 1u);
               }
+#else
+              // steady state: the 8 UMMAs of the k-block behind one elect (issue slots are contended, see ptx.cuh)
+              umma_f16_kblock_pair_elect(tmem_d, tmem_d + kSubStride, static_cast<uint32_t>(adesc0), static_cast<uint32_t>(bdesc0),
+                                         kSubDescStep, static_cast<uint32_t>(desc_hi >> 32), idesc);
+#endif
             } else {
               for (int k = 0; k < tail_ksteps; ++k)
                 for (int j = 0; j < NSUB; ++j) mma(j, k, 1u);
@@ -1267,6 +1275,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         epi_group_store16_prof<F16, 1>(p, e, tacc, n_lo, n_hi, release);
       } else if constexpr (EPI == EPI_DIRECT) {
         epi_group_store16_prof<F16, 2>(p, e, tacc, n_lo, n_hi, release);
+      } else if constexpr (EPI == EPI_BUSY) {
+        release();
+        // p.dmodel == 0: one dependent chain (a warp issues every 4th cycle); else 8 independent chains (every cycle)
+        float a[8], bq = 1.0001f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a[c] = static_cast<float>(lane + c);
+        if (p.dmodel == 0) {
+          for (int i = 0; i < p.heads; ++i) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) a[0] = fmaf(a[0], bq, 0.5f);
+          }
+        } else {
+          for (int i = 0; i < p.heads; ++i) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+              for (int c = 0; c < 8; ++c) a[c] = fmaf(a[c], bq, 0.5f);
+          }
+        }
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc += a[c];
+        if (acc == 1.2345e-33f && p.out0) static_cast<float*>(p.out0)[0] = acc;
       } else if constexpr (EPI == EPI_DISCARD) {
         release();
       } else if constexpr (EPI == EPI_DRAIN) {

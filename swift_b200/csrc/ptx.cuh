@@ -265,6 +265,35 @@ __device__ __forceinline__ void umma_f16_ss_elect(uint32_t tmem_d, uint64_t ades
         : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// One full k-block of the 256x352 tile in a single asm statement: 4 k-steps x 2 sub-tiles = 8 accumulating UMMAs behind ONE
+// elect.  Descriptors are passed as their low words (start address | LBO: only the 14-bit address field changes, by +2 per
+// k-step of 32 bytes) plus the constant high word, so the issuing warp spends ~6 instead of ~14 instructions per UMMA: it
+// shares its scheduler with two epilogue warps and every issue slot it needs is contended (tools/issue_contention.py).
+__device__ __forceinline__ void umma_f16_kblock_pair_elect(uint32_t tmem_d0, uint32_t tmem_d1, uint32_t a_lo, uint32_t b_lo,
+                                                           uint32_t b_sub_step, uint32_t desc_hi, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred q, t;\n\t.reg .b32 a1, a2, a3, b1, b2, b3, c0, c1, c2, c3;\n\t"
+      ".reg .b64 da0, da1, da2, da3, db0, db1, db2, db3, dc0, dc1, dc2, dc3;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      "add.u32 a1, %2, 2;\n\tadd.u32 a2, %2, 4;\n\tadd.u32 a3, %2, 6;\n\t"
+      "add.u32 b1, %3, 2;\n\tadd.u32 b2, %3, 4;\n\tadd.u32 b3, %3, 6;\n\t"
+      "add.u32 c0, %3, %4;\n\tadd.u32 c1, b1, %4;\n\tadd.u32 c2, b2, %4;\n\tadd.u32 c3, b3, %4;\n\t"
+      "mov.b64 da0, {%2, %5};\n\tmov.b64 da1, {a1, %5};\n\tmov.b64 da2, {a2, %5};\n\tmov.b64 da3, {a3, %5};\n\t"
+      "mov.b64 db0, {%3, %5};\n\tmov.b64 db1, {b1, %5};\n\tmov.b64 db2, {b2, %5};\n\tmov.b64 db3, {b3, %5};\n\t"
+      "mov.b64 dc0, {c0, %5};\n\tmov.b64 dc1, {c1, %5};\n\tmov.b64 dc2, {c2, %5};\n\tmov.b64 dc3, {c3, %5};\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da0, db0, %6, t;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%1], da0, dc0, %6, t;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da1, db1, %6, t;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%1], da1, dc1, %6, t;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da2, db2, %6, t;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%1], da2, dc2, %6, t;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da3, db3, %6, t;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%1], da3, dc3, %6, t;\n\t}"
+      :
+      : "r"(tmem_d0), "r"(tmem_d1), "r"(a_lo), "r"(b_lo), "r"(b_sub_step), "r"(desc_hi), "r"(idesc)
+      : "memory");
+}
 template <int CG>
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
   if constexpr (CG == 1)
