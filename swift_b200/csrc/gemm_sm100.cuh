@@ -813,13 +813,12 @@ __device__ __forceinline__ void ln_apply8(uint4 br, float2 st, const float* g, c
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float2 v = h2_to_f2(bw[j]);
-    const float o0 = (unpack_act1<F16>(static_cast<uint16_t>(hw[j] & 0xffffu)) + unpack_act1<F16>(static_cast<uint16_t>(lw[j] & 0xffffu))) +
-                     fmaf(fmaf(v.x, st.x, st.y), g[2 * j], b[2 * j]);
-    const float o1 = (unpack_act1<F16>(static_cast<uint16_t>(hw[j] >> 16)) + unpack_act1<F16>(static_cast<uint16_t>(lw[j] >> 16))) +
-                     fmaf(fmaf(v.y, st.x, st.y), g[2 * j + 1], b[2 * j + 1]);
+    const float2 xhi = unpack_act2<F16>(hw[j]), xlo = unpack_act2<F16>(lw[j]);
+    const float o0 = (xhi.x + xlo.x) + fmaf(fmaf(v.x, st.x, st.y), g[2 * j], b[2 * j]);
+    const float o1 = (xhi.y + xlo.y) + fmaf(fmaf(v.y, st.x, st.y), g[2 * j + 1], b[2 * j + 1]);
     hw[j] = pack_act2<F16>(o0, o1);
-    lw[j] = pack_act2<F16>(o0 - unpack_act1<F16>(static_cast<uint16_t>(hw[j] & 0xffffu)),
-                           o1 - unpack_act1<F16>(static_cast<uint16_t>(hw[j] >> 16)));
+    const float2 back = unpack_act2<F16>(hw[j]);
+    lw[j] = pack_act2<F16>(o0 - back.x, o1 - back.y);
   }
   xh = make_uint4(hw[0], hw[1], hw[2], hw[3]);
   xl = make_uint4(lw[0], lw[1], lw[2], lw[3]);
@@ -836,17 +835,33 @@ __device__ __forceinline__ void ln_part_rc(int it, int lane, int& r, int& c) {
 // issue every x load of the part (they do not depend on the statistics: called as early as registers allow)
 template <int NCH>
 __device__ __forceinline__ void ln_part_load(const GemmParams& p, const EpiCtx& e, int n0, uint4* xh, uint4* xl) {
-  const size_t pitch = static_cast<size_t>(p.N) * 2;                    // elements per xhl row
+  const uint32_t pitch = static_cast<uint32_t>(p.N) * 2;               // elements per xhl row
   const uint16_t* x0 = p.xhl + static_cast<size_t>(e.row0) * pitch + n0;
+  const uint32_t lo_off = static_cast<uint32_t>(p.N) >> 3;             // uint4s between hi and lo of an element
+  if constexpr (NCH == 8) {
+    // (row, chunk) = (4 it + lane / 8, lane % 8): one base pointer, a constant stride of 4 rows per iteration
+    const int r0 = e.lane >> 3;
+    const uint4* px = reinterpret_cast<const uint4*>(x0 + r0 * pitch + (e.lane & 7) * 8);
+    const uint32_t step = pitch >> 1;                                  // 4 rows in uint4 units (4 * pitch * 2 B / 16 B)
 #pragma unroll
-  for (int it = 0; it < NCH; ++it) {
-    int r, c;
-    ln_part_rc<NCH>(it, e.lane, r, c);
-    xh[it] = xl[it] = make_uint4(0u, 0u, 0u, 0u);
-    if (r < e.rows_valid) {
-      const uint4* px = reinterpret_cast<const uint4*>(x0 + r * pitch + c * 8);
-      xh[it] = *px;
-      xl[it] = *(px + (p.N >> 3));
+    for (int it = 0; it < 8; ++it) {
+      xh[it] = xl[it] = make_uint4(0u, 0u, 0u, 0u);
+      if (it * 4 + r0 < e.rows_valid) {
+        xh[it] = px[it * step];
+        xl[it] = px[it * step + lo_off];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int it = 0; it < NCH; ++it) {
+      int r, c;
+      ln_part_rc<NCH>(it, e.lane, r, c);
+      xh[it] = xl[it] = make_uint4(0u, 0u, 0u, 0u);
+      if (r < e.rows_valid) {
+        const uint4* px = reinterpret_cast<const uint4*>(x0 + r * pitch + c * 8);
+        xh[it] = *px;
+        xl[it] = *(px + lo_off);
+      }
     }
   }
 }
@@ -868,6 +883,7 @@ __device__ __forceinline__ void ln_part_apply(const GemmParams& p, const EpiCtx&
     b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
   };
   if constexpr (NCH == 8) load_gb(e.lane & 7);                          // the chunk index is the same in every iteration
+  uint4* px8 = reinterpret_cast<uint4*>(x0 + (e.lane >> 3) * pitch + (e.lane & 7) * 8);
 #pragma unroll
   for (int it = 0; it < NCH; ++it) {
     int r, c;
@@ -877,9 +893,11 @@ __device__ __forceinline__ void ln_part_apply(const GemmParams& p, const EpiCtx&
     if constexpr (NCH != 8) load_gb(c);
     ln_apply8<F16>(q, st, g, b, xh[it], xl[it]);
     if (r < e.rows_valid) {
-      uint4* px = reinterpret_cast<uint4*>(x0 + r * pitch + c * 8);
+      uint4* px;
+      if constexpr (NCH == 8) px = px8 + it * (static_cast<uint32_t>(p.N));     // 4 rows further per iteration
+      else px = reinterpret_cast<uint4*>(x0 + r * pitch + c * 8);
       *px = xh[it];
-      *(px + (p.N >> 3)) = xl[it];
+      *(px + (static_cast<uint32_t>(p.N) >> 3)) = xl[it];
     }
   }
   __syncwarp();
@@ -918,20 +936,19 @@ __device__ __forceinline__ void epi_group_lnres(const GemmParams& p, const EpiCt
   int n_lo, n_hi;
   ln_group_cols<NSUB, CG>(sgrp, n_lo, n_hi);
   const bool va = n_lo < p.N, vb = n_hi < p.N;               // N % 88 == 0: a slot is entirely inside or outside
-  // The branch is parked in registers as fp16 pairs (whatever the operand format).  Row statistics of the ROUNDED values
-  // in one pass: sums of (x - K) and (x - K)^2 about a pivot K taken from the row itself (no cancellation problem).
+  // The branch is parked in registers as fp16 pairs (whatever the operand format).  Row statistics in one pass: sums of
+  // (x - K) and (x - K)^2 about a pivot K taken from the row itself (no cancellation problem).
   float v[kSlot];
   uint32_t wa[44], wb[44];
-  float s1 = 0.f, s2 = 0.f, K;
+  float s1 = 0.f, s2 = 0.f;
   tmem_load_cols<kSlot>(tacc, v);
-  wa[0] = pack_act2<true>(v[0], v[1]);
-  K = h2_to_f2(wa[0]).x;
+  const float K = v[0];
 #pragma unroll
   for (int j = 0; j < 44; ++j) {
     wa[j] = pack_act2<true>(v[2 * j], v[2 * j + 1]);
-    const float2 f = h2_to_f2(wa[j]);
-    s1 += (f.x - K) + (f.y - K);
-    s2 = fmaf(f.x - K, f.x - K, fmaf(f.y - K, f.y - K, s2));
+    const float d0 = v[2 * j] - K, d1 = v[2 * j + 1] - K;   // (statistics of the fp32 accumulators: they differ from those of
+    s1 += d0 + d1;                                          //  the fp16-rounded values by O(2^-12 / sqrt(N)) relative)
+    s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
   }
   tmem_load_cols<kSlot>(tacc + kSlot, v);
   release();
@@ -941,9 +958,9 @@ __device__ __forceinline__ void epi_group_lnres(const GemmParams& p, const EpiCt
 #pragma unroll
     for (int j = 0; j < 44; ++j) {
       wb[j] = pack_act2<true>(v[2 * j], v[2 * j + 1]);
-      const float2 f = h2_to_f2(wb[j]);
-      t1 += (f.x - K) + (f.y - K);
-      t2 = fmaf(f.x - K, f.x - K, fmaf(f.y - K, f.y - K, t2));
+      const float d0 = v[2 * j] - K, d1 = v[2 * j + 1] - K;
+      t1 += d0 + d1;
+      t2 = fmaf(d0, d0, fmaf(d1, d1, t2));
     }
     if (vb) { s1 += t1; s2 += t2; }
   }

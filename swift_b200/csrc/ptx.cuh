@@ -438,6 +438,12 @@ __device__ __forceinline__ uint16_t pack_act1(float x) {
     return *reinterpret_cast<uint16_t*>(&v);
   }
 }
+// both halves of a packed 16-bit pair -> float2 (two HADD2.F32 / two integer ops, no extraction of the halves first)
+template <bool F16>
+__device__ __forceinline__ float2 unpack_act2(uint32_t w) {
+  if constexpr (F16) return __half22float2(*reinterpret_cast<const __half2*>(&w));
+  else return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
 template <bool F16>
 __device__ __forceinline__ float unpack_act1(uint16_t u) {
   if constexpr (F16) return __half2float(*reinterpret_cast<__half*>(&u));
