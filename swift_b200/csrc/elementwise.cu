@@ -141,8 +141,9 @@ __global__ void __launch_bounds__(128, SWB_LN_MIN_BLOCKS) ln_mod_residual_kernel
     const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      o[2 * j] = unpack_act1<F16>(static_cast<uint16_t>(w[j] & 0xffffu));
-      o[2 * j + 1] = unpack_act1<F16>(static_cast<uint16_t>(w[j] >> 16));
+      const float2 f = unpack_act2<F16>(w[j]);
+      o[2 * j] = f.x;
+      o[2 * j + 1] = f.y;
     }
   };
   // all global loads of the row (branch, hi, lo) are issued before the first use
@@ -223,8 +224,8 @@ __global__ void __launch_bounds__(128, SWB_LN_MIN_BLOCKS) ln_mod_residual_kernel
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         h[j] = pack_act2<F16>(o[2 * j], o[2 * j + 1]);
-        l[j] = pack_act2<F16>(o[2 * j] - unpack_act1<F16>(static_cast<uint16_t>(h[j] & 0xffffu)),
-                              o[2 * j + 1] - unpack_act1<F16>(static_cast<uint16_t>(h[j] >> 16)));
+        const float2 back = unpack_act2<F16>(h[j]);
+        l[j] = pack_act2<F16>(o[2 * j] - back.x, o[2 * j + 1] - back.y);
       }
       xh[c] = make_uint4(h[0], h[1], h[2], h[3]);
       xl[c] = make_uint4(l[0], l[1], l[2], l[3]);
