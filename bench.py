@@ -346,7 +346,7 @@ def dominant_kernel_roofline(eng, dev, chunk: int):
     for _ in range(3):
         _lib.check(lib.swb200_gemm_swiglu(eng.model.gemm_tile, f16, A.data_ptr(), D, W.data_ptr(), out.data_ptr(), M, D, Dff, stream))
     torch.cuda.synchronize()
-    n = 20
+    n = 40
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(n):
