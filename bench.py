@@ -114,6 +114,45 @@ def cpu_member_steps_per_sec(n_timed: int, warmup: int = 1):
     return 1.0 / per, per, cores, torch.get_num_threads()
 
 
+def gpu_eager_member_steps_per_sec(dev, batch: int = 2, n_timed: int = 3):
+    """SURVEY.md section 8d's "fair GPU baseline": the reference ALGORITHM as plain PyTorch ops (oracle port with the
+    reference's inference attention branch, F.scaled_dot_product_attention) run eagerly on the same B200, in fp32 with
+    TF32 off and under bf16 autocast.  A reported baseline like cpu_baseline, never part of the product path."""
+    import torch
+    from oracle import swinv2_oracle as orc
+    from swift_b200 import synthetic as syn
+
+    cfg = syn.SWIFT_B
+    sd = {k: v.to(dev) for k, v in syn.random_state_dict(cfg, seed=1).items()}
+    ocfg = dict(orc.make_cfg(**cfg), sdpa=True)
+    lat, cond = (v.to(dev) for v in syn.synthetic_fields(cfg, batch, seed=0))
+    net = lambda x, t, c, a: orc.pass_precond(sd, ocfg, x, t, c, a)
+    out = {"batch": batch, "unit": "member-steps/s", "what": "oracle port of swift.models.swinv2 + scm_solver, eager "
+           "PyTorch ops (cuBLAS / SDPA / ATen kernels) on this GPU"}
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for name, ctx in (("fp32", torch.autocast("cuda", enabled=False)),
+                          ("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
+            try:
+                with torch.no_grad(), ctx:
+                    orc.scm_solver(net, lat, cond, 0.6, num_steps=1)
+                    torch.cuda.synchronize(dev)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(n_timed):
+                        orc.scm_solver(net, lat, cond, 0.6, num_steps=1)
+                    e1.record()
+                    torch.cuda.synchronize(dev)
+                out[name] = batch * n_timed / (e0.elapsed_time(e1) / 1e3)
+            except Exception as e:                               # a baseline leg must not cost the headline line
+                out[name] = None
+                out[name + "_error"] = f"{type(e).__name__}: {e}"[:200]
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -295,8 +334,12 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    cpu = None
+    cpu = gpu_eager = None
     if world == 1 and not args.no_cpu:
+        try:
+            gpu_eager = gpu_eager_member_steps_per_sec(dev)
+        except Exception as e:                                   # a baseline leg must not cost the headline line
+            gpu_eager = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
         v, per, cores, threads = cpu_member_steps_per_sec(2, 1)
         cpu = {"value": v, "unit": "member-steps/s", "cores": cores, "kind": "port",
                "sample": f"2 Swift-B sCM member-steps at batch 1 after 1 warm-up ({per:.2f} s each), fp32 oracle port, "
@@ -316,6 +359,7 @@ def run_ours(args):
         "step_frac_of_sustained_bf16": step_tflops / peaks["bf16_tflops_sustained"],
         "peaks": which,
         "cpu_baseline": cpu,
+        "gpu_eager_baseline": gpu_eager,
         "ensemble_statistics": stats_info,
     }
     if world > 1:

@@ -96,7 +96,7 @@ def modulated_norm(x: torch.Tensor, c: torch.Tensor, p: Params, prefix: str, eps
     return y * (1.0 + scale[:, None, :]) + shift[:, None, :]
 
 
-def cosine_window_attention(xw: torch.Tensor, p: Params, prefix: str, heads: int) -> torch.Tensor:
+def cosine_window_attention(xw: torch.Tensor, p: Params, prefix: str, heads: int, sdpa: bool = False) -> torch.Tensor:
     """Scaled-cosine attention inside each window, before ``wo``.
 
     models/swinv2.py:118-135.  ``xw`` is [nWin*B, n, D].  The fused qkv output is
@@ -104,7 +104,9 @@ def cosine_window_attention(xw: torch.Tensor, p: Params, prefix: str, heads: int
     then chunked into q, k, v, so column h*3*hd + {0..hd-1: q, hd..2hd-1: k,
     2hd..3hd-1: v}.  q and k are L2-normalised (F.normalize eps 1e-12); q is
     multiplied by exp(min(scale_h, ln 100)); softmax logits use scale 1.0; no
-    mask and no position bias.
+    mask and no position bias.  ``sdpa`` selects the reference's inference
+    branch (F.scaled_dot_product_attention); the explicit softmax is its
+    ``jvp`` branch and the default here.
     """
     nb, n, d = xw.shape
     hd = d // heads
@@ -114,8 +116,11 @@ def cosine_window_attention(xw: torch.Tensor, p: Params, prefix: str, heads: int
     logit_scale = torch.clamp(p[prefix + ".scale"], max=math.log(1.0 / 0.01)).exp()  # [1,h,1,1]
     q = q / q.norm(dim=-1, keepdim=True).clamp_min(1e-12) * logit_scale
     k = k / k.norm(dim=-1, keepdim=True).clamp_min(1e-12)
-    attn = torch.softmax(q @ k.transpose(-2, -1), dim=-1)
-    o = attn @ v                                                      # [nb, h, n, hd]
+    if sdpa:                                                          # :128-129 (flash and not jvp)
+        o = F.scaled_dot_product_attention(q, k, v, scale=1.0)
+    else:                                                             # :130-133
+        attn = torch.softmax(q @ k.transpose(-2, -1), dim=-1)
+        o = attn @ v                                                  # [nb, h, n, hd]
     return o.permute(0, 2, 1, 3).reshape(nb, n, d)
 
 
@@ -149,7 +154,7 @@ def swin_block(x: torch.Tensor, c: torch.Tensor, p: Params, i: int, cfg: dict) -
         y = torch.roll(y, shifts=(-shift[0], -shift[1]), dims=(1, 2))
     yw = to_windows(y.reshape(b, n, d), grid, win)                    # :196-197
     nwin = yw.shape[0] // b
-    o = cosine_window_attention(yw, p, pa, cfg["heads"])
+    o = cosine_window_attention(yw, p, pa, cfg["heads"], cfg.get("sdpa", False))
     o = F.linear(o, p[pa + ".wo.weight"])                             # :137
     o = modulated_norm(o, c.repeat_interleave(nwin, dim=0), p, pa + ".norm")  # :138, :184
     o = from_windows(o, grid, win).reshape(b, grid[0], grid[1], d)    # :202-203

@@ -206,3 +206,48 @@ def test_swift_b_rollout_drift_report():
                   f"mean {err.mean():.3e}")
     assert worst[0] < 1e-2                       # the stated bar applies to one step
     assert worst[-1] < 5e-2, "rollout drift after 6 steps larger than expected"
+
+
+@pytest.mark.parametrize("layout", ["trajectory", "step", "numpy"])
+def test_rollout_and_save_fills_the_store(tmp_path, layout):
+    """generate.py:79-152 end to end: lead 0 = unstandardised initial state (:96), leads 1..steps = the physical state of
+    every step, written at [ic, member] of each trajectory in the reference's zarr / npy layout -- identical to stepping
+    the device rollout by hand; a trajectory another rank owns stays at the fill value."""
+    from swift_b200 import synthetic as syn
+    from swift_b200.generate import rollout_and_save
+    from swift_b200.rollout import EnsembleRollout, Normalizers
+    from swift_b200.store import ForecastStore
+    cfg = syn.SWIFT_TINY
+    n_var, steps, (H, W) = cfg["out_channels"], 3, cfg["img_resolution"]
+    net, _ = _build(cfg, n_var)
+    n_forc = cfg["in_channels"] - 2 * n_var
+    forc = syn.synthetic_forcings(cfg, steps + 1, seed=2, n_forcings=n_forc)
+    mean = torch.linspace(-1, 1, n_var).reshape(1, -1, 1, 1).cuda()
+    std = torch.linspace(0.5, 2.0, n_var).reshape(1, -1, 1, 1).cuda()
+    norm = Normalizers(mean, std, 0.2 * torch.ones_like(std))
+    traj = [(1, 0), (0, 1), (1, 1)]                               # (member, ic); (0, 0) belongs to "another rank"
+    x0 = torch.randn(len(traj), n_var, H, W, generator=torch.Generator().manual_seed(11))
+    variables = ["t2m", "z_500", "z_850", "msl", "q_700"]
+    path = str(tmp_path / ("fc.npy" if layout == "numpy" else "fc.zarr"))
+    store = ForecastStore.create(path, variables, 2, 2, steps, np.linspace(-80, 80, H), np.arange(W) * 5.625,
+                                 layout=layout)
+    ro = EnsembleRollout(net, norm, torch.zeros_like(forc).cuda(), traj)
+    info = rollout_and_save(ro, store, x0, steps, forc.pin_memory(), writers=2)
+    assert info["trajectories"] == 3 and info["bytes_written"] == 3 * (steps + 1) * n_var * H * W * 4
+    ref = EnsembleRollout(net, norm, forc.cuda(), traj)
+    ref.set_state(x0.cuda())
+    want = np.zeros((2, 2, steps + 1, n_var, H, W), dtype=np.float32)
+    lead0 = (x0.cuda() * std + mean).cpu().numpy()
+    for b, (m, j) in enumerate(traj):
+        want[j, m, 0] = lead0[b]
+    for k in range(steps):
+        phys = ref.step().cpu().numpy()
+        for b, (m, j) in enumerate(traj):
+            want[j, m, k + 1] = phys[b]
+    got = np.asarray(ForecastStore.open(path).read_all())
+    np.testing.assert_array_equal(got, want)
+    assert not got[0, 0].any() and np.abs(got[1, 1, steps]).max() > 0
+    if layout != "numpy":
+        np.testing.assert_array_equal(store.read("z"), want[:, :, :, 1:3])
+    with pytest.raises(ValueError):
+        rollout_and_save(ro, store, x0, steps + 1)

@@ -39,6 +39,10 @@ def test_forward_and_taps(golden, name, cfgname):
     y = orc.swinv2_forward(p, cfg, torch.cat([lat, cond], 1), torch.from_numpy(g["fwd_t"]),
                            torch.from_numpy(g["fwd_aux"]), taps=taps)
     _close(y, g["fwd_y"])
+    # the reference's two attention branches (swinv2.py:128-133: SDPA at inference, explicit softmax under jvp)
+    y_sdpa = orc.swinv2_forward(p, dict(cfg, sdpa=True), torch.cat([lat, cond], 1), torch.from_numpy(g["fwd_t"]),
+                                torch.from_numpy(g["fwd_aux"]))
+    _close(y_sdpa, g["fwd_y"])
     _close(taps["cond"], g["tap_cond"])
     for i in range(c["depth"]):
         _close(taps[f"block{i}"][:, ::TAP_STRIDE], g[f"tap_block{i}"])
