@@ -50,6 +50,53 @@ def trajectory_seed(member: int, ic: int) -> int:
     return member + 1_000_003 * ic
 
 
+class ReferenceNoise:
+    """The reference's latent stream, replayed with random access (validation mode).
+
+    generate.py:79-118 seeds ONE ``torch.Generator(device).manual_seed(m)`` per member and consumes it in loop order:
+    IC batches of ``batch`` samples (DataLoader order, the last one may be ragged), and inside a batch the lead times,
+    each ``sampler(X, generator)`` call drawing ``torch.randn((bs, C, H, W), generator=..., device=...)``
+    (generating/factory.py:46-61).  A trajectory's noise therefore depends on the batch size and on every batch before
+    it.  All trajectories advance together here, so the call that the reference would make for (member, batch b, lead
+    i) is reproduced by positioning a CUDA generator at that call's Philox offset: a ``randn`` of a given shape advances
+    the offset by a fixed amount (measured once per shape), hence offset(b, i) = b * steps * inc(batch) + i * inc(bs_b).
+    Valid for samplers that draw only the latents (1-step sCM, TrigFlow 2S with S_churn = 0)."""
+
+    def __init__(self, trajectories: Sequence[Tuple[int, int]], n_ic: int, batch: int, steps: int,
+                 sample_shape: Tuple[int, ...], device):
+        if batch < 1 or steps < 1:
+            raise ValueError("ReferenceNoise needs batch >= 1 and the number of lead times the reference was run with")
+        self.device, self.steps, self.batch, self.shape = device, int(steps), int(batch), tuple(sample_shape)
+        self.groups = {}                                 # (member, batch index) -> [(row here, row in the batch)]
+        for row, (m, j) in enumerate(trajectories):
+            if not 0 <= j < n_ic:
+                raise ValueError(f"trajectory ({m}, {j}) outside the {n_ic} initial conditions of the run")
+            self.groups.setdefault((m, j // self.batch), []).append((row, j % self.batch))
+        self.sizes = {b: min(self.batch, n_ic - b * self.batch) for _, b in self.groups}
+        self._inc = {}
+        self._gen = torch.Generator(device=device)
+
+    def _increment(self, bs: int) -> int:
+        if bs not in self._inc:
+            self._gen.manual_seed(0)
+            o0 = self._gen.get_offset()
+            torch.randn((bs,) + self.shape, generator=self._gen, device=self.device)
+            self._inc[bs] = self._gen.get_offset() - o0
+        return self._inc[bs]
+
+    def fill(self, latents: torch.Tensor, step: int) -> None:
+        """latents[row] <- what the reference draws for that trajectory at lead ``step``."""
+        if not 0 <= step < self.steps:
+            raise ValueError(f"lead {step} outside the {self.steps}-step stream being replayed")
+        for (m, b), rows in self.groups.items():
+            bs = self.sizes[b]
+            self._gen.manual_seed(m)                                         # generate.py:83
+            self._gen.set_offset(b * self.steps * self._increment(self.batch) + step * self._increment(bs))
+            z = torch.randn((bs,) + self.shape, generator=self._gen, device=self.device)
+            here = torch.tensor([r for r, _ in rows], device=self.device)
+            latents.index_copy_(0, here, z[[k for _, k in rows]])
+
+
 @dataclass
 class Normalizers:
     """Per-channel affine maps of data/era5.py:80-108 as [1, C, 1, 1] device tensors."""
@@ -68,7 +115,8 @@ class EnsembleRollout:
     """Advances a batch of independent trajectories that live on one GPU."""
 
     def __init__(self, net, norm: Normalizers, forcings_std: torch.Tensor, trajectories: Sequence[Tuple[int, int]],
-                 solver: str = "scm", solver_kwargs: Optional[dict] = None, use_graph: bool = True):
+                 solver: str = "scm", solver_kwargs: Optional[dict] = None, use_graph: bool = True,
+                 noise: Optional["ReferenceNoise"] = None):
         self.net = net
         self.norm = norm
         self.forcings = forcings_std.contiguous()   # [steps(+), n_forc, H, W] standardised, on device
@@ -95,6 +143,8 @@ class EnsembleRollout:
         self.phys = torch.empty(B, self.n_var, *self.res, device=self.device)
         self.seeds = torch.tensor([trajectory_seed(m, j) for m, j in self.traj], dtype=torch.int64, device=self.device)
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.noise = noise                      # None: the per-trajectory Philox streams (default); else the reference's
+        self._step_host = 0                     # host mirror of step_dev (the replayed stream is positioned on the host)
         self.lib = _lib.lib()
         self.model = _fused_target(net)
         # the single-kernel-sequence step: 1-step sCM through the fused CUDA entry point
@@ -126,12 +176,16 @@ class EnsembleRollout:
         """x_std: [B, n_var, H, W] standardised initial conditions, one row per trajectory."""
         self.cond[:, : self.n_var].copy_(x_std)
         self.step_dev.fill_(step)
+        self._step_host = int(step)
 
     # ------------------------------------------------------------------ pieces of one step
     def _stream(self) -> int:
         return torch.cuda.current_stream().cuda_stream
 
     def draw_latents(self) -> torch.Tensor:
+        if self.noise is not None:
+            self.noise.fill(self.latents, self._step_host)
+            return self.latents
         n = self.latents[0].numel()
         _lib.check(self.lib.swb200_rollout_noise(self.latents.data_ptr(), self.seeds.data_ptr(),
                                                  self.step_dev.data_ptr(), len(self.traj), n, self._stream()), "noise")
@@ -152,7 +206,8 @@ class EnsembleRollout:
         eng = self.model.engine()
         t = torch.tensor([torch.pi / 2])                     # diffusion.py:435-436 (fp32 pi/2)
         cos_t, sin_t = float(torch.cos(t)), float(torch.sin(t))
-        self.draw_latents()
+        if self.noise is None:                               # replayed reference noise is drawn outside (not capturable)
+            self.draw_latents()
         self._load_forcings()
         gain, bias = self._cond_vecs
         sd = self.sigma_data
@@ -161,7 +216,7 @@ class EnsembleRollout:
             x_in.mul_(sd)                                    # x_t = latents * sigma_d (diffusion.py:452)
         eng.forward(x_in, self.cond, gain, bias, scale0=1.0 / sd, xt=x_in, alpha=cos_t, beta=-sin_t * sd,
                     rollout=self._glue)
-        n_extra = 3
+        n_extra = 3 if self.noise is None else 2              # own kernels besides the forward: (noise,) forcings, advance
         if self._stats is not None:
             self._stats.accumulate(self.phys, self._truth, step_dev=self.step_dev)
             n_extra += 1
@@ -177,6 +232,9 @@ class EnsembleRollout:
                 self._cond_vecs = self.diffusion._conditioning(self.model, float(torch.tensor([torch.pi / 2])),
                                                                self.solver_kwargs["auxiliary"], len(self.traj),
                                                                self.device)
+            if self.noise is not None:
+                self.draw_latents()
+            self._step_host += 1
             if not self.use_graph:
                 self._fused_step()
             else:
@@ -188,7 +246,8 @@ class EnsembleRollout:
                         self._fused_step()
                     self._graph = g          # capture does not execute: the replay below is the first real step
                 self._graph.replay()
-                self.model.engine().launches += (self.model.engine().launches_per_forward(len(self.traj)) + 3 +
+                self.model.engine().launches += (self.model.engine().launches_per_forward(len(self.traj)) +
+                                                 (3 if self.noise is None else 2) +
                                                  (1 if self._stats is not None else 0))
             return self.phys
         # generic path (multi-step sCM, 2S, non-fused nets, externally supplied forcings)
@@ -199,6 +258,7 @@ class EnsembleRollout:
             self.cond[:, self.n_var:].copy_(f.unsqueeze(0).expand(self.cond.shape[0], -1, -1, -1) if f.dim() == 3 else f)
         kw = {k: v for k, v in self.solver_kwargs.items()}
         y = self._solve(latents=self.draw_latents(), condition=self.cond, **kw)
+        self._step_host += 1
         x_std = self.cond[:, : self.n_var]
         x_phys = torch.addcmul(x_std * self.norm.x_std + self.norm.x_mean, y, self.norm.diff_std)
         x_new = (x_phys - self.norm.x_mean) / self.norm.x_std

@@ -251,3 +251,58 @@ def test_rollout_and_save_fills_the_store(tmp_path, layout):
         np.testing.assert_array_equal(store.read("z"), want[:, :, :, 1:3])
     with pytest.raises(ValueError):
         rollout_and_save(ro, store, x0, steps + 1)
+
+
+def test_reference_noise_stream_replay():
+    """'replay the reference's stream exactly when validating'.  generate.py:79-118 consumes one
+    generator per member in (IC batch, lead time) order; ReferenceNoise positions a generator at the same Philox offset
+    for any (member, batch, lead).  Checked against a literal run of the reference's loop nest (ragged last batch
+    included), then end to end: a rollout step with the replayed latents equals reference-style
+    ``sampler_factory("scm")(X, generator)`` + the affine glue for the second batch's first lead."""
+    from swift_b200 import synthetic as syn
+    from swift_b200.rollout import EnsembleRollout, Normalizers, ReferenceNoise
+    from swift_b200.sampler import sampler_factory
+    cfg = syn.SWIFT_TINY
+    n_var, (H, W) = cfg["out_channels"], cfg["img_resolution"]
+    members, n_ic, batch, steps = 2, 5, 2, 3
+    shape = (n_var, H, W)
+    literal = {}
+    for m in range(members):
+        g = torch.Generator(device="cuda").manual_seed(m)
+        for b in range(0, n_ic, batch):
+            bs = min(batch, n_ic - b)
+            for i in range(steps):
+                z = torch.randn((bs, *shape), generator=g, device="cuda")
+                for k in range(bs):
+                    literal[(m, b + k, i)] = z[k].clone()
+    traj = [(1, 4), (0, 0), (1, 1), (0, 3), (1, 0), (0, 2)]          # any subset, any order, partial batches
+    rn = ReferenceNoise(traj, n_ic, batch, steps, shape, torch.device("cuda"))
+    buf = torch.empty(len(traj), *shape, device="cuda")
+    for i in (2, 0, 1):                                              # random access in the lead time too
+        rn.fill(buf, i)
+        for row, (m, j) in enumerate(traj):
+            assert torch.equal(buf[row], literal[(m, j, i)]), (m, j, i)
+    with pytest.raises(ValueError):
+        rn.fill(buf, steps)
+    # ---- end to end on the second IC batch (ICs 2, 3) of member 1: the reference has drawn batch 0's 3 leads before
+    net, _ = _build(cfg, n_var)
+    n_forc = cfg["in_channels"] - 2 * n_var
+    forc = syn.synthetic_forcings(cfg, steps, seed=4, n_forcings=n_forc).cuda()
+    norm = Normalizers.synthetic(n_var, "cuda", diff=0.2)
+    x0 = torch.randn(2, n_var, H, W, generator=torch.Generator().manual_seed(2)).cuda()
+    tr = [(1, 2), (1, 3)]
+    for use_graph in (True, False):
+        ro = EnsembleRollout(net, norm, forc, tr, use_graph=use_graph,
+                             noise=ReferenceNoise(tr, n_ic, batch, steps, shape, torch.device("cuda")))
+        ro.set_state(x0)
+        got = [ro.step().clone() for _ in range(2)]
+        g = torch.Generator(device="cuda").manual_seed(1)
+        for _ in range(steps):                                       # batch 0's calls
+            torch.randn((batch, *shape), generator=g, device="cuda")
+        sampler = sampler_factory("scm", net, num_steps=1, sigma_min=0.02, sigma_max=200.0, auxiliary=0.6)
+        X = x0.clone()
+        for i in range(2):
+            Xc = torch.cat([X, forc[i].unsqueeze(0).expand(2, -1, -1, -1)], 1)
+            Y = sampler(Xc, generator=g)
+            X = X + 0.2 * Y                                           # synthetic normalisers: mean 0, std 1, diff 0.2
+            assert torch.allclose(got[i], X, rtol=1e-5, atol=1e-5), f"lead {i}, graph={use_graph}"
