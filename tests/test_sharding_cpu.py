@@ -54,3 +54,44 @@ def test_two_rank_gloo_barrier_and_max_reduce():
     assert tmax == 15.0                                                   # max over ranks, as bench.py reports
     assert sorted(gathered[0] + gathered[1]) == sorted((m, j) for j in range(8) for m in range(12))
     assert len(gathered[0]) == len(gathered[1]) == 48
+
+
+def _store_worker(rank, world, port, path):
+    """generate.py's multi-rank output protocol: rank 0 creates the store (run_on_rank0, generate.py:272-282), a
+    barrier, then every rank opens it and writes the trajectories of its own shard -- no lock, no collective."""
+    import numpy as np
+    from swift_b200.store import ForecastStore
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    members, n_ic, steps, h, w = 3, 3, 2, 4, 8
+    variables = ["t2m", "z_500", "z_850", "msl"]
+    if rank == 0:
+        ForecastStore.create(path, variables, n_ic, members, steps, np.arange(h), np.arange(w), layout="trajectory")
+    dist.barrier()
+    store = ForecastStore.open(path)
+    for m, j in shard_trajectories(members, n_ic, rank, world):
+        fields = np.full((1, steps + 1, len(variables), h, w), 100.0 * j + 10.0 * m, dtype=np.float32)
+        fields += np.arange(steps + 1, dtype=np.float32).reshape(1, -1, 1, 1, 1)
+        store.write_trajectories(j, m, fields)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_fill_one_store_without_locks(tmp_path):
+    import numpy as np
+    from swift_b200.store import ForecastStore
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    path = str(tmp_path / "fc.zarr")
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_store_worker, args=(r, 2, port, path)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    got = ForecastStore.open(path).read_all()                     # [ic, member, lead, channel, h, w]
+    want = (100.0 * np.arange(3).reshape(3, 1, 1) + 10.0 * np.arange(3).reshape(1, 3, 1) + np.arange(3).reshape(1, 1, 3))
+    np.testing.assert_array_equal(got[..., 0, 0, 0], want.astype(np.float32))
+    assert (got == got[..., :1, :1, :1]).all()                    # every chunk complete, none torn or missing
