@@ -90,8 +90,9 @@ class ReferenceNoise:
             raise ValueError(f"lead {step} outside the {self.steps}-step stream being replayed")
         for (m, b), rows in self.groups.items():
             bs = self.sizes[b]
+            offset = b * self.steps * self._increment(self.batch) + step * self._increment(bs)   # (measuring reseeds)
             self._gen.manual_seed(m)                                         # generate.py:83
-            self._gen.set_offset(b * self.steps * self._increment(self.batch) + step * self._increment(bs))
+            self._gen.set_offset(offset)
             z = torch.randn((bs,) + self.shape, generator=self._gen, device=self.device)
             here = torch.tensor([r for r, _ in rows], device=self.device)
             latents.index_copy_(0, here, z[[k for _, k in rows]])

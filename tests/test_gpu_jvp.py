@@ -127,3 +127,34 @@ def test_swift_b_tangent_forward_vs_oracle_and_rate():
           f"(plain forward at batch 1: {ms_fwd:.1f} ms; torch.func.jvp of the fp32 PyTorch restatement on the same GPU: "
           f"{ms_ref:.1f} ms)")
     assert e_f < 5e-3 and e_df < 1e-2
+
+
+@pytest.mark.parametrize("name,cfgname", [("tiny", "SWIFT_TINY"), ("small", "SWIFT_SMALL")])
+def test_scm_output_cotangent_vs_reference_loss_golden(golden, name, cfgname):
+    """swift_b200.scm_target.scm_output_cotangent (one stacked primal + tangent pass of the CUDA engine) against the REAL
+    reference's SCMLoss (tests/golden/make_scm_loss_golden.py): loss value and dL/dF_x, three (draw, step, warm-up) cases.
+    Tolerance: the 16-bit-operand error of F (5e-3) and dF (1e-2) propagated through the normalised tangent target."""
+    from swift_b200 import synthetic as syn
+    from swift_b200.scm_target import latitude_weights, scm_output_cotangent, variable_weights
+    from test_gpu_forward import build_net
+    from test_oracle_golden import SCM_LOSS_VARIABLES
+    g = golden("scm_loss")
+    cfg = getattr(syn, cfgname)
+    n_img, (H, W) = cfg["out_channels"], cfg["img_resolution"]
+    net, _ = build_net(cfg, img_channels=n_img)
+    x, cond = (v.cuda() for v in syn.synthetic_fields(cfg, 2, seed=5))
+    w_lat, w_var = latitude_weights(H, "cuda"), variable_weights(SCM_LOSS_VARIABLES[:n_img], "cuda")
+    np.testing.assert_array_equal(w_lat.cpu().numpy(), g[name + "_w_lat"])
+    np.testing.assert_array_equal(w_var.cpu().numpy(), g[name + "_w_var"])
+    for case in range(3):
+        k = f"{name}_{case}_"
+        step, warm = (int(v) for v in g[k + "step_warm"])
+        o = scm_output_cotangent(net, x, torch.from_numpy(g[k + "t"]).cuda(), torch.from_numpy(g[k + "z"]).cuda(), step,
+                                 condition=cond, auxiliary=0.6, tangent_warmup_kimg=warm, w_lat=w_lat, w_var=w_var)
+        ref_cot, ref_loss = torch.from_numpy(g[k + "cot"]).cuda(), float(g[k + "loss"])
+        e_f, e_c = _per_field(o["F"], torch.from_numpy(g[k + "F"]).cuda()), _rel(o["cot"], ref_cot)
+        print(f"{k}: F per-field rel-L2 {e_f:.3e}, cotangent rel-L2 {e_c:.3e}, loss {float(o['loss']):.6f} vs {ref_loss:.6f}")
+        assert e_f < 5e-3 and e_c < 2e-2
+        assert abs(float(o["loss"]) - ref_loss) < 1e-2 * ref_loss
+    with pytest.raises(KeyError):
+        variable_weights(["2m_temperature", "not_a_variable_500"])

@@ -215,3 +215,20 @@ def test_precond_mirror_and_config_loader():
     a = process_auxiliary(0.6, 1, 4, "cpu")
     assert a.shape == (4, 1) and torch.allclose(a, torch.full((4, 1), 0.6))
     assert process_auxiliary(None, 1, 4, "cpu").shape == (1, 1) and process_auxiliary(0.6, 0, 4, "cpu") is None
+
+
+def test_reference_noise_bookkeeping():
+    """rollout.ReferenceNoise: which reference call (member, IC batch) each local trajectory belongs to, ragged last
+    batch, argument checks (the Philox-offset replay itself needs a CUDA generator: tests/test_gpu_rollout.py)."""
+    import torch
+    from swift_b200.rollout import ReferenceNoise
+    traj = [(1, 4), (0, 0), (1, 1), (0, 3), (1, 0)]
+    rn = ReferenceNoise(traj, n_ic=5, batch=2, steps=3, sample_shape=(2, 4, 4), device=torch.device("cpu"))
+    assert rn.groups == {(1, 2): [(0, 0)], (0, 0): [(1, 0)], (1, 0): [(2, 1), (4, 0)], (0, 1): [(3, 1)]}
+    assert rn.sizes == {2: 1, 0: 2, 1: 2}                       # the last reference batch holds one IC
+    with pytest.raises(ValueError):
+        ReferenceNoise([(0, 5)], n_ic=5, batch=2, steps=3, sample_shape=(1,), device=torch.device("cpu"))
+    with pytest.raises(ValueError):
+        ReferenceNoise(traj, n_ic=5, batch=0, steps=3, sample_shape=(1,), device=torch.device("cpu"))
+    with pytest.raises(ValueError):
+        rn.fill(torch.empty(5, 2, 4, 4), 3)

@@ -89,3 +89,32 @@ def test_time_grid_and_embedding():
     f = torch.exp(-math.log(10000.0) * torch.arange(4) / 4)
     np.testing.assert_allclose(e[0, :4].numpy(), torch.sin(0.7 * f).numpy(), rtol=1e-6)
     np.testing.assert_allclose(e[0, 4:].numpy(), torch.cos(0.7 * f).numpy(), rtol=1e-6)
+
+
+SCM_LOSS_VARIABLES = ["2m_temperature", "10m_u_component_of_wind", "mean_sea_level_pressure", "geopotential_500",
+                      "temperature_850", "specific_humidity_700"]
+
+
+@pytest.mark.parametrize("name,cfgname", [("tiny", "SWIFT_TINY"), ("small", "SWIFT_SMALL")])
+def test_scm_loss_and_output_cotangent(golden, name, cfgname):
+    """oracle/scm_loss_oracle.py against the real ``SCMLoss`` (training/loss.py:162-260): loss value and dL/dF_x (what the
+    reverse pass starts from), three (noise draw, step, tangent warm-up) cases per fixture."""
+    from oracle import scm_loss_oracle as so
+    g = golden("scm_loss")
+    c = getattr(syn, cfgname)
+    n_img, (H, W) = c["out_channels"], c["img_resolution"]
+    cfg = orc.make_cfg(**c)
+    p = syn.random_state_dict(c, seed=1)
+    x, cond = syn.synthetic_fields(c, 2, seed=5)
+    w_lat, w_var = so.latitude_weights(H), so.variable_weights(SCM_LOSS_VARIABLES[:n_img])
+    np.testing.assert_array_equal(w_lat.numpy(), g[name + "_w_lat"])
+    np.testing.assert_array_equal(w_var.numpy(), g[name + "_w_var"])
+    net = lambda a, b: orc.pass_precond(p, cfg, a, b, cond, 0.6)
+    for case in range(3):
+        k = f"{name}_{case}_"
+        step, warm = (int(v) for v in g[k + "step_warm"])
+        o = so.scm_loss(net, x, torch.from_numpy(g[k + "t"]), torch.from_numpy(g[k + "z"]), step, warm, w_lat, w_var)
+        assert abs(float(o["loss"]) - float(g[k + "loss"])) < 2e-6 * float(g[k + "loss"])
+        _close(o["F"], g[k + "F"])
+        _close(o["cot"], g[k + "cot"], tol=1e-5)
+    assert so.tangent_warmup(500_000, 3000) == pytest.approx(1 / 6) and so.tangent_warmup(5, 0) == 1.0

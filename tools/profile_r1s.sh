@@ -2,7 +2,7 @@
 # Round-1 last session: new-feature tests, the bench line, the store demo, a fresh launch list, then the full GPU suite.
 # Ordered by value: a clamped call still leaves the early artefacts in gpurun_out/.
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_rollout.py -q -m gpu -k "rollout_and_save or reference_noise" > gpurun_out/r1s_newtests.log 2>&1
+python -m pytest tests/test_gpu_rollout.py tests/test_gpu_jvp.py -q -s -m gpu -k "rollout_and_save or reference_noise or scm_output_cotangent" > gpurun_out/r1s_newtests.log 2>&1
 echo "newtests rc=$?" > gpurun_out/r1s_status.txt
 python bench.py > gpurun_out/bench_r1s.json 2> gpurun_out/bench_r1s.err
 echo "bench rc=$?" >> gpurun_out/r1s_status.txt
