@@ -131,6 +131,7 @@ def gpu_eager_member_steps_per_sec(dev, batch: int = 2, n_timed: int = 3):
            "PyTorch ops (cuBLAS / SDPA / ATen kernels) on this GPU"}
     tf32 = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = False
+    ys = {}
     try:
         for name, ctx in (("fp32", torch.autocast("cuda", enabled=False)),
                           ("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
@@ -141,7 +142,7 @@ def gpu_eager_member_steps_per_sec(dev, batch: int = 2, n_timed: int = 3):
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
                     for _ in range(n_timed):
-                        orc.scm_solver(net, lat, cond, 0.6, num_steps=1)
+                        ys[name] = orc.scm_solver(net, lat, cond, 0.6, num_steps=1)
                     e1.record()
                     torch.cuda.synchronize(dev)
                 out[name] = batch * n_timed / (e0.elapsed_time(e1) / 1e3)
@@ -150,6 +151,10 @@ def gpu_eager_member_steps_per_sec(dev, batch: int = 2, n_timed: int = 3):
                 out[name + "_error"] = f"{type(e).__name__}: {e}"[:200]
     finally:
         torch.backends.cuda.matmul.allow_tf32 = tf32
+    if len(ys) == 2:      # accuracy of plain autocast next to its speed: per-field rel-L2 of one sCM step vs the fp32 run
+        a, b = ys["bf16_autocast"].float(), ys["fp32"]
+        out["bf16_autocast_per_field_rel_l2_max"] = float(((a - b).flatten(2).norm(dim=-1) /
+                                                           b.flatten(2).norm(dim=-1)).max())
     return out
 
 
