@@ -117,8 +117,9 @@ class EnsembleRollout:
 
     def __init__(self, net, norm: Normalizers, forcings_std: torch.Tensor, trajectories: Sequence[Tuple[int, int]],
                  solver: str = "scm", solver_kwargs: Optional[dict] = None, use_graph: bool = True,
-                 noise: Optional["ReferenceNoise"] = None):
+                 noise: Optional["ReferenceNoise"] = None, residual: bool = True):
         self.net = net
+        self.residual = bool(residual)          # data/defaults.yaml:7; False = the network predicts the next state itself
         self.norm = norm
         self.forcings = forcings_std.contiguous()   # [steps(+), n_forc, H, W] standardised, on device
         self.traj = list(trajectories)
@@ -149,7 +150,7 @@ class EnsembleRollout:
         self.lib = _lib.lib()
         self.model = _fused_target(net)
         # the single-kernel-sequence step: 1-step sCM through the fused CUDA entry point
-        self.fused = self.model is not None and solver == "scm" and kw["num_steps"] == 1
+        self.fused = self.model is not None and solver == "scm" and kw["num_steps"] == 1 and self.residual
         self.use_graph = use_graph and self.fused
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._glue = RolloutGlue(self.cond, norm.x_std, norm.x_mean, norm.diff_std, self.phys, norm.zero_channel)
@@ -261,8 +262,12 @@ class EnsembleRollout:
         y = self._solve(latents=self.draw_latents(), condition=self.cond, **kw)
         self._step_host += 1
         x_std = self.cond[:, : self.n_var]
-        x_phys = torch.addcmul(x_std * self.norm.x_std + self.norm.x_mean, y, self.norm.diff_std)
-        x_new = (x_phys - self.norm.x_mean) / self.norm.x_std
+        if self.residual:                                                        # generate.py:120-131
+            x_phys = torch.addcmul(x_std * self.norm.x_std + self.norm.x_mean, y, self.norm.diff_std)
+            x_new = (x_phys - self.norm.x_mean) / self.norm.x_std
+        else:                                                                    # generate.py:132-136
+            x_phys = y * self.norm.x_std + self.norm.x_mean
+            x_new = y.clone()
         if self.norm.zero_channel >= 0:
             x_phys[:, self.norm.zero_channel] = 0
             x_new[:, self.norm.zero_channel] = 0

@@ -309,3 +309,36 @@ def test_reference_noise_stream_replay():
             # epilogue vs separate ops), and a 1-ulp change of an fp32 input can flip its 16-bit operand rounding
             tol = 1e-5 if i == 0 else 5e-3
             assert torch.allclose(got[i], X, rtol=tol, atol=tol), f"lead {i}, graph={use_graph}"
+
+
+def test_non_residual_rollout_branch():
+    """generate.py:132-136 (dataset.residual = False): the sampler output IS the next standardised state and the stored
+    field is unstandardize_x(Y).  Goes through the generic path with the same per-trajectory noise streams."""
+    from swift_b200 import synthetic as syn
+    from swift_b200.rollout import EnsembleRollout, Normalizers
+    from swift_b200.sampler import DiffusionSampler
+    cfg = syn.SWIFT_TINY
+    n_var = cfg["out_channels"]
+    net, _ = _build(cfg, n_var)
+    forc = syn.synthetic_forcings(cfg, 2, seed=2, n_forcings=cfg["in_channels"] - 2 * n_var).cuda()
+    mean = torch.linspace(-1, 1, n_var).reshape(1, -1, 1, 1).cuda()
+    std = torch.linspace(0.5, 2.0, n_var).reshape(1, -1, 1, 1).cuda()
+    norm = Normalizers(mean, std, 0.2 * torch.ones_like(std))
+    traj = [(0, 0), (1, 0)]
+    x0 = torch.randn(2, n_var, 32, 64, generator=torch.Generator().manual_seed(8)).cuda()
+    ro = EnsembleRollout(net, norm, forc, traj, residual=False)
+    assert not ro.fused
+    ro.set_state(x0)
+    twin = EnsembleRollout(net, norm, forc, traj)                 # only to draw the same latents
+    X = x0.clone()
+    for i in range(2):
+        got = ro.step().clone()
+        twin.step_dev.fill_(i)
+        lat = twin.draw_latents().clone()
+        Xc = torch.cat([X, forc[i].unsqueeze(0).expand(2, -1, -1, -1)], 1)
+        Y = DiffusionSampler(net).scm_solver(latents=lat, condition=Xc, auxiliary=0.6, num_steps=1, sigma_min=0.02,
+                                             sigma_max=200.0)
+        tol = 1e-5 if i == 0 else 5e-3
+        assert torch.allclose(got, Y * std + mean, rtol=tol, atol=tol), f"lead {i}"
+        assert torch.allclose(ro.cond[:, :n_var], Y, rtol=tol, atol=tol)
+        X = Y

@@ -232,3 +232,28 @@ def test_reference_noise_bookkeeping():
         ReferenceNoise(traj, n_ic=5, batch=0, steps=3, sample_shape=(1,), device=torch.device("cpu"))
     with pytest.raises(ValueError):
         rn.fill(torch.empty(5, 2, 4, 4), 3)
+
+
+def test_scm_loss_weights_match_reference_golden(golden):
+    """swift_b200.scm_target weights (training/loss.py:28-57) against the buffers of the real SCMLoss."""
+    import numpy as np
+    from swift_b200.scm_target import latitude_weights, variable_weights
+    from swift_b200.generate import era5_variables
+    g = golden("scm_loss")
+    names = ["2m_temperature", "10m_u_component_of_wind", "mean_sea_level_pressure", "geopotential_500",
+             "temperature_850", "specific_humidity_700"]
+    np.testing.assert_array_equal(latitude_weights(32).numpy(), g["tiny_w_lat"])
+    np.testing.assert_array_equal(latitude_weights(64).numpy(), g["small_w_lat"])
+    np.testing.assert_array_equal(variable_weights(names[:5]).numpy(), g["tiny_w_var"])
+    np.testing.assert_array_equal(variable_weights(names[:4]).numpy(), g["small_w_var"])
+    w = variable_weights(era5_variables())                      # the 69 Swift-B variables all have a weight
+    assert w.shape == (1, 69, 1, 1) and abs(float(w.sum()) - 1.0) < 1e-6 and float(w.min()) > 0
+    with pytest.raises(KeyError):
+        variable_weights(["geopotential_475"])
+    with pytest.raises(TypeError):
+        from swift_b200.scm_target import scm_output_cotangent
+        import torch
+
+        class _Net(torch.nn.Module):
+            sigma_data, model = 1.0, torch.nn.Identity()
+        scm_output_cotangent(_Net(), torch.zeros(1, 1, 2, 2), torch.zeros(1), torch.zeros(1, 1, 2, 2), 0)
