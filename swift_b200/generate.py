@@ -125,6 +125,7 @@ def main(argv: Optional[Sequence[str]] = None) -> None:
                       condition_channels=cfg["in_channels"] - n_var, auxiliary_dim=1)
     net.load_state_dict(syn.random_state_dict(cfg, seed=1, prefix="model."), strict=True)
     net = net.to(dev).eval()
+    net.model.max_chunk = 24                                                  # trajectories per kernel launch sequence (bench.py)
     H, W = cfg["img_resolution"]
     variables = era5_variables() if n_var == 69 else [f"field{c}" for c in range(n_var)]
     layout = {"zarr": "trajectory", "zarr-step": "step", "numpy": "numpy"}[args.dump]
