@@ -3,8 +3,10 @@
 This file is a functional, plain-PyTorch fp32 restatement of the reference
 algorithm (stockeh/swift, ``src/swift``).  It is the checker that the CUDA path
 is compared against; it is never the thing that is shipped or measured.  Only
-``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl
-reference`` legs of ``bench.py`` may import it.  The product package
+``tests/``, ``__graft_entry__.smoke()`` and the baseline legs of ``bench.py``
+(``cpu_baseline`` / ``--impl reference`` on the host cores, and the
+``gpu_eager_baseline`` SURVEY.md section 8d asks for: the same plain-PyTorch ops
+run eagerly on the GPU, reported beside the product's number) may import it.  The product package
 ``swift_b200`` must never import anything from ``oracle/``.
 
 Pinning: ``tests/golden/make_golden.py`` (run in the build container, where
