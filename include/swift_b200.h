@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SWB200_ABI_VERSION 11
+#define SWB200_ABI_VERSION 12
 #if defined(__GNUC__)
 #define SWB200_API __attribute__((visibility("default")))
 #else
@@ -217,6 +217,22 @@ SWB200_API int swb200_conditioning_jvp(const swb200_model* m, const float* t, co
 SWB200_API int swb200_forward_jvp(const swb200_model* m, const float* x0, int c0, float scale0, const float* x1, int c1,
                        const float* dx0, int B, const float* gain, const float* bias, const float* dgain, const float* dbias,
                        float* y, float* dy, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- the sCM training loss around the denoiser (training/loss.py:196-260; replaces its ~25 PyTorch elementwise ops) ---- */
+
+/* Before the network: x_t = cos t x + sin t z (:203), dxt = cos t z - sin t x (:211), vx = cos t sin t dxt (:216 without
+ * the 1/sigma_d, which swb200_forward_jvp applies as scale0), vt = cos t sin t (:217).  x, z, x_t, dxt, vx: fp32
+ * [B, C, H, W] (W a multiple of 4, 16-byte aligned); t, vt: fp32 [B]. */
+SWB200_API int swb200_scm_noised_inputs(const float* x, const float* z, const float* t, int B, int C, int H, int W, float* x_t,
+                             float* dxt, float* vx, float* vt, void* stream);
+/* After the network: g = -cos^2 (sd F - dxt) - r (cos sin x_t + sd dF) (:241-243), normalised per sample by
+ * |g| sqrt(1/CHW) + 0.1 (:246-248); cot = dL/dF_x = -2 w_var[c] w_lat[h] g / (B H W) and loss = sum w g^2 / (B H W) -- the
+ * value and output gradient of :253-260 with logvar = 0.  w_var [C] / w_lat [H] may be NULL (= 1).  loss: one fp32 on
+ * the device.  scratch: swb200_scm_target_scratch_bytes(B) bytes, 8-byte aligned (fixed-order fp64 partial sums). */
+SWB200_API size_t swb200_scm_target_scratch_bytes(int B);
+SWB200_API int swb200_scm_tangent_target(const float* F, const float* dF, const float* x_t, const float* dxt, const float* t, float r,
+                              float sigma_data, const float* w_var, const float* w_lat, int B, int C, int H, int W,
+                              float* g, float* cot, float* loss, void* scratch, size_t scratch_bytes, void* stream);
 
 /* ---- ensemble verification statistics on resident trajectories (eval/metrics.py:39-134) ------------------ */
 

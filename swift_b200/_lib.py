@@ -11,7 +11,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SWB_LIB", os.path.join(HERE, "libswift_b200.so"))   # SWB_LIB: A/B builds (tools only)
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 # Every symbol ``include/swift_b200.h`` declares; tests check the library exports exactly these.
 EXPORTS = (
@@ -22,6 +22,7 @@ EXPORTS = (
     "swb200_rollout_advance", "swb200_trace_enable", "swb200_trace_report", "swb200_ln_workspace_bytes",
     "swb200_gemm_ln_residual", "swb200_ensemble_stats", "swb200_jvp_workspace_bytes",
     "swb200_conditioning_jvp_scratch_bytes", "swb200_conditioning_jvp", "swb200_forward_jvp",
+    "swb200_scm_noised_inputs", "swb200_scm_target_scratch_bytes", "swb200_scm_tangent_target",
 )
 
 _i32, _f32, _vp, _sz = C.c_int32, C.c_float, C.c_void_p, C.c_size_t
@@ -86,6 +87,10 @@ def _declare(lib):
         "swb200_conditioning_jvp": (C.c_int, [MP, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
         "swb200_forward_jvp": (C.c_int, [MP, _vp, C.c_int, _f32, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp,
                                          _vp, _sz, _vp]),
+        "swb200_scm_noised_inputs": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+        "swb200_scm_target_scratch_bytes": (_sz, [C.c_int]),
+        "swb200_scm_tangent_target": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _vp, C.c_int, C.c_int, C.c_int,
+                                                C.c_int, _vp, _vp, _vp, _vp, _sz, _vp]),
         "swb200_trace_enable": (C.c_int, [C.c_int]),
         "swb200_trace_report": (C.c_int, [C.c_char_p, _sz]),
     }

@@ -715,6 +715,23 @@ SWB200_API int swb200_ensemble_stats(const float* phys, const float* truth, cons
                                static_cast<cudaStream_t>(stream));
 }
 
+SWB200_API int swb200_scm_noised_inputs(const float* x, const float* z, const float* t, int B, int C, int H, int W, float* x_t,
+                                        float* dxt, float* vx, float* vt, void* stream) {
+  SWB_REQUIRE(x && z && t && x_t && dxt && vx && vt, "swb200_scm_noised_inputs: NULL pointer");
+  return launch_scm_noised_inputs(x, z, t, B, C, H, W, x_t, dxt, vx, vt, static_cast<cudaStream_t>(stream));
+}
+
+SWB200_API size_t swb200_scm_target_scratch_bytes(int B) { return B > 0 ? scm_target_scratch_bytes(B) : 0; }
+
+SWB200_API int swb200_scm_tangent_target(const float* F, const float* dF, const float* x_t, const float* dxt, const float* t,
+                                         float r, float sigma_data, const float* w_var, const float* w_lat, int B, int C, int H,
+                                         int W, float* g, float* cot, float* loss, void* scratch, size_t scratch_bytes,
+                                         void* stream) {
+  SWB_REQUIRE(F && dF && x_t && dxt && t && g && cot && loss && scratch, "swb200_scm_tangent_target: NULL pointer");
+  return launch_scm_tangent_target(F, dF, x_t, dxt, t, r, sigma_data, w_var, w_lat, B, C, H, W, g, cot, loss, scratch,
+                                   scratch_bytes, static_cast<cudaStream_t>(stream));
+}
+
 SWB200_API int swb200_rollout_advance(int32_t* step, void* stream) {
   SWB_REQUIRE(step, "swb200_rollout_advance: NULL pointer");
   return launch_rollout_advance(step, static_cast<cudaStream_t>(stream));

@@ -62,4 +62,12 @@ int launch_conditioning_dual(const CondWeights& w, const float* t, const float* 
 int launch_ensemble_stats(const float* phys, const float* truth, const float* w_lat, int n_ic, int members, int V, int H,
                           int W, const int* step, int out_stride, double* out, cudaStream_t stream);
 
+// sCM training-loss glue (scm_target.cu)
+int launch_scm_noised_inputs(const float* x, const float* z, const float* t, int B, int C, int H, int W, float* x_t,
+                             float* dxt, float* vx, float* vt, cudaStream_t stream);
+size_t scm_target_scratch_bytes(int B);
+int launch_scm_tangent_target(const float* F, const float* dF, const float* x_t, const float* dxt, const float* t, float r,
+                              float sigma_data, const float* w_var, const float* w_lat, int B, int C, int H, int W, float* g,
+                              float* cot, float* loss, void* scratch, size_t scratch_bytes, cudaStream_t stream);
+
 }  // namespace swb

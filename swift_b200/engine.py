@@ -143,14 +143,21 @@ class Engine:
 
     # ------------------------------------------------------------------ forward-mode tangent (sCM training loss)
     def forward_jvp(self, x: torch.Tensor, t: torch.Tensor, aux: Optional[torch.Tensor], dx: torch.Tensor,
-                    dt: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        """(F, dF) = jvp(SwinV2.forward, (x, t), (dx, dt)): x, dx [B, in_channels, H, W]; t, dt [B]."""
+                    dt: torch.Tensor, cond: Optional[torch.Tensor] = None, scale0: float = 1.0
+                    ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(F, dF) = jvp(SwinV2.forward, (x, t), (dx, dt)): x, dx [B, in_channels, H, W]; t, dt [B].
+        With ``cond`` [B, c1, H, W] the network input is cat([x * scale0, cond]) and its tangent cat([dx * scale0, 0])
+        (x, dx [B, in_channels - c1, H, W]): the concat of models/precond.py:143-145 happens in the patch gather."""
         g = self.geom
-        for nm, v in (("x", x), ("dx", dx), ("t", t), ("dt", dt)):
+        for nm, v in (("x", x), ("dx", dx), ("t", t), ("dt", dt)) + ((("cond", cond),) if cond is not None else ()):
             self._check_f32(v, nm)
         B = x.shape[0]
-        if tuple(x.shape[1:]) != (g.in_channels, *g.img) or dx.shape != x.shape or t.shape != (B,) or dt.shape != (B,):
-            raise RuntimeError(f"forward_jvp: x/dx must be [B, {g.in_channels}, {g.img[0]}, {g.img[1]}] and t/dt [B]")
+        c1 = 0 if cond is None else cond.shape[1]
+        c0 = g.in_channels - c1
+        if (tuple(x.shape[1:]) != (c0, *g.img) or dx.shape != x.shape or t.shape != (B,) or dt.shape != (B,)
+                or (cond is not None and (cond.shape[0] != B or tuple(cond.shape[2:]) != tuple(g.img)))):
+            raise RuntimeError(f"forward_jvp: x/dx must be [B, {c0}, {g.img[0]}, {g.img[1]}], cond [B, {c1}, ...] and "
+                               f"t/dt [B]")
         if aux is not None:
             self._check_f32(aux, "auxiliary")
         vecs = [torch.empty(2 * g.depth, B, g.dim, device=self.device, dtype=torch.float32) for _ in range(4)]
@@ -165,7 +172,7 @@ class Engine:
             self._jvp_ws = (buf, base, need)
         y = torch.empty(B, *self.out_shape, device=self.device, dtype=torch.float32)
         dy = torch.empty_like(y)
-        _lib.check(self.lib.swb200_forward_jvp(C.byref(self.model), x.data_ptr(), g.in_channels, 1.0, None, 0,
+        _lib.check(self.lib.swb200_forward_jvp(C.byref(self.model), x.data_ptr(), c0, float(scale0), _lib.ptr(cond), c1,
                                                dx.data_ptr(), B, *[v.data_ptr() for v in vecs], y.data_ptr(),
                                                dy.data_ptr(), self._jvp_ws[1], self._jvp_ws[2], self._stream()),
                    "forward_jvp")

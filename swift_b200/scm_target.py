@@ -16,11 +16,11 @@ the CUDA engine (``swb200_forward_jvp``; the reference runs the network twice he
 """
 from __future__ import annotations
 
-import math
 from typing import Dict, Optional, Sequence
 
 import torch
 
+from . import _lib
 from .precond import process_auxiliary
 
 # training/loss.py:10-25, :36-49
@@ -60,38 +60,47 @@ def scm_output_cotangent(net, x: torch.Tensor, t: torch.Tensor, z: torch.Tensor,
                          ) -> Dict[str, torch.Tensor]:
     """x [B, C, H, W] targets, t = atan(tau / sigma_d) ([B] or [B,1,1,1]), z = sigma_d * N(0,1) like x (the draws of
     loss.py:196-200, made by the caller), ``net`` a PassPrecond around ``swift_b200.swinv2.SwinV2`` on a CUDA device.
-    Returns {"loss", "cot" (= dL/dF_x), "g", "F", "dF", "x_t"}; all detached fp32."""
+    Returns {"loss", "cot" (= dL/dF_x), "g", "F", "dF", "x_t"}; all detached fp32.
+
+    Three C-ABI calls: ``swb200_scm_noised_inputs`` (x_t, dx_t/dt, v_x, v_t), ``swb200_forward_jvp`` (the concat with the
+    condition and the 1/sigma_d scaling happen in its patch gather) and ``swb200_scm_tangent_target`` (g, its per-sample
+    normalisation, cot and the loss)."""
     inner = getattr(net, "module", net)
     model = inner.model
     if not hasattr(model, "engine"):
         raise TypeError("scm_output_cotangent needs swift_b200.swinv2.SwinV2 as net.model (there is no fallback path)")
+    eng = model.engine()
+    lib, dev = eng.lib, x.device
+    stream = torch.cuda.current_stream().cuda_stream
     sd = float(inner.sigma_data)
-    B = x.shape[0]
-    x = x.to(torch.float32)
-    t4 = t.to(device=x.device, dtype=torch.float32).reshape(B, 1, 1, 1)
-    cos_t, sin_t = torch.cos(t4), torch.sin(t4)
-    x_t = cos_t * x + sin_t * z                                         # loss.py:203
-    dxt_dt = cos_t * z - sin_t * x                                      # :211
-    v_x = cos_t * sin_t * dxt_dt / sd                                   # :216
-    v_t = (cos_t * sin_t).reshape(B)                                    # :217
-    x_in, dx_in = x_t / sd, v_x
+    B, C, H, W = x.shape
+    x = x.to(torch.float32).contiguous()
+    z = z.to(device=dev, dtype=torch.float32).contiguous()
+    t1 = t.to(device=dev, dtype=torch.float32).reshape(B).contiguous()
+    if z.shape != x.shape:
+        raise RuntimeError(f"z must have the shape of x {tuple(x.shape)}, got {tuple(z.shape)}")
+    x_t, dxt, v_x = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    v_t = torch.empty_like(t1)
+    _lib.check(lib.swb200_scm_noised_inputs(x.data_ptr(), z.data_ptr(), t1.data_ptr(), B, C, H, W, x_t.data_ptr(),
+                                            dxt.data_ptr(), v_x.data_ptr(), v_t.data_ptr(), stream), "scm_noised_inputs")
+    cond = None
     if condition is not None and inner.condition_channels > 0:          # precond.py:143-145; no tangent in the condition
-        x_in = torch.cat([x_in, condition.to(torch.float32)], dim=1)
-        dx_in = torch.cat([dx_in, torch.zeros_like(condition, dtype=torch.float32)], dim=1)
-    aux = process_auxiliary(auxiliary, inner.auxiliary_dim, B, x.device)
+        cond = condition.to(device=dev, dtype=torch.float32).contiguous()
+    aux = process_auxiliary(auxiliary, inner.auxiliary_dim, B, dev)
     if aux is not None:
         aux = aux.to(torch.float32).expand(B, -1).contiguous()
-    F, dF = model.engine().forward_jvp(x_in.contiguous(), t4.reshape(B).contiguous(), aux, dx_in.contiguous(),
-                                       v_t.contiguous())
+    F, dF = eng.forward_jvp(x_t, t1, aux, v_x, v_t, cond=cond, scale0=1.0 / sd)
     r = min(1.0, step / (tangent_warmup_kimg * 1000)) if tangent_warmup_kimg > 0 else 1.0             # :233-237
-    g = -(cos_t ** 2) * (sd * F - dxt_dt) - r * ((cos_t * sin_t) * x_t + sd * dF)                     # :241-243
-    gn = torch.linalg.vector_norm(g, dim=(1, 2, 3), keepdim=True)
-    g = g / (gn * math.sqrt(gn.numel() / g.numel()) + 0.1)                                            # :246-248
-    w = 1.0
-    if w_var is not None:
-        w = w * w_var
-    if w_lat is not None:
-        w = w * w_lat
-    loss = (w * g.square()).sum(dim=1).mean()                                                         # :253-260
-    cot = -2.0 * w * g / (B * g.shape[2] * g.shape[3])
+    wv = None if w_var is None else w_var.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+    wl = None if w_lat is None else w_lat.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+    if (wv is not None and wv.numel() != C) or (wl is not None and wl.numel() != H):
+        raise RuntimeError(f"w_var must have {C} entries and w_lat {H}")
+    g, cot = torch.empty_like(x), torch.empty_like(x)
+    loss = torch.empty((), device=dev, dtype=torch.float32)
+    need = lib.swb200_scm_target_scratch_bytes(B)
+    scratch = torch.empty(need // 8, dtype=torch.float64, device=dev)
+    _lib.check(lib.swb200_scm_tangent_target(F.data_ptr(), dF.data_ptr(), x_t.data_ptr(), dxt.data_ptr(), t1.data_ptr(),
+                                             float(r), sd, _lib.ptr(wv), _lib.ptr(wl), B, C, H, W, g.data_ptr(),
+                                             cot.data_ptr(), loss.data_ptr(), scratch.data_ptr(), need, stream),
+               "scm_tangent_target")
     return {"loss": loss, "cot": cot, "g": g, "F": F, "dF": dF, "x_t": x_t}

@@ -164,3 +164,44 @@ def test_conditioning_matches_oracle(lib):
             b_ref = sd[pre + ".norm.bias"] * (1 + mod[:, :D]) + mod[:, D:]
             assert _rel(gain[2 * l + j].cpu(), g_ref) < 1e-5
             assert _rel(bias[2 * l + j].cpu(), b_ref) < 1e-5
+
+
+@pytest.mark.parametrize("shape,weights", [((2, 5, 32, 64), True), ((3, 7, 12, 20), False), ((1, 69, 128, 256), True)])
+def test_scm_loss_glue_kernels_vs_oracle(lib, shape, weights):
+    """swb200_scm_noised_inputs / swb200_scm_tangent_target against oracle/scm_loss_oracle.py (itself pinned to the real
+    SCMLoss) with random F / dF, i.e. independent of the network: fp32 elementwise work, fp64 fixed-order reductions."""
+    from oracle import scm_loss_oracle as so
+    B, Cn, H, W = shape
+    g = torch.Generator().manual_seed(B * 100 + Cn)
+    x, z, F, dF = (torch.randn(shape, generator=g).cuda() for _ in range(4))
+    t = (torch.rand(B, generator=g) * 1.5 + 0.02).cuda()
+    x_t, dxt, vx = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    vt = torch.empty_like(t)
+    _check(lib.swb200_scm_noised_inputs(x.data_ptr(), z.data_ptr(), t.data_ptr(), B, Cn, H, W, x_t.data_ptr(),
+                                        dxt.data_ptr(), vx.data_ptr(), vt.data_ptr(), _stream()))
+    t4 = t.view(B, 1, 1, 1)
+    c, s = torch.cos(t4), torch.sin(t4)
+    assert torch.allclose(x_t, c * x + s * z, atol=1e-6, rtol=1e-5)
+    assert torch.allclose(dxt, c * z - s * x, atol=1e-6, rtol=1e-5)
+    assert torch.allclose(vx, c * s * (c * z - s * x), atol=1e-6, rtol=1e-5)
+    assert torch.allclose(vt, (c * s).view(B), atol=1e-7, rtol=1e-5)
+    w_lat = so.latitude_weights(H).cuda() if weights else None
+    w_var = (torch.rand(1, Cn, 1, 1, generator=g) + 0.1).cuda() if weights else None
+    for r, sd in ((1.0, 1.0), (0.25, 0.5)):
+        gbuf, cot = torch.empty_like(x), torch.empty_like(x)
+        loss = torch.empty((), device="cuda")
+        need = lib.swb200_scm_target_scratch_bytes(B)
+        scratch = torch.empty(need // 8, dtype=torch.float64, device="cuda")
+        _check(lib.swb200_scm_tangent_target(F.data_ptr(), dF.data_ptr(), x_t.data_ptr(), dxt.data_ptr(), t.data_ptr(), r, sd,
+                                             None if w_var is None else w_var.data_ptr(),
+                                             None if w_lat is None else w_lat.data_ptr(), B, Cn, H, W, gbuf.data_ptr(),
+                                             cot.data_ptr(), loss.data_ptr(), scratch.data_ptr(), need, _stream()))
+        ref_g = so.scm_tangent_target(F, dF, x_t, dxt, c, s, r, sd)
+        w = (w_var if weights else 1.0) * (w_lat if weights else 1.0)
+        ref_loss = (w * ref_g.square()).sum(dim=1).mean()
+        ref_cot = -2.0 * w * ref_g / (B * H * W)
+        assert _rel(gbuf, ref_g) < 2e-6 and _rel(cot, ref_cot) < 2e-6
+        assert abs(float(loss) - float(ref_loss)) < 1e-5 * float(ref_loss)
+    assert lib.swb200_scm_tangent_target(F.data_ptr(), dF.data_ptr(), x_t.data_ptr(), dxt.data_ptr(), t.data_ptr(), 1.0, 1.0,
+                                         None, None, B, Cn, H, W, gbuf.data_ptr(), cot.data_ptr(), loss.data_ptr(),
+                                         scratch.data_ptr(), 8, _stream()) != 0          # scratch too small: refused
