@@ -446,11 +446,56 @@ def run_tangent(args):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
+    # the whole no-reverse-mode half of the sCM training step (training/loss.py:196-260): noised inputs, primal + tangent
+    # pass, tangent target / loss / output cotangent -- three C-ABI calls (swift_b200/scm_target.py)
+    from swift_b200.generate import era5_variables
+    from swift_b200.scm_target import latitude_weights, scm_output_cotangent, variable_weights
+    xs, cond = x[:, :syn.IMG_CHANNELS].contiguous(), x[:, syn.IMG_CHANNELS:].contiguous()
+    zs = torch.randn_like(xs)
+    w_lat, w_var = latitude_weights(cfg["img_resolution"][0], dev), variable_weights(era5_variables(), dev)
+    kw = dict(condition=cond, auxiliary=0.6, tangent_warmup_kimg=3000, w_lat=w_lat, w_var=w_var)
+    for _ in range(3):
+        out = scm_output_cotangent(net, xs, t, zs, 1_500_000, **kw)
+    torch.cuda.synchronize()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        out = scm_output_cotangent(net, xs, t, zs, 1_500_000, **kw)
+    e3.record()
+    torch.cuda.synchronize()
+    ms_target = e2.elapsed_time(e3) / args.steps
+    # baseline leg: the same half of the loss as eager PyTorch ops on this GPU (oracle port; ONE torch.func.jvp pass, i.e.
+    # without the reference's second, grad-enabled forward), fp32 with TF32 off
+    eager = None
+    if not args.no_cpu:
+        try:
+            from oracle import scm_loss_oracle as so, swinv2_oracle as orc
+            torch.backends.cuda.matmul.allow_tf32 = False
+            sd_gpu = {k: v.to(dev) for k, v in syn.random_state_dict(cfg, seed=1).items()}
+            ocfg = orc.make_cfg(**cfg)
+            onet = lambda a, b: orc.pass_precond(sd_gpu, ocfg, a, b, cond, 0.6)
+            t4 = t.view(1, 1, 1, 1)
+            with torch.no_grad():
+                ref = so.scm_loss(onet, xs, t4, zs, 1_500_000, 3000, w_lat, w_var)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(2):
+                    ref = so.scm_loss(onet, xs, t4, zs, 1_500_000, 3000, w_lat, w_var)
+                torch.cuda.synchronize()
+            eager = {"ms_per_sample": (time.perf_counter() - t0) / 2 * 1e3, "loss": float(ref["loss"]),
+                     "cot_rel_l2_ours_vs_eager_fp32": float((out["cot"] - ref["cot"]).norm() / ref["cot"].norm())}
+        except Exception as e:
+            eager = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     flops = 2 * 2.72e12 + 0.5 * 5 * 8.86e9 * 12        # stacked GEMMs (2x) + five window products per layer instead of two
     print(json.dumps({"metric": "tangent-forward samples/sec (Swift-B, batch 1)", "value": 1e3 / ms, "unit": "samples/s",
                       "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms,
                       "higher_is_better": True, "dtype": "fp16 tensor-core operands, fp32 accumulate / dual kernels",
                       "data": "synthetic", "tflops": flops / ms / 1e9,
+                      "scm_loss_forward_half": {"ms_per_sample": ms_target, "loss": float(out["loss"]),
+                                                "what": "scm_output_cotangent: noised inputs + primal/tangent pass + tangent "
+                                                        "target, loss and dL/dF_x (training/loss.py:196-260 without the "
+                                                        "grad-enabled forward / backward)",
+                                                "eager_pytorch_same_gpu": eager},
                       "config": {"workload": "Swift-B forward-mode tangent forward (jvp of the denoiser w.r.t. x and t)"}}))
 
 
