@@ -27,6 +27,7 @@ from __future__ import annotations
 import json
 import os
 import re
+import threading
 import zlib
 from collections import defaultdict
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
@@ -91,6 +92,7 @@ class ForecastStore:
         self.batch = int(batch) if layout == "trajectory" else 1
         self.compress_level = int(compress_level)
         self._mm: Optional[np.memmap] = None
+        self._mm_lock = threading.Lock()
 
     # ------------------------------------------------------------------------------------------------ creation
     @classmethod
@@ -237,7 +239,9 @@ class ForecastStore:
 
     def _memmap(self) -> np.memmap:
         if self._mm is None:
-            self._mm = np.lib.format.open_memmap(self.path, mode="r+")
+            with self._mm_lock:                                   # writer threads share one mapping
+                if self._mm is None:
+                    self._mm = np.lib.format.open_memmap(self.path, mode="r+")
         return self._mm
 
     def flush(self) -> None:
