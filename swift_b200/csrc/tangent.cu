@@ -24,16 +24,6 @@ namespace swb {
 
 namespace {
 
-template <bool F16>
-__device__ __forceinline__ float pair_load(const uint16_t* row, int D, int i) {
-  return unpack_act1<F16>(row[i]) + unpack_act1<F16>(row[D + i]);
-}
-template <bool F16>
-__device__ __forceinline__ void pair_store(uint16_t* row, int D, int i, float x) {
-  const uint16_t h = pack_act1<F16>(x);
-  row[i] = h;
-  row[D + i] = pack_act1<F16>(x - unpack_act1<F16>(h));
-}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -44,7 +34,37 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ---------------------------------------------------------------------------------------------------------
 // x <- x + LN(b) g + beta ;  dx <- dx + d[LN(b) g + beta]      (one warp per token row)
+// The primal and tangent branch rows live in registers (NV8 groups of 8 values per lane, 16-byte accesses, every load of
+// the row issued before the first use); the residual pairs are read, updated and written one 16-byte group at a time.
+namespace {
+__device__ __forceinline__ void load8(const float4* p, bool ok, float* o) {
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+  if (ok) {
+    a = __ldg(p);
+    b = __ldg(p + 1);
+  }
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+  o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
 template <bool F16>
+__device__ __forceinline__ void pair_update8(uint4* xh, uint4* xl, const float* add) {
+  const uint4 rh = *xh, rl = *xl;
+  const uint32_t wh[4] = {rh.x, rh.y, rh.z, rh.w}, wl[4] = {rl.x, rl.y, rl.z, rl.w};
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 a = unpack_act2<F16>(wh[j]), c = unpack_act2<F16>(wl[j]);
+    const float o0 = (a.x + c.x) + add[2 * j], o1 = (a.y + c.y) + add[2 * j + 1];
+    h[j] = pack_act2<F16>(o0, o1);
+    const float2 back = unpack_act2<F16>(h[j]);
+    l[j] = pack_act2<F16>(o0 - back.x, o1 - back.y);
+  }
+  *xh = make_uint4(h[0], h[1], h[2], h[3]);
+  *xl = make_uint4(l[0], l[1], l[2], l[3]);
+}
+}  // namespace
+
+template <int NV8, bool F16>
 __global__ void __launch_bounds__(128) ln_dual_kernel(const float* __restrict__ branch, uint16_t* __restrict__ xhl,
                                                       const float* __restrict__ gain, const float* __restrict__ bias,
                                                       const float* __restrict__ dgain, const float* __restrict__ dbias,
@@ -52,40 +72,92 @@ __global__ void __launch_bounds__(128) ln_dual_kernel(const float* __restrict__ 
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
-  const float* b = branch + static_cast<size_t>(row) * D;
-  const float* bd = branch + static_cast<size_t>(M + row) * D;
-  float s = 0.f;
-  for (int i = lane; i < D; i += 32) s += b[i];
-  const float mean = warp_sum(s) / D;
-  float v = 0.f;
-  for (int i = lane; i < D; i += 32) v = fmaf(b[i] - mean, b[i] - mean, v);
-  const float rstd = rsqrtf(warp_sum(v) / D + eps);
-  float m1 = 0.f, m2 = 0.f;
-  for (int i = lane; i < D; i += 32) {
-    const float nh = (b[i] - mean) * rstd;
-    m1 += bd[i];
-    m2 = fmaf(nh, bd[i], m2);
+  const int ng = D >> 3;
+  const float4* b4 = reinterpret_cast<const float4*>(branch + static_cast<size_t>(row) * D);
+  const float4* bd4 = reinterpret_cast<const float4*>(branch + static_cast<size_t>(M + row) * D);
+  float v[NV8][8], dv[NV8][8];
+#pragma unroll
+  for (int i = 0; i < NV8; ++i) {
+    const int c = i * 32 + lane;
+    load8(b4 + 2 * c, c < ng, v[i]);
+    load8(bd4 + 2 * c, c < ng, dv[i]);
   }
-  m1 = warp_sum(m1) / D;
-  m2 = warp_sum(m2) / D;
+  const float inv_d = 1.0f / static_cast<float>(D);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[i][j];
+  const float mean = warp_sum(s) * inv_d;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV8; ++i)
+    if (i * 32 + lane < ng) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) var = fmaf(v[i][j] - mean, v[i][j] - mean, var);
+    }
+  const float rstd = rsqrtf(warp_sum(var) * inv_d + eps);
+  float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV8; ++i)
+    if (i * 32 + lane < ng) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[i][j] = (v[i][j] - mean) * rstd;          // n-hat from here on
+        m1 += dv[i][j];
+        m2 = fmaf(v[i][j], dv[i][j], m2);
+      }
+    }
+  m1 = warp_sum(m1) * inv_d;
+  m2 = warp_sum(m2) * inv_d;
   const int smp = row / tokens;
-  const float *g = gain + static_cast<size_t>(smp) * D, *be = bias + static_cast<size_t>(smp) * D;
-  const float *dg = dgain + static_cast<size_t>(smp) * D, *dbe = dbias + static_cast<size_t>(smp) * D;
-  uint16_t* xr = xhl + static_cast<size_t>(row) * 2 * D;
-  uint16_t* xdr = xhl + static_cast<size_t>(M + row) * 2 * D;
-  for (int i = lane; i < D; i += 32) {
-    const float nh = (b[i] - mean) * rstd;
-    const float dnh = rstd * (bd[i] - m1 - nh * m2);
-    pair_store<F16>(xr, D, i, pair_load<F16>(xr, D, i) + fmaf(nh, g[i], be[i]));
-    pair_store<F16>(xdr, D, i, pair_load<F16>(xdr, D, i) + fmaf(dnh, g[i], fmaf(nh, dg[i], dbe[i])));
+  const float4* g4 = reinterpret_cast<const float4*>(gain + static_cast<size_t>(smp) * D);
+  const float4* be4 = reinterpret_cast<const float4*>(bias + static_cast<size_t>(smp) * D);
+  const float4* dg4 = reinterpret_cast<const float4*>(dgain + static_cast<size_t>(smp) * D);
+  const float4* dbe4 = reinterpret_cast<const float4*>(dbias + static_cast<size_t>(smp) * D);
+  uint4* xh = reinterpret_cast<uint4*>(xhl + static_cast<size_t>(row) * 2 * D);
+  uint4* xdh = reinterpret_cast<uint4*>(xhl + static_cast<size_t>(M + row) * 2 * D);
+#pragma unroll
+  for (int i = 0; i < NV8; ++i) {
+    const int c = i * 32 + lane;
+    if (c < ng) {
+      float g[8], be[8], dg[8], dbe[8], add[8], dadd[8];
+      load8(g4 + 2 * c, true, g);
+      load8(be4 + 2 * c, true, be);
+      load8(dg4 + 2 * c, true, dg);
+      load8(dbe4 + 2 * c, true, dbe);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float nh = v[i][j];
+        const float dnh = rstd * (dv[i][j] - m1 - nh * m2);
+        add[j] = fmaf(nh, g[j], be[j]);
+        dadd[j] = fmaf(dnh, g[j], fmaf(nh, dg[j], dbe[j]));
+      }
+      pair_update8<F16>(xh + c, xh + ng + c, add);
+      pair_update8<F16>(xdh + c, xdh + ng + c, dadd);
+    }
   }
 }
 
 int launch_ln_dual(const float* branch2, void* xhl2, const float* gain, const float* bias, const float* dgain,
                    const float* dbias, int M, int D, int tokens, float eps, int act_f16, cudaStream_t stream) {
+  SWB_REQUIRE(D % 8 == 0 && D <= 2048, "ln_dual: dim %d must be a multiple of 8 and at most 2048", D);
+  SWB_REQUIRE(((reinterpret_cast<uintptr_t>(branch2) | reinterpret_cast<uintptr_t>(xhl2) | reinterpret_cast<uintptr_t>(gain) |
+                reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(dgain) | reinterpret_cast<uintptr_t>(dbias)) & 15) == 0,
+              "ln_dual: pointers must be 16-byte aligned");
   dim3 grid((M + 3) / 4);
-  if (act_f16) ln_dual_kernel<true><<<grid, 128, 0, stream>>>(branch2, static_cast<uint16_t*>(xhl2), gain, bias, dgain, dbias, M, D, tokens, eps);
-  else ln_dual_kernel<false><<<grid, 128, 0, stream>>>(branch2, static_cast<uint16_t*>(xhl2), gain, bias, dgain, dbias, M, D, tokens, eps);
+  auto x_ = static_cast<uint16_t*>(xhl2);
+#define SWB_LND(V)                                                                                                    \
+  do {                                                                                                                \
+    if (act_f16) ln_dual_kernel<V, true><<<grid, 128, 0, stream>>>(branch2, x_, gain, bias, dgain, dbias, M, D, tokens, eps);  \
+    else ln_dual_kernel<V, false><<<grid, 128, 0, stream>>>(branch2, x_, gain, bias, dgain, dbias, M, D, tokens, eps);         \
+  } while (0)
+  const int nv8 = (D / 8 + 31) / 32;
+  if (nv8 <= 2) SWB_LND(2);
+  else if (nv8 <= 3) SWB_LND(3);
+  else if (nv8 <= 5) SWB_LND(5);
+  else SWB_LND(8);
+#undef SWB_LND
   SWB_CHECK_CUDA(cudaGetLastError());
   return SWB_OK;
 }
@@ -387,29 +459,42 @@ int launch_attention_dual(const void* qkv, const void* dqkv, float* S, float* dS
 
 // ---------------------------------------------------------------------------------------------------------
 // raw [2M, 2*Dff] fp32, columns in packed tile order (every `tile` columns: [tile/2 gate | tile/2 up]) -> h2 [2M, Dff] 16-bit
+// four consecutive outputs per thread: float4 loads of gate / up / dgate / dup, one 8-byte store per output row
 template <bool F16>
 __global__ void __launch_bounds__(256) swiglu_dual_kernel(const float* __restrict__ raw, uint16_t* __restrict__ h2, int M,
                                                           int Dff, int tile) {
-  const size_t total = static_cast<size_t>(M) * Dff;
+  const int q = Dff >> 2;                                    // groups of 4 outputs per row (tile/2 is a multiple of 4)
+  const size_t total = static_cast<size_t>(M) * q;
   const int half = tile / 2;
   for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const size_t row = idx / Dff;
-    const int j = static_cast<int>(idx - row * Dff);
+    const size_t row = idx / q;
+    const int j = static_cast<int>(idx - row * q) * 4;
     const int col = (j / half) * tile + (j % half);
-    const float* r = raw + row * 2 * Dff;
-    const float* rd = raw + (M + row) * 2 * Dff;
-    const float gte = r[col], up = r[col + half], dg = rd[col], du = rd[col + half];
-    const float sig = 1.0f / (1.0f + __expf(-gte));
-    const float silu = gte * sig;
-    const float dsilu = sig * (1.0f + gte * (1.0f - sig));
-    h2[row * Dff + j] = pack_act1<F16>(silu * up);
-    h2[(M + row) * Dff + j] = pack_act1<F16>(fmaf(dsilu * dg, up, silu * du));
+    const float* r = raw + row * 2 * Dff + col;
+    const float* rd = raw + (M + row) * 2 * Dff + col;
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(r)), u4 = __ldg(reinterpret_cast<const float4*>(r + half));
+    const float4 dg4 = __ldg(reinterpret_cast<const float4*>(rd)), du4 = __ldg(reinterpret_cast<const float4*>(rd + half));
+    const float gte[4] = {g4.x, g4.y, g4.z, g4.w}, up[4] = {u4.x, u4.y, u4.z, u4.w};
+    const float dg[4] = {dg4.x, dg4.y, dg4.z, dg4.w}, du[4] = {du4.x, du4.y, du4.z, du4.w};
+    float o[4], d[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float sig = 1.0f / (1.0f + __expf(-gte[k]));
+      const float silu = gte[k] * sig;
+      const float dsilu = sig * (1.0f + gte[k] * (1.0f - sig));
+      o[k] = silu * up[k];
+      d[k] = fmaf(dsilu * dg[k], up[k], silu * du[k]);
+    }
+    *reinterpret_cast<uint2*>(h2 + row * Dff + j) = make_uint2(pack_act2<F16>(o[0], o[1]), pack_act2<F16>(o[2], o[3]));
+    *reinterpret_cast<uint2*>(h2 + (M + row) * Dff + j) = make_uint2(pack_act2<F16>(d[0], d[1]), pack_act2<F16>(d[2], d[3]));
   }
 }
 
 int launch_swiglu_dual(const float* raw2, void* h2, int M, int Dff, int tile, int act_f16, cudaStream_t stream) {
-  const size_t total = static_cast<size_t>(M) * Dff;
+  SWB_REQUIRE(Dff % 4 == 0 && tile % 8 == 0 && ((reinterpret_cast<uintptr_t>(raw2) | reinterpret_cast<uintptr_t>(h2)) & 15) == 0,
+              "swiglu_dual: Dff %d / tile %d must be multiples of 4 / 8 and the buffers 16-byte aligned", Dff, tile);
+  const size_t total = static_cast<size_t>(M) * (Dff / 4);
   const unsigned blocks = static_cast<unsigned>(std::min<size_t>((total + 255) / 256, 148 * 16));
   if (act_f16) swiglu_dual_kernel<true><<<blocks, 256, 0, stream>>>(raw2, static_cast<uint16_t*>(h2), M, Dff, tile);
   else swiglu_dual_kernel<false><<<blocks, 256, 0, stream>>>(raw2, static_cast<uint16_t*>(h2), M, Dff, tile);
