@@ -164,6 +164,7 @@ int launch_ln_dual(const float* branch2, void* xhl2, const float* gain, const fl
 
 // ---------------------------------------------------------------------------------------------------------
 // raw [2M, 3D] fp32 (packed column order part*D + head*hd + d) -> qkv, dqkv : [3][H][M][pad] 16-bit, q / k normalised
+// one warp per (row, slot): lane l < hd/4 owns elements 4l..4l+3 (float4 loads), lanes < pad/4 store 8 bytes each
 template <bool F16>
 __global__ void __launch_bounds__(128) qkv_dual_pack_kernel(const float* __restrict__ raw, const float* __restrict__ qscale,
                                                             uint16_t* __restrict__ out, uint16_t* __restrict__ dout, int M,
@@ -172,40 +173,40 @@ __global__ void __launch_bounds__(128) qkv_dual_pack_kernel(const float* __restr
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* r = raw + static_cast<size_t>(row) * 3 * D;
   const float* rd = raw + static_cast<size_t>(M + row) * 3 * D;
+  const bool has = 4 * lane < hd;
   for (int slot = warp; slot < 3 * heads; slot += blockDim.x >> 5) {
     const int part = slot / heads, head = slot - part * heads;
-    const float* v = r + slot * hd;
-    const float* dv = rd + slot * hd;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), dv = v;
+    if (has) {
+      v = __ldg(reinterpret_cast<const float4*>(r + slot * hd) + lane);
+      dv = __ldg(reinterpret_cast<const float4*>(rd + slot * hd) + lane);
+    }
     float inv = 1.f, proj = 0.f, sc = 1.f;
     if (part < 2) {
-      float ss = 0.f, dot = 0.f;
-      for (int i = lane; i < hd; i += 32) {
-        ss = fmaf(v[i], v[i], ss);
-        dot = fmaf(v[i], dv[i], dot);
-      }
-      ss = warp_sum(ss);
-      dot = warp_sum(dot);
+      const float ss = warp_sum(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w);
+      const float dot = warp_sum(v.x * dv.x + v.y * dv.y + v.z * dv.z + v.w * dv.w);
       const float nrm = sqrtf(ss);
       inv = 1.0f / fmaxf(nrm, 1e-12f);
       proj = nrm > 1e-12f ? dot * inv * inv : 0.f;         // (u . dv) / |v| with u = v / |v|
       if (part == 0) sc = qscale[head];
     }
-    uint16_t* o = out + (static_cast<size_t>(slot) * M + row) * pad;
-    uint16_t* od = dout + (static_cast<size_t>(slot) * M + row) * pad;
-    for (int i = lane; i < pad; i += 32) {
-      float a = 0.f, da = 0.f;
-      if (i < hd) {
-        a = v[i] * inv * sc;
-        da = (part < 2) ? (dv[i] - v[i] * proj) * inv * sc : dv[i];
-      }
-      o[i] = pack_act1<F16>(a);
-      od[i] = pack_act1<F16>(da);
+    if (4 * lane < pad) {
+      const float k = inv * sc;
+      float4 a = make_float4(v.x * k, v.y * k, v.z * k, v.w * k), da = dv;     // lanes beyond hd hold zeros
+      if (part < 2) da = make_float4((dv.x - v.x * proj) * k, (dv.y - v.y * proj) * k, (dv.z - v.z * proj) * k,
+                                     (dv.w - v.w * proj) * k);
+      const size_t o = (static_cast<size_t>(slot) * M + row) * pad + 4 * lane;
+      *reinterpret_cast<uint2*>(out + o) = make_uint2(pack_act2<F16>(a.x, a.y), pack_act2<F16>(a.z, a.w));
+      *reinterpret_cast<uint2*>(dout + o) = make_uint2(pack_act2<F16>(da.x, da.y), pack_act2<F16>(da.z, da.w));
     }
   }
 }
 
 int launch_qkv_dual_pack(const float* raw2, const float* qscale, void* qkv, void* dqkv, int M, int D, int heads, int hd,
                          int pad, int act_f16, cudaStream_t stream) {
+  SWB_REQUIRE(hd % 4 == 0 && pad % 4 == 0 && hd <= 128 && pad <= 128 && D % 4 == 0 &&
+                  ((reinterpret_cast<uintptr_t>(raw2) | reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(dqkv)) & 15) == 0,
+              "qkv_dual_pack: head dim %d / pad %d must be multiples of 4 (<= 128) and the buffers 16-byte aligned", hd, pad);
   if (act_f16) qkv_dual_pack_kernel<true><<<M, 128, 0, stream>>>(raw2, qscale, static_cast<uint16_t*>(qkv), static_cast<uint16_t*>(dqkv), M, D, heads, hd, pad);
   else qkv_dual_pack_kernel<false><<<M, 128, 0, stream>>>(raw2, qscale, static_cast<uint16_t*>(qkv), static_cast<uint16_t*>(dqkv), M, D, heads, hd, pad);
   SWB_CHECK_CUDA(cudaGetLastError());
