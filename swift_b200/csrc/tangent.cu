@@ -6,7 +6,7 @@
 // plain fp32 epilogue; the kernels here apply the derivative rules of what sits between the GEMMs:
 //   ln_dual_kernel         ModulatedNorm + residual (models/swinv2.py:77-86, :211-212) with tangent gain / bias
 //   qkv_dual_pack_kernel   F.normalize(q, k) * logit scale (:123-127) and its Jacobian, packed for the attention stage
-//   attn_scores_dual / attn_softmax_dual / attn_out_dual   windowed softmax attention (:129-135, :189-209):
+//   attn_scores_dual / attn_out_dual (softmax fused)       windowed softmax attention (:129-135, :189-209):
 //                          S = q k^T, dS = dq k^T + q dk^T,  P = softmax S,  dP = P (dS - sum_j P dS),
 //                          O = P v, dO = dP v + P dv   (explicit-softmax path the reference selects with jvp=True)
 //   swiglu_dual_kernel     silu(gate) * up (:99-100)
@@ -322,45 +322,11 @@ __global__ void __launch_bounds__(128) attn_scores_dual_kernel(const uint16_t* _
   }
 }
 
-// rows of 256: P = softmax(S), dP = P (dS - sum_j P dS), in place     (one warp per row)
-__global__ void __launch_bounds__(256) attn_softmax_dual_kernel(float* __restrict__ S, float* __restrict__ dS, size_t rows) {
-  const size_t row = static_cast<size_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int lane = threadIdx.x & 31;
-  float* s = S + row * 256;
-  float* ds = dS + row * 256;
-  float v[8], dv[8], mx = -INFINITY;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    v[i] = s[i * 32 + lane];
-    dv[i] = ds[i * 32 + lane];
-    mx = fmaxf(mx, v[i]);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  float z = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    v[i] = __expf(v[i] - mx);
-    z += v[i];
-  }
-  const float inv = 1.0f / warp_sum(z);
-  float c = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    v[i] *= inv;
-    c = fmaf(v[i], dv[i], c);
-  }
-  c = warp_sum(c);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    s[i * 32 + lane] = v[i];
-    ds[i * 32 + lane] = v[i] * (dv[i] - c);
-  }
-}
-
 // O = P v ; dO = dP v + P dv   -> attn2 [2M, D] 16-bit at the tokens' own rows, column head*hd + d.
-// one block per (item, 64-row tile); 4 warps x 16 rows on the tensor cores; P / dP rounded to the 16-bit operand format
+// one block per (item, 64-row tile); 4 warps x 16 rows on the tensor cores.  The row softmax and its tangent,
+//     P = softmax(S),  dP = P (dS - sum_j P dS),
+// happen while the 64 x 256 score rows are staged into shared memory (one warp per row, 8 consecutive keys per lane), so
+// P / dP exist only as 16-bit operands in shared memory and S / dS are read from HBM exactly once.
 template <bool F16>
 __global__ void __launch_bounds__(128) attn_out_dual_kernel(const float* __restrict__ P, const float* __restrict__ dP,
                                                             const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ dqkv,
@@ -383,12 +349,39 @@ __global__ void __launch_bounds__(128) attn_out_dual_kernel(const float* __restr
   asm volatile("cp.async.commit_group;" ::: "memory");
   const float* Pi = P + static_cast<size_t>(item) * 65536 + static_cast<size_t>(ti) * 256;
   const float* dPi = dP + static_cast<size_t>(item) * 65536 + static_cast<size_t>(ti) * 256;
-  for (int idx = tid; idx < 64 * 64; idx += 128) {                    // 64 rows x 64 float4
-    const int r = idx >> 6, c4 = idx & 63;
-    const float4 a = *reinterpret_cast<const float4*>(Pi + r * 256 + c4 * 4);
-    const float4 d = *reinterpret_cast<const float4*>(dPi + r * 256 + c4 * 4);
-    *reinterpret_cast<uint2*>(sp + r * kPPitch + c4 * 4) = make_uint2(pack_act2<F16>(a.x, a.y), pack_act2<F16>(a.z, a.w));
-    *reinterpret_cast<uint2*>(sdp + r * kPPitch + c4 * 4) = make_uint2(pack_act2<F16>(d.x, d.y), pack_act2<F16>(d.z, d.w));
+#pragma unroll 2
+  for (int rr = 0; rr < 16; ++rr) {                                   // this warp's 16 rows, 8 keys per lane
+    const int r = warp * 16 + rr;
+    const float4 a0 = *reinterpret_cast<const float4*>(Pi + r * 256 + lane * 8), a1 = *reinterpret_cast<const float4*>(Pi + r * 256 + lane * 8 + 4);
+    const float4 d0 = *reinterpret_cast<const float4*>(dPi + r * 256 + lane * 8), d1 = *reinterpret_cast<const float4*>(dPi + r * 256 + lane * 8 + 4);
+    float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+    float mx = v[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, v[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float z = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[i] = __expf(v[i] - mx);
+      z += v[i];
+    }
+    const float inv = 1.0f / warp_sum(z);
+    float c = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[i] *= inv;
+      c = fmaf(v[i], dv[i], c);
+    }
+    c = warp_sum(c);
+    float dp[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dp[i] = v[i] * (dv[i] - c);
+    *reinterpret_cast<uint4*>(sp + r * kPPitch + lane * 8) =
+        make_uint4(pack_act2<F16>(v[0], v[1]), pack_act2<F16>(v[2], v[3]), pack_act2<F16>(v[4], v[5]), pack_act2<F16>(v[6], v[7]));
+    *reinterpret_cast<uint4*>(sdp + r * kPPitch + lane * 8) =
+        make_uint4(pack_act2<F16>(dp[0], dp[1]), pack_act2<F16>(dp[2], dp[3]), pack_act2<F16>(dp[4], dp[5]), pack_act2<F16>(dp[6], dp[7]));
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
@@ -450,8 +443,6 @@ int launch_attention_dual(const void* qkv, const void* dqkv, float* S, float* dS
   SWB_REQUIRE(hd == 88 && pad == 96, "attention_dual: the tensor-core kernels are specialised for head_dim 88 padded to 96");
   if (act_f16) attn_scores_dual_kernel<true><<<dim3(16, items), 128, kScoresSmem, stream>>>(q, dq, S, dS, g);
   else attn_scores_dual_kernel<false><<<dim3(16, items), 128, kScoresSmem, stream>>>(q, dq, S, dS, g);
-  const size_t rows = static_cast<size_t>(items) * 256;
-  attn_softmax_dual_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(S, dS, rows);
   if (act_f16) attn_out_dual_kernel<true><<<dim3(4, items), 128, kOutSmem, stream>>>(S, dS, q, dq, static_cast<uint16_t*>(attn2), g);
   else attn_out_dual_kernel<false><<<dim3(4, items), 128, kOutSmem, stream>>>(S, dS, q, dq, static_cast<uint16_t*>(attn2), g);
   SWB_CHECK_CUDA(cudaGetLastError());
