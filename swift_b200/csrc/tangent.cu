@@ -19,6 +19,7 @@
 #include "ptx.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace swb {
 
@@ -421,6 +422,152 @@ __global__ void __launch_bounds__(128) attn_out_dual_kernel(const float* __restr
   }
 }
 
+// Fused dual attention: scores, softmax, output and their tangents in one pass over the keys, nothing materialised.
+// With p~ = exp(S - m) (running row maximum m, flash-attention style) and l = sum p~:
+//     O = (sum_j p~_j v_j) / l,     c = (sum_j p~_j dS_j) / l,
+//     dO = sum_j dP_j v_j + P_j dv_j  with dP_j = P_j (dS_j - c)   =   (sum_j (p~_j dS_j) v_j + p~_j dv_j) / l - c O,
+// so O, the combined tangent accumulator, l and c are all rescaled by exp(m_old - m_new) per 64-key chunk.
+// One block per (item, 64-row tile); 4 warps x 16 rows; S / dS live in mma.sync accumulators whose layout is the next
+// MMA's A fragment (p~ and p~ dS are packed straight from registers); K / dK / V / dV arrive in 64-key chunks by cp.async.
+template <bool F16>
+__global__ void __launch_bounds__(128) attn_fused_dual_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ dqkv,
+                                                              uint16_t* __restrict__ attn2, AttnDualGeom g) {
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  uint16_t* sq = reinterpret_cast<uint16_t*>(smem_dyn);
+  uint16_t* sdq = sq + 64 * kDPitch;
+  uint16_t* sk = sdq + 64 * kDPitch;
+  uint16_t* sdk = sk + 64 * kDPitch;
+  uint16_t* sv = sdk + 64 * kDPitch;
+  uint16_t* sdv = sv + 64 * kDPitch;
+  const int item = blockIdx.y;
+  const int head = item % g.heads;
+  const int bw = item / g.heads;
+  const int nwin = (g.gh / 16) * (g.gw / 16);
+  const int win = bw % nwin, b = bw / nwin;
+  const int ti = blockIdx.x * 64;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const size_t slot_q = static_cast<size_t>(head) * g.M * g.pad, slot_k = static_cast<size_t>(g.heads + head) * g.M * g.pad;
+  const size_t slot_v = static_cast<size_t>(2 * g.heads + head) * g.M * g.pad;
+  gather_rows_async(qkv + slot_q, sq, g, b, win, ti, 64, tid, 128);
+  gather_rows_async(dqkv + slot_q, sdq, g, b, win, ti, 64, tid, 128);
+  const uint32_t uq = static_cast<uint32_t>(__cvta_generic_to_shared(sq)), udq = static_cast<uint32_t>(__cvta_generic_to_shared(sdq));
+  const uint32_t uk = static_cast<uint32_t>(__cvta_generic_to_shared(sk)), udk = static_cast<uint32_t>(__cvta_generic_to_shared(sdk));
+  const uint32_t uv = static_cast<uint32_t>(__cvta_generic_to_shared(sv)), udv = static_cast<uint32_t>(__cvta_generic_to_shared(sdv));
+  float o[12][4] = {}, da[12][4] = {};
+  float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f}, crow[2] = {0.f, 0.f};
+  const int ar = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, ac = (lane >> 4) * 8;
+#pragma unroll 1
+  for (int kc = 0; kc < 4; ++kc) {
+    __syncthreads();                                                  // the previous chunk's operands are consumed
+    gather_rows_async(qkv + slot_k, sk, g, b, win, kc * 64, 64, tid, 128);
+    gather_rows_async(dqkv + slot_k, sdk, g, b, win, kc * 64, 64, tid, 128);
+    gather_rows_async(qkv + slot_v, sv, g, b, win, kc * 64, 64, tid, 128);
+    gather_rows_async(dqkv + slot_v, sdv, g, b, win, kc * 64, 64, tid, 128);
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    // ---- S = q k^T, dS = dq k^T + q dk^T for this warp's 16 rows x 64 keys
+    float s[8][4] = {}, ds[8][4] = {};
+#pragma unroll
+    for (int kt = 0; kt < 6; kt += 2) {
+      uint32_t qa[2][4], dqa[2][4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        ldsm4(uq + (ar * kDPitch + (kt + h) * 16 + ac) * 2, qa[h][0], qa[h][1], qa[h][2], qa[h][3]);
+        ldsm4(udq + (ar * kDPitch + (kt + h) * 16 + ac) * 2, dqa[h][0], dqa[h][1], dqa[h][2], dqa[h][3]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int key = nt * 8 + (lane & 7), c = (lane >> 3) * 8;
+        uint32_t b0, b1, b2, b3, d0, d1, d2, d3;
+        ldsm4(uk + (key * kDPitch + kt * 16 + c) * 2, b0, b1, b2, b3);
+        ldsm4(udk + (key * kDPitch + kt * 16 + c) * 2, d0, d1, d2, d3);
+        mma16816<F16>(s[nt], qa[0], b0, b1);
+        mma16816<F16>(s[nt], qa[1], b2, b3);
+        mma16816<F16>(ds[nt], dqa[0], b0, b1);
+        mma16816<F16>(ds[nt], dqa[1], b2, b3);
+        mma16816<F16>(ds[nt], qa[0], d0, d1);
+        mma16816<F16>(ds[nt], qa[1], d2, d3);
+      }
+    }
+    // ---- online softmax: row h = 0 (lane / 4) holds s[nt][0..1], row h = 1 (lane / 4 + 8) holds s[nt][2..3]
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float mx = mrow[h];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) mx = fmaxf(mx, fmaxf(s[nt][2 * h], s[nt][2 * h + 1]));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      const float scale = __expf(mrow[h] - mx);
+      mrow[h] = mx;
+      float z = 0.f, e = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float pj = __expf(s[nt][2 * h + j] - mx);
+          s[nt][2 * h + j] = pj;                       // p~
+          ds[nt][2 * h + j] *= pj;                     // p~ dS
+          z += pj;
+          e += ds[nt][2 * h + j];
+        }
+      }
+      z += __shfl_xor_sync(0xffffffffu, z, 1);
+      z += __shfl_xor_sync(0xffffffffu, z, 2);
+      e += __shfl_xor_sync(0xffffffffu, e, 1);
+      e += __shfl_xor_sync(0xffffffffu, e, 2);
+      lrow[h] = fmaf(lrow[h], scale, z);
+      crow[h] = fmaf(crow[h], scale, e);
+#pragma unroll
+      for (int nt = 0; nt < 12; ++nt) {
+        o[nt][2 * h] *= scale; o[nt][2 * h + 1] *= scale;
+        da[nt][2 * h] *= scale; da[nt][2 * h + 1] *= scale;
+      }
+    }
+    // ---- O += p~ v ; dacc += (p~ dS) v + p~ dv      (accumulator pairs of two key octets = one k16 A fragment)
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t pa[4], ea[4];
+      pa[0] = pack_act2<F16>(s[2 * kk][0], s[2 * kk][1]);
+      pa[1] = pack_act2<F16>(s[2 * kk][2], s[2 * kk][3]);
+      pa[2] = pack_act2<F16>(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pa[3] = pack_act2<F16>(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+      ea[0] = pack_act2<F16>(ds[2 * kk][0], ds[2 * kk][1]);
+      ea[1] = pack_act2<F16>(ds[2 * kk][2], ds[2 * kk][3]);
+      ea[2] = pack_act2<F16>(ds[2 * kk + 1][0], ds[2 * kk + 1][1]);
+      ea[3] = pack_act2<F16>(ds[2 * kk + 1][2], ds[2 * kk + 1][3]);
+      const int key = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, c = (lane >> 4) * 8;
+#pragma unroll
+      for (int np = 0; np < 6; ++np) {
+        uint32_t b0, b1, b2, b3, d0, d1, d2, d3;
+        ldsm4_trans(uv + (key * kDPitch + np * 16 + c) * 2, b0, b1, b2, b3);
+        ldsm4_trans(udv + (key * kDPitch + np * 16 + c) * 2, d0, d1, d2, d3);
+        mma16816<F16>(o[2 * np], pa, b0, b1);
+        mma16816<F16>(o[2 * np + 1], pa, b2, b3);
+        mma16816<F16>(da[2 * np], ea, b0, b1);
+        mma16816<F16>(da[2 * np + 1], ea, b2, b3);
+        mma16816<F16>(da[2 * np], pa, d0, d1);
+        mma16816<F16>(da[2 * np + 1], pa, d2, d3);
+      }
+    }
+  }
+  const int D = g.heads * g.hd;
+  const int gq = lane >> 2, t4 = lane & 3;
+  const int row0 = window_token_row(g, b, win, ti + warp * 16 + gq), row1 = window_token_row(g, b, win, ti + warp * 16 + gq + 8);
+  const float inv0 = 1.0f / lrow[0], inv1 = 1.0f / lrow[1];
+  const float c0 = crow[0] * inv0, c1 = crow[1] * inv1;
+#pragma unroll
+  for (int nt = 0; nt < 11; ++nt) {                                   // 11 x 8 = 88 real head-dim columns
+    const int col = head * g.hd + nt * 8 + 2 * t4;
+    const float oa = o[nt][0] * inv0, ob = o[nt][1] * inv0, oc = o[nt][2] * inv1, od = o[nt][3] * inv1;
+    *reinterpret_cast<uint32_t*>(attn2 + static_cast<size_t>(row0) * D + col) = pack_act2<F16>(oa, ob);
+    *reinterpret_cast<uint32_t*>(attn2 + static_cast<size_t>(row1) * D + col) = pack_act2<F16>(oc, od);
+    *reinterpret_cast<uint32_t*>(attn2 + static_cast<size_t>(g.M + row0) * D + col) =
+        pack_act2<F16>(fmaf(-c0, oa, da[nt][0] * inv0), fmaf(-c0, ob, da[nt][1] * inv0));
+    *reinterpret_cast<uint32_t*>(attn2 + static_cast<size_t>(g.M + row1) * D + col) =
+        pack_act2<F16>(fmaf(-c1, oc, da[nt][2] * inv1), fmaf(-c1, od, da[nt][3] * inv1));
+  }
+}
+
 int launch_attention_dual(const void* qkv, const void* dqkv, float* S, float* dS, void* attn2, int B, int gh, int gw,
                           int heads, int hd, int pad, int shift_h, int shift_w, int act_f16, cudaStream_t stream) {
   SWB_REQUIRE(gh % 16 == 0 && gw % 16 == 0 && hd <= 96, "attention_dual: grid %dx%d / head_dim %d unsupported", gh, gw, hd);
@@ -441,6 +588,20 @@ int launch_attention_dual(const void* qkv, const void* dqkv, float* S, float* dS
     attr_done = true;
   }
   SWB_REQUIRE(hd == 88 && pad == 96, "attention_dual: the tensor-core kernels are specialised for head_dim 88 padded to 96");
+  static const bool split = getenv("SWB_DUAL_ATTN_SPLIT") != nullptr;        // tools only: the three-stage A/B path
+  if (!split) {
+    constexpr int kFusedSmem = 6 * 64 * kDPitch * 2;                          // 78 KB: two blocks per SM
+    static bool fused_attr = false;
+    if (!fused_attr) {
+      SWB_CHECK_CUDA(cudaFuncSetAttribute(attn_fused_dual_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem));
+      SWB_CHECK_CUDA(cudaFuncSetAttribute(attn_fused_dual_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem));
+      fused_attr = true;
+    }
+    if (act_f16) attn_fused_dual_kernel<true><<<dim3(4, items), 128, kFusedSmem, stream>>>(q, dq, static_cast<uint16_t*>(attn2), g);
+    else attn_fused_dual_kernel<false><<<dim3(4, items), 128, kFusedSmem, stream>>>(q, dq, static_cast<uint16_t*>(attn2), g);
+    SWB_CHECK_CUDA(cudaGetLastError());
+    return SWB_OK;
+  }
   if (act_f16) attn_scores_dual_kernel<true><<<dim3(16, items), 128, kScoresSmem, stream>>>(q, dq, S, dS, g);
   else attn_scores_dual_kernel<false><<<dim3(16, items), 128, kScoresSmem, stream>>>(q, dq, S, dS, g);
   if (act_f16) attn_out_dual_kernel<true><<<dim3(4, items), 128, kOutSmem, stream>>>(S, dS, q, dq, static_cast<uint16_t*>(attn2), g);
