@@ -43,7 +43,12 @@ def rollout_and_save(ro: EnsembleRollout, store: ForecastStore, x0_std: torch.Te
                      forcings_host: Optional[torch.Tensor] = None, writers: int = 4) -> dict:
     """Advance every trajectory of ``ro`` by ``steps`` and write leads 0..steps of each into ``store`` at
     [ic, member] = ``ro.traj[b]``.  ``x0_std`` [B, n_var, H, W]: standardised initial conditions (host or device).
-    Returns timing counters."""
+    Returns timing counters.
+
+    Host memory: the "trajectory" layout keeps every lead time of a trajectory in one chunk, so all B x (steps+1) fields
+    are held on the host until the rollout ends (the reference holds bs x (steps+1) per batch, generate.py:95); for long
+    rollouts of many resident trajectories (96 x 61 Swift-B states = 53 GB) use the "step" or "numpy" layout, which
+    stream every lead time to disk while the GPU keeps stepping."""
     if steps != store.steps:
         raise ValueError(f"store was created for {store.steps} steps, rollout asked for {steps}")
     B = len(ro.traj)
