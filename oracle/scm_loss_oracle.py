@@ -2,8 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY: imported by tests/ (and nothing else); the product path never calls it.
 Pinned to the reference: ``tests/golden/make_scm_loss_golden.py`` runs the real ``SCMLoss`` and records the loss and its
-gradient with respect to the network output (``tests/golden/scm_loss.npz``); ``tests/test_oracle_golden.py`` checks this
-file against them.
+gradient with respect to the network output, plus the parameter gradients of ``loss.backward()`` for one case per fixture
+(``tests/golden/scm_loss.npz``); ``tests/test_oracle_golden.py`` checks this file against them.
 
 The loss value is a function of the detached tangent target ``g`` only,
 
@@ -79,3 +79,17 @@ def scm_loss(net: Callable, x: torch.Tensor, t: torch.Tensor, z: torch.Tensor, s
     loss = (w * g.square()).sum(dim=1).mean()                           # :253-260 with F - sg(F) = 0, logvar = 0
     cot = -2.0 * w * g / (g.shape[0] * g.shape[2] * g.shape[3])
     return {"loss": loss, "cot": cot, "g": g, "F": F, "dF": dF, "x_t": x_t}
+
+
+def scm_parameter_gradients(net_of: Callable, params: Dict[str, torch.Tensor], x: torch.Tensor, t: torch.Tensor,
+                            z: torch.Tensor, step: int, tangent_warmup_kimg: int, w_lat: torch.Tensor, w_var: torch.Tensor,
+                            sigma_data: float = 1.0) -> Dict[str, torch.Tensor]:
+    """d loss / d parameter of one ``SCMLoss`` evaluation (what ``loss.backward()`` leaves in ``.grad``, trainer.py:206-214):
+    the target of the reverse pass.  ``net_of(p)`` returns the denoiser ``(x_in, t_flat) -> F`` bound to the parameter dict
+    ``p``.  The loss only sees the parameters through ``F_x`` (g is detached, loss.py:241-248), so the gradients are the
+    vector-Jacobian product of the grad-enabled forward (:227) with ``cot = dL/dF_x``."""
+    out = scm_loss(net_of(params), x, t, z, step, tangent_warmup_kimg, w_lat, w_var, sigma_data)
+    leaf = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+    F = net_of(leaf)(out["x_t"] / sigma_data, t.flatten())
+    F.backward(out["cot"])
+    return {k: v.grad for k, v in leaf.items() if v.grad is not None}

@@ -5,7 +5,9 @@ Run in the build container only:    python tests/golden/make_scm_loss_golden.py
 ``SCMLoss.forward`` returns one scalar, but what the backward pass of the training step consumes is its gradient with
 respect to the network output F_x -- the (normalised, detached) tangent target g scaled by the loss weights.  It is
 recorded here with a tensor hook on the output of the reference network's grad-enabled call, together with the loss, on
-the tiny / small fixtures of ``swift_b200.synthetic``.  The loss draws tau and z from the global RNG; both are reproduced
+the tiny / small fixtures of ``swift_b200.synthetic``.  For the first case of each fixture the parameter gradients of
+``loss.backward()`` are recorded too (norm of every tensor, strided samples of nine of them): the target of the reverse
+pass that is not built yet.  The loss draws tau and z from the global RNG; both are reproduced
 by re-seeding and repeating the reference's own calls (``loguniform``, then ``randn_like``) and stored, so a restatement
 can be checked as a deterministic function of (x, condition, t, z, step).
 """
@@ -23,6 +25,10 @@ from make_golden import build_reference, install_shims  # noqa: E402
 
 VARIABLES = ["2m_temperature", "10m_u_component_of_wind", "mean_sea_level_pressure", "geopotential_500",
              "temperature_850", "specific_humidity_700"]
+GRAD_SAMPLES = ["model.head.head.0.weight", "model.transformer.layers.1.1.w1.weight", "model.transformer.layers.0.0.to_qkv.weight",
+                "model.transformer.layers.0.0.scale", "model.transformer.layers.1.0.norm.modulation.weight", "model.pos_embed",
+                "model.patch_embed.emb.weight", "model.latent_embed.l1.weight", "model.auxiliary_embed.weight"]
+GRAD_STRIDE = 31
 NOISE = dict(dist="loguniform", sigma_min=0.02, sigma_max=200.0)       # experiment/era5-swinv2-1.4-scm.yaml:13-16
 
 
@@ -78,6 +84,14 @@ def main():
             out[k + "loss"] = np.array(loss.item(), dtype=np.float64)
             out[k + "F"] = net.outputs[0].numpy()
             out[k + "cot"] = net.grads[0].numpy()
+            if case == 0:
+                # what the reverse pass must deliver: d loss / d parameter (norm of every tensor + strided samples of a few)
+                named = dict(net.module.named_parameters())
+                names = sorted(n for n, p_ in named.items() if p_.grad is not None)
+                out[k + "grad_names"] = np.array(names)
+                out[k + "grad_norms"] = np.array([float(named[n].grad.norm()) for n in names], dtype=np.float64)
+                for n in GRAD_SAMPLES:
+                    out[k + "grad:" + n] = named[n].grad.flatten()[::GRAD_STRIDE].numpy().copy()
             print(k, "loss", loss.item(), "cot norm", float(net.grads[0].norm()))
         out[name + "_w_lat"] = loss_fn.w_lat.numpy()
         out[name + "_w_var"] = loss_fn.w_var.numpy()

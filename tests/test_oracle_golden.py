@@ -118,3 +118,32 @@ def test_scm_loss_and_output_cotangent(golden, name, cfgname):
         _close(o["F"], g[k + "F"])
         _close(o["cot"], g[k + "cot"], tol=1e-5)
     assert so.tangent_warmup(500_000, 3000) == pytest.approx(1 / 6) and so.tangent_warmup(5, 0) == 1.0
+
+
+@pytest.mark.parametrize("name,cfgname", [("tiny", "SWIFT_TINY"), ("small", "SWIFT_SMALL")])
+def test_scm_parameter_gradients_match_reference_backward(golden, name, cfgname):
+    """The target of the reverse pass (not built yet in the CUDA path): d loss / d parameter of the real reference's
+    ``SCMLoss(...).backward()`` -- the norm of EVERY parameter gradient and strided samples of nine tensors -- reproduced by
+    the oracle as the vector-Jacobian product of its forward with cot = dL/dF_x."""
+    from oracle import scm_loss_oracle as so
+    g = golden("scm_loss")
+    c = getattr(syn, cfgname)
+    n_img, (H, W) = c["out_channels"], c["img_resolution"]
+    cfg = orc.make_cfg(**c)
+    p = syn.random_state_dict(c, seed=1)
+    x, cond = syn.synthetic_fields(c, 2, seed=5)
+    w_lat, w_var = so.latitude_weights(H), so.variable_weights(SCM_LOSS_VARIABLES[:n_img])
+    k = f"{name}_0_"
+    step, warm = (int(v) for v in g[k + "step_warm"])
+    grads = so.scm_parameter_gradients(lambda q: (lambda a, b: orc.pass_precond(q, cfg, a, b, cond, 0.6)), p, x,
+                                       torch.from_numpy(g[k + "t"]), torch.from_numpy(g[k + "z"]), step, warm, w_lat, w_var)
+    names = [str(s) for s in g[k + "grad_names"]]
+    assert sorted(names) == sorted("model." + n for n in p)                  # every parameter receives a gradient
+    for nm, ref in zip(names, g[k + "grad_norms"]):
+        got = float(grads[nm[len("model."):]].norm())
+        assert abs(got - ref) < 2e-5 * ref, (nm, got, ref)
+    sampled = [kk for kk in g if kk.startswith(k + "grad:")]
+    assert len(sampled) == 9
+    for kk in sampled:
+        nm = kk.split("grad:")[1][len("model."):]
+        _close(grads[nm].flatten()[::31], g[kk], tol=5e-5)
