@@ -104,3 +104,22 @@ def scm_output_cotangent(net, x: torch.Tensor, t: torch.Tensor, z: torch.Tensor,
                                              cot.data_ptr(), loss.data_ptr(), scratch.data_ptr(), need, stream),
                "scm_tangent_target")
     return {"loss": loss, "cot": cot, "g": g, "F": F, "dF": dF, "x_t": x_t}
+
+
+def hybrid_scm_backward(net_grad: torch.nn.Module, net_cuda, x: torch.Tensor, t: torch.Tensor, z: torch.Tensor, step: int,
+                        condition: Optional[torch.Tensor] = None, auxiliary=None, **loss_kwargs) -> Dict[str, torch.Tensor]:
+    """The backward of one sCM training step with the reverse pass delegated (until this library has one): loss value,
+    tangent target and ``cot = dL/dF_x`` come from the CUDA path (``scm_output_cotangent`` on ``net_cuda``, a PassPrecond
+    around ``swift_b200.swinv2.SwinV2`` holding the same weights), then the grad-capable twin ``net_grad`` -- the
+    reference's ``PassPrecond(SwinV2)`` / its DDP wrapper -- runs the one grad-enabled forward of ``loss.py:227`` and
+    ``F_x.backward(cot)``.  Leaves exactly the ``.grad`` that ``SCMLoss(...)(net, x, step, ...).backward()`` leaves
+    (trainer.py:206-214), without ``torch.func.jvp`` through the eager module; returns the dict of
+    ``scm_output_cotangent`` (``loss`` for logging)."""
+    out = scm_output_cotangent(net_cuda, x, t, z, step, condition=condition, auxiliary=auxiliary, **loss_kwargs)
+    sd = float(getattr(net_cuda, "module", net_cuda).sigma_data)
+    with torch.enable_grad():
+        F_x = net_grad(out["x_t"] / sd, t.to(x.device).reshape(-1), condition, auxiliary)
+    if F_x.shape != out["cot"].shape:
+        raise RuntimeError(f"net_grad returned {tuple(F_x.shape)}, expected {tuple(out['cot'].shape)}")
+    F_x.backward(out["cot"])
+    return out

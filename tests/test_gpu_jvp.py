@@ -158,3 +158,58 @@ def test_scm_output_cotangent_vs_reference_loss_golden(golden, name, cfgname):
         assert abs(float(o["loss"]) - ref_loss) < 1e-2 * ref_loss
     with pytest.raises(KeyError):
         variable_weights(["2m_temperature", "not_a_variable_500"])
+
+
+class _OracleModule(torch.nn.Module):
+    """A grad-capable stand-in for the reference's PassPrecond(SwinV2) (same call signature, same state-dict values),
+    built from the fp32 oracle functions: test infrastructure for the hybrid training step."""
+
+    def __init__(self, sd, ocfg):
+        super().__init__()
+        self.ocfg = ocfg
+        self.names = list(sd)
+        for i, (k, v) in enumerate(sd.items()):
+            self.register_parameter(f"p{i}", torch.nn.Parameter(v.clone()))
+
+    def params(self):
+        return {k: getattr(self, f"p{i}") for i, k in enumerate(self.names)}
+
+    def forward(self, x, t, condition=None, auxiliary=None):
+        from oracle import swinv2_oracle as orc
+        return orc.pass_precond(self.params(), self.ocfg, x, t, condition, auxiliary)
+
+
+def test_hybrid_scm_training_step_gradients_vs_reference_backward(golden):
+    """scm_target.hybrid_scm_backward: cot from the CUDA path, reverse pass by a grad-capable twin -> the parameter
+    gradients of the REAL reference's SCMLoss(...).backward() (tests/golden/scm_loss.npz): the norm of every tensor's
+    gradient and strided samples of nine tensors."""
+    from oracle import swinv2_oracle as orc
+    from swift_b200 import synthetic as syn
+    from swift_b200.scm_target import hybrid_scm_backward, latitude_weights, variable_weights
+    from test_gpu_forward import build_net
+    from test_oracle_golden import SCM_LOSS_VARIABLES
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = golden("scm_loss")
+    cfg = syn.SWIFT_TINY
+    n_img, (H, W) = cfg["out_channels"], cfg["img_resolution"]
+    net, sd = build_net(cfg, img_channels=n_img)
+    twin = _OracleModule(sd, orc.make_cfg(**cfg)).cuda()
+    x, cond = (v.cuda() for v in syn.synthetic_fields(cfg, 2, seed=5))
+    k = "tiny_0_"
+    step, warm = (int(v) for v in g[k + "step_warm"])
+    out = hybrid_scm_backward(twin, net, x, torch.from_numpy(g[k + "t"]).cuda(), torch.from_numpy(g[k + "z"]).cuda(), step,
+                              condition=cond, auxiliary=0.6, tangent_warmup_kimg=warm, w_lat=latitude_weights(H, "cuda"),
+                              w_var=variable_weights(SCM_LOSS_VARIABLES[:n_img], "cuda"))
+    assert abs(float(out["loss"]) - float(g[k + "loss"])) < 1e-2 * float(g[k + "loss"])
+    grads = {name: p.grad for name, p in twin.params().items()}
+    worst = 0.0
+    for nm, ref in zip((str(s) for s in g[k + "grad_names"]), g[k + "grad_norms"]):
+        got = float(grads[nm[len("model."):]].norm())
+        worst = max(worst, abs(got - ref) / ref)
+    worst_s = 0.0
+    for kk in g:
+        if kk.startswith(k + "grad:"):
+            nm = kk.split("grad:")[1][len("model."):]
+            worst_s = max(worst_s, _rel(grads[nm].flatten()[::31].cpu(), torch.from_numpy(g[kk])))
+    print(f"hybrid sCM step (tiny): worst gradient-norm error {worst:.3e}, worst sampled-gradient rel-L2 {worst_s:.3e}")
+    assert worst < 5e-2 and worst_s < 5e-2
