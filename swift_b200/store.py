@@ -292,4 +292,7 @@ class ForecastStore:
     def coordinate(self, name: str) -> np.ndarray:
         with open(os.path.join(self.path, name, ".zarray")) as f:
             za = json.load(f)
-        return np.fromfile(os.path.join(self.path, name, "0"), dtype=za["dtype"]).reshape(za["shape"])
+        file = os.path.join(self.path, name, "0")
+        if not os.path.exists(file):                               # an empty axis has no chunk
+            return np.zeros(za["shape"], dtype=za["dtype"])
+        return np.fromfile(file, dtype=za["dtype"]).reshape(za["shape"])

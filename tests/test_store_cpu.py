@@ -134,3 +134,48 @@ def test_errors(tmp_path):
         st.write_trajectories(0, 2, _rollout(1, 2, len(VARS), 2, 2, 0))
     with pytest.raises(ValueError):
         st.write_trajectories(0, 0, _rollout(1, 3, len(VARS), 2, 2, 0))
+
+
+def test_empty_store_and_single_lead(tmp_path):
+    """Edge cases: no initial conditions at all (an empty --samples selection) and a zero-step rollout (lead 0 only)."""
+    st = ForecastStore.create(str(tmp_path / "e.zarr"), VARS, 0, 3, 2, np.arange(4), np.arange(4))
+    assert st.read("z").shape == (0, 3, 3, 3, 4, 4) and st.read_all().shape == (0, 3, 3, len(VARS), 4, 4)
+    assert st.coordinate("time").shape == (0,)
+    one = ForecastStore.create(str(tmp_path / "o.zarr"), VARS, 1, 1, 0, np.arange(4), np.arange(4), layout="step")
+    r = _rollout(1, 0, len(VARS), 4, 4, seed=1)
+    one.write_trajectories(0, 0, r)
+    np.testing.assert_array_equal(one.read_all()[0, 0], r[0])
+
+
+def test_round_trip_property():
+    """Any (layout, batch, ragged n_ic, variable mix): what is written per (ic, member) block is what read_all returns, and
+    every chunk file has exactly the size the .zarray metadata promises."""
+    import tempfile
+    from hypothesis import given, settings, strategies as hs
+
+    @settings(max_examples=25, deadline=None)
+    @given(layout=hs.sampled_from(["trajectory", "step"]), batch=hs.integers(1, 3), n_ic=hs.integers(1, 5),
+           members=hs.integers(1, 3), steps=hs.integers(0, 3), n_lev=hs.integers(0, 3), n_single=hs.integers(0, 2),
+           level=hs.sampled_from([0, 1]), seed=hs.integers(0, 10_000))
+    def run(layout, batch, n_ic, members, steps, n_lev, n_single, level, seed):
+        variables = [f"s{i}" for i in range(n_single)] + [f"p_{100 * (k + 1)}" for k in range(n_lev)]
+        if not variables:
+            variables = ["only"]
+        h, w = 3, 4
+        with tempfile.TemporaryDirectory() as d:
+            st = ForecastStore.create(os.path.join(d, "f.zarr"), variables, n_ic, members, steps, np.arange(h), np.arange(w),
+                                      layout=layout, batch=batch, compress_level=level)
+            full = _rollout(n_ic * members, steps, len(variables), h, w, seed).reshape(n_ic, members, steps + 1,
+                                                                                       len(variables), h, w)
+            b = st.batch
+            for m in range(members):
+                for s0 in range(0, n_ic, b):
+                    st.write_trajectories(s0, m, full[s0:s0 + b, m])
+            np.testing.assert_array_equal(st.read_all(), full)
+            if level == 0:
+                for var in st.channels:
+                    want = int(np.prod(st.chunk_shape(var))) * 4
+                    files = [f for f in os.listdir(os.path.join(d, "f.zarr", var)) if not f.startswith(".")]
+                    assert files and all(os.path.getsize(os.path.join(d, "f.zarr", var, f)) == want for f in files)
+
+    run()
