@@ -231,11 +231,15 @@ def run_ours(args):
     traj = shard_trajectories(MEMBERS, n_ic, rank, world)
     B = len(traj)
     total_steps = args.warmup + args.steps + 2
-    forc_host = syn.synthetic_forcings(cfg, total_steps, seed=0).pin_memory()
+    # forcings: a TIME-indexed table; IC j is the analysis at 6 h file index j (consecutive dataset indices, what the
+    # reference's DataLoader yields), so trajectory (m, j) reads row j + step at every step (generate.py:105-110)
+    ic_times = {j: j for j in range(n_ic)}
+    forc_host = syn.synthetic_forcings(cfg, n_ic + total_steps, seed=0).pin_memory()
     forc_dev = forc_host.to(dev)
     norm = Normalizers.synthetic(syn.IMG_CHANNELS, dev, diff=0.1)
     skw = dict(num_steps=20, sigma_min=0.02, sigma_max=200.0, auxiliary=0.6) if args.solver == "2s" else None
-    ro = EnsembleRollout(net, norm, forc_dev, traj, solver=args.solver, solver_kwargs=skw, use_graph=not args.no_graph)
+    ro = EnsembleRollout(net, norm, forc_dev, traj, solver=args.solver, solver_kwargs=skw, use_graph=not args.no_graph,
+                         ic_times=ic_times, interval=6)
     stats = None
     if not args.no_stats and len(traj) % MEMBERS == 0:
         # eval/metrics.py on the device: per-step sufficient statistics inside the step's CUDA graph, one NCCL all_gather
@@ -298,18 +302,18 @@ def run_ours(args):
         checksum[0] += float(view[0, 0, 0, 0]) + float(view[-1, -1, -1, -1])
 
     ro.set_state(x0.to(dev, non_blocking=True))                                    # H2D: initial conditions
-    ro.run_to_host(1, out_host, forc_host, first_forcing=0, on_host=consume)       # one untimed step
+    ro.run_to_host(1, out_host, forc_host, on_host=consume)                        # one untimed step
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
     e2.record()
-    ro.run_to_host(e2e_steps, out_host, forc_host, first_forcing=1, on_host=consume)
+    ro.run_to_host(e2e_steps, out_host, forc_host, on_host=consume)
     e3.record()
     wall_ms = (time.perf_counter() - t_wall0) * 1e3
     barrier()
     e2e_ms = max_over_ranks(max(e2.elapsed_time(e3), wall_ms))
     e2e_value = B * world * e2e_steps / (e2e_ms / 1e3)
-    h2d = forc_host[0].numel() * 4
+    h2d = len(ro.forcing_rows(1)) * forc_host[0].numel() * 4       # one forcings row per distinct IC valid time per step
     d2h = out_host[0].numel() * 4
     if not math.isfinite(checksum[0]):
         raise RuntimeError("end-to-end leg produced non-finite output")

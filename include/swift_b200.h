@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SWB200_ABI_VERSION 12
+#define SWB200_ABI_VERSION 13
 #if defined(__GNUC__)
 #define SWB200_API __attribute__((visibility("default")))
 #else
@@ -196,9 +196,13 @@ SWB200_API int swb200_trace_report(char* buf, size_t buf_bytes);
  * torch.Generator of generate.py:83 / factory.py:52-56 with a stream that depends only on (seed, step, element). */
 SWB200_API int swb200_rollout_noise(float* latents, const uint64_t* seeds, const int32_t* step, int B, int64_t n_per_sample,
                          void* stream);
-/* cond[b, state_channels + f, :] = table[*step, f, :] for f < n_forcings (standardised forcings, generate.py:100-117) */
+/* cond[b, state_channels + f, :] = table[base[b] + *step * stride, f, :] for f < n_forcings: the standardised forcings the
+ * reference fetches per sample and step as `get_forcings(j + i*interval//6) for j in idx` (generate.py:100-117).  table:
+ * fp32 [n_times, n_forcings, hw], indexed by time (6 h file index); base: int32 [B], the table row of every trajectory's
+ * initial time (NULL = 0 for all); stride = interval // 6.  Rows outside the table are written as NaN (never read). */
 SWB200_API int swb200_rollout_forcings(float* cond, int total_channels, int state_channels, const float* table, int n_forcings,
-                            const int32_t* step, int B, int hw, void* stream);
+                            int n_times, const int32_t* base, int stride, const int32_t* step, int B, int hw,
+                            void* stream);
 /* *step += 1 (device-side, so a captured graph of one step can be replayed for the whole rollout) */
 SWB200_API int swb200_rollout_advance(int32_t* step, void* stream);
 
@@ -241,10 +245,12 @@ SWB200_API int swb200_scm_tangent_target(const float* F, const float* dF, const 
  * Writes, per (ic, var), the four latitude-weighted sums from which the reference's scores follow
  *   [0] sum w (mean_n p - y)^2   [1] sum_n sum w |p_n - y|   [2] sum_{i<j} sum w |p_i - p_j|   [3] sum w var_n(p)
  * as fp64 at out[(step ? *step : 0) * out_stride + (ic * n_var + var) * 4 + k]; `step` is a DEVICE pointer (the
- * rollout's step counter) so the call can sit inside the replayed CUDA graph of a 6 h step.
+ * rollout's step counter) so the call can sit inside the replayed CUDA graph of a 6 h step; `out` then has n_steps rows
+ * and a counter outside [0, n_steps) writes nothing.
  *   rmse = mean_ic sqrt([0] / HW)    crps = mean_ic([1] / (N HW) - [2] / (N (N-1) HW))    ssr = mean_ic sqrt([3] / HW) / rmse */
 SWB200_API int swb200_ensemble_stats(const float* phys, const float* truth, const float* w_lat, int n_ic, int members,
-                          int n_var, int H, int W, const int32_t* step, int out_stride, double* out, void* stream);
+                          int n_var, int H, int W, const int32_t* step, int n_steps, int out_stride, double* out,
+                          void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SWB_LIB", os.path.join(HERE, "libswift_b200.so"))   # SWB_LIB: A/B builds (tools only)
 
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 # Every symbol ``include/swift_b200.h`` declares; tests check the library exports exactly these.
 EXPORTS = (
@@ -76,12 +76,14 @@ def _declare(lib):
         "swb200_window_attention": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                               C.c_int, _vp]),
         "swb200_rollout_noise": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int64, _vp]),
-        "swb200_rollout_forcings": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp]),
+        "swb200_rollout_forcings": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int,
+                                              C.c_int, _vp]),
         "swb200_rollout_advance": (C.c_int, [_vp, _vp]),
         "swb200_ln_workspace_bytes": (_sz, [C.c_int, C.c_int]),
         "swb200_gemm_ln_residual": (C.c_int, [C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int,
                                               C.c_int, _vp, C.c_int, _vp]),
-        "swb200_ensemble_stats": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp]),
+        "swb200_ensemble_stats": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int,
+                                            _vp, _vp]),
         "swb200_jvp_workspace_bytes": (_sz, [MP]),
         "swb200_conditioning_jvp_scratch_bytes": (_sz, [MP, C.c_int]),
         "swb200_conditioning_jvp": (C.c_int, [MP, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

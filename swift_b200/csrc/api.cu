@@ -701,17 +701,20 @@ SWB200_API int swb200_rollout_noise(float* latents, const uint64_t* seeds, const
 }
 
 SWB200_API int swb200_rollout_forcings(float* cond, int total_channels, int state_channels, const float* table, int n_forcings,
-                            const int32_t* step, int B, int hw, void* stream) {
+                            int n_times, const int32_t* base, int stride, const int32_t* step, int B, int hw,
+                            void* stream) {
   SWB_REQUIRE(cond && table && step && B > 0, "swb200_rollout_forcings: NULL pointer or B=%d", B);
-  return launch_rollout_forcings(cond, total_channels, state_channels, table, n_forcings, step, B, hw,
+  return launch_rollout_forcings(cond, total_channels, state_channels, table, n_forcings, n_times, base, stride, step, B, hw,
                                  static_cast<cudaStream_t>(stream));
 }
 
 SWB200_API int swb200_ensemble_stats(const float* phys, const float* truth, const float* w_lat, int n_ic, int members,
-                                     int n_var, int H, int W, const int32_t* step, int out_stride, double* out, void* stream) {
+                                     int n_var, int H, int W, const int32_t* step, int n_steps, int out_stride, double* out,
+                                     void* stream) {
   SWB_REQUIRE(phys && truth && w_lat && out, "swb200_ensemble_stats: NULL pointer");
+  SWB_REQUIRE(step == nullptr || n_steps > 0, "swb200_ensemble_stats: n_steps %d with a device step counter", n_steps);
   SWB_REQUIRE(step == nullptr || out_stride >= n_ic * n_var * 4, "swb200_ensemble_stats: out_stride %d < n_ic*n_var*4", out_stride);
-  return launch_ensemble_stats(phys, truth, w_lat, n_ic, members, n_var, H, W, step, out_stride, out,
+  return launch_ensemble_stats(phys, truth, w_lat, n_ic, members, n_var, H, W, step, n_steps, out_stride, out,
                                static_cast<cudaStream_t>(stream));
 }
 

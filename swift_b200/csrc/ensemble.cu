@@ -20,9 +20,10 @@ constexpr int kMaxMembers = 32;
 template <int NMAX>
 __global__ void __launch_bounds__(256) ensemble_stats_kernel(const float* __restrict__ phys, const float* __restrict__ truth,
                                                              const float* __restrict__ w_lat, int N, int V, int H, int W,
-                                                             const int* __restrict__ step, int out_stride,
-                                                             double* __restrict__ out) {
+                                                             const int* __restrict__ step, int n_steps,
+                                                             int out_stride, double* __restrict__ out) {
   const int v = blockIdx.x, ic = blockIdx.y;
+  if (step && (*step < 0 || *step >= n_steps)) return;      // a row outside `out` (host bookkeeping error): never write
   const size_t hw = static_cast<size_t>(H) * W;
   const float* p0 = phys + (static_cast<size_t>(ic) * N * V + v) * hw;
   const size_t mstride = static_cast<size_t>(V) * hw;
@@ -78,14 +79,14 @@ __global__ void __launch_bounds__(256) ensemble_stats_kernel(const float* __rest
 }
 
 int launch_ensemble_stats(const float* phys, const float* truth, const float* w_lat, int n_ic, int members, int V, int H,
-                          int W, const int* step, int out_stride, double* out, cudaStream_t stream) {
+                          int W, const int* step, int n_steps, int out_stride, double* out, cudaStream_t stream) {
   SWB_REQUIRE(members >= 1 && members <= kMaxMembers, "ensemble_stats: %d members unsupported (1..%d)", members, kMaxMembers);
   SWB_REQUIRE(n_ic > 0 && V > 0 && H > 0 && W > 0, "ensemble_stats: empty problem");
   dim3 grid(V, n_ic);
   if (members <= 16)
-    ensemble_stats_kernel<16><<<grid, 256, 0, stream>>>(phys, truth, w_lat, members, V, H, W, step, out_stride, out);
+    ensemble_stats_kernel<16><<<grid, 256, 0, stream>>>(phys, truth, w_lat, members, V, H, W, step, n_steps, out_stride, out);
   else
-    ensemble_stats_kernel<32><<<grid, 256, 0, stream>>>(phys, truth, w_lat, members, V, H, W, step, out_stride, out);
+    ensemble_stats_kernel<32><<<grid, 256, 0, stream>>>(phys, truth, w_lat, members, V, H, W, step, n_steps, out_stride, out);
   SWB_CHECK_CUDA(cudaGetLastError());
   return SWB_OK;
 }

@@ -42,8 +42,8 @@ int launch_window_attention_tc(const void* qkv, void* out, int B, int gh, int gw
 // rollout glue (rollout.cu)
 int launch_rollout_noise(float* latents, const unsigned long long* seeds, const int* step, int B,
                          long long n_per_sample, cudaStream_t stream);
-int launch_rollout_forcings(float* cond, int total_ch, int state_ch, const float* table, int n_forc, const int* step,
-                            int B, int hw, cudaStream_t stream);
+int launch_rollout_forcings(float* cond, int total_ch, int state_ch, const float* table, int n_forc, int n_times,
+                            const int* base, int stride, const int* step, int B, int hw, cudaStream_t stream);
 int launch_rollout_advance(int* step, cudaStream_t stream);
 
 // forward-mode tangent companions (tangent.cu); "2" buffers hold primal rows 0..M-1 followed by tangent rows M..2M-1
@@ -60,7 +60,7 @@ int launch_conditioning_dual(const CondWeights& w, const float* t, const float* 
 
 // ensemble verification statistics (ensemble.cu): out[(*step) * out_stride + (ic * V + v) * 4 + k]
 int launch_ensemble_stats(const float* phys, const float* truth, const float* w_lat, int n_ic, int members, int V, int H,
-                          int W, const int* step, int out_stride, double* out, cudaStream_t stream);
+                          int W, const int* step, int n_steps, int out_stride, double* out, cudaStream_t stream);
 
 // sCM training-loss glue (scm_target.cu)
 int launch_scm_noised_inputs(const float* x, const float* z, const float* t, int B, int C, int H, int W, float* x_t,

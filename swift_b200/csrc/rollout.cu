@@ -55,23 +55,40 @@ int launch_rollout_noise(float* latents, const unsigned long long* seeds, const 
   return SWB_OK;
 }
 
-// cond[b, state_ch + f, :] = table[step, f, :]   (the reference appends standardised forcings every step,
-// generate.py:100-117; here they come from a pre-staged [steps, n_forc, H*W] device table)
+// cond[b, state_ch + f, :] = table[base[b] + step * stride, f, :]
+// The reference appends, every step i and for every sample of the batch, the standardised forcings of the file
+// `j + i * interval // 6` where j is the dataset (time) index of that sample's initial condition (generate.py:100-117):
+// ICs have different valid times, so the table is indexed by TIME (6 h file index relative to its first row) and every
+// trajectory carries the row of its initial time in `base` (NULL: every trajectory starts at row 0).  A row outside the
+// table is a host-side bookkeeping error (the host checks before launching); the kernel then writes NaN, never reads
+// out of bounds.
 __global__ void __launch_bounds__(256) rollout_forcings_kernel(float* __restrict__ cond, int total_ch, int state_ch,
-                                                               const float* __restrict__ table, int n_forc,
+                                                               const float* __restrict__ table, int n_forc, int n_times,
+                                                               const int* __restrict__ base, int stride,
                                                                const int* __restrict__ step, int hw4) {
   const int b = blockIdx.z, f = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= hw4) return;
-  const float4 v = __ldg(reinterpret_cast<const float4*>(table + (static_cast<size_t>(*step) * n_forc + f) * hw4 * 4) + i);
+  const long long row = static_cast<long long>(base ? base[b] : 0) + static_cast<long long>(*step) * stride;
+  float4 v;
+  if (row < 0 || row >= n_times) {
+    const float nan = __int_as_float(0x7fc00000);
+    v = make_float4(nan, nan, nan, nan);
+  } else {
+    v = __ldg(reinterpret_cast<const float4*>(table + (static_cast<size_t>(row) * n_forc + f) * hw4 * 4) + i);
+  }
   reinterpret_cast<float4*>(cond + (static_cast<size_t>(b) * total_ch + state_ch + f) * hw4 * 4)[i] = v;
 }
 
-int launch_rollout_forcings(float* cond, int total_ch, int state_ch, const float* table, int n_forc, const int* step,
-                            int B, int hw, cudaStream_t stream) {
-  SWB_REQUIRE(hw % 4 == 0 && state_ch + n_forc <= total_ch, "rollout_forcings: bad channel layout");
+int launch_rollout_forcings(float* cond, int total_ch, int state_ch, const float* table, int n_forc, int n_times,
+                            const int* base, int stride, const int* step, int B, int hw, cudaStream_t stream) {
+  SWB_REQUIRE(hw % 4 == 0 && state_ch + n_forc <= total_ch && n_times > 0 && stride >= 0,
+              "rollout_forcings: bad channel layout / table (hw=%d, channels %d+%d of %d, %d rows, stride %d)", hw,
+              state_ch, n_forc, total_ch, n_times, stride);
+  if (n_forc == 0) return SWB_OK;
   dim3 grid((hw / 4 + 255) / 256, n_forc, B);
-  rollout_forcings_kernel<<<grid, 256, 0, stream>>>(cond, total_ch, state_ch, table, n_forc, step, hw / 4);
+  rollout_forcings_kernel<<<grid, 256, 0, stream>>>(cond, total_ch, state_ch, table, n_forc, n_times, base, stride, step,
+                                                    hw / 4);
   SWB_CHECK_CUDA(cudaGetLastError());
   return SWB_OK;
 }

@@ -5,6 +5,7 @@ PyTorch is used for device memory and streams only; every FLOP of the forward ru
 from __future__ import annotations
 
 import ctypes as C
+import itertools
 import math
 from typing import Dict, Optional, Tuple
 
@@ -19,8 +20,12 @@ def _aligned_buffer(nbytes: int, device: torch.device, align: int = 1024) -> Tup
     return buf, base
 
 
+_GENERATION = itertools.count(1)
+
+
 class Engine:
-    """One packed SwinV2 denoiser on one GPU."""
+    """One packed SwinV2 denoiser on one GPU.  ``generation`` is unique per Engine object of the process: whatever caches
+    device pointers into an engine (captured CUDA graphs, conditioning vectors) keys on it, never on ``id()``."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], geom: packing.Geometry, device: torch.device,
                  split_embed: bool = True, split_head: bool = True, max_chunk: int = 8, act_fp16: bool = True,
@@ -30,6 +35,7 @@ class Engine:
         self.lib = _lib.lib()
         self.geom = geom
         self.device = device
+        self.generation = next(_GENERATION)
         with torch.cuda.device(device):
             self.model, self._keep = packing.pack(state_dict, geom, device, split_embed, split_head, act_fp16,
                                                    gemm_tile, attn_impl, fuse_ln)

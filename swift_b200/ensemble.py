@@ -61,7 +61,7 @@ class EnsembleStatistics:
         stride = self.n_ic * self.n_var * 4
         _lib.check(_lib.lib().swb200_ensemble_stats(phys.data_ptr(), truth.data_ptr(), self.w_lat.data_ptr(), self.n_ic,
                                                     self.members, self.n_var, self.res[0], self.res[1],
-                                                    _lib.ptr(step_dev), stride, out.data_ptr(),
+                                                    _lib.ptr(step_dev), self.steps, stride, out.data_ptr(),
                                                     torch.cuda.current_stream().cuda_stream), "ensemble_stats")
 
     # ------------------------------------------------------------------ exchange

@@ -144,12 +144,14 @@ def main(argv: Optional[Sequence[str]] = None) -> None:
         args.output, "numpy", variables, args.ics, args.members, args.steps, (H, W))
     traj = shard_trajectories(args.members, args.ics, rank, world)
     x0 = torch.stack([syn.synthetic_fields(cfg, 1, seed=j)[1][0, :n_var] for _, j in traj]) if traj else None
-    forc = syn.synthetic_forcings(cfg, args.steps + 1, seed=0, n_forcings=n_forc)
+    stride = args.interval // 6
+    ic_times = {j: j for j in range(args.ics)}                                # IC j = the analysis at 6 h file index j
+    forc = syn.synthetic_forcings(cfg, args.ics + args.steps * stride + 1, seed=0, n_forcings=n_forc)
     info = {"trajectories": 0}
     if traj:
         skw = dict(num_steps=20, sigma_min=0.02, sigma_max=200.0, auxiliary=0.6) if args.solver == "2s" else None
         ro = EnsembleRollout(net, Normalizers.synthetic(n_var, dev, diff=0.1), forc.to(dev), traj, solver=args.solver,
-                             solver_kwargs=skw)
+                             solver_kwargs=skw, ic_times=ic_times, interval=args.interval)
         info = rollout_and_save(ro, store, x0, args.steps, forc.pin_memory())
     if world > 1:
         dist.barrier()

@@ -19,14 +19,16 @@ Differences from the reference, all documented in DESIGN.md:
   * every trajectory owns its noise stream: Philox4x32-10 keyed by ``trajectory_seed(member, ic)`` with counter
     (element, step), so a trajectory's result does not depend on world size or batching (the reference's per-member
     ``torch.Generator`` is consumed in batch order);
-  * forcings are pre-staged on the device as a [steps, n_forcings, H, W] table instead of one HDF5 read per sample
-    per step on the main thread.
+  * forcings are pre-staged on the device as a TIME-indexed [n_times, n_forcings, H, W] table (row = 6 h file index)
+    instead of one HDF5 read per sample per step on the main thread; trajectory b reads row
+    ``ic_times[ic_b] + step * (interval // 6)`` -- the reference's ``get_forcings(j + int(i * interval // 6)) for j in
+    idx`` (generate.py:105-110), where j is the dataset (time) index of the sample's initial condition.
 """
 from __future__ import annotations
 
 import ctypes as C
 from dataclasses import dataclass
-from typing import Callable, List, Optional, Sequence, Tuple
+from typing import Callable, Dict, List, Optional, Sequence, Tuple, Union
 
 import torch
 
@@ -117,13 +119,40 @@ class EnsembleRollout:
 
     def __init__(self, net, norm: Normalizers, forcings_std: torch.Tensor, trajectories: Sequence[Tuple[int, int]],
                  solver: str = "scm", solver_kwargs: Optional[dict] = None, use_graph: bool = True,
-                 noise: Optional["ReferenceNoise"] = None, residual: bool = True):
+                 noise: Optional["ReferenceNoise"] = None, residual: bool = True,
+                 ic_times: Union[None, Sequence[int], Dict[int, int]] = None, interval: int = 6):
+        """``forcings_std`` [n_times, n_forc, H, W]: standardised forcings indexed by time (one row per 6 h file).
+        ``ic_times[j]``: the row that holds the forcings valid at the initial time of IC j (the reference's dataset index
+        of that sample, generate.py:108) -- a sequence indexed by IC or a dict; ``interval``: hours per step (6, 12, 24:
+        generate.py:31), so trajectory (m, j) reads row ``ic_times[j] + step * interval // 6`` at lead ``step``.
+        ICs have different valid times in the reference, so ``ic_times`` is mandatory as soon as the trajectories span
+        more than one IC (pass zeros for ICs that share one valid time)."""
         self.net = net
         self.residual = bool(residual)          # data/defaults.yaml:7; False = the network predicts the next state itself
         self.norm = norm
-        self.forcings = forcings_std.contiguous()   # [steps(+), n_forc, H, W] standardised, on device
+        self.forcings = forcings_std.contiguous()   # [n_times, n_forc, H, W] standardised, on device, indexed by time
         self.traj = list(trajectories)
         self.device = forcings_std.device
+        if self.forcings.dim() != 4:
+            raise ValueError(f"forcings_std must be [n_times, n_forc, H, W], got {tuple(self.forcings.shape)}")
+        if interval % 6 != 0 or interval <= 0:
+            raise ValueError(f"interval must be a positive multiple of 6 hours, got {interval}")
+        self.stride = int(interval) // 6                                           # generate.py:109
+        ics = sorted({j for _, j in self.traj})
+        if ic_times is None:
+            if len(ics) > 1:
+                raise ValueError(f"the trajectories span {len(ics)} initial conditions: pass ic_times (the forcings-table row "
+                                 "of every IC's initial time; the reference reads get_forcings(j + i*interval//6) per IC j, "
+                                 "generate.py:105-110)")
+            ic_times = {j: 0 for j in ics}
+        try:
+            base = [int(ic_times[j]) for _, j in self.traj]
+        except (KeyError, IndexError) as e:
+            raise ValueError(f"ic_times has no entry for an initial condition of this rank: {e}") from None
+        if base and (min(base) < 0 or max(base) >= self.forcings.shape[0]):
+            raise ValueError(f"ic_times rows {min(base)}..{max(base)} outside the {self.forcings.shape[0]}-row forcings table")
+        self._base_host = base
+        self.base = torch.tensor(base, dtype=torch.int32, device=self.device)
         self.diffusion = DiffusionSampler(net)
         kw = dict(num_steps=1, sigma_min=0.02, sigma_max=200.0, auxiliary=0.6)      # generate.py:255-260
         kw.update(solver_kwargs or {})
@@ -155,6 +184,7 @@ class EnsembleRollout:
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._glue = RolloutGlue(self.cond, norm.x_std, norm.x_mean, norm.diff_std, self.phys, norm.zero_channel)
         self._cond_vecs = None
+        self._engine_gen = -1                   # Engine.generation the graph / conditioning vectors were made for
         self._stats = None
         self._truth: Optional[torch.Tensor] = None
 
@@ -176,9 +206,29 @@ class EnsembleRollout:
     # ------------------------------------------------------------------ state
     def set_state(self, x_std: torch.Tensor, step: int = 0) -> None:
         """x_std: [B, n_var, H, W] standardised initial conditions, one row per trajectory."""
+        if step < 0:
+            raise ValueError(f"step must be >= 0, got {step}")
         self.cond[:, : self.n_var].copy_(x_std)
         self.step_dev.fill_(step)
         self._step_host = int(step)
+
+    def forcing_rows(self, step: Optional[int] = None) -> List[int]:
+        """Distinct rows of the forcings table read at lead ``step`` (default: the coming step)."""
+        s = self._step_host if step is None else int(step)
+        return sorted({b + s * self.stride for b in self._base_host})
+
+    def _check_bounds(self, table_needed: bool) -> None:
+        """Raise BEFORE launching when the coming step would leave the forcings table or the statistics buffer (the
+        kernels read / write rows addressed by the device step counter)."""
+        if table_needed and self.forcings.shape[1] > 0:
+            rows = self.forcing_rows()
+            if rows and rows[-1] >= self.forcings.shape[0]:
+                raise RuntimeError(f"step {self._step_host} needs forcings row {rows[-1]} but the table has "
+                                   f"{self.forcings.shape[0]} rows (ic_times up to {max(self._base_host)}, stride "
+                                   f"{self.stride})")
+        if self._stats is not None and self._step_host >= self._stats.steps:
+            raise RuntimeError(f"step {self._step_host} exceeds the {self._stats.steps} steps the attached "
+                               "EnsembleStatistics was sized for")
 
     # ------------------------------------------------------------------ pieces of one step
     def _stream(self) -> int:
@@ -197,6 +247,7 @@ class EnsembleRollout:
         hw = self.res[0] * self.res[1]
         _lib.check(self.lib.swb200_rollout_forcings(self.cond.data_ptr(), self.cond.shape[1], self.n_var,
                                                     self.forcings.data_ptr(), self.forcings.shape[1],
+                                                    self.forcings.shape[0], self.base.data_ptr(), self.stride,
                                                     self.step_dev.data_ptr(), len(self.traj), hw, self._stream()),
                    "forcings")
 
@@ -229,7 +280,12 @@ class EnsembleRollout:
     def step(self, forcings_i: Optional[torch.Tensor] = None) -> torch.Tensor:
         """One 6 h advance of every trajectory; returns the physical state [B, n_var, H, W] (a view of a static
         buffer that the next step overwrites)."""
+        self._check_bounds(table_needed=forcings_i is None)
         if self.fused and forcings_i is None:
+            gen = self.model.engine().generation
+            if gen != self._engine_gen:          # weights re-packed / knobs changed: the captured graph and the cached
+                self._graph, self._cond_vecs = None, None      # conditioning vectors point into the old engine's buffers
+                self._engine_gen = gen
             if self._cond_vecs is None:
                 self._cond_vecs = self.diffusion._conditioning(self.model, float(torch.tensor([torch.pi / 2])),
                                                                self.solver_kwargs["auxiliary"], len(self.traj),
@@ -280,15 +336,20 @@ class EnsembleRollout:
 
     @torch.no_grad()
     def run_to_host(self, steps: int, out_host: torch.Tensor, forcings_host: Optional[torch.Tensor] = None,
-                    first_forcing: int = 0, on_host: Optional[Callable[[int, torch.Tensor], None]] = None) -> None:
-        """The loop of generate.py:97-136 with HOST buffers: per step the standardised forcings of that step come from
-        ``forcings_host`` [>= first_forcing + steps, n_forc, H, W] (pinned) and the new physical state of every trajectory
+                    on_host: Optional[Callable[[int, torch.Tensor], None]] = None) -> None:
+        """The loop of generate.py:97-136 with HOST buffers: per step the standardised forcings every IC needs at that
+        lead (rows ``ic_times[j] + step * interval // 6`` of ``forcings_host``, a pinned time-indexed table with the
+        device table's shape) are copied host -> device -- what the reference fetches with ``get_forcings`` per sample,
+        de-duplicated over the members of an IC -- and the new physical state of every trajectory
         lands in ``out_host`` [steps or 2, B, n_var, H, W] (pinned; with 2 slots they are used alternately).
         The reference blocks on ``.cpu()`` every step (generate.py:129); here the device->host copy of step i runs on a
         copy stream while step i+1 computes (the state is first parked in a device staging buffer, because the next
         step overwrites ``phys``).  ``on_host(i, view)`` is called once step i's data is complete in host memory."""
         if out_host.dim() != 5 or tuple(out_host.shape[1:]) != tuple(self.phys.shape) or not out_host.is_pinned():
             raise RuntimeError(f"out_host must be a pinned [slots, {', '.join(map(str, self.phys.shape))}] tensor")
+        if forcings_host is not None and tuple(forcings_host.shape) != tuple(self.forcings.shape):
+            raise RuntimeError(f"forcings_host must mirror the device table {tuple(self.forcings.shape)}, got "
+                               f"{tuple(forcings_host.shape)}")
         slots = out_host.shape[0]
         if slots < min(2, steps):
             raise RuntimeError("out_host needs at least 2 slots (one is written while the other is consumed)")
@@ -300,7 +361,9 @@ class EnsembleRollout:
         drained = [torch.cuda.Event() for _ in range(2)]
         for i in range(steps):
             if forcings_host is not None:
-                self.forcings[first_forcing + i].copy_(forcings_host[first_forcing + i], non_blocking=True)
+                self._check_bounds(table_needed=True)
+                for r in self.forcing_rows():
+                    self.forcings[r].copy_(forcings_host[r], non_blocking=True)
             x_phys = self.step()
             if i > 0:
                 main.wait_event(drained[(i - 1) & 1])          # the copy stream has finished reading the staging buffer

@@ -47,7 +47,7 @@ class DiffusionSampler:
         else:
             aux_key = auxiliary
         eng = model.engine()
-        key = (id(eng), float(t_val), aux_key, B, str(device))
+        key = (eng.generation, float(t_val), aux_key, B, str(device))
         hit = self._cond_cache.get(key)
         if hit is not None:
             return hit

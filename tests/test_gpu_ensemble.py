@@ -63,7 +63,7 @@ def test_scored_rollout(use_graph):
     H, W = cfg["img_resolution"]
     n_forc = cfg["in_channels"] - 2 * n_var
     forc = torch.randn(steps + 2, n_forc, H, W, device="cuda")
-    ro = EnsembleRollout(net, Normalizers.synthetic(n_var, "cuda"), forc, traj, use_graph=use_graph)
+    ro = EnsembleRollout(net, Normalizers.synthetic(n_var, "cuda"), forc, traj, use_graph=use_graph, ic_times=[0, 1])
     lat = np.linspace(-88, 88, H)
     st = EnsembleStatistics(members, n_ic, n_var, (H, W), lat, steps, "cuda")
     truth = torch.zeros(n_ic, n_var, H, W, device="cuda")
@@ -80,4 +80,4 @@ def test_scored_rollout(use_graph):
         for k, fn in (("rmse", mo.rmse), ("crps", mo.crps), ("ssr", mo.spread_skill)):
             torch.testing.assert_close(sc[k][i].cpu(), fn(pred, truths[i].double().cpu(), lat), rtol=1e-5, atol=1e-7)
     with pytest.raises(ValueError):
-        EnsembleRollout(net, Normalizers.synthetic(n_var, "cuda"), forc, traj[1:]).attach_statistics(st, truth)
+        EnsembleRollout(net, Normalizers.synthetic(n_var, "cuda"), forc, traj[1:], ic_times=[0, 1]).attach_statistics(st, truth)

@@ -40,8 +40,9 @@ def test_noise_matches_philox_oracle():
     assert abs(float(big.mean())) < 3e-3 and abs(float(big.std()) - 1) < 3e-3
 
 
-def _oracle_rollout(sd, cfg, n_var, traj, x0, forc, norm, steps):
-    """generate.py:97-136 with the oracle network and the oracle noise stream; returns the list of physical states."""
+def _oracle_rollout(sd, cfg, n_var, traj, x0, forc, norm, steps, ic_times=None, stride=1):
+    """generate.py:97-136 with the oracle network and the oracle noise stream; returns the list of physical states.
+    Forcings as the reference fetches them: get_forcings(j + i * interval // 6) per sample, j = the IC's time index."""
     from oracle import philox_oracle as ph, swinv2_oracle as orc
     from swift_b200.rollout import trajectory_seed
     ocfg = orc.make_cfg(**cfg)
@@ -52,38 +53,112 @@ def _oracle_rollout(sd, cfg, n_var, traj, x0, forc, norm, steps):
     for i in range(steps):
         lat = torch.stack([torch.from_numpy(ph.normal(trajectory_seed(m, j), i, n)).reshape(x0[0].shape)
                            for m, j in traj])
-        f = forc[i].unsqueeze(0).expand(len(traj), -1, -1, -1)
+        rows = [(ic_times[j] if ic_times is not None else 0) + i * stride for _, j in traj]
+        f = torch.stack([forc[r] for r in rows])
         x, phys = orc.rollout_step(lambda c: orc.scm_solver(net, lat, c, 0.6, num_steps=1), x, f,
                                    norm["mean"], norm["std"], norm["diff"], n_var)
         out.append(phys)
     return out
 
 
-@pytest.mark.parametrize("use_graph", [True, False], ids=["graph", "eager"])
-def test_fused_rollout_vs_oracle(use_graph):
+@pytest.mark.parametrize("use_graph,interval", [(True, 6), (False, 6), (True, 12)], ids=["graph", "eager", "graph-12h"])
+def test_fused_rollout_vs_oracle(use_graph, interval):
+    """Four ICs with DIFFERENT valid times (generate.py:105-110: every sample gets the forcings of its own time index
+    j + i * interval // 6), through the captured graph: every forcing row of the table is distinct, so a trajectory that
+    read another IC's row (what a step-indexed table did) fails the 1e-2 bar by orders of magnitude."""
     from swift_b200 import synthetic as syn
     from swift_b200.rollout import EnsembleRollout, Normalizers
     cfg = syn.SWIFT_TINY
     n_var, steps = cfg["out_channels"], 4
     net, sd = _build(cfg, n_var)
-    traj = [(0, 0), (1, 0), (0, 1)]
+    traj = [(0, 0), (1, 0), (0, 1), (0, 2), (1, 2), (1, 3)]
+    ic_times = {0: 2, 1: 0, 2: 5, 3: 3}
+    stride = interval // 6
     g = torch.Generator().manual_seed(3)
     x0 = torch.randn(len(traj), n_var, 32, 64, generator=g)
-    forc = syn.synthetic_forcings(cfg, steps, seed=1, n_forcings=cfg["in_channels"] - 2 * n_var)
+    n_forc = cfg["in_channels"] - 2 * n_var
+    n_times = max(ic_times.values()) + (steps - 1) * stride + 1
+    forc = torch.randn(n_times, n_forc, 32, 64, generator=g)           # every row differs in every channel
     mean = torch.linspace(-1, 1, n_var).reshape(1, -1, 1, 1)
     std = torch.linspace(0.5, 2.0, n_var).reshape(1, -1, 1, 1)
     diff = torch.linspace(0.05, 0.3, n_var).reshape(1, -1, 1, 1)
     norm = Normalizers(mean.cuda(), std.cuda(), diff.cuda())
-    ro = EnsembleRollout(net, norm, forc.cuda(), traj, use_graph=use_graph)
+    ro = EnsembleRollout(net, norm, forc.cuda(), traj, use_graph=use_graph, ic_times=ic_times, interval=interval)
     assert ro.fused
     ro.set_state(x0.cuda())
-    got = [ro.step().cpu().clone() for _ in range(steps)]
-    ref = _oracle_rollout(sd, cfg, n_var, traj, x0, forc, dict(mean=mean, std=std, diff=diff), steps)
+    got = []
+    for i in range(steps):
+        got.append(ro.step().cpu().clone())
+        for b, (_, j) in enumerate(traj):                             # the condition buffer holds THIS IC's forcings
+            assert torch.equal(ro.cond[b, n_var:].cpu(), forc[ic_times[j] + i * stride]), (i, b)
+    ref = _oracle_rollout(sd, cfg, n_var, traj, x0, forc, dict(mean=mean, std=std, diff=diff), steps, ic_times, stride)
     for i, (a, b) in enumerate(zip(got, ref)):
         d = ((a - b).flatten(2).norm(dim=-1) / (b - mean).flatten(2).norm(dim=-1)).max().item()
         print(f"rollout step {i + 1}: per-field rel-L2 (anomaly-normalised) max {d:.3e}")
         assert d < 1e-2
     assert int(ro.step_dev.item()) == steps
+    with pytest.raises(RuntimeError, match="forcings row"):           # one more step would leave the table
+        ro.step()
+    assert int(ro.step_dev.item()) == steps                           # nothing was launched
+
+
+def test_rollout_refuses_ambiguous_forcings_and_overruns():
+    from swift_b200 import synthetic as syn
+    from swift_b200.ensemble import EnsembleStatistics
+    from swift_b200.rollout import EnsembleRollout, Normalizers
+    cfg = syn.SWIFT_TINY
+    n_var = cfg["out_channels"]
+    net, _ = _build(cfg, n_var)
+    forc = syn.synthetic_forcings(cfg, 3, seed=1, n_forcings=cfg["in_channels"] - 2 * n_var).cuda()
+    norm = Normalizers.synthetic(n_var, "cuda")
+    with pytest.raises(ValueError, match="ic_times"):                 # two ICs, no valid times given
+        EnsembleRollout(net, norm, forc, [(0, 0), (0, 1)])
+    with pytest.raises(ValueError, match="outside"):
+        EnsembleRollout(net, norm, forc, [(0, 0), (0, 1)], ic_times=[0, 3])
+    with pytest.raises(ValueError, match="no entry"):
+        EnsembleRollout(net, norm, forc, [(0, 0), (0, 1)], ic_times={0: 0})
+    with pytest.raises(ValueError, match="interval"):
+        EnsembleRollout(net, norm, forc, [(0, 0)], interval=9)
+    traj = [(0, 0), (1, 0)]
+    ro = EnsembleRollout(net, norm, forc, traj)
+    st = EnsembleStatistics(2, 1, n_var, (32, 64), np.linspace(-80, 80, 32), steps=2, device="cuda")
+    truth = torch.zeros(1, n_var, 32, 64, device="cuda")
+    ro.attach_statistics(st, truth)
+    ro.set_state(torch.zeros(2, n_var, 32, 64, device="cuda"))
+    ro.run(2)
+    before = st.sums.clone()
+    with pytest.raises(RuntimeError, match="EnsembleStatistics"):     # third step: table still has a row, stats do not
+        ro.step()
+    assert torch.equal(st.sums, before)
+    with pytest.raises(ValueError):
+        ro.set_state(torch.zeros(2, n_var, 32, 64, device="cuda"), step=-1)
+
+
+def test_rollout_recaptures_after_weight_reload():
+    """The captured graph and the cached conditioning vectors point into the Engine's packed weights; a load_state_dict
+    rebuilds the engine (new generation), and the next step must re-capture instead of replaying against freed memory."""
+    from swift_b200 import synthetic as syn
+    from swift_b200.rollout import EnsembleRollout, Normalizers
+    cfg = syn.SWIFT_TINY
+    n_var = cfg["out_channels"]
+    net, _ = _build(cfg, n_var)
+    forc = syn.synthetic_forcings(cfg, 4, seed=1, n_forcings=cfg["in_channels"] - 2 * n_var).cuda()
+    norm = Normalizers.synthetic(n_var, "cuda", diff=0.2)
+    traj = [(0, 0), (1, 0)]
+    x0 = torch.randn(2, n_var, 32, 64, generator=torch.Generator().manual_seed(9)).cuda()
+    ro = EnsembleRollout(net, norm, forc, traj)
+    ro.set_state(x0)
+    first = ro.step().clone()
+    gen0 = net.model.engine().generation
+    sd2 = syn.random_state_dict(cfg, seed=2)
+    net.load_state_dict({"model." + k: v for k, v in sd2.items()}, strict=True)
+    ro.set_state(x0)
+    second = ro.step().clone()
+    assert net.model.engine().generation != gen0
+    fresh = EnsembleRollout(net, norm, forc, traj)
+    fresh.set_state(x0)
+    assert torch.equal(second, fresh.step()), "replayed a graph captured against the previous weights"
+    assert not torch.equal(first, second)
 
 
 def test_graph_equals_eager_and_batching_invariance():
@@ -92,14 +167,14 @@ def test_graph_equals_eager_and_batching_invariance():
     cfg = syn.SWIFT_TINY
     n_var = cfg["out_channels"]
     net, _ = _build(cfg, n_var)
-    forc = syn.synthetic_forcings(cfg, 3, seed=2, n_forcings=cfg["in_channels"] - 2 * n_var).cuda()
+    forc = syn.synthetic_forcings(cfg, 4, seed=2, n_forcings=cfg["in_channels"] - 2 * n_var).cuda()
     norm = Normalizers.synthetic(n_var, "cuda", diff=0.2)
     traj = [(0, 0), (1, 0), (2, 0), (0, 1), (1, 1)]
     x0 = torch.randn(len(traj), n_var, 32, 64, generator=torch.Generator().manual_seed(5)).cuda()
 
     def run(sel, use_graph, chunk):
         net.model.max_chunk = chunk
-        ro = EnsembleRollout(net, norm, forc, [traj[i] for i in sel], use_graph=use_graph)
+        ro = EnsembleRollout(net, norm, forc, [traj[i] for i in sel], use_graph=use_graph, ic_times=[0, 1])
         ro.set_state(x0[sel])
         for _ in range(3):
             out = ro.step()
@@ -145,14 +220,16 @@ def test_run_to_host_pipelined_copies_match_device_rollout():
     n_var = cfg["out_channels"]
     net, _ = _build(cfg, n_var)
     steps = 4
-    forc_host = syn.synthetic_forcings(cfg, steps, seed=2, n_forcings=cfg["in_channels"] - 2 * n_var).pin_memory()
+    ic_times = [3, 0]                                              # IC 0 starts 18 h after IC 1
+    forc_host = torch.randn(steps + 3, cfg["in_channels"] - 2 * n_var, 32, 64,
+                            generator=torch.Generator().manual_seed(2)).pin_memory()
     norm = Normalizers.synthetic(n_var, "cuda", diff=0.2)
     traj = [(0, 0), (1, 0), (0, 1)]
     x0 = torch.randn(len(traj), n_var, 32, 64, generator=torch.Generator().manual_seed(7)).cuda()
-    a = EnsembleRollout(net, norm, forc_host.cuda(), traj)
+    a = EnsembleRollout(net, norm, forc_host.cuda(), traj, ic_times=ic_times)
     a.set_state(x0)
     ref = [a.step().cpu() for _ in range(steps)]
-    b = EnsembleRollout(net, norm, torch.zeros_like(forc_host).cuda(), traj)      # forcings arrive step by step
+    b = EnsembleRollout(net, norm, torch.zeros_like(forc_host).cuda(), traj, ic_times=ic_times)   # forcings arrive step by step
     b.set_state(x0)
     out = torch.empty(2, *b.phys.shape).pin_memory()
     seen = {}
@@ -166,9 +243,15 @@ def test_run_to_host_pipelined_copies_match_device_rollout():
 
 def test_swift_b_rollout_drift_report():
     """BASELINE.json north_star: 'per-field relative L2 of at most 1e-2 after one step, with rollout drift reported per
-    step'.  Swift-B, 2 trajectories x 6 six-hour steps, the fused / graph-replayed CUDA step against the fp32 oracle
-    (run on the GPU with TF32 off) that is fed ITS OWN previous state and the same noise stream: the curve is the
-    divergence of two chaotic-free affine-plus-network recursions started from the same analysis."""
+    step'.  Swift-B, one full 12-member ensemble x 60 six-hour steps (15 days), the fused / graph-replayed CUDA step
+    against the fp32 oracle (run on the GPU with TF32 off) with the same noise streams.  Per step, three numbers:
+      state : per-field rel-L2 between the two FREE-RUNNING recursions' physical states (each fed its own output);
+      Y free: the same for the network increments Y = (X_{i+1} - X_i) / sigma_diff of the two recursions -- the state
+              dilutes a network error by sigma_diff / |X| (0.1 here), Y does not;
+      Y local: the oracle evaluated on the CUDA path's OWN input state of that step vs the CUDA increment: the error one
+              step adds, free of accumulated divergence (this is the number the 1e-2 bar is about, at every lead).
+    The curve is written to $SWB_REPORT_DIR/r02_drift60.txt (default gpurun_out/) for profiles/."""
+    import os
     from oracle import philox_oracle as ph, swinv2_oracle as orc
     from swift_b200 import synthetic as syn
     from swift_b200.rollout import EnsembleRollout, Normalizers, trajectory_seed
@@ -176,36 +259,59 @@ def test_swift_b_rollout_drift_report():
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     cfg = syn.SWIFT_B
-    n_var, steps = syn.IMG_CHANNELS, 6
+    members = int(os.environ.get("SWB_DRIFT_MEMBERS", "12"))
+    n_var, steps = syn.IMG_CHANNELS, int(os.environ.get("SWB_DRIFT_STEPS", "60"))
     net, sd = build_net(cfg, img_channels=n_var)
-    traj = [(0, 0), (1, 0)]
-    H, W = cfg["img_resolution"]
-    x0 = syn.synthetic_fields(cfg, 1, seed=0)[1][:, :n_var].expand(2, -1, -1, -1).contiguous()
+    net.model.max_chunk = 12
+    traj = [(m, 0) for m in range(members)]
+    x0 = syn.synthetic_fields(cfg, 1, seed=0)[1][:, :n_var].expand(members, -1, -1, -1).contiguous()
     forc = syn.synthetic_forcings(cfg, steps, seed=0)
-    norm = Normalizers.synthetic(n_var, "cuda", diff=0.1)
+    diff = 0.1
+    norm = Normalizers.synthetic(n_var, "cuda", diff=diff)
     ro = EnsembleRollout(net, norm, forc.cuda(), traj, use_graph=True)
     ro.set_state(x0.cuda())
-    got = [ro.step().clone() for _ in range(steps)]
     ocfg = orc.make_cfg(**cfg)
     sd_gpu = {k: v.cuda() for k, v in sd.items()}
     onet = lambda x, t, c, a: orc.pass_precond(sd_gpu, ocfg, x, t, c, a)
     one = torch.ones(1, n_var, 1, 1, device="cuda")
-    x = x0.cuda()
     n = x0[0].numel()
-    worst = []
+
+    def rel(a, b):
+        return (a - b).flatten(2).norm(dim=-1) / b.flatten(2).norm(dim=-1)
+
+    x_ref = x0.cuda()                 # oracle recursion (standardised == physical here: mean 0, std 1)
+    x_cuda_prev = x0.cuda().clone()
+    lines = [f"# Swift-B sCM rollout drift, {members} members x {steps} steps, fp16-operand CUDA path vs fp32 oracle "
+             f"(sigma_diff {diff})", "# step lead_h state_max state_mean Yfree_max Yfree_mean Ylocal_max Ylocal_mean"]
+    first_local, worst_local, last_state = None, 0.0, None
     with torch.no_grad():
         for i in range(steps):
             lat = torch.stack([torch.from_numpy(ph.normal(trajectory_seed(m, j), i, n)).reshape(x0[0].shape)
                                for m, j in traj]).cuda()
-            f = forc[i].cuda().unsqueeze(0).expand(len(traj), -1, -1, -1)
-            x, phys = orc.rollout_step(lambda c: orc.scm_solver(onet, lat, c, 0.6, num_steps=1), x, f,
-                                       0 * one, one, 0.1 * one, n_var)
-            err = ((got[i] - phys).flatten(2).norm(dim=-1) / phys.flatten(2).norm(dim=-1))
-            worst.append(err.max().item())
-            print(f"Swift-B rollout step {i + 1} (+{6 * (i + 1)} h): per-field rel-L2 of the state max {err.max():.3e} "
-                  f"mean {err.mean():.3e}")
-    assert worst[0] < 1e-2                       # the stated bar applies to one step
-    assert worst[-1] < 5e-2, "rollout drift after 6 steps larger than expected"
+            f = forc[i].cuda().unsqueeze(0).expand(members, -1, -1, -1)
+            solve = lambda c: orc.scm_solver(onet, lat, c, 0.6, num_steps=1)
+            _, phys_local = orc.rollout_step(solve, x_cuda_prev, f, 0 * one, one, diff * one, n_var)
+            x_ref_new, phys_ref = orc.rollout_step(solve, x_ref, f, 0 * one, one, diff * one, n_var)
+            phys = ro.step().clone()
+            y_cuda = (phys - x_cuda_prev) / diff
+            y_free = (phys_ref - x_ref) / diff
+            y_local = (phys_local - x_cuda_prev) / diff
+            e_s, e_f, e_l = rel(phys, phys_ref), rel(y_cuda, y_free), rel(y_cuda, y_local)
+            lines.append(f"{i + 1:3d} {6 * (i + 1):4d} {e_s.max():.3e} {e_s.mean():.3e} {e_f.max():.3e} {e_f.mean():.3e} "
+                         f"{e_l.max():.3e} {e_l.mean():.3e}")
+            print(lines[-1])
+            if first_local is None:
+                first_local = e_l.max().item()
+            worst_local = max(worst_local, e_l.max().item())
+            last_state = e_s.max().item()
+            x_ref, x_cuda_prev = x_ref_new, phys
+    out_dir = os.environ.get("SWB_REPORT_DIR", os.path.join(os.path.dirname(os.path.dirname(__file__)), "gpurun_out"))
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "r02_drift60.txt"), "w") as fh:
+            fh.write("\n".join(lines) + "\n")
+    assert first_local < 1e-2                    # the stated bar: one step
+    assert worst_local < 1e-2, "a later step's own error exceeds the one-step bar"
+    assert last_state == last_state and last_state < 0.5, "free-running recursions diverged: see the curve"   # (reported, not a bar)
 
 
 @pytest.mark.parametrize("layout", ["trajectory", "step", "numpy"])
@@ -231,10 +337,10 @@ def test_rollout_and_save_fills_the_store(tmp_path, layout):
     path = str(tmp_path / ("fc.npy" if layout == "numpy" else "fc.zarr"))
     store = ForecastStore.create(path, variables, 2, 2, steps, np.linspace(-80, 80, H), np.arange(W) * 5.625,
                                  layout=layout)
-    ro = EnsembleRollout(net, norm, torch.zeros_like(forc).cuda(), traj)
+    ro = EnsembleRollout(net, norm, torch.zeros_like(forc).cuda(), traj, ic_times=[0, 1])
     info = rollout_and_save(ro, store, x0, steps, forc.pin_memory(), writers=2)
     assert info["trajectories"] == 3 and info["bytes_written"] == 3 * (steps + 1) * n_var * H * W * 4
-    ref = EnsembleRollout(net, norm, forc.cuda(), traj)
+    ref = EnsembleRollout(net, norm, forc.cuda(), traj, ic_times=[0, 1])
     ref.set_state(x0.cuda())
     want = np.zeros((2, 2, steps + 1, n_var, H, W), dtype=np.float32)
     lead0 = (x0.cuda() * std + mean).cpu().numpy()
@@ -292,7 +398,7 @@ def test_reference_noise_stream_replay():
     x0 = torch.randn(2, n_var, H, W, generator=torch.Generator().manual_seed(2)).cuda()
     tr = [(1, 2), (1, 3)]
     for use_graph in (True, False):
-        ro = EnsembleRollout(net, norm, forc, tr, use_graph=use_graph,
+        ro = EnsembleRollout(net, norm, forc, tr, use_graph=use_graph, ic_times={2: 0, 3: 0},
                              noise=ReferenceNoise(tr, n_ic, batch, steps, shape, torch.device("cuda")))
         ro.set_state(x0)
         got = [ro.step().clone() for _ in range(2)]

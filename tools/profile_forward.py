@@ -23,8 +23,8 @@ def main():
     if len(sys.argv) > 1:
         net.model.fuse_ln = int(sys.argv[1])
     traj = [(m, 0) for m in range(8)]
-    forc = syn.synthetic_forcings(cfg, 4, seed=0).cuda()
-    ro = EnsembleRollout(net, Normalizers.synthetic(69, "cuda"), forc, traj, use_graph=False)
+    forc = syn.synthetic_forcings(cfg, 24, seed=0).cuda()
+    ro = EnsembleRollout(net, Normalizers.synthetic(69, "cuda"), forc, traj, use_graph=False, ic_times=list(range(8)))
     ro.set_state(torch.randn(len(traj), 69, 128, 256, device="cuda"))
     for _ in range(2):
         ro.step()

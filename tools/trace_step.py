@@ -27,8 +27,8 @@ def main():
     if len(sys.argv) > 3:
         net.model.fuse_ln = int(sys.argv[3])
     traj = shard_trajectories(12, 8, 0, 1)
-    forc = syn.synthetic_forcings(cfg, steps + 8, seed=0).cuda()
-    ro = EnsembleRollout(net, Normalizers.synthetic(69, "cuda"), forc, traj, use_graph=False)
+    forc = syn.synthetic_forcings(cfg, steps + 16, seed=0).cuda()
+    ro = EnsembleRollout(net, Normalizers.synthetic(69, "cuda"), forc, traj, use_graph=False, ic_times=list(range(8)))
     ro.set_state(torch.randn(len(traj), 69, 128, 256, device="cuda"))
     for _ in range(3):
         ro.step()
