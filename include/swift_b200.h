@@ -56,6 +56,7 @@ typedef struct swb200_model {
   int32_t attn_impl;          /* window attention: 0 = auto (tcgen05 kernel for shifts that are multiples of 8), 1 = mma.sync, 2 = tcgen05 */
   int32_t act_fp16;           /* 16-bit tensor-core operand format of activations AND packed weights: 1 = fp16, 0 = bf16 */
   int32_t fuse_ln;            /* LayerNorm + modulation + residual add in the GEMM epilogue: bit 0 = wo, bit 1 = w2 (host default 2); 0 = separate kernel */
+  int32_t attn_fp16;          /* with act_fp16 = 0: keep q / k / v and P in fp16 inside the attention (bounded by construction); ignored when act_fp16 */
   float timestep_weight;
   const void* w_embed;
   const float* b_embed;
@@ -143,9 +144,10 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
  * tile: 1 = 128x176 single CTA, 2 = 256x176 CTA pair (cta_group::2), 3 = 256x352 CTA pair. */
 SWB200_API int swb200_gemm(int epi, int tile, int act_fp16, const void* A, int lda, const void* W, int ldw, void* out,
                 int ldo, int M, int N, int K, void* stream);
-/* qkv projection with fused scaled-cosine normalisation: out = bf16 [3][heads][M][96]; W packed as w_qkv. */
-SWB200_API int swb200_gemm_qkv(int tile, int act_fp16, const void* A, int lda, const void* W, const float* qscale, void* out, int M,
-                    int dim, int heads, void* stream);
+/* qkv projection with fused scaled-cosine normalisation: out = 16-bit [3][heads][M][96] in fp16 when qkv_fp16 else bf16
+ * (bf16 operands with an fp16 q/k/v output is the bf16 model with fp16 attention internals); W packed as w_qkv. */
+SWB200_API int swb200_gemm_qkv(int tile, int act_fp16, int qkv_fp16, const void* A, int lda, const void* W, const float* qscale,
+                    void* out, int M, int dim, int heads, void* stream);
 /* SwiGLU up-projection: out[M, dff] = silu(gate) * up; W packed as w_1. */
 SWB200_API int swb200_gemm_swiglu(int tile, int act_fp16, const void* A, int lda, const void* W, void* out, int M, int dim, int dff,
                        void* stream);
@@ -176,10 +178,11 @@ SWB200_API int swb200_patch_gather(const swb200_model* m, const float* x0, int c
  * branch is fp32 [M, dim], or the 16-bit operand format when branch_16bit. */
 SWB200_API int swb200_ln_mod_residual(const void* branch, int branch_16bit, void* xhl, const float* gain, const float* bias,
                            int M, int dim, int tokens, int act_fp16, void* stream);
-/* shifted-window cosine attention on the packed qkv buffer; out 16-bit [M, heads*88].
+/* shifted-window cosine attention on the packed qkv buffer (fp16 when qkv_fp16 else bf16; P uses the same format);
+ * out 16-bit [M, heads*88], fp16 when out_fp16 else bf16 (out_fp16 needs qkv_fp16).
  * impl: 0 auto, 1 general-shift mma.sync kernel, 2 tcgen05/TMEM/TMA kernel (shift must be a multiple of 8). */
 SWB200_API int swb200_window_attention(const void* qkv, void* out, int B, int grid_h, int grid_w, int heads, int shift_h,
-                            int shift_w, int act_fp16, int impl, void* stream);
+                            int shift_w, int qkv_fp16, int out_fp16, int impl, void* stream);
 
 /* ---- tracing ---------------------------------------------------------------------------------------------- */
 
@@ -189,6 +192,14 @@ SWB200_API int swb200_window_attention(const void* qkv, void* out, int B, int gr
  * {"kernel": {"ms": total, "launches": n}, ...} into buf. */
 SWB200_API int swb200_trace_enable(int on);
 SWB200_API int swb200_trace_report(char* buf, size_t buf_bytes);
+
+/* fp16 range diagnostics.  Every fp16 conversion of an activation saturates at +-65504 instead of producing inf; with
+ * `counters` set (DEVICE pointer to 6 zero-initialised uint64, NULL switches the diagnostics off again; process-global,
+ * not thread-safe) every later swb200_forward adds, after the kernel that produced a tensor, the number of its elements
+ * sitting at the saturation value:  [0] residual stream hi  [1] residual stream lo  [2] packed q/k/v  [3] attention output
+ * [4] wo / w2 branch outputs (un-fused LayerNorm path only; the fused epilogue never stores them)  [5] SwiGLU hidden.
+ * Non-zero counts mean the checkpoint's activations leave the fp16 range: run that model with act_fp16 = 0 (bf16). */
+SWB200_API int swb200_debug_saturation(uint64_t* counters);
 
 /* ---- rollout glue around the sampler (generate.py:97-118), graph-capturable ------------------------------ */
 

@@ -23,6 +23,7 @@ EXPORTS = (
     "swb200_gemm_ln_residual", "swb200_ensemble_stats", "swb200_jvp_workspace_bytes",
     "swb200_conditioning_jvp_scratch_bytes", "swb200_conditioning_jvp", "swb200_forward_jvp",
     "swb200_scm_noised_inputs", "swb200_scm_target_scratch_bytes", "swb200_scm_tangent_target",
+    "swb200_debug_saturation",
 )
 
 _i32, _f32, _vp, _sz = C.c_int32, C.c_float, C.c_void_p, C.c_size_t
@@ -34,7 +35,7 @@ class Model(C.Structure):
         [(n, _i32) for n in ("img_h", "img_w", "patch_h", "patch_w", "win_h", "win_w", "shift_h", "shift_w",
                              "in_channels", "out_channels", "depth", "dim", "heads", "dff", "aux_dim",
                              "k_embed", "split_embed", "split_head", "gemm_tile", "attn_impl", "act_fp16",
-                             "fuse_ln")]
+                             "fuse_ln", "attn_fp16")]
         + [("timestep_weight", _f32)]
         + [(n, _vp) for n in ("w_embed", "b_embed", "pos_embed", "aux_w", "aux_b", "l1_w", "l1_b", "l2_w", "l2_b",
                               "mod_w", "mod_b", "ln_gamma", "ln_beta", "qscale", "w_qkv", "w_o", "w_1", "w_2",
@@ -66,7 +67,7 @@ def _declare(lib):
         "swb200_forward": (C.c_int, [MP, _vp, C.c_int, _f32, _vp, C.c_int, C.c_int, _vp, _vp, UP, _vp, _vp, _sz, _vp]),
         "swb200_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int,
                                   C.c_int, C.c_int, _vp]),
-        "swb200_gemm_qkv": (C.c_int, [C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+        "swb200_gemm_qkv": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
         "swb200_gemm_swiglu": (C.c_int, [C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
         "swb200_gemm_embed": (C.c_int, [C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp, C.c_int, _vp,
                                         C.c_int, C.c_int, _vp]),
@@ -74,7 +75,7 @@ def _declare(lib):
         "swb200_patch_gather": (C.c_int, [MP, _vp, C.c_int, _f32, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp]),
         "swb200_ln_mod_residual": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
         "swb200_window_attention": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                              C.c_int, _vp]),
+                                              C.c_int, C.c_int, _vp]),
         "swb200_rollout_noise": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int64, _vp]),
         "swb200_rollout_forcings": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int,
                                               C.c_int, _vp]),
@@ -93,6 +94,7 @@ def _declare(lib):
         "swb200_scm_target_scratch_bytes": (_sz, [C.c_int]),
         "swb200_scm_tangent_target": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _vp, C.c_int, C.c_int, C.c_int,
                                                 C.c_int, _vp, _vp, _vp, _vp, _sz, _vp]),
+        "swb200_debug_saturation": (C.c_int, [_vp]),
         "swb200_trace_enable": (C.c_int, [C.c_int]),
         "swb200_trace_report": (C.c_int, [C.c_char_p, _sz]),
     }

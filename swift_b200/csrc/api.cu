@@ -51,6 +51,10 @@ struct TraceScope {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// fp16 range diagnostics (swb200_debug_saturation): device counters, one per tensor class of swb200_forward
+enum SatSlot { SAT_X_HI = 0, SAT_X_LO, SAT_QKV, SAT_ATTN, SAT_BRANCH, SAT_H, SAT_NSLOTS };
+unsigned long long* g_sat_counters = nullptr;
+
 struct Geom {
   int gh, gw, tokens, pp, k_embed_total, k_head_total;
 };
@@ -201,6 +205,9 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
   const Geom g = geom(m);
   const int D = m->dim, H = m->heads, Dff = m->dff;
   const int F16 = m->act_fp16 ? 1 : 0;
+  // q / k / v and P in fp16 even when the GEMM operands are bf16: the attention kernel's operand format is independent of
+  // the GEMMs' (its inputs come out of an epilogue, its output goes into one), and q_hat*scale <= 100, k_hat <= 1, P <= 1
+  const int AF16 = (F16 || m->attn_fp16) ? 1 : 0;
   const int kDefaultCG = m->gemm_tile;          // tile config of every GEMM (the w1 packing depends on it)
   const size_t img_in0 = static_cast<size_t>(c0) * m->img_h * m->img_w;
   const size_t img_in1 = static_cast<size_t>(c1) * m->img_h * m->img_w;
@@ -224,6 +231,16 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
     // the fused epilogue spins on statistics published by other CTAs of its grid: if the device cannot keep the whole grid
     // resident (reported before anything is launched) the same update runs as GEMM + LayerNorm kernel instead
     bool fuse_wo = (m->fuse_ln & 1) != 0, fuse_w2 = (m->fuse_ln & 2) != 0;
+    // debug only: count fp16 values sitting at the saturation value after the kernel that produced them
+    auto sat = [&](int slot, const void* buf, long long rows, int cols, long long pitch) -> int {
+      if (g_sat_counters == nullptr) return SWB_OK;
+      return launch_count_saturated_f16(buf, rows, cols, pitch, g_sat_counters + slot, stream);
+    };
+    auto sat_x = [&]() -> int {
+      if (g_sat_counters == nullptr || !F16) return SWB_OK;
+      int r = sat(SAT_X_HI, xhl, M, D, 2 * D);
+      return r ? r : sat(SAT_X_LO, static_cast<const uint16_t*>(xhl) + D, M, D, 2 * D);
+    };
     void* lnws = ws + w.lnws;
     int ln_gen = 0;                             // fused launches of this chunk so far (the first one clears the counters)
 
@@ -244,6 +261,7 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
       { TraceScope ts_(T_EMBED, stream);
       rc = launch_gemm(EPI_EMBED, kDefaultCG, F16, a_emb, g.k_embed_total, m->w_embed, g.k_embed_total, p, stream); }
       if (rc) return rc;
+      if ((rc = sat_x())) return rc;
     }
     // 3. transformer blocks
     for (int l = 0; l < m->depth; ++l) {
@@ -254,15 +272,18 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
         p.qscale = m->qscale + static_cast<size_t>(l) * H;
         p.heads = H;
         p.dmodel = D;
+        p.qkv_f16 = AF16;
         const auto* wq = static_cast<const __nv_bfloat16*>(m->w_qkv) + static_cast<size_t>(l) * 3 * D * D;
         { TraceScope ts_(T_QKV, stream);
         rc = launch_gemm(EPI_QKV, kDefaultCG, F16, xhl, 2 * D, wq, D, p, stream); }
         if (rc) return rc;
+        if (AF16 && (rc = sat(SAT_QKV, qkv, 3LL * H * M, kHeadDimPad, kHeadDimPad))) return rc;
       }
       { TraceScope ts_(T_ATTN, stream);
       rc = launch_window_attention(qkv, attn, bc, g.gh, g.gw, H, shifted ? m->shift_h : 0, shifted ? m->shift_w : 0,
-                                   F16, m->attn_impl, stream); }
+                                   AF16, F16, m->attn_impl, stream); }
       if (rc) return rc;
+      if (F16 && (rc = sat(SAT_ATTN, attn, M, D, D))) return rc;
       const auto* wo = static_cast<const __nv_bfloat16*>(m->w_o) + static_cast<size_t>(l) * D * D;
       const float* gain_a = gain + (static_cast<size_t>(2 * l) * B + b0) * D;
       const float* bias_a = bias + (static_cast<size_t>(2 * l) * B + b0) * D;
@@ -282,10 +303,12 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
         { TraceScope ts_(T_WO, stream);
         rc = launch_gemm(epi_branch, kDefaultCG, F16, attn, D, wo, D, p, stream); }
         if (rc) return rc;
+        if (BR16 && (rc = sat(SAT_BRANCH, branch, M, D, D))) return rc;
         { TraceScope ts_(T_LN, stream);
         rc = launch_ln_mod_residual(branch, BR16, xhl, gain_a, bias_a, M, D, g.tokens, 1e-6f, F16, stream); }
         if (rc) return rc;
       }
+      if ((rc = sat_x())) return rc;
       {
         GemmParams p = base_params(M, 2 * Dff, D);
         p.out0 = hbuf;
@@ -294,6 +317,7 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
         { TraceScope ts_(T_W1, stream);
         rc = launch_gemm(EPI_SWIGLU, kDefaultCG, F16, xhl, 2 * D, w1, D, p, stream); }
         if (rc) return rc;
+        if (F16 && (rc = sat(SAT_H, hbuf, M, Dff, Dff))) return rc;
       }
       const auto* w2 = static_cast<const __nv_bfloat16*>(m->w_2) + static_cast<size_t>(l) * D * Dff;
       const float* gain_f = gain + (static_cast<size_t>(2 * l + 1) * B + b0) * D;
@@ -313,10 +337,12 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
         { TraceScope ts_(T_W2, stream);
         rc = launch_gemm(epi_branch, kDefaultCG, F16, hbuf, Dff, w2, Dff, p, stream); }
         if (rc) return rc;
+        if (BR16 && (rc = sat(SAT_BRANCH, branch, M, D, D))) return rc;
         { TraceScope ts_(T_LN, stream);
         rc = launch_ln_mod_residual(branch, BR16, xhl, gain_f, bias_f, M, D, g.tokens, 1e-6f, F16, stream); }
         if (rc) return rc;
       }
+      if ((rc = sat_x())) return rc;
     }
     // 4. head GEMM + pixel shuffle + sampler update
     {
@@ -356,8 +382,9 @@ SWB200_API int swb200_gemm(int epi, int tile, int act_fp16, const void* A, int l
   return launch_gemm(epi, tile, act_fp16, A, lda, W, ldw, p, static_cast<cudaStream_t>(stream));
 }
 
-SWB200_API int swb200_gemm_qkv(int tile, int act_fp16, const void* A, int lda, const void* W, const float* qscale, void* out, int M,
-                    int dim, int heads, void* stream) {
+SWB200_API int swb200_gemm_qkv(int tile, int act_fp16, int qkv_fp16, const void* A, int lda, const void* W, const float* qscale,
+                    void* out, int M, int dim, int heads, void* stream) {
+  SWB_REQUIRE(!act_fp16 || qkv_fp16, "swb200_gemm_qkv: fp16 operands with a bf16 q/k/v output is not a supported combination");
   SWB_REQUIRE(A && W && qscale && out, "swb200_gemm_qkv: NULL pointer");
   SWB_REQUIRE(dim == heads * kHeadDim, "swb200_gemm_qkv: need head_dim 88 (dim=%d heads=%d)", dim, heads);
   GemmParams p = base_params(M, 3 * dim, dim);
@@ -365,6 +392,7 @@ SWB200_API int swb200_gemm_qkv(int tile, int act_fp16, const void* A, int lda, c
   p.qscale = qscale;
   p.heads = heads;
   p.dmodel = dim;
+  p.qkv_f16 = qkv_fp16 ? 1 : 0;
   return launch_gemm(EPI_QKV, tile, act_fp16, A, lda, W, dim, p, static_cast<cudaStream_t>(stream));
 }
 
@@ -472,9 +500,9 @@ SWB200_API int swb200_ln_mod_residual(const void* branch, int branch_16bit, void
 }
 
 SWB200_API int swb200_window_attention(const void* qkv, void* out, int B, int grid_h, int grid_w, int heads, int shift_h,
-                            int shift_w, int act_fp16, int impl, void* stream) {
+                            int shift_w, int qkv_fp16, int out_fp16, int impl, void* stream) {
   SWB_REQUIRE(qkv && out, "swb200_window_attention: NULL pointer");
-  return launch_window_attention(qkv, out, B, grid_h, grid_w, heads, shift_h, shift_w, act_fp16, impl,
+  return launch_window_attention(qkv, out, B, grid_h, grid_w, heads, shift_h, shift_w, qkv_fp16, out_fp16, impl,
                                  static_cast<cudaStream_t>(stream));
 }
 
@@ -733,6 +761,11 @@ SWB200_API int swb200_scm_tangent_target(const float* F, const float* dF, const 
   SWB_REQUIRE(F && dF && x_t && dxt && t && g && cot && loss && scratch, "swb200_scm_tangent_target: NULL pointer");
   return launch_scm_tangent_target(F, dF, x_t, dxt, t, r, sigma_data, w_var, w_lat, B, C, H, W, g, cot, loss, scratch,
                                    scratch_bytes, static_cast<cudaStream_t>(stream));
+}
+
+SWB200_API int swb200_debug_saturation(uint64_t* counters) {
+  g_sat_counters = reinterpret_cast<unsigned long long*>(counters);
+  return SWB_OK;
 }
 
 SWB200_API int swb200_rollout_advance(int32_t* step, void* stream) {

@@ -66,7 +66,7 @@ __device__ __forceinline__ uint32_t pack2_act(float lo, float hi) {
   }
 }
 
-template <bool F16>
+template <bool F16, bool OUT_F16>
 __global__ void __launch_bounds__(att::kThreads, 1)
 window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int M, int gh, int gw,
                         int heads, int shift_h, int shift_w) {
@@ -206,8 +206,8 @@ window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
 #pragma unroll
   for (int nt = 0; nt < 11; ++nt) {
     const int c = nt * 8 + 2 * t4;
-    *reinterpret_cast<uint32_t*>(sQ + (q0 + g) * kPitch + c) = pack2_act<F16>(o[nt][0] * inv0, o[nt][1] * inv0);
-    *reinterpret_cast<uint32_t*>(sQ + (q0 + g + 8) * kPitch + c) = pack2_act<F16>(o[nt][2] * inv1, o[nt][3] * inv1);
+    *reinterpret_cast<uint32_t*>(sQ + (q0 + g) * kPitch + c) = pack2_act<OUT_F16>(o[nt][0] * inv0, o[nt][1] * inv0);
+    *reinterpret_cast<uint32_t*>(sQ + (q0 + g + 8) * kPitch + c) = pack2_act<OUT_F16>(o[nt][2] * inv1, o[nt][3] * inv1);
   }
   __syncwarp();
   const int dmodel = heads * kHd;
@@ -219,18 +219,21 @@ window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
 }
 
 int launch_window_attention(const void* qkv, void* out, int B, int gh, int gw, int heads, int shift_h, int shift_w,
-                            int act_f16, int impl, cudaStream_t stream) {
+                            int act_f16, int out_f16, int impl, cudaStream_t stream) {
   using namespace att;
+  SWB_REQUIRE(act_f16 || !out_f16, "window_attention: bf16 q/k/v with fp16 output is not a supported combination");
   SWB_REQUIRE(impl >= 0 && impl <= 2, "window_attention: impl must be 0 (auto), 1 (mma.sync) or 2 (tcgen05)");
   if (impl == 2 || (impl == 0 && shift_h % 8 == 0 && shift_w % 8 == 0))
-    return launch_window_attention_tc(qkv, out, B, gh, gw, heads, shift_h, shift_w, act_f16, stream);
+    return launch_window_attention_tc(qkv, out, B, gh, gw, heads, shift_h, shift_w, act_f16, out_f16, stream);
   SWB_REQUIRE(gh % kWin == 0 && gw % kWin == 0, "window_attention: token grid %dx%d not divisible by 16x16 windows",
               gh, gw);
   static bool attr_done = false;
   if (!attr_done) {
-    SWB_CHECK_CUDA(cudaFuncSetAttribute(window_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SWB_CHECK_CUDA(cudaFuncSetAttribute(window_attention_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         kSmemBytes));
-    SWB_CHECK_CUDA(cudaFuncSetAttribute(window_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SWB_CHECK_CUDA(cudaFuncSetAttribute(window_attention_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kSmemBytes));
+    SWB_CHECK_CUDA(cudaFuncSetAttribute(window_attention_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         kSmemBytes));
     attr_done = true;
   }
@@ -238,10 +241,12 @@ int launch_window_attention(const void* qkv, void* out, int B, int gh, int gw, i
   dim3 grid((gh / kWin) * (gw / kWin), heads, B);
   auto q_ = static_cast<const __nv_bfloat16*>(qkv);
   auto o_ = static_cast<__nv_bfloat16*>(out);
-  if (act_f16)
-    window_attention_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(q_, o_, M, gh, gw, heads, shift_h, shift_w);
+  if (act_f16 && out_f16)
+    window_attention_kernel<true, true><<<grid, kThreads, kSmemBytes, stream>>>(q_, o_, M, gh, gw, heads, shift_h, shift_w);
+  else if (act_f16)
+    window_attention_kernel<true, false><<<grid, kThreads, kSmemBytes, stream>>>(q_, o_, M, gh, gw, heads, shift_h, shift_w);
   else
-    window_attention_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(q_, o_, M, gh, gw, heads, shift_h, shift_w);
+    window_attention_kernel<false, false><<<grid, kThreads, kSmemBytes, stream>>>(q_, o_, M, gh, gw, heads, shift_h, shift_w);
   SWB_CHECK_CUDA(cudaGetLastError());
   return SWB_OK;
 }

@@ -71,7 +71,10 @@ __device__ __forceinline__ void warp_store_rows_2p(uint8_t* g_row0, size_t pitch
   __syncwarp();
 }
 
-template <bool F16>
+// F16: format of q / k / v and P (the tensor-core operands of this kernel); OUT_F16: format of the output rows (the A
+// operand of the wo GEMM, i.e. the model's operand format).  (F16, !OUT_F16) is the bf16 model with fp16 attention
+// internals: q_hat * scale <= 100, k_hat <= 1 and P <= 1 are bounded, so fp16's 8x finer rounding is free accuracy.
+template <bool F16, bool OUT_F16>
 __global__ void __launch_bounds__(atc::kThreads, 1)
 window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant__ CUtensorMap tmap64,
                            const AttnTcParams p) {
@@ -259,7 +262,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __
       const float inv = 1.0f / sum;
       uint32_t w[44];
 #pragma unroll
-      for (int j = 0; j < 44; ++j) w[j] = pack_act2<F16>(o[2 * j] * inv, o[2 * j + 1] * inv);
+      for (int j = 0; j < 44; ++j) w[j] = pack_act2<OUT_F16>(o[2 * j] * inv, o[2 * j + 1] * inv);
       // this warp's 32 rows: block blk = 2h + quad/2 (8x8 tokens), lines 4*(quad&1) .. +3
       const int blk = 2 * h + (quad >> 1);
       const int x0 = ((2 * wx + (blk & 1) + p.shift_bx) % nbx) * 8;
@@ -313,8 +316,9 @@ static int make_tmap_qkv(CUtensorMap* out, const void* qkv, bool f16, int heads,
 }
 
 int launch_window_attention_tc(const void* qkv, void* out, int B, int gh, int gw, int heads, int shift_h, int shift_w,
-                               int act_f16, cudaStream_t stream) {
+                               int act_f16, int out_f16, cudaStream_t stream) {
   using namespace atc;
+  SWB_REQUIRE(act_f16 || !out_f16, "window_attention_tc: bf16 q/k/v with fp16 output is not a supported combination");
   SWB_REQUIRE(gh % 16 == 0 && gw % 16 == 0 && shift_h % 8 == 0 && shift_w % 8 == 0,
               "window_attention_tc: grid %dx%d / shift %d,%d unsupported", gh, gw, shift_h, shift_w);
   SWB_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
@@ -326,10 +330,12 @@ int launch_window_attention_tc(const void* qkv, void* out, int B, int gh, int gw
   if (rc) return rc;
   static bool attr_done = false;
   if (!attr_done) {
-    SWB_CHECK_CUDA(cudaFuncSetAttribute(window_attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kSmemBytes));
-    SWB_CHECK_CUDA(cudaFuncSetAttribute(window_attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kSmemBytes));
+    SWB_CHECK_CUDA(cudaFuncSetAttribute(window_attention_tc_kernel<true, true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    SWB_CHECK_CUDA(cudaFuncSetAttribute(window_attention_tc_kernel<true, false>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    SWB_CHECK_CUDA(cudaFuncSetAttribute(window_attention_tc_kernel<false, false>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_done = true;
   }
   AttnTcParams p;
@@ -343,10 +349,12 @@ int launch_window_attention_tc(const void* qkv, void* out, int B, int gh, int gw
   p.out = out;
   const int items = B * (gh / 16) * (gw / 16) * heads;
   const int grid = items < num_sms() ? items : num_sms();
-  if (act_f16)
-    window_attention_tc_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(t128, t64, p);
+  if (act_f16 && out_f16)
+    window_attention_tc_kernel<true, true><<<grid, kThreads, kSmemBytes, stream>>>(t128, t64, p);
+  else if (act_f16)
+    window_attention_tc_kernel<true, false><<<grid, kThreads, kSmemBytes, stream>>>(t128, t64, p);
   else
-    window_attention_tc_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(t128, t64, p);
+    window_attention_tc_kernel<false, false><<<grid, kThreads, kSmemBytes, stream>>>(t128, t64, p);
   SWB_CHECK_CUDA(cudaGetLastError());
   return SWB_OK;
 }

@@ -6,6 +6,7 @@
 #include "ptx.cuh"
 
 #include <cuda_bf16.h>
+#include <algorithm>
 
 namespace swb {
 
@@ -366,6 +367,44 @@ int launch_conditioning(const CondWeights& w, const float* t, const float* aux, 
   if (cond_out)
     SWB_CHECK_CUDA(cudaMemcpyAsync(cond_out, c, static_cast<size_t>(B) * D * sizeof(float),
                                    cudaMemcpyDeviceToDevice, stream));
+  SWB_CHECK_CUDA(cudaGetLastError());
+  return SWB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fp16 range diagnostics: every fp16 conversion of an activation saturates at +-65504 (F2FP.SATFINITE, ptx.cuh) instead
+// of producing inf.  This scan counts the elements of a 16-bit [rows, cols] tensor (row pitch `pitch` elements) that sit
+// exactly at the saturation value -- |x| = 65504 = 0x7BFF -- so a checkpoint whose activations leave the fp16 range is
+// reported instead of silently clipped (swb200_debug_saturation; off by default, costs nothing when off).
+__global__ void __launch_bounds__(256) count_saturated_f16_kernel(const uint16_t* __restrict__ p, long long rows, int cols8,
+                                                                  long long pitch, unsigned long long* __restrict__ counter) {
+  unsigned n = 0;
+  const long long total = rows * cols8;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cols8;
+    const int c = static_cast<int>(i - r * cols8);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p + r * pitch) + c);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      n += ((w[k] & 0x7fffu) == 0x7bffu) ? 1u : 0u;
+      n += (((w[k] >> 16) & 0x7fffu) == 0x7bffu) ? 1u : 0u;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd(counter, static_cast<unsigned long long>(n));
+}
+
+int launch_count_saturated_f16(const void* buf, long long rows, int cols, long long pitch, unsigned long long* counter,
+                               cudaStream_t stream) {
+  SWB_REQUIRE(cols % 8 == 0 && pitch % 8 == 0 && (reinterpret_cast<uintptr_t>(buf) & 15) == 0,
+              "count_saturated: cols / pitch must be multiples of 8 elements and the buffer 16-byte aligned");
+  if (rows <= 0 || cols <= 0) return SWB_OK;
+  const long long total = rows * (cols / 8);
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 8LL * num_sms()));
+  count_saturated_f16_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(buf), rows, cols / 8, pitch, counter);
   SWB_CHECK_CUDA(cudaGetLastError());
   return SWB_OK;
 }

@@ -57,6 +57,7 @@ struct GemmParams {
   // EPI_QKV
   const float* qscale;     // [heads]  exp(min(scale, ln 100))
   int heads, dmodel;       // N == 3 * dmodel
+  int qkv_f16;             // format of the packed q / k / v output (may be fp16 while the GEMM operands are bf16)
   // EPI_HEAD
   const float* xt;         // [B, C, H, W] or null
   const float* fprev;      // [B, C, H, W] or null
@@ -700,7 +701,12 @@ __device__ __forceinline__ bool qkv_slot_pack(const GemmParams& p, int n0, float
 #pragma unroll
     for (int j = 0; j < kHeadDim; ++j) v[j] *= inv;
   }
-  pack_row16<F16, 44>(v, w);
+  if constexpr (F16) {
+    pack_row16<true, 44>(v, w);
+  } else {                                                   // bf16 operands: q / k / v may still be stored as fp16
+    if (p.qkv_f16) pack_row16<true, 44>(v, w);
+    else pack_row16<false, 44>(v, w);
+  }
   w[44] = w[45] = w[46] = w[47] = 0u;
   return true;
 }

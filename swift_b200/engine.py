@@ -29,7 +29,7 @@ class Engine:
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], geom: packing.Geometry, device: torch.device,
                  split_embed: bool = True, split_head: bool = True, max_chunk: int = 8, act_fp16: bool = True,
-                 gemm_tile: int = 3, attn_impl: int = 0, fuse_ln: int = 2):
+                 gemm_tile: int = 3, attn_impl: int = 0, fuse_ln: int = 2, attn_fp16: bool = True):
         if device.type != "cuda":
             raise RuntimeError("swift_b200 runs on CUDA devices only (no CPU fallback)")
         self.lib = _lib.lib()
@@ -38,7 +38,7 @@ class Engine:
         self.generation = next(_GENERATION)
         with torch.cuda.device(device):
             self.model, self._keep = packing.pack(state_dict, geom, device, split_embed, split_head, act_fp16,
-                                                   gemm_tile, attn_impl, fuse_ln)
+                                                   gemm_tile, attn_impl, fuse_ln, attn_fp16)
         self.fuse_ln = int(fuse_ln)
         self.act_fp16 = act_fp16
         _lib.check(self.lib.swb200_validate(C.byref(self.model)), "validate")
@@ -78,6 +78,23 @@ class Engine:
         if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
             raise RuntimeError(f"{name}: expected a contiguous float32 CUDA tensor, got {t.dtype} on {t.device} "
                                f"(contiguous={t.is_contiguous()}); swift_b200 has no CPU fallback")
+
+    # ------------------------------------------------------------------ fp16 range diagnostics
+    SATURATION_SLOTS = ("x_hi", "x_lo", "qkv", "attn", "branch", "h")
+
+    def count_saturation(self, on: bool = True) -> None:
+        """Switch the fp16 saturation counters of ``swb200_debug_saturation`` on (zeroed) or off.  Process-global."""
+        if on:
+            self._sat = torch.zeros(len(self.SATURATION_SLOTS), dtype=torch.int64, device=self.device)
+            _lib.check(self.lib.swb200_debug_saturation(self._sat.data_ptr()), "debug_saturation")
+        else:
+            _lib.check(self.lib.swb200_debug_saturation(None), "debug_saturation")
+
+    def saturation_counts(self) -> Dict[str, int]:
+        """Elements found at +-65504 since ``count_saturation(True)``, per tensor class (synchronises)."""
+        if getattr(self, "_sat", None) is None:
+            raise RuntimeError("call count_saturation(True) first")
+        return dict(zip(self.SATURATION_SLOTS, self._sat.tolist()))
 
     # ------------------------------------------------------------------ conditioning
     def conditioning(self, t: torch.Tensor, aux: Optional[torch.Tensor], want_cond: bool = False):

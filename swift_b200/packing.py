@@ -75,7 +75,8 @@ def check_supported(g: Geometry) -> None:
 
 
 def pack(sd: Dict[str, torch.Tensor], g: Geometry, device: torch.device, split_embed: bool = True,
-         split_head: bool = True, act_fp16: bool = True, gemm_tile: int = 3, attn_impl: int = 0, fuse_ln: int = 2):
+         split_head: bool = True, act_fp16: bool = True, gemm_tile: int = 3, attn_impl: int = 0, fuse_ln: int = 2,
+         attn_fp16: bool = True):
     """Returns (``_lib.Model`` struct, dict of device tensors that must stay alive as long as the struct is used)."""
     check_supported(g)
     bf = torch.float16 if act_fp16 else torch.bfloat16     # one 16-bit operand format for activations and weights
@@ -152,6 +153,7 @@ def pack(sd: Dict[str, torch.Tensor], g: Geometry, device: torch.device, split_e
     m.gemm_tile = int(gemm_tile)
     m.attn_impl = int(attn_impl)
     m.fuse_ln = int(fuse_ln)
+    m.attn_fp16 = int(attn_fp16)
     m.timestep_weight = float(g.timestep_weight)
     for name in ("w_embed", "b_embed", "pos_embed", "aux_w", "aux_b", "l1_w", "l1_b", "l2_w", "l2_b", "mod_w",
                  "mod_b", "ln_gamma", "ln_beta", "qscale", "w_qkv", "w_o", "w_1", "w_2", "w_head"):

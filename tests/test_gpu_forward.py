@@ -130,12 +130,17 @@ def test_swift_b_one_step_vs_oracle_and_golden(golden):
     assert err.max() < 0.5 * TOL
     sub = per_field_rel_l2(y[:, :, ::8, ::8], torch.from_numpy(g["scm1_sub"]))
     assert sub.max() < TOL                  # vs the REAL reference's sub-sampled output (512 points per field)
+    # the bf16 operand format north_star names: GEMM operands bf16, attention internals (q, k, v, P) fp16 -- must meet the
+    # same bar; with bf16 attention internals as well (attn_fp16 = False) it is borderline, which is reported
     net.model.act_fp16 = False
-    yb = DiffusionSampler(net).scm_solver(latents=lat.cuda(), condition=cond.cuda(), auxiliary=0.6, num_steps=1,
-                                          sigma_min=0.02, sigma_max=200.0)
-    errb = per_field_rel_l2(yb, ref)
-    print(f"swift_b scm1 (bf16 operands): per-field rel-L2 max {errb.max():.4e} mean {errb.mean():.4e}")
-    assert errb.max() < 1.5 * TOL
+    for attn_fp16, bar in ((True, TOL), (False, 1.5 * TOL)):
+        net.model.attn_fp16 = attn_fp16
+        yb = DiffusionSampler(net).scm_solver(latents=lat.cuda(), condition=cond.cuda(), auxiliary=0.6, num_steps=1,
+                                              sigma_min=0.02, sigma_max=200.0)
+        errb = per_field_rel_l2(yb, ref)
+        print(f"swift_b scm1 (bf16 GEMM operands, {'fp16' if attn_fp16 else 'bf16'} attention internals): per-field "
+              f"rel-L2 max {errb.max():.4e} mean {errb.mean():.4e}")
+        assert errb.max() < bar
 
 
 def test_swift_b_trigflow_2s_vs_oracle():
@@ -199,3 +204,77 @@ def test_chunked_batch_matches_single():
         net.model.max_chunk = 2
         y_chunk = net(lat.cuda(), t, cond.cuda(), 0.6)
     assert torch.equal(y_all, y_chunk)
+
+
+def test_fp16_range_stress_and_saturation_counters():
+    """fp16 operands (the default) have a range of +-65504; every conversion saturates there instead of producing inf
+    (DESIGN.md numerics contract).  A checkpoint with outlier channels is where fp16 and bf16 part ways, so the behaviour
+    at and beyond the limit is pinned here on fixtures whose wo branch and SwiGLU hidden are scaled towards it
+    (LayerNorm follows both, so the fp32 oracle's output hardly moves with the scale):
+      * below the limit (|branch|, |h| up to ~1e4): no saturation is counted and the 1e-2 bar holds;
+      * beyond it: the output stays finite, ``Engine.saturation_counts()`` reports the clipped elements per tensor class
+        (the documented signal to run that checkpoint with ``act_fp16 = False``), and the bf16 operand mode -- same
+        weights -- still meets the bar."""
+    from oracle import swinv2_oracle as orc
+    from swift_b200 import synthetic as syn
+    cfg = syn.SWIFT_SMALL
+    net, sd = build_net(cfg, fuse_ln=0)                      # un-fused LayerNorm: both branch outputs pass through fp16
+    lat, cond = syn.synthetic_fields(cfg, 1, seed=4)
+    x = torch.cat([lat, cond], 1).cuda()
+    t = torch.tensor([1.1], device="cuda")
+    aux = torch.tensor([[0.6]], device="cuda")
+    ocfg = orc.make_cfg(**cfg)
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    hd = cfg["dim"] // cfg["heads"]
+
+    def run(k_wo, k_w1, act_fp16):
+        """wo branch scaled by 2^k_wo (split between the v rows of to_qkv and wo, so the WEIGHTS stay far inside the fp16
+        range), SwiGLU hidden by 4^k_w1 (w1 x 2^k_w1); powers of two keep the weights bf16-representable."""
+        sd2 = dict(sd)
+        for k in sd:
+            if k.endswith(".0.wo.weight"):
+                sd2[k] = sd[k] * 2.0 ** (k_wo - k_wo // 2)
+            elif k.endswith(".0.to_qkv.weight"):
+                w = sd[k].clone().reshape(cfg["heads"], 3, hd, -1)       # rows: (head, q|k|v, d) (swinv2.py:120-121)
+                w[:, 2] *= 2.0 ** (k_wo // 2)
+                sd2[k] = w.reshape(sd[k].shape)
+            elif k.endswith(".1.w1.weight"):
+                sd2[k] = sd[k] * 2.0 ** k_w1
+        net.load_state_dict({"model." + k: v for k, v in sd2.items()}, strict=True)
+        net.model.act_fp16 = act_fp16
+        eng = net.model.engine()
+        eng.count_saturation(True)
+        try:
+            with torch.no_grad():
+                y = net.model(x, t, aux)
+            counts = eng.saturation_counts()
+        finally:
+            eng.count_saturation(False)
+        with torch.no_grad():
+            ref = orc.swinv2_forward({k: v.cuda() for k, v in sd2.items()}, ocfg, x, t, aux)
+        return y, ref, counts
+
+    y, ref, c = run(0, 0, True)
+    assert sum(c.values()) == 0, c
+    assert per_field_rel_l2(y, ref).max() < TOL
+    # find the scales at which the branch / the hidden start to clip
+    k_wo = next(k for k in range(6, 30) if run(k, 0, True)[2]["branch"] > 0)
+    k_w1 = next(k for k in range(2, 14) if run(0, k, True)[2]["h"] > 0)
+    print(f"fp16 range: wo branch clips from x2^{k_wo}, SwiGLU hidden from w1 x2^{k_w1} (x4^{k_w1})")
+    # two octaves below the first clipped element: in range, parity holds
+    y, ref, c = run(k_wo - 2, k_w1 - 1, True)
+    e_near = per_field_rel_l2(y, ref).max().item()
+    assert sum(c.values()) == 0, c
+    assert e_near < TOL, e_near
+    # two octaves beyond: clipped, counted, finite; bf16 operands keep the bar on the same weights
+    y, ref, c = run(k_wo + 2, k_w1 + 1, True)
+    e_far = per_field_rel_l2(y, ref).max().item()
+    assert torch.isfinite(y).all(), "saturating conversions must never produce inf / NaN"
+    assert c["branch"] > 0 and c["h"] > 0, c
+    yb, refb, cb = run(k_wo + 2, k_w1 + 1, False)
+    e_bf16 = per_field_rel_l2(yb, refb).max().item()
+    print(f"fp16 range: near-limit err {e_near:.3e} (counts 0); beyond: fp16 err {e_far:.3e} with {c}; bf16 err {e_bf16:.3e}")
+    assert cb["qkv"] == 0, cb                                 # bf16 mode: only its fp16 attention internals are scanned
+    assert e_bf16 < TOL, e_bf16
+    assert torch.isfinite(yb).all()

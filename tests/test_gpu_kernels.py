@@ -115,11 +115,11 @@ def _window_attention_ref(qkv, B, gh, gw, H, shift):
     return o.permute(1, 2, 3, 0, 4).reshape(M, H * HD)
 
 
-@ACT
+@pytest.mark.parametrize("f16,o16", [(1, 1), (0, 0), (1, 0)], ids=["fp16", "bf16", "fp16qkv-bf16out"])
 @pytest.mark.parametrize("impl", [2, 1], ids=["tcgen05", "mma_sync"])
 @pytest.mark.parametrize("shift", [(0, 0), (8, 8), (8, 0), (3, 5)])
 @pytest.mark.parametrize("B,gh,gw,H", [(1, 16, 32, 3), (2, 32, 32, 2), (1, 64, 128, 12)])
-def test_window_attention(lib, shift, B, gh, gw, H, f16, impl):
+def test_window_attention(lib, shift, B, gh, gw, H, f16, o16, impl):
     if impl == 2 and (shift[0] % 8 or shift[1] % 8):
         pytest.skip("the tcgen05 kernel handles shifts that are multiples of 8 (Swift uses 8)")
     M = B * gh * gw
@@ -130,13 +130,14 @@ def test_window_attention(lib, shift, B, gh, gw, H, f16, impl):
     raw[0] = torch.nn.functional.normalize(raw[0], dim=-1) * qs
     raw[1] = torch.nn.functional.normalize(raw[1], dim=-1)
     qkv = raw.to(_adt(f16)).contiguous()
-    out = torch.full((M, H * HD), float("nan"), device="cuda", dtype=_adt(f16))
-    _check(lib.swb200_window_attention(qkv.data_ptr(), out.data_ptr(), B, gh, gw, H, shift[0], shift[1], f16, impl,
+    out = torch.full((M, H * HD), float("nan"), device="cuda", dtype=_adt(o16))
+    _check(lib.swb200_window_attention(qkv.data_ptr(), out.data_ptr(), B, gh, gw, H, shift[0], shift[1], f16, o16, impl,
                                        _stream()))
     torch.cuda.synchronize()
     ref = _window_attention_ref(qkv, B, gh, gw, H, shift)
     assert torch.isfinite(out.float()).all()
-    assert _rel(out.float(), ref) < (1e-3 if f16 else 8e-3), f"{_rel(out.float(), ref):.3e}"   # P / output rounding
+    tol = 1e-3 if o16 else (3.5e-3 if f16 else 8e-3)      # P / output rounding; fp16 P with a bf16 output: the output's only
+    assert _rel(out.float(), ref) < tol, f"{_rel(out.float(), ref):.3e}"
 
 
 def test_conditioning_matches_oracle(lib):

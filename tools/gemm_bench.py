@@ -44,7 +44,7 @@ def main():
     hb = torch.empty(M, Dff, device="cuda", dtype=dt)
     for cg in cgs:
         cases = {
-            "qkv": (lambda: lib.swb200_gemm_qkv(cg, f16, x.data_ptr(), D, wq.data_ptr(), qs.data_ptr(), qkv.data_ptr(), M, D, H, st), 2.0 * M * 3 * D * D),
+            "qkv": (lambda: lib.swb200_gemm_qkv(cg, f16, f16, x.data_ptr(), D, wq.data_ptr(), qs.data_ptr(), qkv.data_ptr(), M, D, H, st), 2.0 * M * 3 * D * D),
             "wo": (lambda: lib.swb200_gemm(epi_br, cg, f16, x.data_ptr(), D, wo.data_ptr(), D, br.data_ptr(), D, M, D, D, st), 2.0 * M * D * D),
             "w1": (lambda: lib.swb200_gemm_swiglu(cg, f16, x.data_ptr(), D, w1.data_ptr(), hb.data_ptr(), M, D, Dff, st), 2.0 * M * 2 * Dff * D),
             "w2": (lambda: lib.swb200_gemm(epi_br, cg, f16, h.data_ptr(), Dff, w2.data_ptr(), Dff, br.data_ptr(), D, M, D, Dff, st), 2.0 * M * D * Dff),

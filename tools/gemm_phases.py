@@ -66,7 +66,7 @@ def main():
             if name == "qkv":
                 qs = torch.full((12,), 10.0, device="cuda")
                 o2 = torch.empty(3 * 12 * M * 96, device="cuda", dtype=torch.float16)
-                fn = lambda: _lib.check(lib.swb200_gemm_qkv(tile, 1, A.data_ptr(), K, W.data_ptr(), qs.data_ptr(), o2.data_ptr(), M, 1056, 12, st))
+                fn = lambda: _lib.check(lib.swb200_gemm_qkv(tile, 1, 1, A.data_ptr(), K, W.data_ptr(), qs.data_ptr(), o2.data_ptr(), M, 1056, 12, st))
             else:
                 o2 = torch.empty(M, N // 2, device="cuda", dtype=torch.float16)
                 fn = lambda: _lib.check(lib.swb200_gemm_swiglu(tile, 1, A.data_ptr(), K, W.data_ptr(), o2.data_ptr(), M, 1056, N // 2, st))

@@ -11,7 +11,7 @@ for path in sys.argv[1:]:
     l.swb200_gemm_swiglu.restype = C.c_int
     l.swb200_gemm_swiglu.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     l.swb200_gemm_qkv.restype = C.c_int
-    l.swb200_gemm_qkv.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    l.swb200_gemm_qkv.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     libs.append((path.split("/")[-1], l))
 M, N, K = 8 * 8192, 5632, 1056
 st = torch.cuda.current_stream().cuda_stream
@@ -30,7 +30,7 @@ def run(l, which, reps):
         if which == "swiglu":
             rc = l.swb200_gemm_swiglu(3, 1, A.data_ptr(), K, W.data_ptr(), o2.data_ptr(), M, 1056, N // 2, st)
         else:
-            rc = l.swb200_gemm_qkv(3, 1, A.data_ptr(), K, Wq.data_ptr(), qs.data_ptr(), o3.data_ptr(), M, 1056, 12, st)
+            rc = l.swb200_gemm_qkv(3, 1, 1, A.data_ptr(), K, Wq.data_ptr(), qs.data_ptr(), o3.data_ptr(), M, 1056, 12, st)
         assert rc == 0
     e1.record()
     torch.cuda.synchronize()
