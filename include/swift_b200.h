@@ -249,6 +249,117 @@ SWB200_API int swb200_scm_tangent_target(const float* F, const float* dF, const 
                               float sigma_data, const float* w_var, const float* w_lat, int B, int C, int H, int W,
                               float* g, float* cot, float* loss, void* scratch, size_t scratch_bytes, void* stream);
 
+/* ---- reverse mode: the grad-enabled forward + backward of the sCM training step ---------------------------
+ * Reference: `F_x = net(x_t / sigma_d, t, condition, auxiliary)` under autograd (training/loss.py:226-232) followed by
+ * `loss.backward()` (training/trainer.py:199-219).  The training path computes with bf16 tensor-core operands and fp32
+ * accumulation / residual stream / gradients (the reference trains under bf16 autocast); `base.act_fp16` must be 0.
+ * Every Linear's dgrad (dX = dY W) and wgrad (dW = dY^T X, split-K over the tokens) is the tcgen05 GEMM of the forecast
+ * path; swift_b200/csrc/train.cu and attention_bwd.cu hold the derivative rules in between.
+ *
+ * Weights: `base` (geometry, fp32 conditioning parameters, bf16 w_embed / w_head packs as for swb200_forward) plus plain
+ * bf16 copies of the four per-layer matrices in the REFERENCE's row order and their transposes (the dgrad operands):
+ *   w_qkv [depth][3*dim, dim] rows (head, q|k|v, d) as `rearrange(.., "b n (h d) -> b h n d").chunk(3)` reads them
+ *   (models/swinv2.py:119-121); w_1 [depth][2*dff, dim] rows [gate | up] (:99); w_o [depth][dim, dim]; w_2 [depth][dim, dff];
+ *   wt_* = the same matrices transposed ([depth][K, N]); wt_head [dim, kp_head] = head weight^T, kp_head =
+ *   out_channels*p1*p2 rounded up to 8 (zero padded). */
+typedef struct swb200_train_model {
+  swb200_model base;
+  const void* w_qkv;
+  const void* w_o;
+  const void* w_1;
+  const void* w_2;
+  const void* wt_qkv;
+  const void* wt_o;
+  const void* wt_1;
+  const void* wt_2;
+  const void* wt_head;
+  int32_t kp_head;
+} swb200_train_model;
+
+/* fp32 gradient buffers (DEVICE).  accumulate != 0: add to what the buffers hold (gradient accumulation over micro
+ * batches), else overwrite.  Layouts:
+ *   w_qkv / w_o / w_1 / w_2 : as the corresponding swb200_train_model matrices ([depth][N, K], reference row order)
+ *   w_head  [out_channels*p1*p2, dim] (reference row order "(c p1 p2)")
+ *   w_embed_t [k_embed, dim]: TRANSPOSED patch-embed weight gradient, rows in the packed "(c p1 p2)" input-feature order
+ *             (rows >= in_channels*p1*p2 are padding); b_embed [dim]; pos_embed [tokens, dim]
+ *   dscale [depth, heads]: gradient with respect to s = exp(min(scale, ln 100)) (the host applies ds/dscale)
+ *   dgain / dbias [2*depth, B, dim]: gradients of the per-sample LayerNorm gain / bias vectors of swb200_conditioning,
+ *             consumed by swb200_conditioning_backward. */
+typedef struct swb200_train_grads {
+  float* w_qkv;
+  float* w_o;
+  float* w_1;
+  float* w_2;
+  float* w_head;
+  float* w_embed_t;
+  float* b_embed;
+  float* pos_embed;
+  float* dscale;
+  float* dgain;
+  float* dbias;
+  int32_t accumulate;
+} swb200_train_grads;
+
+/* fp32 gradients of the conditioning parameters (shapes of the swb200_model fields of the same names; mod_w / mod_b /
+ * ln_gamma / ln_beta stacked over the 2*depth ModulatedNorms). */
+typedef struct swb200_cond_grads {
+  float* aux_w;
+  float* aux_b;
+  float* l1_w;
+  float* l1_b;
+  float* l2_w;
+  float* l2_b;
+  float* mod_w;
+  float* mod_b;
+  float* ln_gamma;
+  float* ln_beta;
+} swb200_cond_grads;
+
+/* Bytes of the activation tape one grad-enabled forward of B samples writes (and the backward reads), and of the scratch
+ * workspace shared by forward and backward; both 1024-byte aligned.  Host only. */
+SWB200_API size_t swb200_train_tape_bytes(const swb200_train_model* m, int B);
+SWB200_API size_t swb200_train_workspace_bytes(const swb200_train_model* m, int B);
+/* F = SwinV2(cat([x0*scale0, x1])) like swb200_forward (y: NCHW fp32 [B, out_channels, H, W]) on the un-fused training
+ * path, saving per layer the residual pairs, packed q/k/v + inverse norms, attention output, pre-LayerNorm branches,
+ * gate / up and the SwiGLU hidden into `tape`. */
+SWB200_API int swb200_train_forward(const swb200_train_model* m, const float* x0, int c0, float scale0, const float* x1, int c1,
+                         int B, const float* gain, const float* bias, float* y, void* tape, size_t tape_bytes,
+                         void* workspace, size_t workspace_bytes, void* stream);
+/* The backward, in the order a caller overlaps it with gradient communication (trainer.py:76-84 wraps the net in DDP):
+ *   head:  cot = dL/dF (NCHW fp32) -> w_head gradient, the gradient of the residual stream enters `workspace`;
+ *   layer l = depth-1 .. 0: gradients of w_2, w_1, w_o, w_qkv, dscale, dgain / dbias rows 2l+1 and 2l;
+ *   embed: w_embed_t, b_embed, pos_embed.
+ * `workspace` carries the residual-stream gradient from call to call and must not be touched in between. */
+SWB200_API int swb200_train_backward_head(const swb200_train_model* m, int B, const float* cot, const void* tape,
+                               void* workspace, size_t workspace_bytes, const swb200_train_grads* grads, void* stream);
+SWB200_API int swb200_train_backward_layer(const swb200_train_model* m, int layer, int B, const float* gain, const void* tape,
+                                void* workspace, size_t workspace_bytes, const swb200_train_grads* grads, void* stream);
+SWB200_API int swb200_train_backward_embed(const swb200_train_model* m, int B, const void* tape, void* workspace,
+                                size_t workspace_bytes, const swb200_train_grads* grads, void* stream);
+/* Conditioning backward: dgain / dbias [2*depth, B, dim] -> gradients of the LayerNorm affines, the 2*depth modulation
+ * Linears, the latent MLP and the auxiliary embedding.  fwd_scratch: the scratch buffer swb200_conditioning was given for
+ * the same (t, aux) batch, untouched since (it holds the embedding, the MLP activations and the modulation vectors).
+ * scratch: swb200_conditioning_backward_scratch_bytes(m, B) bytes. */
+SWB200_API size_t swb200_conditioning_backward_scratch_bytes(const swb200_model* m, int B);
+SWB200_API int swb200_conditioning_backward(const swb200_model* m, const float* aux, int B, const void* fwd_scratch,
+                                 const float* dgain, const float* dbias, const swb200_cond_grads* grads, int accumulate,
+                                 void* scratch, size_t scratch_bytes, void* stream);
+/* Unit-test entry points of the reverse-mode kernels (see swift_b200/csrc/kernels.h for the argument meaning). */
+SWB200_API int swb200_gemm_splitk(int tile, const void* A, int lda, const void* W, int ldw, float* partials, int ldo, int M,
+                       int N, int K_per_split, int splits, void* stream);
+SWB200_API int swb200_transpose16(const void* in, int rows, int cols, int64_t ldi, void* out, int64_t ldo, void* stream);
+SWB200_API size_t swb200_ln_backward_scratch_bytes(int M, int dim, int tokens);
+SWB200_API int swb200_ln_backward(float* dx, const float* add, const float* branch, const float* gain, void* db16, float* dgain,
+                       float* dbias, int M, int dim, int tokens, int accumulate, void* scratch, size_t scratch_bytes,
+                       void* stream);
+SWB200_API int swb200_swiglu_backward(const float* dh, const void* gu, void* dgu, int M, int dff, void* stream);
+SWB200_API size_t swb200_attention_backward_scratch_bytes(int B, int grid_h, int grid_w, int heads);
+SWB200_API int swb200_attention_backward(const void* qkv, const void* O, const void* dO, const float* invn, const float* qscale,
+                              void* dqkv, float* dscale, int B, int grid_h, int grid_w, int heads, int shift_h, int shift_w,
+                              int accumulate, void* scratch, size_t scratch_bytes, void* stream);
+SWB200_API int swb200_qkv_pack_train(const float* raw, const float* qscale, void* packed, float* invn, int M, int heads,
+                          void* stream);
+
 /* ---- ensemble verification statistics on resident trajectories (eval/metrics.py:39-134) ------------------ */
 
 /* phys [n_ic * members, n_var, H, W] physical-space forecasts, member m of initial condition j at row j*members + m

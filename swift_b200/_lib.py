@@ -24,6 +24,11 @@ EXPORTS = (
     "swb200_conditioning_jvp_scratch_bytes", "swb200_conditioning_jvp", "swb200_forward_jvp",
     "swb200_scm_noised_inputs", "swb200_scm_target_scratch_bytes", "swb200_scm_tangent_target",
     "swb200_debug_saturation",
+    "swb200_train_tape_bytes", "swb200_train_workspace_bytes", "swb200_train_forward", "swb200_train_backward_head",
+    "swb200_train_backward_layer", "swb200_train_backward_embed", "swb200_conditioning_backward_scratch_bytes",
+    "swb200_conditioning_backward", "swb200_gemm_splitk", "swb200_transpose16", "swb200_ln_backward_scratch_bytes",
+    "swb200_ln_backward", "swb200_swiglu_backward", "swb200_attention_backward_scratch_bytes", "swb200_attention_backward",
+    "swb200_qkv_pack_train",
 )
 
 _i32, _f32, _vp, _sz = C.c_int32, C.c_float, C.c_void_p, C.c_size_t
@@ -50,6 +55,24 @@ class Update(C.Structure):
                 ("d_std", _vp), ("phys", _vp)]
 
 
+class TrainModel(C.Structure):
+    """``struct swb200_train_model``: the bf16 base model + plain / transposed bf16 copies of the per-layer matrices."""
+    _fields_ = ([("base", Model)]
+                + [(n, _vp) for n in ("w_qkv", "w_o", "w_1", "w_2", "wt_qkv", "wt_o", "wt_1", "wt_2", "wt_head")]
+                + [("kp_head", _i32)])
+
+
+class TrainGrads(C.Structure):
+    """``struct swb200_train_grads`` (fp32 device buffers)."""
+    _fields_ = ([(n, _vp) for n in ("w_qkv", "w_o", "w_1", "w_2", "w_head", "w_embed_t", "b_embed", "pos_embed", "dscale",
+                                    "dgain", "dbias")] + [("accumulate", _i32)])
+
+
+class CondGrads(C.Structure):
+    """``struct swb200_cond_grads``."""
+    _fields_ = [(n, _vp) for n in ("aux_w", "aux_b", "l1_w", "l1_b", "l2_w", "l2_b", "mod_w", "mod_b", "ln_gamma", "ln_beta")]
+
+
 _ANY_ABI = bool(os.environ.get("SWB_LIB_ANYABI"))     # tools only: time an older build of the library (A/B of kernels)
 _lock = threading.Lock()
 _lib = None
@@ -57,7 +80,26 @@ _lib = None
 
 def _declare(lib):
     MP, UP = C.POINTER(Model), C.POINTER(Update)
+    TP, GP, CP = C.POINTER(TrainModel), C.POINTER(TrainGrads), C.POINTER(CondGrads)
     sig = {
+        "swb200_train_tape_bytes": (_sz, [TP, C.c_int]),
+        "swb200_train_workspace_bytes": (_sz, [TP, C.c_int]),
+        "swb200_train_forward": (C.c_int, [TP, _vp, C.c_int, _f32, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
+        "swb200_train_backward_head": (C.c_int, [TP, C.c_int, _vp, _vp, _vp, _sz, GP, _vp]),
+        "swb200_train_backward_layer": (C.c_int, [TP, C.c_int, C.c_int, _vp, _vp, _vp, _sz, GP, _vp]),
+        "swb200_train_backward_embed": (C.c_int, [TP, C.c_int, _vp, _vp, _sz, GP, _vp]),
+        "swb200_conditioning_backward_scratch_bytes": (_sz, [MP, C.c_int]),
+        "swb200_conditioning_backward": (C.c_int, [MP, _vp, C.c_int, _vp, _vp, _vp, CP, C.c_int, _vp, _sz, _vp]),
+        "swb200_gemm_splitk": (C.c_int, [C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         _vp]),
+        "swb200_transpose16": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int64, _vp, C.c_int64, _vp]),
+        "swb200_ln_backward_scratch_bytes": (_sz, [C.c_int, C.c_int, C.c_int]),
+        "swb200_ln_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _sz, _vp]),
+        "swb200_swiglu_backward": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+        "swb200_attention_backward_scratch_bytes": (_sz, [C.c_int, C.c_int, C.c_int, C.c_int]),
+        "swb200_attention_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                C.c_int, C.c_int, _vp, _sz, _vp]),
+        "swb200_qkv_pack_train": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
         "swb200_abi_version": (C.c_int, []),
         "swb200_last_error": (C.c_char_p, []),
         "swb200_validate": (C.c_int, [MP]),

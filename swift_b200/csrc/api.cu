@@ -774,3 +774,484 @@ SWB200_API int swb200_rollout_advance(int32_t* step, void* stream) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ reverse mode
+// The grad-enabled forward and the backward of the sCM training step (training/loss.py:226-260, trainer.py:199-219):
+// see include/swift_b200.h for the contract, train.cu / attention_bwd.cu for the kernels between the GEMMs.
+
+namespace {
+
+struct Tape {
+  size_t a_emb, x, x_stride, layers, layer_stride;
+  size_t qkv, invn, attn, b1, gu, h, b2;        // offsets inside one layer block
+  size_t total;
+};
+Tape carve_tape(const swb200_model* m, int B) {
+  const Geom g = geom(m);
+  const size_t M = static_cast<size_t>(B) * g.tokens, D = m->dim, Dff = m->dff;
+  Tape t;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 1024);
+    return o;
+  };
+  t.a_emb = take(M * g.k_embed_total * 2);
+  t.x_stride = align_up(M * D * 2 * 2, 1024);
+  t.x = take(t.x_stride * (2 * static_cast<size_t>(m->depth) + 1));
+  t.layers = off;
+  size_t loff = 0;
+  auto ltake = [&](size_t bytes) {
+    size_t o = loff;
+    loff = align_up(loff + bytes, 1024);
+    return o;
+  };
+  t.qkv = ltake(static_cast<size_t>(3) * m->heads * M * kHeadDimPad * 2);
+  t.invn = ltake(static_cast<size_t>(2) * m->heads * M * 4);
+  t.attn = ltake(M * D * 2);
+  t.b1 = ltake(M * D * 4);
+  t.gu = ltake(M * 2 * Dff * 2);
+  t.h = ltake(M * Dff * 2);
+  t.b2 = ltake(M * D * 4);
+  t.layer_stride = loff;
+  t.total = t.layers + t.layer_stride * m->depth;
+  return t;
+}
+
+// split-K factor of a weight-gradient GEMM [n_out, k_in] contracting over `tokens` rows: enough tiles for ~2 waves of the
+// 74 CTA pairs, at least 512 tokens per split
+int choose_splits(int n_out, int k_in, int tokens) {
+  const int tiles = ((n_out + 255) / 256) * ((k_in + 351) / 352);
+  int s = 1;
+  while (s < 16 && tiles * s < 128 && tokens % (2 * s * kBlockK) == 0 && tokens / (2 * s) >= 512) s *= 2;
+  return s;
+}
+
+struct TrainWs {
+  size_t dx, tmp, dy16, da16, dyT, xT, part, lnpart, Lbuf, Dbuf, dspart, total;
+};
+TrainWs carve_train_ws(const swb200_train_model* tm, int B) {
+  const swb200_model* m = &tm->base;
+  const Geom g = geom(m);
+  const size_t M = static_cast<size_t>(B) * g.tokens, D = m->dim, Dff = m->dff, Kp = tm->kp_head;
+  const size_t Ke = m->k_embed;
+  TrainWs w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 1024);
+    return o;
+  };
+  w.dx = take(M * D * 4);
+  w.tmp = take(M * std::max(Dff, 3 * D) * 4);
+  const size_t wide = std::max(std::max(3 * D, 2 * Dff), Kp);
+  w.dy16 = take(M * wide * 2);
+  w.da16 = take(M * D * 2);
+  w.dyT = take(wide * M * 2);
+  w.xT = take(std::max(std::max(Dff, D), Ke) * M * 2);
+  const int Mi = static_cast<int>(M);
+  size_t pf = 0;
+  auto need = [&](size_t n_out, size_t k_in) {
+    pf = std::max(pf, static_cast<size_t>(choose_splits(static_cast<int>(n_out), static_cast<int>(k_in), Mi)) * n_out * k_in);
+  };
+  need(3 * D, D);
+  need(D, D);
+  need(2 * Dff, D);
+  need(D, Dff);
+  need(Kp, D);
+  need(Ke, D);
+  w.part = take(pf * 4);
+  w.lnpart = take((ln_bwd_partial_floats(Mi, m->dim) + 2 * static_cast<size_t>(B) * D + colsum_partial_floats(Mi, m->dim)) * 4);
+  w.Lbuf = take(static_cast<size_t>(m->heads) * M * 4);
+  w.Dbuf = take(static_cast<size_t>(m->heads) * M * 4);
+  const size_t items = static_cast<size_t>(B) * (g.gh / 16) * (g.gw / 16) * m->heads;
+  w.dspart = take((items * 4 + static_cast<size_t>(m->heads) * 4) * 4);
+  w.total = off;
+  return w;
+}
+
+int validate_train(const swb200_train_model* tm) {
+  SWB_REQUIRE(tm != nullptr, "train model is NULL");
+  int rc = validate(&tm->base);
+  if (rc) return rc;
+  SWB_REQUIRE(tm->base.act_fp16 == 0, "the training path computes with bf16 operands: base.act_fp16 must be 0");
+  SWB_REQUIRE(tm->w_qkv && tm->w_o && tm->w_1 && tm->w_2 && tm->wt_qkv && tm->wt_o && tm->wt_1 && tm->wt_2 && tm->wt_head,
+              "train model: NULL weight pointer");
+  const Geom g = geom(&tm->base);
+  SWB_REQUIRE(tm->kp_head % 8 == 0 && tm->kp_head >= tm->base.out_channels * g.pp, "kp_head=%d invalid", tm->kp_head);
+  return SWB_OK;
+}
+
+// dW [n_out, k_in] (+)= dyT [n_out, tokens] * xT [k_in, tokens]^T, split-K over the tokens; `out_rows` <= n_out rows are kept
+int wgrad(const swb200_train_model* tm, const void* dyT, int n_out, const void* xT, int k_in, int tokens, float* part,
+          float* out, int out_rows, int accumulate, cudaStream_t stream) {
+  const int S = choose_splits(n_out, k_in, tokens);
+  GemmParams p = base_params(n_out, k_in, tokens / S);
+  p.out0 = part;
+  p.ldo = k_in;
+  p.splits = S;
+  int rc = launch_gemm(EPI_STORE_F32, tm->base.gemm_tile, 0, dyT, tokens, xT, tokens, p, stream);
+  if (rc) return rc;
+  return launch_splitk_reduce(part, S, static_cast<long long>(n_out) * k_in, out, static_cast<long long>(out_rows) * k_in,
+                              accumulate, stream);
+}
+
+// out [tokens, n_in] = dy16 [tokens, k] * wt [n_in, k]^T
+int dgrad(const swb200_train_model* tm, const void* dy16, int k, const void* wt, int n_in, int tokens, void* out, int epi,
+          cudaStream_t stream) {
+  GemmParams p = base_params(tokens, n_in, k);
+  p.out0 = out;
+  p.ldo = n_in;
+  return launch_gemm(epi, tm->base.gemm_tile, 0, dy16, k, wt, k, p, stream);
+}
+
+}  // namespace
+
+extern "C" {
+
+SWB200_API size_t swb200_train_tape_bytes(const swb200_train_model* tm, int B) {
+  if (validate_train(tm) != SWB_OK || B <= 0) return 0;
+  return carve_tape(&tm->base, B).total;
+}
+
+SWB200_API size_t swb200_train_workspace_bytes(const swb200_train_model* tm, int B) {
+  if (validate_train(tm) != SWB_OK || B <= 0) return 0;
+  return carve_train_ws(tm, B).total;
+}
+
+SWB200_API int swb200_train_forward(const swb200_train_model* tm, const float* x0, int c0, float scale0, const float* x1, int c1,
+                                    int B, const float* gain, const float* bias, float* y, void* tape_, size_t tape_bytes,
+                                    void* workspace, size_t workspace_bytes, void* stream_) {
+  int rc = validate_train(tm);
+  if (rc) return rc;
+  const swb200_model* m = &tm->base;
+  SWB_REQUIRE(B > 0 && x0 && gain && bias && y && tape_ && workspace, "train_forward: NULL argument or B=%d", B);
+  SWB_REQUIRE(c0 + c1 == m->in_channels && (c1 == 0 || x1 != nullptr), "train_forward: c0+c1=%d != in_channels=%d", c0 + c1,
+              m->in_channels);
+  const Tape t = carve_tape(m, B);
+  const TrainWs w = carve_train_ws(tm, B);
+  SWB_REQUIRE(tape_bytes >= t.total && workspace_bytes >= w.total, "train_forward: tape (%zu < %zu) or workspace (%zu < %zu) too small",
+              tape_bytes, t.total, workspace_bytes, w.total);
+  SWB_REQUIRE(((reinterpret_cast<uintptr_t>(tape_) | reinterpret_cast<uintptr_t>(workspace)) & 1023) == 0,
+              "train_forward: tape and workspace must be 1024-byte aligned");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const Geom g = geom(m);
+  const int D = m->dim, H = m->heads, Dff = m->dff, tile = m->gemm_tile;
+  const int M = B * g.tokens;
+  uint8_t* tp = static_cast<uint8_t*>(tape_);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  float* raw = reinterpret_cast<float*>(ws + w.tmp);
+  auto xbuf = [&](int i) { return tp + t.x + t.x_stride * static_cast<size_t>(i); };
+  void* a_emb = tp + t.a_emb;
+  rc = launch_patch_gather(x0, c0, scale0, x1, c1, a_emb, g.k_embed_total, m->k_embed, m->split_embed, 0, B, m->img_h, m->img_w,
+                           m->patch_h, m->patch_w, stream);
+  if (rc) return rc;
+  {
+    GemmParams p = base_params(M, D, g.k_embed_total);
+    p.out0 = xbuf(0);
+    p.ldo = 2 * D;
+    p.bias = m->b_embed;
+    p.pos = m->pos_embed;
+    p.pos_rows = g.tokens;
+    rc = launch_gemm(EPI_EMBED, tile, 0, a_emb, g.k_embed_total, m->w_embed, g.k_embed_total, p, stream);
+    if (rc) return rc;
+  }
+  const size_t xbytes = static_cast<size_t>(M) * D * 2 * 2;
+  for (int l = 0; l < m->depth; ++l) {
+    uint8_t* lb = tp + t.layers + t.layer_stride * static_cast<size_t>(l);
+    const bool shifted = (m->shift_h || m->shift_w) && (l & 1);
+    void* x0p = xbuf(2 * l);
+    void* x1p = xbuf(2 * l + 1);
+    void* x2p = xbuf(2 * l + 2);
+    {   // to_qkv (reference row order) -> raw fp32 -> normalise / scale / pack
+      GemmParams p = base_params(M, 3 * D, D);
+      p.out0 = raw;
+      p.ldo = 3 * D;
+      const auto* wq = static_cast<const __nv_bfloat16*>(tm->w_qkv) + static_cast<size_t>(l) * 3 * D * D;
+      rc = launch_gemm(EPI_STORE_F32, tile, 0, x0p, 2 * D, wq, D, p, stream);
+      if (rc) return rc;
+      rc = launch_qkv_pack_train(raw, m->qscale + static_cast<size_t>(l) * H, lb + t.qkv, reinterpret_cast<float*>(lb + t.invn), M,
+                                 H, kHeadDim, kHeadDimPad, stream);
+      if (rc) return rc;
+    }
+    rc = launch_window_attention(lb + t.qkv, lb + t.attn, B, g.gh, g.gw, H, shifted ? m->shift_h : 0, shifted ? m->shift_w : 0, 0, 0,
+                                 m->attn_impl, stream);
+    if (rc) return rc;
+    {
+      GemmParams p = base_params(M, D, D);
+      p.out0 = lb + t.b1;
+      p.ldo = D;
+      const auto* wo = static_cast<const __nv_bfloat16*>(tm->w_o) + static_cast<size_t>(l) * D * D;
+      rc = launch_gemm(EPI_STORE_F32, tile, 0, lb + t.attn, D, wo, D, p, stream);
+      if (rc) return rc;
+    }
+    SWB_CHECK_CUDA(cudaMemcpyAsync(x1p, x0p, xbytes, cudaMemcpyDeviceToDevice, stream));
+    rc = launch_ln_mod_residual(lb + t.b1, 0, x1p, gain + static_cast<size_t>(2 * l) * B * D, bias + static_cast<size_t>(2 * l) * B * D,
+                                M, D, g.tokens, 1e-6f, 0, stream);
+    if (rc) return rc;
+    {
+      GemmParams p = base_params(M, 2 * Dff, D);
+      p.out0 = lb + t.gu;
+      p.ldo = 2 * Dff;
+      const auto* w1 = static_cast<const __nv_bfloat16*>(tm->w_1) + static_cast<size_t>(l) * 2 * Dff * D;
+      rc = launch_gemm(EPI_STORE_ACT, tile, 0, x1p, 2 * D, w1, D, p, stream);
+      if (rc) return rc;
+      rc = launch_swiglu_fwd_train(lb + t.gu, lb + t.h, M, Dff, stream);
+      if (rc) return rc;
+    }
+    {
+      GemmParams p = base_params(M, D, Dff);
+      p.out0 = lb + t.b2;
+      p.ldo = D;
+      const auto* w2 = static_cast<const __nv_bfloat16*>(tm->w_2) + static_cast<size_t>(l) * D * Dff;
+      rc = launch_gemm(EPI_STORE_F32, tile, 0, lb + t.h, Dff, w2, Dff, p, stream);
+      if (rc) return rc;
+    }
+    SWB_CHECK_CUDA(cudaMemcpyAsync(x2p, x1p, xbytes, cudaMemcpyDeviceToDevice, stream));
+    rc = launch_ln_mod_residual(lb + t.b2, 0, x2p, gain + static_cast<size_t>(2 * l + 1) * B * D,
+                                bias + static_cast<size_t>(2 * l + 1) * B * D, M, D, g.tokens, 1e-6f, 0, stream);
+    if (rc) return rc;
+  }
+  swb200_update u = {};
+  u.beta = 1.0f;
+  u.zero_channel = -1;
+  return swb200_gemm_head(tile, m, xbuf(2 * m->depth), 2 * D, g.k_head_total, B, &u, y, stream_);
+}
+
+SWB200_API int swb200_train_backward_head(const swb200_train_model* tm, int B, const float* cot, const void* tape_,
+                                          void* workspace, size_t workspace_bytes, const swb200_train_grads* gr, void* stream_) {
+  int rc = validate_train(tm);
+  if (rc) return rc;
+  const swb200_model* m = &tm->base;
+  SWB_REQUIRE(B > 0 && cot && tape_ && workspace && gr && gr->w_head, "train_backward_head: NULL argument");
+  const Tape t = carve_tape(m, B);
+  const TrainWs w = carve_train_ws(tm, B);
+  SWB_REQUIRE(workspace_bytes >= w.total, "train_backward_head: workspace too small");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const Geom g = geom(m);
+  const int D = m->dim, M = B * g.tokens, Kp = tm->kp_head, Nh = m->out_channels * g.pp;
+  const uint8_t* tp = static_cast<const uint8_t*>(tape_);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  void* dF16 = ws + w.dy16;
+  rc = launch_cot_patchify(cot, dF16, B, m->out_channels, m->img_h, m->img_w, m->patch_h, m->patch_w, Kp, stream);
+  if (rc) return rc;
+  rc = dgrad(tm, dF16, Kp, tm->wt_head, D, M, ws + w.dx, EPI_STORE_F32, stream);
+  if (rc) return rc;
+  rc = launch_transpose16(dF16, M, Kp, Kp, ws + w.dyT, M, stream);
+  if (rc) return rc;
+  const void* xL = tp + t.x + t.x_stride * static_cast<size_t>(2 * m->depth);
+  rc = launch_transpose16(xL, M, D, 2 * D, ws + w.xT, M, stream);
+  if (rc) return rc;
+  return wgrad(tm, ws + w.dyT, Kp, ws + w.xT, D, M, reinterpret_cast<float*>(ws + w.part), gr->w_head, Nh, gr->accumulate, stream);
+}
+
+SWB200_API int swb200_train_backward_layer(const swb200_train_model* tm, int l, int B, const float* gain, const void* tape_,
+                                           void* workspace, size_t workspace_bytes, const swb200_train_grads* gr, void* stream_) {
+  int rc = validate_train(tm);
+  if (rc) return rc;
+  const swb200_model* m = &tm->base;
+  SWB_REQUIRE(B > 0 && gain && tape_ && workspace && gr && l >= 0 && l < m->depth, "train_backward_layer: bad argument (layer %d)", l);
+  SWB_REQUIRE(gr->w_qkv && gr->w_o && gr->w_1 && gr->w_2 && gr->dscale && gr->dgain && gr->dbias, "train_backward_layer: NULL gradient buffer");
+  const Tape t = carve_tape(m, B);
+  const TrainWs w = carve_train_ws(tm, B);
+  SWB_REQUIRE(workspace_bytes >= w.total, "train_backward_layer: workspace too small");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const Geom g = geom(m);
+  const int D = m->dim, H = m->heads, Dff = m->dff, M = B * g.tokens, acc = gr->accumulate;
+  const uint8_t* tp = static_cast<const uint8_t*>(tape_);
+  const uint8_t* lb = tp + t.layers + t.layer_stride * static_cast<size_t>(l);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  float* dx = reinterpret_cast<float*>(ws + w.dx);
+  float* tmp = reinterpret_cast<float*>(ws + w.tmp);
+  void* dy16 = ws + w.dy16;
+  void* dyT = ws + w.dyT;
+  void* xT = ws + w.xT;
+  float* part = reinterpret_cast<float*>(ws + w.part);
+  float* lnpart = reinterpret_cast<float*>(ws + w.lnpart);
+  const void* x0p = tp + t.x + t.x_stride * static_cast<size_t>(2 * l);
+  const void* x1p = tp + t.x + t.x_stride * static_cast<size_t>(2 * l + 1);
+  const bool shifted = (m->shift_h || m->shift_w) && (l & 1);
+  const size_t vec = static_cast<size_t>(B) * D;
+  using bf = __nv_bfloat16;
+
+  // ---- feed-forward branch: x2 = x1 + LNmod(w2 (silu(g) u)),  [g | u] = w1 x1
+  rc = launch_ln_bwd(dx, nullptr, reinterpret_cast<const float*>(lb + t.b2), gain + (2 * l + 1) * vec, dy16, lnpart,
+                     gr->dgain + (2 * l + 1) * vec, gr->dbias + (2 * l + 1) * vec, M, D, g.tokens, 1e-6f, acc, stream);
+  if (rc) return rc;
+  if ((rc = launch_transpose16(dy16, M, D, D, dyT, M, stream))) return rc;
+  if ((rc = launch_transpose16(lb + t.h, M, Dff, Dff, xT, M, stream))) return rc;
+  if ((rc = wgrad(tm, dyT, D, xT, Dff, M, part, gr->w_2 + static_cast<size_t>(l) * D * Dff, D, acc, stream))) return rc;
+  if ((rc = dgrad(tm, dy16, D, static_cast<const bf*>(tm->wt_2) + static_cast<size_t>(l) * Dff * D, Dff, M, tmp, EPI_STORE_F32, stream)))
+    return rc;
+  if ((rc = launch_swiglu_bwd(tmp, lb + t.gu, dy16, M, Dff, stream))) return rc;
+  if ((rc = launch_transpose16(dy16, M, 2 * Dff, 2 * Dff, dyT, M, stream))) return rc;
+  if ((rc = launch_transpose16(x1p, M, D, 2 * D, xT, M, stream))) return rc;
+  if ((rc = wgrad(tm, dyT, 2 * Dff, xT, D, M, part, gr->w_1 + static_cast<size_t>(l) * 2 * Dff * D, 2 * Dff, acc, stream))) return rc;
+  if ((rc = dgrad(tm, dy16, 2 * Dff, static_cast<const bf*>(tm->wt_1) + static_cast<size_t>(l) * D * 2 * Dff, D, M, tmp, EPI_STORE_F32,
+                  stream)))
+    return rc;
+  // ---- attention branch: x1 = x0 + LNmod(wo attention(qkv x0));  dx <- dx + (w1 dgrad) on the way
+  rc = launch_ln_bwd(dx, tmp, reinterpret_cast<const float*>(lb + t.b1), gain + (2 * l) * vec, dy16, lnpart, gr->dgain + (2 * l) * vec,
+                     gr->dbias + (2 * l) * vec, M, D, g.tokens, 1e-6f, acc, stream);
+  if (rc) return rc;
+  if ((rc = launch_transpose16(dy16, M, D, D, dyT, M, stream))) return rc;
+  if ((rc = launch_transpose16(lb + t.attn, M, D, D, xT, M, stream))) return rc;
+  if ((rc = wgrad(tm, dyT, D, xT, D, M, part, gr->w_o + static_cast<size_t>(l) * D * D, D, acc, stream))) return rc;
+  if ((rc = dgrad(tm, dy16, D, static_cast<const bf*>(tm->wt_o) + static_cast<size_t>(l) * D * D, D, M, ws + w.da16, EPI_STORE_ACT, stream)))
+    return rc;
+  float* dspart = reinterpret_cast<float*>(ws + w.dspart);
+  rc = launch_attention_bwd(lb + t.qkv, lb + t.attn, ws + w.da16, reinterpret_cast<const float*>(lb + t.invn),
+                            m->qscale + static_cast<size_t>(l) * H, dy16, reinterpret_cast<float*>(ws + w.Lbuf),
+                            reinterpret_cast<float*>(ws + w.Dbuf), dspart, B, g.gh, g.gw, H, kHeadDim, kHeadDimPad,
+                            shifted ? m->shift_h : 0, shifted ? m->shift_w : 0, stream);
+  if (rc) return rc;
+  {   // ds[head] = sum over (sample, window, 64-row tile) of the block partials: [bw][head][4] -> [head][4] -> [head]
+    const int per = B * (g.gh / 16) * (g.gw / 16);
+    float* small = dspart + static_cast<size_t>(per) * H * 4;
+    if ((rc = launch_reduce_partials(dspart, per, H * 4, small, 1, 0, stream))) return rc;
+    if ((rc = launch_reduce_partials(small, 4, 1, gr->dscale + static_cast<size_t>(l) * H, H, acc, stream))) return rc;
+  }
+  if ((rc = launch_transpose16(dy16, M, 3 * D, 3 * D, dyT, M, stream))) return rc;
+  if ((rc = launch_transpose16(x0p, M, D, 2 * D, xT, M, stream))) return rc;
+  if ((rc = wgrad(tm, dyT, 3 * D, xT, D, M, part, gr->w_qkv + static_cast<size_t>(l) * 3 * D * D, 3 * D, acc, stream))) return rc;
+  if ((rc = dgrad(tm, dy16, 3 * D, static_cast<const bf*>(tm->wt_qkv) + static_cast<size_t>(l) * D * 3 * D, D, M, tmp, EPI_STORE_F32,
+                  stream)))
+    return rc;
+  return launch_add_f32(dx, tmp, dx, nullptr, static_cast<long long>(M) * D, stream);
+}
+
+SWB200_API int swb200_train_backward_embed(const swb200_train_model* tm, int B, const void* tape_, void* workspace,
+                                           size_t workspace_bytes, const swb200_train_grads* gr, void* stream_) {
+  int rc = validate_train(tm);
+  if (rc) return rc;
+  const swb200_model* m = &tm->base;
+  SWB_REQUIRE(B > 0 && tape_ && workspace && gr && gr->w_embed_t && gr->b_embed && gr->pos_embed, "train_backward_embed: NULL argument");
+  const Tape t = carve_tape(m, B);
+  const TrainWs w = carve_train_ws(tm, B);
+  SWB_REQUIRE(workspace_bytes >= w.total, "train_backward_embed: workspace too small");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const Geom g = geom(m);
+  const int D = m->dim, M = B * g.tokens, Ke = m->k_embed, acc = gr->accumulate;
+  const uint8_t* tp = static_cast<const uint8_t*>(tape_);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  float* dx = reinterpret_cast<float*>(ws + w.dx);
+  float* lnpart = reinterpret_cast<float*>(ws + w.lnpart);
+  if ((rc = launch_add_f32(dx, nullptr, nullptr, ws + w.dy16, static_cast<long long>(M) * D, stream))) return rc;
+  if ((rc = launch_sum_over_samples(dx, B, static_cast<long long>(g.tokens) * D, gr->pos_embed, acc, stream))) return rc;
+  if ((rc = launch_colsum(dx, M, D, lnpart, gr->b_embed, acc, stream))) return rc;
+  if ((rc = launch_transpose16(ws + w.dy16, M, D, D, ws + w.dyT, M, stream))) return rc;
+  if ((rc = launch_transpose16(tp + t.a_emb, M, Ke, g.k_embed_total, ws + w.xT, M, stream))) return rc;
+  return wgrad(tm, ws + w.xT, Ke, ws + w.dyT, D, M, reinterpret_cast<float*>(ws + w.part), gr->w_embed_t, Ke, acc, stream);
+}
+
+SWB200_API size_t swb200_conditioning_backward_scratch_bytes(const swb200_model* m, int B) {
+  if (m == nullptr || B <= 0) return 0;
+  return conditioning_bwd_scratch_floats(B, m->dim, 2 * m->depth) * sizeof(float);
+}
+
+SWB200_API int swb200_conditioning_backward(const swb200_model* m, const float* aux, int B, const void* fwd_scratch,
+                                            const float* dgain, const float* dbias, const swb200_cond_grads* gr, int accumulate,
+                                            void* scratch, size_t scratch_bytes, void* stream) {
+  int rc = validate(m);
+  if (rc) return rc;
+  SWB_REQUIRE(B > 0 && fwd_scratch && dgain && dbias && gr && scratch, "conditioning_backward: NULL argument");
+  SWB_REQUIRE(gr->l1_w && gr->l1_b && gr->l2_w && gr->l2_b && gr->mod_w && gr->mod_b && gr->ln_gamma && gr->ln_beta,
+              "conditioning_backward: NULL gradient buffer");
+  SWB_REQUIRE(scratch_bytes >= swb200_conditioning_backward_scratch_bytes(m, B), "conditioning_backward: scratch too small");
+  CondWeights w;
+  w.aux_w = m->aux_w;
+  w.aux_b = m->aux_b;
+  w.aux_dim = m->aux_dim;
+  w.l1_w = m->l1_w;
+  w.l1_b = m->l1_b;
+  w.l2_w = m->l2_w;
+  w.l2_b = m->l2_b;
+  w.mod_w = m->mod_w;
+  w.mod_b = m->mod_b;
+  w.ln_gamma = m->ln_gamma;
+  w.ln_beta = m->ln_beta;
+  CondGrads g;
+  g.aux_w = gr->aux_w;
+  g.aux_b = gr->aux_b;
+  g.l1_w = gr->l1_w;
+  g.l1_b = gr->l1_b;
+  g.l2_w = gr->l2_w;
+  g.l2_b = gr->l2_b;
+  g.mod_w = gr->mod_w;
+  g.mod_b = gr->mod_b;
+  g.ln_gamma = gr->ln_gamma;
+  g.ln_beta = gr->ln_beta;
+  const float* aux_eff = (m->aux_dim > 0 && m->aux_w != nullptr) ? aux : nullptr;
+  return launch_conditioning_bwd(w, g, aux_eff, static_cast<const float*>(fwd_scratch), dgain, dbias, B, m->dim, 2 * m->depth,
+                                 static_cast<float*>(scratch), accumulate, static_cast<cudaStream_t>(stream));
+}
+
+// ---- unit-test entry points of the reverse-mode kernels
+SWB200_API int swb200_gemm_splitk(int tile, const void* A, int lda, const void* W, int ldw, float* partials, int ldo, int M, int N,
+                                  int K_per_split, int splits, void* stream) {
+  SWB_REQUIRE(A && W && partials, "swb200_gemm_splitk: NULL pointer");
+  GemmParams p = base_params(M, N, K_per_split);
+  p.out0 = partials;
+  p.ldo = ldo;
+  p.splits = splits;
+  return launch_gemm(EPI_STORE_F32, tile, 0, A, lda, W, ldw, p, static_cast<cudaStream_t>(stream));
+}
+
+SWB200_API int swb200_transpose16(const void* in, int rows, int cols, int64_t ldi, void* out, int64_t ldo, void* stream) {
+  SWB_REQUIRE(in && out, "swb200_transpose16: NULL pointer");
+  return launch_transpose16(in, rows, cols, ldi, out, ldo, static_cast<cudaStream_t>(stream));
+}
+
+SWB200_API size_t swb200_ln_backward_scratch_bytes(int M, int dim, int tokens) {
+  if (M <= 0 || dim <= 0 || tokens <= 0) return 0;
+  return (ln_bwd_partial_floats(M, dim) + 2 * static_cast<size_t>(M / tokens) * dim) * sizeof(float);
+}
+
+SWB200_API int swb200_ln_backward(float* dx, const float* add, const float* branch, const float* gain, void* db16, float* dgain,
+                                  float* dbias, int M, int dim, int tokens, int accumulate, void* scratch, size_t scratch_bytes,
+                                  void* stream) {
+  SWB_REQUIRE(dx && branch && gain && db16 && dgain && dbias && scratch, "swb200_ln_backward: NULL pointer");
+  SWB_REQUIRE(scratch_bytes >= swb200_ln_backward_scratch_bytes(M, dim, tokens), "swb200_ln_backward: scratch too small");
+  return launch_ln_bwd(dx, add, branch, gain, db16, static_cast<float*>(scratch), dgain, dbias, M, dim, tokens, 1e-6f, accumulate,
+                       static_cast<cudaStream_t>(stream));
+}
+
+SWB200_API int swb200_swiglu_backward(const float* dh, const void* gu, void* dgu, int M, int dff, void* stream) {
+  SWB_REQUIRE(dh && gu && dgu, "swb200_swiglu_backward: NULL pointer");
+  return launch_swiglu_bwd(dh, gu, dgu, M, dff, static_cast<cudaStream_t>(stream));
+}
+
+SWB200_API size_t swb200_attention_backward_scratch_bytes(int B, int grid_h, int grid_w, int heads) {
+  if (B <= 0 || grid_h <= 0 || grid_w <= 0 || heads <= 0) return 0;
+  const size_t M = static_cast<size_t>(B) * grid_h * grid_w;
+  const size_t items = static_cast<size_t>(B) * (grid_h / 16) * (grid_w / 16) * heads;
+  return (2 * heads * M + items * 4 + static_cast<size_t>(heads) * 4) * sizeof(float);
+}
+
+SWB200_API int swb200_attention_backward(const void* qkv, const void* O, const void* dO, const float* invn, const float* qscale,
+                                         void* dqkv, float* dscale, int B, int grid_h, int grid_w, int heads, int shift_h,
+                                         int shift_w, int accumulate, void* scratch, size_t scratch_bytes, void* stream_) {
+  SWB_REQUIRE(qkv && O && dO && invn && qscale && dqkv && dscale && scratch, "swb200_attention_backward: NULL pointer");
+  SWB_REQUIRE(scratch_bytes >= swb200_attention_backward_scratch_bytes(B, grid_h, grid_w, heads),
+              "swb200_attention_backward: scratch too small");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const size_t M = static_cast<size_t>(B) * grid_h * grid_w;
+  float* Lbuf = static_cast<float*>(scratch);
+  float* Dbuf = Lbuf + heads * M;
+  float* dspart = Dbuf + heads * M;
+  int rc = launch_attention_bwd(qkv, O, dO, invn, qscale, dqkv, Lbuf, Dbuf, dspart, B, grid_h, grid_w, heads, kHeadDim, kHeadDimPad,
+                                shift_h, shift_w, stream);
+  if (rc) return rc;
+  const int per = B * (grid_h / 16) * (grid_w / 16);
+  float* small = dspart + static_cast<size_t>(per) * heads * 4;
+  if ((rc = launch_reduce_partials(dspart, per, heads * 4, small, 1, 0, stream))) return rc;
+  return launch_reduce_partials(small, 4, 1, dscale, heads, accumulate, stream);
+}
+
+SWB200_API int swb200_qkv_pack_train(const float* raw, const float* qscale, void* packed, float* invn, int M, int heads,
+                                     void* stream) {
+  SWB_REQUIRE(raw && qscale && packed && invn, "swb200_qkv_pack_train: NULL pointer");
+  return launch_qkv_pack_train(raw, qscale, packed, invn, M, heads, kHeadDim, kHeadDimPad, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -49,6 +49,10 @@ struct GemmParams {
   void* out0;
   void* out1;
   int ldo;                 // row pitch (elements) of out0/out1 for the plain / embed / swiglu epilogues
+  // split-K (EPI_STORE_F32 only; the weight-gradient GEMMs contract over tokens and have few output tiles): the K
+  // extent of A and W is splits * K, split s reads columns [s*K, (s+1)*K) and stores its partial product at rows
+  // [s*M, (s+1)*M) of out0 ([splits * M, ldo]); K % 64 == 0 when splits > 1.  0 / 1 = no split.
+  int splits;
   int tma_store;           // EPI_STORE_ACT / EPI_QKV / EPI_SWIGLU: write the 16-bit output with TMA tile stores (tmap_o0/o1)
   // EPI_EMBED
   const float* bias;       // [N]
@@ -1075,7 +1079,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   const int tiles_n = (p.N + kTileN - 1) / kTileN;
   const int tiles_m = (p.M + kBlockM * CG - 1) / (kBlockM * CG);
-  const int num_tiles = tiles_m * tiles_n;
+  const int tiles_mn = tiles_m * tiles_n;
+  const int num_tiles = tiles_mn * (p.splits > 1 ? p.splits : 1);       // split-K: split-major tile order
   const int num_kb = (p.K + kBlockK - 1) / kBlockK;
   const int tail_k = p.K - (num_kb - 1) * kBlockK;
   const int tail_ksteps = (tail_k + kUmmaK - 1) / kUmmaK;
@@ -1120,9 +1125,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
+      const int split = tile / tiles_mn, tmn = tile - split * tiles_mn;
+      const int tm = tmn / tiles_n, tn = tmn - tm * tiles_n;
       const int row0 = tm * (kBlockM * CG) + static_cast<int>(cta_rank) * kBlockM;
       const int col0 = tn * kTileN + static_cast<int>(cta_rank) * S::kBRows;
+      const int k0 = split * p.K;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u, 1);
         if (cta_rank == 0) mbar_arrive_expect_tx_elect(full_bar(stage), S::kStageBytes * CG);
@@ -1130,11 +1137,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const uint32_t b_dst = smem_b + stage * S::kBBytes;
         if constexpr (CG == 2) {
           const uint32_t bar = full_leader0 + 8u * stage;
-          tma_load_2d_pair_elect(a_dst, &tmap_a, bar, kb * kBlockK, row0);
-          tma_load_2d_pair_elect(b_dst, &tmap_b, bar, kb * kBlockK, col0);
+          tma_load_2d_pair_elect(a_dst, &tmap_a, bar, k0 + kb * kBlockK, row0);
+          tma_load_2d_pair_elect(b_dst, &tmap_b, bar, k0 + kb * kBlockK, col0);
         } else {
-          tma_load_2d_elect(a_dst, &tmap_a, full_bar(stage), kb * kBlockK, row0);
-          tma_load_2d_elect(b_dst, &tmap_b, full_bar(stage), kb * kBlockK, col0);
+          tma_load_2d_elect(a_dst, &tmap_a, full_bar(stage), k0 + kb * kBlockK, row0);
+          tma_load_2d_elect(b_dst, &tmap_b, full_bar(stage), k0 + kb * kBlockK, col0);
         }
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
@@ -1248,7 +1255,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const uint32_t par = static_cast<uint32_t>(it) & 1u;
-      const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
+      const int split = tile / tiles_mn, tmn = tile - split * tiles_mn;
+      const int tm = tmn / tiles_n, tn = tmn - tm * tiles_n;
       const int n_tile = tn * kTileN;
       if constexpr (EPI == EPI_LN_RES) {
         const int r0 = tm * (kBlockM * CG) + static_cast<int>(cta_rank) * kBlockM + quad * 32;
@@ -1269,6 +1277,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       e.row0 = tm * (kBlockM * CG) + static_cast<int>(cta_rank) * kBlockM + quad * 32;
       const int rv = p.M - e.row0;
       e.rows_valid = rv < 0 ? 0 : (rv > 32 ? 32 : rv);
+      if constexpr (EPI == EPI_STORE_F32) e.row0 += split * p.M;       // split-K partial products are stacked along the rows
       // Accumulator columns [0,88) and [88,176) of sub-tile j hold the global 88-column slots
       //   CG == 2:  s = j and s = NSUB + j   (the pair splits the staged W rows in two contiguous halves)
       //   CG == 1:  s = 0 and s = 1

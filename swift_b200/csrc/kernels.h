@@ -63,6 +63,44 @@ int launch_conditioning_dual(const CondWeights& w, const float* t, const float* 
                              float timestep_weight, float* scratch, float* gain, float* bias, float* dgain, float* dbias,
                              cudaStream_t stream);
 
+// ---- reverse mode (train.cu, attention_bwd.cu): see the headers of those files
+struct CondGrads {          // fp32 gradients of the conditioning parameters, same shapes as CondWeights
+  float* aux_w;
+  float* aux_b;
+  float* l1_w;
+  float* l1_b;
+  float* l2_w;
+  float* l2_b;
+  float* mod_w;
+  float* mod_b;
+  float* ln_gamma;
+  float* ln_beta;
+};
+int launch_swiglu_fwd_train(const void* gu, void* h, int M, int Dff, cudaStream_t stream);
+int launch_swiglu_bwd(const float* dh, const void* gu, void* dgu, int M, int Dff, cudaStream_t stream);
+int launch_qkv_pack_train(const float* raw, const float* qscale, void* packed, float* invn, int M, int heads, int hd,
+                          int pad, cudaStream_t stream);
+int launch_transpose16(const void* in, int R, int C, long long ldi, void* out, long long ldo, cudaStream_t stream);
+size_t ln_bwd_partial_floats(int M, int D);       // + 2*B*D floats of reduction scratch behind it
+int launch_ln_bwd(float* dx, const float* add, const float* branch, const float* gain, void* db16, float* part,
+                  float* dgain, float* dbias, int M, int D, int tokens, float eps, int accumulate, cudaStream_t stream);
+int launch_reduce_partials(const float* part, int per, int width, float* out, int groups, int accumulate,
+                           cudaStream_t stream);
+size_t colsum_partial_floats(int R, int W);
+int launch_colsum(const float* in, int R, int W, float* part, float* out, int accumulate, cudaStream_t stream);
+int launch_splitk_reduce(const float* part, int splits, long long stride, float* out, long long n, int accumulate,
+                         cudaStream_t stream);
+int launch_add_f32(const float* a, const float* b, float* dst, void* dst16, long long n, cudaStream_t stream);
+int launch_cot_patchify(const float* cot, void* dF, int B, int C, int H, int W, int p1, int p2, int Kp, cudaStream_t stream);
+int launch_sum_over_samples(const float* dx, int B, long long per, float* out, int accumulate, cudaStream_t stream);
+size_t conditioning_bwd_scratch_floats(int B, int D, int L);
+int launch_conditioning_bwd(const CondWeights& w, const CondGrads& g, const float* aux, const float* fwd_scratch,
+                            const float* dgain, const float* dbias, int B, int D, int L, float* scratch, int accumulate,
+                            cudaStream_t stream);
+int launch_attention_bwd(const void* qkv, const void* O, const void* dO, const float* invn, const float* qscale, void* dqkv,
+                         float* Lbuf, float* Dbuf, float* ds_part, int B, int gh, int gw, int heads, int hd, int pad,
+                         int shift_h, int shift_w, cudaStream_t stream);
+
 // ensemble verification statistics (ensemble.cu): out[(*step) * out_stride + (ic * V + v) * 4 + k]
 int launch_ensemble_stats(const float* phys, const float* truth, const float* w_lat, int n_ic, int members, int V, int H,
                           int W, const int* step, int n_steps, int out_stride, double* out, cudaStream_t stream);

@@ -10,9 +10,8 @@
 
 Because F_x - sg(F_x) == 0, the loss value and its gradient with respect to the network output depend on g only:
 ``dL/dF_x = -2 w g / (B H W)``.  ``scm_output_cotangent`` returns exactly that, from ONE stacked primal + tangent pass of
-the CUDA engine (``swb200_forward_jvp``; the reference runs the network twice here).  The reverse pass that would consume
-``cot`` is not built: with the reference module as ``net`` for the backward, a training step is
-``F_x = net(...); F_x.backward(cot)`` -- see INTEGRATION.md.
+the CUDA engine (``swb200_forward_jvp``; the reference runs the network twice here).  ``scm_backward`` then runs the
+grad-enabled forward and ``F_x.backward(cot)`` through the reverse-mode path of ``training.py``.
 """
 from __future__ import annotations
 
@@ -106,20 +105,23 @@ def scm_output_cotangent(net, x: torch.Tensor, t: torch.Tensor, z: torch.Tensor,
     return {"loss": loss, "cot": cot, "g": g, "F": F, "dF": dF, "x_t": x_t}
 
 
-def hybrid_scm_backward(net_grad: torch.nn.Module, net_cuda, x: torch.Tensor, t: torch.Tensor, z: torch.Tensor, step: int,
-                        condition: Optional[torch.Tensor] = None, auxiliary=None, **loss_kwargs) -> Dict[str, torch.Tensor]:
-    """The backward of one sCM training step with the reverse pass delegated (until this library has one): loss value,
-    tangent target and ``cot = dL/dF_x`` come from the CUDA path (``scm_output_cotangent`` on ``net_cuda``, a PassPrecond
-    around ``swift_b200.swinv2.SwinV2`` holding the same weights), then the grad-capable twin ``net_grad`` -- the
-    reference's ``PassPrecond(SwinV2)`` / its DDP wrapper -- runs the one grad-enabled forward of ``loss.py:227`` and
-    ``F_x.backward(cot)``.  Leaves exactly the ``.grad`` that ``SCMLoss(...)(net, x, step, ...).backward()`` leaves
-    (trainer.py:206-214), without ``torch.func.jvp`` through the eager module; returns the dict of
-    ``scm_output_cotangent`` (``loss`` for logging)."""
-    out = scm_output_cotangent(net_cuda, x, t, z, step, condition=condition, auxiliary=auxiliary, **loss_kwargs)
-    sd = float(getattr(net_cuda, "module", net_cuda).sigma_data)
+def scm_backward(net, x: torch.Tensor, t: torch.Tensor, z: torch.Tensor, step: int, condition: Optional[torch.Tensor] = None,
+                 auxiliary=None, **loss_kwargs) -> Dict[str, torch.Tensor]:
+    """The backward of one sCM training step, all of it on the CUDA path: loss value, tangent target and
+    ``cot = dL/dF_x`` from ``scm_output_cotangent`` (one stacked primal + tangent pass), then the one grad-enabled forward of
+    ``loss.py:227`` through ``net`` -- a PassPrecond around ``swift_b200.swinv2.SwinV2`` in ``.train()`` mode, i.e. the
+    reverse-mode path of ``training.py`` -- and ``F_x.backward(cot)``.  Leaves in ``.grad`` what
+    ``SCMLoss(...)(net, x, step, ...).backward()`` leaves (trainer.py:206-214); returns the dict of
+    ``scm_output_cotangent`` (``loss`` for logging).  No eager PyTorch module takes part."""
+    inner = getattr(net, "module", net)
+    if inner.model.logvar_embed is not None:
+        raise NotImplementedError("SCMLoss with a logvar head (exp(-logvar) weighting, loss.py:221-257) is not implemented; "
+                                  "model/swinv2.yaml has logvar: false")
+    if not inner.model.training:
+        raise RuntimeError("scm_backward needs net.train(): the reverse-mode path is selected by training mode")
+    out = scm_output_cotangent(net, x, t, z, step, condition=condition, auxiliary=auxiliary, **loss_kwargs)
+    sd = float(inner.sigma_data)
     with torch.enable_grad():
-        F_x = net_grad(out["x_t"] / sd, t.to(x.device).reshape(-1), condition, auxiliary)
-    if F_x.shape != out["cot"].shape:
-        raise RuntimeError(f"net_grad returned {tuple(F_x.shape)}, expected {tuple(out['cot'].shape)}")
+        F_x = net(out["x_t"] / sd, t.to(x.device).reshape(-1), condition, auxiliary)
     F_x.backward(out["cot"])
     return out

@@ -6,8 +6,12 @@ Selecting it: point hydra's ``model._target_`` at ``swift_b200.swinv2.SwinV2`` (
 same keyword arguments (``models/precond.py:123-131``) and ``load_state_dict(state["ema"])`` succeeds strictly.
 
 The sub-modules below only *hold parameters* under the reference's names; none of them has a ``forward``.
-``SwinV2.forward`` packs the parameters once per checkpoint (bf16 GEMM weights, reordered rows -- see
-``packing.py``) and calls ``libswift_b200.so``.  Inference only: there is no autograd graph and no CPU path.
+``SwinV2.forward`` packs the parameters once per checkpoint (16-bit GEMM weights, reordered rows -- see
+``packing.py``) and calls ``libswift_b200.so``.  There is no CPU path.  Three modes:
+  * inference (``torch.no_grad()`` or ``.eval()``): the fused forecast kernels;
+  * ``jvp=True``: the forward-mode tangent path of the sCM loss (``torch.func.jvp`` works through it);
+  * ``.train()`` with grad enabled: the reverse-mode path of ``training.py`` -- ``F_x.backward(cot)`` /
+    ``loss.backward()`` fill the parameters' ``.grad`` as the reference module does (training/loss.py:226-260).
 """
 from __future__ import annotations
 
@@ -19,6 +23,7 @@ import torch.nn as nn
 
 from . import packing
 from .engine import Engine
+from .training import DenoiserTrainFn, TrainEngine
 
 try:  # when the reference package is importable, be an ``AbstractNetwork`` so isinstance checks keep working
     from swift.models.abstract import AbstractNetwork as _Base  # type: ignore
@@ -168,6 +173,9 @@ class SwinV2(_Base):
         self._init_weights()
         self._engine: Optional[Engine] = None
         self._engine_key = None
+        self._train_engine: Optional[TrainEngine] = None
+        self._train_engine_key = None
+        self._grad_hook = None       # on_stage callback of TrainEngine.backward (training.GradientAllReduce.hook) or None
         self.split_embed = True      # [hi|lo] bf16 operands for the two small end GEMMs (accuracy, <1% of FLOPs)
         self.split_head = True
         self.act_fp16 = True         # tensor-core operands in fp16 (else bf16): 8x smaller rounding error, same tcgen05 rate
@@ -208,13 +216,49 @@ class SwinV2(_Base):
             self._engine_key = key
         return self._engine
 
+    def train_engine(self) -> TrainEngine:
+        """The bf16 training engine (grad-enabled forward + backward) for the current parameter values."""
+        key = (self._params_key(), self.gemm_tile, self.attn_impl)
+        if self._train_engine is None or self._train_engine_key != key:
+            dev = self.pos_embed.device
+            if dev.type != "cuda":
+                raise RuntimeError("swift_b200.SwinV2 runs on CUDA only: move the module to a B200 with .cuda(); "
+                                   "there is no CPU fallback")
+            old = self._train_engine
+            self._train_engine = TrainEngine({k: v for k, v in self.state_dict().items()}, self.geometry, dev,
+                                             self.gemm_tile, self.attn_impl)
+            if old is not None:                  # keep the activation tape / workspace / gradient buffers across steps
+                self._train_engine._tape, self._train_engine._ws = old._tape, old._ws
+                self._train_engine._cond_scratch = old._cond_scratch
+                self._train_engine.grads, self._train_engine._gstruct, self._train_engine._cstruct = (
+                    old.grads, old._gstruct, old._cstruct)
+            self._train_engine_key = key
+        return self._train_engine
+
     # ------------------------------------------------------------------ reference-compatible forward
     def forward(self, x: torch.Tensor, t: torch.Tensor, auxiliary: Optional[torch.Tensor] = None, jvp: bool = False,
                 return_logvar: bool = False) -> Union[torch.Tensor, tuple]:
         """models/swinv2.py:305-330.  x [B, in_channels, H, W]; t scalar, [1] or [B]; auxiliary [B, aux_dim] or None."""
-        if self.training and torch.is_grad_enabled() and not jvp:
-            raise RuntimeError("swift_b200.SwinV2 is inference-only: call .eval() / use torch.no_grad()")
         B = x.shape[0]
+        if self.training and torch.is_grad_enabled() and not jvp:
+            # reverse mode: the grad-enabled forward of training/loss.py:227 (bf16 operands, activation tape kept)
+            if self.logvar_embed is not None:
+                raise NotImplementedError("the reverse-mode path does not implement the logvar head (model/swinv2.yaml: "
+                                          "logvar: false); SCMLoss with logvar would train on a different objective")
+            if torch.is_autocast_enabled():
+                x = x.float()
+            x32 = x.to(torch.float32).contiguous()
+            t32 = t.detach().to(device=x.device, dtype=torch.float32)
+            if t32.dim() == 0 or (t32.dim() == 1 and t32.shape[0] == 1):
+                t32 = t32.reshape(-1).repeat(B)
+            aux32 = None
+            if self.auxiliary_embed is not None and auxiliary is not None:
+                aux32 = auxiliary.detach().to(device=x.device, dtype=torch.float32).reshape(-1, self.auxiliary_dim)
+                if aux32.shape[0] == 1 and B > 1:
+                    aux32 = aux32.expand(B, -1)
+                aux32 = aux32.contiguous()
+            names = tuple(n for n, _ in self.named_parameters())
+            return DenoiserTrainFn.apply(x32, t32.reshape(B).contiguous(), aux32, self, names, *self.parameters())
         if not jvp:                                                # (a detach would drop the forward-mode tangents)
             x, t = x.detach(), t.detach()
         x = x.to(torch.float32).contiguous()

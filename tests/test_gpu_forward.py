@@ -182,14 +182,16 @@ def test_module_contract():
         m.cpu()(x.cpu(), torch.tensor(0.5))
     with torch.no_grad():                                   # jvp=True alone is the plain forward (explicit-softmax flag)
         assert torch.equal(m.cuda()(x, torch.tensor(0.5, device="cuda"), torch.tensor([[0.6]], device="cuda"), jvp=True), y)
-    with pytest.raises(NotImplementedError):                # no reverse mode: the backward pass is not part of this library
+    with pytest.raises(NotImplementedError):                # the jvp=True node is forward-mode only (reverse mode: .train())
         xg = x.clone().requires_grad_(True)
         m(xg, torch.tensor(0.5, device="cuda"), torch.tensor([[0.6]], device="cuda"), jvp=True).sum().backward()
     with pytest.raises(NotImplementedError):
         SwinV2(**{**cfg, "window_size": [8, 8]})
-    m.train()
-    with pytest.raises(RuntimeError):
-        m(x, torch.tensor(0.5, device="cuda"))
+    m.train()                                               # grad-enabled training mode = the reverse-mode path
+    y_t = m(x, torch.tensor(0.5, device="cuda"), torch.tensor([[0.6]], device="cuda"))
+    assert y_t.requires_grad and y_t.shape == y.shape
+    with pytest.raises(NotImplementedError):                # parameter gradients only
+        m(x.clone().requires_grad_(True), torch.tensor(0.5, device="cuda"))
 
 
 def test_chunked_batch_matches_single():
