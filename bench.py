@@ -503,6 +503,182 @@ def run_tangent(args):
                       "config": {"workload": "Swift-B forward-mode tangent forward (jvp of the denoiser w.r.t. x and t)"}}))
 
 
+def run_train(args):
+    """BASELINE.json configs[4]: the sCM training step -- forward-mode tangent pass (loss, dL/dF), grad-enabled forward,
+    backward, data-parallel gradient all-reduce overlapped with the backward, MuonWithAuxAdam, EMA -- Swift-B, local batch
+    1 per GPU (configs/experiment/era5-swinv2-1.4-scm.yaml), synthetic ERA5-shaped batches.  Not the headline metric."""
+    import torch
+    import torch.distributed as dist
+
+    from swift_b200 import synthetic as syn
+    from swift_b200.generate import era5_variables
+    from swift_b200.optim import MuonWithAuxAdam, swinv2_param_groups
+    from swift_b200.precond import PassPrecond
+    from swift_b200.scm_target import latitude_weights, variable_weights
+    from swift_b200.training import GradientAllReduce, scm_train_step
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        sys.stdout.flush()
+        stdout_fd = os.dup(1)
+        os.dup2(2, 1)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    cfg = syn.SWIFT_B
+    B = args.train_batch
+    model_cfg = dict(_target_="swift_b200.swinv2.SwinV2", window_size=cfg["window_size"], shift_size=cfg["shift_size"],
+                     patch_size=cfg["patch_size"], depth=cfg["depth"], dim=cfg["dim"], heads=cfg["heads"])
+    net = PassPrecond(model_cfg, img_resolution=cfg["img_resolution"], img_channels=syn.IMG_CHANNELS,
+                      condition_channels=syn.COND_CHANNELS, auxiliary_dim=1, sigma_min=0.0, sigma_max=float("inf"))
+    net.load_state_dict(syn.random_state_dict(cfg, seed=1, prefix="model."), strict=True)      # same weights on every rank
+    net = net.to(dev).train()
+    opt = MuonWithAuxAdam(swinv2_param_groups(net))                                            # configs/optimizer/muon.yaml
+    ema = [p.detach().clone() for p in net.parameters()]
+    H, W = cfg["img_resolution"]
+    w_lat, w_var = latitude_weights(H, dev), variable_weights(era5_variables(), dev)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)                                 # every rank its own batch
+
+    def batch():
+        x = torch.randn(B, syn.IMG_CHANNELS, H, W, device=dev, generator=gen)
+        cond = torch.randn(B, syn.COND_CHANNELS, H, W, device=dev, generator=gen)
+        u = torch.rand(B, device=dev, generator=gen)
+        sigma = torch.exp(math.log(0.02) + u * (math.log(200.0) - math.log(0.02)))             # loss/noise: loguniform(0.02, 200)
+        return x, cond, torch.atan(sigma), torch.randn(x.shape, device=dev, generator=gen)
+
+    ema_beta = 0.5 ** (B * world / 500e3)
+    kimg = [1_500_000]
+
+    def one_step(reducer, timers=None):
+        x, cond, t, z = batch()
+        mark = (lambda k: timers.setdefault(k, []).append(_ev())) if timers is not None else (lambda k: None)
+        mark("start")
+        out = scm_train_step(net, x, t, z, kimg[0], condition=cond, auxiliary=0.6, reducer=reducer, tangent_warmup_kimg=3000,
+                             w_lat=w_lat, w_var=w_var)
+        mark("fwd_bwd")
+        for buf in net.model._train_engine.grads.values():                                     # trainer.py:221-230
+            torch.nan_to_num_(buf, nan=0.0, posinf=1e5, neginf=-1e5)
+        opt.step()
+        mark("optimizer")
+        torch._foreach_lerp_(ema, [p.detach() for p in net.parameters()], 1.0 - ema_beta)      # trainer.py:240-241
+        mark("ema")
+        kimg[0] += B * world
+        return out
+
+    def _ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    def timed(reducer, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = one_step(reducer)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps, out
+
+    reducer = GradientAllReduce(net.model)
+    for _ in range(max(3, args.warmup)):
+        one_step(reducer)
+    clocks = ClockSampler(local)
+    clocks.start()
+    ms, out = timed(reducer, args.steps)
+    clock_info = clocks.stop()
+    torch.cuda.synchronize()
+    comm_ms = reducer.comm_ms() / max(1, args.steps + max(3, args.warmup))
+    bytes_per_step = reducer.bytes // max(1, args.steps + max(3, args.warmup))
+    ms_nocomm = None
+    if world > 1:                                            # the same steps without the all-reduce: what the overlap hides
+        ms_nocomm, _ = timed(GradientAllReduce(net.model, enabled=False), max(3, args.steps // 2))
+    timers = {}
+    for _ in range(3):                                       # phase breakdown (events between the phases)
+        one_step(reducer, timers)
+    torch.cuda.synchronize()
+    order = ["start", "fwd_bwd", "optimizer", "ema"]
+    brk = {b: sum(x0.elapsed_time(x1) for x0, x1 in zip(timers[a], timers[b])) / 3 for a, b in zip(order, order[1:])}
+    loss = float(out["loss"])
+    if not math.isfinite(loss):
+        raise RuntimeError("training bench produced a non-finite loss")
+    eager = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        eager = eager_training_step_ms(dev, cfg, w_lat, w_var)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # FLOPs of one sample-step: tangent pass 2 x forward GEMMs (+ dual products), grad-enabled forward 1 x, backward 2 x
+    flops = (2 + 1 + 2) * FLOP_PER_MEMBER_STEP
+    line = {"metric": "sCM training samples/sec", "value": B * world / (ms / 1e3), "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16 tensor-core operands, fp32 accumulate / gradients / optimiser state "
+            "(tangent pass: fp16 operands)", "data": "synthetic",
+            "config": {"workload": "Swift-B sCM training step (tangent forward + grad-enabled forward + backward + all-reduce + "
+                                   "MuonWithAuxAdam + EMA), local batch %d per GPU" % B, "global_batch": B * world,
+                       "parallelism": f"dp{world}", "device": torch.cuda.get_device_name(dev)},
+            "clocks": clock_info, "loss": loss, "breakdown_ms": brk,
+            "step_tflops_per_gpu": B * flops / (ms / 1e3) / 1e12,
+            "allreduce": {"bytes_per_step": int(bytes_per_step), "comm_ms_per_step": comm_ms, "step_ms_without_allreduce": ms_nocomm,
+                          "exposed_ms": None if ms_nocomm is None else max(0.0, ms - ms_nocomm),
+                          "hidden_ms": None if ms_nocomm is None else max(0.0, comm_ms - max(0.0, ms - ms_nocomm)),
+                          "how": "per-stage NCCL all-reduce on a side stream behind an event (training.GradientAllReduce)"},
+            "eager_pytorch_same_gpu": eager}
+    if world > 1:
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        os.dup2(2, 1)
+        dist.destroy_process_group()
+
+
+def eager_training_step_ms(dev, cfg, w_lat, w_var):
+    """Baseline leg: the reference ALGORITHM of one training step's forward + backward (oracle port: torch.func.jvp pass,
+    grad-enabled forward, backward) as eager PyTorch ops on this GPU, fp32 with TF32 off and under bf16 autocast."""
+    import torch
+    from oracle import scm_loss_oracle as so, swinv2_oracle as orc
+    from swift_b200 import synthetic as syn
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        sd = {k: v.to(dev) for k, v in syn.random_state_dict(cfg, seed=1).items()}
+        ocfg = orc.make_cfg(**cfg)
+        x = torch.randn(1, syn.IMG_CHANNELS, *cfg["img_resolution"], device=dev)
+        cond = torch.randn(1, syn.COND_CHANNELS, *cfg["img_resolution"], device=dev)
+        t4, z = torch.full((1, 1, 1, 1), 0.9, device=dev), torch.randn_like(x)
+        net_of = lambda p: (lambda a, b: orc.pass_precond(p, ocfg, a, b, cond, 0.6))
+        res = {}
+        for name, ctx in (("fp32", torch.autocast("cuda", enabled=False)), ("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
+            with ctx:
+                so.scm_parameter_gradients(net_of, sd, x, t4, z, 1_500_000, 3000, w_lat, w_var)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(2):
+                    so.scm_parameter_gradients(net_of, sd, x, t4, z, 1_500_000, 3000, w_lat, w_var)
+                torch.cuda.synchronize()
+            res[name + "_ms_per_sample"] = (time.perf_counter() - t0) / 2 * 1e3
+        res["what"] = "oracle port: jvp pass + grad-enabled forward + backward, no optimiser"
+        return res
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -513,8 +689,10 @@ def main():
     ap.add_argument("--solver", default="scm", choices=["scm", "2s"],
                     help="scm: Swift 1-step consistency sampler (headline); 2s: TrigFlow diffusion baseline, 20 Heun steps = "
                          "39 denoiser calls per 6 h step (BASELINE.json configs[3])")
-    ap.add_argument("--mode", default="rollout", choices=["rollout", "tangent"],
-                    help="rollout: the headline forecast benchmark; tangent: the forward-mode tangent forward of the sCM loss")
+    ap.add_argument("--mode", default="rollout", choices=["rollout", "tangent", "train"],
+                    help="rollout: the headline forecast benchmark; tangent: the forward-mode tangent forward of the sCM loss; "
+                         "train: the whole sCM training step, data parallel under torchrun (BASELINE.json configs[4])")
+    ap.add_argument("--train-batch", type=int, default=1, help="--mode train: samples per GPU and step")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end leg (0 = same as --steps)")
     ap.add_argument("--fuse-ln", type=int, default=-1, help="override SwinV2.fuse_ln (bit 0: wo, bit 1: w2; 0 = separate LN kernel)")
     ap.add_argument("--no-stats", action="store_true", help="do not accumulate the on-device ensemble scores")
@@ -525,6 +703,8 @@ def main():
         run_reference(args)
     elif args.mode == "tangent":
         run_tangent(args)
+    elif args.mode == "train":
+        run_train(args)
     else:
         run_ours(args)
 

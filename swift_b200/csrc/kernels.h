@@ -101,6 +101,13 @@ int launch_attention_bwd(const void* qkv, const void* O, const void* dO, const f
                          float* Lbuf, float* Dbuf, float* ds_part, int B, int gh, int gw, int heads, int hd, int pad,
                          int shift_h, int shift_w, cudaStream_t stream);
 
+// optimiser step (muon.cu): Muon's momentum + Newton-Schulz orthogonalisation + parameter update for one matrix; AuxAdam
+size_t muon_workspace_bytes(int rows, int cols);
+int launch_muon_step(float* param, const float* grad, float* momentum, int rows, int cols, float lr, float weight_decay, float beta,
+                     int nesterov, int ns_steps, void* workspace, size_t ws_bytes, cudaStream_t st);
+int launch_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float wd,
+                     int step, cudaStream_t st);
+
 // ensemble verification statistics (ensemble.cu): out[(*step) * out_stride + (ic * V + v) * 4 + k]
 int launch_ensemble_stats(const float* phys, const float* truth, const float* w_lat, int n_ic, int members, int V, int H,
                           int W, const int* step, int n_steps, int out_stride, double* out, cudaStream_t stream);

@@ -218,18 +218,26 @@ class GradientAllReduce:
     l's 75 MB travel over NVLink while layer l-1 is being differentiated.  ``finish()`` makes the compute stream wait for
     the last collective.  With a gloo group (CPU tests) the same sequence runs synchronously."""
 
-    def __init__(self, engine: TrainEngine, group=None):
+    def __init__(self, module, group=None, enabled: bool = True):
+        """``module``: the ``swift_b200.SwinV2`` whose (current) training engine owns the gradient buffers."""
         import torch.distributed as dist
-        self.dist, self.engine, self.group = dist, engine, group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.stream = torch.cuda.Stream(device=engine.device) if engine.device.type == "cuda" else None
+        self.dist, self.module, self.group = dist, module, group
+        self.world = dist.get_world_size(group) if (dist.is_initialized() and enabled) else 1
+        dev = next(module.parameters()).device
+        self.stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
         self.bytes = 0
         self._events: List[Tuple[torch.cuda.Event, torch.cuda.Event]] = []
 
     def hook(self, kind: str, layer: int) -> None:
         if self.world == 1:
             return
-        bufs = self.engine.stage_buffers(kind, layer)
+        bufs = self.module._train_engine.stage_buffers(kind, layer)
+        if self.stream is None:                      # host tensors (gloo, CPU tests of the bookkeeping): synchronous
+            for b in bufs:
+                self.dist.all_reduce(b, op=self.dist.ReduceOp.SUM, group=self.group)
+                b.mul_(1.0 / self.world)
+                self.bytes += b.numel() * 4
+            return
         ready = torch.cuda.Event()
         ready.record(torch.cuda.current_stream())
         with torch.cuda.stream(self.stream):
@@ -244,7 +252,7 @@ class GradientAllReduce:
             self._events.append((e0, e1))
 
     def finish(self) -> None:
-        if self.world > 1:
+        if self.world > 1 and self.stream is not None:
             torch.cuda.current_stream().wait_stream(self.stream)
 
     def comm_ms(self) -> float:
@@ -280,3 +288,41 @@ class DenoiserTrainFn(torch.autograd.Function):
             gname = by_name.get(n)
             grads.append(None if gname is None else gname.reshape(params[n].shape).clone())
         return (None, None, None, None, None, *grads)
+
+
+# ---------------------------------------------------------------------------------------------- the training step
+def scm_train_step(net, x: torch.Tensor, t: torch.Tensor, z: torch.Tensor, step: int, condition: Optional[torch.Tensor] = None,
+                   auxiliary=None, reducer: Optional[GradientAllReduce] = None, accumulate: bool = False,
+                   **loss_kwargs) -> Dict[str, torch.Tensor]:
+    """Forward + tangent + backward of one sCM training step without autograd in the loop (what ``Trainer._forward_step`` +
+    ``loss.backward()`` do, trainer.py:189-219): ``scm_target.scm_output_cotangent`` (loss, cot from one stacked primal +
+    tangent pass), ``TrainEngine.forward`` (the concat with the condition and the 1/sigma_d scaling fused in the patch
+    gather) and ``TrainEngine.backward`` with ``reducer.hook`` after every stage, so the data-parallel all-reduce of a
+    finished layer overlaps the backward of the next.  Afterwards every parameter's ``.grad`` is a VIEW of the engine's
+    flat gradient buffers (valid until the next backward; run the optimiser before it).  Returns the cotangent dict."""
+    from .precond import process_auxiliary
+    from .scm_target import scm_output_cotangent
+    inner = getattr(net, "module", net)
+    model = inner.model
+    if model.logvar_embed is not None:
+        raise NotImplementedError("SCMLoss with a logvar head is not implemented on the CUDA path (model/swinv2.yaml: logvar: false)")
+    out = scm_output_cotangent(net, x, t, z, step, condition=condition, auxiliary=auxiliary, **loss_kwargs)
+    eng = model.train_engine()
+    B, dev = x.shape[0], x.device
+    aux = process_auxiliary(auxiliary, inner.auxiliary_dim, B, dev)
+    if aux is not None:
+        aux = aux.to(torch.float32).expand(B, -1).contiguous()
+    cond = None
+    if condition is not None and inner.condition_channels > 0:
+        cond = condition.to(device=dev, dtype=torch.float32).contiguous()
+    t1 = t.to(device=dev, dtype=torch.float32).reshape(B).contiguous()
+    eng.forward(out["x_t"], cond, t1, aux, scale0=1.0 / float(inner.sigma_data))
+    eng.backward(out["cot"], accumulate=accumulate, on_stage=reducer.hook if reducer is not None else None)
+    if reducer is not None:
+        reducer.finish()
+    params = dict(model.named_parameters())
+    grads = eng.parameter_gradients({n: p for n, p in params.items() if n.endswith(".scale")})
+    for n, p in params.items():
+        gview = grads.get(n)
+        p.grad = None if gview is None else gview.reshape(p.shape)
+    return out

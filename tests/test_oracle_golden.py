@@ -147,3 +147,22 @@ def test_scm_parameter_gradients_match_reference_backward(golden, name, cfgname)
     for kk in sampled:
         nm = kk.split("grad:")[1][len("model."):]
         _close(grads[nm].flatten()[::31], g[kk], tol=5e-5)
+
+
+def test_muon_oracle_matches_reference_golden(golden):
+    """oracle/muon_oracle.py against the REAL reference's muon_update / adam_update (tests/golden/make_muon_golden.py)."""
+    from oracle import muon_oracle as mo
+    g = golden("muon")
+    torch.set_num_threads(1)
+    for name in ("wide", "tall", "square", "scale"):
+        grad, mom = torch.from_numpy(g[f"{name}_grad"]), torch.from_numpy(g[f"{name}_mom"])
+        upd, mom_new = mo.muon_update(grad, mom, beta=0.95)
+        assert torch.equal(mom_new, torch.from_numpy(g[f"{name}_mom_new"])), name
+        # same bf16 op sequence; the CPU matmul may block the reduction differently from run to run of the build
+        ref = torch.from_numpy(g[f"{name}_update"])
+        assert ((upd - ref).norm() / ref.norm()).item() < 2e-2, name
+    p, gr = torch.from_numpy(g["adam_p"]), torch.from_numpy(g["adam_g"])
+    p2, b1, b2 = mo.adam_step(p, gr, torch.from_numpy(g["adam_b1"]), torch.from_numpy(g["adam_b2"]), 3, lr=1e-2, weight_decay=0.1)
+    assert torch.allclose(b1, torch.from_numpy(g["adam_b1_new"])) and torch.allclose(b2, torch.from_numpy(g["adam_b2_new"]))
+    ref_p = p * (1 - 1e-2 * 0.1) - 1e-2 * torch.from_numpy(g["adam_update"])
+    assert torch.allclose(p2, ref_p, rtol=1e-6, atol=1e-7)

@@ -95,3 +95,64 @@ def test_two_ranks_fill_one_store_without_locks(tmp_path):
     want = (100.0 * np.arange(3).reshape(3, 1, 1) + 10.0 * np.arange(3).reshape(1, 3, 1) + np.arange(3).reshape(1, 1, 3))
     np.testing.assert_array_equal(got[..., 0, 0, 0], want.astype(np.float32))
     assert (got == got[..., :1, :1, :1]).all()                    # every chunk complete, none torn or missing
+
+
+def _allreduce_worker(rank, world, port, q):
+    """GradientAllReduce bookkeeping on host tensors: every stage's buffers are averaged over the ranks exactly once."""
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from swift_b200.training import GradientAllReduce
+
+    class FakeEngine:                      # the engine's gradient-buffer contract without a GPU
+        def __init__(self):
+            g = torch.Generator().manual_seed(100 + rank)
+            self.grads = {"head": torch.randn(4, 3, generator=g), "l1": torch.randn(5, generator=g),
+                          "l0": torch.randn(2, 2, generator=g), "embed": torch.randn(3, generator=g),
+                          "cond": torch.randn(6, generator=g)}
+
+        def stage_buffers(self, kind, layer):
+            return [self.grads[{"head": "head", "embed": "embed", "cond": "cond"}.get(kind, f"l{layer}")]]
+
+    class FakeModule(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(1))
+            self._train_engine = FakeEngine()
+
+    m = FakeModule()
+    local = {k: v.clone() for k, v in m._train_engine.grads.items()}
+    red = GradientAllReduce(m)
+    for kind, layer in (("head", -1), ("layer", 1), ("layer", 0), ("embed", -1), ("cond", -1)):
+        red.hook(kind, layer)
+    red.finish()
+    gathered = {}
+    for k, v in local.items():
+        parts = [torch.empty_like(v) for _ in range(world)]
+        dist.all_gather(parts, v)
+        gathered[k] = torch.stack(parts).mean(0)
+    ok = all(torch.allclose(m._train_engine.grads[k], gathered[k], atol=1e-7) for k in local)
+    same = []
+    for k, v in m._train_engine.grads.items():                 # bit-identical on every rank after the reduction
+        parts = [torch.empty_like(v) for _ in range(world)]
+        dist.all_gather(parts, v)
+        same.append(all(torch.equal(parts[0], p) for p in parts))
+    q.put((rank, ok and all(same), red.bytes))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_two_ranks_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_allreduce_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[1] for r in res] == [True, True]
+    assert res[0][2] == res[1][2] == (12 + 5 + 4 + 3 + 6) * 4
