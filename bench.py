@@ -551,13 +551,14 @@ def run_train(args):
 
     ema_beta = 0.5 ** (B * world / 500e3)
     kimg = [1_500_000]
+    phase = {}
 
     def one_step(reducer, timers=None):
         x, cond, t, z = batch()
         mark = (lambda k: timers.setdefault(k, []).append(_ev())) if timers is not None else (lambda k: None)
         mark("start")
         out = scm_train_step(net, x, t, z, kimg[0], condition=cond, auxiliary=0.6, reducer=reducer, tangent_warmup_kimg=3000,
-                             w_lat=w_lat, w_var=w_var)
+                             w_lat=w_lat, w_var=w_var, timers=phase if timers is not None else None)
         mark("fwd_bwd")
         for buf in net.model._train_engine.grads.values():                                     # trainer.py:221-230
             torch.nan_to_num_(buf, nan=0.0, posinf=1e5, neginf=-1e5)
@@ -614,6 +615,8 @@ def run_train(args):
     torch.cuda.synchronize()
     order = ["start", "fwd_bwd", "optimizer", "ema"]
     brk = {b: sum(x0.elapsed_time(x1) for x0, x1 in zip(timers[a], timers[b])) / 3 for a, b in zip(order, order[1:])}
+    order = ["t0", "pack_tangent", "tangent_loss", "pack_train", "train_forward", "backward"]
+    brk.update({"fwd_bwd." + b: sum(x0.elapsed_time(x1) for x0, x1 in zip(phase[a], phase[b])) / 3 for a, b in zip(order, order[1:])})
     loss = float(out["loss"])
     if not math.isfinite(loss):
         raise RuntimeError("training bench produced a non-finite loss")

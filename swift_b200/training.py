@@ -293,7 +293,7 @@ class DenoiserTrainFn(torch.autograd.Function):
 # ---------------------------------------------------------------------------------------------- the training step
 def scm_train_step(net, x: torch.Tensor, t: torch.Tensor, z: torch.Tensor, step: int, condition: Optional[torch.Tensor] = None,
                    auxiliary=None, reducer: Optional[GradientAllReduce] = None, accumulate: bool = False,
-                   **loss_kwargs) -> Dict[str, torch.Tensor]:
+                   timers: Optional[dict] = None, **loss_kwargs) -> Dict[str, torch.Tensor]:
     """Forward + tangent + backward of one sCM training step without autograd in the loop (what ``Trainer._forward_step`` +
     ``loss.backward()`` do, trainer.py:189-219): ``scm_target.scm_output_cotangent`` (loss, cot from one stacked primal +
     tangent pass), ``TrainEngine.forward`` (the concat with the condition and the 1/sigma_d scaling fused in the patch
@@ -306,8 +306,20 @@ def scm_train_step(net, x: torch.Tensor, t: torch.Tensor, z: torch.Tensor, step:
     model = inner.model
     if model.logvar_embed is not None:
         raise NotImplementedError("SCMLoss with a logvar head is not implemented on the CUDA path (model/swinv2.yaml: logvar: false)")
+
+    def mark(name):                       # optional phase timing (bench.py --mode train): CUDA events on the launch stream
+        if timers is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            timers.setdefault(name, []).append(e)
+
+    mark("t0")
+    model.engine()                        # (re-)pack the 16-bit weights of the tangent path for the current parameters
+    mark("pack_tangent")
     out = scm_output_cotangent(net, x, t, z, step, condition=condition, auxiliary=auxiliary, **loss_kwargs)
+    mark("tangent_loss")
     eng = model.train_engine()
+    mark("pack_train")
     B, dev = x.shape[0], x.device
     aux = process_auxiliary(auxiliary, inner.auxiliary_dim, B, dev)
     if aux is not None:
@@ -317,7 +329,9 @@ def scm_train_step(net, x: torch.Tensor, t: torch.Tensor, z: torch.Tensor, step:
         cond = condition.to(device=dev, dtype=torch.float32).contiguous()
     t1 = t.to(device=dev, dtype=torch.float32).reshape(B).contiguous()
     eng.forward(out["x_t"], cond, t1, aux, scale0=1.0 / float(inner.sigma_data))
+    mark("train_forward")
     eng.backward(out["cot"], accumulate=accumulate, on_stage=reducer.hook if reducer is not None else None)
+    mark("backward")
     if reducer is not None:
         reducer.finish()
     params = dict(model.named_parameters())
