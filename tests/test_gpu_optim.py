@@ -71,8 +71,8 @@ def test_adam_step_vs_golden(golden):
     opt.step()
     ref = torch.from_numpy(g["adam_p"]) * (1 - 1e-2 * 0.1) - 1e-2 * torch.from_numpy(g["adam_update"])
     assert torch.allclose(p.detach().cpu(), ref, rtol=2e-5, atol=1e-7)
-    assert torch.allclose(opt.state[p]["exp_avg"].cpu(), torch.from_numpy(g["adam_b1_new"]), rtol=1e-5, atol=1e-10)
-    assert torch.allclose(opt.state[p]["exp_avg_sq"].cpu(), torch.from_numpy(g["adam_b2_new"]), rtol=1e-5, atol=1e-12)
+    assert torch.allclose(opt.state[p]["exp_avg"].cpu(), torch.from_numpy(g["adam_b1_new"]), rtol=1e-5, atol=1e-8)
+    assert torch.allclose(opt.state[p]["exp_avg_sq"].cpu(), torch.from_numpy(g["adam_b2_new"]), rtol=1e-5, atol=1e-10)
 
 
 def test_optimizer_refuses_cpu_parameters():
