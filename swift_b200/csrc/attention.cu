@@ -227,15 +227,15 @@ int launch_window_attention(const void* qkv, void* out, int B, int gh, int gw, i
     return launch_window_attention_tc(qkv, out, B, gh, gw, heads, shift_h, shift_w, act_f16, out_f16, stream);
   SWB_REQUIRE(gh % kWin == 0 && gw % kWin == 0, "window_attention: token grid %dx%d not divisible by 16x16 windows",
               gh, gw);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDevice<bool> attr_done;
+  if (!attr_done.get()) {
     SWB_CHECK_CUDA(cudaFuncSetAttribute(window_attention_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         kSmemBytes));
     SWB_CHECK_CUDA(cudaFuncSetAttribute(window_attention_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         kSmemBytes));
     SWB_CHECK_CUDA(cudaFuncSetAttribute(window_attention_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         kSmemBytes));
-    attr_done = true;
+    attr_done.set(true);
   }
   const int M = B * gh * gw;
   dim3 grid((gh / kWin) * (gw / kWin), heads, B);

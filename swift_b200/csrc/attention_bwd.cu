@@ -369,11 +369,11 @@ int launch_attention_bwd(const void* qkv, const void* O, const void* dO, const f
   g.shift_h = shift_h; g.shift_w = shift_w; g.pad = pad; g.hd = hd;
   const int items = B * (gh / 16) * (gw / 16) * heads;
   constexpr int kSmem = 4 * kTile * kPitch * 2 + 2 * kTile * 4 + 64;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDevice<bool> attr_done;
+  if (!attr_done.get()) {
     SWB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     SWB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    attr_done = true;
+    attr_done.set(true);
   }
   attn_bwd_dq_kernel<<<dim3(4, items), 128, kSmem, stream>>>(static_cast<const uint16_t*>(qkv), static_cast<const uint16_t*>(O),
                                                             static_cast<const uint16_t*>(dO), invn, qscale,

@@ -328,15 +328,15 @@ int launch_window_attention_tc(const void* qkv, void* out, int B, int gh, int gw
   if (rc) return rc;
   rc = make_tmap_qkv(&t64, qkv, act_f16 != 0, heads, B, gh, gw, 32, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDevice<bool> attr_done;
+  if (!attr_done.get()) {
     SWB_CHECK_CUDA(cudaFuncSetAttribute(window_attention_tc_kernel<true, true>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     SWB_CHECK_CUDA(cudaFuncSetAttribute(window_attention_tc_kernel<true, false>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     SWB_CHECK_CUDA(cudaFuncSetAttribute(window_attention_tc_kernel<false, false>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_done = true;
+    attr_done.set(true);
   }
   AttnTcParams p;
   p.B = B;

@@ -34,7 +34,18 @@ constexpr int SWB_ERR_INVALID = -2;     // bad argument / unsupported configurat
 constexpr int SWB_ERR_DRIVER = -3;      // driver entry point or tensor-map encode failure
 constexpr int SWB_ERR_RESIDENCY = -4;   // the fused LayerNorm GEMM needs every CTA of its grid resident and the device cannot hold them
 
-int num_sms();
+int num_sms();            // of the calling thread's current device
+
+// One-time per-DEVICE initialisation (cudaFuncSetAttribute, occupancy queries) keyed by the current device id: a process
+// that drives several GPUs must repeat it on each of them.  Usage:  static PerDevice<bool> done;  if (!done.get()) {...; done.set(true);}
+constexpr int kMaxDevices = 64;
+int current_device();
+template <typename T>
+struct PerDevice {
+  T v[kMaxDevices] = {};
+  T get() const { return v[current_device()]; }
+  void set(T x) { v[current_device()] = x; }
+};
 
 // 16-bit (fp16 / bf16) row-major [rows, cols] with row pitch `pitch_elems` -> 2-D TMA descriptor with a
 // [box_rows x box_cols] SWIZZLE_128B box (box_cols * 2 bytes must be 128)

@@ -18,14 +18,20 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+
 int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  static PerDevice<int> n;
+  if (n.get() == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, current_device());
+    n.set(v);
   }
-  return n;
+  return n.get();
 }
 
 // ----------------------------------------------------------------------------- TMA descriptors
@@ -85,10 +91,10 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
                        const GemmParams& p, cudaStream_t stream) {
   using S = GemmCfg<NSUB, CG>;
   auto kern = gemm_tcgen05_kernel<NSUB, CG, EPI, F16>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDevice<bool> attr_done;
+  if (!attr_done.get()) {
     SWB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    attr_done = true;
+    attr_done.set(true);
   }
   const int tiles_n = (p.N + S::kTileN - 1) / S::kTileN;
   const int tiles_m = (p.M + kBlockM * CG - 1) / (kBlockM * CG);
@@ -107,7 +113,7 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   cfg.blockDim = dim3(S::kThreads);
   cfg.dynamicSmemBytes = S::kTotal;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
@@ -115,13 +121,35 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if constexpr (EPI == EPI_LN_RES) {
-    // the statistics exchange spins on other CTAs of this grid: every cluster has to be resident
-    static int max_clusters = -1;
-    if (max_clusters < 0) SWB_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
-    if (max_clusters < clusters) {
-      set_error("gemm_ln_residual: only %d of %d CTA clusters can be co-resident", max_clusters, clusters);
+    // The statistics exchange spins on other CTAs of this grid: every cluster has to be resident AT THE SAME TIME.  An
+    // occupancy query only speaks for an idle device, so the kernel is launched COOPERATIVELY: the driver then starts
+    // the grid only when all of it fits next to whatever else is running (other streams, other processes under MPS)
+    // and fails the launch -- instead of deadlocking -- when it never can.  Either failure is reported as
+    // SWB_ERR_RESIDENCY before anything ran, and swb200_forward falls back to GEMM + LayerNorm kernel.
+    static PerDevice<int> max_clusters;                    // 0 = not queried yet
+    if (max_clusters.get() == 0) {
+      int mc = 0;
+      SWB_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&mc, kern, &cfg));
+      max_clusters.set(mc > 0 ? mc : -1);
+    }
+    if (max_clusters.get() < clusters) {
+      set_error("gemm_ln_residual: only %d of %d CTA clusters can be co-resident", max_clusters.get(), clusters);
       return SWB_ERR_RESIDENCY;
     }
+    static const bool cooperative = getenv("SWB_LN_NO_COOPERATIVE") == nullptr;     // A/B knob (tools only)
+    if (cooperative) {
+      attr[1].id = cudaLaunchAttributeCooperative;
+      attr[1].val.cooperative = 1;
+      cfg.numAttrs = 2;
+    }
+    const cudaError_t err = cudaLaunchKernelEx(&cfg, kern, ta, tb, to0, to1, p);
+    if (err == cudaErrorCooperativeLaunchTooLarge || err == cudaErrorLaunchOutOfResources) {
+      cudaGetLastError();                                   // clear the sticky-less launch error
+      set_error("gemm_ln_residual: cooperative launch of %d clusters refused (%s)", clusters, cudaGetErrorString(err));
+      return SWB_ERR_RESIDENCY;
+    }
+    SWB_CHECK_CUDA(err);
+    return SWB_OK;
   }
   SWB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to0, to1, p));
   return SWB_OK;

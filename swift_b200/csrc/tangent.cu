@@ -579,23 +579,23 @@ int launch_attention_dual(const void* qkv, const void* dqkv, float* S, float* dS
   const auto* dq = static_cast<const uint16_t*>(dqkv);
   constexpr int kScoresSmem = 4 * 64 * kDPitch * 2;                          // 53 KB
   constexpr int kOutSmem = 2 * 64 * kPPitch * 2 + 2 * 256 * kDPitch * 2;     // 174 KB
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDevice<bool> attr_done;
+  if (!attr_done.get()) {
     SWB_CHECK_CUDA(cudaFuncSetAttribute(attn_scores_dual_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScoresSmem));
     SWB_CHECK_CUDA(cudaFuncSetAttribute(attn_scores_dual_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScoresSmem));
     SWB_CHECK_CUDA(cudaFuncSetAttribute(attn_out_dual_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kOutSmem));
     SWB_CHECK_CUDA(cudaFuncSetAttribute(attn_out_dual_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kOutSmem));
-    attr_done = true;
+    attr_done.set(true);
   }
   SWB_REQUIRE(hd == 88 && pad == 96, "attention_dual: the tensor-core kernels are specialised for head_dim 88 padded to 96");
   static const bool split = getenv("SWB_DUAL_ATTN_SPLIT") != nullptr;        // tools only: the three-stage A/B path
   if (!split) {
     constexpr int kFusedSmem = 6 * 64 * kDPitch * 2;                          // 78 KB: two blocks per SM
-    static bool fused_attr = false;
-    if (!fused_attr) {
+    static PerDevice<bool> fused_attr;
+    if (!fused_attr.get()) {
       SWB_CHECK_CUDA(cudaFuncSetAttribute(attn_fused_dual_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem));
       SWB_CHECK_CUDA(cudaFuncSetAttribute(attn_fused_dual_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem));
-      fused_attr = true;
+      fused_attr.set(true);
     }
     if (act_f16) attn_fused_dual_kernel<true><<<dim3(4, items), 128, kFusedSmem, stream>>>(q, dq, static_cast<uint16_t*>(attn2), g);
     else attn_fused_dual_kernel<false><<<dim3(4, items), 128, kFusedSmem, stream>>>(q, dq, static_cast<uint16_t*>(attn2), g);

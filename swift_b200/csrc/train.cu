@@ -346,10 +346,10 @@ int launch_ln_bwd(float* dx, const float* add, const float* branch, const float*
               tokens, kLnBwdRowsPerBlock);
   const int blocks = M / kLnBwdRowsPerBlock;
   const size_t smem = static_cast<size_t>(8) * 2 * D * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDevice<bool> attr_done;
+  if (!attr_done.get()) {
     SWB_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * kLnBwdMaxIter * 128 * 4));
-    attr_done = true;
+    attr_done.set(true);
   }
   ln_bwd_kernel<<<blocks, 256, smem, stream>>>(dx, add, branch, gain, static_cast<uint16_t*>(db16), part, M, D, tokens, eps);
   SWB_CHECK_CUDA(cudaGetLastError());

@@ -216,3 +216,46 @@ def test_gemm_ln_residual_epilogue(lib, cg, B, T, D, K, f16):
         assert _rel(got, x_ref) < (8e-5 if f16 else 2e-4), f"gen {gen}: {_rel(got, x_ref):.3e}"
         assert _rel(xhl[:, :D].float(), x_ref) < (6e-4 if f16 else 5e-3)
         x_ref = got.clone()
+
+
+@pytest.mark.timeout(180)
+def test_gemm_ln_residual_next_to_a_busy_stream(lib):
+    """The fused LayerNorm epilogue spins on statistics published by other CTAs of its own grid, so all of its clusters
+    must be co-resident.  The kernel is launched cooperatively: with a second stream keeping every SM busy (long GEMMs
+    of another library) the launch waits for room instead of starting half a grid that can never finish -- the failure
+    mode was a watchdog trap that kills the context.  Same results as the solo run, bit for bit."""
+    f16, cg = 1, 3
+    B, T, D, K = 4, 8192, 1056, 2816
+    M = B * T
+    A = _rand_bf16((M, K), 31, dtype=torch.float16)
+    W = _rand_bf16((D, K), 32, 0.05, dtype=torch.float16)
+    g = torch.Generator(device="cuda").manual_seed(33)
+    x = torch.randn(M, D, device="cuda", generator=g)
+    hi = x.half()
+    xhl0 = torch.cat([hi, (x - hi.float()).half()], 1).contiguous()
+    gain = torch.randn(B, D, device="cuda", generator=g)
+    bias = torch.randn(B, D, device="cuda", generator=g)
+    ws = torch.empty(lib.swb200_ln_workspace_bytes(M, D) + 256, dtype=torch.uint8, device="cuda")
+    ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+
+    def run(xhl, gen):
+        _check(lib.swb200_gemm_ln_residual(cg, f16, A.data_ptr(), K, W.data_ptr(), K, xhl.data_ptr(), gain.data_ptr(),
+                                           bias.data_ptr(), M, D, T, ws_ptr, gen, _stream()))
+
+    solo = xhl0.clone()
+    run(solo, 0)
+    torch.cuda.synchronize()
+    busy = torch.cuda.Stream()
+    a = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16)
+    b = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16)
+    together = xhl0.clone()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(busy):
+        for _ in range(40):                        # ~40 x 0.8 ms of kernels that fill every SM
+            c = a @ b
+    for i in range(6):                             # our launches arrive while the other stream's grid is running
+        t = xhl0.clone() if i < 5 else together
+        run(t, 1 + i)
+    torch.cuda.synchronize()
+    assert torch.equal(together, solo)
+    assert torch.isfinite(c.float()).all()
