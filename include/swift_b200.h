@@ -104,6 +104,35 @@ typedef struct swb200_update {
   float* phys;
 } swb200_update;
 
+/* DEVICE pointers to the fp32 parameters of a reference checkpoint, by their `SwinV2.state_dict()` names
+ * (models/swinv2.py:278-292): what swb200_pack_weights turns into the packed layouts above.
+ * The per-layer members are HOST arrays of `depth` device pointers. */
+typedef struct swb200_ref_params {
+  const float* pos_embed;              /* pos_embed [1, tokens, dim] */
+  const float* patch_w;                /* patch_embed.emb.weight [dim, p1*p2*in_channels], feature order (p1 p2 c) */
+  const float* patch_b;                /* patch_embed.emb.bias [dim] */
+  const float* aux_w;                  /* auxiliary_embed.weight [dim, aux_dim] or NULL */
+  const float* aux_b;
+  const float* l1_w;                   /* latent_embed.l1.weight [dim, dim] ... */
+  const float* l1_b;
+  const float* l2_w;
+  const float* l2_b;
+  const float* head_w;                 /* head.head.0.weight [out_channels*p1*p2, dim] */
+  const float* const* scale;           /* transformer.layers.{l}.0.scale [1, heads, 1, 1] */
+  const float* const* attn_ln_w;       /* ...{l}.0.norm.norm.weight [dim] */
+  const float* const* attn_ln_b;
+  const float* const* attn_mod_w;      /* ...{l}.0.norm.modulation.weight [2*dim, dim] */
+  const float* const* attn_mod_b;
+  const float* const* to_qkv;          /* ...{l}.0.to_qkv.weight [3*dim, dim] */
+  const float* const* wo;              /* ...{l}.0.wo.weight [dim, dim] */
+  const float* const* ff_ln_w;         /* ...{l}.1.norm.norm.weight */
+  const float* const* ff_ln_b;
+  const float* const* ff_mod_w;
+  const float* const* ff_mod_b;
+  const float* const* w1;              /* ...{l}.1.w1.weight [2*dff, dim] */
+  const float* const* w2;              /* ...{l}.1.w2.weight [dim, dff] */
+} swb200_ref_params;
+
 /* ---- library ------------------------------------------------------------------------------------------ */
 SWB200_API int swb200_abi_version(void);
 SWB200_API const char* swb200_last_error(void);          /* message for the last non-zero return code on this thread */
@@ -111,6 +140,15 @@ SWB200_API const char* swb200_last_error(void);          /* message for the last
 /* Check that `m` is a configuration the kernels support (16x16 windows, head_dim 88, mlp dim % 88 == 0, ...).
  * Returns 0 or SWB200 error with swb200_last_error() set.  Host only. */
 SWB200_API int swb200_validate(const swb200_model* m);
+
+/* Build the packed model from a reference checkpoint.  In: the geometry and option fields of `m` (img_*, patch_*, win_*,
+ * shift_*, in_channels, out_channels, depth, dim, heads, dff, aux_dim, k_embed, split_embed, split_head, gemm_tile,
+ * attn_impl, act_fp16, fuse_ln, attn_fp16, timestep_weight); `ref`: the fp32 parameters on the device; `packed`: a device
+ * buffer of swb200_packed_bytes(m) bytes, 256-byte aligned, that must outlive every use of `m`.  Out: every weight
+ * pointer of `m` points into `packed` (b_embed = NULL: the bias is folded into the position table).  The conversions are
+ * enqueued on `stream`. */
+SWB200_API size_t swb200_packed_bytes(const swb200_model* m);
+SWB200_API int swb200_pack_weights(swb200_model* m, const swb200_ref_params* ref, void* packed, size_t packed_bytes, void* stream);
 
 /* Bytes of device workspace needed to push `chunk` samples through swb200_forward at once. Host only. */
 SWB200_API size_t swb200_workspace_bytes(const swb200_model* m, int chunk);

@@ -29,6 +29,7 @@ EXPORTS = (
     "swb200_conditioning_backward", "swb200_gemm_splitk", "swb200_transpose16", "swb200_ln_backward_scratch_bytes",
     "swb200_ln_backward", "swb200_swiglu_backward", "swb200_attention_backward_scratch_bytes", "swb200_attention_backward",
     "swb200_qkv_pack_train", "swb200_muon_workspace_bytes", "swb200_muon_step", "swb200_adam_step",
+    "swb200_packed_bytes", "swb200_pack_weights",
 )
 
 _i32, _f32, _vp, _sz = C.c_int32, C.c_float, C.c_void_p, C.c_size_t
@@ -53,6 +54,14 @@ class Update(C.Structure):
     _fields_ = [("xt", _vp), ("fprev", _vp), ("out_f", _vp), ("alpha", _f32), ("beta", _f32), ("gamma", _f32),
                 ("state", _vp), ("state_channels", _i32), ("zero_channel", _i32), ("x_std", _vp), ("x_mean", _vp),
                 ("d_std", _vp), ("phys", _vp)]
+
+
+class RefParams(C.Structure):
+    """``struct swb200_ref_params``: device pointers to a reference checkpoint's fp32 parameters."""
+    _PP = C.POINTER(C.c_void_p)
+    _fields_ = ([(n, _vp) for n in ("pos_embed", "patch_w", "patch_b", "aux_w", "aux_b", "l1_w", "l1_b", "l2_w", "l2_b", "head_w")]
+                + [(n, C.POINTER(C.c_void_p)) for n in ("scale", "attn_ln_w", "attn_ln_b", "attn_mod_w", "attn_mod_b", "to_qkv", "wo",
+                                                         "ff_ln_w", "ff_ln_b", "ff_mod_w", "ff_mod_b", "w1", "w2")])
 
 
 class TrainModel(C.Structure):
@@ -82,6 +91,8 @@ def _declare(lib):
     MP, UP = C.POINTER(Model), C.POINTER(Update)
     TP, GP, CP = C.POINTER(TrainModel), C.POINTER(TrainGrads), C.POINTER(CondGrads)
     sig = {
+        "swb200_packed_bytes": (_sz, [MP]),
+        "swb200_pack_weights": (C.c_int, [MP, C.POINTER(RefParams), _vp, _sz, _vp]),
         "swb200_train_tape_bytes": (_sz, [TP, C.c_int]),
         "swb200_train_workspace_bytes": (_sz, [TP, C.c_int]),
         "swb200_train_forward": (C.c_int, [TP, _vp, C.c_int, _f32, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),

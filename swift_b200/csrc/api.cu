@@ -1272,4 +1272,126 @@ SWB200_API int swb200_adam_step(float* param, const float* grad, float* exp_avg,
                           static_cast<cudaStream_t>(stream));
 }
 
+// ---- checkpoint packing
+namespace {
+struct PackLayout {
+  size_t w_embed, pos, aux_w, aux_b, l1_w, l1_b, l2_w, l2_b, mod_w, mod_b, ln_gamma, ln_beta, qscale, w_qkv, w_o, w_1, w_2, w_head,
+      total;
+};
+PackLayout pack_layout(const swb200_model* m) {
+  const Geom g = geom(m);
+  const size_t D = m->dim, L = m->depth, Dff = m->dff, H = m->heads;
+  PackLayout p;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  p.w_embed = take(D * g.k_embed_total * 2);
+  p.pos = take(static_cast<size_t>(g.tokens) * D * 4);
+  p.aux_w = take(D * std::max(1, m->aux_dim) * 4);
+  p.aux_b = take(D * 4);
+  p.l1_w = take(D * D * 4);
+  p.l1_b = take(D * 4);
+  p.l2_w = take(D * D * 4);
+  p.l2_b = take(D * 4);
+  p.mod_w = take(2 * L * 2 * D * D * 4);
+  p.mod_b = take(2 * L * 2 * D * 4);
+  p.ln_gamma = take(2 * L * D * 4);
+  p.ln_beta = take(2 * L * D * 4);
+  p.qscale = take(L * H * 4);
+  p.w_qkv = take(L * 3 * D * D * 2);
+  p.w_o = take(L * D * D * 2);
+  p.w_1 = take(L * 2 * Dff * D * 2);
+  p.w_2 = take(L * D * Dff * 2);
+  p.w_head = take(static_cast<size_t>(m->out_channels) * g.pp * g.k_head_total * 2);
+  p.total = off;
+  return p;
+}
+}  // namespace
+
+SWB200_API size_t swb200_packed_bytes(const swb200_model* m) {
+  if (validate(m) != SWB_OK) return 0;
+  return pack_layout(m).total;
+}
+
+SWB200_API int swb200_pack_weights(swb200_model* m, const swb200_ref_params* r, void* packed, size_t packed_bytes, void* stream_) {
+  int rc = validate(m);
+  if (rc) return rc;
+  SWB_REQUIRE(r && packed, "pack_weights: NULL argument");
+  SWB_REQUIRE(r->pos_embed && r->patch_w && r->patch_b && r->l1_w && r->l1_b && r->l2_w && r->l2_b && r->head_w && r->scale &&
+                  r->attn_ln_w && r->attn_ln_b && r->attn_mod_w && r->attn_mod_b && r->to_qkv && r->wo && r->ff_ln_w && r->ff_ln_b &&
+                  r->ff_mod_w && r->ff_mod_b && r->w1 && r->w2,
+              "pack_weights: NULL parameter pointer");
+  SWB_REQUIRE(m->aux_dim == 0 || (r->aux_w && r->aux_b), "pack_weights: aux_dim=%d but no auxiliary_embed parameters", m->aux_dim);
+  const PackLayout p = pack_layout(m);
+  SWB_REQUIRE(packed_bytes >= p.total && (reinterpret_cast<uintptr_t>(packed) & 255) == 0,
+              "pack_weights: buffer too small (%zu < %zu) or not 256-byte aligned", packed_bytes, p.total);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const Geom g = geom(m);
+  const int D = m->dim, L = m->depth, Dff = m->dff, H = m->heads, F16 = m->act_fp16 ? 1 : 0;
+  uint8_t* base = static_cast<uint8_t*>(packed);
+  auto f32p = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
+  auto copy = [&](size_t off, const float* src, size_t n) -> int {
+    SWB_CHECK_CUDA(cudaMemcpyAsync(base + off, src, n * 4, cudaMemcpyDeviceToDevice, st));
+    return SWB_OK;
+  };
+  if ((rc = launch_pack_embed(r->patch_w, base + p.w_embed, D, m->in_channels, g.pp, m->k_embed, m->split_embed, F16, st))) return rc;
+  if ((rc = launch_pack_pos(r->pos_embed, r->patch_b, f32p(p.pos), static_cast<long long>(g.tokens) * D, D, st))) return rc;
+  if (m->aux_dim > 0) {
+    if ((rc = copy(p.aux_w, r->aux_w, static_cast<size_t>(D) * m->aux_dim))) return rc;
+    if ((rc = copy(p.aux_b, r->aux_b, D))) return rc;
+  }
+  if ((rc = copy(p.l1_w, r->l1_w, static_cast<size_t>(D) * D))) return rc;
+  if ((rc = copy(p.l1_b, r->l1_b, D))) return rc;
+  if ((rc = copy(p.l2_w, r->l2_w, static_cast<size_t>(D) * D))) return rc;
+  if ((rc = copy(p.l2_b, r->l2_b, D))) return rc;
+  const int half = kHeadDim * (m->gemm_tile == 3 ? 2 : 1);
+  for (int l = 0; l < L; ++l) {
+    const float* mw[2] = {r->attn_mod_w[l], r->ff_mod_w[l]};
+    const float* mb[2] = {r->attn_mod_b[l], r->ff_mod_b[l]};
+    const float* gw[2] = {r->attn_ln_w[l], r->ff_ln_w[l]};
+    const float* gb[2] = {r->attn_ln_b[l], r->ff_ln_b[l]};
+    for (int k = 0; k < 2; ++k) {
+      const size_t i = 2 * static_cast<size_t>(l) + k;
+      SWB_REQUIRE(mw[k] && mb[k] && gw[k] && gb[k], "pack_weights: NULL norm parameter in layer %d", l);
+      if ((rc = copy(p.mod_w + i * 2 * D * D * 4, mw[k], static_cast<size_t>(2) * D * D))) return rc;
+      if ((rc = copy(p.mod_b + i * 2 * D * 4, mb[k], static_cast<size_t>(2) * D))) return rc;
+      if ((rc = copy(p.ln_gamma + i * D * 4, gw[k], D))) return rc;
+      if ((rc = copy(p.ln_beta + i * D * 4, gb[k], D))) return rc;
+    }
+    SWB_REQUIRE(r->scale[l] && r->to_qkv[l] && r->wo[l] && r->w1[l] && r->w2[l], "pack_weights: NULL weight in layer %d", l);
+    if ((rc = launch_pack_qscale(r->scale[l], f32p(p.qscale) + static_cast<size_t>(l) * H, H, st))) return rc;
+    if ((rc = launch_pack_rows(r->to_qkv[l], base + p.w_qkv + static_cast<size_t>(l) * 3 * D * D * 2, 3 * D, D, D, 0, 1, H, kHeadDim, F16, st)))
+      return rc;
+    if ((rc = launch_pack_rows(r->wo[l], base + p.w_o + static_cast<size_t>(l) * D * D * 2, D, D, D, 0, 0, 0, 0, F16, st))) return rc;
+    if ((rc = launch_pack_rows(r->w1[l], base + p.w_1 + static_cast<size_t>(l) * 2 * Dff * D * 2, 2 * Dff, D, D, 0, 2, half, Dff, F16, st)))
+      return rc;
+    if ((rc = launch_pack_rows(r->w2[l], base + p.w_2 + static_cast<size_t>(l) * D * Dff * 2, D, Dff, Dff, 0, 0, 0, 0, F16, st))) return rc;
+  }
+  if ((rc = launch_pack_rows(r->head_w, base + p.w_head, m->out_channels * g.pp, D, g.k_head_total, m->split_head ? D : 0, 0, 0, 0, F16, st)))
+    return rc;
+  m->w_embed = base + p.w_embed;
+  m->b_embed = nullptr;
+  m->pos_embed = f32p(p.pos);
+  m->aux_w = m->aux_dim > 0 ? f32p(p.aux_w) : nullptr;
+  m->aux_b = m->aux_dim > 0 ? f32p(p.aux_b) : nullptr;
+  m->l1_w = f32p(p.l1_w);
+  m->l1_b = f32p(p.l1_b);
+  m->l2_w = f32p(p.l2_w);
+  m->l2_b = f32p(p.l2_b);
+  m->mod_w = f32p(p.mod_w);
+  m->mod_b = f32p(p.mod_b);
+  m->ln_gamma = f32p(p.ln_gamma);
+  m->ln_beta = f32p(p.ln_beta);
+  m->qscale = f32p(p.qscale);
+  m->w_qkv = base + p.w_qkv;
+  m->w_o = base + p.w_o;
+  m->w_1 = base + p.w_1;
+  m->w_2 = base + p.w_2;
+  m->w_head = base + p.w_head;
+  return SWB_OK;
+}
+
 }  // extern "C"

@@ -101,6 +101,13 @@ int launch_attention_bwd(const void* qkv, const void* O, const void* dO, const f
                          float* Lbuf, float* Dbuf, float* ds_part, int B, int gh, int gw, int heads, int hd, int pad,
                          int shift_h, int shift_w, cudaStream_t stream);
 
+// checkpoint packing (pack.cu); mode 0 plain, 1 qkv row order (a = heads, b = head dim), 2 w1 tile interleave (a = half, b = dff)
+int launch_pack_rows(const float* src, void* dst, int rows, int K, int ldd, int dup, int mode, int a, int b, int f16,
+                     cudaStream_t st);
+int launch_pack_embed(const float* src, void* dst, int D, int C, int pp, int k_embed, int split, int f16, cudaStream_t st);
+int launch_pack_pos(const float* pos, const float* bias, float* out, long long n, int D, cudaStream_t st);
+int launch_pack_qscale(const float* scale, float* out, int heads, cudaStream_t st);
+
 // optimiser step (muon.cu): Muon's momentum + Newton-Schulz orthogonalisation + parameter update for one matrix; AuxAdam
 size_t muon_workspace_bytes(int rows, int cols);
 int launch_muon_step(float* param, const float* grad, float* momentum, int rows, int cols, float lr, float weight_decay, float beta,

@@ -74,80 +74,65 @@ def check_supported(g: Geometry) -> None:
         raise NotImplementedError(f"token grid {g.grid} must be a multiple of the 16x16 window")
 
 
+def _layer_names(l: int):
+    a, f = f"transformer.layers.{l}.0", f"transformer.layers.{l}.1"
+    return {"scale": a + ".scale", "attn_ln_w": a + ".norm.norm.weight", "attn_ln_b": a + ".norm.norm.bias",
+            "attn_mod_w": a + ".norm.modulation.weight", "attn_mod_b": a + ".norm.modulation.bias",
+            "to_qkv": a + ".to_qkv.weight", "wo": a + ".wo.weight", "ff_ln_w": f + ".norm.norm.weight",
+            "ff_ln_b": f + ".norm.norm.bias", "ff_mod_w": f + ".norm.modulation.weight",
+            "ff_mod_b": f + ".norm.modulation.bias", "w1": f + ".w1.weight", "w2": f + ".w2.weight"}
+
+
+def ref_params(sd: Dict[str, torch.Tensor], g: Geometry, device: torch.device):
+    """``struct swb200_ref_params`` for a reference-schema state dict: (struct, fp32 device tensors + pointer arrays that
+    must stay alive until the packing kernels have run)."""
+    import ctypes as C
+    f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
+    keep = []
+
+    def ptr(key):
+        t = f32(sd[key])
+        keep.append(t)
+        return t.data_ptr()
+
+    r = _lib.RefParams()
+    r.pos_embed, r.patch_w, r.patch_b = ptr("pos_embed"), ptr("patch_embed.emb.weight"), ptr("patch_embed.emb.bias")
+    has_aux = bool(g.aux_dim) and "auxiliary_embed.weight" in sd
+    if has_aux:
+        r.aux_w, r.aux_b = ptr("auxiliary_embed.weight"), ptr("auxiliary_embed.bias")
+    r.l1_w, r.l1_b = ptr("latent_embed.l1.weight"), ptr("latent_embed.l1.bias")
+    r.l2_w, r.l2_b = ptr("latent_embed.l2.weight"), ptr("latent_embed.l2.bias")
+    r.head_w = ptr("head.head.0.weight")
+    names = [_layer_names(l) for l in range(g.depth)]
+    for field in names[0]:
+        arr = (C.c_void_p * g.depth)(*[ptr(names[l][field]) for l in range(g.depth)])
+        keep.append(arr)
+        setattr(r, field, arr)
+    return r, keep, has_aux
+
+
 def pack(sd: Dict[str, torch.Tensor], g: Geometry, device: torch.device, split_embed: bool = True,
          split_head: bool = True, act_fp16: bool = True, gemm_tile: int = 3, attn_impl: int = 0, fuse_ln: int = 2,
          attn_fp16: bool = True):
-    """Returns (``_lib.Model`` struct, dict of device tensors that must stay alive as long as the struct is used)."""
+    """Returns (``_lib.Model`` struct, dict of device tensors that must stay alive as long as the struct is used).
+    The conversions themselves are ``swb200_pack_weights`` (csrc/pack.cu): this function only collects the parameter
+    pointers of the state dict and owns the packed buffer."""
+    import ctypes as C
     check_supported(g)
-    bf = torch.float16 if act_fp16 else torch.bfloat16     # one 16-bit operand format for activations and weights
-    D, H, L, Dff, pp = g.dim, g.heads, g.depth, g.dff, g.pp
-    f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
-    keep: Dict[str, torch.Tensor] = {}
+    D, L, Dff = g.dim, g.depth, g.dff
     if gemm_tile == 3 and Dff % (2 * HEAD_DIM):
         gemm_tile = 2                               # 352-wide tiles need whole gate/up slot pairs
-    half = HEAD_DIM * (2 if gemm_tile == 3 else 1)
-
-    # patch-embed: reference feature order "(p1 p2 c)" -> ours "(c p1 p2)"; zero pad to k_embed; duplicate for [hi|lo]
-    w = f32(sd["patch_embed.emb.weight"])
-    C_in = g.in_channels
-    assert w.shape == (D, pp * C_in), w.shape
-    w = w.reshape(D, pp, C_in).permute(0, 2, 1).reshape(D, C_in * pp)
-    w = torch.nn.functional.pad(w, (0, g.k_embed - C_in * pp))
-    if split_embed:
-        w = torch.cat([w, w], dim=1)
-    keep["w_embed"] = w.to(bf).contiguous()
-    # the patch-embed bias is folded into the position table: x = A W^T + (pos + bias) costs one operand in the epilogue
-    keep["pos_embed"] = (f32(sd["pos_embed"]).reshape(g.tokens, D) + f32(sd["patch_embed.emb.bias"])[None, :]).contiguous()
-
-    if g.aux_dim and "auxiliary_embed.weight" in sd:
-        keep["aux_w"] = f32(sd["auxiliary_embed.weight"])
-        keep["aux_b"] = f32(sd["auxiliary_embed.bias"])
-    for n in ("l1", "l2"):
-        keep[f"{n}_w"] = f32(sd[f"latent_embed.{n}.weight"])
-        keep[f"{n}_b"] = f32(sd[f"latent_embed.{n}.bias"])
-
-    mod_w, mod_b, gam, bet, qs, wq, wo, w1, w2 = [], [], [], [], [], [], [], [], []
-    for l in range(L):
-        a, f = f"transformer.layers.{l}.0", f"transformer.layers.{l}.1"
-        for blk in (a, f):
-            mod_w.append(f32(sd[blk + ".norm.modulation.weight"]))
-            mod_b.append(f32(sd[blk + ".norm.modulation.bias"]))
-            gam.append(f32(sd[blk + ".norm.norm.weight"]))
-            bet.append(f32(sd[blk + ".norm.norm.bias"]))
-        # exp(clamp(scale, max=ln 100)) (models/swinv2.py:125-126)
-        qs.append(torch.clamp(f32(sd[a + ".scale"]).reshape(H), max=math.log(1.0 / 0.01)).exp())
-        # to_qkv rows are h*3hd + part*hd + d (rearrange then chunk, models/swinv2.py:120-121) -> part*D + h*hd + d
-        q = f32(sd[a + ".to_qkv.weight"]).reshape(H, 3, HEAD_DIM, D).permute(1, 0, 2, 3).reshape(3 * D, D)
-        wq.append(q.to(bf))
-        wo.append(f32(sd[a + ".wo.weight"]).to(bf))
-        # w1 rows: [gate(Dff) | up(Dff)] (chunk(2), models/swinv2.py:99) -> per GEMM tile of 2*half rows:
-        # [half gate rows | half up rows] (half = 88 for the 176-wide tiles, 176 for the 352-wide tile)
-        w1_ = f32(sd[f + ".w1.weight"])
-        gate, up = w1_[:Dff].reshape(Dff // half, 1, half, D), w1_[Dff:].reshape(Dff // half, 1, half, D)
-        w1.append(torch.cat([gate, up], dim=1).reshape(2 * Dff, D).to(bf))
-        w2.append(f32(sd[f + ".w2.weight"]).to(bf))
-    keep["mod_w"] = torch.cat(mod_w, 0).contiguous()
-    keep["mod_b"] = torch.cat(mod_b, 0).contiguous()
-    keep["ln_gamma"] = torch.stack(gam, 0).contiguous()
-    keep["ln_beta"] = torch.stack(bet, 0).contiguous()
-    keep["qscale"] = torch.stack(qs, 0).contiguous()
-    keep["w_qkv"] = torch.stack(wq, 0).contiguous()
-    keep["w_o"] = torch.stack(wo, 0).contiguous()
-    keep["w_1"] = torch.stack(w1, 0).contiguous()
-    keep["w_2"] = torch.stack(w2, 0).contiguous()
-    wh = f32(sd["head.head.0.weight"])
-    assert wh.shape == (g.out_channels * pp, D)
-    if split_head:
-        wh = torch.cat([wh, wh], dim=1)
-    keep["w_head"] = wh.to(bf).contiguous()
-
+    sd = dict(sd)
+    assert tuple(sd["patch_embed.emb.weight"].shape) == (D, g.pp * g.in_channels), sd["patch_embed.emb.weight"].shape
+    assert tuple(sd["head.head.0.weight"].shape) == (g.out_channels * g.pp, D)
+    ref, keep_src, has_aux = ref_params(sd, g, device)
     m = _lib.Model()
     m.img_h, m.img_w = g.img
     m.patch_h, m.patch_w = g.patch
     m.win_h, m.win_w = g.window
     m.shift_h, m.shift_w = g.shift
-    m.in_channels, m.out_channels, m.depth, m.dim, m.heads = g.in_channels, g.out_channels, L, D, H
-    m.dff, m.aux_dim, m.k_embed = Dff, (g.aux_dim if "aux_w" in keep else 0), g.k_embed
+    m.in_channels, m.out_channels, m.depth, m.dim, m.heads = g.in_channels, g.out_channels, L, D, g.heads
+    m.dff, m.aux_dim, m.k_embed = Dff, (g.aux_dim if has_aux else 0), g.k_embed
     m.split_embed, m.split_head = int(split_embed), int(split_head)
     m.act_fp16 = int(act_fp16)
     m.gemm_tile = int(gemm_tile)
@@ -155,9 +140,28 @@ def pack(sd: Dict[str, torch.Tensor], g: Geometry, device: torch.device, split_e
     m.fuse_ln = int(fuse_ln)
     m.attn_fp16 = int(attn_fp16)
     m.timestep_weight = float(g.timestep_weight)
-    for name in ("w_embed", "b_embed", "pos_embed", "aux_w", "aux_b", "l1_w", "l1_b", "l2_w", "l2_b", "mod_w",
-                 "mod_b", "ln_gamma", "ln_beta", "qscale", "w_qkv", "w_o", "w_1", "w_2", "w_head"):
-        setattr(m, name, keep[name].data_ptr() if name in keep else None)
+    lib = _lib.lib()
+    nbytes = lib.swb200_packed_bytes(C.byref(m))
+    if nbytes == 0:
+        _lib.check(lib.swb200_validate(C.byref(m)), "packed_bytes")
+    buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+    base = (buf.data_ptr() + 255) // 256 * 256
+    _lib.check(lib.swb200_pack_weights(C.byref(m), C.byref(ref), base, nbytes, torch.cuda.current_stream(device).cuda_stream),
+               "pack_weights")
+    keep: Dict[str, object] = {"packed": buf, "_sources": keep_src}
+    bf = torch.float16 if act_fp16 else torch.bfloat16
+
+    def view(ptr_value, shape, dtype):              # typed views into the packed buffer (tools / benches read them)
+        off = ptr_value - buf.data_ptr()
+        n = int(torch.tensor(shape).prod().item()) * torch.empty((), dtype=dtype).element_size()
+        return buf[off:off + n].view(dtype).reshape(shape)
+
+    keep["w_qkv"] = view(m.w_qkv, (L, 3 * D, D), bf)
+    keep["w_o"] = view(m.w_o, (L, D, D), bf)
+    keep["w_1"] = view(m.w_1, (L, 2 * Dff, D), bf)
+    keep["w_2"] = view(m.w_2, (L, D, Dff), bf)
+    keep["qscale"] = view(m.qscale, (L, g.heads), torch.float32)
+    keep["pos_embed"] = view(m.pos_embed, (g.tokens, D), torch.float32)
     return m, keep
 
 

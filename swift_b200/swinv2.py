@@ -25,8 +25,17 @@ from . import packing
 from .engine import Engine
 from .training import DenoiserTrainFn, TrainEngine
 
-try:  # when the reference package is importable, be an ``AbstractNetwork`` so isinstance checks keep working
-    from swift.models.abstract import AbstractNetwork as _Base  # type: ignore
+try:
+    # When the reference package is importable, BE a ``swift.models.swinv2.SwinV2``: ``train.py:271`` gates the optimiser's
+    # parameter grouping on ``isinstance(net.model, SwinV2)`` (imported at train.py:21), so a replacement that is not a
+    # subclass silently trains with different weight-decay / Muon groups.  Only the type is inherited: the reference's
+    # constructor (which would build its nn.Modules) is bypassed, every method it defines is overridden below.
+    from swift.models.abstract import AbstractNetwork as _Abstract  # type: ignore
+    from swift.models.swinv2 import SwinV2 as _RefSwinV2  # type: ignore
+
+    class _Base(_RefSwinV2):
+        def __init__(self, img_resolution, in_channels: int, out_channels: int):
+            _Abstract.__init__(self, img_resolution, in_channels, out_channels)
 except Exception:  # pragma: no cover - the normal case on the GPU box
     class _Base(nn.Module):
         """Same attributes as swift.models.abstract.AbstractNetwork (models/abstract.py:12-35)."""

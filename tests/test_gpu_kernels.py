@@ -206,3 +206,39 @@ def test_scm_loss_glue_kernels_vs_oracle(lib, shape, weights):
     assert lib.swb200_scm_tangent_target(F.data_ptr(), dF.data_ptr(), x_t.data_ptr(), dxt.data_ptr(), t.data_ptr(), 1.0, 1.0,
                                          None, None, B, Cn, H, W, gbuf.data_ptr(), cot.data_ptr(), loss.data_ptr(),
                                          scratch.data_ptr(), 8, _stream()) != 0          # scratch too small: refused
+
+
+@pytest.mark.parametrize("act_fp16", [True, False], ids=["fp16", "bf16"])
+@pytest.mark.parametrize("gemm_tile", [3, 2])
+@pytest.mark.parametrize("cfgname", ["SWIFT_TINY", "SWIFT_SMALL"])
+def test_pack_weights_matches_layout_oracle(lib, cfgname, gemm_tile, act_fp16):
+    """swb200_pack_weights (the C-ABI checkpoint packer, driven through ctypes from raw parameter pointers) writes exactly the
+    layouts of oracle/pack_oracle.py, whose meaning tests/test_host_cpu.py::test_packed_layouts_reproduce_oracle proves."""
+    import ctypes as C
+    from oracle import pack_oracle
+    from swift_b200 import _lib, packing, synthetic as syn
+    c = getattr(syn, cfgname)
+    g = packing.Geometry(img=packing._pair(c["img_resolution"]), patch=packing._pair(c["patch_size"]),
+                         window=packing._pair(c["window_size"]), shift=packing._pair(c["shift_size"]),
+                         in_channels=c["in_channels"], out_channels=c["out_channels"], depth=c["depth"], dim=c["dim"],
+                         heads=c["heads"], aux_dim=c["auxiliary_dim"], timestep_weight=1.0)
+    sd = syn.random_state_dict(c, seed=3)
+    dev = torch.device("cuda")
+    want = pack_oracle.pack_layouts(sd, g, dev, act_fp16=act_fp16, gemm_tile=gemm_tile)
+    m, keep = packing.pack(sd, g, dev, act_fp16=act_fp16, gemm_tile=gemm_tile)
+    torch.cuda.synchronize()
+    buf = keep["packed"]
+    for name, ref in want.items():
+        ptr = getattr(m, name)
+        assert ptr, name
+        off = ptr - buf.data_ptr()
+        got = buf[off:off + ref.numel() * ref.element_size()].view(ref.dtype).reshape(ref.shape)
+        if ref.dtype == torch.float32 and name in ("qscale", "pos_embed"):
+            assert torch.allclose(got, ref, rtol=1e-6, atol=0), name          # expf / one fp32 add
+        else:
+            assert torch.equal(got, ref), name
+    assert m.b_embed is None
+    # error paths of the C entry point
+    assert lib.swb200_pack_weights(C.byref(m), None, buf.data_ptr(), buf.numel(), None) != 0
+    r, _keep, _ = packing.ref_params(sd, g, dev)
+    assert lib.swb200_pack_weights(C.byref(m), C.byref(r), (buf.data_ptr() + 255) // 256 * 256, 16, None) != 0
