@@ -114,6 +114,26 @@ def cpu_member_steps_per_sec(n_timed: int, warmup: int = 1):
     return 1.0 / per, per, cores, torch.get_num_threads()
 
 
+def gpu_eager_best(dev, batches=(2, 8)):
+    """The eager-PyTorch baseline at several batch sizes (the product runs 24 trajectories per launch sequence, so the
+    baseline gets its best batch too); returns the per-batch results and the best fp32 / bf16 rates."""
+    runs = []
+    for b in batches:
+        try:
+            runs.append(gpu_eager_member_steps_per_sec(dev, batch=b))
+        except Exception as e:
+            runs.append({"batch": b, "unavailable": f"{type(e).__name__}: {e}"[:200]})
+    best = {"unit": "member-steps/s", "what": runs[0].get("what") if runs else None, "per_batch": runs}
+    for key in ("fp32", "bf16_autocast"):
+        vals = [(r[key], r["batch"]) for r in runs if r.get(key)]
+        if vals:
+            best[key], best[key + "_batch"] = max(vals)
+    acc = [r["bf16_autocast_per_field_rel_l2_max"] for r in runs if "bf16_autocast_per_field_rel_l2_max" in r]
+    if acc:
+        best["bf16_autocast_per_field_rel_l2_max"] = max(acc)
+    return best
+
+
 def gpu_eager_member_steps_per_sec(dev, batch: int = 2, n_timed: int = 3):
     """SURVEY.md section 8d's "fair GPU baseline": the reference ALGORITHM as plain PyTorch ops (oracle port with the
     reference's inference attention branch, F.scaled_dot_product_attention) run eagerly on the same B200, in fp32 with
@@ -285,7 +305,17 @@ def run_ours(args):
     e1.record()
     barrier()
     clock_info = clocks.stop()
-    ms = max_over_ranks(e0.elapsed_time(e1))
+    ms_local = e0.elapsed_time(e1)
+    ms = max_over_ranks(ms_local)
+    # per-rank step time and SM clock: the N-GPU value is the MAX over ranks, so a single power-capped straggler sets it
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([ms_local / args.steps, float(clock_info.get("sm_mhz") or 0.0)], device=dev, dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        t_r = [float(a[0]) for a in allr]
+        per_rank = {"ms_per_step": t_r, "sm_mhz": [float(a[1]) for a in allr], "min": min(t_r), "median": statistics.median(t_r),
+                    "max": max(t_r)}
     launches = eng.launches - launches0
     member_steps = B * world * args.steps
     value = member_steps / (ms / 1e3)
@@ -334,6 +364,61 @@ def run_ours(args):
                       "collective": "all_gather over NCCL" if world > 1 else "none (1 GPU)",
                       "last_step": {m: float(sc[m][k].mean()) for m in ("rmse", "crps", "ssr")}}
 
+    # ---------------- strong scaling: the FIXED 12 x 64 workload of BASELINE.json configs[2] split over the ranks
+    strong = None
+    if not args.no_strong and args.solver == "scm":
+        del ro
+        torch.cuda.empty_cache()
+        n_ic_s = 64
+        traj_s = shard_trajectories(MEMBERS, n_ic_s, rank, world)
+        s_steps = 2
+        forc_s = syn.synthetic_forcings(cfg, n_ic_s + s_steps + 2, seed=0).to(dev)
+        ro_s = EnsembleRollout(net, norm, forc_s, traj_s, use_graph=not args.no_graph, ic_times={j: j for j in range(n_ic_s)})
+        st_s = None
+        if len(traj_s) % MEMBERS == 0:
+            import numpy as np
+            from swift_b200.ensemble import EnsembleStatistics
+            H_, W_ = cfg["img_resolution"]
+            st_s = EnsembleStatistics(MEMBERS, len(traj_s) // MEMBERS, syn.IMG_CHANNELS, (H_, W_), np.linspace(-89.3, 89.3, H_),
+                                      s_steps + 2, dev)
+            ro_s.attach_statistics(st_s, torch.zeros(len(traj_s) // MEMBERS, syn.IMG_CHANNELS, H_, W_, device=dev))
+        x0_s = torch.stack([syn.synthetic_fields(cfg, 1, seed=j)[1][0, :syn.IMG_CHANNELS] for _, j in traj_s[::MEMBERS]])
+        ro_s.set_state(x0_s.repeat_interleave(MEMBERS, 0)[:len(traj_s)].to(dev))
+        ro_s.step()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(s_steps):
+            ro_s.step()
+        s1.record()
+        barrier()
+        ms_s = max_over_ranks(s0.elapsed_time(s1)) / s_steps
+        g_ms = 0.0
+        if st_s is not None:
+            s2, s3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s2.record()
+            st_s.scores(st_s.gather())
+            s3.record()
+            torch.cuda.synchronize()
+            g_ms = max_over_ranks(s2.elapsed_time(s3))
+        strong = {"workload": "12 members x 64 ICs = 768 trajectories in total (BASELINE.json configs[2]), split over the ranks",
+                  "trajectories_per_gpu": len(traj_s), "steps_timed": s_steps, "ms_per_step": ms_s,
+                  "member_steps_per_s": MEMBERS * n_ic_s / (ms_s / 1e3), "statistics_gather_ms": g_ms,
+                  "time_to_solution_s": {"what": "46 080 member-steps (60 steps) + the all_gather of the ensemble statistics, "
+                                                 "extrapolated from the timed steps", "value": 60 * ms_s / 1e3 + g_ms / 1e3}}
+        del ro_s
+        torch.cuda.empty_cache()
+
+    # ---------------- other configurations of BASELINE.json, short runs recorded beside the headline (1 GPU only)
+    extras = None
+    if world == 1 and not args.no_extras and args.solver == "scm":
+        extras = {}
+        try:
+            extras["trigflow_2s"] = short_2s(net, norm, cfg, dev)
+            extras["training_step"] = short_train(dev)
+        except Exception as e:                                   # an extra must not cost the headline line
+            extras["error"] = f"{type(e).__name__}: {e}"[:300]
+
     # ---------------- roofline of the dominant kernel (SwiGLU up-projection GEMM: 42.5 % of the FLOPs), timed alone
     roof = dominant_kernel_roofline(eng, dev, min(args.chunk, 8))
     peaks, which = measured_peaks()
@@ -346,7 +431,7 @@ def run_ours(args):
     cpu = gpu_eager = None
     if world == 1 and not args.no_cpu:
         try:
-            gpu_eager = gpu_eager_member_steps_per_sec(dev)
+            gpu_eager = gpu_eager_best(dev)
         except Exception as e:                                   # a baseline leg must not cost the headline line
             gpu_eager = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
         v, per, cores, threads = cpu_member_steps_per_sec(2, 1)
@@ -363,6 +448,9 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "member-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps},
         "gpu_launches": launches,
+        "per_rank": per_rank,
+        "strong_scaling": strong,
+        "extras": extras,
         "roofline": roof,
         "step_tflops_per_gpu": step_tflops,
         "step_frac_of_sustained_bf16": step_tflops / peaks["bf16_tflops_sustained"],
@@ -416,7 +504,54 @@ def dominant_kernel_roofline(eng, dev, chunk: int):
             # ncu --set full capture profiles/r01s_ncu_w1.txt (158.80 + 322.83 MB); algorithmic bytes: A 138 MB + W 12 MB
             # + h 369 MB = 519 MB
             "traffic": 481.63e6 if chunk == 8 else None, "traffic_unit": "bytes/launch (ncu dram read+write)",
+            "traffic_source": "profiles/r01s_ncu_w1.txt (ncu --set full of this kernel at this shape, round 1; not re-measured "
+                              "in this run: ncu is never run inside a timed bench)",
             "launch_ms": ms, "flops_per_launch": flops, "peak_source": f"{which} burst bf16"}
+
+
+def short_2s(net, norm, cfg, dev):
+    """BASELINE.json configs[3], short: one 6 h step of the TrigFlow 2S sampler (20 Heun steps = 39 denoiser calls per
+    member-step) for one 12-member ensemble."""
+    import torch
+    from swift_b200 import synthetic as syn
+    from swift_b200.rollout import EnsembleRollout
+    traj = [(m, 0) for m in range(MEMBERS)]
+    forc = syn.synthetic_forcings(cfg, 4, seed=0).to(dev)
+    ro = EnsembleRollout(net, norm, forc, traj, solver="2s", solver_kwargs=dict(num_steps=20, sigma_min=0.02, sigma_max=200.0,
+                                                                               auxiliary=0.6))
+    ro.set_state(syn.synthetic_fields(cfg, 1, seed=0)[1][:, :syn.IMG_CHANNELS].expand(MEMBERS, -1, -1, -1).contiguous().to(dev))
+    ro.step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ro.step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return {"member_steps_per_s": MEMBERS / (ms / 1e3), "denoiser_calls_per_s": 39 * MEMBERS / (ms / 1e3), "ms_per_step": ms,
+            "trajectories": MEMBERS, "what": "TrigFlow 2S, 20 steps (39 calls per member-step), one 12-member ensemble, 1 step timed"}
+
+
+def short_train(dev):
+    """BASELINE.json configs[4], short: three sCM training steps (tangent forward, grad-enabled forward, backward, Muon +
+    AuxAdam, EMA) at local batch 1 on this GPU; `python bench.py --mode train` under torchrun is the full line."""
+    import torch
+    t = _train_setup(dev, 0, 1, 1)
+    for _ in range(2):
+        t["one_step"](None)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        out = t["one_step"](None)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    res = {"samples_per_s": 1e3 / ms, "ms_per_step": ms, "loss": float(out["loss"]),
+           "what": "Swift-B sCM training step, local batch 1: tangent pass + grad-enabled forward + backward + MuonWithAuxAdam + EMA"}
+    del t
+    torch.cuda.empty_cache()
+    return res
 
 
 def run_tangent(args):
@@ -503,33 +638,23 @@ def run_tangent(args):
                       "config": {"workload": "Swift-B forward-mode tangent forward (jvp of the denoiser w.r.t. x and t)"}}))
 
 
-def run_train(args):
-    """BASELINE.json configs[4]: the sCM training step -- forward-mode tangent pass (loss, dL/dF), grad-enabled forward,
-    backward, data-parallel gradient all-reduce overlapped with the backward, MuonWithAuxAdam, EMA -- Swift-B, local batch
-    1 per GPU (configs/experiment/era5-swinv2-1.4-scm.yaml), synthetic ERA5-shaped batches.  Not the headline metric."""
+def _train_setup(dev, rank: int, world: int, B: int):
+    """Model, optimiser, EMA and the step closure of the sCM training benchmark (trainer.py:189-247)."""
     import torch
-    import torch.distributed as dist
 
     from swift_b200 import synthetic as syn
     from swift_b200.generate import era5_variables
     from swift_b200.optim import MuonWithAuxAdam, swinv2_param_groups
     from swift_b200.precond import PassPrecond
     from swift_b200.scm_target import latitude_weights, variable_weights
-    from swift_b200.training import GradientAllReduce, scm_train_step
+    from swift_b200.training import scm_train_step
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        sys.stdout.flush()
-        stdout_fd = os.dup(1)
-        os.dup2(2, 1)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    def _ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
     cfg = syn.SWIFT_B
-    B = args.train_batch
     model_cfg = dict(_target_="swift_b200.swinv2.SwinV2", window_size=cfg["window_size"], shift_size=cfg["shift_size"],
                      patch_size=cfg["patch_size"], depth=cfg["depth"], dim=cfg["dim"], heads=cfg["heads"])
     net = PassPrecond(model_cfg, img_resolution=cfg["img_resolution"], img_channels=syn.IMG_CHANNELS,
@@ -568,6 +693,38 @@ def run_train(args):
         mark("ema")
         kimg[0] += B * world
         return out
+
+    return {"one_step": one_step, "net": net, "phase": phase, "w_lat": w_lat, "w_var": w_var, "cfg": cfg}
+
+
+def run_train(args):
+    """BASELINE.json configs[4]: the sCM training step -- forward-mode tangent pass (loss, dL/dF), grad-enabled forward,
+    backward, data-parallel gradient all-reduce overlapped with the backward, MuonWithAuxAdam, EMA -- Swift-B, local batch
+    1 per GPU (configs/experiment/era5-swinv2-1.4-scm.yaml), synthetic ERA5-shaped batches.  Not the headline metric."""
+    import torch
+    import torch.distributed as dist
+
+    from swift_b200 import synthetic as syn
+    from swift_b200.generate import era5_variables
+    from swift_b200.optim import MuonWithAuxAdam, swinv2_param_groups
+    from swift_b200.precond import PassPrecond
+    from swift_b200.scm_target import latitude_weights, variable_weights
+    from swift_b200.training import GradientAllReduce, scm_train_step
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        sys.stdout.flush()
+        stdout_fd = os.dup(1)
+        os.dup2(2, 1)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B = args.train_batch
+    ts = _train_setup(dev, rank, world, B)
+    one_step, net, phase, w_lat, w_var, cfg = (ts[k] for k in ("one_step", "net", "phase", "w_lat", "w_var", "cfg"))
 
     def _ev():
         e = torch.cuda.Event(enable_timing=True)
@@ -699,6 +856,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end leg (0 = same as --steps)")
     ap.add_argument("--fuse-ln", type=int, default=-1, help="override SwinV2.fuse_ln (bit 0: wo, bit 1: w2; 0 = separate LN kernel)")
     ap.add_argument("--no-stats", action="store_true", help="do not accumulate the on-device ensemble scores")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (fixed 12 x 64 workload)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short TrigFlow-2S / training-step summaries")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
