@@ -399,13 +399,16 @@ SWB200_API int swb200_qkv_pack_train(const float* raw, const float* qscale, void
                           void* stream);
 
 /* ---- optimiser step of the sCM training configuration (training/optimizers/muon.py: MuonWithAuxAdam) ------
- * Muon for one 2-D parameter [rows, cols] (fp32, both extents multiples of 8): momentum <- lerp(momentum, grad, 1 - beta);
- * update = nesterov ? lerp(grad, momentum, beta) : momentum (muon.py:36-45); five (ns_steps) quintic Newton-Schulz steps in
- * bf16 on the tcgen05 GEMM (muon.py:5-33); param <- param (1 - lr wd) - lr max(1, rows/cols)^0.5 update (muon.py:42,
- * :232-233).  grad is not modified.  workspace: swb200_muon_workspace_bytes(rows, cols) bytes, 1024-byte aligned. */
-SWB200_API size_t swb200_muon_workspace_bytes(int rows, int cols);
-SWB200_API int swb200_muon_step(float* param, const float* grad, float* momentum, int rows, int cols, float lr, float weight_decay,
-                     float beta, int nesterov, int ns_steps, void* workspace, size_t workspace_bytes, void* stream);
+ * Muon for `batch` 2-D parameters of ONE shape [rows, cols] (fp32, both extents multiples of 8; params / grads / momenta are
+ * HOST arrays of `batch` device pointers): momentum <- lerp(momentum, grad, 1 - beta); update = nesterov ? lerp(grad,
+ * momentum, beta) : momentum (muon.py:36-45); five (ns_steps) quintic Newton-Schulz steps in bf16 on the tcgen05 GEMM, all
+ * matrices of the stack in one batched launch per product (muon.py:5-33); param <- param (1 - lr wd) -
+ * lr max(1, rows/cols)^0.5 update (muon.py:42, :232-233).  grads are not modified.
+ * workspace: swb200_muon_workspace_bytes(rows, cols, batch) bytes, 1024-byte aligned. */
+SWB200_API size_t swb200_muon_workspace_bytes(int rows, int cols, int batch);
+SWB200_API int swb200_muon_step(float* const* params, const float* const* grads, float* const* momenta, int batch, int rows, int cols,
+                     float lr, float weight_decay, float beta, int nesterov, int ns_steps, void* workspace,
+                     size_t workspace_bytes, void* stream);
 /* AuxAdam for one tensor of n elements (muon.py:147-152, :261-266); step counts from 1. */
 SWB200_API int swb200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                      float beta2, float eps, float weight_decay, int step, void* stream);

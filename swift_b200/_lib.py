@@ -111,8 +111,9 @@ def _declare(lib):
         "swb200_attention_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                 C.c_int, C.c_int, _vp, _sz, _vp]),
         "swb200_qkv_pack_train": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
-        "swb200_muon_workspace_bytes": (_sz, [C.c_int, C.c_int]),
-        "swb200_muon_step": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _f32, _f32, _f32, C.c_int, C.c_int, _vp, _sz, _vp]),
+        "swb200_muon_workspace_bytes": (_sz, [C.c_int, C.c_int, C.c_int]),
+        "swb200_muon_step": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int,
+                                       _f32, _f32, _f32, C.c_int, C.c_int, _vp, _sz, _vp]),
         "swb200_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, _f32, _f32, _f32, _f32, _f32, C.c_int, _vp]),
         "swb200_abi_version": (C.c_int, []),
         "swb200_last_error": (C.c_char_p, []),

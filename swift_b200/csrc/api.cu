@@ -1254,15 +1254,16 @@ SWB200_API int swb200_qkv_pack_train(const float* raw, const float* qscale, void
   return launch_qkv_pack_train(raw, qscale, packed, invn, M, heads, kHeadDim, kHeadDimPad, static_cast<cudaStream_t>(stream));
 }
 
-SWB200_API size_t swb200_muon_workspace_bytes(int rows, int cols) {
-  return (rows >= 8 && cols >= 8) ? muon_workspace_bytes(rows, cols) : 0;
+SWB200_API size_t swb200_muon_workspace_bytes(int rows, int cols, int batch) {
+  return (rows >= 8 && cols >= 8 && batch >= 1) ? muon_workspace_bytes(rows, cols, batch) : 0;
 }
 
-SWB200_API int swb200_muon_step(float* param, const float* grad, float* momentum, int rows, int cols, float lr, float weight_decay,
-                                float beta, int nesterov, int ns_steps, void* workspace, size_t workspace_bytes, void* stream) {
-  SWB_REQUIRE(param && grad && momentum && workspace, "swb200_muon_step: NULL pointer");
-  return launch_muon_step(param, grad, momentum, rows, cols, lr, weight_decay, beta, nesterov, ns_steps, workspace, workspace_bytes,
-                          static_cast<cudaStream_t>(stream));
+SWB200_API int swb200_muon_step(float* const* params, const float* const* grads, float* const* momenta, int batch, int rows, int cols,
+                                float lr, float weight_decay, float beta, int nesterov, int ns_steps, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  SWB_REQUIRE(params && grads && momenta && workspace, "swb200_muon_step: NULL pointer");
+  return launch_muon_step(params, grads, momenta, batch, rows, cols, lr, weight_decay, beta, nesterov, ns_steps, workspace,
+                          workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 SWB200_API int swb200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,

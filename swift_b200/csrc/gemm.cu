@@ -98,7 +98,7 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   }
   const int tiles_n = (p.N + S::kTileN - 1) / S::kTileN;
   const int tiles_m = (p.M + kBlockM * CG - 1) / (kBlockM * CG);
-  const int num_tiles = tiles_m * tiles_n * (p.splits > 1 ? p.splits : 1);
+  const int num_tiles = tiles_m * tiles_n * (p.splits > 1 ? p.splits : 1) * (p.batch > 1 ? p.batch : 1);
   int clusters = num_sms() / CG;
   if (clusters > num_tiles) clusters = num_tiles;
   if constexpr (EPI == EPI_LN_RES) {
@@ -188,15 +188,17 @@ int launch_gemm(int epi, int tile, int act_f16, const void* A, int lda, const vo
               p.K);
   SWB_REQUIRE(p.splits <= 1 || (epi == EPI_STORE_F32 && p.K % kBlockK == 0),
               "gemm: split-K needs the fp32 store epilogue and K %% 64 == 0 (epi=%d K=%d splits=%d)", epi, p.K, p.splits);
+  SWB_REQUIRE(p.batch <= 1 || epi == EPI_STORE_F32, "gemm: batched problems need the fp32 store epilogue (epi=%d)", epi);
   SWB_REQUIRE(tile >= 1 && tile <= 3, "gemm: tile config must be 1 (128x176), 2 (256x176) or 3 (256x352), got %d", tile);
   const int cg = tile == 1 ? 1 : 2;
   const int nsub = tile == 3 ? 2 : 1;
   const bool f16 = act_f16 != 0;
   CUtensorMap ta, tb, to0, to1;
   const uint64_t k_total = static_cast<uint64_t>(p.K) * (p.splits > 1 ? p.splits : 1);
-  int rc = make_tmap_16bit_2d(&ta, A, f16, p.M, k_total, lda, kBlockM, kBlockK);
+  const uint64_t nb = p.batch > 1 ? p.batch : 1;
+  int rc = make_tmap_16bit_2d(&ta, A, f16, p.M * nb, k_total, lda, kBlockM, kBlockK);
   if (rc) return rc;
-  rc = make_tmap_16bit_2d(&tb, W, f16, p.N, k_total, ldw, kUmmaN * nsub / cg, kBlockK);
+  rc = make_tmap_16bit_2d(&tb, W, f16, p.N * nb, k_total, ldw, kUmmaN * nsub / cg, kBlockK);
   if (rc) return rc;
   // 16-bit outputs leave through TMA tile stores: a 64-column box (SWIZZLE_128B image) plus the 24-column rest of an
   // 88-column slot (plain image), or the 32-column rest of a padded 96-column q/k/v row (SWIZZLE_64B image)

@@ -53,6 +53,11 @@ struct GemmParams {
   // extent of A and W is splits * K, split s reads columns [s*K, (s+1)*K) and stores its partial product at rows
   // [s*M, (s+1)*M) of out0 ([splits * M, ldo]); K % 64 == 0 when splits > 1.  0 / 1 = no split.
   int splits;
+  // batched GEMM (EPI_STORE_F32 only; the Newton-Schulz chains of same-shaped matrices): A is [batch * M, K], W is
+  // [batch * N, K], problem b multiplies rows [b*M, (b+1)*M) of A with rows [b*N, (b+1)*N) of W and stores at rows
+  // [(b * splits + s) * M, ...) of out0.  Rows of a tile beyond M / N belong to the next problem: they only feed
+  // accumulator rows / columns that the store masks.  0 / 1 = one problem.
+  int batch;
   int tma_store;           // EPI_STORE_ACT / EPI_QKV / EPI_SWIGLU: write the 16-bit output with TMA tile stores (tmap_o0/o1)
   // EPI_EMBED
   const float* bias;       // [N]
@@ -1080,7 +1085,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int tiles_n = (p.N + kTileN - 1) / kTileN;
   const int tiles_m = (p.M + kBlockM * CG - 1) / (kBlockM * CG);
   const int tiles_mn = tiles_m * tiles_n;
-  const int num_tiles = tiles_mn * (p.splits > 1 ? p.splits : 1);       // split-K: split-major tile order
+  const int nsplit = p.splits > 1 ? p.splits : 1;
+  const int num_tiles = tiles_mn * nsplit * (p.batch > 1 ? p.batch : 1);   // (batch, split)-major tile order
   const int num_kb = (p.K + kBlockK - 1) / kBlockK;
   const int tail_k = p.K - (num_kb - 1) * kBlockK;
   const int tail_ksteps = (tail_k + kUmmaK - 1) / kUmmaK;
@@ -1125,10 +1131,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int split = tile / tiles_mn, tmn = tile - split * tiles_mn;
+      const int bs = tile / tiles_mn, tmn = tile - bs * tiles_mn;
+      const int bidx = bs / nsplit, split = bs - bidx * nsplit;
       const int tm = tmn / tiles_n, tn = tmn - tm * tiles_n;
-      const int row0 = tm * (kBlockM * CG) + static_cast<int>(cta_rank) * kBlockM;
-      const int col0 = tn * kTileN + static_cast<int>(cta_rank) * S::kBRows;
+      const int row0 = bidx * p.M + tm * (kBlockM * CG) + static_cast<int>(cta_rank) * kBlockM;
+      const int col0 = bidx * p.N + tn * kTileN + static_cast<int>(cta_rank) * S::kBRows;
       const int k0 = split * p.K;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u, 1);
@@ -1255,7 +1262,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const uint32_t par = static_cast<uint32_t>(it) & 1u;
-      const int split = tile / tiles_mn, tmn = tile - split * tiles_mn;
+      const int bs = tile / tiles_mn, tmn = tile - bs * tiles_mn;      // bs = batch * splits + split: the output block
       const int tm = tmn / tiles_n, tn = tmn - tm * tiles_n;
       const int n_tile = tn * kTileN;
       if constexpr (EPI == EPI_LN_RES) {
@@ -1277,7 +1284,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       e.row0 = tm * (kBlockM * CG) + static_cast<int>(cta_rank) * kBlockM + quad * 32;
       const int rv = p.M - e.row0;
       e.rows_valid = rv < 0 ? 0 : (rv > 32 ? 32 : rv);
-      if constexpr (EPI == EPI_STORE_F32) e.row0 += split * p.M;       // split-K partial products are stacked along the rows
+      if constexpr (EPI == EPI_STORE_F32) e.row0 += bs * p.M;          // (batch, split) results are stacked along the rows
       // Accumulator columns [0,88) and [88,176) of sub-tile j hold the global 88-column slots
       //   CG == 2:  s = j and s = NSUB + j   (the pair splits the staged W rows in two contiguous halves)
       //   CG == 1:  s = 0 and s = 1

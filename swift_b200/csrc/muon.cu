@@ -32,16 +32,24 @@ __global__ void __launch_bounds__(256) muon_prepare_kernel(const float* __restri
                                                            uint16_t* __restrict__ U16, float* __restrict__ part, long long n,
                                                            float beta, int nesterov) {
   float ss = 0.f;
-  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-  if (i < n) {
-    const float g = grad[i];
-    const float m = fmaf(1.0f - beta, g - mom[i], mom[i]);
-    mom[i] = m;
-    const float u = nesterov ? fmaf(beta, m - g, g) : m;
-    const uint16_t b = bf16_bits(u);
-    U16[i] = b;
-    const float r = bits_f(b);
-    ss = r * r;
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;      // group of 4 elements (n % 4 == 0)
+  if (4 * i < n) {
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(grad) + i);
+    float4 m4 = reinterpret_cast<float4*>(mom)[i];
+    const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+    float m[4] = {m4.x, m4.y, m4.z, m4.w};
+    uint16_t b[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      m[j] = fmaf(1.0f - beta, g[j] - m[j], m[j]);
+      const float u = nesterov ? fmaf(beta, m[j] - g[j], g[j]) : m[j];
+      b[j] = bf16_bits(u);
+      const float r = bits_f(b[j]);
+      ss = fmaf(r, r, ss);
+    }
+    reinterpret_cast<float4*>(mom)[i] = make_float4(m[0], m[1], m[2], m[3]);
+    reinterpret_cast<uint2*>(U16)[i] = make_uint2(static_cast<uint32_t>(b[0]) | (static_cast<uint32_t>(b[1]) << 16),
+                                                  static_cast<uint32_t>(b[2]) | (static_cast<uint32_t>(b[3]) << 16));
   }
   __shared__ float red[8];
 #pragma unroll
@@ -71,31 +79,68 @@ __global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restri
 
 // X16 <- bf16(X16 / (sqrt(norm2) + 1e-7))
 __global__ void __launch_bounds__(256) muon_normalize_kernel(uint16_t* __restrict__ X16, const float* __restrict__ norm2, long long n) {
-  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-  if (i >= n) return;
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;      // group of 8 elements
+  if (8 * i >= n) return;
   const float inv = 1.0f / (bf16_round(sqrtf(norm2[0])) + 1e-7f);
-  X16[i] = bf16_bits(bits_f(X16[i]) * inv);
+  uint4 r = reinterpret_cast<uint4*>(X16)[i];
+  uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    w[j] = pack_bf16x2(__uint_as_float(w[j] << 16) * inv, __uint_as_float(w[j] & 0xffff0000u) * inv);
+  reinterpret_cast<uint4*>(X16)[i] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 // out16[i] = bf16(alpha * x16[i] + beta * bf16(sum_s y[s * stride + i]))     (x16 may be NULL: alpha term dropped)
-__global__ void __launch_bounds__(256) muon_combine_kernel(uint16_t* __restrict__ out16, float alpha, const uint16_t* __restrict__ x16,
+// 8 elements per thread: 16-byte loads / stores (n and stride are multiples of 8: every extent is a multiple of 8)
+__global__ void __launch_bounds__(256) muon_combine_kernel(uint16_t* out16, float alpha, const uint16_t* x16,
                                                            float beta, const float* __restrict__ y, int splits, long long stride,
-                                                           long long n) {
+                                                           long long n8, long long per8) {
+  // batched: problem b = i / per8 holds its `splits` partial products at y[(b * splits + s) * stride ..]; stride == 8 * per8
   const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-  if (i >= n) return;
-  float acc = 0.f;
-  for (int s = 0; s < splits; ++s) acc += y[s * stride + i];
-  float v = beta * bf16_round(acc);
-  if (x16) v = bf16_round(v) + bf16_round(alpha * bits_f(x16[i]));
-  out16[i] = bf16_bits(v);
+  if (i >= n8) return;
+  const long long b = i / per8, j = i - b * per8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int s = 0; s < splits; ++s) {
+    const float4* p = reinterpret_cast<const float4*>(y + (b * splits + s) * stride) + 2 * j;
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+    acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+  }
+  float xv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (x16) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(x16) + i);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      xv[2 * j] = __uint_as_float(w[j] << 16);
+      xv[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+    }
+  }
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float v0 = beta * bf16_round(acc[2 * j]), v1 = beta * bf16_round(acc[2 * j + 1]);
+    if (x16) {
+      v0 = bf16_round(v0) + bf16_round(alpha * xv[2 * j]);
+      v1 = bf16_round(v1) + bf16_round(alpha * xv[2 * j + 1]);
+    }
+    o[j] = pack_bf16x2(v0, v1);
+  }
+  reinterpret_cast<uint4*>(out16)[i] = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 // p <- p (1 - lr wd) - lr scale X   (muon.py:42, :232-233); X is the orthogonalised update in the parameter's orientation
 __global__ void __launch_bounds__(256) muon_apply_kernel(float* __restrict__ p, const uint16_t* __restrict__ X16, long long n, float decay,
                                                          float step) {
-  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-  if (i >= n) return;
-  p[i] = fmaf(p[i], decay, -step * bits_f(X16[i]));
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;      // group of 4 elements
+  if (4 * i >= n) return;
+  float4 v = reinterpret_cast<float4*>(p)[i];
+  const uint2 x = __ldg(reinterpret_cast<const uint2*>(X16) + i);
+  v.x = fmaf(v.x, decay, -step * __uint_as_float(x.x << 16));
+  v.y = fmaf(v.y, decay, -step * __uint_as_float(x.x & 0xffff0000u));
+  v.z = fmaf(v.z, decay, -step * __uint_as_float(x.y << 16));
+  v.w = fmaf(v.w, decay, -step * __uint_as_float(x.y & 0xffff0000u));
+  reinterpret_cast<float4*>(p)[i] = v;
 }
 
 // AuxAdam (muon.py:147-152, :261-266): buf1 <- lerp(buf1, g, 1-b1); buf2 <- lerp(buf2, g^2, 1-b2);
@@ -117,8 +162,8 @@ __global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, c
 inline unsigned blocks_for(long long n) { return static_cast<unsigned>((n + 255) / 256); }
 inline size_t up(size_t v) { return (v + 1023) / 1024 * 1024; }
 
-int ns_splits(int m, int k) {          // X X^T: [m, m] output tiles of 256 x 176, contraction k
-  const int tiles = ((m + 255) / 256) * ((m + 175) / 176);
+int ns_splits(int m, int k, int batch) {          // X X^T: [m, m] output tiles of 256 x 176 per problem, contraction k
+  const int tiles = ((m + 255) / 256) * ((m + 175) / 176) * batch;
   int s = 1;
   while (s < 16 && tiles * s < 96 && k % (2 * s * kBlockK) == 0 && k / (2 * s) >= 512) s *= 2;
   return s;
@@ -127,8 +172,8 @@ int ns_splits(int m, int k) {          // X X^T: [m, m] output tiles of 256 x 17
 struct MuonWs {
   size_t U, UT, A32, A16, B16, BX32, part, total;
 };
-MuonWs carve_muon(int rows, int cols) {
-  const size_t m = std::min(rows, cols), n = std::max(rows, cols);
+MuonWs carve_muon(int rows, int cols, int batch) {
+  const size_t m = std::min(rows, cols), n = std::max(rows, cols), nb = batch;
   MuonWs w;
   size_t off = 0;
   auto take = [&](size_t b) {
@@ -136,18 +181,19 @@ MuonWs carve_muon(int rows, int cols) {
     off = up(off + b);
     return o;
   };
-  w.U = take(m * n * 2);
-  w.UT = take(m * n * 2);
-  w.A32 = take(static_cast<size_t>(ns_splits(static_cast<int>(m), static_cast<int>(n))) * m * m * 4);
-  w.A16 = take(m * m * 2);
-  w.B16 = take(m * m * 2);
-  w.BX32 = take(m * n * 4);
-  w.part = take((static_cast<size_t>(blocks_for(static_cast<long long>(m) * n)) + 4) * 4);
+  w.U = take(nb * m * n * 2);
+  w.UT = take(nb * m * n * 2);
+  w.A32 = take(nb * static_cast<size_t>(ns_splits(static_cast<int>(m), static_cast<int>(n), batch)) * m * m * 4);
+  w.A16 = take(nb * m * m * 2);
+  w.B16 = take(nb * m * m * 2);
+  w.BX32 = take(nb * m * n * 4);
+  w.part = take(nb * (static_cast<size_t>(blocks_for(static_cast<long long>(m) * n / 4)) + 4) * 4);
   w.total = off;
   return w;
 }
 
-int gemm_f32(int tile, const void* A, int lda, const void* W, int ldw, float* out, int M, int N, int K, int splits, cudaStream_t st) {
+int gemm_f32(int tile, const void* A, int lda, const void* W, int ldw, float* out, int M, int N, int K, int splits, int batch,
+             cudaStream_t st) {
   GemmParams p = {};
   p.M = M;
   p.N = N;
@@ -155,31 +201,39 @@ int gemm_f32(int tile, const void* A, int lda, const void* W, int ldw, float* ou
   p.out0 = out;
   p.ldo = N;
   p.splits = splits;
+  p.batch = batch;
   return launch_gemm(EPI_STORE_F32, tile, 0, A, lda, W, ldw, p, st);
 }
 
 }  // namespace
 
-size_t muon_workspace_bytes(int rows, int cols) { return carve_muon(rows, cols).total; }
+size_t muon_workspace_bytes(int rows, int cols, int batch) { return carve_muon(rows, cols, batch).total; }
 
-int launch_muon_step(float* param, const float* grad, float* momentum, int rows, int cols, float lr, float weight_decay, float beta,
-                     int nesterov, int ns_steps, void* workspace, size_t ws_bytes, cudaStream_t st) {
+// `batch` parameters of one shape [rows, cols] (HOST arrays of device pointers): the elementwise kernels run per matrix,
+// the Newton-Schulz GEMMs / combinations / transposes once for the whole stack (batched GEMM: enough tiles to fill the GPU).
+int launch_muon_step(float* const* param, const float* const* grad, float* const* momentum, int batch, int rows, int cols, float lr,
+                     float weight_decay, float beta, int nesterov, int ns_steps, void* workspace, size_t ws_bytes, cudaStream_t st) {
   SWB_REQUIRE(rows >= 8 && cols >= 8 && rows % 8 == 0 && cols % 8 == 0,
               "muon_step: %d x %d unsupported (both extents multiples of 8; vectors are handled by the host wrapper)", rows, cols);
-  const MuonWs w = carve_muon(rows, cols);
+  SWB_REQUIRE(batch >= 1 && batch <= 4096, "muon_step: batch %d out of range", batch);
+  const MuonWs w = carve_muon(rows, cols, batch);
   SWB_REQUIRE(ws_bytes >= w.total && (reinterpret_cast<uintptr_t>(workspace) & 1023) == 0,
               "muon_step: workspace too small (%zu < %zu) or not 1024-byte aligned", ws_bytes, w.total);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   const long long n_el = static_cast<long long>(rows) * cols;
-  uint16_t* U = reinterpret_cast<uint16_t*>(ws + w.U);       // parameter orientation [rows, cols]
-  uint16_t* UT = reinterpret_cast<uint16_t*>(ws + w.UT);     // [cols, rows]
+  uint16_t* U = reinterpret_cast<uint16_t*>(ws + w.U);       // [batch] parameter orientation [rows, cols]
+  uint16_t* UT = reinterpret_cast<uint16_t*>(ws + w.UT);     // [batch] [cols, rows]
   float* part = reinterpret_cast<float*>(ws + w.part);
-  const unsigned nb = blocks_for(n_el);
-  muon_prepare_kernel<<<nb, 256, 0, st>>>(grad, momentum, U, part, n_el, beta, nesterov);
-  sum_partials_kernel<<<1, 256, 0, st>>>(part, static_cast<int>(nb), part + nb);
-  muon_normalize_kernel<<<nb, 256, 0, st>>>(U, part + nb, n_el);
+  const unsigned nb = blocks_for(n_el / 4);
+  for (int i = 0; i < batch; ++i) {
+    SWB_REQUIRE(param[i] && grad[i] && momentum[i], "muon_step: NULL pointer for matrix %d", i);
+    float* pi = part + static_cast<size_t>(i) * (nb + 4);
+    muon_prepare_kernel<<<nb, 256, 0, st>>>(grad[i], momentum[i], U + i * n_el, pi, n_el, beta, nesterov);
+    sum_partials_kernel<<<1, 256, 0, st>>>(pi, static_cast<int>(nb), pi + nb);
+    muon_normalize_kernel<<<blocks_for(n_el / 8), 256, 0, st>>>(U + i * n_el, pi + nb, n_el);
+  }
   SWB_CHECK_CUDA(cudaGetLastError());
-  int rc = launch_transpose16(U, rows, cols, cols, UT, rows, st);
+  int rc = launch_transpose16_batched(U, rows, cols, UT, batch, st);
   if (rc) return rc;
   // X: the wide orientation [m, n] (m <= n);  XT: [n, m]
   const bool tall = rows > cols;
@@ -192,19 +246,20 @@ int launch_muon_step(float* param, const float* grad, float* momentum, int rows,
   float* BX32 = reinterpret_cast<float*>(ws + w.BX32);
   const float a = 3.4445f, b = -4.7750f, c = 2.0315f;
   const long long mm = static_cast<long long>(m) * m, mn = static_cast<long long>(m) * n;
-  const int S = ns_splits(m, n);
+  const int S = ns_splits(m, n, batch);
   for (int it = 0; it < ns_steps; ++it) {
-    if ((rc = gemm_f32(2, X, n, X, n, A32, m, m, n, S, st))) return rc;                        // A = X X^T
-    muon_combine_kernel<<<blocks_for(mm), 256, 0, st>>>(A16, 0.f, nullptr, 1.0f, A32, S, mm, mm);
-    if ((rc = gemm_f32(2, A16, m, A16, m, A32, m, m, m, 1, st))) return rc;                    // A A (A symmetric)
-    muon_combine_kernel<<<blocks_for(mm), 256, 0, st>>>(B16, b, A16, c, A32, 1, mm, mm);       // B = b A + c A A
-    if ((rc = gemm_f32(3, B16, m, XT, m, BX32, m, n, m, 1, st))) return rc;                    // B X
-    muon_combine_kernel<<<blocks_for(mn), 256, 0, st>>>(X, a, X, 1.0f, BX32, 1, mn, mn);       // X = a X + B X
+    if ((rc = gemm_f32(2, X, n, X, n, A32, m, m, n, S, batch, st))) return rc;                        // A = X X^T
+    muon_combine_kernel<<<blocks_for(batch * mm / 8), 256, 0, st>>>(A16, 0.f, nullptr, 1.0f, A32, S, mm, batch * mm / 8, mm / 8);
+    if ((rc = gemm_f32(2, A16, m, A16, m, A32, m, m, m, 1, batch, st))) return rc;                    // A A (A symmetric)
+    muon_combine_kernel<<<blocks_for(batch * mm / 8), 256, 0, st>>>(B16, b, A16, c, A32, 1, mm, batch * mm / 8, mm / 8);   // B = b A + c A A
+    if ((rc = gemm_f32(3, B16, m, XT, m, BX32, m, n, m, 1, batch, st))) return rc;                    // B X
+    muon_combine_kernel<<<blocks_for(batch * mn / 8), 256, 0, st>>>(X, a, X, 1.0f, BX32, 1, mn, batch * mn / 8, mn / 8);   // X = a X + B X
     SWB_CHECK_CUDA(cudaGetLastError());
-    if ((rc = launch_transpose16(X, m, n, n, XT, m, st))) return rc;
+    if ((rc = launch_transpose16_batched(X, m, n, XT, batch, st))) return rc;
   }
   const float scale = sqrtf(fmaxf(1.0f, static_cast<float>(rows) / static_cast<float>(cols)));
-  muon_apply_kernel<<<nb, 256, 0, st>>>(param, U, n_el, 1.0f - lr * weight_decay, lr * scale);
+  for (int i = 0; i < batch; ++i)
+    muon_apply_kernel<<<blocks_for(n_el / 4), 256, 0, st>>>(param[i], U + i * n_el, n_el, 1.0f - lr * weight_decay, lr * scale);
   SWB_CHECK_CUDA(cudaGetLastError());
   return SWB_OK;
 }

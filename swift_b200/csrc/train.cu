@@ -159,8 +159,11 @@ int launch_qkv_pack_train(const float* raw, const float* qscale, void* packed, f
 // 16-bit transpose: in [R, C] (row pitch ldi) -> out [C, R] (row pitch ldo).  The weight-gradient GEMMs contract over the
 // token axis, and the tcgen05 GEMM takes both operands K-major: dY^T [features, tokens] and X^T [features, tokens].
 __global__ void __launch_bounds__(256) transpose16_kernel(const uint16_t* __restrict__ in, int R, int C, long long ldi,
-                                                          uint16_t* __restrict__ out, long long ldo) {
+                                                          uint16_t* __restrict__ out, long long ldo, long long batch_in,
+                                                          long long batch_out) {
   __shared__ uint16_t tile[64][66];
+  in += blockIdx.z * batch_in;               // batched: problem z at element offsets z * batch_in / z * batch_out
+  out += blockIdx.z * batch_out;
   const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
@@ -187,7 +190,17 @@ int launch_transpose16(const void* in, int R, int C, long long ldi, void* out, l
                   (reinterpret_cast<uintptr_t>(out) & 3) == 0,
               "transpose16: even extents / pitches and 4-byte aligned buffers required (R=%d C=%d)", R, C);
   dim3 grid((C + 63) / 64, (R + 63) / 64);
-  transpose16_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(in), R, C, ldi, static_cast<uint16_t*>(out), ldo);
+  transpose16_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(in), R, C, ldi, static_cast<uint16_t*>(out), ldo, 0, 0);
+  SWB_CHECK_CUDA(cudaGetLastError());
+  return SWB_OK;
+}
+
+// `batch` contiguous [R, C] matrices -> `batch` contiguous [C, R] matrices
+int launch_transpose16_batched(const void* in, int R, int C, void* out, int batch, cudaStream_t stream) {
+  SWB_REQUIRE(R % 2 == 0 && C % 2 == 0 && batch >= 1 && batch <= 65535, "transpose16_batched: even extents required (R=%d C=%d)", R, C);
+  dim3 grid((C + 63) / 64, (R + 63) / 64, batch);
+  transpose16_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(in), R, C, C, static_cast<uint16_t*>(out), R,
+                                               static_cast<long long>(R) * C, static_cast<long long>(R) * C);
   SWB_CHECK_CUDA(cudaGetLastError());
   return SWB_OK;
 }

@@ -47,24 +47,39 @@ class MuonWithAuxAdam(torch.optim.Optimizer):
             raise RuntimeError("swift_b200.optim: parameters and gradients must be contiguous float32 CUDA tensors "
                                "(there is no CPU path)")
 
-    def _workspace(self, rows: int, cols: int, device):
-        need = self.lib.swb200_muon_workspace_bytes(rows, cols)
+    def _workspace(self, rows: int, cols: int, batch: int, device):
+        need = self.lib.swb200_muon_workspace_bytes(rows, cols, batch)
         if self._ws is None or self._ws[2] < need or self._ws[0].device != device:
             buf, base = _aligned_buffer(need, device)
             self._ws = (buf, base, need)
         return self._ws
 
-    def _muon(self, p: torch.Tensor, grad: torch.Tensor, mom: torch.Tensor, lr: float, wd: float, beta: float) -> None:
-        self._check(p), self._check(grad)
-        rows = p.shape[0]
-        cols = p.numel() // rows                                   # 4-D filters are viewed as [len, -1] (muon.py:39-40)
+    MAX_STACK_BYTES = 4 << 30       # workspace cap of one batched call (a stack of 12 Swift-B w1 matrices needs ~1.3 GB)
+
+    def _muon_many(self, items, lr: float, wd: float, beta: float) -> None:
+        """items: [(param, grad, momentum)] owned by this rank.  Matrices of one shape go through ONE batched
+        ``swb200_muon_step`` (the Newton-Schulz products of the whole stack are single batched GEMM launches)."""
+        import ctypes as C
+        groups = {}
+        for p, g, m in items:
+            self._check(p), self._check(g)
+            rows = p.shape[0]
+            cols = p.numel() // rows                               # 4-D filters are viewed as [len, -1] (muon.py:39-40)
+            if min(rows, cols) < 8 or rows % 8 or cols % 8:
+                self._muon_small(p, g, m, rows, cols, lr, wd, beta)
+            else:
+                groups.setdefault((rows, cols, p.device), []).append((p, g, m))
         stream = torch.cuda.current_stream().cuda_stream
-        if min(rows, cols) < 8 or rows % 8 or cols % 8:
-            self._muon_small(p, grad, mom, rows, cols, lr, wd, beta)
-            return
-        ws = self._workspace(rows, cols, p.device)
-        _lib.check(self.lib.swb200_muon_step(p.data_ptr(), grad.data_ptr(), mom.data_ptr(), rows, cols, float(lr), float(wd),
-                                             float(beta), 1, 5, ws[1], ws[2], stream), "muon_step")
+        for (rows, cols, dev), lst in groups.items():
+            per = max(1, self.lib.swb200_muon_workspace_bytes(rows, cols, 1))
+            step = max(1, min(len(lst), self.MAX_STACK_BYTES // per))
+            for i in range(0, len(lst), step):
+                part = lst[i:i + step]
+                n = len(part)
+                ws = self._workspace(rows, cols, n, dev)
+                arr = lambda k: (C.c_void_p * n)(*[t[k].data_ptr() for t in part])
+                _lib.check(self.lib.swb200_muon_step(arr(0), arr(1), arr(2), n, rows, cols, float(lr), float(wd), float(beta), 1, 5,
+                                                     ws[1], ws[2], stream), "muon_step")
 
     @staticmethod
     def _muon_small(p, grad, mom, rows, cols, lr, wd, beta) -> None:
@@ -101,6 +116,7 @@ class MuonWithAuxAdam(torch.optim.Optimizer):
             if group["use_muon"]:
                 params = group["params"]
                 pad = params + [torch.empty_like(params[-1])] * (world - len(params) % world) if distributed else params
+                mine = []                      # the matrices of this rank: params[base + rank] for every base (muon.py:218-221)
                 for base_i in range(0, len(params), world):
                     if base_i + rank < len(params):
                         p = params[base_i + rank]
@@ -109,8 +125,10 @@ class MuonWithAuxAdam(torch.optim.Optimizer):
                         st = self.state[p]
                         if len(st) == 0:
                             st["momentum_buffer"] = torch.zeros_like(p)
-                        self._muon(p, p.grad, st["momentum_buffer"], group["lr"], group["weight_decay"], group["momentum"])
-                    if distributed:
+                        mine.append((p, p.grad, st["momentum_buffer"]))
+                self._muon_many(mine, group["lr"], group["weight_decay"], group["momentum"])
+                if distributed:                # same collectives as the reference, after this rank's updates instead of between them
+                    for base_i in range(0, len(params), world):
                         dist.all_gather(pad[base_i:base_i + world], pad[base_i + rank], group=self._group)
             else:
                 stream = torch.cuda.current_stream().cuda_stream
