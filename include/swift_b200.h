@@ -218,9 +218,10 @@ SWB200_API int swb200_ln_mod_residual(const void* branch, int branch_16bit, void
                            int M, int dim, int tokens, int act_fp16, void* stream);
 /* shifted-window cosine attention on the packed qkv buffer (fp16 when qkv_fp16 else bf16; P uses the same format);
  * out 16-bit [M, heads*88], fp16 when out_fp16 else bf16 (out_fp16 needs qkv_fp16).
- * impl: 0 auto, 1 general-shift mma.sync kernel, 2 tcgen05/TMEM/TMA kernel (shift must be a multiple of 8). */
+ * impl: 0 auto, 1 general-shift mma.sync kernel, 2 tcgen05/TMEM/TMA kernel (shift must be a multiple of 8).
+ * lse (optional, tcgen05 kernel only): fp32 [heads][M], the log-sum-exp of every score row (saved for the backward). */
 SWB200_API int swb200_window_attention(const void* qkv, void* out, int B, int grid_h, int grid_w, int heads, int shift_h,
-                            int shift_w, int qkv_fp16, int out_fp16, int impl, void* stream);
+                            int shift_w, int qkv_fp16, int out_fp16, int impl, float* lse, void* stream);
 
 /* ---- tracing ---------------------------------------------------------------------------------------------- */
 
@@ -392,9 +393,11 @@ SWB200_API int swb200_ln_backward(float* dx, const float* add, const float* bran
                        void* stream);
 SWB200_API int swb200_swiglu_backward(const float* dh, const void* gu, void* dgu, int M, int dff, void* stream);
 SWB200_API size_t swb200_attention_backward_scratch_bytes(int B, int grid_h, int grid_w, int heads);
+/* impl 1: flash-style mma.sync kernels (any shift, recompute the row statistics); impl 2: the tcgen05 / TMEM kernel (shift a
+ * multiple of 8; lse = the log-sum-exp rows the tcgen05 forward wrote). */
 SWB200_API int swb200_attention_backward(const void* qkv, const void* O, const void* dO, const float* invn, const float* qscale,
-                              void* dqkv, float* dscale, int B, int grid_h, int grid_w, int heads, int shift_h, int shift_w,
-                              int accumulate, void* scratch, size_t scratch_bytes, void* stream);
+                              const float* lse, int impl, void* dqkv, float* dscale, int B, int grid_h, int grid_w, int heads,
+                              int shift_h, int shift_w, int accumulate, void* scratch, size_t scratch_bytes, void* stream);
 SWB200_API int swb200_qkv_pack_train(const float* raw, const float* qscale, void* packed, float* invn, int M, int heads,
                           void* stream);
 

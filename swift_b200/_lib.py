@@ -108,8 +108,8 @@ def _declare(lib):
         "swb200_ln_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _sz, _vp]),
         "swb200_swiglu_backward": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp]),
         "swb200_attention_backward_scratch_bytes": (_sz, [C.c_int, C.c_int, C.c_int, C.c_int]),
-        "swb200_attention_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                                C.c_int, C.c_int, _vp, _sz, _vp]),
+        "swb200_attention_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                C.c_int, C.c_int, C.c_int, _vp, _sz, _vp]),
         "swb200_qkv_pack_train": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
         "swb200_muon_workspace_bytes": (_sz, [C.c_int, C.c_int, C.c_int]),
         "swb200_muon_step": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int,
@@ -132,7 +132,7 @@ def _declare(lib):
         "swb200_patch_gather": (C.c_int, [MP, _vp, C.c_int, _f32, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp]),
         "swb200_ln_mod_residual": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
         "swb200_window_attention": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                              C.c_int, C.c_int, _vp]),
+                                              C.c_int, C.c_int, _vp, _vp]),
         "swb200_rollout_noise": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int64, _vp]),
         "swb200_rollout_forcings": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int,
                                               C.c_int, _vp]),

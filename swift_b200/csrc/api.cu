@@ -500,10 +500,10 @@ SWB200_API int swb200_ln_mod_residual(const void* branch, int branch_16bit, void
 }
 
 SWB200_API int swb200_window_attention(const void* qkv, void* out, int B, int grid_h, int grid_w, int heads, int shift_h,
-                            int shift_w, int qkv_fp16, int out_fp16, int impl, void* stream) {
+                            int shift_w, int qkv_fp16, int out_fp16, int impl, float* lse, void* stream) {
   SWB_REQUIRE(qkv && out, "swb200_window_attention: NULL pointer");
   return launch_window_attention(qkv, out, B, grid_h, grid_w, heads, shift_h, shift_w, qkv_fp16, out_fp16, impl,
-                                 static_cast<cudaStream_t>(stream));
+                                 static_cast<cudaStream_t>(stream), lse);
 }
 
 }  // extern "C"
@@ -783,7 +783,7 @@ namespace {
 
 struct Tape {
   size_t a_emb, x, x_stride, layers, layer_stride;
-  size_t qkv, invn, attn, b1, gu, h, b2;        // offsets inside one layer block
+  size_t qkv, invn, lse, attn, b1, gu, h, b2;   // offsets inside one layer block
   size_t total;
 };
 Tape carve_tape(const swb200_model* m, int B) {
@@ -808,6 +808,7 @@ Tape carve_tape(const swb200_model* m, int B) {
   };
   t.qkv = ltake(static_cast<size_t>(3) * m->heads * M * kHeadDimPad * 2);
   t.invn = ltake(static_cast<size_t>(2) * m->heads * M * 4);
+  t.lse = ltake(static_cast<size_t>(m->heads) * M * 4);
   t.attn = ltake(M * D * 2);
   t.b1 = ltake(M * D * 4);
   t.gu = ltake(M * 2 * Dff * 2);
@@ -865,9 +866,15 @@ TrainWs carve_train_ws(const swb200_train_model* tm, int B) {
   w.Lbuf = take(static_cast<size_t>(m->heads) * M * 4);
   w.Dbuf = take(static_cast<size_t>(m->heads) * M * 4);
   const size_t items = static_cast<size_t>(B) * (g.gh / 16) * (g.gw / 16) * m->heads;
-  w.dspart = take((items * 4 + static_cast<size_t>(m->heads) * 4) * 4);
+  w.dspart = take((items * 8 + static_cast<size_t>(m->heads) * 8) * 4);
   w.total = off;
   return w;
+}
+
+// the tcgen05 attention kernels (forward with log-sum-exp output, backward) handle shifts that are multiples of 8
+bool attn_tc_path(const swb200_model* m, bool shifted) {
+  if (m->attn_impl == 1) return false;
+  return !shifted || (m->shift_h % 8 == 0 && m->shift_w % 8 == 0);
 }
 
 int validate_train(const swb200_train_model* tm) {
@@ -975,7 +982,7 @@ SWB200_API int swb200_train_forward(const swb200_train_model* tm, const float* x
       if (rc) return rc;
     }
     rc = launch_window_attention(lb + t.qkv, lb + t.attn, B, g.gh, g.gw, H, shifted ? m->shift_h : 0, shifted ? m->shift_w : 0, 0, 0,
-                                 m->attn_impl, stream);
+                                 m->attn_impl, stream, attn_tc_path(m, shifted) ? reinterpret_cast<float*>(lb + t.lse) : nullptr);
     if (rc) return rc;
     {
       GemmParams p = base_params(M, D, D);
@@ -1100,16 +1107,24 @@ SWB200_API int swb200_train_backward_layer(const swb200_train_model* tm, int l, 
   if ((rc = dgrad(tm, dy16, D, static_cast<const bf*>(tm->wt_o) + static_cast<size_t>(l) * D * D, D, M, ws + w.da16, EPI_STORE_ACT, stream)))
     return rc;
   float* dspart = reinterpret_cast<float*>(ws + w.dspart);
-  rc = launch_attention_bwd(lb + t.qkv, lb + t.attn, ws + w.da16, reinterpret_cast<const float*>(lb + t.invn),
-                            m->qscale + static_cast<size_t>(l) * H, dy16, reinterpret_cast<float*>(ws + w.Lbuf),
-                            reinterpret_cast<float*>(ws + w.Dbuf), dspart, B, g.gh, g.gw, H, kHeadDim, kHeadDimPad,
-                            shifted ? m->shift_h : 0, shifted ? m->shift_w : 0, stream);
+  const bool tc = attn_tc_path(m, shifted);
+  const int nper = tc ? 8 : 4;                  // partial sums of the logit-scale gradient per (sample, window, head)
+  if (tc)
+    rc = launch_attention_bwd_tc(lb + t.qkv, lb + t.attn, ws + w.da16, reinterpret_cast<const float*>(lb + t.lse),
+                                 reinterpret_cast<const float*>(lb + t.invn), m->qscale + static_cast<size_t>(l) * H, dy16,
+                                 reinterpret_cast<float*>(ws + w.Dbuf), dspart, B, g.gh, g.gw, H, shifted ? m->shift_h : 0,
+                                 shifted ? m->shift_w : 0, stream);
+  else
+    rc = launch_attention_bwd(lb + t.qkv, lb + t.attn, ws + w.da16, reinterpret_cast<const float*>(lb + t.invn),
+                              m->qscale + static_cast<size_t>(l) * H, dy16, reinterpret_cast<float*>(ws + w.Lbuf),
+                              reinterpret_cast<float*>(ws + w.Dbuf), dspart, B, g.gh, g.gw, H, kHeadDim, kHeadDimPad,
+                              shifted ? m->shift_h : 0, shifted ? m->shift_w : 0, stream);
   if (rc) return rc;
-  {   // ds[head] = sum over (sample, window, 64-row tile) of the block partials: [bw][head][4] -> [head][4] -> [head]
+  {   // ds[head] = sum over (sample, window) and the kernel's partials per item: [bw][head][nper] -> [head][nper] -> [head]
     const int per = B * (g.gh / 16) * (g.gw / 16);
-    float* small = dspart + static_cast<size_t>(per) * H * 4;
-    if ((rc = launch_reduce_partials(dspart, per, H * 4, small, 1, 0, stream))) return rc;
-    if ((rc = launch_reduce_partials(small, 4, 1, gr->dscale + static_cast<size_t>(l) * H, H, acc, stream))) return rc;
+    float* small = dspart + static_cast<size_t>(per) * H * nper;
+    if ((rc = launch_reduce_partials(dspart, per, H * nper, small, 1, 0, stream))) return rc;
+    if ((rc = launch_reduce_partials(small, nper, 1, gr->dscale + static_cast<size_t>(l) * H, H, acc, stream))) return rc;
   }
   if ((rc = launch_transpose16(dy16, M, 3 * D, 3 * D, dyT, M, stream))) return rc;
   if ((rc = launch_transpose16(x0p, M, D, 2 * D, xT, M, stream))) return rc;
@@ -1225,13 +1240,16 @@ SWB200_API size_t swb200_attention_backward_scratch_bytes(int B, int grid_h, int
   if (B <= 0 || grid_h <= 0 || grid_w <= 0 || heads <= 0) return 0;
   const size_t M = static_cast<size_t>(B) * grid_h * grid_w;
   const size_t items = static_cast<size_t>(B) * (grid_h / 16) * (grid_w / 16) * heads;
-  return (2 * heads * M + items * 4 + static_cast<size_t>(heads) * 4) * sizeof(float);
+  return (2 * heads * M + items * 8 + static_cast<size_t>(heads) * 8) * sizeof(float);
 }
 
 SWB200_API int swb200_attention_backward(const void* qkv, const void* O, const void* dO, const float* invn, const float* qscale,
-                                         void* dqkv, float* dscale, int B, int grid_h, int grid_w, int heads, int shift_h,
-                                         int shift_w, int accumulate, void* scratch, size_t scratch_bytes, void* stream_) {
+                                         const float* lse, int impl, void* dqkv, float* dscale, int B, int grid_h, int grid_w,
+                                         int heads, int shift_h, int shift_w, int accumulate, void* scratch, size_t scratch_bytes,
+                                         void* stream_) {
   SWB_REQUIRE(qkv && O && dO && invn && qscale && dqkv && dscale && scratch, "swb200_attention_backward: NULL pointer");
+  SWB_REQUIRE(impl == 1 || impl == 2, "swb200_attention_backward: impl must be 1 (mma.sync) or 2 (tcgen05)");
+  SWB_REQUIRE(impl == 1 || lse != nullptr, "swb200_attention_backward: the tcgen05 kernel needs the forward's log-sum-exp");
   SWB_REQUIRE(scratch_bytes >= swb200_attention_backward_scratch_bytes(B, grid_h, grid_w, heads),
               "swb200_attention_backward: scratch too small");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -1239,13 +1257,16 @@ SWB200_API int swb200_attention_backward(const void* qkv, const void* O, const v
   float* Lbuf = static_cast<float*>(scratch);
   float* Dbuf = Lbuf + heads * M;
   float* dspart = Dbuf + heads * M;
-  int rc = launch_attention_bwd(qkv, O, dO, invn, qscale, dqkv, Lbuf, Dbuf, dspart, B, grid_h, grid_w, heads, kHeadDim, kHeadDimPad,
-                                shift_h, shift_w, stream);
+  const int nper = impl == 2 ? 8 : 4;
+  int rc = impl == 2 ? launch_attention_bwd_tc(qkv, O, dO, lse, invn, qscale, dqkv, Dbuf, dspart, B, grid_h, grid_w, heads, shift_h,
+                                               shift_w, stream)
+                     : launch_attention_bwd(qkv, O, dO, invn, qscale, dqkv, Lbuf, Dbuf, dspart, B, grid_h, grid_w, heads, kHeadDim,
+                                            kHeadDimPad, shift_h, shift_w, stream);
   if (rc) return rc;
   const int per = B * (grid_h / 16) * (grid_w / 16);
-  float* small = dspart + static_cast<size_t>(per) * heads * 4;
-  if ((rc = launch_reduce_partials(dspart, per, heads * 4, small, 1, 0, stream))) return rc;
-  return launch_reduce_partials(small, 4, 1, dscale, heads, accumulate, stream);
+  float* small = dspart + static_cast<size_t>(per) * heads * nper;
+  if ((rc = launch_reduce_partials(dspart, per, heads * nper, small, 1, 0, stream))) return rc;
+  return launch_reduce_partials(small, nper, 1, dscale, heads, accumulate, stream);
 }
 
 SWB200_API int swb200_qkv_pack_train(const float* raw, const float* qscale, void* packed, float* invn, int M, int heads,

@@ -219,12 +219,13 @@ window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
 }
 
 int launch_window_attention(const void* qkv, void* out, int B, int gh, int gw, int heads, int shift_h, int shift_w,
-                            int act_f16, int out_f16, int impl, cudaStream_t stream) {
+                            int act_f16, int out_f16, int impl, cudaStream_t stream, float* lse) {
   using namespace att;
   SWB_REQUIRE(act_f16 || !out_f16, "window_attention: bf16 q/k/v with fp16 output is not a supported combination");
   SWB_REQUIRE(impl >= 0 && impl <= 2, "window_attention: impl must be 0 (auto), 1 (mma.sync) or 2 (tcgen05)");
   if (impl == 2 || (impl == 0 && shift_h % 8 == 0 && shift_w % 8 == 0))
-    return launch_window_attention_tc(qkv, out, B, gh, gw, heads, shift_h, shift_w, act_f16, out_f16, stream);
+    return launch_window_attention_tc(qkv, out, B, gh, gw, heads, shift_h, shift_w, act_f16, out_f16, stream, lse);
+  SWB_REQUIRE(lse == nullptr, "window_attention: the log-sum-exp output needs the tcgen05 kernel (shift a multiple of 8)");
   SWB_REQUIRE(gh % kWin == 0 && gw % kWin == 0, "window_attention: token grid %dx%d not divisible by 16x16 windows",
               gh, gw);
   static PerDevice<bool> attr_done;

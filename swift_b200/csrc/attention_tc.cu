@@ -52,6 +52,7 @@ struct AttnTcParams {
   int B, gh, gw, heads, M;
   int shift_by, shift_bx;     // cyclic shift in units of 8 tokens
   void* out;                  // [M, heads*88] 16-bit
+  float* lse;                 // optional [heads][M]: log-sum-exp of every score row (what the backward needs), or null
 };
 
 // rows of a warp are 32 tokens = 4 token-grid lines of 8: row r sits at (r>>3)*pitch8 + (r&7)*pitch1 bytes
@@ -245,6 +246,12 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(P_FULL0 + h));
+      if (p.lse != nullptr) {                                // training forward: L_i = max_i + ln(sum_j exp(S_ij - max_i))
+        const int blk_ = 2 * h + (quad >> 1);
+        const int xl = ((2 * wx + (blk_ & 1) + p.shift_bx) % nbx) * 8 + (lane & 7);
+        const int yl = ((2 * wy + (blk_ >> 1) + p.shift_by) % nby) * 8 + 4 * (quad & 1) + (lane >> 3);
+        p.lse[static_cast<size_t>(head) * p.M + (static_cast<size_t>(b) * p.gh + yl) * p.gw + xl] = mx + __logf(sum);
+      }
       // O_h = P_h V
       mbar_wait(bar(O_FULL0 + h), par, 32);
       tcgen05_fence_after();
@@ -316,7 +323,7 @@ static int make_tmap_qkv(CUtensorMap* out, const void* qkv, bool f16, int heads,
 }
 
 int launch_window_attention_tc(const void* qkv, void* out, int B, int gh, int gw, int heads, int shift_h, int shift_w,
-                               int act_f16, int out_f16, cudaStream_t stream) {
+                               int act_f16, int out_f16, cudaStream_t stream, float* lse) {
   using namespace atc;
   SWB_REQUIRE(act_f16 || !out_f16, "window_attention_tc: bf16 q/k/v with fp16 output is not a supported combination");
   SWB_REQUIRE(gh % 16 == 0 && gw % 16 == 0 && shift_h % 8 == 0 && shift_w % 8 == 0,
@@ -347,6 +354,7 @@ int launch_window_attention_tc(const void* qkv, void* out, int B, int gh, int gw
   p.shift_by = shift_h / 8;
   p.shift_bx = shift_w / 8;
   p.out = out;
+  p.lse = lse;
   const int items = B * (gh / 16) * (gw / 16) * heads;
   const int grid = items < num_sms() ? items : num_sms();
   if (act_f16 && out_f16)

@@ -35,10 +35,14 @@ int launch_conditioning(const CondWeights& w, const float* t, const float* aux, 
 // normalised and q scaled by the GEMM epilogue); out is [M, heads*88] in the same 16-bit format in un-shifted token order.
 // impl: 0 = auto (tcgen05 kernel when the shift is a multiple of 8, else the mma.sync kernel), 1 = mma.sync, 2 = tcgen05
 // act_f16: format of q / k / v (and of P inside the kernel); out_f16: format of `out` (fp16 out needs fp16 q/k/v)
+// lse (optional, tcgen05 kernel only): fp32 [heads][M] log-sum-exp of every score row, saved for the backward
 int launch_window_attention(const void* qkv, void* out, int B, int gh, int gw, int heads, int shift_h, int shift_w,
-                            int act_f16, int out_f16, int impl, cudaStream_t stream);
+                            int act_f16, int out_f16, int impl, cudaStream_t stream, float* lse = nullptr);
 int launch_window_attention_tc(const void* qkv, void* out, int B, int gh, int gw, int heads, int shift_h, int shift_w,
-                               int act_f16, int out_f16, cudaStream_t stream);
+                               int act_f16, int out_f16, cudaStream_t stream, float* lse = nullptr);
+int launch_attention_bwd_tc(const void* qkv, const void* O, const void* dO, const float* L, const float* invn, const float* qscale,
+                            void* dqkv, float* Dbuf, float* ds_part, int B, int gh, int gw, int heads, int shift_h, int shift_w,
+                            cudaStream_t stream);
 
 // elements of a fp16 [rows, cols] tensor (row pitch in elements) with |x| == 65504 are added to *counter
 int launch_count_saturated_f16(const void* buf, long long rows, int cols, long long pitch, unsigned long long* counter,

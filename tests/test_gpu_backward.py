@@ -122,9 +122,10 @@ def _attention_ref(raw, qscale, B, gh, gw, H, shift):
     return o.reshape(M, H * HD)
 
 
-@pytest.mark.parametrize("shift", [(0, 0), (8, 8)])
-@pytest.mark.parametrize("B,gh,gw,H", [(1, 16, 32, 3), (2, 32, 32, 2)])
-def test_attention_backward(lib, shift, B, gh, gw, H):
+@pytest.mark.parametrize("impl", [2, 1], ids=["tcgen05", "mma_sync"])
+@pytest.mark.parametrize("shift", [(0, 0), (8, 8), (8, 0)])
+@pytest.mark.parametrize("B,gh,gw,H", [(1, 16, 32, 3), (2, 32, 32, 2), (1, 64, 128, 12)])
+def test_attention_backward(lib, shift, B, gh, gw, H, impl):
     M, D = B * gh * gw, H * HD
     g = torch.Generator(device="cuda").manual_seed(11)
     raw = torch.randn(M, 3 * D, device="cuda", generator=g)
@@ -133,16 +134,32 @@ def test_attention_backward(lib, shift, B, gh, gw, H):
     invn = torch.empty(2, H, M, device="cuda")
     _check(lib.swb200_qkv_pack_train(raw.data_ptr(), qscale.data_ptr(), packed.data_ptr(), invn.data_ptr(), M, H, _stream()))
     O = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
-    _check(lib.swb200_window_attention(packed.data_ptr(), O.data_ptr(), B, gh, gw, H, shift[0], shift[1], 0, 0, 0, _stream()))
+    lse = torch.full((H, M), float("nan"), device="cuda")
+    _check(lib.swb200_window_attention(packed.data_ptr(), O.data_ptr(), B, gh, gw, H, shift[0], shift[1], 0, 0, 2, lse.data_ptr(),
+                                       _stream()))
     dO = (torch.randn(M, D, device="cuda", generator=g) * 1e-5).to(torch.bfloat16)
     dqkv = torch.full((M, 3 * D), float("nan"), device="cuda", dtype=torch.bfloat16)
     dscale = torch.zeros(H, device="cuda")
     need = lib.swb200_attention_backward_scratch_bytes(B, gh, gw, H)
     scratch = torch.empty(need, dtype=torch.uint8, device="cuda")
     _check(lib.swb200_attention_backward(packed.data_ptr(), O.data_ptr(), dO.data_ptr(), invn.data_ptr(), qscale.data_ptr(),
-                                         dqkv.data_ptr(), dscale.data_ptr(), B, gh, gw, H, shift[0], shift[1], 0, scratch.data_ptr(),
-                                         need, _stream()))
+                                         lse.data_ptr(), impl, dqkv.data_ptr(), dscale.data_ptr(), B, gh, gw, H, shift[0], shift[1], 0,
+                                         scratch.data_ptr(), need, _stream()))
     torch.cuda.synchronize()
+    # the log-sum-exp rows of the forward against the definition (token order)
+    rq = raw.reshape(M, H, 3, HD)
+    qn = torch.nn.functional.normalize(rq[:, :, 0].double(), dim=-1) * qscale.double()[None, :, None]
+    kn = torch.nn.functional.normalize(rq[:, :, 1].double(), dim=-1)
+
+    def win(t):                                                      # [M, H, HD] -> [BW, H, 256, HD]
+        t = t.reshape(B, gh, gw, H, HD)
+        t = torch.roll(t, shifts=(-shift[0], -shift[1]), dims=(1, 2))
+        return t.reshape(B, gh // 16, 16, gw // 16, 16, H, HD).permute(0, 1, 3, 5, 2, 4, 6).reshape(-1, H, 256, HD)
+
+    lse_ref = torch.logsumexp(win(qn) @ win(kn).transpose(-1, -2), dim=-1)                       # [BW, H, 256]
+    lse_ref = lse_ref.reshape(B, gh // 16, gw // 16, H, 16, 16).permute(0, 1, 4, 2, 5, 3).reshape(B, gh, gw, H)
+    lse_ref = torch.roll(lse_ref, shifts=(shift[0], shift[1]), dims=(1, 2)).reshape(M, H).t()
+    assert torch.allclose(lse.double(), lse_ref, rtol=0, atol=3e-2), (lse.double() - lse_ref).abs().max()
     # the packed operands and the inverse norms against the definition
     r = raw.reshape(M, H, 3, HD).permute(2, 1, 0, 3)
     assert _rel(invn[0], 1 / r[0].norm(dim=-1)) < 1e-5 and _rel(invn[1], 1 / r[1].norm(dim=-1)) < 1e-5

@@ -132,7 +132,7 @@ def test_window_attention(lib, shift, B, gh, gw, H, f16, o16, impl):
     qkv = raw.to(_adt(f16)).contiguous()
     out = torch.full((M, H * HD), float("nan"), device="cuda", dtype=_adt(o16))
     _check(lib.swb200_window_attention(qkv.data_ptr(), out.data_ptr(), B, gh, gw, H, shift[0], shift[1], f16, o16, impl,
-                                       _stream()))
+                                       None, _stream()))
     torch.cuda.synchronize()
     ref = _window_attention_ref(qkv, B, gh, gw, H, shift)
     assert torch.isfinite(out.float()).all()
