@@ -412,6 +412,10 @@ SWB200_API size_t swb200_muon_workspace_bytes(int rows, int cols, int batch);
 SWB200_API int swb200_muon_step(float* const* params, const float* const* grads, float* const* momenta, int batch, int rows, int cols,
                      float lr, float weight_decay, float beta, int nesterov, int ns_steps, void* workspace,
                      size_t workspace_bytes, void* stream);
+/* The same update for a vector-shaped parameter (rows == 1 or cols == 1, at most 4096 elements; Swift-B: the [1, heads, 1, 1]
+ * logit scales, which train.py:289 also hands to Muon): the Newton-Schulz products collapse to scalars. */
+SWB200_API int swb200_muon_vector_step(float* param, const float* grad, float* momentum, int rows, int cols, float lr,
+                            float weight_decay, float beta, int nesterov, int ns_steps, void* stream);
 /* AuxAdam for one tensor of n elements (muon.py:147-152, :261-266); step counts from 1. */
 SWB200_API int swb200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                      float beta2, float eps, float weight_decay, int step, void* stream);

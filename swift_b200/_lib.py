@@ -28,7 +28,7 @@ EXPORTS = (
     "swb200_train_backward_layer", "swb200_train_backward_embed", "swb200_conditioning_backward_scratch_bytes",
     "swb200_conditioning_backward", "swb200_gemm_splitk", "swb200_transpose16", "swb200_ln_backward_scratch_bytes",
     "swb200_ln_backward", "swb200_swiglu_backward", "swb200_attention_backward_scratch_bytes", "swb200_attention_backward",
-    "swb200_qkv_pack_train", "swb200_muon_workspace_bytes", "swb200_muon_step", "swb200_adam_step",
+    "swb200_qkv_pack_train", "swb200_muon_workspace_bytes", "swb200_muon_step", "swb200_adam_step", "swb200_muon_vector_step",
     "swb200_packed_bytes", "swb200_pack_weights",
 )
 
@@ -114,6 +114,7 @@ def _declare(lib):
         "swb200_muon_workspace_bytes": (_sz, [C.c_int, C.c_int, C.c_int]),
         "swb200_muon_step": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int,
                                        _f32, _f32, _f32, C.c_int, C.c_int, _vp, _sz, _vp]),
+        "swb200_muon_vector_step": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _f32, _f32, _f32, C.c_int, C.c_int, _vp]),
         "swb200_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, _f32, _f32, _f32, _f32, _f32, C.c_int, _vp]),
         "swb200_abi_version": (C.c_int, []),
         "swb200_last_error": (C.c_char_p, []),

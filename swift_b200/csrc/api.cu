@@ -1287,6 +1287,13 @@ SWB200_API int swb200_muon_step(float* const* params, const float* const* grads,
                           workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
+SWB200_API int swb200_muon_vector_step(float* param, const float* grad, float* momentum, int rows, int cols, float lr,
+                                       float weight_decay, float beta, int nesterov, int ns_steps, void* stream) {
+  SWB_REQUIRE(param && grad && momentum, "swb200_muon_vector_step: NULL pointer");
+  return launch_muon_vector(param, grad, momentum, rows, cols, lr, weight_decay, beta, nesterov, ns_steps,
+                            static_cast<cudaStream_t>(stream));
+}
+
 SWB200_API int swb200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                                 float beta2, float eps, float weight_decay, int step, void* stream) {
   SWB_REQUIRE(param && grad && exp_avg && exp_avg_sq, "swb200_adam_step: NULL pointer");

@@ -116,6 +116,8 @@ int launch_pack_qscale(const float* scale, float* out, int heads, cudaStream_t s
 size_t muon_workspace_bytes(int rows, int cols, int batch);
 int launch_muon_step(float* const* param, const float* const* grad, float* const* momentum, int batch, int rows, int cols, float lr,
                      float weight_decay, float beta, int nesterov, int ns_steps, void* workspace, size_t ws_bytes, cudaStream_t st);
+int launch_muon_vector(float* param, const float* grad, float* momentum, int rows, int cols, float lr, float weight_decay, float beta,
+                       int nesterov, int ns_steps, cudaStream_t st);
 int launch_transpose16_batched(const void* in, int R, int C, void* out, int batch, cudaStream_t stream);
 int launch_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float wd,
                      int step, cudaStream_t st);

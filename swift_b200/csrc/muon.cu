@@ -159,6 +159,58 @@ __global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, c
   p[i] = fmaf(p[i], 1.0f - lr * wd, -lr * upd);
 }
 
+// Muon for a VECTOR-shaped parameter (1 x n or n x 1; Swift-B: the [1, heads, 1, 1] logit scales): with one row the
+// Newton-Schulz products collapse to scalars -- A = X X^T = |X|^2, B = b A + c A A, X <- a X + B X -- evaluated with the same
+// bf16 roundings as the matrix path.  One block per vector.
+__global__ void __launch_bounds__(256) muon_vector_kernel(float* __restrict__ p, const float* __restrict__ grad, float* __restrict__ mom,
+                                                          int n, float beta, int nesterov, int ns_steps, float decay, float step) {
+  __shared__ float red[256];
+  auto block_sum = [&](float v) {
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+      if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+      __syncthreads();
+    }
+    const float r = red[0];
+    __syncthreads();
+    return r;
+  };
+  constexpr int kMax = 16;                             // n <= 4096
+  float x[kMax];
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMax; ++j) {
+    const int i = threadIdx.x + 256 * j;
+    x[j] = 0.f;
+    if (i < n) {
+      const float g = grad[i];
+      const float m = fmaf(1.0f - beta, g - mom[i], mom[i]);
+      mom[i] = m;
+      x[j] = bf16_round(nesterov ? fmaf(beta, m - g, g) : m);
+      ss = fmaf(x[j], x[j], ss);
+    }
+  }
+  const float inv = 1.0f / (bf16_round(sqrtf(block_sum(ss))) + 1e-7f);
+#pragma unroll
+  for (int j = 0; j < kMax; ++j) x[j] = bf16_round(x[j] * inv);
+  const float a = 3.4445f, b = -4.7750f, c = 2.0315f;
+  for (int it = 0; it < ns_steps; ++it) {
+    float s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMax; ++j) s2 = fmaf(x[j], x[j], s2);
+    const float A = bf16_round(block_sum(s2));
+    const float B = bf16_round(bf16_round(b * A) + bf16_round(c * bf16_round(A * A)));
+#pragma unroll
+    for (int j = 0; j < kMax; ++j) x[j] = bf16_round(bf16_round(a * x[j]) + bf16_round(B * x[j]));
+  }
+#pragma unroll
+  for (int j = 0; j < kMax; ++j) {
+    const int i = threadIdx.x + 256 * j;
+    if (i < n) p[i] = fmaf(p[i], decay, -step * x[j]);
+  }
+}
+
 inline unsigned blocks_for(long long n) { return static_cast<unsigned>((n + 255) / 256); }
 inline size_t up(size_t v) { return (v + 1023) / 1024 * 1024; }
 
@@ -260,6 +312,18 @@ int launch_muon_step(float* const* param, const float* const* grad, float* const
   const float scale = sqrtf(fmaxf(1.0f, static_cast<float>(rows) / static_cast<float>(cols)));
   for (int i = 0; i < batch; ++i)
     muon_apply_kernel<<<blocks_for(n_el / 4), 256, 0, st>>>(param[i], U + i * n_el, n_el, 1.0f - lr * weight_decay, lr * scale);
+  SWB_CHECK_CUDA(cudaGetLastError());
+  return SWB_OK;
+}
+
+// rows x cols with min(rows, cols) == 1
+int launch_muon_vector(float* param, const float* grad, float* momentum, int rows, int cols, float lr, float weight_decay, float beta,
+                       int nesterov, int ns_steps, cudaStream_t st) {
+  SWB_REQUIRE((rows == 1 || cols == 1) && rows * cols >= 1 && rows * cols <= 4096,
+              "muon_vector: %d x %d is not a vector of at most 4096 elements", rows, cols);
+  const float scale = sqrtf(fmaxf(1.0f, static_cast<float>(rows) / static_cast<float>(cols)));
+  muon_vector_kernel<<<1, 256, 0, st>>>(param, grad, momentum, rows * cols, beta, nesterov, ns_steps, 1.0f - lr * weight_decay,
+                                        lr * scale);
   SWB_CHECK_CUDA(cudaGetLastError());
   return SWB_OK;
 }

@@ -81,25 +81,15 @@ class MuonWithAuxAdam(torch.optim.Optimizer):
                 _lib.check(self.lib.swb200_muon_step(arr(0), arr(1), arr(2), n, rows, cols, float(lr), float(wd), float(beta), 1, 5,
                                                      ws[1], ws[2], stream), "muon_step")
 
-    @staticmethod
-    def _muon_small(p, grad, mom, rows, cols, lr, wd, beta) -> None:
-        """Matrices the GEMM kernel does not tile (Swift-B: only the [1, heads, 1, 1] logit scales, 12 numbers each): the same
-        update rule written out with tensor ops on the device -- host-side plumbing, no tensor-core work to speak of."""
-        a, b, c = 3.4445, -4.7750, 2.0315
-        mom.lerp_(grad, 1 - beta)
-        X = torch.lerp(grad, mom, beta).reshape(rows, cols).bfloat16()
-        tall = rows > cols
-        if tall:
-            X = X.mT
-        X = X / (X.norm() + 1e-7)
-        for _ in range(5):
-            A = X @ X.mT
-            B = b * A + c * A @ A
-            X = a * X + B @ X
-        if tall:
-            X = X.mT
-        upd = X.to(torch.float32) * max(1, rows / cols) ** 0.5
-        p.mul_(1 - lr * wd).add_(upd.reshape(p.shape), alpha=-lr)
+    def _muon_small(self, p, grad, mom, rows, cols, lr, wd, beta) -> None:
+        """Shapes the GEMM kernel does not tile.  Vectors (Swift-B: the [1, heads, 1, 1] logit scales, which train.py:289
+        hands to Muon as well) have their own kernel: with one row the Newton-Schulz products are scalars."""
+        if min(rows, cols) != 1 or rows * cols > 4096:
+            raise NotImplementedError(f"swift_b200 Muon handles matrices whose extents are multiples of 8 and vectors of at "
+                                      f"most 4096 elements, got {rows} x {cols}")
+        _lib.check(self.lib.swb200_muon_vector_step(p.data_ptr(), grad.data_ptr(), mom.data_ptr(), rows, cols, float(lr),
+                                                    float(wd), float(beta), 1, 5, torch.cuda.current_stream().cuda_stream),
+                   "muon_vector_step")
 
     # ------------------------------------------------------------------ step
     @torch.no_grad()
