@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libswift_b200.so")
-SOURCES = ["gemm.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "attention_bwd.cu", "attention_bwd_tc.cu", "rollout.cu", "ensemble.cu", "tangent.cu", "scm_target.cu", "train.cu", "muon.cu", "pack.cu", "api.cu"]
+SOURCES = ["gemm.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "attention_bwd.cu", "attention_bwd_tc.cu", "attention_dual_tc.cu", "rollout.cu", "ensemble.cu", "tangent.cu", "scm_target.cu", "train.cu", "muon.cu", "pack.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 NVCC_FLAGS += os.environ.get("SWB_NVCC_DEFINES", "").split()      # e.g. "-DSWB_A_TMEM=1" for A/B builds of one kernel choice

@@ -62,6 +62,8 @@ int launch_qkv_dual_pack(const float* raw2, const float* qscale, void* qkv, void
                          int pad, int act_f16, cudaStream_t stream);
 int launch_attention_dual(const void* qkv, const void* dqkv, float* S, float* dS, void* attn2, int B, int gh, int gw,
                           int heads, int hd, int pad, int shift_h, int shift_w, int act_f16, cudaStream_t stream);
+int launch_attention_dual_tc(const void* qkv, const void* dqkv, void* attn2, int B, int gh, int gw, int heads, int shift_h, int shift_w,
+                             int act_f16, cudaStream_t stream);
 int launch_swiglu_dual(const float* raw2, void* h2, int M, int Dff, int tile, int act_f16, cudaStream_t stream);
 int launch_conditioning_dual(const CondWeights& w, const float* t, const float* dt, const float* aux, int B, int D, int L,
                              float timestep_weight, float* scratch, float* gain, float* bias, float* dgain, float* dbias,

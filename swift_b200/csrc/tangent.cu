@@ -571,6 +571,10 @@ __global__ void __launch_bounds__(128) attn_fused_dual_kernel(const uint16_t* __
 int launch_attention_dual(const void* qkv, const void* dqkv, float* S, float* dS, void* attn2, int B, int gh, int gw,
                           int heads, int hd, int pad, int shift_h, int shift_w, int act_f16, cudaStream_t stream) {
   SWB_REQUIRE(gh % 16 == 0 && gw % 16 == 0 && hd <= 96, "attention_dual: grid %dx%d / head_dim %d unsupported", gh, gw, hd);
+  // the tcgen05 / TMEM kernel (attention_dual_tc.cu) for shifts that are multiples of 8; SWB_DUAL_ATTN_MMA: A/B knob (tools)
+  static const bool force_mma = getenv("SWB_DUAL_ATTN_MMA") != nullptr || getenv("SWB_DUAL_ATTN_SPLIT") != nullptr;
+  if (!force_mma && hd == 88 && pad == 96 && shift_h % 8 == 0 && shift_w % 8 == 0)
+    return launch_attention_dual_tc(qkv, dqkv, attn2, B, gh, gw, heads, shift_h, shift_w, act_f16, stream);
   AttnDualGeom g;
   g.B = B; g.gh = gh; g.gw = gw; g.heads = heads; g.M = B * gh * gw;
   g.shift_h = shift_h; g.shift_w = shift_w; g.pad = pad; g.hd = hd;
