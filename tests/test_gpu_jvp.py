@@ -182,15 +182,19 @@ def test_scm_training_step_gradients_vs_reference_backward(golden):
                            w_var=variable_weights(SCM_LOSS_VARIABLES[:n_img], "cuda"))
         assert abs(float(out["loss"]) - float(g[k + "loss"])) < 1e-2 * float(g[k + "loss"])
         grads = {"model." + name: p.grad for name, p in net.model.named_parameters()}
-        worst = 0.0
+        worst, worst_nm, worst_mat = 0.0, "", 0.0
         for nm, ref in zip((str(s) for s in g[k + "grad_names"]), g[k + "grad_norms"]):
             got = float(grads[nm].norm())
-            worst = max(worst, abs(got - ref) / ref)
+            e = abs(got - ref) / ref
+            if e > worst:
+                worst, worst_nm = e, nm
+            if not nm.endswith(".scale"):            # (the logit scale: one number per head, a sum of cancelling terms)
+                worst_mat = max(worst_mat, e)
         worst_s = 0.0
         for kk in g:
             if kk.startswith(k + "grad:"):
                 nm = kk.split("grad:")[1]
                 worst_s = max(worst_s, _rel(grads[nm].flatten()[::31].cpu(), torch.from_numpy(g[kk])))
-        print(f"sCM step on the CUDA path ({cfgname}): worst gradient-norm error {worst:.3e}, worst sampled-gradient rel-L2 "
-              f"{worst_s:.3e}")
-        assert worst < 5e-2 and worst_s < 5e-2
+        print(f"sCM step on the CUDA path ({cfgname}): worst gradient-norm error {worst:.3e} ({worst_nm}), without the logit "
+              f"scales {worst_mat:.3e}; worst sampled-gradient rel-L2 {worst_s:.3e}")
+        assert worst < 5e-2 and worst_mat < 1e-2 and worst_s < 5e-2
