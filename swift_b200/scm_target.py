@@ -68,6 +68,10 @@ def scm_output_cotangent(net, x: torch.Tensor, t: torch.Tensor, z: torch.Tensor,
     model = inner.model
     if not hasattr(model, "engine"):
         raise TypeError("scm_output_cotangent needs swift_b200.swinv2.SwinV2 as net.model (there is no fallback path)")
+    if getattr(model, "logvar_embed", None) is not None:
+        # loss.py:221-257: with logvar the term is weighted by exp(-logvar) and + logvar is added; not implemented here, and a
+        # silently different objective would be worse than an error (model/swinv2.yaml: logvar: false)
+        raise NotImplementedError("SCMLoss with a logvar head is not implemented on the CUDA path")
     eng = model.engine()
     lib, dev = eng.lib, x.device
     stream = torch.cuda.current_stream().cuda_stream
