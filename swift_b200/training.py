@@ -121,7 +121,7 @@ class TrainEngine:
 
     # ------------------------------------------------------------------ backward
     def backward(self, cot: torch.Tensor, accumulate: bool = False,
-                 on_stage: Optional[Callable[[str, int], None]] = None) -> Dict[str, torch.Tensor]:
+                 on_stage: Optional[Callable[[str, int], None]] = None, cond_exchange=None) -> Dict[str, torch.Tensor]:
         """Parameter gradients of ``sum(F * cot)`` for the last ``forward``.  ``on_stage(kind, layer)`` is called after
         the kernels of a stage have been enqueued ("head", "layer" l = depth-1 .. 0, "embed", "cond"): the hook for
         overlapping the gradient all-reduce of finished stages with the rest of the backward."""
@@ -152,14 +152,21 @@ class TrainEngine:
         if on_stage:
             on_stage("embed", -1)
         bp = C.byref(self.model.base)
-        need = self.lib.swb200_conditioning_backward_scratch_bytes(bp, B)
+        dgain, dbias, fwd_scratch, Bc, kind = self.grads["dgain"], self.grads["dbias"], self._cond_scratch, B, "cond"
+        if cond_exchange is not None:
+            # data parallel: instead of all-reducing the conditioning gradients (the 24 modulation Linears alone are 214 MB
+            # of fp32), every rank receives every rank's per-sample INPUTS of this stage (a few hundred KB) and evaluates the
+            # whole global batch -- the gradients are sums of per-sample outer products, so all ranks get the same, already
+            # averaged result with no collective on the gradients themselves
+            dgain, dbias, fwd_scratch, aux, Bc = cond_exchange(self, dgain, dbias, fwd_scratch, aux, B)
+            kind = "cond_replicated"
+        need = self.lib.swb200_conditioning_backward_scratch_bytes(bp, Bc)
         scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
-        _lib.check(self.lib.swb200_conditioning_backward(bp, _lib.ptr(aux), B, self._cond_scratch.data_ptr(),
-                                                         self.grads["dgain"].data_ptr(), self.grads["dbias"].data_ptr(),
-                                                         C.byref(self._cstruct), int(bool(accumulate)), scratch.data_ptr(), need,
-                                                         st), "conditioning_backward")
+        _lib.check(self.lib.swb200_conditioning_backward(bp, _lib.ptr(aux), Bc, fwd_scratch.data_ptr(), dgain.data_ptr(),
+                                                         dbias.data_ptr(), C.byref(self._cstruct), int(bool(accumulate)),
+                                                         scratch.data_ptr(), need, st), "conditioning_backward")
         if on_stage:
-            on_stage("cond", -1)
+            on_stage(kind, -1)
         return self.grads
 
     # ------------------------------------------------------------------ flat buffers -> reference parameter names
@@ -207,6 +214,8 @@ class TrainEngine:
             return [gr["w_2"][layer], gr["w_1"][layer], gr["w_o"][layer], gr["w_qkv"][layer], gr["dscale"][layer]]
         if kind == "embed":
             return [gr["w_embed_t"], gr["b_embed"], gr["pos_embed"]]
+        if kind == "cond_replicated":           # evaluated on the gathered global batch: already identical on every rank
+            return []
         return [gr[n] for n in ("l1_w", "l1_b", "l2_w", "l2_b", "mod_w", "mod_b", "ln_gamma", "ln_beta", "aux_w", "aux_b") if n in gr]
 
 
@@ -250,6 +259,44 @@ class GradientAllReduce:
                 self.bytes += b.numel() * 4
             e1.record(self.stream)
             self._events.append((e0, e1))
+
+    def exchange_conditioning(self, engine: "TrainEngine", dgain, dbias, fwd_scratch, aux, B: int):
+        """``cond_exchange`` of ``TrainEngine.backward``: one ``all_gather`` of every rank's conditioning-stage inputs (the
+        per-sample gain / bias gradients, the embedding / MLP activations and modulation vectors ``swb200_conditioning``
+        left in its scratch, the auxiliary input) -> the same tensors for the global batch of ``world * B`` samples, the
+        gradients pre-scaled by 1 / world so that the stage's output is the data-parallel MEAN."""
+        if self.world == 1:
+            return dgain, dbias, fwd_scratch, aux, B
+        g = engine.geom
+        D, L2 = g.dim, 2 * g.depth
+        n_sc = B * (3 * D + L2 * 2 * D)
+        sc = fwd_scratch.view(torch.float32)[:n_sc]
+        parts = [dgain.reshape(-1), dbias.reshape(-1), sc]
+        if aux is not None:
+            parts.append(aux.reshape(-1))
+        mine = torch.cat(parts).contiguous()
+        allr = torch.empty(self.world, mine.numel(), dtype=torch.float32, device=mine.device)
+        self.dist.all_gather_into_tensor(allr, mine, group=self.group)
+        self.bytes += allr.numel() * 4
+        W, o = self.world, 0
+        n_g = L2 * B * D
+
+        def take(n):
+            nonlocal o
+            v = allr[:, o:o + n]
+            o += n
+            return v
+
+        dg = take(n_g).reshape(W, L2, B, D).permute(1, 0, 2, 3).reshape(L2, W * B, D).mul(1.0 / W).contiguous()
+        db = take(n_g).reshape(W, L2, B, D).permute(1, 0, 2, 3).reshape(L2, W * B, D).mul(1.0 / W).contiguous()
+        scr = take(n_sc)
+        emb = scr[:, :B * D].reshape(W * B, D)
+        h1 = scr[:, B * D:2 * B * D].reshape(W * B, D)
+        cv = scr[:, 2 * B * D:3 * B * D].reshape(W * B, D)
+        mod = scr[:, 3 * B * D:].reshape(W * B, L2 * 2 * D)
+        scratch_all = torch.cat([emb.reshape(-1), h1.reshape(-1), cv.reshape(-1), mod.reshape(-1)]).contiguous()
+        aux_all = take(aux.numel()).reshape(W * B, -1).contiguous() if aux is not None else None
+        return dg, db, scratch_all, aux_all, W * B
 
     def finish(self) -> None:
         if self.world > 1 and self.stream is not None:
@@ -330,7 +377,8 @@ def scm_train_step(net, x: torch.Tensor, t: torch.Tensor, z: torch.Tensor, step:
     t1 = t.to(device=dev, dtype=torch.float32).reshape(B).contiguous()
     eng.forward(out["x_t"], cond, t1, aux, scale0=1.0 / float(inner.sigma_data))
     mark("train_forward")
-    eng.backward(out["cot"], accumulate=accumulate, on_stage=reducer.hook if reducer is not None else None)
+    eng.backward(out["cot"], accumulate=accumulate, on_stage=reducer.hook if reducer is not None else None,
+                 cond_exchange=reducer.exchange_conditioning if reducer is not None else None)
     mark("backward")
     if reducer is not None:
         reducer.finish()
