@@ -253,9 +253,8 @@ class GradientAllReduce:
             self.stream.wait_event(ready)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(self.stream)
-            for b in bufs:
-                self.dist.all_reduce(b, op=self.dist.ReduceOp.SUM, group=self.group)
-                b.mul_(1.0 / self.world)
+            for b in bufs:                            # NCCL averages inside the collective: no extra kernel per buffer
+                self.dist.all_reduce(b, op=self.dist.ReduceOp.AVG, group=self.group)
                 self.bytes += b.numel() * 4
             e1.record(self.stream)
             self._events.append((e0, e1))
