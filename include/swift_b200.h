@@ -354,6 +354,12 @@ typedef struct swb200_cond_grads {
   float* ln_beta;
 } swb200_cond_grads;
 
+/* Build the training model from a reference checkpoint on the device (like swb200_pack_weights): in: the geometry / option
+ * fields of m->base (act_fp16 = 0, split_embed = split_head = 1); out: every pointer of *m and kp_head, pointing into `packed`
+ * (swb200_train_packed_bytes(m) bytes, 256-byte aligned, must outlive every use of *m). */
+SWB200_API size_t swb200_train_packed_bytes(const swb200_train_model* m);
+SWB200_API int swb200_pack_train_weights(swb200_train_model* m, const swb200_ref_params* ref, void* packed, size_t packed_bytes,
+                              void* stream);
 /* Bytes of the activation tape one grad-enabled forward of B samples writes (and the backward reads), and of the scratch
  * workspace shared by forward and backward; both 1024-byte aligned.  Host only. */
 SWB200_API size_t swb200_train_tape_bytes(const swb200_train_model* m, int B);

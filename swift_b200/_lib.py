@@ -29,7 +29,7 @@ EXPORTS = (
     "swb200_conditioning_backward", "swb200_gemm_splitk", "swb200_transpose16", "swb200_ln_backward_scratch_bytes",
     "swb200_ln_backward", "swb200_swiglu_backward", "swb200_attention_backward_scratch_bytes", "swb200_attention_backward",
     "swb200_qkv_pack_train", "swb200_muon_workspace_bytes", "swb200_muon_step", "swb200_adam_step", "swb200_muon_vector_step",
-    "swb200_packed_bytes", "swb200_pack_weights",
+    "swb200_packed_bytes", "swb200_pack_weights", "swb200_train_packed_bytes", "swb200_pack_train_weights",
 )
 
 _i32, _f32, _vp, _sz = C.c_int32, C.c_float, C.c_void_p, C.c_size_t
@@ -93,6 +93,8 @@ def _declare(lib):
     sig = {
         "swb200_packed_bytes": (_sz, [MP]),
         "swb200_pack_weights": (C.c_int, [MP, C.POINTER(RefParams), _vp, _sz, _vp]),
+        "swb200_train_packed_bytes": (_sz, [TP]),
+        "swb200_pack_train_weights": (C.c_int, [TP, C.POINTER(RefParams), _vp, _sz, _vp]),
         "swb200_train_tape_bytes": (_sz, [TP, C.c_int]),
         "swb200_train_workspace_bytes": (_sz, [TP, C.c_int]),
         "swb200_train_forward": (C.c_int, [TP, _vp, C.c_int, _f32, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),

@@ -1345,7 +1345,8 @@ SWB200_API size_t swb200_packed_bytes(const swb200_model* m) {
   return pack_layout(m).total;
 }
 
-SWB200_API int swb200_pack_weights(swb200_model* m, const swb200_ref_params* r, void* packed, size_t packed_bytes, void* stream_) {
+static int pack_weights_impl(swb200_model* m, const swb200_ref_params* r, void* packed, size_t packed_bytes, void* stream_,
+                             bool layer_matrices) {
   int rc = validate(m);
   if (rc) return rc;
   SWB_REQUIRE(r && packed, "pack_weights: NULL argument");
@@ -1392,6 +1393,7 @@ SWB200_API int swb200_pack_weights(swb200_model* m, const swb200_ref_params* r, 
     }
     SWB_REQUIRE(r->scale[l] && r->to_qkv[l] && r->wo[l] && r->w1[l] && r->w2[l], "pack_weights: NULL weight in layer %d", l);
     if ((rc = launch_pack_qscale(r->scale[l], f32p(p.qscale) + static_cast<size_t>(l) * H, H, st))) return rc;
+    if (!layer_matrices) continue;               // the training model keeps its own (reference-order) copies of these four
     if ((rc = launch_pack_rows(r->to_qkv[l], base + p.w_qkv + static_cast<size_t>(l) * 3 * D * D * 2, 3 * D, D, D, 0, 1, H, kHeadDim, F16, st)))
       return rc;
     if ((rc = launch_pack_rows(r->wo[l], base + p.w_o + static_cast<size_t>(l) * D * D * 2, D, D, D, 0, 0, 0, 0, F16, st))) return rc;
@@ -1420,6 +1422,89 @@ SWB200_API int swb200_pack_weights(swb200_model* m, const swb200_ref_params* r, 
   m->w_1 = base + p.w_1;
   m->w_2 = base + p.w_2;
   m->w_head = base + p.w_head;
+  return SWB_OK;
+}
+
+SWB200_API int swb200_pack_weights(swb200_model* m, const swb200_ref_params* r, void* packed, size_t packed_bytes, void* stream) {
+  return pack_weights_impl(m, r, packed, packed_bytes, stream, true);
+}
+
+// ---- checkpoint packing for the training path: the base model (bf16) + plain / transposed bf16 copies
+namespace {
+struct TrainPackLayout {
+  size_t base, w_qkv, w_o, w_1, w_2, wt_qkv, wt_o, wt_1, wt_2, wt_head, total;
+  int kp_head;
+};
+TrainPackLayout train_pack_layout(const swb200_model* m) {
+  const Geom g = geom(m);
+  const size_t D = m->dim, L = m->depth, Dff = m->dff;
+  TrainPackLayout p;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  p.kp_head = (m->out_channels * g.pp + 7) / 8 * 8;
+  p.base = take(pack_layout(m).total);
+  p.w_qkv = take(L * 3 * D * D * 2);
+  p.w_o = take(L * D * D * 2);
+  p.w_1 = take(L * 2 * Dff * D * 2);
+  p.w_2 = take(L * D * Dff * 2);
+  p.wt_qkv = take(L * D * 3 * D * 2);
+  p.wt_o = take(L * D * D * 2);
+  p.wt_1 = take(L * D * 2 * Dff * 2);
+  p.wt_2 = take(L * Dff * D * 2);
+  p.wt_head = take(D * static_cast<size_t>(p.kp_head) * 2);
+  p.total = off;
+  return p;
+}
+}  // namespace
+
+SWB200_API size_t swb200_train_packed_bytes(const swb200_train_model* tm) {
+  if (tm == nullptr || validate(&tm->base) != SWB_OK) return 0;
+  return train_pack_layout(&tm->base).total;
+}
+
+SWB200_API int swb200_pack_train_weights(swb200_train_model* tm, const swb200_ref_params* r, void* packed, size_t packed_bytes,
+                                         void* stream_) {
+  SWB_REQUIRE(tm && r && packed, "pack_train_weights: NULL argument");
+  swb200_model* m = &tm->base;
+  int rc = validate(m);
+  if (rc) return rc;
+  SWB_REQUIRE(m->act_fp16 == 0 && m->split_embed == 1 && m->split_head == 1,
+              "pack_train_weights: the training path uses bf16 operands with split embed / head operands");
+  const TrainPackLayout p = train_pack_layout(m);
+  SWB_REQUIRE(packed_bytes >= p.total && (reinterpret_cast<uintptr_t>(packed) & 255) == 0,
+              "pack_train_weights: buffer too small (%zu < %zu) or not 256-byte aligned", packed_bytes, p.total);
+  uint8_t* base = static_cast<uint8_t*>(packed);
+  if ((rc = pack_weights_impl(m, r, base + p.base, pack_layout(m).total, stream_, false))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const Geom g = geom(m);
+  const int D = m->dim, L = m->depth, Dff = m->dff, Nh = m->out_channels * g.pp;
+  for (int l = 0; l < L; ++l) {
+    const size_t ls = static_cast<size_t>(l);
+    if ((rc = launch_pack_rows(r->to_qkv[l], base + p.w_qkv + ls * 3 * D * D * 2, 3 * D, D, D, 0, 0, 0, 0, 0, st))) return rc;
+    if ((rc = launch_pack_rows(r->wo[l], base + p.w_o + ls * D * D * 2, D, D, D, 0, 0, 0, 0, 0, st))) return rc;
+    if ((rc = launch_pack_rows(r->w1[l], base + p.w_1 + ls * 2 * Dff * D * 2, 2 * Dff, D, D, 0, 0, 0, 0, 0, st))) return rc;
+    if ((rc = launch_pack_rows(r->w2[l], base + p.w_2 + ls * D * Dff * 2, D, Dff, Dff, 0, 0, 0, 0, 0, st))) return rc;
+    if ((rc = launch_pack_transposed(r->to_qkv[l], base + p.wt_qkv + ls * D * 3 * D * 2, 3 * D, D, 3 * D, 0, st))) return rc;
+    if ((rc = launch_pack_transposed(r->wo[l], base + p.wt_o + ls * D * D * 2, D, D, D, 0, st))) return rc;
+    if ((rc = launch_pack_transposed(r->w1[l], base + p.wt_1 + ls * D * 2 * Dff * 2, 2 * Dff, D, 2 * Dff, 0, st))) return rc;
+    if ((rc = launch_pack_transposed(r->w2[l], base + p.wt_2 + ls * Dff * D * 2, D, Dff, D, 0, st))) return rc;
+  }
+  SWB_CHECK_CUDA(cudaMemsetAsync(base + p.wt_head, 0, static_cast<size_t>(D) * p.kp_head * 2, st));
+  if ((rc = launch_pack_transposed(r->head_w, base + p.wt_head, Nh, D, p.kp_head, 0, st))) return rc;
+  tm->w_qkv = base + p.w_qkv;
+  tm->w_o = base + p.w_o;
+  tm->w_1 = base + p.w_1;
+  tm->w_2 = base + p.w_2;
+  tm->wt_qkv = base + p.wt_qkv;
+  tm->wt_o = base + p.wt_o;
+  tm->wt_1 = base + p.wt_1;
+  tm->wt_2 = base + p.wt_2;
+  tm->wt_head = base + p.wt_head;
+  tm->kp_head = p.kp_head;
   return SWB_OK;
 }
 

@@ -110,6 +110,7 @@ int launch_attention_bwd(const void* qkv, const void* O, const void* dO, const f
 // checkpoint packing (pack.cu); mode 0 plain, 1 qkv row order (a = heads, b = head dim), 2 w1 tile interleave (a = half, b = dff)
 int launch_pack_rows(const float* src, void* dst, int rows, int K, int ldd, int dup, int mode, int a, int b, int f16,
                      cudaStream_t st);
+int launch_pack_transposed(const float* src, void* dst, int N, int K, int ldd, int f16, cudaStream_t st);
 int launch_pack_embed(const float* src, void* dst, int D, int C, int pp, int k_embed, int split, int f16, cudaStream_t st);
 int launch_pack_pos(const float* pos, const float* bias, float* out, long long n, int D, cudaStream_t st);
 int launch_pack_qscale(const float* scale, float* out, int heads, cudaStream_t st);

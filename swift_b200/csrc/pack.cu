@@ -73,8 +73,34 @@ __global__ void pack_qscale_kernel(const float* __restrict__ scale, float* __res
   if (i < heads) out[i] = expf(fminf(scale[i], 4.605170185988092f));       // exp(clamp(scale, max=ln 100)), swinv2.py:125-126
 }
 
+// dst[k, n] = cvt(src[n, k]) (src fp32 [N, K] row-major, dst 16-bit [K, ldd]): the transposed copies the dgrad GEMMs read
+__global__ void __launch_bounds__(256) pack_transposed_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int N, int K,
+                                                              int ldd, int f16) {
+  __shared__ float tile[32][33];
+  const int n0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + ty + 8 * i, k = k0 + tx;
+    tile[ty + 8 * i][tx] = (n < N && k < K) ? __ldg(src + static_cast<size_t>(n) * K + k) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = k0 + ty + 8 * i, n = n0 + tx;
+    if (k < K && n < N) dst[static_cast<size_t>(k) * ldd + n] = cvt16(tile[tx][ty + 8 * i], f16);
+  }
+}
+
 inline unsigned nblk(long long n) { return static_cast<unsigned>((n + 255) / 256); }
 }  // namespace
+
+int launch_pack_transposed(const float* src, void* dst, int N, int K, int ldd, int f16, cudaStream_t st) {
+  dim3 grid((K + 31) / 32, (N + 31) / 32);
+  pack_transposed_kernel<<<grid, 256, 0, st>>>(src, static_cast<uint16_t*>(dst), N, K, ldd, f16);
+  SWB_CHECK_CUDA(cudaGetLastError());
+  return SWB_OK;
+}
 
 int launch_pack_rows(const float* src, void* dst, int rows, int K, int ldd, int dup, int mode, int a, int b, int f16,
                      cudaStream_t st) {

@@ -168,67 +168,30 @@ def pack(sd: Dict[str, torch.Tensor], g: Geometry, device: torch.device, split_e
 def pack_train(sd: Dict[str, torch.Tensor], g: Geometry, device: torch.device, gemm_tile: int = 3, attn_impl: int = 0):
     """``struct swb200_train_model`` for the grad-enabled forward / backward (include/swift_b200.h): bf16 operands; the
     four per-layer matrices as plain bf16 copies in the REFERENCE's row order plus their transposes (dgrad operands);
-    embed / head packs and the fp32 conditioning parameters as in ``pack``.  Returns (struct, tensors to keep alive)."""
+    embed / head packs and the fp32 conditioning parameters as in ``pack``.  The conversions are
+    ``swb200_pack_train_weights`` (csrc/pack.cu).  Returns (struct, tensors to keep alive)."""
+    import ctypes as C
     check_supported(g)
-    bf = torch.bfloat16
-    D, H, L, Dff, pp = g.dim, g.heads, g.depth, g.dff, g.pp
-    f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
-    keep: Dict[str, torch.Tensor] = {}
-    w = f32(sd["patch_embed.emb.weight"]).reshape(D, pp, g.in_channels).permute(0, 2, 1).reshape(D, g.in_channels * pp)
-    w = torch.nn.functional.pad(w, (0, g.k_embed - g.in_channels * pp))
-    keep["w_embed"] = torch.cat([w, w], dim=1).to(bf).contiguous()
-    keep["pos_embed"] = (f32(sd["pos_embed"]).reshape(g.tokens, D) + f32(sd["patch_embed.emb.bias"])[None, :]).contiguous()
-    if g.aux_dim and "auxiliary_embed.weight" in sd:
-        keep["aux_w"] = f32(sd["auxiliary_embed.weight"])
-        keep["aux_b"] = f32(sd["auxiliary_embed.bias"])
-    for n in ("l1", "l2"):
-        keep[f"{n}_w"] = f32(sd[f"latent_embed.{n}.weight"])
-        keep[f"{n}_b"] = f32(sd[f"latent_embed.{n}.bias"])
-    names = {"mod_w": [], "mod_b": [], "ln_gamma": [], "ln_beta": [], "qscale": [], "t_qkv": [], "t_o": [], "t_1": [], "t_2": []}
-    for l in range(L):
-        a, f = f"transformer.layers.{l}.0", f"transformer.layers.{l}.1"
-        for blk in (a, f):
-            names["mod_w"].append(f32(sd[blk + ".norm.modulation.weight"]))
-            names["mod_b"].append(f32(sd[blk + ".norm.modulation.bias"]))
-            names["ln_gamma"].append(f32(sd[blk + ".norm.norm.weight"]))
-            names["ln_beta"].append(f32(sd[blk + ".norm.norm.bias"]))
-        names["qscale"].append(torch.clamp(f32(sd[a + ".scale"]).reshape(H), max=math.log(1.0 / 0.01)).exp())
-        names["t_qkv"].append(f32(sd[a + ".to_qkv.weight"]).to(bf))
-        names["t_o"].append(f32(sd[a + ".wo.weight"]).to(bf))
-        names["t_1"].append(f32(sd[f + ".w1.weight"]).to(bf))
-        names["t_2"].append(f32(sd[f + ".w2.weight"]).to(bf))
-    keep["mod_w"] = torch.cat(names["mod_w"], 0).contiguous()
-    keep["mod_b"] = torch.cat(names["mod_b"], 0).contiguous()
-    for n in ("ln_gamma", "ln_beta", "qscale"):
-        keep[n] = torch.stack(names[n], 0).contiguous()
-    for n in ("qkv", "o", "1", "2"):
-        keep["t_" + n] = torch.stack(names["t_" + n], 0).contiguous()                       # [L, N, K]
-        keep["tt_" + n] = keep["t_" + n].transpose(1, 2).contiguous()                       # [L, K, N]
-    wh = f32(sd["head.head.0.weight"])
-    nh = g.out_channels * pp
-    kp = (nh + 7) // 8 * 8
-    keep["w_head"] = torch.cat([wh, wh], dim=1).to(bf).contiguous()
-    keep["tt_head"] = torch.nn.functional.pad(wh.t(), (0, kp - nh)).to(bf).contiguous()    # [D, kp]
-
+    ref, keep_src, has_aux = ref_params(dict(sd), g, device)
     tm = _lib.TrainModel()
     m = tm.base
     m.img_h, m.img_w = g.img
     m.patch_h, m.patch_w = g.patch
     m.win_h, m.win_w = g.window
     m.shift_h, m.shift_w = g.shift
-    m.in_channels, m.out_channels, m.depth, m.dim, m.heads = g.in_channels, g.out_channels, L, D, H
-    m.dff, m.aux_dim, m.k_embed = Dff, (g.aux_dim if "aux_w" in keep else 0), g.k_embed
+    m.in_channels, m.out_channels, m.depth, m.dim, m.heads = g.in_channels, g.out_channels, g.depth, g.dim, g.heads
+    m.dff, m.aux_dim, m.k_embed = g.dff, (g.aux_dim if has_aux else 0), g.k_embed
     m.split_embed, m.split_head = 1, 1
     m.act_fp16, m.attn_fp16, m.fuse_ln = 0, 0, 0
     m.gemm_tile = int(gemm_tile)
     m.attn_impl = int(attn_impl)
     m.timestep_weight = float(g.timestep_weight)
-    for name in ("w_embed", "pos_embed", "aux_w", "aux_b", "l1_w", "l1_b", "l2_w", "l2_b", "mod_w", "mod_b", "ln_gamma",
-                 "ln_beta", "qscale", "w_head"):
-        setattr(m, name, keep[name].data_ptr() if name in keep else None)
-    for n in ("qkv", "o", "1", "2"):
-        setattr(tm, "w_" + n, keep["t_" + n].data_ptr())
-        setattr(tm, "wt_" + n, keep["tt_" + n].data_ptr())
-    tm.wt_head = keep["tt_head"].data_ptr()
-    tm.kp_head = kp
-    return tm, keep
+    lib = _lib.lib()
+    nbytes = lib.swb200_train_packed_bytes(C.byref(tm))
+    if nbytes == 0:
+        _lib.check(lib.swb200_validate(C.byref(m)), "train_packed_bytes")
+    buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+    base = (buf.data_ptr() + 255) // 256 * 256
+    _lib.check(lib.swb200_pack_train_weights(C.byref(tm), C.byref(ref), base, nbytes,
+                                             torch.cuda.current_stream(device).cuda_stream), "pack_train_weights")
+    return tm, {"packed": buf, "_sources": keep_src}
