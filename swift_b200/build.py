@@ -19,8 +19,11 @@ LIB = os.path.join(HERE, "libswift_b200.so")
 SOURCES = ["gemm.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "attention_bwd.cu", "attention_bwd_tc.cu", "attention_dual_tc.cu", "rollout.cu", "ensemble.cu", "tangent.cu", "scm_target.cu", "train.cu", "muon.cu", "pack.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
-NVCC_FLAGS += os.environ.get("SWB_NVCC_DEFINES", "").split()      # e.g. "-DSWB_A_TMEM=1" for A/B builds of one kernel choice
+_EXTRA = os.environ.get("SWB_NVCC_DEFINES", "").split()           # e.g. "-DSWB_A_TMEM=1" for A/B builds of one kernel choice
+NVCC_FLAGS += _EXTRA
 LIB = os.environ.get("SWB_LIB_OUT", LIB)
+if _EXTRA:                                                         # A/B builds keep their own object directory
+    BUILD = os.path.join(CSRC, "build_" + hashlib.sha256(" ".join(_EXTRA).encode()).hexdigest()[:8])
 
 
 def _nvcc() -> str:

@@ -85,11 +85,23 @@ int make_tmap_16bit_2d(CUtensorMap* out, const void* ptr, bool is_f16, uint64_t 
   return make_tmap_16bit_2d_swz(out, ptr, is_f16, rows, cols, pitch_elems, box_rows, box_cols, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+#ifdef SWB_PROFILE_EPILOGUES
+__device__ unsigned long long g_gemm_prof[16];
+extern "C" __attribute__((visibility("default"))) int swb200_debug_gemm_prof(unsigned long long* out16, int reset) {
+  if (out16 && cudaMemcpyFromSymbol(out16, g_gemm_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return 1;
+  if (reset) {
+    unsigned long long z[16] = {};
+    if (cudaMemcpyToSymbol(g_gemm_prof, z, sizeof(z)) != cudaSuccess) return 1;
+  }
+  return 0;
+}
+#endif
+
 // ----------------------------------------------------------------------------- launch
 template <int NSUB, int CG, int EPI, bool F16>
 static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to0, const CUtensorMap& to1,
                        const GemmParams& p, cudaStream_t stream) {
-  using S = GemmCfg<NSUB, CG>;
+  using S = GemmCfg<NSUB, CG, EPI == EPI_LN_RES>;
   auto kern = gemm_tcgen05_kernel<NSUB, CG, EPI, F16>;
   static PerDevice<bool> attr_done;
   if (!attr_done.get()) {
@@ -101,6 +113,10 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   const int num_tiles = tiles_m * tiles_n * (p.splits > 1 ? p.splits : 1) * (p.batch > 1 ? p.batch : 1);
   int clusters = num_sms() / CG;
   if (clusters > num_tiles) clusters = num_tiles;
+#ifdef SWB_PROFILE_EPILOGUES
+  static const int max_cl = getenv("SWB_GEMM_MAX_CLUSTERS") ? atoi(getenv("SWB_GEMM_MAX_CLUSTERS")) : 0;   // part of the chip only
+  if (max_cl > 0 && clusters > max_cl) clusters = max_cl;
+#endif
   if constexpr (EPI == EPI_LN_RES) {
     // the groups that exchange LayerNorm statistics (the tiles_n column tiles of one row block) must run at the same
     // time: keep the cluster count a multiple of tiles_n so that they sit on neighbouring clusters in every wave
@@ -190,6 +206,16 @@ int launch_gemm(int epi, int tile, int act_f16, const void* A, int lda, const vo
               "gemm: split-K needs the fp32 store epilogue and K %% 64 == 0 (epi=%d K=%d splits=%d)", epi, p.K, p.splits);
   SWB_REQUIRE(p.batch <= 1 || epi == EPI_STORE_F32, "gemm: batched problems need the fp32 store epilogue (epi=%d)", epi);
   SWB_REQUIRE(tile >= 1 && tile <= 3, "gemm: tile config must be 1 (128x176), 2 (256x176) or 3 (256x352), got %d", tile);
+  // sub-tile 0 of the 256x352 tile runs two k-blocks ahead of sub-tile 1 (gemm_sm100.cuh); SWB_GEMM_SKEW: A/B knob (tools only)
+  static const int skew_env = getenv("SWB_GEMM_SKEW") ? atoi(getenv("SWB_GEMM_SKEW")) : 2;
+  p.skew = skew_env;
+#ifdef SWB_PROFILE_EPILOGUES
+  SWB_CHECK_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&p.prof), g_gemm_prof));
+  static const bool nomma = getenv("SWB_GEMM_NOMMA") != nullptr;       // TMA feed rate alone (see gemm_sm100.cuh)
+  if (nomma) p.ln_debug |= 4;
+  static const bool noload = getenv("SWB_GEMM_NOLOAD") != nullptr;     // no TMA loads either: the epilogue alone
+  if (noload) p.ln_debug |= 8;
+#endif
   const int cg = tile == 1 ? 1 : 2;
   const int nsub = tile == 3 ? 2 : 1;
   const bool f16 = act_f16 != 0;

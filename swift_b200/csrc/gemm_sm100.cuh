@@ -91,6 +91,11 @@ struct GemmParams {
   int ln_stride;
   float ln_eps;
   int ln_debug;            // profiling only (SWB_LN_DEBUG): bit 0 = do not wait for the other groups, bit 1 = skip the x update
+  // 256x352 tile only: sub-tile 0 runs `skew` k-blocks ahead of sub-tile 1 at both ends of a tile, so its accumulator is
+  // published (and drained, and handed back) while the tensor pipe still works on sub-tile 1 -- the hand-over latency of
+  // the single accumulator set hides behind the other sub-tile's MMAs.  0 = both sub-tiles in lock step.
+  int skew;
+  unsigned long long* prof;   // cycle counters of a -DSWB_PROFILE_EPILOGUES build (null otherwise)
 };
 
 constexpr int kBlockM = 128;     // rows of A per CTA
@@ -103,7 +108,13 @@ constexpr int kTmemCols = 512;
 constexpr int kHeadDim = 88;     // Swift-B head dim
 constexpr int kHeadDimPad = 96;  // q/k/v rows are stored padded to 96 (K of QK^T must be a multiple of 16)
 
-template <int NSUB, int CG>
+#ifndef SWB_GEMM_MAX_STAGES
+#define SWB_GEMM_MAX_STAGES 8
+#endif
+
+// LNSTATS: the fused-LayerNorm epilogue keeps 32 x (rstd, shift) per epilogue warp in shared memory; without it the
+// 256x352 tile has room for a fifth pipeline stage.
+template <int NSUB, int CG, bool LNSTATS = false>
 struct GemmCfg {
   static_assert(NSUB == 1 || (NSUB == 2 && CG == 2), "the 352-wide tile needs the CTA pair");
   static constexpr int kTileN = kUmmaN * NSUB;
@@ -113,11 +124,11 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kEpiWarps = 4 * NSUB;
   static constexpr int kThreads = 128 + 32 * kEpiWarps;
-  static constexpr int kScratchBytes = kEpiWarps * (4096 + 256);   // per-warp 32 x 128 B transpose buffer + 32 x (rstd, shift)
+  static constexpr int kScratchBytes = kEpiWarps * (4096 + (LNSTATS ? 256 : 0));   // per-warp 32 x 128 B transpose buffer (+ 32 x (rstd, shift))
   static constexpr int kBarBytes = 1024;
   static constexpr int kMaxSmem = 227 * 1024;
   static constexpr int kStagesRaw = (kMaxSmem - kScratchBytes - kBarBytes - 1024) / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kStages = kStagesRaw > SWB_GEMM_MAX_STAGES ? SWB_GEMM_MAX_STAGES : kStagesRaw;
   static constexpr int kTotal = kStages * kStageBytes + kScratchBytes + kBarBytes + 1024;  // +1024 alignment slack
   static_assert(kBBytes % 1024 == 0 && (kUmmaN / CG) * 128 % 1024 == 0, "SWIZZLE_128B tiles need 1024-byte alignment");
   static_assert(kStages >= 3, "pipeline too shallow");
@@ -223,8 +234,19 @@ __device__ __forceinline__ void pack_row16(const float* v, uint32_t* w) {   // 2
   for (int i = 0; i < NW; ++i) w[i] = pack_act2<F16>(v[2 * i], v[2 * i + 1]);
 }
 
+#ifdef SWB_PROFILE_EPILOGUES
+// cycle counters of a profiling build (tools/gemm_roles.py): [0] issuer total, [1] issuer waiting for TMA data, [2] issuer
+// waiting for a free accumulator, [3] tiles (issuer), [4] producer waiting for a free stage, [5] epilogue warps waiting for
+// an accumulator, [6] accumulator published -> handed back, [7] handed back -> end of the tile's epilogue, [8] warp-tiles,
+// [9] of [7]: waiting for an earlier TMA store to release the scratch buffer, [10] producer total
+#define SWB_PROF(x) x
+#else
+#define SWB_PROF(x)
+#endif
+
 // Per-warp epilogue context
 struct EpiCtx {
+  SWB_PROF(long long store_wait;)
   int row0;          // first row of this warp's 32-row block
   int rows_valid;    // rows of it inside M
   int lane;
@@ -239,8 +261,10 @@ struct EpiCtx {
 // elected lane issues the store: no LDS, no STG, full-line writes generated by the copy engine.
 __device__ __forceinline__ void epi_scratch_acquire(EpiCtx& e) {
   if (e.pending) {
+    SWB_PROF(const long long t0 = clock64();)
     if (e.lane == 0) bulk_wait_read_all();
     __syncwarp();
+    SWB_PROF(e.store_wait += clock64() - t0;)
     e.pending = false;
   }
 }
@@ -1057,7 +1081,7 @@ __global__ void __launch_bounds__(GemmCfg<NSUB, CG>::kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_o0, const __grid_constant__ CUtensorMap tmap_o1,
                     const GemmParams p) {
-  using S = GemmCfg<NSUB, CG>;
+  using S = GemmCfg<NSUB, CG, EPI == EPI_LN_RES>;
   constexpr int kStages = S::kStages;
   constexpr int BN = kUmmaN;
   constexpr int kTileN = S::kTileN;
@@ -1101,7 +1125,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
+#ifdef SWB_PROFILE_EPILOGUES
+      mbar_init(full_bar(s), (CG == 2 && (p.ln_debug & 8)) ? 2 : 1);
+#else
       mbar_init(full_bar(s), 1);
+#endif
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -1130,6 +1158,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const uint32_t full_leader0 = (CG == 2) ? mapa_u32(full_bar(0), 0) : full_bar(0);
     int stage = 0;
     uint32_t phase = 0;
+    SWB_PROF(long long pw = 0; const long long pt0 = clock64();)
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int bs = tile / tiles_mn, tmn = tile - bs * tiles_mn;
       const int bidx = bs / nsplit, split = bs - bidx * nsplit;
@@ -1138,7 +1167,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int col0 = bidx * p.N + tn * kTileN + static_cast<int>(cta_rank) * S::kBRows;
       const int k0 = split * p.K;
       for (int kb = 0; kb < num_kb; ++kb) {
+        SWB_PROF(const long long tw = clock64();)
         mbar_wait(empty_bar(stage), phase ^ 1u, 1);
+        SWB_PROF(pw += clock64() - tw;)
+#ifdef SWB_PROFILE_EPILOGUES
+        if (p.ln_debug & 8) {       // profiling: nothing is loaded -- with bit 2 the epilogue runs alone
+          if (cta_rank == 0) mbar_arrive_expect_tx_elect(full_bar(stage), 0);
+          else if (lane == 0) mbar_arrive_cluster(full_leader0 + 8u * stage);     // (keeps the two producers in step)
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          continue;
+        }
+#endif
         if (cta_rank == 0) mbar_arrive_expect_tx_elect(full_bar(stage), S::kStageBytes * CG);
         const uint32_t a_dst = smem_a + stage * S::kABytes;
         const uint32_t b_dst = smem_b + stage * S::kBBytes;
@@ -1153,6 +1193,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
     }
+    SWB_PROF(if (lane == 0) { atomicAdd(&p.prof[4], (unsigned long long)pw); atomicAdd(&p.prof[10], (unsigned long long)(clock64() - pt0)); })
   } else if (warp == 1) {
     // ===================================== UMMA issuer (leader CTA; whole warp converged) =======================
     if (cta_rank == 0) {
@@ -1164,19 +1205,75 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      // skew: at most kStages - 2 k-blocks (the stages of a tile end are held while sub-tile 1 catches up) and num_kb / 2
+#ifdef SWB_PROFILE_EPILOGUES
+      const bool nomma = (p.ln_debug & 4) != 0;     // profiling: no MMA is issued -- the rate at which TMA alone can feed the tiles
+#else
+      constexpr bool nomma = false;
+#endif
+      SWB_PROF(long long iw_full = 0; long long iw_acc = 0; const long long it0 = clock64();)
+      int skew = (NSUB == 2) ? p.skew : 0;
+      skew = skew > kStages - 2 ? kStages - 2 : skew;
+      skew = skew > num_kb / 2 ? num_kb / 2 : skew;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
         const uint32_t par = static_cast<uint32_t>(it) & 1u;
         uint32_t tmem_d;
         if constexpr (NSUB == 1) {
           // double-buffered accumulator: stage it&1, re-used every second tile
+          SWB_PROF(const long long tw_ = clock64();)
           mbar_wait(tempty_bar(par), ((static_cast<uint32_t>(it) >> 1) & 1u) ^ 1u, 2);
+          SWB_PROF(iw_acc += clock64() - tw_;)
           tcgen05_fence_after();
           tmem_d = tmem_base + par * kSubStride;
         } else {
           tmem_d = tmem_base;
         }
-        for (int kb = 0; kb < num_kb; ++kb) {
+        int kb_begin = 0, kb_end = num_kb;
+#if !SWB_A_TMEM
+        if constexpr (NSUB == 2) {
+          if (skew > 0) {
+            // ---- head of a skewed tile: sub-tile 0 alone over the first `skew` k-blocks (its accumulator was published
+            // `skew` k-blocks before the end of the previous tile, so it has been drained by now), then sub-tile 1 over the
+            // same stages, which it releases
+            int s = stage;
+            uint32_t ph = phase;
+            SWB_PROF(const long long tw_ = clock64();)
+            mbar_wait(tempty_bar(0), par ^ 1u, 2);
+            SWB_PROF(iw_acc += clock64() - tw_;)
+            tcgen05_fence_after();
+            for (int kb = 0; kb < skew; ++kb) {
+              SWB_PROF(const long long tf_ = clock64();)
+              mbar_wait(full_bar(s), ph, 3);
+              SWB_PROF(iw_full += clock64() - tf_;)
+              tcgen05_fence_after();
+              const uint64_t ad = desc_hi | static_cast<uint64_t>(((smem_a + s * S::kABytes) & 0x3FFFFu) >> 4);
+              const uint64_t bd = desc_hi | static_cast<uint64_t>(((smem_b + s * S::kBBytes) & 0x3FFFFu) >> 4);
+#pragma unroll
+              for (int k = 0; k < kKSteps; ++k) umma_f16_ss_elect<CG>(tmem_d, ad + 2u * k, bd + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (++s == kStages) { s = 0; ph ^= 1u; }
+            }
+            SWB_PROF(const long long tw2_ = clock64();)
+            mbar_wait(tempty_bar(1), par ^ 1u, 2);
+            SWB_PROF(iw_acc += clock64() - tw2_;)
+            tcgen05_fence_after();
+            for (int kb = 0; kb < skew; ++kb) {
+              const uint64_t ad = desc_hi | static_cast<uint64_t>(((smem_a + stage * S::kABytes) & 0x3FFFFu) >> 4);
+              const uint64_t bd = desc_hi | static_cast<uint64_t>(((smem_b + stage * S::kBBytes) & 0x3FFFFu) >> 4);
+#pragma unroll
+              for (int k = 0; k < kKSteps; ++k)
+                umma_f16_ss_elect<CG>(tmem_d + kSubStride, ad + 2u * k, bd + kSubDescStep + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_commit_elect<CG>(empty_bar(stage));
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+            kb_begin = skew;
+            kb_end = num_kb - skew;
+          }
+        }
+#endif
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          SWB_PROF(const long long tf_ = clock64();)
           mbar_wait(full_bar(stage), phase, 3);             // TMA bytes of this stage have landed (both CTAs)
+          SWB_PROF(iw_full += clock64() - tf_;)
           tcgen05_fence_after();
           const uint64_t adesc0 = desc_hi | static_cast<uint64_t>(((smem_a + stage * S::kABytes) & 0x3FFFFu) >> 4);
           const uint64_t bdesc0 = desc_hi | static_cast<uint64_t>(((smem_b + stage * S::kBBytes) & 0x3FFFFu) >> 4);
@@ -1208,6 +1305,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             };
 #else
             auto mma = [&](int j, int k, uint32_t acc) {
+              if (nomma) return;
               umma_f16_ss_elect<CG>(tmem_d + j * kSubStride, adesc0 + 2u * k, bdesc0 + j * kSubDescStep + 2u * k, idesc, acc);
             };
 #endif
@@ -1216,7 +1314,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               // of the previous tile has drained it, so start on sub 0 while sub 1 may still be read
 #pragma unroll 1
               for (int j = 0; j < NSUB; ++j) {
+                SWB_PROF(const long long tw_ = clock64();)
                 mbar_wait(tempty_bar(j), par ^ 1u, 2);
+                SWB_PROF(iw_acc += clock64() - tw_;)
                 tcgen05_fence_after();
                 for (int k = 0; k < nk; ++k) mma(j, k, k != 0 ? 1u : 0u);
               }
@@ -1229,7 +1329,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               }
 #else
               // steady state: the 8 UMMAs of the k-block behind one elect (issue slots are contended, see ptx.cuh)
-              umma_f16_kblock_pair_elect(tmem_d, tmem_d + kSubStride, static_cast<uint32_t>(adesc0), static_cast<uint32_t>(bdesc0),
+              if (!nomma) umma_f16_kblock_pair_elect(tmem_d, tmem_d + kSubStride, static_cast<uint32_t>(adesc0), static_cast<uint32_t>(bdesc0),
                                          kSubDescStep, static_cast<uint32_t>(desc_hi >> 32), idesc);
 #endif
             } else {
@@ -1240,8 +1340,47 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           umma_commit_elect<CG>(empty_bar(stage));          // smem stage reusable once these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
+#if !SWB_A_TMEM
+        if constexpr (NSUB == 2) {
+          if (skew > 0) {
+            // ---- tail of a skewed tile: sub-tile 0 finishes first and is published while sub-tile 1 still runs
+            int s = stage;
+            uint32_t ph = phase;
+            for (int kb = num_kb - skew; kb < num_kb; ++kb) {
+              SWB_PROF(const long long tf_ = clock64();)
+              mbar_wait(full_bar(s), ph, 3);
+              SWB_PROF(iw_full += clock64() - tf_;)
+              tcgen05_fence_after();
+              const uint64_t ad = desc_hi | static_cast<uint64_t>(((smem_a + s * S::kABytes) & 0x3FFFFu) >> 4);
+              const uint64_t bd = desc_hi | static_cast<uint64_t>(((smem_b + s * S::kBBytes) & 0x3FFFFu) >> 4);
+              const int nk = (kb == num_kb - 1) ? tail_ksteps : kKSteps;
+              for (int k = 0; k < nk; ++k) umma_f16_ss_elect<CG>(tmem_d, ad + 2u * k, bd + 2u * k, idesc, 1u);
+              if (++s == kStages) { s = 0; ph ^= 1u; }
+            }
+            umma_commit_elect<CG>(tfull_bar(0));
+            for (int kb = num_kb - skew; kb < num_kb; ++kb) {
+              const uint64_t ad = desc_hi | static_cast<uint64_t>(((smem_a + stage * S::kABytes) & 0x3FFFFu) >> 4);
+              const uint64_t bd = desc_hi | static_cast<uint64_t>(((smem_b + stage * S::kBBytes) & 0x3FFFFu) >> 4);
+              const int nk = (kb == num_kb - 1) ? tail_ksteps : kKSteps;
+              for (int k = 0; k < nk; ++k)
+                umma_f16_ss_elect<CG>(tmem_d + kSubStride, ad + 2u * k, bd + kSubDescStep + 2u * k, idesc, 1u);
+              umma_commit_elect<CG>(empty_bar(stage));
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+            umma_commit_elect<CG>(tfull_bar(1));
+            continue;
+          }
+        }
+#endif
         umma_commit_elect<CG>(tfull_bar(NSUB == 1 ? par : 0));   // accumulator(s) complete -> epilogue (both CTAs)
+        if constexpr (NSUB == 2) umma_commit_elect<CG>(tfull_bar(1));     // (every epilogue group waits on its own barrier)
       }
+      SWB_PROF(if (lane == 0) {
+        atomicAdd(&p.prof[0], (unsigned long long)(clock64() - it0));
+        atomicAdd(&p.prof[1], (unsigned long long)iw_full);
+        atomicAdd(&p.prof[2], (unsigned long long)iw_acc);
+        atomicAdd(&p.prof[3], (unsigned long long)it);
+      })
     }
   }
   } else {
@@ -1258,6 +1397,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     e.to0 = &tmap_o0;
     e.to1 = &tmap_o1;
     e.pending = false;
+    SWB_PROF(e.store_wait = 0; long long ew_full = 0; long long ew_drain = 0; long long ew_rest = 0; long long t_rel = 0;)
     const uint32_t stat_smem = scratch0 + S::kEpiWarps * 4096 + (warp - 4) * 256;
     int it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
@@ -1276,7 +1416,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         mbar_wait(tfull_bar(par), (static_cast<uint32_t>(it) >> 1) & 1u, 4);
         tacc = tmem_base + par * kSubStride;
       } else {
-        mbar_wait(tfull_bar(0), par, 4);
+        SWB_PROF(const long long tw_ = clock64();)
+        mbar_wait(tfull_bar(grp), par, 4);
+        SWB_PROF(t_rel = clock64(); ew_full += t_rel - tw_;)
         tacc = tmem_base + grp * kSubStride;
       }
       tcgen05_fence_after();
@@ -1299,6 +1441,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if constexpr (CG == 2) mbar_arrive_cluster(tempty_leader0 + 8u * bar_idx);
           else mbar_arrive(tempty_bar(bar_idx));
         }
+        SWB_PROF({ const long long t_ = clock64(); ew_drain += t_ - t_rel; t_rel = t_; })
       };
       const int n_lo = n_tile + s_lo * kSlot, n_hi = n_tile + s_hi * kSlot;
       if constexpr (EPI == EPI_SWIGLU) {
@@ -1365,7 +1508,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         release();
       }
+      SWB_PROF(ew_rest += clock64() - t_rel;)
     }
+    SWB_PROF(if (lane == 0) {
+      atomicAdd(&p.prof[5], (unsigned long long)ew_full);
+      atomicAdd(&p.prof[6], (unsigned long long)ew_drain);
+      atomicAdd(&p.prof[7], (unsigned long long)ew_rest);
+      atomicAdd(&p.prof[8], (unsigned long long)it);
+      atomicAdd(&p.prof[9], (unsigned long long)e.store_wait);
+    })
     epi_scratch_acquire(e);     // outstanding TMA stores have finished reading this warp's smem
   }
 

@@ -15,6 +15,9 @@ import torch
 from swift_b200 import _lib
 
 
+NSM = 2 * int(os.environ["SWB_GEMM_MAX_CLUSTERS"]) if os.environ.get("SWB_GEMM_MAX_CLUSTERS") else 148   # profiling builds only
+
+
 class Smi:
     """median SM clock / power while a block runs (nvidia-smi sampled every 100 ms)"""
 
@@ -41,12 +44,17 @@ def main():
     st = torch.cuda.current_stream().cuda_stream
     shapes = {"qkv": (3168, 1056), "wo": (1056, 1056), "w1": (5632, 1056), "w2": (1056, 2816)}
     print(f"M = {M}; tile config {tile}; fp16 operands; each variant runs back to back for ~{secs:.0f} s with nvidia-smi sampling")
+    if os.environ.get("SWB_PHASE_SHAPES"):
+        shapes = {k: v for k, v in shapes.items() if k in os.environ["SWB_PHASE_SHAPES"].split(",")}
     for name, (N, K) in shapes.items():
         A = (torch.randn(M, K, device="cuda") * 0.5).half()
         W = (torch.randn(N, K, device="cuda") * 0.05).half()
         out = torch.empty(M, N, device="cuda", dtype=torch.float16)
         res = {}
         variants = ((6, "mainloop"), (7, "+drain"), (8, "+smem"), (9, "direct"), (1, "store16"))
+        if os.environ.get("SWB_PHASE_VARIANTS"):         # e.g. "6,1": main loop and store16 only
+            keep = {int(x) for x in os.environ["SWB_PHASE_VARIANTS"].split(",")}
+            variants = tuple(v for v in variants if v[0] in keep)
         if os.environ.get("SWB_LIB_ANYABI"):
             variants = ((1, "store16"),)                 # older builds do not have the profiling epilogues
         for epi, label in variants:
@@ -62,7 +70,7 @@ def main():
                 e1.record()
                 torch.cuda.synchronize()
             res[label] = (e0.elapsed_time(e1) / reps, smi.mhz, smi.watt)
-        if name in ("qkv", "w1"):                       # the real fused epilogue of this shape
+        if name in ("qkv", "w1") and not os.environ.get("SWB_PHASE_VARIANTS"):   # the real fused epilogue of this shape
             if name == "qkv":
                 qs = torch.full((12,), 10.0, device="cuda")
                 o2 = torch.empty(3 * 12 * M * 96, device="cuda", dtype=torch.float16)
@@ -86,7 +94,7 @@ def main():
         fl = 2.0 * M * N * K
         print(f"  {name:4s} N={N:5d} K={K:5d}: " + "\n        " + "\n        ".join(
             f"{k:9s} {v[0] * 1e3:7.1f} us ({fl / v[0] / 1e9:6.0f} TF/s, {v[1]:4.0f} MHz, {v[2]:4.0f} W, "
-            f"{fl / (v[0] * 1e-3) / (148 * v[1] * 1e6):5.0f} FLOP/clk/SM)" for k, v in res.items()))
+            f"{fl / (v[0] * 1e-3) / (NSM * v[1] * 1e6):5.0f} FLOP/clk/SM)" for k, v in res.items()))
         del A, W, out
 
 
