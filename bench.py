@@ -245,6 +245,8 @@ def run_ours(args):
     net.model.max_chunk = args.chunk
     if args.fuse_ln >= 0:
         net.model.fuse_ln = args.fuse_ln
+    if args.x_single >= 0:
+        net.model.x_single = bool(args.x_single)
     eng = net.model.engine()
 
     n_ic = ICS_PER_GPU * n_gpus
@@ -855,6 +857,7 @@ def main():
     ap.add_argument("--train-batch", type=int, default=1, help="--mode train: samples per GPU and step")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end leg (0 = same as --steps)")
     ap.add_argument("--fuse-ln", type=int, default=-1, help="override SwinV2.fuse_ln (bit 0: wo, bit 1: w2; 0 = separate LN kernel)")
+    ap.add_argument("--x-single", type=int, default=-1, help="override SwinV2.x_single (1: one fp16 value per residual element, 0: [hi | lo] pair)")
     ap.add_argument("--no-stats", action="store_true", help="do not accumulate the on-device ensemble scores")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (fixed 12 x 64 workload)")
     ap.add_argument("--no-extras", action="store_true", help="skip the short TrigFlow-2S / training-step summaries")

@@ -11,7 +11,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SWB_LIB", os.path.join(HERE, "libswift_b200.so"))   # SWB_LIB: A/B builds (tools only)
 
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 # Every symbol ``include/swift_b200.h`` declares; tests check the library exports exactly these.
 EXPORTS = (
@@ -41,7 +41,7 @@ class Model(C.Structure):
         [(n, _i32) for n in ("img_h", "img_w", "patch_h", "patch_w", "win_h", "win_w", "shift_h", "shift_w",
                              "in_channels", "out_channels", "depth", "dim", "heads", "dff", "aux_dim",
                              "k_embed", "split_embed", "split_head", "gemm_tile", "attn_impl", "act_fp16",
-                             "fuse_ln", "attn_fp16")]
+                             "fuse_ln", "attn_fp16", "x_single")]
         + [("timestep_weight", _f32)]
         + [(n, _vp) for n in ("w_embed", "b_embed", "pos_embed", "aux_w", "aux_b", "l1_w", "l1_b", "l2_w", "l2_b",
                               "mod_w", "mod_b", "ln_gamma", "ln_beta", "qscale", "w_qkv", "w_o", "w_1", "w_2",

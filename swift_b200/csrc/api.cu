@@ -145,6 +145,9 @@ GemmParams base_params(int M, int N, int K) {
 }  // namespace
 
 extern "C" {
+static int gemm_head_impl(int tile, const swb200_model* m, const void* A, int lda, int K, int ldw, int B, const swb200_update* upd,
+                          float* y, void* stream);
+
 
 SWB200_API int swb200_abi_version(void) { return SWB200_ABI_VERSION; }
 SWB200_API const char* swb200_last_error(void) { return get_error(); }
@@ -208,6 +211,9 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
   // q / k / v and P in fp16 even when the GEMM operands are bf16: the attention kernel's operand format is independent of
   // the GEMMs' (its inputs come out of an epilogue, its output goes into one), and q_hat*scale <= 100, k_hat <= 1, P <= 1
   const int AF16 = (F16 || m->attn_fp16) ? 1 : 0;
+  // fp16 forecast path: the residual stream is ONE fp16 value per element (the hi half of xhl; section 2 of DESIGN.md)
+  const int XS = (F16 && m->x_single) ? 1 : 0;
+  const int FX = F16 | (XS << 1);             // format word of the kernels that touch the residual stream
   const int kDefaultCG = m->gemm_tile;          // tile config of every GEMM (the w1 packing depends on it)
   const size_t img_in0 = static_cast<size_t>(c0) * m->img_h * m->img_w;
   const size_t img_in1 = static_cast<size_t>(c1) * m->img_h * m->img_w;
@@ -239,6 +245,7 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
     auto sat_x = [&]() -> int {
       if (g_sat_counters == nullptr || !F16) return SWB_OK;
       int r = sat(SAT_X_HI, xhl, M, D, 2 * D);
+      if (XS) return r;
       return r ? r : sat(SAT_X_LO, static_cast<const uint16_t*>(xhl) + D, M, D, 2 * D);
     };
     void* lnws = ws + w.lnws;
@@ -259,7 +266,7 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
       p.pos = m->pos_embed;
       p.pos_rows = g.tokens;
       { TraceScope ts_(T_EMBED, stream);
-      rc = launch_gemm(EPI_EMBED, kDefaultCG, F16, a_emb, g.k_embed_total, m->w_embed, g.k_embed_total, p, stream); }
+      rc = launch_gemm(EPI_EMBED, kDefaultCG, FX, a_emb, g.k_embed_total, m->w_embed, g.k_embed_total, p, stream); }
       if (rc) return rc;
       if ((rc = sat_x())) return rc;
     }
@@ -290,7 +297,7 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
       if (fuse_wo) {
         // wo projection + LayerNorm + modulation + residual add in one kernel (no branch buffer)
         { TraceScope ts_(T_WO, stream);
-        rc = swb200_gemm_ln_residual(kDefaultCG, F16, attn, D, wo, D, xhl, gain_a, bias_a, M, D, g.tokens, lnws, ln_gen,
+        rc = swb200_gemm_ln_residual(kDefaultCG, FX, attn, D, wo, D, xhl, gain_a, bias_a, M, D, g.tokens, lnws, ln_gen,
                                      stream_); }
         if (rc == SWB_ERR_RESIDENCY) fuse_wo = fuse_w2 = false;
         else if (rc) return rc;
@@ -305,7 +312,7 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
         if (rc) return rc;
         if (BR16 && (rc = sat(SAT_BRANCH, branch, M, D, D))) return rc;
         { TraceScope ts_(T_LN, stream);
-        rc = launch_ln_mod_residual(branch, BR16, xhl, gain_a, bias_a, M, D, g.tokens, 1e-6f, F16, stream); }
+        rc = launch_ln_mod_residual(branch, BR16, xhl, gain_a, bias_a, M, D, g.tokens, 1e-6f, FX, stream); }
         if (rc) return rc;
       }
       if ((rc = sat_x())) return rc;
@@ -324,7 +331,7 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
       const float* bias_f = bias + (static_cast<size_t>(2 * l + 1) * B + b0) * D;
       if (fuse_w2) {
         { TraceScope ts_(T_W2, stream);
-        rc = swb200_gemm_ln_residual(kDefaultCG, F16, hbuf, Dff, w2, Dff, xhl, gain_f, bias_f, M, D, g.tokens, lnws,
+        rc = swb200_gemm_ln_residual(kDefaultCG, FX, hbuf, Dff, w2, Dff, xhl, gain_f, bias_f, M, D, g.tokens, lnws,
                                      ln_gen, stream_); }
         if (rc == SWB_ERR_RESIDENCY) fuse_wo = fuse_w2 = false;
         else if (rc) return rc;
@@ -339,7 +346,7 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
         if (rc) return rc;
         if (BR16 && (rc = sat(SAT_BRANCH, branch, M, D, D))) return rc;
         { TraceScope ts_(T_LN, stream);
-        rc = launch_ln_mod_residual(branch, BR16, xhl, gain_f, bias_f, M, D, g.tokens, 1e-6f, F16, stream); }
+        rc = launch_ln_mod_residual(branch, BR16, xhl, gain_f, bias_f, M, D, g.tokens, 1e-6f, FX, stream); }
         if (rc) return rc;
       }
       if ((rc = sat_x())) return rc;
@@ -354,8 +361,8 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
       if (u.phys) u.phys += b0 * img_out;
       // the head reads the residual pair directly: K = 2D ([hi | lo] x [W | W]) or K = D (hi only), row pitch 2D
       { TraceScope ts_(T_HEAD, stream);
-      rc = swb200_gemm_head(kDefaultCG, m, xhl, 2 * D, g.k_head_total, bc, &u, y ? y + b0 * img_out : nullptr,
-                            stream_); }
+      rc = gemm_head_impl(kDefaultCG, m, xhl, 2 * D, XS ? D : g.k_head_total, g.k_head_total, bc, &u,
+                          y ? y + b0 * img_out : nullptr, stream_); }
       if (rc) return rc;
     }
   }
@@ -457,6 +464,12 @@ SWB200_API int swb200_gemm_ln_residual(int tile, int act_fp16, const void* A, in
 
 SWB200_API int swb200_gemm_head(int tile, const swb200_model* m, const void* A, int lda, int K, int B,
                      const swb200_update* upd, float* y, void* stream) {
+  return gemm_head_impl(tile, m, A, lda, K, K, B, upd, y, stream);
+}
+
+// K < ldw: only the first K columns of the packed head weight [W | W] are used (single-value residual stream)
+static int gemm_head_impl(int tile, const swb200_model* m, const void* A, int lda, int K, int ldw, int B, const swb200_update* upd,
+                   float* y, void* stream) {
   SWB_REQUIRE(m && A && upd && (y || upd->state), "swb200_gemm_head: NULL pointer");
   const Geom g = geom(m);
   GemmParams p = base_params(B * g.tokens, m->out_channels * g.pp, K);
@@ -481,7 +494,7 @@ SWB200_API int swb200_gemm_head(int tile, const swb200_model* m, const void* A, 
   p.d_std = upd->d_std;
   p.phys = upd->phys;
   p.zero_channel = upd->state ? upd->zero_channel : -1;
-  return launch_gemm(EPI_HEAD, tile, m->act_fp16 ? 1 : 0, A, lda, m->w_head, K, p, static_cast<cudaStream_t>(stream));
+  return launch_gemm(EPI_HEAD, tile, m->act_fp16 ? 1 : 0, A, lda, m->w_head, ldw, p, static_cast<cudaStream_t>(stream));
 }
 
 SWB200_API int swb200_patch_gather(const swb200_model* m, const float* x0, int c0, float scale0, const float* x1, int c1, int B,

@@ -125,7 +125,8 @@ int launch_patch_gather(const float* src0, int C0, float scale0, const float* sr
 #ifndef SWB_LN_MIN_BLOCKS
 #define SWB_LN_MIN_BLOCKS 4
 #endif
-template <int NV8, bool F16, bool BR16>
+// PAIR = false: x is the hi half alone (row pitch still 2D), one rounding per update; lo is neither read nor written.
+template <int NV8, bool F16, bool BR16, bool PAIR>
 __global__ void __launch_bounds__(128, SWB_LN_MIN_BLOCKS) ln_mod_residual_kernel(const void* __restrict__ branch_, uint16_t* __restrict__ xhl,
                                                               const float* __restrict__ gain,
                                                               const float* __restrict__ bias, int M, int D,
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(128, SWB_LN_MIN_BLOCKS) ln_mod_residual_kernel
     for (int i = 0; i < NV8; ++i) {
       const int c = i * 32 + lane;
       rh[i] = (c < ng) ? xh[c] : make_uint4(0u, 0u, 0u, 0u);
-      rl[i] = (c < ng) ? xl[c] : make_uint4(0u, 0u, 0u, 0u);
+      rl[i] = (PAIR && c < ng) ? xl[c] : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
     for (int i = 0; i < NV8; ++i) unpack8(raw[i], v[i]);
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(128, SWB_LN_MIN_BLOCKS) ln_mod_residual_kernel
     for (int i = 0; i < NV8; ++i) {
       const int c = i * 32 + lane;
       rh[i] = (c < ng) ? xh[c] : make_uint4(0u, 0u, 0u, 0u);
-      rl[i] = (c < ng) ? xl[c] : make_uint4(0u, 0u, 0u, 0u);
+      rl[i] = (PAIR && c < ng) ? xl[c] : make_uint4(0u, 0u, 0u, 0u);
     }
   }
   float sum = 0.f;
@@ -225,11 +226,13 @@ __global__ void __launch_bounds__(128, SWB_LN_MIN_BLOCKS) ln_mod_residual_kernel
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         h[j] = pack_act2<F16>(o[2 * j], o[2 * j + 1]);
-        const float2 back = unpack_act2<F16>(h[j]);
-        l[j] = pack_act2<F16>(o[2 * j] - back.x, o[2 * j + 1] - back.y);
+        if constexpr (PAIR) {
+          const float2 back = unpack_act2<F16>(h[j]);
+          l[j] = pack_act2<F16>(o[2 * j] - back.x, o[2 * j + 1] - back.y);
+        }
       }
       xh[c] = make_uint4(h[0], h[1], h[2], h[3]);
-      xl[c] = make_uint4(l[0], l[1], l[2], l[3]);
+      if constexpr (PAIR) xl[c] = make_uint4(l[0], l[1], l[2], l[3]);
     }
   }
 }
@@ -240,16 +243,21 @@ int launch_ln_mod_residual(const void* branch, int branch_16bit, void* xhl, cons
   SWB_REQUIRE(((reinterpret_cast<uintptr_t>(branch) | reinterpret_cast<uintptr_t>(gain) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(xhl) & 15) == 0,
               "ln_mod_residual: pointers must be 16-byte aligned");
+  const bool x_single = (act_f16 & 2) != 0;                 // format word: bit 0 = fp16 operands, bit 1 = single-value residual stream
+  act_f16 &= 1;
+  SWB_REQUIRE(!x_single || act_f16, "ln_mod_residual: the single-value residual stream needs fp16 operands");
   const int rows_per_block = 4;
   dim3 grid((M + rows_per_block - 1) / rows_per_block);
   auto x_ = static_cast<uint16_t*>(xhl);
-#define SWB_LN3(V, F, R) ln_mod_residual_kernel<V, F, R><<<grid, 128, 0, stream>>>(branch, x_, gain, bias, M, D, tokens, eps)
+#define SWB_LN3(V, F, R, P) ln_mod_residual_kernel<V, F, R, P><<<grid, 128, 0, stream>>>(branch, x_, gain, bias, M, D, tokens, eps)
 #define SWB_LN(V)                                                   \
   do {                                                              \
-    if (act_f16) {                                                  \
-      if (branch_16bit) SWB_LN3(V, true, true); else SWB_LN3(V, true, false);   \
+    if (x_single) {                                                 \
+      if (branch_16bit) SWB_LN3(V, true, true, false); else SWB_LN3(V, true, false, false);   \
+    } else if (act_f16) {                                           \
+      if (branch_16bit) SWB_LN3(V, true, true, true); else SWB_LN3(V, true, false, true);   \
     } else {                                                        \
-      if (branch_16bit) SWB_LN3(V, false, true); else SWB_LN3(V, false, false); \
+      if (branch_16bit) SWB_LN3(V, false, true, true); else SWB_LN3(V, false, false, true); \
     }                                                               \
   } while (0)
   const int nv8 = (D / 8 + 31) / 32;

@@ -101,7 +101,8 @@ extern "C" __attribute__((visibility("default"))) int swb200_debug_gemm_prof(uns
 template <int NSUB, int CG, int EPI, bool F16>
 static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to0, const CUtensorMap& to1,
                        const GemmParams& p, cudaStream_t stream) {
-  using S = GemmCfg<NSUB, CG, EPI == EPI_LN_RES>;
+  constexpr bool kLn = EPI == EPI_LN_RES || EPI == EPI_LN_RES1;
+  using S = GemmCfg<NSUB, CG, kLn>;
   auto kern = gemm_tcgen05_kernel<NSUB, CG, EPI, F16>;
   static PerDevice<bool> attr_done;
   if (!attr_done.get()) {
@@ -117,7 +118,7 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   static const int max_cl = getenv("SWB_GEMM_MAX_CLUSTERS") ? atoi(getenv("SWB_GEMM_MAX_CLUSTERS")) : 0;   // part of the chip only
   if (max_cl > 0 && clusters > max_cl) clusters = max_cl;
 #endif
-  if constexpr (EPI == EPI_LN_RES) {
+  if constexpr (kLn) {
     // the groups that exchange LayerNorm statistics (the tiles_n column tiles of one row block) must run at the same
     // time: keep the cluster count a multiple of tiles_n so that they sit on neighbouring clusters in every wave
     SWB_REQUIRE(clusters >= tiles_n, "gemm_ln_residual: %d column tiles need at least as many CTA clusters (%d)", tiles_n,
@@ -136,7 +137,7 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if constexpr (EPI == EPI_LN_RES) {
+  if constexpr (kLn) {
     // The statistics exchange spins on other CTAs of this grid: every cluster has to be resident AT THE SAME TIME.  An
     // occupancy query only speaks for an idle device, so the kernel is launched COOPERATIVELY: the driver then starts
     // the grid only when all of it fits next to whatever else is running (other streams, other processes under MPS)
@@ -182,6 +183,9 @@ static int launch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, con
     case EPI_SWIGLU: return launch_inst<NSUB, CG, EPI_SWIGLU, F16>(ta, tb, to0, to1, p, stream);
     case EPI_HEAD: return launch_inst<NSUB, CG, EPI_HEAD, F16>(ta, tb, to0, to1, p, stream);
     case EPI_LN_RES: return launch_inst<NSUB, CG, EPI_LN_RES, F16>(ta, tb, to0, to1, p, stream);
+    case EPI_LN_RES1:
+      if constexpr (F16) return launch_inst<NSUB, CG, EPI_LN_RES1, true>(ta, tb, to0, to1, p, stream);
+      break;
 #ifdef SWB_PROFILE_EPILOGUES      // measurement-only epilogues (tools/gemm_phases.py): build with SWB_NVCC_DEFINES=-DSWB_PROFILE_EPILOGUES
     case EPI_BUSY: return launch_inst<NSUB, CG, EPI_BUSY, F16>(ta, tb, to0, to1, p, stream);
     case EPI_DISCARD: return launch_inst<NSUB, CG, EPI_DISCARD, F16>(ta, tb, to0, to1, p, stream);
@@ -218,7 +222,10 @@ int launch_gemm(int epi, int tile, int act_f16, const void* A, int lda, const vo
 #endif
   const int cg = tile == 1 ? 1 : 2;
   const int nsub = tile == 3 ? 2 : 1;
-  const bool f16 = act_f16 != 0;
+  const bool f16 = (act_f16 & 1) != 0;        // bit 1 of the format word: single-value residual stream (EPI_EMBED / EPI_LN_RES)
+  p.x_single = (act_f16 >> 1) & 1;
+  SWB_REQUIRE(!p.x_single || f16, "gemm: the single-value residual stream needs fp16 operands");
+  if (epi == EPI_LN_RES && p.x_single) epi = EPI_LN_RES1;
   CUtensorMap ta, tb, to0, to1;
   const uint64_t k_total = static_cast<uint64_t>(p.K) * (p.splits > 1 ? p.splits : 1);
   const uint64_t nb = p.batch > 1 ? p.batch : 1;

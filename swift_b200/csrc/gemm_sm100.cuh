@@ -36,6 +36,8 @@ enum GemmEpilogue : int {
   EPI_HEAD = 5,        // pixel-shuffle to NCHW + sampler update: y = alpha*xt + beta*F + gamma*fprev
   EPI_LN_RES = 10,     // x += LayerNorm(acc) * gain[b] + bias[b] on the residual pair xhl (row statistics exchanged between
                        // the CTAs that hold the other column tiles of the same rows)
+  EPI_LN_RES1 = 12,    // EPI_LN_RES on the single-value residual stream (x = the hi half of xhl alone): chosen by launch_gemm from
+                       // bit 1 of the format word; a compile-time variant because both paths in one kernel spill 130 registers
   EPI_DISCARD = 6,     // profiling: accumulators handed back unread (main-loop rate)
   EPI_DRAIN = 7,       // profiling: accumulators read out of TMEM, nothing stored (main loop + drain)
   EPI_SMEM_ONLY = 8,   // profiling: EPI_STORE_ACT without its global stores (drain + pack + smem transposes)
@@ -95,6 +97,9 @@ struct GemmParams {
   // published (and drained, and handed back) while the tensor pipe still works on sub-tile 1 -- the hand-over latency of
   // the single accumulator set hides behind the other sub-tile's MMAs.  0 = both sub-tiles in lock step.
   int skew;
+  // EPI_EMBED / EPI_LN_RES: the residual stream is ONE 16-bit value per element (the `hi` half of xhl, still at row pitch
+  // 2N); the `lo` half is neither read nor written.  fp16 forecast path only (swb200_model.x_single).
+  int x_single;
   unsigned long long* prof;   // cycle counters of a -DSWB_PROFILE_EPILOGUES build (null otherwise)
 };
 
@@ -124,7 +129,10 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kEpiWarps = 4 * NSUB;
   static constexpr int kThreads = 128 + 32 * kEpiWarps;
-  static constexpr int kScratchBytes = kEpiWarps * (4096 + (LNSTATS ? 256 : 0));   // per-warp 32 x 128 B transpose buffer (+ 32 x (rstd, shift))
+  // per-warp 32 x 128 B transpose buffer; the fused-LayerNorm epilogue has two (both 64-column parts of the branch are parked
+  // there across the statistics exchange) + 32 x (rstd, shift)
+  static constexpr int kScratchPerWarp = LNSTATS ? 8192 : 4096;
+  static constexpr int kScratchBytes = kEpiWarps * (kScratchPerWarp + (LNSTATS ? 256 : 0));
   static constexpr int kBarBytes = 1024;
   static constexpr int kMaxSmem = 227 * 1024;
   static constexpr int kStagesRaw = (kMaxSmem - kScratchBytes - kBarBytes - 1024) / kStageBytes;
@@ -359,7 +367,7 @@ __device__ __forceinline__ void epi_slot_store(const GemmParams& p, const EpiCtx
       const size_t pitch = static_cast<size_t>(p.ldo) * 2;
       if (blk < 2) warp_store_rows<4>(g, pitch, reinterpret_cast<const uint4*>(w), e.scratch, e.lane, e.rows_valid, cols_valid >> 3);
       else warp_store_rows<3>(g, pitch, reinterpret_cast<const uint4*>(w), e.scratch, e.lane, e.rows_valid, cols_valid >> 3);
-      if constexpr (EPI == EPI_EMBED) {
+      if (EPI == EPI_EMBED && !p.x_single) {
         // residual stream is kept as a 16-bit [hi | lo] pair (hi doubles as the next GEMM's A operand): lo at column N + n
         uint32_t wl[16];
 #pragma unroll
@@ -833,6 +841,16 @@ __device__ __forceinline__ unsigned ld_relaxed_gpu_u32(const unsigned* p) {
   return v;
 }
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// counter += 1 with release semantics at gpu scope: everything this thread -- and, through the __syncwarp before it, its
+// warp -- wrote before is visible to whoever observes the new count (no L1 invalidation, unlike __threadfence())
+__device__ __forceinline__ void red_release_gpu_inc(unsigned* p) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+__device__ __forceinline__ float2 ld_relaxed_gpu_f2(const float2* p) {
+  float2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ float2 ld_shared_f2(uint32_t addr) {
   float2 v;
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
@@ -844,8 +862,21 @@ __device__ __forceinline__ void st_shared_f2(uint32_t addr, float2 v) {
 __device__ __forceinline__ float2 h2_to_f2(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
 
 // 8 consecutive columns of one row: x (hi + lo) += fma(branch * rstd + shift, gain, bias); re-split into hi / lo
-template <bool F16>
+template <bool F16, bool SINGLE>
 __device__ __forceinline__ void ln_apply8(uint4 br, float2 st, const float* g, const float* b, uint4& xh, uint4& xl) {
+  if constexpr (SINGLE) {                                             // x is the hi half alone: one rounding per update
+    const uint32_t bw[4] = {br.x, br.y, br.z, br.w};
+    uint32_t hw[4] = {xh.x, xh.y, xh.z, xh.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 v = h2_to_f2(bw[j]);
+      const float2 xhi = unpack_act2<F16>(hw[j]);
+      hw[j] = pack_act2<F16>(xhi.x + fmaf(fmaf(v.x, st.x, st.y), g[2 * j], b[2 * j]),
+                             xhi.y + fmaf(fmaf(v.y, st.x, st.y), g[2 * j + 1], b[2 * j + 1]));
+    }
+    xh = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    return;
+  }
   const uint32_t bw[4] = {br.x, br.y, br.z, br.w};
   uint32_t hw[4] = {xh.x, xh.y, xh.z, xh.w};
   uint32_t lw[4] = {xl.x, xl.y, xl.z, xl.w};
@@ -930,7 +961,7 @@ __device__ __forceinline__ void ln_part_apply(const GemmParams& p, const EpiCtx&
     const uint4 q = ld_shared_v4(e.scratch + r * 128 + ((c ^ (r & 7)) << 4));
     const float2 st = ld_shared_f2(stat_smem + r * 8);
     if constexpr (NCH != 8) load_gb(c);
-    ln_apply8<F16>(q, st, g, b, xh[it], xl[it]);
+    ln_apply8<F16, false>(q, st, g, b, xh[it], xl[it]);
     if (r < e.rows_valid) {
       uint4* px;
       if constexpr (NCH == 8) px = px8 + it * (static_cast<uint32_t>(p.N));     // 4 rows further per iteration
@@ -942,13 +973,70 @@ __device__ __forceinline__ void ln_part_apply(const GemmParams& p, const EpiCtx&
   __syncwarp();
 }
 
+// ---- single-value residual stream (p.x_single): x is the hi half alone.  All x loads of a warp-tile fit in registers
+// (22 x 16 bytes per lane), so they are issued in one go BEFORE the statistics exchange and its latency hides theirs.
+template <int NCH>
+__device__ __forceinline__ void ln_part_load1(const GemmParams& p, const EpiCtx& e, int n0, uint4* xh) {
+  const uint32_t pitch = static_cast<uint32_t>(p.N) * 2;               // elements per xhl row
+  const uint16_t* x0 = p.xhl + static_cast<size_t>(e.row0) * pitch + n0;
+#pragma unroll
+  for (int it = 0; it < NCH; ++it) {
+    int r, c;
+    ln_part_rc<NCH>(it, e.lane, r, c);
+    xh[it] = make_uint4(0u, 0u, 0u, 0u);
+    if (r < e.rows_valid SWB_PROF(&& !(p.ln_debug & 32))) xh[it] = *reinterpret_cast<const uint4*>(x0 + r * pitch + c * 8);
+  }
+}
+// park NCH 16-byte chunks of every lane's row in a 4 KB transpose buffer (read back in the coalesced orientation)
+template <int NCH>
+__device__ __forceinline__ void ln_stage_branch(uint32_t scratch, int lane, const uint32_t* w) {
+  const uint4* w4 = reinterpret_cast<const uint4*>(w);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) st_shared_v4(scratch + lane * 128 + ((c ^ (lane & 7)) << 4), w4[c]);
+}
+template <bool F16, int NCH>
+__device__ __forceinline__ void ln_part_apply1(const GemmParams& p, const EpiCtx& e, uint32_t stat_smem, uint32_t scratch,
+                                               int n0, const float* gn, const float* bs, const uint4* xh) {
+  const size_t pitch = static_cast<size_t>(p.N) * 2;
+  uint16_t* x0 = p.xhl + static_cast<size_t>(e.row0) * pitch + n0;
+  float g[8], b[8];
+  auto load_gb = [&](int c) {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gn + n0 + c * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gn + n0 + c * 8 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bs + n0 + c * 8)), b1 = __ldg(reinterpret_cast<const float4*>(bs + n0 + c * 8 + 4));
+    g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+    b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+  };
+#ifdef SWB_PROFILE_EPILOGUES
+  const bool no_gb = (p.ln_debug & 64) != 0, no_st = (p.ln_debug & 16) != 0;
+  if (no_gb) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { g[j] = 1.f; b[j] = 0.f; }
+  }
+#else
+  constexpr bool no_gb = false, no_st = false;
+#endif
+  if constexpr (NCH == 8) { if (!no_gb) load_gb(e.lane & 7); }          // the chunk index is the same in every iteration
+#pragma unroll
+  for (int it = 0; it < NCH; ++it) {
+    int r, c;
+    ln_part_rc<NCH>(it, e.lane, r, c);
+    const uint4 q = ld_shared_v4(scratch + r * 128 + ((c ^ (r & 7)) << 4));
+    const float2 st = ld_shared_f2(stat_smem + r * 8);
+    if constexpr (NCH != 8) { if (!no_gb) load_gb(c); }
+    uint4 xv = xh[it], dummy = make_uint4(0u, 0u, 0u, 0u);
+    ln_apply8<F16, true>(q, st, g, b, xv, dummy);
+    if (r < e.rows_valid && (!no_st || xv.x == 0x7fc01234u)) *reinterpret_cast<uint4*>(x0 + r * pitch + c * 8) = xv;
+  }
+  __syncwarp();
+}
+
 // L2 prefetch of the x hi / lo segments this warp will update (issued before the warp waits for the accumulator, a whole
 // main loop ahead of their use)
 __device__ __forceinline__ void ln_prefetch_x(const GemmParams& p, int row0, int rows_valid, int lane, int n_lo, int n_hi) {
   if (lane >= rows_valid) return;
   const uint16_t* xr = p.xhl + static_cast<size_t>(row0 + lane) * (2 * p.N);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < (p.x_single ? 2 : 4); ++k) {
     const int n0 = (k & 1) ? n_hi : n_lo;
     if (n0 < p.N) {
       const uint16_t* a = xr + n0 + ((k & 2) ? p.N : 0);
@@ -969,7 +1057,7 @@ __device__ __forceinline__ void ln_group_cols(int s, int& lo, int& hi) {
   }
 }
 
-template <int NSUB, int CG, bool F16, typename Release>
+template <int NSUB, int CG, bool F16, bool SINGLE, typename Release>
 __device__ __forceinline__ void epi_group_lnres(const GemmParams& p, const EpiCtx& e, uint32_t stat_smem, uint32_t tacc, int sgrp,
                                                 int nslots, Release&& release) {
   int n_lo, n_hi;
@@ -1009,17 +1097,26 @@ __device__ __forceinline__ void epi_group_lnres(const GemmParams& p, const EpiCt
   const float sum = cnt ? fmaf(fc, K, s1) : 0.f;             // sum x      = s1 + n K
   const float m2 = cnt ? fmaxf(s2 - s1 * s1 / fc, 0.f) : 0.f;   // sum (x - mean_p)^2
   // publish, then wait for the other groups of these 32 rows
+  SWB_PROF(long long tq0 = clock64();)
   const int row = e.row0 + e.lane;
   __stcg(p.ln_stats + static_cast<size_t>(sgrp) * p.ln_stride + row, make_float2(sum, m2));
   __syncwarp();
   unsigned* counter = p.ln_counter + (e.row0 >> 5);
-  if (e.lane == 0) {
-    __threadfence();
-    atomicAdd(counter, 1u);
-  }
-  // the x loads of the first part go out before the wait
+  if (e.lane == 0) red_release_gpu_inc(counter);
+  SWB_PROF({ const long long t_ = clock64(); if (e.lane == 0) atomicAdd(&p.prof[11], (unsigned long long)(t_ - tq0)); tq0 = t_; })
+  constexpr bool single = SINGLE;
+  // single-value stream: every x load of this warp-tile goes out before the wait; pair: the loads of the first part
   uint4 xhA[8], xlA[8], xhB[3], xlB[3];
-  ln_part_load<8>(p, e, va ? n_lo : n_hi, xhA, xlA);
+  uint4 xs0[8], xs1[3], xs2[8], xs3[3];
+  if constexpr (single) {
+    // the two 64-column parts of the branch wait in shared memory (frees 64 registers for the x loads)
+    ln_stage_branch<8>(e.scratch, e.lane, wa);
+    ln_stage_branch<8>(e.scratch + 4096, e.lane, wb);
+    if (va) { ln_part_load1<8>(p, e, n_lo, xs0); ln_part_load1<3>(p, e, n_lo + 64, xs1); }
+    if (vb) { ln_part_load1<8>(p, e, n_hi, xs2); ln_part_load1<3>(p, e, n_hi + 64, xs3); }
+  } else {
+    ln_part_load<8>(p, e, va ? n_lo : n_hi, xhA, xlA);
+  }
   if (!(p.ln_debug & 1) && ld_relaxed_gpu_u32(counter) < p.ln_target) {
     const long long t0 = clock64();
     while (ld_relaxed_gpu_u32(counter) < p.ln_target) {
@@ -1031,13 +1128,17 @@ __device__ __forceinline__ void epi_group_lnres(const GemmParams& p, const EpiCt
       }
     }
   }
-  fence_acq_rel_gpu();                                       // pairs with the publishers' __threadfence + atomicAdd
+  SWB_PROF({ const long long t_ = clock64(); if (e.lane == 0) atomicAdd(&p.prof[12], (unsigned long long)(t_ - tq0)); tq0 = t_; })
+  // The partials are read with gpu-scope loads (L2, never L1) that are ISSUED after the poll above has seen the final count:
+  // an SM does not speculate loads past the branch that consumes the polled value, and every publisher's statistics were
+  // visible at gpu scope before its release-increment.  A fence.acq_rel here would add nothing but an L1 invalidation
+  // (CCTL.IVALL: the gain / bias rows would miss L1 in every part) and a wait for the x loads in flight.
   // merge the partials (Chan et al.): mean, M2 over all N columns
   constexpr int kMaxGroups = 12;
   float2 part[kMaxGroups];
 #pragma unroll
   for (int s = 0; s < kMaxGroups; ++s)
-    part[s] = s < nslots ? __ldcg(p.ln_stats + static_cast<size_t>(s) * p.ln_stride + row) : make_float2(0.f, 0.f);
+    part[s] = s < nslots ? ld_relaxed_gpu_f2(p.ln_stats + static_cast<size_t>(s) * p.ln_stride + row) : make_float2(0.f, 0.f);
   float tot = 0.f;
 #pragma unroll
   for (int s = 0; s < kMaxGroups; ++s) tot += part[s].x;
@@ -1059,7 +1160,19 @@ __device__ __forceinline__ void epi_group_lnres(const GemmParams& p, const EpiCt
   const int b = e.row0 / p.tokens;                           // tokens % 32 == 0: the 32 rows belong to one sample
   const float* gn = p.gain + static_cast<size_t>(b) * p.N;
   const float* bs = p.lnbias + static_cast<size_t>(b) * p.N;
+  SWB_PROF({ const long long t_ = clock64(); if (e.lane == 0) atomicAdd(&p.prof[13], (unsigned long long)(t_ - tq0)); tq0 = t_; })
   if (p.ln_debug & 2) return;
+  if constexpr (single) {
+    // (the __syncwarp after the statistics store also orders the staged branch parts)
+    if (va) ln_part_apply1<F16, 8>(p, e, stat_smem, e.scratch, n_lo, gn, bs, xs0);
+    if (vb) ln_part_apply1<F16, 8>(p, e, stat_smem, e.scratch + 4096, n_hi, gn, bs, xs2);
+    ln_stage_branch<3>(e.scratch, e.lane, wa + 32);             // the 24-column tails take the buffers over
+    ln_stage_branch<3>(e.scratch + 4096, e.lane, wb + 32);
+    __syncwarp();
+    if (va) ln_part_apply1<F16, 3>(p, e, stat_smem, e.scratch, n_lo + 64, gn, bs, xs1);
+    if (vb) ln_part_apply1<F16, 3>(p, e, stat_smem, e.scratch + 4096, n_hi + 64, gn, bs, xs3);
+    return;
+  }
   // parts: (lo, 64 columns) (lo, 24) (hi, 64) (hi, 24); the loads of the next part are in flight while one is applied
   if (va) {
     ln_part_load<3>(p, e, n_lo + 64, xhB, xlB);
@@ -1081,7 +1194,7 @@ __global__ void __launch_bounds__(GemmCfg<NSUB, CG>::kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_o0, const __grid_constant__ CUtensorMap tmap_o1,
                     const GemmParams p) {
-  using S = GemmCfg<NSUB, CG, EPI == EPI_LN_RES>;
+  using S = GemmCfg<NSUB, CG, EPI == EPI_LN_RES || EPI == EPI_LN_RES1>;
   constexpr int kStages = S::kStages;
   constexpr int BN = kUmmaN;
   constexpr int kTileN = S::kTileN;
@@ -1393,19 +1506,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const uint32_t tempty_leader0 = (CG == 2) ? mapa_u32(tempty_bar(0), 0) : tempty_bar(0);
     EpiCtx e;
     e.lane = lane;
-    e.scratch = scratch0 + (warp - 4) * 4096;
+    e.scratch = scratch0 + (warp - 4) * S::kScratchPerWarp;
     e.to0 = &tmap_o0;
     e.to1 = &tmap_o1;
     e.pending = false;
     SWB_PROF(e.store_wait = 0; long long ew_full = 0; long long ew_drain = 0; long long ew_rest = 0; long long t_rel = 0;)
-    const uint32_t stat_smem = scratch0 + S::kEpiWarps * 4096 + (warp - 4) * 256;
+    const uint32_t stat_smem = scratch0 + S::kEpiWarps * S::kScratchPerWarp + (warp - 4) * 256;
     int it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const uint32_t par = static_cast<uint32_t>(it) & 1u;
       const int bs = tile / tiles_mn, tmn = tile - bs * tiles_mn;      // bs = batch * splits + split: the output block
       const int tm = tmn / tiles_n, tn = tmn - tm * tiles_n;
       const int n_tile = tn * kTileN;
-      if constexpr (EPI == EPI_LN_RES) {
+      if constexpr (EPI == EPI_LN_RES || EPI == EPI_LN_RES1) {
         const int r0 = tm * (kBlockM * CG) + static_cast<int>(cta_rank) * kBlockM + quad * 32;
         int lo, hi;
         ln_group_cols<NSUB, CG>(tn * NSUB + grp, lo, hi);
@@ -1459,8 +1572,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         release();
         epi_slot_store<EPI, F16, true>(p, e, 0u, n_lo, va);
         epi_slot_store<EPI, F16, true>(p, e, 0u, n_hi, vb);
-      } else if constexpr (EPI == EPI_LN_RES) {
-        epi_group_lnres<NSUB, CG, F16>(p, e, stat_smem, tacc, tn * NSUB + grp, tiles_n * NSUB, release);
+      } else if constexpr (EPI == EPI_LN_RES || EPI == EPI_LN_RES1) {
+        epi_group_lnres<NSUB, CG, F16, EPI == EPI_LN_RES1>(p, e, stat_smem, tacc, tn * NSUB + grp, tiles_n * NSUB, release);
       } else if constexpr (EPI == EPI_SMEM_ONLY) {
         epi_group_store16_prof<F16, 1>(p, e, tacc, n_lo, n_hi, release);
       } else if constexpr (EPI == EPI_DIRECT) {

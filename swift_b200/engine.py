@@ -29,7 +29,8 @@ class Engine:
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], geom: packing.Geometry, device: torch.device,
                  split_embed: bool = True, split_head: bool = True, max_chunk: int = 8, act_fp16: bool = True,
-                 gemm_tile: int = 3, attn_impl: int = 0, fuse_ln: int = 2, attn_fp16: bool = True):
+                 gemm_tile: int = 3, attn_impl: int = 0, fuse_ln: int = 2, attn_fp16: bool = True,
+                 x_single: bool = True):
         if device.type != "cuda":
             raise RuntimeError("swift_b200 runs on CUDA devices only (no CPU fallback)")
         self.lib = _lib.lib()
@@ -38,7 +39,7 @@ class Engine:
         self.generation = next(_GENERATION)
         with torch.cuda.device(device):
             self.model, self._keep = packing.pack(state_dict, geom, device, split_embed, split_head, act_fp16,
-                                                   gemm_tile, attn_impl, fuse_ln, attn_fp16)
+                                                   gemm_tile, attn_impl, fuse_ln, attn_fp16, x_single)
         self.fuse_ln = int(fuse_ln)
         self.act_fp16 = act_fp16
         _lib.check(self.lib.swb200_validate(C.byref(self.model)), "validate")

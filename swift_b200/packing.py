@@ -113,7 +113,7 @@ def ref_params(sd: Dict[str, torch.Tensor], g: Geometry, device: torch.device):
 
 def pack(sd: Dict[str, torch.Tensor], g: Geometry, device: torch.device, split_embed: bool = True,
          split_head: bool = True, act_fp16: bool = True, gemm_tile: int = 3, attn_impl: int = 0, fuse_ln: int = 2,
-         attn_fp16: bool = True):
+         attn_fp16: bool = True, x_single: bool = True):
     """Returns (``_lib.Model`` struct, dict of device tensors that must stay alive as long as the struct is used).
     The conversions themselves are ``swb200_pack_weights`` (csrc/pack.cu): this function only collects the parameter
     pointers of the state dict and owns the packed buffer."""
@@ -139,6 +139,7 @@ def pack(sd: Dict[str, torch.Tensor], g: Geometry, device: torch.device, split_e
     m.attn_impl = int(attn_impl)
     m.fuse_ln = int(fuse_ln)
     m.attn_fp16 = int(attn_fp16)
+    m.x_single = int(bool(x_single) and bool(act_fp16))
     m.timestep_weight = float(g.timestep_weight)
     lib = _lib.lib()
     nbytes = lib.swb200_packed_bytes(C.byref(m))

@@ -188,6 +188,8 @@ class SwinV2(_Base):
         self.split_embed = True      # [hi|lo] bf16 operands for the two small end GEMMs (accuracy, <1% of FLOPs)
         self.split_head = True
         self.act_fp16 = True         # tensor-core operands in fp16 (else bf16): 8x smaller rounding error, same tcgen05 rate
+        self.x_single = True         # fp16 mode only: the forecast path's residual stream is ONE fp16 value per element (not a [hi | lo]
+                                     # pair): 40 % less residual traffic, one extra 2^-11 rounding per update
         self.attn_fp16 = True        # bf16 mode only: q / k / v and P stay fp16 inside the attention kernel (bounded values)
         self.gemm_tile = 3           # 1: 128x176 single CTA, 2: 256x176 CTA pair, 3: 256x352 CTA pair
         self.attn_impl = 0           # 0: tcgen05 attention when the shift is a multiple of 8, 1: mma.sync kernel, 2: tcgen05
@@ -213,7 +215,7 @@ class SwinV2(_Base):
     def engine(self) -> Engine:
         """The packed CUDA engine for the current parameter values (re-packed when parameters change)."""
         key = (self._params_key(), self.split_embed, self.split_head, self.max_chunk, self.act_fp16, self.gemm_tile, self.attn_impl,
-               self.fuse_ln, self.attn_fp16)
+               self.fuse_ln, self.attn_fp16, self.x_single)
         if self._engine is None or self._engine_key != key:
             dev = self.pos_embed.device
             if dev.type != "cuda":
@@ -221,7 +223,8 @@ class SwinV2(_Base):
                                    "there is no CPU fallback")
             sd = {k: v for k, v in self.state_dict().items()}
             self._engine = Engine(sd, self.geometry, dev, self.split_embed, self.split_head, self.max_chunk,
-                                  self.act_fp16, self.gemm_tile, self.attn_impl, self.fuse_ln, self.attn_fp16)
+                                  self.act_fp16, self.gemm_tile, self.attn_impl, self.fuse_ln, self.attn_fp16,
+                                  self.x_single)
             self._engine_key = key
         return self._engine
 

@@ -22,7 +22,7 @@ def per_field_rel_l2(y, ref):
     return num / den          # [B, C]
 
 
-def build_net(cfg, seed=1, img_channels=None, act_fp16=True, fuse_ln=None):
+def build_net(cfg, seed=1, img_channels=None, act_fp16=True, fuse_ln=None, x_single=None):
     from swift_b200 import synthetic as syn
     from swift_b200.precond import PassPrecond
     img_channels = cfg["out_channels"] if img_channels is None else img_channels
@@ -38,18 +38,22 @@ def build_net(cfg, seed=1, img_channels=None, act_fp16=True, fuse_ln=None):
     net.model.act_fp16 = act_fp16
     if fuse_ln is not None:
         net.model.fuse_ln = fuse_ln
+    if x_single is not None:
+        net.model.x_single = x_single
     return net.cuda().eval(), {k[len("model."):]: v for k, v in sd.items()}
 
 
 @pytest.mark.parametrize("fuse_ln", [0, 1, 2, 3], ids=["ln_kernel", "ln_in_wo", "ln_in_w2", "ln_in_wo_w2"])
-@pytest.mark.parametrize("act_fp16", [True, False], ids=["act_fp16", "act_bf16"])
+@pytest.mark.parametrize("act_fp16,x_single", [(True, True), (True, False), (False, False)],
+                         ids=["act_fp16_x_single", "act_fp16_x_pair", "act_bf16"])
 @pytest.mark.parametrize("name,cfgname", [("tiny", "SWIFT_TINY"), ("small", "SWIFT_SMALL")])
-def test_module_forward_vs_reference_golden(golden, name, cfgname, act_fp16, fuse_ln):
-    """fuse_ln: LayerNorm + modulation + residual add as its own kernel or in the wo / w2 GEMM epilogue."""
+def test_module_forward_vs_reference_golden(golden, name, cfgname, act_fp16, x_single, fuse_ln):
+    """fuse_ln: LayerNorm + modulation + residual add as its own kernel or in the wo / w2 GEMM epilogue; x_single: the
+    residual stream as one fp16 value per element (default in fp16 mode) or as the [hi | lo] pair."""
     from swift_b200 import synthetic as syn
     g = golden(name)
     cfg = getattr(syn, cfgname)
-    net, _ = build_net(cfg, act_fp16=act_fp16, fuse_ln=fuse_ln)
+    net, _ = build_net(cfg, act_fp16=act_fp16, fuse_ln=fuse_ln, x_single=x_single)
     lat, cond = syn.synthetic_fields(cfg, 2, seed=3)
     with torch.no_grad():
         y = net(lat.cuda(), torch.from_numpy(g["fwd_t"]).cuda(), cond.cuda(), torch.from_numpy(g["fwd_aux"]).cuda())
@@ -126,10 +130,22 @@ def test_swift_b_one_step_vs_oracle_and_golden(golden):
     assert np.allclose(ref[:, :, ::8, ::8].cpu().numpy(), g["scm1_sub"], rtol=2e-3, atol=2e-4), \
         "GPU fp32 oracle drifted from the reference digest"
     err = per_field_rel_l2(y, ref)
-    print(f"swift_b scm1 (fp16 operands): per-field rel-L2 max {err.max():.4e} mean {err.mean():.4e}")
-    assert err.max() < 0.5 * TOL
+    print(f"swift_b scm1 (fp16 operands, single-value residual stream = the default): per-field rel-L2 max {err.max():.4e} "
+          f"mean {err.mean():.4e}")
+    assert err.max() < 0.3 * TOL
     sub = per_field_rel_l2(y[:, :, ::8, ::8], torch.from_numpy(g["scm1_sub"]))
     assert sub.max() < TOL                  # vs the REAL reference's sub-sampled output (512 points per field)
+    # the [hi | lo] residual pair (x_single = False): 0.5e-3 closer, 40 % more residual traffic
+    net.model.x_single = False
+    for fuse_ln in (2, 3):
+        net.model.fuse_ln = fuse_ln
+        yp = DiffusionSampler(net).scm_solver(latents=lat.cuda(), condition=cond.cuda(), auxiliary=0.6, num_steps=1,
+                                              sigma_min=0.02, sigma_max=200.0)
+        errp = per_field_rel_l2(yp, ref)
+        print(f"swift_b scm1 (fp16 operands, [hi | lo] residual pair, fuse_ln {fuse_ln}): per-field rel-L2 max {errp.max():.4e} "
+              f"mean {errp.mean():.4e}")
+        assert errp.max() < 0.2 * TOL
+    net.model.x_single = True
     # the bf16 operand format north_star names: GEMM operands bf16, attention internals (q, k, v, P) fp16 -- must meet the
     # same bar; with bf16 attention internals as well (attn_fp16 = False) it is borderline, which is reported
     net.model.act_fp16 = False

@@ -135,6 +135,52 @@ def test_gemm_embed_epilogue(lib, cg, f16):
     assert torch.equal(lo, ((hi.float() + lo.float()) - hi.float()).to(_adt(f16)))
 
 
+@pytest.mark.parametrize("cg", [3, 2, 1], ids=["tile256x352", "tile256x176", "tile128x176"])
+def test_gemm_embed_epilogue_single_value_stream(lib, cg):
+    """Format word 3: only the hi half of the residual buffer is written."""
+    B, T, D, K = 2, 512, 264, 56
+    M = B * T
+    A = _rand_bf16((M, K), 9, dtype=torch.float16)
+    W = _rand_bf16((D, K), 10, 0.1, dtype=torch.float16)
+    pos = torch.randn(T, D, device="cuda")
+    xhl = torch.full((M, 2 * D), float("nan"), device="cuda", dtype=torch.float16)
+    _check(lib.swb200_gemm_embed(cg, 3, A.data_ptr(), K, W.data_ptr(), K, None, pos.data_ptr(), T, xhl.data_ptr(), M, D,
+                                 _stream()))
+    torch.cuda.synchronize()
+    ref = A.float() @ W.float().t() + pos.repeat(B, 1)
+    assert torch.isnan(xhl[:, D:]).all()
+    assert _rel(xhl[:, :D].float(), ref) < 6e-4
+
+
+@pytest.mark.parametrize("cg", [3, 2], ids=["tile256x352", "tile256x176"])
+@pytest.mark.parametrize("B,T,D,K", [(3, 256, 264, 264), (3, 256, 1056, 1056), (2, 512, 1056, 2816), (6, 8192, 1056, 264)])
+def test_gemm_ln_residual_epilogue_single_value_stream(lib, cg, B, T, D, K):
+    """EPI_LN_RES with format word 3: x (hi half only) += LayerNorm(A W^T) * gain + bias, one fp16 rounding per update; the lo
+    half is neither read nor written."""
+    M = B * T
+    A = _rand_bf16((M, K), 21, dtype=torch.float16)
+    W = _rand_bf16((D, K), 22, 0.05, dtype=torch.float16)
+    g = torch.Generator(device="cuda").manual_seed(23)
+    hi = torch.randn(M, D, device="cuda", generator=g).half()
+    xhl = torch.cat([hi, torch.full_like(hi, float("nan"))], 1).contiguous()
+    x_ref = hi.float()
+    ws = torch.empty(lib.swb200_ln_workspace_bytes(M, D) + 256, dtype=torch.uint8, device="cuda")
+    ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+    branch = (A.float() @ W.float().t()).half().float()
+    for gen in range(2):
+        gain = torch.randn(B, D, device="cuda", generator=g)
+        bias = torch.randn(B, D, device="cuda", generator=g)
+        _check(lib.swb200_gemm_ln_residual(cg, 3, A.data_ptr(), K, W.data_ptr(), K, xhl.data_ptr(), gain.data_ptr(),
+                                           bias.data_ptr(), M, D, T, ws_ptr, gen, _stream()))
+        torch.cuda.synchronize()
+        ln = torch.nn.functional.layer_norm(branch, (D,), eps=1e-6).reshape(B, T, D)
+        x_ref = x_ref + (ln * gain[:, None] + bias[:, None]).reshape(M, D)
+        got = xhl[:, :D].float()
+        assert torch.isnan(xhl[:, D:]).all()
+        assert _rel(got, x_ref) < 6e-4, f"gen {gen}: {_rel(got, x_ref):.3e}"
+        x_ref = got.clone()
+
+
 @ACT
 @pytest.mark.parametrize("cg", [3, 2, 1], ids=["tile256x352", "tile256x176", "tile128x176"])
 @pytest.mark.parametrize("mode", ["plain", "scm", "heun"])

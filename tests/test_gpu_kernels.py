@@ -70,6 +70,35 @@ def test_patch_gather(lib, split, p1, p2, C0, C1, H, W, f16):
         assert _rel(A[:, :kp].float()[:, :Cin * p1 * p2] + A[:, kp:].float()[:, :Cin * p1 * p2], ref) < 2e-5 * (0.2 if f16 else 1)
 
 
+@pytest.mark.parametrize("br16", [0, 1], ids=["branch_fp32", "branch_16bit"])
+@pytest.mark.parametrize("D", [264, 1056])
+def test_ln_mod_residual_single_value_stream(lib, D, br16):
+    """Format word 3 (fp16 operands + single-value residual stream): x is the hi half alone, rounded once per update; the lo
+    half of the buffer is neither read nor written."""
+    B, T = 3, 256
+    M = B * T
+    branch = torch.randn(M, D, device="cuda") * 3 + 0.7
+    if br16:
+        branch = branch.half()
+    hi = torch.randn(M, D, device="cuda").half()
+    poison = torch.full((M, D), float("nan"), device="cuda", dtype=torch.float16)
+    xhl = torch.cat([hi, poison], 1).contiguous()
+    gain = torch.randn(B, D, device="cuda")
+    bias = torch.randn(B, D, device="cuda")
+    x_ref = hi.float() + torch.nn.functional.layer_norm(branch.float(), (D,), eps=1e-6).reshape(B, T, D).mul(
+        gain[:, None]).add(bias[:, None]).reshape(M, D)
+    _check(lib.swb200_ln_mod_residual(branch.data_ptr(), br16, xhl.data_ptr(), gain.data_ptr(), bias.data_ptr(), M, D, T,
+                                      3, _stream()))
+    torch.cuda.synchronize()
+    assert torch.isnan(xhl[:, D:]).all()                               # lo untouched
+    got = xhl[:, :D].float()
+    assert _rel(got, x_ref) < 6e-4, f"{_rel(got, x_ref):.3e}"
+    # one correctly rounded fp16 value per element (up to the summation order of the statistics)
+    assert (got - x_ref.half().float()).abs().max() <= 2 * torch.finfo(torch.float16).eps * x_ref.abs().max()
+    rc = lib.swb200_ln_mod_residual(branch.data_ptr(), br16, xhl.data_ptr(), gain.data_ptr(), bias.data_ptr(), M, D, T, 2, _stream())
+    assert rc != 0 and b"fp16" in lib.swb200_last_error()              # bf16 keeps the pair
+
+
 @ACT
 @pytest.mark.parametrize("br16", [0, 1], ids=["branch_fp32", "branch_16bit"])
 @pytest.mark.parametrize("D", [264, 528, 1056])
