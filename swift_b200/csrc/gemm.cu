@@ -86,11 +86,11 @@ int make_tmap_16bit_2d(CUtensorMap* out, const void* ptr, bool is_f16, uint64_t 
 }
 
 #ifdef SWB_PROFILE_EPILOGUES
-__device__ unsigned long long g_gemm_prof[16];
-extern "C" __attribute__((visibility("default"))) int swb200_debug_gemm_prof(unsigned long long* out16, int reset) {
-  if (out16 && cudaMemcpyFromSymbol(out16, g_gemm_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return 1;
+__device__ unsigned long long g_gemm_prof[24];
+extern "C" __attribute__((visibility("default"))) int swb200_debug_gemm_prof(unsigned long long* out24, int reset) {
+  if (out24 && cudaMemcpyFromSymbol(out24, g_gemm_prof, sizeof(unsigned long long) * 24) != cudaSuccess) return 1;
   if (reset) {
-    unsigned long long z[16] = {};
+    unsigned long long z[24] = {};
     if (cudaMemcpyToSymbol(g_gemm_prof, z, sizeof(z)) != cudaSuccess) return 1;
   }
   return 0;
@@ -251,6 +251,15 @@ int launch_gemm(int epi, int tile, int act_f16, const void* A, int lda, const vo
     rc = make_tmap_16bit_2d_swz(&to0, p.out0, f16, rows, kHeadDimPad, kHeadDimPad, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     rc = make_tmap_16bit_2d_swz(&to1, p.out0, f16, rows, kHeadDimPad, kHeadDimPad, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    p.tma_store = 1;
+  }
+  if (epi == EPI_LN_RES1 && tile == 3) {
+    // the residual stream (hi half of xhl: [M, N] at row pitch 2N) travels by TMA: 64-column SWIZZLE_128B boxes and the
+    // 24-column rest of an 88-column slot, 32 rows each, for loads and stores alike
+    rc = make_tmap_16bit_2d_swz(&to0, p.xhl, true, p.M, p.N, 2 * static_cast<uint64_t>(p.N), 32, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_tmap_16bit_2d_swz(&to1, p.xhl, true, p.M, p.N, 2 * static_cast<uint64_t>(p.N), 32, 24, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
     p.tma_store = 1;
   }

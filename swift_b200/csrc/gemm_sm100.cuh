@@ -262,6 +262,9 @@ struct EpiCtx {
   const CUtensorMap* to0;   // output tensor maps of the TMA-store epilogues: 64-column box (SWIZZLE_128B) ...
   const CUtensorMap* to1;   // ... and the tail box (24 columns un-swizzled, or 32 columns SWIZZLE_64B for qkv)
   bool pending;      // a TMA store issued by lane 0 may still be reading the scratch buffer
+  // EPI_LN_RES1 on the 256x352 tile: x travels by TMA (tile loads into the two 4 KB buffers, updated in place, tile stores)
+  uint32_t xbar;     // two mbarriers (8 bytes apart): data of buffer 0 / 1 has landed
+  uint32_t xph;      // bit b: parity of buffer b's next completion
 };
 
 // ---- TMA-store epilogue pieces.  Every lane owns one row of the warp's 32-row block and writes its 16-byte chunks
@@ -1030,6 +1033,63 @@ __device__ __forceinline__ void ln_part_apply1(const GemmParams& p, const EpiCtx
   __syncwarp();
 }
 
+// ---- single-value residual stream on the 256x352 tile: x by TMA.  The two 64-column parts of the warp's rows are loaded
+// into its two 4 KB buffers (SWIZZLE_128B image: lane = row) BEFORE the warp waits for the accumulator, updated in place in
+// the row-per-lane orientation the accumulator arrives in (no transpose of the branch, statistics stay in registers) and
+// stored as tiles; the two 24-column tails follow through the same buffers.  No LSU traffic for x at all.
+__device__ __forceinline__ void lnx_load(const EpiCtx& e, int buf, bool tail, int n0) {
+  const uint32_t bar = e.xbar + 8u * buf;
+  if (e.lane == 0) mbar_arrive_expect_tx(bar, tail ? 32u * 48u : 4096u);
+  __syncwarp();
+  tma_load_2d_elect(e.scratch + 4096u * buf, tail ? e.to1 : e.to0, bar, n0, e.row0);
+}
+__device__ __forceinline__ void lnx_begin_tile(const GemmParams& p, EpiCtx& e, int n_lo, int n_hi) {
+  if (e.rows_valid <= 0) return;
+  epi_scratch_acquire(e);                                     // the previous tile's stores have left the buffers
+  if (n_lo < p.N) lnx_load(e, 0, false, n_lo);
+  if (n_hi < p.N) lnx_load(e, 1, false, n_hi);
+  if (e.lane == 0) {                                          // the tails follow through the same buffers: have them in L2 by then
+    if (n_lo < p.N) tma_prefetch_2d(e.to1, n_lo + 64, e.row0);
+    if (n_hi < p.N) tma_prefetch_2d(e.to1, n_hi + 64, e.row0);
+  }
+}
+// NCH chunks (8 columns each) of this lane's row: x += (branch * rstd + shift) * gain + bias, in place in the buffer
+template <bool F16, int NCH>
+__device__ __forceinline__ void lnx_apply(const GemmParams& p, EpiCtx& e, int buf, const uint32_t* w, int n0, float2 st,
+                                          const float* gn, const float* bs) {
+  const uint32_t bar = e.xbar + 8u * buf;
+  SWB_PROF(const long long ta_ = clock64();)
+  mbar_wait(bar, (e.xph >> buf) & 1u, 40 + buf);
+  SWB_PROF(if (e.lane == 0) atomicAdd(&p.prof[NCH == 8 ? 14 : 15], (unsigned long long)(clock64() - ta_));)
+  e.xph ^= 1u << buf;
+  const uint32_t base = e.scratch + 4096u * buf;
+  // three phases, so that the (volatile) shared-memory accesses do not serialise the chunks: every x chunk of the row is
+  // read, then the arithmetic runs with the gain / bias loads (the same address in every lane: one L1 wavefront each)
+  // free to be scheduled ahead, then everything is written back
+  auto addr = [&](int c) { return NCH == 8 ? base + e.lane * 128 + ((c ^ (e.lane & 7)) << 4) : base + e.lane * 48 + c * 16; };
+  uint4 xv[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) xv[c] = ld_shared_v4(addr(c));
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    uint4 dummy = make_uint4(0u, 0u, 0u, 0u);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gn + n0 + c * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gn + n0 + c * 8 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bs + n0 + c * 8)), b1 = __ldg(reinterpret_cast<const float4*>(bs + n0 + c * 8 + 4));
+    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    ln_apply8<F16, true>(make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]), st, g, b, xv[c], dummy);
+  }
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) st_shared_v4(addr(c), xv[c]);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (e.lane == 0) {
+    tma_store_2d(NCH == 8 ? e.to0 : e.to1, base, n0, e.row0);
+    bulk_commit_group();
+  }
+  e.pending = true;
+}
+
 // L2 prefetch of the x hi / lo segments this warp will update (issued before the warp waits for the accumulator, a whole
 // main loop ahead of their use)
 __device__ __forceinline__ void ln_prefetch_x(const GemmParams& p, int row0, int rows_valid, int lane, int n_lo, int n_hi) {
@@ -1058,8 +1118,9 @@ __device__ __forceinline__ void ln_group_cols(int s, int& lo, int& hi) {
 }
 
 template <int NSUB, int CG, bool F16, bool SINGLE, typename Release>
-__device__ __forceinline__ void epi_group_lnres(const GemmParams& p, const EpiCtx& e, uint32_t stat_smem, uint32_t tacc, int sgrp,
+__device__ __forceinline__ void epi_group_lnres(const GemmParams& p, EpiCtx& e, uint32_t stat_smem, uint32_t tacc, int sgrp,
                                                 int nslots, Release&& release) {
+  constexpr bool kXTma = SINGLE && NSUB == 2;                 // x by TMA (lnx_*): its loads were issued by lnx_begin_tile
   int n_lo, n_hi;
   ln_group_cols<NSUB, CG>(sgrp, n_lo, n_hi);
   const bool va = n_lo < p.N, vb = n_hi < p.N;               // N % 88 == 0: a slot is entirely inside or outside
@@ -1108,7 +1169,8 @@ __device__ __forceinline__ void epi_group_lnres(const GemmParams& p, const EpiCt
   // single-value stream: every x load of this warp-tile goes out before the wait; pair: the loads of the first part
   uint4 xhA[8], xlA[8], xhB[3], xlB[3];
   uint4 xs0[8], xs1[3], xs2[8], xs3[3];
-  if constexpr (single) {
+  if constexpr (kXTma) {
+  } else if constexpr (single) {
     // the two 64-column parts of the branch wait in shared memory (frees 64 registers for the x loads)
     ln_stage_branch<8>(e.scratch, e.lane, wa);
     ln_stage_branch<8>(e.scratch + 4096, e.lane, wb);
@@ -1155,11 +1217,37 @@ __device__ __forceinline__ void epi_group_lnres(const GemmParams& p, const EpiCt
     }
   }
   const float rstd = rsqrtf(M2 / static_cast<float>(p.N) + p.ln_eps);
-  st_shared_f2(stat_smem + e.lane * 8, make_float2(rstd, -mean * rstd));
-  __syncwarp();
   const int b = e.row0 / p.tokens;                           // tokens % 32 == 0: the 32 rows belong to one sample
   const float* gn = p.gain + static_cast<size_t>(b) * p.N;
   const float* bs = p.lnbias + static_cast<size_t>(b) * p.N;
+  if constexpr (kXTma) {
+    const float2 st = make_float2(rstd, -mean * rstd);
+    SWB_PROF({ const long long t_ = clock64(); if (e.lane == 0) atomicAdd(&p.prof[13], (unsigned long long)(t_ - tq0)); tq0 = t_; })
+    // the 24-column tails re-use the buffers: each is requested as soon as its buffer's store has been read, so that the
+    // other slot's arithmetic covers the round trip
+    if (va) {
+      lnx_apply<F16, 8>(p, e, 0, wa, n_lo, st, gn, bs);
+      SWB_PROF(const long long tb_ = clock64();)
+      if (e.lane == 0) bulk_wait_read_all();
+      __syncwarp();
+      SWB_PROF(e.store_wait += clock64() - tb_;)
+      lnx_load(e, 0, true, n_lo + 64);
+    }
+    if (vb) {
+      lnx_apply<F16, 8>(p, e, 1, wb, n_hi, st, gn, bs);
+      SWB_PROF(const long long tb_ = clock64();)
+      if (e.lane == 0) bulk_wait_read_all();
+      __syncwarp();
+      SWB_PROF(e.store_wait += clock64() - tb_;)
+      lnx_load(e, 1, true, n_hi + 64);
+    }
+    if (va) lnx_apply<F16, 3>(p, e, 0, wa + 32, n_lo + 64, st, gn, bs);
+    if (vb) lnx_apply<F16, 3>(p, e, 1, wb + 32, n_hi + 64, st, gn, bs);
+    SWB_PROF({ const long long t_ = clock64(); if (e.lane == 0) atomicAdd(&p.prof[16], (unsigned long long)(t_ - tq0)); })
+    return;
+  }
+  st_shared_f2(stat_smem + e.lane * 8, make_float2(rstd, -mean * rstd));
+  __syncwarp();
   SWB_PROF({ const long long t_ = clock64(); if (e.lane == 0) atomicAdd(&p.prof[13], (unsigned long long)(t_ - tq0)); tq0 = t_; })
   if (p.ln_debug & 2) return;
   if constexpr (single) {
@@ -1248,6 +1336,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), 4 * CG);   // one arrive per epilogue warp (of one group) of every CTA in the pair
+    }
+    if constexpr (EPI == EPI_LN_RES1 && NSUB == 2) {
+      for (int s = 0; s < 2 * S::kEpiWarps; ++s) mbar_init(bars + 512u + 8u * s, 1);   // x tile loads of the epilogue warps
     }
     fence_mbar_init_cluster();
   }
@@ -1510,6 +1601,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     e.to0 = &tmap_o0;
     e.to1 = &tmap_o1;
     e.pending = false;
+    e.xbar = bars + 512u + 16u * (warp - 4);
+    e.xph = 0u;
     SWB_PROF(e.store_wait = 0; long long ew_full = 0; long long ew_drain = 0; long long ew_rest = 0; long long t_rel = 0;)
     const uint32_t stat_smem = scratch0 + S::kEpiWarps * S::kScratchPerWarp + (warp - 4) * 256;
     int it = 0;
@@ -1522,7 +1615,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int r0 = tm * (kBlockM * CG) + static_cast<int>(cta_rank) * kBlockM + quad * 32;
         int lo, hi;
         ln_group_cols<NSUB, CG>(tn * NSUB + grp, lo, hi);
-        ln_prefetch_x(p, r0, p.M - r0, lane, lo, hi);
+        if constexpr (EPI == EPI_LN_RES1 && NSUB == 2) {
+          // the x tiles of this warp's rows start their way into shared memory a whole main loop before they are needed
+          e.row0 = r0;
+          e.rows_valid = p.M - r0 < 0 ? 0 : (p.M - r0 > 32 ? 32 : p.M - r0);
+          lnx_begin_tile(p, e, lo, hi);
+        } else {
+          ln_prefetch_x(p, r0, p.M - r0, lane, lo, hi);
+        }
       }
       uint32_t tacc;                                        // column 0 of the accumulator this warp drains
       if constexpr (NSUB == 1) {

@@ -114,6 +114,11 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* tmap,
       : "memory");
 }
 
+// L2 prefetch of a 2-D tile
+__device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1)
+               : "memory");
+}
 // 2-D tile store smem -> global (bulk async group of the issuing thread); the smem image uses the tensor map's swizzle
 __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -124,6 +129,8 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all bulk stores committed by this thread have finished READING shared memory (the buffer may be overwritten)
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... all but the most recent group
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------- tcgen05 / TMEM
 template <int CG>

@@ -54,7 +54,7 @@ def main():
         for _ in range(200):                      # reach the power-capped steady state
             fn()
         torch.cuda.synchronize()
-        buf = (ctypes.c_ulonglong * 16)()
+        buf = (ctypes.c_ulonglong * 24)()
         prof(buf, 1)
         reps = 50
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -76,6 +76,9 @@ def main():
         if c[11]:
             print(f"{'':13s} fused LayerNorm epilogue per warp-tile: publish (store + fence + atomic) {c[11] / wt:6.0f}, x loads + poll "
                   f"{c[12] / wt:6.0f}, acquire fence + partials + merge {c[13] / wt:6.0f}, apply {(c[7] - c[11] - c[12] - c[13]) / wt:6.0f}")
+        if c[14]:
+            print(f"{'':13s} x by TMA: waiting for the 64-column tiles {c[14] / wt:6.0f}, for the tails {c[15] / wt:6.0f}; the four "
+                  f"in-place updates + stores, measured directly: {c[16] / wt:6.0f}")
         del A, W, out
 
 
