@@ -55,7 +55,7 @@ typedef struct swb200_model {
   int32_t gemm_tile;          /* GEMM tile: 1 = 128x176 single CTA, 2 = 256x176 CTA pair, 3 = 256x352 CTA pair (default) */
   int32_t attn_impl;          /* window attention: 0 = auto (tcgen05 kernel for shifts that are multiples of 8), 1 = mma.sync, 2 = tcgen05 */
   int32_t act_fp16;           /* 16-bit tensor-core operand format of activations AND packed weights: 1 = fp16, 0 = bf16 */
-  int32_t fuse_ln;            /* LayerNorm + modulation + residual add in the GEMM epilogue: bit 0 = wo, bit 1 = w2 (host default 2); 0 = separate kernel */
+  int32_t fuse_ln;            /* LayerNorm + modulation + residual add in the GEMM epilogue: bit 0 = wo, bit 1 = w2 (host default 3); 0 = separate kernel */
   int32_t attn_fp16;          /* with act_fp16 = 0: keep q / k / v and P in fp16 inside the attention (bounded by construction); ignored when act_fp16 */
   int32_t x_single;           /* with act_fp16 = 1: the forecast path keeps the residual stream as ONE fp16 value per element (the hi half of
                                  the [hi | lo] pair; lo is neither read nor written) -- 40 % less residual traffic for one extra 2^-11 rounding

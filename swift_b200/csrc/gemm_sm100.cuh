@@ -1081,12 +1081,21 @@ __device__ __forceinline__ void lnx_apply(const GemmParams& p, EpiCtx& e, int bu
   }
 #pragma unroll
   for (int c = 0; c < NCH; ++c) st_shared_v4(addr(c), xv[c]);
+#ifdef SWB_PROFILE_EPILOGUES
+  if (!(p.ln_debug & 128)) fence_proxy_async_smem();
+  __syncwarp();
+  if (e.lane == 0) {
+    if (!(p.ln_debug & 256)) tma_store_2d(NCH == 8 ? e.to0 : e.to1, base, n0, e.row0);
+    bulk_commit_group();
+  }
+#else
   fence_proxy_async_smem();
   __syncwarp();
   if (e.lane == 0) {
     tma_store_2d(NCH == 8 ? e.to0 : e.to1, base, n0, e.row0);
     bulk_commit_group();
   }
+#endif
   e.pending = true;
 }
 

@@ -29,7 +29,7 @@ class Engine:
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], geom: packing.Geometry, device: torch.device,
                  split_embed: bool = True, split_head: bool = True, max_chunk: int = 8, act_fp16: bool = True,
-                 gemm_tile: int = 3, attn_impl: int = 0, fuse_ln: int = 2, attn_fp16: bool = True,
+                 gemm_tile: int = 3, attn_impl: int = 0, fuse_ln: int = 3, attn_fp16: bool = True,
                  x_single: bool = True):
         if device.type != "cuda":
             raise RuntimeError("swift_b200 runs on CUDA devices only (no CPU fallback)")

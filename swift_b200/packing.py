@@ -112,7 +112,7 @@ def ref_params(sd: Dict[str, torch.Tensor], g: Geometry, device: torch.device):
 
 
 def pack(sd: Dict[str, torch.Tensor], g: Geometry, device: torch.device, split_embed: bool = True,
-         split_head: bool = True, act_fp16: bool = True, gemm_tile: int = 3, attn_impl: int = 0, fuse_ln: int = 2,
+         split_head: bool = True, act_fp16: bool = True, gemm_tile: int = 3, attn_impl: int = 0, fuse_ln: int = 3,
          attn_fp16: bool = True, x_single: bool = True):
     """Returns (``_lib.Model`` struct, dict of device tensors that must stay alive as long as the struct is used).
     The conversions themselves are ``swb200_pack_weights`` (csrc/pack.cu): this function only collects the parameter

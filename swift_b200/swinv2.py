@@ -193,8 +193,9 @@ class SwinV2(_Base):
         self.attn_fp16 = True        # bf16 mode only: q / k / v and P stay fp16 inside the attention kernel (bounded values)
         self.gemm_tile = 3           # 1: 128x176 single CTA, 2: 256x176 CTA pair, 3: 256x352 CTA pair
         self.attn_impl = 0           # 0: tcgen05 attention when the shift is a multiple of 8, 1: mma.sync kernel, 2: tcgen05
-        self.fuse_ln = 2             # LayerNorm + modulation + residual add in the GEMM epilogue: bit 0 = wo, bit 1 = w2; 0 = separate kernel
-                                     # (measured: w2 only is fastest; the short-K wo GEMM becomes epilogue-bound when fused)
+        self.fuse_ln = 3             # LayerNorm + modulation + residual add in the GEMM epilogue: bit 0 = wo, bit 1 = w2; 0 = separate kernel
+                                     # (both since the single-value stream moves x by TMA; with the [hi | lo] pair the short-K wo GEMM is
+                                     # epilogue-bound when fused and 2 is the faster setting)
         self.max_chunk = 8           # samples pushed through the kernels per launch sequence
 
     def _init_weights(self):
