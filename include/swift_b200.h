@@ -193,7 +193,10 @@ SWB200_API int swb200_gemm_qkv(int tile, int act_fp16, int qkv_fp16, const void*
 SWB200_API int swb200_gemm_swiglu(int tile, int act_fp16, const void* A, int lda, const void* W, void* out, int M, int dim, int dff,
                        void* stream);
 /* Patch-embed: x[M,dim] = A*W^T + bias + pos[row % tokens] (bias may be NULL), written as the 16-bit residual pair xhl[M, 2*dim] =
- * [hi | lo] with x = hi + lo (hi is the A operand of the next GEMM, row pitch 2*dim). */
+ * [hi | lo] with x = hi + lo (hi is the A operand of the next GEMM, row pitch 2*dim).
+ * FORMAT WORD: in swb200_gemm_embed, swb200_gemm_ln_residual and swb200_ln_mod_residual the `act_fp16` argument is a bit set:
+ * bit 0 = fp16 operands (else bf16), bit 1 (value 2, needs bit 0) = single-value residual stream: x is the hi half of xhl alone
+ * (still at row pitch 2*dim), rounded to fp16 once per update; the lo half is neither read nor written (swb200_model.x_single). */
 SWB200_API int swb200_gemm_embed(int tile, int act_fp16, const void* A, int lda, const void* W, int K, const float* bias,
                       const float* pos, int tokens, void* xhl, int M, int dim, void* stream);
 /* Fused post-norm residual update (swinv2.py:83-86, :137-138, :100-101, :211-212):

@@ -153,7 +153,12 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
       set_error("gemm_ln_residual: only %d of %d CTA clusters can be co-resident", max_clusters.get(), clusters);
       return SWB_ERR_RESIDENCY;
     }
-    static const bool cooperative = getenv("SWB_LN_NO_COOPERATIVE") == nullptr;     // A/B knob (tools only)
+    // Nsight Compute cannot replay a cooperative cluster launch (it aborts the process with "LaunchFailed"), and it
+    // serialises kernels, so under its injection (the variables ncu exports to the target) the occupancy check above does
+    // speak for the device: launch normally there.  SWB_LN_NO_COOPERATIVE: A/B knob (tools only).
+    static const bool cooperative = getenv("SWB_LN_NO_COOPERATIVE") == nullptr &&
+                                    getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") == nullptr &&
+                                    getenv("NV_NSIGHT_INJECTION_PORT_BASE") == nullptr;
     if (cooperative) {
       attr[1].id = cudaLaunchAttributeCooperative;
       attr[1].val.cooperative = 1;
