@@ -505,10 +505,10 @@ def dominant_kernel_roofline(eng, dev, chunk: int):
     return {"kernel": "gemm_tcgen05_kernel<NSUB=%d,CG=2,EPI_SWIGLU> (w1 up-projection, 42.5%% of FLOPs)" % (2 if eng.model.gemm_tile == 3 else 1), "bound": "tensor",
             "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape (chunk 8) from the committed
-            # ncu --set full capture profiles/r01s_ncu_w1.txt (158.80 + 322.83 MB); algorithmic bytes: A 138 MB + W 12 MB
+            # ncu --set full capture profiles/r02b_ncu_w1.txt (158.84 + 321.65 MB); algorithmic bytes: A 138 MB + W 12 MB
             # + h 369 MB = 519 MB
-            "traffic": 481.63e6 if chunk == 8 else None, "traffic_unit": "bytes/launch (ncu dram read+write)",
-            "traffic_source": "profiles/r01s_ncu_w1.txt (ncu --set full of this kernel at this shape, round 1; not re-measured "
+            "traffic": 480.49e6 if chunk == 8 else None, "traffic_unit": "bytes/launch (ncu dram read+write)",
+            "traffic_source": "profiles/r02b_ncu_w1.txt (ncu --set full of this kernel at this shape, round 2; not re-measured "
                               "in this run: ncu is never run inside a timed bench)",
             "launch_ms": ms, "flops_per_launch": flops, "peak_source": f"{which} burst bf16"}
 
