@@ -203,8 +203,10 @@ SWB200_API int swb200_gemm_embed(int tile, int act_fp16, const void* A, int lda,
  *     x <- x + LayerNorm(A W^T) * gain[b] + bias[b]     on the residual pair xhl[M, 2*dim] (in place), b = row / tokens,
  * A [M, K] (row pitch lda), W [dim, K]; gain / bias fp32 [B, dim].  The row statistics are exchanged between the CTAs
  * that hold the column tiles of a row through `ln_ws` (swb200_ln_workspace_bytes(M, dim) bytes, 256-byte aligned,
- * private to the stream).  `gen` numbers the launches that share ln_ws since its counters were last cleared:
- * launch 0 clears them (a memset node on `stream`), launch g expects the g launches before it to have completed.
+ * private to the stream).  `gen` numbers the launches that share ln_ws since it was last cleared: launch 0 clears it (a
+ * memset node on `stream`); every launch tags the partials it publishes with 1 + gen % 7 (three low mantissa bits of M2), so
+ * consecutive launches on one workspace must use consecutive `gen` values (a launch must never find its own tag left
+ * behind by an earlier one).
  * Every CTA of the grid must be resident: the launcher checks the occupancy and returns -4 (nothing launched) when the
  * device cannot hold the grid -- swb200_forward then runs the same update as GEMM + swb200_ln_mod_residual; do not run
  * other kernels on the device concurrently. */

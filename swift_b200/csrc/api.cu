@@ -443,7 +443,9 @@ SWB200_API int swb200_gemm_ln_residual(int tile, int act_fp16, const void* A, in
   SWB_REQUIRE(tile >= 1 && tile <= 3, "swb200_gemm_ln_residual: tile config must be 1, 2 or 3 (got %d)", tile);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const LnWs l = ln_ws_layout(M, dim);
-  if (gen == 0) SWB_CHECK_CUDA(cudaMemsetAsync(ln_ws, 0, l.counters_bytes, stream));
+  // launch 0 clears every (group, row) slot (tag 0 = "nothing published"); launch g tags its partials 1 + g % 7: a slot is
+  // rewritten by every launch, so the tag it holds when launch g starts is launch g-1's, never launch g's
+  if (gen == 0) SWB_CHECK_CUDA(cudaMemsetAsync(ln_ws, 0, l.total, stream));
   const int tile_n = tile == 3 ? 2 * kUmmaN : kUmmaN;
   const int groups = (dim + tile_n - 1) / tile_n * (tile == 3 ? 2 : 1);
   SWB_REQUIRE(groups <= 12, "swb200_gemm_ln_residual: dim %d needs %d statistics groups (at most 12 are supported)", dim, groups);
@@ -452,10 +454,9 @@ SWB200_API int swb200_gemm_ln_residual(int tile, int act_fp16, const void* A, in
   p.gain = gain;
   p.lnbias = bias;
   p.tokens = tokens;
-  p.ln_counter = static_cast<unsigned*>(ln_ws);
   p.ln_stats = reinterpret_cast<float2*>(static_cast<uint8_t*>(ln_ws) + l.counters_bytes);
   p.ln_stride = l.stride;
-  p.ln_target = static_cast<unsigned>(groups) * static_cast<unsigned>(gen + 1);
+  p.ln_tag = 1u + static_cast<unsigned>(gen) % 7u;
   p.ln_eps = 1e-6f;
   static const int dbg = getenv("SWB_LN_DEBUG") ? atoi(getenv("SWB_LN_DEBUG")) : 0;   // profiling knob, see GemmParams
   p.ln_debug = dbg;

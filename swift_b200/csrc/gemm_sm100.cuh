@@ -88,8 +88,7 @@ struct GemmParams {
   const float* gain;       // [B, N]  gamma * (1 + scale(t))
   const float* lnbias;     // [B, N]  beta * (1 + scale(t)) + shift(t)
   float2* ln_stats;        // [tiles_n * NSUB][ln_stride]  per-row partial (sum, M2) of each 176-column group
-  unsigned* ln_counter;    // [ceil(M / 32)]  groups that have published their partials (monotonic over launches)
-  unsigned ln_target;      // counter value that completes this launch
+  unsigned ln_tag;         // 1..7: generation tag of this launch, carried in the three low mantissa bits of every published M2
   int ln_stride;
   float ln_eps;
   int ln_debug;            // profiling only (SWB_LN_DEBUG): bit 0 = do not wait for the other groups, bit 1 = skip the x update
@@ -833,26 +832,16 @@ __device__ __forceinline__ void epi_group_swiglu(const GemmParams& p, EpiCtx& e,
 // wait on this exchange).  The partials are merged with Chan's formula; the branch is held in registers as fp16 pairs
 // (the same rounding the stand-alone LN kernel sees in fp16 mode) and goes through the coalescing transpose, x hi / lo
 // are read and written in place with full-line accesses.
-__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned ld_relaxed_gpu_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
-// counter += 1 with release semantics at gpu scope: everything this thread -- and, through the __syncwarp before it, its
-// warp -- wrote before is visible to whoever observes the new count (no L1 invalidation, unlike __threadfence())
-__device__ __forceinline__ void red_release_gpu_inc(unsigned* p) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
-}
+// one 64-bit scalar access per (sum, M2) partial: single-copy atomic, so a reader sees a partial whole or not at all
 __device__ __forceinline__ float2 ld_relaxed_gpu_f2(const float2* p) {
-  float2 v;
-  asm volatile("ld.relaxed.gpu.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
-  return v;
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return make_float2(__uint_as_float(static_cast<unsigned>(v)), __uint_as_float(static_cast<unsigned>(v >> 32)));
+}
+__device__ __forceinline__ void st_relaxed_gpu_f2(float2* p, float2 v) {
+  const unsigned long long u = static_cast<unsigned long long>(__float_as_uint(v.x)) |
+                               (static_cast<unsigned long long>(__float_as_uint(v.y)) << 32);
+  asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(u) : "memory");
 }
 __device__ __forceinline__ float2 ld_shared_f2(uint32_t addr) {
   float2 v;
@@ -1168,11 +1157,13 @@ __device__ __forceinline__ void epi_group_lnres(const GemmParams& p, EpiCtx& e, 
   const float m2 = cnt ? fmaxf(s2 - s1 * s1 / fc, 0.f) : 0.f;   // sum (x - mean_p)^2
   // publish, then wait for the other groups of these 32 rows
   SWB_PROF(long long tq0 = clock64();)
+  // The partial IS the message: M2 >= 0 carries this launch's generation tag in its three low mantissa bits (2^-20 relative),
+  // written with one 64-bit store -- no counter, no release, no fence.  Every (group, row) slot is rewritten by every launch
+  // that shares the workspace, so a reader that finds this launch's tag has this launch's partial (launches are ordered
+  // by the stream; the slots start cleared, tag 0, which no launch uses).
   const int row = e.row0 + e.lane;
-  __stcg(p.ln_stats + static_cast<size_t>(sgrp) * p.ln_stride + row, make_float2(sum, m2));
-  __syncwarp();
-  unsigned* counter = p.ln_counter + (e.row0 >> 5);
-  if (e.lane == 0) red_release_gpu_inc(counter);
+  st_relaxed_gpu_f2(p.ln_stats + static_cast<size_t>(sgrp) * p.ln_stride + row,
+                    make_float2(sum, __uint_as_float((__float_as_uint(m2) & ~7u) | p.ln_tag)));
   SWB_PROF({ const long long t_ = clock64(); if (e.lane == 0) atomicAdd(&p.prof[11], (unsigned long long)(t_ - tq0)); tq0 = t_; })
   constexpr bool single = SINGLE;
   // single-value stream: every x load of this warp-tile goes out before the wait; pair: the loads of the first part
@@ -1188,28 +1179,35 @@ __device__ __forceinline__ void epi_group_lnres(const GemmParams& p, EpiCtx& e, 
   } else {
     ln_part_load<8>(p, e, va ? n_lo : n_hi, xhA, xlA);
   }
-  if (!(p.ln_debug & 1) && ld_relaxed_gpu_u32(counter) < p.ln_target) {
+  // every lane polls the partials of its own row until all of them carry this launch's tag (gpu-scope loads: L2)
+  constexpr int kMaxGroups = 12;
+  float2 part[kMaxGroups];
+  SWB_PROF({ const long long t_ = clock64(); if (e.lane == 0) atomicAdd(&p.prof[12], (unsigned long long)(t_ - tq0)); tq0 = t_; })
+  {
     const long long t0 = clock64();
-    while (ld_relaxed_gpu_u32(counter) < p.ln_target) {
-      __nanosleep(32);
+    for (;;) {
+      bool ok = true;
+#pragma unroll
+      for (int s = 0; s < kMaxGroups; ++s) {
+        part[s] = make_float2(0.f, 0.f);
+        if (s < nslots) {
+          part[s] = ld_relaxed_gpu_f2(p.ln_stats + static_cast<size_t>(s) * p.ln_stride + row);
+          ok = ok && ((__float_as_uint(part[s].y) & 7u) == p.ln_tag);
+        }
+      }
+      if (__all_sync(0xffffffffu, ok) || (p.ln_debug & 1)) break;
+      __nanosleep(20);
       if (clock64() - t0 > SWB_WATCHDOG_CYCLES) {
-        printf("[swift_b200] LayerNorm statistics watchdog: block %d warp %d rows %d.. (%u of %u)\n", (int)blockIdx.x,
-               (int)(threadIdx.x >> 5), e.row0, ld_acquire_gpu_u32(counter), p.ln_target);
+        if (e.lane == 0)
+          printf("[swift_b200] LayerNorm statistics watchdog: block %d warp %d rows %d.. (tag %u)\n", (int)blockIdx.x,
+                 (int)(threadIdx.x >> 5), e.row0, p.ln_tag);
         __trap();
       }
     }
-  }
-  SWB_PROF({ const long long t_ = clock64(); if (e.lane == 0) atomicAdd(&p.prof[12], (unsigned long long)(t_ - tq0)); tq0 = t_; })
-  // The partials are read with gpu-scope loads (L2, never L1) that are ISSUED after the poll above has seen the final count:
-  // an SM does not speculate loads past the branch that consumes the polled value, and every publisher's statistics were
-  // visible at gpu scope before its release-increment.  A fence.acq_rel here would add nothing but an L1 invalidation
-  // (CCTL.IVALL: the gain / bias rows would miss L1 in every part) and a wait for the x loads in flight.
-  // merge the partials (Chan et al.): mean, M2 over all N columns
-  constexpr int kMaxGroups = 12;
-  float2 part[kMaxGroups];
 #pragma unroll
-  for (int s = 0; s < kMaxGroups; ++s)
-    part[s] = s < nslots ? ld_relaxed_gpu_f2(p.ln_stats + static_cast<size_t>(s) * p.ln_stride + row) : make_float2(0.f, 0.f);
+    for (int s = 0; s < kMaxGroups; ++s) part[s].y = __uint_as_float(__float_as_uint(part[s].y) & ~7u);
+  }
+  // merge the partials (Chan et al.): mean, M2 over all N columns
   float tot = 0.f;
 #pragma unroll
   for (int s = 0; s < kMaxGroups; ++s) tot += part[s].x;
