@@ -295,6 +295,12 @@ SWB200_API size_t swb200_scm_target_scratch_bytes(int B);
 SWB200_API int swb200_scm_tangent_target(const float* F, const float* dF, const float* x_t, const float* dxt, const float* t, float r,
                               float sigma_data, const float* w_var, const float* w_lat, int B, int C, int H, int W,
                               float* g, float* cot, float* loss, void* scratch, size_t scratch_bytes, void* stream);
+/* SCMLoss with a logvar head (training/loss.py:227-232, :252-258): L = mean_{b,h,w} sum_c [exp(-logvar_b) w g^2 + logvar_b];
+ * cot = exp(-logvar_b) * (-2 w g) / (B H W), dlogvar [B] = dL/dlogvar_b = (C H W - exp(-logvar_b) sum_{c,h,w} w g^2) / (B H W). */
+SWB200_API int swb200_scm_tangent_target_logvar(const float* F, const float* dF, const float* x_t, const float* dxt, const float* t,
+                                     float r, float sigma_data, const float* w_var, const float* w_lat, int B, int C, int H,
+                                     int W, const float* logvar, float* g, float* cot, float* loss, float* dlogvar,
+                                     void* scratch, size_t scratch_bytes, void* stream);
 
 /* ---- reverse mode: the grad-enabled forward + backward of the sCM training step ---------------------------
  * Reference: `F_x = net(x_t / sigma_d, t, condition, auxiliary)` under autograd (training/loss.py:226-232) followed by
@@ -397,6 +403,16 @@ SWB200_API size_t swb200_conditioning_backward_scratch_bytes(const swb200_model*
 SWB200_API int swb200_conditioning_backward(const swb200_model* m, const float* aux, int B, const void* fwd_scratch,
                                  const float* dgain, const float* dbias, const swb200_cond_grads* grads, int accumulate,
                                  void* scratch, size_t scratch_bytes, void* stream);
+/* The same with a logvar head (models/swinv2.py:281, :326-327: logvar = logvar_embed(c), c the conditioning vector): lv_w [dim]
+ * its weight, dlogvar [B] = dL/dlogvar; adds dlogvar_b * lv_w to the gradient of c before the latent MLP is differentiated and
+ * writes (or accumulates) the head's own gradients g_lv_w [dim], g_lv_b [1].  lv_w = dlogvar = NULL: no head. */
+SWB200_API int swb200_conditioning_backward_logvar(const swb200_model* m, const float* aux, int B, const void* fwd_scratch,
+                                        const float* dgain, const float* dbias, const swb200_cond_grads* gr, int accumulate,
+                                        void* scratch, size_t scratch_bytes, const float* lv_w, const float* dlogvar,
+                                        float* g_lv_w, float* g_lv_b, void* stream);
+/* logvar [B] = lv_w . c_b + lv_b from the forward scratch of swb200_conditioning (same (t, aux) batch, untouched since). */
+SWB200_API int swb200_logvar_head(const swb200_model* m, const void* fwd_scratch, const float* lv_w, const float* lv_b, int B,
+                       float* logvar, void* stream);
 /* Unit-test entry points of the reverse-mode kernels (see swift_b200/csrc/kernels.h for the argument meaning). */
 SWB200_API int swb200_gemm_splitk(int tile, const void* A, int lda, const void* W, int ldw, float* partials, int ldo, int M,
                        int N, int K_per_split, int splits, void* stream);

@@ -10,7 +10,11 @@ The loss value is a function of the detached tangent target ``g`` only,
     L = mean_{b,h,w} sum_c  w_var[c] w_lat[h] (F - sg(F) - g)^2 = mean sum w g^2,        dL/dF = -2 w g / (B H W),
 
 so the reverse pass of the training step starts from ``cot = dL/dF``; everything up to ``cot`` needs the network forward
-and its forward-mode tangent only (no reverse mode).  ``logvar`` = 0 (``model/swinv2.yaml:8``: logvar off).
+and its forward-mode tangent only (no reverse mode).  With a logvar head (``logvar: true``; loss.py:227-232, :252-258; off in
+``model/swinv2.yaml:8``) the grad-enabled call returns (F_x, logvar [B]) and
+
+    L = mean_{b,h,w} sum_c [exp(-logvar_b) w g^2 + logvar_b],   dL/dF = -2 exp(-logvar_b) w g / (B H W),
+    dL/dlogvar_b = (C H W - exp(-logvar_b) sum_{c,h,w} w g^2) / (B H W).
 """
 from __future__ import annotations
 
@@ -62,7 +66,7 @@ def scm_tangent_target(F: torch.Tensor, dF: torch.Tensor, x_t: torch.Tensor, dxt
 
 
 def scm_loss(net: Callable, x: torch.Tensor, t: torch.Tensor, z: torch.Tensor, step: int, tangent_warmup_kimg: int,
-             w_lat: torch.Tensor, w_var: torch.Tensor, sigma_data: float = 1.0) -> Dict[str, torch.Tensor]:
+             w_lat: torch.Tensor, w_var: torch.Tensor, sigma_data: float = 1.0, logvar=None) -> Dict[str, torch.Tensor]:
     """loss.py:192-260 as a deterministic function of the draws (t = atan(tau / sigma_d) [B,1,1,1], z = sigma_d * N(0,1)).
 
     ``net(x_in, t_flat) -> F`` is the denoiser with condition / auxiliary bound (the reference's ``wrapper``, :213-214);
@@ -76,8 +80,17 @@ def scm_loss(net: Callable, x: torch.Tensor, t: torch.Tensor, z: torch.Tensor, s
     F, dF = F.detach(), dF.detach()
     g = scm_tangent_target(F, dF, x_t, dxt_dt, cos_t, sin_t, tangent_warmup(step, tangent_warmup_kimg), sigma_data)
     w = w_var * w_lat
+    bhw = g.shape[0] * g.shape[2] * g.shape[3]
+    if logvar is not None:                                              # :227-232, :252-258 (``logvar`` [B], detached values)
+        lv = logvar.detach().reshape(-1, 1, 1, 1).to(g.dtype)
+        e = torch.exp(-lv)
+        loss = (e * (w * g.square()) + lv).sum(dim=1).mean()
+        cot = -2.0 * e * w * g / bhw
+        s_b = (w * g.square()).sum(dim=(1, 2, 3))
+        dlogvar = (g.shape[1] * g.shape[2] * g.shape[3] - e.flatten() * s_b) / bhw
+        return {"loss": loss, "cot": cot, "g": g, "F": F, "dF": dF, "x_t": x_t, "dlogvar": dlogvar}
     loss = (w * g.square()).sum(dim=1).mean()                           # :253-260 with F - sg(F) = 0, logvar = 0
-    cot = -2.0 * w * g / (g.shape[0] * g.shape[2] * g.shape[3])
+    cot = -2.0 * w * g / bhw
     return {"loss": loss, "cot": cot, "g": g, "F": F, "dF": dF, "x_t": x_t}
 
 
@@ -93,3 +106,21 @@ def scm_parameter_gradients(net_of: Callable, params: Dict[str, torch.Tensor], x
     F = net_of(leaf)(out["x_t"] / sigma_data, t.flatten())
     F.backward(out["cot"])
     return {k: v.grad for k, v in leaf.items() if v.grad is not None}
+
+
+def scm_parameter_gradients_logvar(net_of: Callable, net_lv_of: Callable, params: Dict[str, torch.Tensor], x: torch.Tensor,
+                                   t: torch.Tensor, z: torch.Tensor, step: int, tangent_warmup_kimg: int, w_lat: torch.Tensor,
+                                   w_var: torch.Tensor, sigma_data: float = 1.0) -> Dict[str, torch.Tensor]:
+    """``scm_parameter_gradients`` for a model with a logvar head: ``net_lv_of(p)`` returns ``(x_in, t_flat) -> (F, logvar)``
+    (the grad-enabled call of loss.py:222-232).  Both outputs receive their cotangents: dL/dF_x and dL/dlogvar."""
+    with torch.no_grad():
+        _, lv = net_lv_of(params)(torch.zeros_like(x), t.flatten())      # logvar depends on (t, aux) only
+    out = scm_loss(net_of(params), x, t, z, step, tangent_warmup_kimg, w_lat, w_var, sigma_data, logvar=lv)
+    leaf = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+    F, lv2 = net_lv_of(leaf)(out["x_t"] / sigma_data, t.flatten())
+    torch.autograd.backward([F, lv2], [out["cot"], out["dlogvar"].to(lv2.dtype)])
+    grads = {k: v.grad for k, v in leaf.items() if v.grad is not None}
+    grads["__loss__"] = out["loss"].detach()
+    grads["__dlogvar__"] = out["dlogvar"].detach()
+    grads["__cot__"] = out["cot"].detach()
+    return grads

@@ -777,6 +777,23 @@ SWB200_API int swb200_scm_tangent_target(const float* F, const float* dF, const 
                                    scratch_bytes, static_cast<cudaStream_t>(stream));
 }
 
+SWB200_API int swb200_scm_tangent_target_logvar(const float* F, const float* dF, const float* x_t, const float* dxt,
+                                                const float* t, float r, float sigma_data, const float* w_var,
+                                                const float* w_lat, int B, int C, int H, int W, const float* logvar, float* g,
+                                                float* cot, float* loss, float* dlogvar, void* scratch, size_t scratch_bytes,
+                                                void* stream) {
+  SWB_REQUIRE(F && dF && x_t && dxt && t && g && cot && loss && scratch && logvar && dlogvar,
+              "swb200_scm_tangent_target_logvar: NULL pointer");
+  return launch_scm_tangent_target(F, dF, x_t, dxt, t, r, sigma_data, w_var, w_lat, B, C, H, W, g, cot, loss, scratch,
+                                   scratch_bytes, static_cast<cudaStream_t>(stream), logvar, dlogvar);
+}
+
+SWB200_API int swb200_logvar_head(const swb200_model* m, const void* fwd_scratch, const float* lv_w, const float* lv_b, int B,
+                                  float* logvar, void* stream) {
+  SWB_REQUIRE(m && fwd_scratch && lv_w && lv_b && logvar && B > 0, "swb200_logvar_head: NULL pointer");
+  return launch_logvar_head(static_cast<const float*>(fwd_scratch), lv_w, lv_b, B, m->dim, logvar, static_cast<cudaStream_t>(stream));
+}
+
 SWB200_API int swb200_debug_saturation(uint64_t* counters) {
   g_sat_counters = reinterpret_cast<unsigned long long*>(counters);
   return SWB_OK;
@@ -1181,7 +1198,16 @@ SWB200_API size_t swb200_conditioning_backward_scratch_bytes(const swb200_model*
 SWB200_API int swb200_conditioning_backward(const swb200_model* m, const float* aux, int B, const void* fwd_scratch,
                                             const float* dgain, const float* dbias, const swb200_cond_grads* gr, int accumulate,
                                             void* scratch, size_t scratch_bytes, void* stream) {
+  return swb200_conditioning_backward_logvar(m, aux, B, fwd_scratch, dgain, dbias, gr, accumulate, scratch, scratch_bytes,
+                                             nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+SWB200_API int swb200_conditioning_backward_logvar(const swb200_model* m, const float* aux, int B, const void* fwd_scratch,
+                                                   const float* dgain, const float* dbias, const swb200_cond_grads* gr,
+                                                   int accumulate, void* scratch, size_t scratch_bytes, const float* lv_w,
+                                                   const float* dlogvar, float* g_lv_w, float* g_lv_b, void* stream) {
   int rc = validate(m);
+  SWB_REQUIRE((lv_w == nullptr) == (dlogvar == nullptr), "conditioning_backward: lv_w and dlogvar come together");
   if (rc) return rc;
   SWB_REQUIRE(B > 0 && fwd_scratch && dgain && dbias && gr && scratch, "conditioning_backward: NULL argument");
   SWB_REQUIRE(gr->l1_w && gr->l1_b && gr->l2_w && gr->l2_b && gr->mod_w && gr->mod_b && gr->ln_gamma && gr->ln_beta,
@@ -1212,7 +1238,8 @@ SWB200_API int swb200_conditioning_backward(const swb200_model* m, const float* 
   g.ln_beta = gr->ln_beta;
   const float* aux_eff = (m->aux_dim > 0 && m->aux_w != nullptr) ? aux : nullptr;
   return launch_conditioning_bwd(w, g, aux_eff, static_cast<const float*>(fwd_scratch), dgain, dbias, B, m->dim, 2 * m->depth,
-                                 static_cast<float*>(scratch), accumulate, static_cast<cudaStream_t>(stream));
+                                 static_cast<float*>(scratch), accumulate, static_cast<cudaStream_t>(stream), lv_w, dlogvar,
+                                 g_lv_w, g_lv_b);
 }
 
 // ---- unit-test entry points of the reverse-mode kernels

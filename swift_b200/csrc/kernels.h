@@ -102,7 +102,11 @@ int launch_sum_over_samples(const float* dx, int B, long long per, float* out, i
 size_t conditioning_bwd_scratch_floats(int B, int D, int L);
 int launch_conditioning_bwd(const CondWeights& w, const CondGrads& g, const float* aux, const float* fwd_scratch,
                             const float* dgain, const float* dbias, int B, int D, int L, float* scratch, int accumulate,
-                            cudaStream_t stream);
+                            cudaStream_t stream, const float* lv_w = nullptr, const float* dlogvar = nullptr,
+                            float* g_lv_w = nullptr, float* g_lv_b = nullptr);
+// logvar[b] = lv_w . c_b + lv_b on the conditioning vector c kept in the forward scratch of launch_conditioning
+int launch_logvar_head(const float* fwd_scratch, const float* lv_w, const float* lv_b, int B, int D, float* logvar,
+                       cudaStream_t stream);
 int launch_attention_bwd(const void* qkv, const void* O, const void* dO, const float* invn, const float* qscale, void* dqkv,
                          float* Lbuf, float* Dbuf, float* ds_part, int B, int gh, int gw, int heads, int hd, int pad,
                          int shift_h, int shift_w, cudaStream_t stream);
@@ -135,6 +139,7 @@ int launch_scm_noised_inputs(const float* x, const float* z, const float* t, int
 size_t scm_target_scratch_bytes(int B);
 int launch_scm_tangent_target(const float* F, const float* dF, const float* x_t, const float* dxt, const float* t, float r,
                               float sigma_data, const float* w_var, const float* w_lat, int B, int C, int H, int W, float* g,
-                              float* cot, float* loss, void* scratch, size_t scratch_bytes, cudaStream_t stream);
+                              float* cot, float* loss, void* scratch, size_t scratch_bytes, cudaStream_t stream,
+                              const float* logvar = nullptr, float* dlogvar = nullptr);
 
 }  // namespace swb

@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(kScmThreads) scm_target_finish_kernel(float4* 
                                                                         const double* __restrict__ part, int nparts,
                                                                         const float* __restrict__ w_var,
                                                                         const float* __restrict__ w_lat, int C, int H, int W4,
-                                                                        float inv_bhw, double* __restrict__ loss_part) {
+                                                                        float inv_bhw, const float* __restrict__ logvar,
+                                                                        double* __restrict__ loss_part) {
   __shared__ double red[kScmThreads / 32];
   __shared__ float inv_den;
   const int b = blockIdx.y;
@@ -99,6 +100,8 @@ __global__ void __launch_bounds__(kScmThreads) scm_target_finish_kernel(float4* 
   }
   __syncthreads();
   const float inv = inv_den;
+  // logvar head (loss.py:227-232, :252-258): the squared term of sample b is weighted by exp(-logvar_b)
+  const float elv = logvar ? expf(-__ldg(logvar + b)) : 1.0f;
   const size_t base = static_cast<size_t>(b) * n4;
   const size_t hw4 = static_cast<size_t>(H) * W4;
   double acc = 0.0;
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(kScmThreads) scm_target_finish_kernel(float4* 
     float4 v = g[base + i];
     v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
     g[base + i] = v;
-    const float k = -2.0f * w * inv_bhw;
+    const float k = -2.0f * w * inv_bhw * elv;
     cot[base + i] = make_float4(k * v.x, k * v.y, k * v.z, k * v.w);
     acc += static_cast<double>(w) * (static_cast<double>(v.x * v.x + v.y * v.y) + static_cast<double>(v.z * v.z + v.w * v.w));
   }
@@ -117,11 +120,24 @@ __global__ void __launch_bounds__(kScmThreads) scm_target_finish_kernel(float4* 
   if (threadIdx.x == 0) loss_part[static_cast<size_t>(b) * gridDim.x + blockIdx.x] = tot;
 }
 
-__global__ void scm_loss_sum_kernel(const double* __restrict__ loss_part, int n, float inv_bhw, float* __restrict__ loss) {
+// loss = mean_{b,h,w} sum_c [exp(-lv_b) w g^2 + lv_b];  dL/dlv_b = (-exp(-lv_b) S_b + C H W) / (B H W),  S_b = sum_{c,h,w} w g^2
+// (fixed summation order; without a logvar head lv = 0 and the second term vanishes)
+__global__ void scm_loss_sum_kernel(const double* __restrict__ loss_part, int B, int nb, float inv_bhw, double chw,
+                                    const float* __restrict__ logvar, float* __restrict__ dlogvar, float* __restrict__ loss) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double s = 0.0;
-    for (int k = 0; k < n; ++k) s += loss_part[k];
-    *loss = static_cast<float>(s * static_cast<double>(inv_bhw));
+    double tot = 0.0;
+    for (int b = 0; b < B; ++b) {
+      double sb = 0.0;
+      for (int k = 0; k < nb; ++k) sb += loss_part[static_cast<size_t>(b) * nb + k];
+      if (logvar) {
+        const double lv = static_cast<double>(logvar[b]), e = exp(-lv);
+        tot += e * sb + chw * lv;
+        if (dlogvar) dlogvar[b] = static_cast<float>((chw - e * sb) * static_cast<double>(inv_bhw));
+      } else {
+        tot += sb;
+      }
+    }
+    *loss = static_cast<float>(tot * static_cast<double>(inv_bhw));
   }
 }
 
@@ -146,7 +162,8 @@ size_t scm_target_scratch_bytes(int B) { return static_cast<size_t>(2) * B * kSc
 
 int launch_scm_tangent_target(const float* F, const float* dF, const float* x_t, const float* dxt, const float* t, float r,
                               float sigma_data, const float* w_var, const float* w_lat, int B, int C, int H, int W, float* g,
-                              float* cot, float* loss, void* scratch, size_t scratch_bytes, cudaStream_t stream) {
+                              float* cot, float* loss, void* scratch, size_t scratch_bytes, cudaStream_t stream,
+                              const float* logvar, float* dlogvar) {
   SWB_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && W % 4 == 0, "scm_tangent_target: need B, C, H > 0 and W a multiple of 4 (W=%d)", W);
   SWB_REQUIRE(scratch_bytes >= scm_target_scratch_bytes(B), "scm_tangent_target: scratch of %zu bytes, need %zu", scratch_bytes,
               scm_target_scratch_bytes(B));
@@ -161,9 +178,9 @@ int launch_scm_tangent_target(const float* F, const float* dF, const float* x_t,
                                                          t, r, sigma_data, n4, reinterpret_cast<float4*>(g), part);
   SWB_CHECK_CUDA(cudaGetLastError());
   scm_target_finish_kernel<<<grid, kScmThreads, 0, stream>>>(reinterpret_cast<float4*>(g), reinterpret_cast<float4*>(cot), part, nb,
-                                                            w_var, w_lat, C, H, W / 4, inv_bhw, loss_part);
+                                                            w_var, w_lat, C, H, W / 4, inv_bhw, logvar, loss_part);
   SWB_CHECK_CUDA(cudaGetLastError());
-  scm_loss_sum_kernel<<<1, 32, 0, stream>>>(loss_part, B * nb, inv_bhw, loss);
+  scm_loss_sum_kernel<<<1, 32, 0, stream>>>(loss_part, B, nb, inv_bhw, static_cast<double>(C) * H * W, logvar, dlogvar, loss);
   SWB_CHECK_CUDA(cudaGetLastError());
   return SWB_OK;
 }

@@ -603,9 +603,25 @@ size_t conditioning_bwd_scratch_floats(int B, int D, int L) {
 }
 
 // fwd_scratch: what launch_conditioning left behind: emb [B,D] | h1 [B,D] | c [B,D] | mod [B, L*2D]
+// dc[b, k] += dlv[b] * lv_w[k]: the logvar head's contribution to the gradient of the conditioning vector
+__global__ void __launch_bounds__(256) logvar_dcond_kernel(float* __restrict__ dc, const float* __restrict__ dlv,
+                                                           const float* __restrict__ lv_w, int B, int D) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= B * D) return;
+  dc[i] = fmaf(__ldg(dlv + i / D), __ldg(lv_w + i % D), dc[i]);
+}
+
+int launch_logvar_head(const float* fwd_scratch, const float* lv_w, const float* lv_b, int B, int D, float* logvar,
+                       cudaStream_t stream) {
+  const float* c = fwd_scratch + static_cast<size_t>(2) * B * D;          // [emb | h1 | c | mod ...]
+  gemv_plain_kernel<<<1, 256, 0, stream>>>(lv_w, lv_b, c, logvar, 1, D, B);
+  SWB_CHECK_CUDA(cudaGetLastError());
+  return SWB_OK;
+}
+
 int launch_conditioning_bwd(const CondWeights& w, const CondGrads& g, const float* aux, const float* fwd_scratch,
                             const float* dgain, const float* dbias, int B, int D, int L, float* scratch, int accumulate,
-                            cudaStream_t stream) {
+                            cudaStream_t stream, const float* lv_w, const float* dlogvar, float* g_lv_w, float* g_lv_b) {
   const float* emb = fwd_scratch;
   const float* h1 = emb + static_cast<size_t>(B) * D;
   const float* c = h1 + static_cast<size_t>(B) * D;
@@ -627,6 +643,11 @@ int launch_conditioning_bwd(const CondWeights& w, const CondGrads& g, const floa
   };
   int rc = gemv_t(w.mod_w, dmod, v0, NM, D);                                       // v0 = dc
   if (rc) return rc;
+  if (lv_w != nullptr && dlogvar != nullptr) {
+    // logvar = logvar_embed(c) (models/swinv2.py:326-327): its weight / bias gradients and its share of dc
+    if (g_lv_w != nullptr) outer_accum_kernel<<<1, 256, 0, stream>>>(dlogvar, c, g_lv_w, g_lv_b, 1, D, B, accumulate);
+    logvar_dcond_kernel<<<(B * D + 255) / 256, 256, 0, stream>>>(v0, dlogvar, lv_w, B, D);
+  }
   gemv_plain_kernel<<<(D + 7) / 8, 256, 0, stream>>>(w.l2_w, w.l2_b, h1, z, D, D, B);      // z2
   silu_bwd_kernel<<<(B * D + 255) / 256, 256, 0, stream>>>(v0, z, v1, B * D);               // v1 = dz2
   outer_accum_kernel<<<D, 256, 0, stream>>>(v1, h1, g.l2_w, g.l2_b, D, D, B, accumulate);

@@ -119,6 +119,17 @@ class Engine:
         self.launches += 5
         return (gain, bias, cond) if want_cond else (gain, bias)
 
+    def logvar_head(self, weight: torch.Tensor, bias: torch.Tensor, B: int) -> torch.Tensor:
+        """logvar [B] = logvar_embed(c) (models/swinv2.py:326-327) for the batch of the last ``conditioning`` call (its scratch
+        holds the conditioning vector c); weight [1, dim] / bias [1] fp32 on this device."""
+        lv = torch.empty(B, device=self.device, dtype=torch.float32)
+        w = weight.detach().to(torch.float32).reshape(-1).contiguous()
+        b = bias.detach().to(torch.float32).reshape(-1).contiguous()
+        _lib.check(self.lib.swb200_logvar_head(C.byref(self.model), self._cond_scratch.data_ptr(), w.data_ptr(), b.data_ptr(), B,
+                                               lv.data_ptr(), self._stream()), "logvar_head")
+        self.launches += 1
+        return lv
+
     # ------------------------------------------------------------------ forward
     def forward(self, x0: torch.Tensor, x1: Optional[torch.Tensor], gain: torch.Tensor, bias: torch.Tensor,
                 out: Optional[torch.Tensor] = None, scale0: float = 1.0, xt: Optional[torch.Tensor] = None,

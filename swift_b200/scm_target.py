@@ -9,7 +9,7 @@
     L   = mean sum w (F_x - sg(F_x) - g)^2                                           :253-260
 
 Because F_x - sg(F_x) == 0, the loss value and its gradient with respect to the network output depend on g only:
-``dL/dF_x = -2 w g / (B H W)``.  ``scm_output_cotangent`` returns exactly that, from ONE stacked primal + tangent pass of
+``dL/dF_x = -2 w g / (B H W)`` (times exp(-logvar_b) for a model with a logvar head, which also receives dL/dlogvar).  ``scm_output_cotangent`` returns exactly that, from ONE stacked primal + tangent pass of
 the CUDA engine (``swb200_forward_jvp``; the reference runs the network twice here).  ``scm_backward`` then runs the
 grad-enabled forward and ``F_x.backward(cot)`` through the reverse-mode path of ``training.py``.
 """
@@ -55,23 +55,30 @@ def variable_weights(variables: Sequence[str], device=None) -> torch.Tensor:
 @torch.no_grad()
 def scm_output_cotangent(net, x: torch.Tensor, t: torch.Tensor, z: torch.Tensor, step: int,
                          condition: Optional[torch.Tensor] = None, auxiliary=None, tangent_warmup_kimg: int = 0,
-                         w_lat: Optional[torch.Tensor] = None, w_var: Optional[torch.Tensor] = None
-                         ) -> Dict[str, torch.Tensor]:
+                         w_lat: Optional[torch.Tensor] = None, w_var: Optional[torch.Tensor] = None,
+                         logvar=None) -> Dict[str, torch.Tensor]:
     """x [B, C, H, W] targets, t = atan(tau / sigma_d) ([B] or [B,1,1,1]), z = sigma_d * N(0,1) like x (the draws of
     loss.py:196-200, made by the caller), ``net`` a PassPrecond around ``swift_b200.swinv2.SwinV2`` on a CUDA device.
     Returns {"loss", "cot" (= dL/dF_x), "g", "F", "dF", "x_t"}; all detached fp32.
 
     Three C-ABI calls: ``swb200_scm_noised_inputs`` (x_t, dx_t/dt, v_x, v_t), ``swb200_forward_jvp`` (the concat with the
     condition and the 1/sigma_d scaling happen in its patch gather) and ``swb200_scm_tangent_target`` (g, its per-sample
-    normalisation, cot and the loss)."""
+    normalisation, cot and the loss).
+
+    Models with a logvar head (``logvar: true``; loss.py:227-232, :252-258) need ``logvar``: a [B] tensor, or a callable
+    ``x_t -> [B] tensor`` evaluated once the noised inputs exist (the grad-enabled forward that produces it takes x_t).  The
+    sample's squared term is then weighted by exp(-logvar_b), ``+ logvar_b`` is added, and the dict also carries
+    ``"dlogvar"`` = dL/dlogvar [B] (``swb200_scm_tangent_target_logvar``)."""
     inner = getattr(net, "module", net)
     model = inner.model
     if not hasattr(model, "engine"):
         raise TypeError("scm_output_cotangent needs swift_b200.swinv2.SwinV2 as net.model (there is no fallback path)")
-    if getattr(model, "logvar_embed", None) is not None:
-        # loss.py:221-257: with logvar the term is weighted by exp(-logvar) and + logvar is added; not implemented here, and a
-        # silently different objective would be worse than an error (model/swinv2.yaml: logvar: false)
-        raise NotImplementedError("SCMLoss with a logvar head is not implemented on the CUDA path")
+    has_lv = getattr(model, "logvar_embed", None) is not None
+    if has_lv and logvar is None:
+        # a silently different objective would be worse than an error
+        raise RuntimeError("this model has a logvar head: scm_output_cotangent needs logvar (a [B] tensor or a callable of x_t)")
+    if not has_lv and logvar is not None:
+        raise RuntimeError("logvar given for a model without a logvar head")
     eng = model.engine()
     lib, dev = eng.lib, x.device
     stream = torch.cuda.current_stream().cuda_stream
@@ -102,6 +109,15 @@ def scm_output_cotangent(net, x: torch.Tensor, t: torch.Tensor, z: torch.Tensor,
     loss = torch.empty((), device=dev, dtype=torch.float32)
     need = lib.swb200_scm_target_scratch_bytes(B)
     scratch = torch.empty(need // 8, dtype=torch.float64, device=dev)
+    if has_lv:
+        lv = logvar(x_t) if callable(logvar) else logvar
+        lv = lv.detach().to(device=dev, dtype=torch.float32).reshape(B).contiguous()
+        dlv = torch.empty_like(lv)
+        _lib.check(lib.swb200_scm_tangent_target_logvar(F.data_ptr(), dF.data_ptr(), x_t.data_ptr(), dxt.data_ptr(), t1.data_ptr(),
+                                                        float(r), sd, _lib.ptr(wv), _lib.ptr(wl), B, C, H, W, lv.data_ptr(),
+                                                        g.data_ptr(), cot.data_ptr(), loss.data_ptr(), dlv.data_ptr(),
+                                                        scratch.data_ptr(), need, stream), "scm_tangent_target_logvar")
+        return {"loss": loss, "cot": cot, "g": g, "F": F, "dF": dF, "x_t": x_t, "logvar": lv, "dlogvar": dlv}
     _lib.check(lib.swb200_scm_tangent_target(F.data_ptr(), dF.data_ptr(), x_t.data_ptr(), dxt.data_ptr(), t1.data_ptr(),
                                              float(r), sd, _lib.ptr(wv), _lib.ptr(wl), B, C, H, W, g.data_ptr(),
                                              cot.data_ptr(), loss.data_ptr(), scratch.data_ptr(), need, stream),
@@ -118,13 +134,23 @@ def scm_backward(net, x: torch.Tensor, t: torch.Tensor, z: torch.Tensor, step: i
     ``SCMLoss(...)(net, x, step, ...).backward()`` leaves (trainer.py:206-214); returns the dict of
     ``scm_output_cotangent`` (``loss`` for logging).  No eager PyTorch module takes part."""
     inner = getattr(net, "module", net)
-    if inner.model.logvar_embed is not None:
-        raise NotImplementedError("SCMLoss with a logvar head (exp(-logvar) weighting, loss.py:221-257) is not implemented; "
-                                  "model/swinv2.yaml has logvar: false")
     if not inner.model.training:
         raise RuntimeError("scm_backward needs net.train(): the reverse-mode path is selected by training mode")
-    out = scm_output_cotangent(net, x, t, z, step, condition=condition, auxiliary=auxiliary, **loss_kwargs)
     sd = float(inner.sigma_data)
+    if inner.model.logvar_embed is not None:
+        # loss.py:222-232: the grad-enabled call returns (F_x, logvar); logvar weights the loss, so that call runs as soon as
+        # x_t exists and both outputs receive their cotangents afterwards
+        held = {}
+
+        def grad_forward(x_t):
+            with torch.enable_grad():
+                held["F_x"], held["logvar"] = net(x_t / sd, t.to(x.device).reshape(-1), condition, auxiliary, return_logvar=True)
+            return held["logvar"]
+
+        out = scm_output_cotangent(net, x, t, z, step, condition=condition, auxiliary=auxiliary, logvar=grad_forward, **loss_kwargs)
+        torch.autograd.backward([held["F_x"], held["logvar"]], [out["cot"], out["dlogvar"]])
+        return out
+    out = scm_output_cotangent(net, x, t, z, step, condition=condition, auxiliary=auxiliary, **loss_kwargs)
     with torch.enable_grad():
         F_x = net(out["x_t"] / sd, t.to(x.device).reshape(-1), condition, auxiliary)
     F_x.backward(out["cot"])

@@ -223,10 +223,7 @@ class SwinV2(_Base):
                 raise RuntimeError("swift_b200.SwinV2 runs on CUDA only: move the module to a B200 with .cuda(); "
                                    "there is no CPU fallback")
             sd = {k: v for k, v in self.state_dict().items()}
-            # single-value fp16 stream: the patch-embed operand is one fp16 value as well (its output is rounded to fp16 anyway:
-            # Swift-B one step 1.93e-3 -> 2.05e-3, patch gather + embed GEMM 25 % faster); bf16 mode keeps the [hi | lo] operand
-            split_embed = self.split_embed and not (self.act_fp16 and self.x_single)
-            self._engine = Engine(sd, self.geometry, dev, split_embed, self.split_head, self.max_chunk,
+            self._engine = Engine(sd, self.geometry, dev, self.split_embed, self.split_head, self.max_chunk,
                                   self.act_fp16, self.gemm_tile, self.attn_impl, self.fuse_ln, self.attn_fp16,
                                   self.x_single)
             self._engine_key = key
@@ -258,9 +255,6 @@ class SwinV2(_Base):
         B = x.shape[0]
         if self.training and torch.is_grad_enabled() and not jvp:
             # reverse mode: the grad-enabled forward of training/loss.py:227 (bf16 operands, activation tape kept)
-            if self.logvar_embed is not None:
-                raise NotImplementedError("the reverse-mode path does not implement the logvar head (model/swinv2.yaml: "
-                                          "logvar: false); SCMLoss with logvar would train on a different objective")
             if torch.is_autocast_enabled():
                 x = x.float()
             x32 = x.to(torch.float32).contiguous()
@@ -274,7 +268,8 @@ class SwinV2(_Base):
                     aux32 = aux32.expand(B, -1)
                 aux32 = aux32.contiguous()
             names = tuple(n for n, _ in self.named_parameters())
-            return DenoiserTrainFn.apply(x32, t32.reshape(B).contiguous(), aux32, self, names, *self.parameters())
+            want_lv = self.logvar_embed is not None and return_logvar
+            return DenoiserTrainFn.apply(x32, t32.reshape(B).contiguous(), aux32, self, names, want_lv, *self.parameters())
         if not jvp:                                                # (a detach would drop the forward-mode tangents)
             x, t = x.detach(), t.detach()
         x = x.to(torch.float32).contiguous()
@@ -296,8 +291,7 @@ class SwinV2(_Base):
             return _DenoiserFn.apply(x, t, aux, self)        # (the engine is built inside the node, below any transform)
         eng = self.engine()
         want_lv = self.logvar_embed is not None and return_logvar
-        cond = eng.conditioning(t, aux, want_cond=want_lv)
+        cond = eng.conditioning(t, aux)
+        lv = eng.logvar_head(self.logvar_embed.weight, self.logvar_embed.bias, B) if want_lv else None   # models/swinv2.py:326-328
         y = eng.forward(x, None, cond[0], cond[1])
-        if want_lv:                                                # models/swinv2.py:326-328
-            return y, torch.nn.functional.linear(cond[2], self.logvar_embed.weight, self.logvar_embed.bias).squeeze(-1)
-        return y
+        return (y, lv) if want_lv else y

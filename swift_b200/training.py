@@ -37,6 +37,13 @@ class TrainEngine:
             gemm_tile = 2
         with torch.cuda.device(device):
             self.model, self._keep = packing.pack_train(state_dict, geom, device, gemm_tile, attn_impl)
+        # logvar head (models/swinv2.py:281, :326-327): logvar = logvar_embed(c) on the conditioning vector; fp32 copies
+        self.lv_w = self.lv_b = None
+        if "logvar_embed.weight" in state_dict:
+            self.lv_w = state_dict["logvar_embed.weight"].detach().to(device=device, dtype=torch.float32).reshape(-1).contiguous()
+            self.lv_b = state_dict["logvar_embed.bias"].detach().to(device=device, dtype=torch.float32).reshape(-1).contiguous()
+        self._cond = None            # (B, gain, bias, t, aux) of the last conditioning()
+        self.logvar: Optional[torch.Tensor] = None   # [B] of the last conditioning() when the model has the head
         self._tape = None            # (buffer, base, bytes, B)
         self._ws = None
         self._cond_scratch: Optional[torch.Tensor] = None
@@ -79,6 +86,8 @@ class TrainEngine:
               "ln_gamma": z(2 * L, D), "ln_beta": z(2 * L, D)}
         if self.model.base.aux_dim:
             gr["aux_w"], gr["aux_b"] = z(D, g.aux_dim), z(D)
+        if self.lv_w is not None:
+            gr["lv_w"], gr["lv_b"] = z(D), z(1)
         self.grads = gr
         gs = _lib.TrainGrads()
         for n in ("w_qkv", "w_o", "w_1", "w_2", "w_head", "w_embed_t", "b_embed", "pos_embed", "dscale", "dgain", "dbias"):
@@ -90,18 +99,11 @@ class TrainEngine:
         return gr
 
     # ------------------------------------------------------------------ forward
-    def forward(self, x0: torch.Tensor, x1: Optional[torch.Tensor], t: torch.Tensor, aux: Optional[torch.Tensor],
-                scale0: float = 1.0) -> torch.Tensor:
-        """F = SwinV2(cat([x0 * scale0, x1], 1), t, aux) with the activation tape kept for ``backward``."""
+    def conditioning(self, t: torch.Tensor, aux: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        """The conditioning stage of the grad-enabled forward (per-sample gain / bias of every ModulatedNorm; activations kept
+        for the backward).  With a logvar head, returns (and keeps in ``self.logvar``) logvar [B] = logvar_embed(c)."""
         g = self.geom
-        for nm, v in (("x0", x0), ("t", t)) + ((("x1", x1),) if x1 is not None else ()) + ((("aux", aux),) if aux is not None else ()):
-            if not (v.is_cuda and v.dtype == torch.float32 and v.is_contiguous()):
-                raise RuntimeError(f"{nm}: expected a contiguous float32 CUDA tensor (swift_b200 has no CPU fallback)")
-        B, c0 = x0.shape[0], x0.shape[1]
-        c1 = 0 if x1 is None else x1.shape[1]
-        if c0 + c1 != g.in_channels or tuple(x0.shape[2:]) != g.img or t.shape != (B,):
-            raise RuntimeError(f"train forward: inputs {tuple(x0.shape)} (+{c1} channels), t {tuple(t.shape)} do not match the model")
-        tp = C.byref(self.model)
+        B = t.shape[0]
         bp = C.byref(self.model.base)
         gain = torch.empty(2 * g.depth, B, g.dim, device=self.device, dtype=torch.float32)
         bias = torch.empty_like(gain)
@@ -111,6 +113,31 @@ class TrainEngine:
         _lib.check(self.lib.swb200_conditioning(bp, t.data_ptr(), _lib.ptr(aux), B, gain.data_ptr(), bias.data_ptr(), None,
                                                 self._cond_scratch.data_ptr(), self._cond_scratch.numel(), self._stream()),
                    "conditioning")
+        self._cond = (B, gain, bias)
+        self.logvar = None
+        if self.lv_w is not None:
+            self.logvar = torch.empty(B, device=self.device, dtype=torch.float32)
+            _lib.check(self.lib.swb200_logvar_head(bp, self._cond_scratch.data_ptr(), self.lv_w.data_ptr(), self.lv_b.data_ptr(), B,
+                                                   self.logvar.data_ptr(), self._stream()), "logvar_head")
+        return self.logvar
+
+    def forward(self, x0: torch.Tensor, x1: Optional[torch.Tensor], t: torch.Tensor, aux: Optional[torch.Tensor],
+                scale0: float = 1.0, reuse_conditioning: bool = False) -> torch.Tensor:
+        """F = SwinV2(cat([x0 * scale0, x1], 1), t, aux) with the activation tape kept for ``backward``.
+        ``reuse_conditioning``: ``conditioning(t, aux)`` has just been called for this batch (logvar models need its output
+        before the loss target can be finished)."""
+        g = self.geom
+        for nm, v in (("x0", x0), ("t", t)) + ((("x1", x1),) if x1 is not None else ()) + ((("aux", aux),) if aux is not None else ()):
+            if not (v.is_cuda and v.dtype == torch.float32 and v.is_contiguous()):
+                raise RuntimeError(f"{nm}: expected a contiguous float32 CUDA tensor (swift_b200 has no CPU fallback)")
+        B, c0 = x0.shape[0], x0.shape[1]
+        c1 = 0 if x1 is None else x1.shape[1]
+        if c0 + c1 != g.in_channels or tuple(x0.shape[2:]) != g.img or t.shape != (B,):
+            raise RuntimeError(f"train forward: inputs {tuple(x0.shape)} (+{c1} channels), t {tuple(t.shape)} do not match the model")
+        tp = C.byref(self.model)
+        if not (reuse_conditioning and self._cond is not None and self._cond[0] == B):
+            self.conditioning(t, aux)
+        _, gain, bias = self._cond
         tape, ws = self._buffers(B)
         y = torch.empty(B, g.out_channels, *g.img, device=self.device, dtype=torch.float32)
         _lib.check(self.lib.swb200_train_forward(tp, x0.data_ptr(), c0, float(scale0), _lib.ptr(x1), c1, B, gain.data_ptr(),
@@ -121,7 +148,8 @@ class TrainEngine:
 
     # ------------------------------------------------------------------ backward
     def backward(self, cot: torch.Tensor, accumulate: bool = False,
-                 on_stage: Optional[Callable[[str, int], None]] = None, cond_exchange=None) -> Dict[str, torch.Tensor]:
+                 on_stage: Optional[Callable[[str, int], None]] = None, cond_exchange=None,
+                 dlogvar: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """Parameter gradients of ``sum(F * cot)`` for the last ``forward``.  ``on_stage(kind, layer)`` is called after
         the kernels of a stage have been enqueued ("head", "layer" l = depth-1 .. 0, "embed", "cond"): the hook for
         overlapping the gradient all-reduce of finished stages with the rest of the backward."""
@@ -153,7 +181,14 @@ class TrainEngine:
             on_stage("embed", -1)
         bp = C.byref(self.model.base)
         dgain, dbias, fwd_scratch, Bc, kind = self.grads["dgain"], self.grads["dbias"], self._cond_scratch, B, "cond"
-        if cond_exchange is not None:
+        if (dlogvar is not None) != (self.lv_w is not None) and dlogvar is not None:
+            raise RuntimeError("dlogvar given for a model without a logvar head")
+        if dlogvar is not None:
+            dlogvar = dlogvar.detach().to(device=self.device, dtype=torch.float32).reshape(B).contiguous()
+        if cond_exchange is not None and dlogvar is not None:
+            dgain, dbias, fwd_scratch, aux, Bc, dlogvar = cond_exchange(self, dgain, dbias, fwd_scratch, aux, B, dlogvar)
+            kind = "cond_replicated"
+        elif cond_exchange is not None:
             # data parallel: instead of all-reducing the conditioning gradients (the 24 modulation Linears alone are 214 MB
             # of fp32), every rank receives every rank's per-sample INPUTS of this stage (a few hundred KB) and evaluates the
             # whole global batch -- the gradients are sums of per-sample outer products, so all ranks get the same, already
@@ -162,9 +197,19 @@ class TrainEngine:
             kind = "cond_replicated"
         need = self.lib.swb200_conditioning_backward_scratch_bytes(bp, Bc)
         scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
-        _lib.check(self.lib.swb200_conditioning_backward(bp, _lib.ptr(aux), Bc, fwd_scratch.data_ptr(), dgain.data_ptr(),
-                                                         dbias.data_ptr(), C.byref(self._cstruct), int(bool(accumulate)),
-                                                         scratch.data_ptr(), need, st), "conditioning_backward")
+        if dlogvar is not None:
+            # the head's gradient enters the conditioning vector before the latent MLP is differentiated (swinv2.py:326-327)
+            _lib.check(self.lib.swb200_conditioning_backward_logvar(
+                bp, _lib.ptr(aux), Bc, fwd_scratch.data_ptr(), dgain.data_ptr(), dbias.data_ptr(), C.byref(self._cstruct),
+                int(bool(accumulate)), scratch.data_ptr(), need, self.lv_w.data_ptr(), dlogvar.data_ptr(),
+                self.grads["lv_w"].data_ptr(), self.grads["lv_b"].data_ptr(), st), "conditioning_backward_logvar")
+        else:
+            if self.lv_w is not None and not accumulate:
+                self.grads["lv_w"].zero_()
+                self.grads["lv_b"].zero_()
+            _lib.check(self.lib.swb200_conditioning_backward(bp, _lib.ptr(aux), Bc, fwd_scratch.data_ptr(), dgain.data_ptr(),
+                                                             dbias.data_ptr(), C.byref(self._cstruct), int(bool(accumulate)),
+                                                             scratch.data_ptr(), need, st), "conditioning_backward")
         if on_stage:
             on_stage(kind, -1)
         return self.grads
@@ -203,6 +248,9 @@ class TrainEngine:
         if "aux_w" in gr:
             out["auxiliary_embed.weight"] = gr["aux_w"]
             out["auxiliary_embed.bias"] = gr["aux_b"]
+        if "lv_w" in gr:
+            out["logvar_embed.weight"] = gr["lv_w"].reshape(1, D)
+            out["logvar_embed.bias"] = gr["lv_b"]
         return out
 
     def stage_buffers(self, kind: str, layer: int) -> List[torch.Tensor]:
@@ -216,7 +264,8 @@ class TrainEngine:
             return [gr["w_embed_t"], gr["b_embed"], gr["pos_embed"]]
         if kind == "cond_replicated":           # evaluated on the gathered global batch: already identical on every rank
             return []
-        return [gr[n] for n in ("l1_w", "l1_b", "l2_w", "l2_b", "mod_w", "mod_b", "ln_gamma", "ln_beta", "aux_w", "aux_b") if n in gr]
+        return [gr[n] for n in ("l1_w", "l1_b", "l2_w", "l2_b", "mod_w", "mod_b", "ln_gamma", "ln_beta", "aux_w", "aux_b", "lv_w",
+                                "lv_b") if n in gr]
 
 
 class GradientAllReduce:
@@ -259,13 +308,13 @@ class GradientAllReduce:
             e1.record(self.stream)
             self._events.append((e0, e1))
 
-    def exchange_conditioning(self, engine: "TrainEngine", dgain, dbias, fwd_scratch, aux, B: int):
+    def exchange_conditioning(self, engine: "TrainEngine", dgain, dbias, fwd_scratch, aux, B: int, dlogvar=None):
         """``cond_exchange`` of ``TrainEngine.backward``: one ``all_gather`` of every rank's conditioning-stage inputs (the
         per-sample gain / bias gradients, the embedding / MLP activations and modulation vectors ``swb200_conditioning``
         left in its scratch, the auxiliary input) -> the same tensors for the global batch of ``world * B`` samples, the
         gradients pre-scaled by 1 / world so that the stage's output is the data-parallel MEAN."""
         if self.world == 1:
-            return dgain, dbias, fwd_scratch, aux, B
+            return (dgain, dbias, fwd_scratch, aux, B) if dlogvar is None else (dgain, dbias, fwd_scratch, aux, B, dlogvar)
         g = engine.geom
         D, L2 = g.dim, 2 * g.depth
         n_sc = B * (3 * D + L2 * 2 * D)
@@ -273,6 +322,8 @@ class GradientAllReduce:
         parts = [dgain.reshape(-1), dbias.reshape(-1), sc]
         if aux is not None:
             parts.append(aux.reshape(-1))
+        if dlogvar is not None:
+            parts.append(dlogvar.reshape(-1))
         mine = torch.cat(parts).contiguous()
         allr = torch.empty(self.world, mine.numel(), dtype=torch.float32, device=mine.device)
         self.dist.all_gather_into_tensor(allr, mine, group=self.group)
@@ -295,6 +346,8 @@ class GradientAllReduce:
         mod = scr[:, 3 * B * D:].reshape(W * B, L2 * 2 * D)
         scratch_all = torch.cat([emb.reshape(-1), h1.reshape(-1), cv.reshape(-1), mod.reshape(-1)]).contiguous()
         aux_all = take(aux.numel()).reshape(W * B, -1).contiguous() if aux is not None else None
+        if dlogvar is not None:                                     # a gradient like dgain / dbias: mean over the ranks
+            return dg, db, scratch_all, aux_all, W * B, take(B).reshape(W * B).mul(1.0 / W).contiguous()
         return dg, db, scratch_all, aux_all, W * B
 
     def finish(self) -> None:
@@ -315,25 +368,31 @@ class DenoiserTrainFn(torch.autograd.Function):
     module does (training/loss.py:226-260).  Inputs (x, t, auxiliary) get no gradient: the sCM loss does not need one."""
 
     @staticmethod
-    def forward(ctx, x, t, aux, module, names, *params):
+    def forward(ctx, x, t, aux, module, names, want_logvar, *params):
         eng = module.train_engine()
-        ctx.module, ctx.names, ctx.eng = module, names, eng
+        ctx.module, ctx.names, ctx.eng, ctx.want_logvar = module, names, eng, want_logvar
         if x.requires_grad:
             raise NotImplementedError("swift_b200.SwinV2 computes parameter gradients only (no gradient w.r.t. the input)")
-        return eng.forward(x, None, t, aux)
+        y = eng.forward(x, None, t, aux)
+        if want_logvar:                          # (F_x, logvar) as models/swinv2.py:326-328
+            return y, eng.logvar.clone()
+        return y
 
     @staticmethod
-    def backward(ctx, cot):
+    def backward(ctx, cot, dlogvar=None):
         eng = ctx.eng
         hook = ctx.module._grad_hook
-        eng.backward(cot.to(torch.float32).contiguous(), accumulate=False, on_stage=hook)
+        if ctx.want_logvar and dlogvar is None:
+            dlogvar = torch.zeros_like(eng.logvar)
+        eng.backward(cot.to(torch.float32).contiguous(), accumulate=False, on_stage=hook,
+                     dlogvar=dlogvar if ctx.want_logvar else None)
         params = dict(ctx.module.named_parameters())
         by_name = eng.parameter_gradients({n: p for n, p in params.items() if n.endswith(".scale")})
         grads = []
         for n in ctx.names:                      # clones: autograd may keep what it is handed, the flat buffers are re-used
             gname = by_name.get(n)
             grads.append(None if gname is None else gname.reshape(params[n].shape).clone())
-        return (None, None, None, None, None, *grads)
+        return (None, None, None, None, None, None, *grads)
 
 
 # ---------------------------------------------------------------------------------------------- the training step
@@ -350,8 +409,7 @@ def scm_train_step(net, x: torch.Tensor, t: torch.Tensor, z: torch.Tensor, step:
     from .scm_target import scm_output_cotangent
     inner = getattr(net, "module", net)
     model = inner.model
-    if model.logvar_embed is not None:
-        raise NotImplementedError("SCMLoss with a logvar head is not implemented on the CUDA path (model/swinv2.yaml: logvar: false)")
+    has_lv = model.logvar_embed is not None
 
     def mark(name):                       # optional phase timing (bench.py --mode train): CUDA events on the launch stream
         if timers is not None:
@@ -362,22 +420,26 @@ def scm_train_step(net, x: torch.Tensor, t: torch.Tensor, z: torch.Tensor, step:
     mark("t0")
     model.engine()                        # (re-)pack the 16-bit weights of the tangent path for the current parameters
     mark("pack_tangent")
-    out = scm_output_cotangent(net, x, t, z, step, condition=condition, auxiliary=auxiliary, **loss_kwargs)
-    mark("tangent_loss")
-    eng = model.train_engine()
-    mark("pack_train")
     B, dev = x.shape[0], x.device
     aux = process_auxiliary(auxiliary, inner.auxiliary_dim, B, dev)
     if aux is not None:
         aux = aux.to(torch.float32).expand(B, -1).contiguous()
+    t1 = t.to(device=dev, dtype=torch.float32).reshape(B).contiguous()
+    # logvar head: the loss weights sample b by exp(-logvar_b) (loss.py:252-258), and logvar depends on (t, aux) only: the
+    # conditioning stage of the grad-enabled forward runs first and hands it to the loss target
+    logvar = model.train_engine().conditioning(t1, aux) if has_lv else None
+    out = scm_output_cotangent(net, x, t, z, step, condition=condition, auxiliary=auxiliary, logvar=logvar, **loss_kwargs)
+    mark("tangent_loss")
+    eng = model.train_engine()
+    mark("pack_train")
     cond = None
     if condition is not None and inner.condition_channels > 0:
         cond = condition.to(device=dev, dtype=torch.float32).contiguous()
-    t1 = t.to(device=dev, dtype=torch.float32).reshape(B).contiguous()
-    eng.forward(out["x_t"], cond, t1, aux, scale0=1.0 / float(inner.sigma_data))
+    eng.forward(out["x_t"], cond, t1, aux, scale0=1.0 / float(inner.sigma_data), reuse_conditioning=has_lv)
     mark("train_forward")
     eng.backward(out["cot"], accumulate=accumulate, on_stage=reducer.hook if reducer is not None else None,
-                 cond_exchange=reducer.exchange_conditioning if reducer is not None else None)
+                 cond_exchange=reducer.exchange_conditioning if reducer is not None else None,
+                 dlogvar=out.get("dlogvar"))
     mark("backward")
     if reducer is not None:
         reducer.finish()

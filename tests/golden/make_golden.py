@@ -62,13 +62,13 @@ def install_shims():
     sys.path.insert(0, REF_SRC)
 
 
-def build_reference(cfg: dict, sd: dict, img_channels: int):
+def build_reference(cfg: dict, sd: dict, img_channels: int, logvar: bool = False):
     from swift.models.precond import PassPrecond
 
     model_cfg = dict(_target_="swift.models.swinv2.SwinV2",
                      window_size=cfg["window_size"], shift_size=cfg["shift_size"],
                      patch_size=cfg["patch_size"], depth=cfg["depth"], dim=cfg["dim"], heads=cfg["heads"],
-                     logvar=False, timestep_weight=1.0)
+                     logvar=logvar, timestep_weight=1.0)
     net = PassPrecond(model_cfg, img_resolution=cfg["img_resolution"], img_channels=img_channels,
                       condition_channels=cfg["in_channels"] - img_channels,
                       auxiliary_dim=cfg["auxiliary_dim"], sigma_min=0.0, sigma_max=float("inf"), sigma_data=1.0)

@@ -198,3 +198,74 @@ def test_scm_training_step_gradients_vs_reference_backward(golden):
         print(f"sCM step on the CUDA path ({cfgname}): worst gradient-norm error {worst:.3e} ({worst_nm}), without the logit "
               f"scales {worst_mat:.3e}; worst sampled-gradient rel-L2 {worst_s:.3e}")
         assert worst < 5e-2 and worst_mat < 1e-2 and worst_s < 5e-2
+
+
+@pytest.mark.parametrize("route", ["autograd", "train_step"])
+def test_scm_logvar_training_step_vs_reference_backward(golden, route):
+    """SCMLoss with a logvar head (loss.py:222-232, :252-258) on the CUDA path, both routes: ``scm_backward`` (the grad-enabled
+    call returns (F_x, logvar) and both receive cotangents through autograd) and ``scm_train_step`` (no autograd in the loop),
+    against the REAL reference's loss, logvar, dL/dlogvar and parameter gradients (tests/golden/scm_logvar.npz)."""
+    from swift_b200 import synthetic as syn
+    from swift_b200.precond import PassPrecond
+    from swift_b200.scm_target import scm_backward, latitude_weights, variable_weights
+    from swift_b200.training import scm_train_step
+    from test_oracle_golden import SCM_LOSS_VARIABLES
+    g = golden("scm_logvar")
+    for cfgname, k in (("SWIFT_TINY", "tiny_"), ("SWIFT_SMALL", "small_")):
+        cfg = getattr(syn, cfgname)
+        n_img, (H, W) = cfg["out_channels"], cfg["img_resolution"]
+        model_cfg = dict(_target_="swift_b200.swinv2.SwinV2", window_size=cfg["window_size"], shift_size=cfg["shift_size"],
+                         patch_size=cfg["patch_size"], depth=cfg["depth"], dim=cfg["dim"], heads=cfg["heads"], logvar=True,
+                         timestep_weight=1.0)
+        net = PassPrecond(model_cfg, img_resolution=cfg["img_resolution"], img_channels=n_img,
+                          condition_channels=cfg["in_channels"] - n_img, auxiliary_dim=cfg["auxiliary_dim"], sigma_data=1.0)
+        net.load_state_dict(syn.random_state_dict(cfg, seed=1, prefix="model.", logvar=True), strict=True)
+        net = net.cuda().train()
+        x, cond = (v.cuda() for v in syn.synthetic_fields(cfg, 2, seed=5))
+        step, warm = (int(v) for v in g[k + "step_warm"])
+        fn = scm_backward if route == "autograd" else scm_train_step
+        out = fn(net, x, torch.from_numpy(g[k + "t"]).cuda(), torch.from_numpy(g[k + "z"]).cuda(), step, condition=cond,
+                 auxiliary=0.6, tangent_warmup_kimg=warm, w_lat=latitude_weights(H, "cuda"),
+                 w_var=variable_weights(SCM_LOSS_VARIABLES[:n_img], "cuda"))
+        assert abs(float(out["loss"]) - float(g[k + "loss"])) < 1e-2 * abs(float(g[k + "loss"]))
+        assert _rel(out["logvar"].cpu(), torch.from_numpy(g[k + "logvar"]).flatten()) < 2e-3
+        assert _rel(out["dlogvar"].cpu(), torch.from_numpy(g[k + "dlogvar"]).flatten()) < 1e-2
+        assert _rel(out["cot"].cpu(), torch.from_numpy(g[k + "cot"])) < 2e-3
+        grads = {"model." + name: p.grad for name, p in net.model.named_parameters()}
+        worst, worst_nm = 0.0, ""
+        for nm, ref in zip((str(s) for s in g[k + "grad_names"]), g[k + "grad_norms"]):
+            e = abs(float(grads[nm].norm()) - ref) / ref
+            if e > worst and not nm.endswith(".scale"):
+                worst, worst_nm = e, nm
+        worst_s = 0.0
+        for kk in g:
+            if kk.startswith(k + "grad:"):
+                nm = kk.split("grad:")[1]
+                worst_s = max(worst_s, _rel(grads[nm].flatten()[::31].cpu().float(), torch.from_numpy(g[kk])))
+        print(f"sCM step with a logvar head ({cfgname}, {route}): worst gradient-norm error {worst:.3e} ({worst_nm}); worst "
+              f"sampled-gradient rel-L2 {worst_s:.3e}; head gradient norms {float(grads['model.logvar_embed.weight'].norm()):.4e} "
+              f"{float(grads['model.logvar_embed.bias'].norm()):.4e}")
+        assert worst < 1e-2 and worst_s < 5e-2
+
+
+def test_eval_forward_returns_logvar_through_the_c_abi():
+    """``net(x, t, ..., return_logvar=True)`` in eval mode (models/swinv2.py:326-328): logvar = logvar_embed(c) from
+    ``swb200_logvar_head`` against the oracle."""
+    from oracle import swinv2_oracle as orc
+    from swift_b200 import synthetic as syn
+    from swift_b200.swinv2 import SwinV2
+    cfg = syn.SWIFT_TINY
+    m = SwinV2(img_resolution=cfg["img_resolution"], in_channels=cfg["in_channels"], out_channels=cfg["out_channels"],
+               window_size=cfg["window_size"], shift_size=cfg["shift_size"], patch_size=cfg["patch_size"], depth=cfg["depth"],
+               dim=cfg["dim"], heads=cfg["heads"], auxiliary_dim=cfg["auxiliary_dim"], logvar=True)
+    sd = syn.random_state_dict(cfg, seed=1, logvar=True)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    x = torch.randn(3, cfg["in_channels"], *cfg["img_resolution"])
+    t = torch.tensor([0.3, 0.9, 1.4])
+    aux = torch.full((3, 1), 0.6)
+    with torch.no_grad():
+        y, lv = m(x.cuda(), t.cuda(), aux.cuda(), return_logvar=True)
+    yo, lvo = orc.swinv2_forward(sd, orc.make_cfg(**cfg, logvar=True), x, t, aux, return_logvar=True)
+    assert lv.shape == (3,) and _rel(lv.cpu(), lvo) < 1e-5
+    assert _rel(y.cpu(), yo) < 5e-3

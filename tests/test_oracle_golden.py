@@ -149,6 +149,42 @@ def test_scm_parameter_gradients_match_reference_backward(golden, name, cfgname)
         _close(grads[nm].flatten()[::31], g[kk], tol=5e-5)
 
 
+@pytest.mark.parametrize("name,cfgname", [("tiny", "SWIFT_TINY"), ("small", "SWIFT_SMALL")])
+def test_scm_logvar_loss_and_gradients_match_reference(golden, name, cfgname):
+    """SCMLoss around a model WITH a logvar head (loss.py:222-232, :252-258; tests/golden/make_scm_logvar_golden.py ran the real
+    reference): loss, logvar, dL/dF_x, dL/dlogvar, the norm of every parameter gradient and strided samples -- reproduced by
+    the oracle (both outputs of the grad-enabled call receive their cotangents)."""
+    from oracle import scm_loss_oracle as so
+    g = golden("scm_logvar")
+    c = getattr(syn, cfgname)
+    n_img, (H, W) = c["out_channels"], c["img_resolution"]
+    cfg = orc.make_cfg(**c, logvar=True)
+    p = syn.random_state_dict(c, seed=1, logvar=True)
+    x, cond = syn.synthetic_fields(c, 2, seed=5)
+    w_lat, w_var = so.latitude_weights(H), so.variable_weights(SCM_LOSS_VARIABLES[:n_img])
+    k = name + "_"
+    step, warm = (int(v) for v in g[k + "step_warm"])
+    aux = torch.full((2, 1), 0.6)
+
+    def net_lv_of(q):
+        return lambda a, b: orc.swinv2_forward(q, cfg, torch.cat([a, cond], 1), b.flatten(), aux, return_logvar=True)
+
+    grads = so.scm_parameter_gradients_logvar(lambda q: (lambda a, b: orc.pass_precond(q, cfg, a, b, cond, 0.6)), net_lv_of, p, x,
+                                              torch.from_numpy(g[k + "t"]), torch.from_numpy(g[k + "z"]), step, warm, w_lat, w_var)
+    assert abs(float(grads.pop("__loss__")) - float(g[k + "loss"])) < 2e-5 * abs(float(g[k + "loss"]))
+    _close(grads.pop("__dlogvar__"), g[k + "dlogvar"], tol=2e-5)
+    _close(grads.pop("__cot__"), g[k + "cot"], tol=2e-5)
+    names = [str(s) for s in g[k + "grad_names"]]
+    assert sorted(names) == sorted("model." + n for n in p)                  # the head's parameters included
+    for nm, ref in zip(names, g[k + "grad_norms"]):
+        got = float(grads[nm[len("model."):]].norm())
+        assert abs(got - ref) < 5e-5 * ref, (nm, got, ref)
+    for kk in g:
+        if kk.startswith(k + "grad:"):
+            nm = kk.split("grad:")[1][len("model."):]
+            _close(grads[nm].flatten()[::31], g[kk], tol=1e-4)
+
+
 def test_muon_oracle_matches_reference_golden(golden):
     """oracle/muon_oracle.py against the REAL reference's muon_update / adam_update (tests/golden/make_muon_golden.py)."""
     from oracle import muon_oracle as mo
