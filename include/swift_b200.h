@@ -295,6 +295,10 @@ SWB200_API size_t swb200_scm_target_scratch_bytes(int B);
 SWB200_API int swb200_scm_tangent_target(const float* F, const float* dF, const float* x_t, const float* dxt, const float* t, float r,
                               float sigma_data, const float* w_var, const float* w_lat, int B, int C, int H, int W,
                               float* g, float* cot, float* loss, void* scratch, size_t scratch_bytes, void* stream);
+/* Distillation (training/loss.py:205-210): with a pretrained v-prediction teacher, dx_t/dt = sigma_d * F_teacher(x_t / sigma_d, t)
+ * replaces cos(t) z - sin(t) x; overwrites dxt and v_x = cos(t) sin(t) dx_t/dt / sigma_d of swb200_scm_noised_inputs. */
+SWB200_API int swb200_scm_distill_direction(const float* F_teacher, const float* t, float sigma_data, int B, int C, int H, int W,
+                                 float* dxt, float* vx, void* stream);
 /* SCMLoss with a logvar head (training/loss.py:227-232, :252-258): L = mean_{b,h,w} sum_c [exp(-logvar_b) w g^2 + logvar_b];
  * cot = exp(-logvar_b) * (-2 w g) / (B H W), dlogvar [B] = dL/dlogvar_b = (C H W - exp(-logvar_b) sum_{c,h,w} w g^2) / (B H W). */
 SWB200_API int swb200_scm_tangent_target_logvar(const float* F, const float* dF, const float* x_t, const float* dxt, const float* t,

@@ -66,14 +66,19 @@ def scm_tangent_target(F: torch.Tensor, dF: torch.Tensor, x_t: torch.Tensor, dxt
 
 
 def scm_loss(net: Callable, x: torch.Tensor, t: torch.Tensor, z: torch.Tensor, step: int, tangent_warmup_kimg: int,
-             w_lat: torch.Tensor, w_var: torch.Tensor, sigma_data: float = 1.0, logvar=None) -> Dict[str, torch.Tensor]:
+             w_lat: torch.Tensor, w_var: torch.Tensor, sigma_data: float = 1.0, logvar=None,
+             net_pretrained: Callable = None) -> Dict[str, torch.Tensor]:
     """loss.py:192-260 as a deterministic function of the draws (t = atan(tau / sigma_d) [B,1,1,1], z = sigma_d * N(0,1)).
 
     ``net(x_in, t_flat) -> F`` is the denoiser with condition / auxiliary bound (the reference's ``wrapper``, :213-214);
     it must be differentiable in forward mode (``torch.func.jvp``).  Returns loss, cot = dL/dF, g, F, dF, x_t."""
     cos_t, sin_t = torch.cos(t), torch.sin(t)
     x_t = cos_t * x + sin_t * z                                         # :203
-    dxt_dt = cos_t * z - sin_t * x                                      # :211 (no distillation)
+    if net_pretrained is not None:                                      # :205-209 distillation: a frozen v-prediction teacher
+        with torch.no_grad():
+            dxt_dt = sigma_data * net_pretrained(x_t / sigma_data, t.flatten())
+    else:
+        dxt_dt = cos_t * z - sin_t * x                                  # :211
     v_x = cos_t * sin_t * dxt_dt / sigma_data                           # :216
     v_t = cos_t * sin_t                                                 # :217
     F, dF = torch.func.jvp(lambda a, b: net(a, b.flatten()), (x_t / sigma_data, t), (v_x, v_t))      # :218-221

@@ -31,6 +31,7 @@ EXPORTS = (
     "swb200_qkv_pack_train", "swb200_muon_workspace_bytes", "swb200_muon_step", "swb200_adam_step", "swb200_muon_vector_step",
     "swb200_packed_bytes", "swb200_pack_weights", "swb200_train_packed_bytes", "swb200_pack_train_weights",
     "swb200_conditioning_backward_logvar", "swb200_logvar_head", "swb200_scm_tangent_target_logvar",
+    "swb200_scm_distill_direction",
 )
 
 _i32, _f32, _vp, _sz = C.c_int32, C.c_float, C.c_void_p, C.c_size_t
@@ -106,6 +107,7 @@ def _declare(lib):
         "swb200_conditioning_backward": (C.c_int, [MP, _vp, C.c_int, _vp, _vp, _vp, CP, C.c_int, _vp, _sz, _vp]),
         "swb200_conditioning_backward_logvar": (C.c_int, [MP, _vp, C.c_int, _vp, _vp, _vp, CP, C.c_int, _vp, _sz, _vp, _vp, _vp, _vp,
                                                           _vp]),
+        "swb200_scm_distill_direction": (C.c_int, [_vp, _vp, _f32, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
         "swb200_logvar_head": (C.c_int, [MP, _vp, _vp, _vp, C.c_int, _vp, _vp]),
         "swb200_scm_tangent_target_logvar": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _vp, C.c_int, C.c_int, C.c_int,
                                                        C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

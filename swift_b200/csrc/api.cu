@@ -788,6 +788,12 @@ SWB200_API int swb200_scm_tangent_target_logvar(const float* F, const float* dF,
                                    scratch_bytes, static_cast<cudaStream_t>(stream), logvar, dlogvar);
 }
 
+SWB200_API int swb200_scm_distill_direction(const float* F_teacher, const float* t, float sigma_data, int B, int C, int H, int W,
+                                            float* dxt, float* vx, void* stream) {
+  SWB_REQUIRE(F_teacher && t && dxt && vx, "swb200_scm_distill_direction: NULL pointer");
+  return launch_scm_distill_direction(F_teacher, t, sigma_data, B, C, H, W, dxt, vx, static_cast<cudaStream_t>(stream));
+}
+
 SWB200_API int swb200_logvar_head(const swb200_model* m, const void* fwd_scratch, const float* lv_w, const float* lv_b, int B,
                                   float* logvar, void* stream) {
   SWB_REQUIRE(m && fwd_scratch && lv_w && lv_b && logvar && B > 0, "swb200_logvar_head: NULL pointer");

@@ -137,6 +137,8 @@ int launch_ensemble_stats(const float* phys, const float* truth, const float* w_
 int launch_scm_noised_inputs(const float* x, const float* z, const float* t, int B, int C, int H, int W, float* x_t,
                              float* dxt, float* vx, float* vt, cudaStream_t stream);
 size_t scm_target_scratch_bytes(int B);
+int launch_scm_distill_direction(const float* F_teacher, const float* t, float sigma_data, int B, int C, int H, int W, float* dxt,
+                                 float* vx, cudaStream_t stream);
 int launch_scm_tangent_target(const float* F, const float* dF, const float* x_t, const float* dxt, const float* t, float r,
                               float sigma_data, const float* w_var, const float* w_lat, int B, int C, int H, int W, float* g,
                               float* cot, float* loss, void* scratch, size_t scratch_bytes, cudaStream_t stream,

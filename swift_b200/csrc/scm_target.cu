@@ -141,6 +141,22 @@ __global__ void scm_loss_sum_kernel(const double* __restrict__ loss_part, int B,
   }
 }
 
+// distillation (loss.py:205-210): dx_t/dt = sigma_d * F_teacher replaces cos z - sin x, and with it v_x = cos sin dx_t/dt / sigma_d
+__global__ void __launch_bounds__(kScmThreads) scm_distill_direction_kernel(const float4* __restrict__ Ft, const float* __restrict__ t,
+                                                                            float sd, size_t n4, float4* __restrict__ dxt,
+                                                                            float4* __restrict__ vx) {
+  const int b = blockIdx.y;
+  float s, c;
+  sincosf(t[b], &s, &c);
+  const float cs = c * s;
+  const size_t base = static_cast<size_t>(b) * n4;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 f = __ldg(Ft + base + i);
+    dxt[base + i] = make_float4(sd * f.x, sd * f.y, sd * f.z, sd * f.w);
+    vx[base + i] = make_float4(cs * f.x, cs * f.y, cs * f.z, cs * f.w);
+  }
+}
+
 static int blocks_per_sample(size_t n4) {
   const size_t want = (n4 + kScmThreads * 4 - 1) / (kScmThreads * 4);
   return static_cast<int>(want < 1 ? 1 : (want > kScmMaxBlocks ? kScmMaxBlocks : want));
@@ -154,6 +170,17 @@ int launch_scm_noised_inputs(const float* x, const float* z, const float* t, int
   scm_noised_inputs_kernel<<<grid, kScmThreads, 0, stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(z),
                                                             t, n4, reinterpret_cast<float4*>(x_t), reinterpret_cast<float4*>(dxt),
                                                             reinterpret_cast<float4*>(vx), vt);
+  SWB_CHECK_CUDA(cudaGetLastError());
+  return SWB_OK;
+}
+
+int launch_scm_distill_direction(const float* F_teacher, const float* t, float sigma_data, int B, int C, int H, int W, float* dxt,
+                                 float* vx, cudaStream_t stream) {
+  SWB_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && W % 4 == 0, "scm_distill_direction: need B, C, H > 0 and W a multiple of 4 (W=%d)", W);
+  const size_t n4 = static_cast<size_t>(C) * H * (W / 4);
+  dim3 grid(blocks_per_sample(n4), B);
+  scm_distill_direction_kernel<<<grid, kScmThreads, 0, stream>>>(reinterpret_cast<const float4*>(F_teacher), t, sigma_data, n4,
+                                                                reinterpret_cast<float4*>(dxt), reinterpret_cast<float4*>(vx));
   SWB_CHECK_CUDA(cudaGetLastError());
   return SWB_OK;
 }

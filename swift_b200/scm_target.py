@@ -56,7 +56,7 @@ def variable_weights(variables: Sequence[str], device=None) -> torch.Tensor:
 def scm_output_cotangent(net, x: torch.Tensor, t: torch.Tensor, z: torch.Tensor, step: int,
                          condition: Optional[torch.Tensor] = None, auxiliary=None, tangent_warmup_kimg: int = 0,
                          w_lat: Optional[torch.Tensor] = None, w_var: Optional[torch.Tensor] = None,
-                         logvar=None) -> Dict[str, torch.Tensor]:
+                         logvar=None, net_pretrained=None) -> Dict[str, torch.Tensor]:
     """x [B, C, H, W] targets, t = atan(tau / sigma_d) ([B] or [B,1,1,1]), z = sigma_d * N(0,1) like x (the draws of
     loss.py:196-200, made by the caller), ``net`` a PassPrecond around ``swift_b200.swinv2.SwinV2`` on a CUDA device.
     Returns {"loss", "cot" (= dL/dF_x), "g", "F", "dF", "x_t"}; all detached fp32.
@@ -68,7 +68,12 @@ def scm_output_cotangent(net, x: torch.Tensor, t: torch.Tensor, z: torch.Tensor,
     Models with a logvar head (``logvar: true``; loss.py:227-232, :252-258) need ``logvar``: a [B] tensor, or a callable
     ``x_t -> [B] tensor`` evaluated once the noised inputs exist (the grad-enabled forward that produces it takes x_t).  The
     sample's squared term is then weighted by exp(-logvar_b), ``+ logvar_b`` is added, and the dict also carries
-    ``"dlogvar"`` = dL/dlogvar [B] (``swb200_scm_tangent_target_logvar``)."""
+    ``"dlogvar"`` = dL/dlogvar [B] (``swb200_scm_tangent_target_logvar``).
+
+    Distillation (loss.py:205-210; ``SCMLoss(distillation=True)`` + ``Trainer(net_pretrained=...)``): ``net_pretrained`` is the
+    frozen v-prediction teacher, called once as ``net_pretrained(x_t / sigma_d, t, condition, auxiliary)`` under ``no_grad``
+    (any module that returns a CUDA tensor: e.g. a second ``PassPrecond`` around ``swift_b200.SwinV2`` in eval mode, which then
+    runs the forecast kernels); ``swb200_scm_distill_direction`` puts sigma_d * F_teacher in the place of cos z - sin x."""
     inner = getattr(net, "module", net)
     model = inner.model
     if not hasattr(model, "engine"):
@@ -93,6 +98,13 @@ def scm_output_cotangent(net, x: torch.Tensor, t: torch.Tensor, z: torch.Tensor,
     v_t = torch.empty_like(t1)
     _lib.check(lib.swb200_scm_noised_inputs(x.data_ptr(), z.data_ptr(), t1.data_ptr(), B, C, H, W, x_t.data_ptr(),
                                             dxt.data_ptr(), v_x.data_ptr(), v_t.data_ptr(), stream), "scm_noised_inputs")
+    if net_pretrained is not None:
+        Ft = net_pretrained(x_t / sd, t1, condition, auxiliary)
+        Ft = Ft.detach().to(device=dev, dtype=torch.float32).contiguous()
+        if Ft.shape != x.shape:
+            raise RuntimeError(f"net_pretrained returned {tuple(Ft.shape)}, expected {tuple(x.shape)}")
+        _lib.check(lib.swb200_scm_distill_direction(Ft.data_ptr(), t1.data_ptr(), sd, B, C, H, W, dxt.data_ptr(), v_x.data_ptr(),
+                                                    stream), "scm_distill_direction")
     cond = None
     if condition is not None and inner.condition_channels > 0:          # precond.py:143-145; no tangent in the condition
         cond = condition.to(device=dev, dtype=torch.float32).contiguous()

@@ -269,3 +269,29 @@ def test_eval_forward_returns_logvar_through_the_c_abi():
     yo, lvo = orc.swinv2_forward(sd, orc.make_cfg(**cfg, logvar=True), x, t, aux, return_logvar=True)
     assert lv.shape == (3,) and _rel(lv.cpu(), lvo) < 1e-5
     assert _rel(y.cpu(), yo) < 5e-3
+
+
+def test_scm_distillation_cotangent_vs_reference(golden):
+    """The distillation branch (loss.py:205-210) on the CUDA path: the teacher is a second PassPrecond around swift_b200.SwinV2 in
+    eval mode (seed-2 weights: the forecast kernels), ``swb200_scm_distill_direction`` swaps the tangent direction; loss and
+    dL/dF_x against the REAL reference's ``SCMLoss(distillation=True)`` (tests/golden/scm_distill.npz)."""
+    from swift_b200 import synthetic as syn
+    from swift_b200.scm_target import scm_output_cotangent, latitude_weights, variable_weights
+    from test_gpu_forward import build_net
+    from test_oracle_golden import SCM_LOSS_VARIABLES
+    g = golden("scm_distill")
+    for cfgname, k in (("SWIFT_TINY", "tiny_"), ("SWIFT_SMALL", "small_")):
+        cfg = getattr(syn, cfgname)
+        n_img, (H, W) = cfg["out_channels"], cfg["img_resolution"]
+        net, _ = build_net(cfg, img_channels=n_img)
+        teacher, _ = build_net(cfg, seed=2, img_channels=n_img)
+        x, cond = (v.cuda() for v in syn.synthetic_fields(cfg, 2, seed=5))
+        step, warm = (int(v) for v in g[k + "step_warm"])
+        with torch.no_grad():
+            out = scm_output_cotangent(net, x, torch.from_numpy(g[k + "t"]).cuda(), torch.from_numpy(g[k + "z"]).cuda(), step,
+                                       condition=cond, auxiliary=0.6, tangent_warmup_kimg=warm, w_lat=latitude_weights(H, "cuda"),
+                                       w_var=variable_weights(SCM_LOSS_VARIABLES[:n_img], "cuda"), net_pretrained=teacher)
+        e_cot = _rel(out["cot"].cpu(), torch.from_numpy(g[k + "cot"]))
+        print(f"{k}: distillation cotangent rel-L2 {e_cot:.3e}, loss {float(out['loss']):.6f} vs {float(g[k + 'loss']):.6f}")
+        assert e_cot < 3e-3
+        assert abs(float(out["loss"]) - float(g[k + "loss"])) < 1e-3 * float(g[k + "loss"])

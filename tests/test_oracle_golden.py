@@ -185,6 +185,26 @@ def test_scm_logvar_loss_and_gradients_match_reference(golden, name, cfgname):
             _close(grads[nm].flatten()[::31], g[kk], tol=1e-4)
 
 
+@pytest.mark.parametrize("name,cfgname", [("tiny", "SWIFT_TINY"), ("small", "SWIFT_SMALL")])
+def test_scm_distillation_loss_matches_reference(golden, name, cfgname):
+    """``SCMLoss(distillation=True)`` with a ``net_pretrained`` teacher (loss.py:205-210; the real reference ran in
+    tests/golden/make_scm_distill_golden.py with the seed-2 fixture as teacher): loss and dL/dF_x from the oracle."""
+    from oracle import scm_loss_oracle as so
+    g = golden("scm_distill")
+    c = getattr(syn, cfgname)
+    n_img, (H, W) = c["out_channels"], c["img_resolution"]
+    cfg = orc.make_cfg(**c)
+    p, p_teacher = syn.random_state_dict(c, seed=1), syn.random_state_dict(c, seed=2)
+    x, cond = syn.synthetic_fields(c, 2, seed=5)
+    k = name + "_"
+    step, warm = (int(v) for v in g[k + "step_warm"])
+    out = so.scm_loss(lambda a, b: orc.pass_precond(p, cfg, a, b, cond, 0.6), x, torch.from_numpy(g[k + "t"]),
+                      torch.from_numpy(g[k + "z"]), step, warm, so.latitude_weights(H), so.variable_weights(SCM_LOSS_VARIABLES[:n_img]),
+                      net_pretrained=lambda a, b: orc.pass_precond(p_teacher, cfg, a, b, cond, 0.6))
+    assert abs(float(out["loss"]) - float(g[k + "loss"])) < 2e-5 * float(g[k + "loss"])
+    _close(out["cot"], g[k + "cot"], tol=5e-5)
+
+
 def test_muon_oracle_matches_reference_golden(golden):
     """oracle/muon_oracle.py against the REAL reference's muon_update / adam_update (tests/golden/make_muon_golden.py)."""
     from oracle import muon_oracle as mo
