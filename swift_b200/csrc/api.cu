@@ -252,14 +252,18 @@ SWB200_API int swb200_forward(const swb200_model* m, const float* x0, int c0, fl
     int ln_gen = 0;                             // fused launches of this chunk so far (the first one clears the counters)
 
     // 1. concat + patchify + cast
+    // single-value stream: the embed output is rounded to fp16 anyway, so the patch operand is its hi half alone (the lo half is
+    // not written, K = k_embed on the first half of the packed [W | W]; row pitches unchanged): Swift-B one step 1.93e-3 ->
+    // 2.05e-3.  The tangent / training paths keep the split operand.
+    const int ES = (XS || !m->split_embed) ? 0 : 1;
     { TraceScope ts_(T_GATHER, stream);
     rc = launch_patch_gather(x0 + b0 * img_in0, c0, scale0, x1 ? x1 + b0 * img_in1 : nullptr, c1, a_emb,
-                             g.k_embed_total, m->k_embed, m->split_embed, F16, bc, m->img_h, m->img_w, m->patch_h,
+                             g.k_embed_total, m->k_embed, ES, F16, bc, m->img_h, m->img_w, m->patch_h,
                              m->patch_w, stream); }
     if (rc) return rc;
     // 2. patch-embed GEMM (+bias +pos_embed)
     {
-      GemmParams p = base_params(M, D, g.k_embed_total);
+      GemmParams p = base_params(M, D, ES ? g.k_embed_total : m->k_embed);
       p.out0 = xhl;
       p.ldo = 2 * D;
       p.bias = m->b_embed;
