@@ -215,8 +215,9 @@ int launch_gemm(int epi, int tile, int act_f16, const void* A, int lda, const vo
               "gemm: split-K needs the fp32 store epilogue and K %% 64 == 0 (epi=%d K=%d splits=%d)", epi, p.K, p.splits);
   SWB_REQUIRE(p.batch <= 1 || epi == EPI_STORE_F32, "gemm: batched problems need the fp32 store epilogue (epi=%d)", epi);
   SWB_REQUIRE(tile >= 1 && tile <= 3, "gemm: tile config must be 1 (128x176), 2 (256x176) or 3 (256x352), got %d", tile);
-  // sub-tile 0 of the 256x352 tile runs two k-blocks ahead of sub-tile 1 (gemm_sm100.cuh); SWB_GEMM_SKEW: A/B knob (tools only)
-  static const int skew_env = getenv("SWB_GEMM_SKEW") ? atoi(getenv("SWB_GEMM_SKEW")) : 2;
+  // sub-tile 0 of the 256x352 tile runs three k-blocks ahead of sub-tile 1 (the kernel clamps to its pipeline depth - 2: two
+  // with the fused LayerNorm's four stages; gemm_sm100.cuh); SWB_GEMM_SKEW: A/B knob (tools only)
+  static const int skew_env = getenv("SWB_GEMM_SKEW") ? atoi(getenv("SWB_GEMM_SKEW")) : 3;
   p.skew = skew_env;
 #ifdef SWB_PROFILE_EPILOGUES
   SWB_CHECK_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&p.prof), g_gemm_prof));
