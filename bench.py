@@ -207,7 +207,7 @@ def workload_config(n_gpus: int, where: str, solver: str = "scm"):
             "member_steps_per_bench_step": MEMBERS * ICS_PER_GPU * n_gpus,
             "sharding": f"(member, IC) over {n_gpus} GPU(s), no collective on the forecast path",
             "l2_policy": "inputs larger than L2 (96 trajectories x 18.5 MB inputs, 216 MB workspace per sample)",
-            "step": "one CUDA graph per 6h step: Philox latents, forcings, the denoiser kernels per trajectory chunk (LayerNorm fused into the w2 GEMM, sCM update and std/unstd glue fused in the head epilogue), ensemble statistics",
+            "step": "one CUDA graph per 6h step: Philox latents, forcings, the denoiser kernels per trajectory chunk (LayerNorm + residual update fused into the wo / w2 GEMM epilogues, sCM update and std/unstd glue fused in the head epilogue), ensemble statistics",
             "device": where}
 
 
@@ -446,7 +446,12 @@ def run_ours(args):
         "metric": "forecast member-steps/sec", "value": value, "unit": "member-steps/s", "n_gpus": n_gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
-        "dtype": ("fp16" if eng.act_fp16 else "bf16") + " tensor-core operands (tcgen05 kind::f16), fp32 accumulate / residual / LayerNorm / softmax",
+        "dtype": ("fp16" if eng.act_fp16 else "bf16") + " tensor-core operands (tcgen05 kind::f16), fp32 accumulate / LayerNorm / softmax; "
+                 "residual stream " + ("stored as ONE fp16 value per element, updated in fp32 (x_single)"
+                                       if (eng.act_fp16 and net.model.x_single) else "stored as a 16-bit [hi | lo] pair (~22 bits), updated in fp32"),
+        "numerics_knobs": {"act_fp16": bool(eng.act_fp16), "x_single": bool(eng.act_fp16 and net.model.x_single),
+                           "fuse_ln": int(net.model.fuse_ln), "one_step_rel_l2_max": "2.0e-3 (x_single) / 1.4e-3 (pair), bar 1e-2: "
+                                                                                     "profiles/r02b_numerics.txt"},
         "data": "synthetic", "config": workload_config(n_gpus, torch.cuda.get_device_name(dev), args.solver),
         "clocks": clock_info,
         "e2e": {"value": e2e_value, "unit": "member-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
