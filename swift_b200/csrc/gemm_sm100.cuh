@@ -826,7 +826,7 @@ __device__ __forceinline__ void epi_group_swiglu(const GemmParams& p, EpiCtx& e,
 //     x <- x + LayerNorm(branch) * gain[b] + bias[b],     branch = A W^T  (wo or w2 projection)
 // done in the GEMM epilogue, so the branch never exists in HBM.  A LayerNorm row spans every column tile, while one
 // epilogue warp only sees its 176 columns of 32 rows: each warp publishes the (sum, M2) of its part of the rows to
-// global memory, bumps a per-32-row counter and spins until all tiles_n * NSUB groups of those rows have arrived (they
+// global memory (generation-tagged, see epi_group_lnres) and polls until all tiles_n * NSUB groups of those rows have arrived (they
 // run at the same time on neighbouring clusters of this persistent kernel: the launcher keeps the number of clusters a
 // multiple of tiles_n, every CTA is resident, and the accumulator has already been handed back, so main loops never
 // wait on this exchange).  The partials are merged with Chan's formula; the branch is held in registers as fp16 pairs
