@@ -325,8 +325,9 @@ class GradientAllReduce:
         if dlogvar is not None:
             parts.append(dlogvar.reshape(-1))
         mine = torch.cat(parts).contiguous()
-        allr = torch.empty(self.world, mine.numel(), dtype=torch.float32, device=mine.device)
-        self.dist.all_gather_into_tensor(allr, mine, group=self.group)
+        flat = torch.empty(self.world * mine.numel(), dtype=torch.float32, device=mine.device)
+        self.dist.all_gather_into_tensor(flat, mine, group=self.group)      # (a flat output: what both NCCL and gloo accept)
+        allr = flat.view(self.world, mine.numel())
         self.bytes += allr.numel() * 4
         W, o = self.world, 0
         n_g = L2 * B * D

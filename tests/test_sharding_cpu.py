@@ -156,3 +156,64 @@ def test_gradient_allreduce_two_ranks_gloo():
         p.join(timeout=60)
     assert [r[1] for r in res] == [True, True]
     assert res[0][2] == res[1][2] == (12 + 5 + 4 + 3 + 6) * 4
+
+
+def _exchange_worker(rank, world, port, q):
+    """GradientAllReduce.exchange_conditioning on host tensors (gloo): the per-sample inputs of the replicated conditioning stage
+    -- gain / bias gradients, the forward scratch [emb | h1 | c | mod], the auxiliary input and dL/dlogvar -- gathered into the
+    global batch in rank-major order, gradients pre-scaled by 1 / world."""
+    import os
+    import types
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from swift_b200.training import GradientAllReduce
+
+    D, L, B = 4, 1, 2
+    L2 = 2 * L
+    eng = types.SimpleNamespace(geom=types.SimpleNamespace(dim=D, depth=L), grads={})
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(1))
+            self._train_engine = eng
+
+    def mk(r):
+        g = torch.Generator().manual_seed(7 + r)
+        dgain, dbias = torch.randn(L2, B, D, generator=g), torch.randn(L2, B, D, generator=g)
+        emb, h1, c = (torch.randn(B, D, generator=g) for _ in range(3))
+        mod = torch.randn(B, L2 * 2 * D, generator=g)
+        aux, dlv = torch.randn(B, 1, generator=g), torch.randn(B, generator=g)
+        return dgain, dbias, emb, h1, c, mod, aux, dlv
+
+    dgain, dbias, emb, h1, c, mod, aux, dlv = mk(rank)
+    scratch = torch.cat([emb.reshape(-1), h1.reshape(-1), c.reshape(-1), mod.reshape(-1), torch.zeros(5)]).contiguous()
+    red = GradientAllReduce(M())
+    dg, db, sc, aux_all, WB, dlv_all = red.exchange_conditioning(eng, dgain, dbias, scratch.view(torch.uint8), aux, B, dlv)
+    parts = [mk(r) for r in range(world)]
+    ok = WB == world * B
+    ok &= torch.allclose(dg, torch.cat([p[0] for p in parts], 1) / world) and torch.allclose(db, torch.cat([p[1] for p in parts], 1) / world)
+    want_sc = torch.cat([torch.cat([p[i] for p in parts], 0).reshape(-1) for i in (2, 3, 4, 5)])
+    ok &= torch.equal(sc.view(torch.float32)[:want_sc.numel()], want_sc)
+    ok &= torch.equal(aux_all, torch.cat([p[6] for p in parts], 0))
+    ok &= torch.allclose(dlv_all, torch.cat([p[7] for p in parts], 0) / world)
+    # without a logvar head the call keeps its five-tuple
+    ok &= len(red.exchange_conditioning(eng, dgain, dbias, scratch.view(torch.uint8), aux, B)) == 5
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_exchange_conditioning_with_logvar_two_ranks_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_exchange_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[1] for r in res] == [True, True]
