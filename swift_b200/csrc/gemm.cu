@@ -219,6 +219,10 @@ int launch_gemm(int epi, int tile, int act_f16, const void* A, int lda, const vo
   // with the fused LayerNorm's four stages; gemm_sm100.cuh); SWB_GEMM_SKEW: A/B knob (tools only)
   static const int skew_env = getenv("SWB_GEMM_SKEW") ? atoi(getenv("SWB_GEMM_SKEW")) : 3;
   p.skew = skew_env;
+  // the fused-LayerNorm GEMMs: one k-block (their two epilogue groups meet again in the statistics exchange, so a group that
+  // starts early only waits longer there: 384.9 vs 383.2 member-steps/s with 2); SWB_GEMM_SKEW_LN: A/B knob (tools only)
+  static const int skew_ln_env = getenv("SWB_GEMM_SKEW_LN") ? atoi(getenv("SWB_GEMM_SKEW_LN")) : 1;
+  if (epi == EPI_LN_RES || epi == EPI_LN_RES1) p.skew = skew_ln_env;
 #ifdef SWB_PROFILE_EPILOGUES
   SWB_CHECK_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&p.prof), g_gemm_prof));
   static const bool nomma = getenv("SWB_GEMM_NOMMA") != nullptr;       // TMA feed rate alone (see gemm_sm100.cuh)
