@@ -450,7 +450,7 @@ def run_ours(args):
                  "residual stream " + ("stored as ONE fp16 value per element, updated in fp32 (x_single)"
                                        if (eng.act_fp16 and net.model.x_single) else "stored as a 16-bit [hi | lo] pair (~22 bits), updated in fp32"),
         "numerics_knobs": {"act_fp16": bool(eng.act_fp16), "x_single": bool(eng.act_fp16 and net.model.x_single),
-                           "fuse_ln": int(net.model.fuse_ln), "one_step_rel_l2_max": "2.0e-3 (x_single) / 1.4e-3 (pair), bar 1e-2: "
+                           "fuse_ln": int(net.model.effective_fuse_ln()), "one_step_rel_l2_max": "2.0e-3 (x_single) / 1.4e-3 (pair), bar 1e-2: "
                                                                                      "profiles/r02b_numerics.txt"},
         "data": "synthetic", "config": workload_config(n_gpus, torch.cuda.get_device_name(dev), args.solver),
         "clocks": clock_info,

@@ -193,9 +193,9 @@ class SwinV2(_Base):
         self.attn_fp16 = True        # bf16 mode only: q / k / v and P stay fp16 inside the attention kernel (bounded values)
         self.gemm_tile = 3           # 1: 128x176 single CTA, 2: 256x176 CTA pair, 3: 256x352 CTA pair
         self.attn_impl = 0           # 0: tcgen05 attention when the shift is a multiple of 8, 1: mma.sync kernel, 2: tcgen05
-        self.fuse_ln = 3             # LayerNorm + modulation + residual add in the GEMM epilogue: bit 0 = wo, bit 1 = w2; 0 = separate kernel
-                                     # (both since the single-value stream moves x by TMA; with the [hi | lo] pair the short-K wo GEMM is
-                                     # epilogue-bound when fused and 2 is the faster setting)
+        self.fuse_ln = None          # LayerNorm + modulation + residual add in the GEMM epilogue: bit 0 = wo, bit 1 = w2; 0 = separate kernel;
+                                     # None = automatic (effective_fuse_ln): 3 with the single-value stream (x travels by TMA), 2 with the
+                                     # [hi | lo] pair (the short-K wo GEMM is epilogue-bound when fused: measured)
         self.max_chunk = 8           # samples pushed through the kernels per launch sequence
 
     def _init_weights(self):
@@ -210,13 +210,18 @@ class SwinV2(_Base):
                     nn.init.zeros_(m.bias)
 
     # ------------------------------------------------------------------ engine management
+    def effective_fuse_ln(self) -> int:
+        if self.fuse_ln is not None:
+            return int(self.fuse_ln)
+        return 3 if (self.act_fp16 and self.x_single) else 2
+
     def _params_key(self):
         return tuple((p.data_ptr(), p._version, p.device) for p in self.parameters())
 
     def engine(self) -> Engine:
         """The packed CUDA engine for the current parameter values (re-packed when parameters change)."""
         key = (self._params_key(), self.split_embed, self.split_head, self.max_chunk, self.act_fp16, self.gemm_tile, self.attn_impl,
-               self.fuse_ln, self.attn_fp16, self.x_single)
+               self.effective_fuse_ln(), self.attn_fp16, self.x_single)
         if self._engine is None or self._engine_key != key:
             dev = self.pos_embed.device
             if dev.type != "cuda":
@@ -224,7 +229,7 @@ class SwinV2(_Base):
                                    "there is no CPU fallback")
             sd = {k: v for k, v in self.state_dict().items()}
             self._engine = Engine(sd, self.geometry, dev, self.split_embed, self.split_head, self.max_chunk,
-                                  self.act_fp16, self.gemm_tile, self.attn_impl, self.fuse_ln, self.attn_fp16,
+                                  self.act_fp16, self.gemm_tile, self.attn_impl, self.effective_fuse_ln(), self.attn_fp16,
                                   self.x_single)
             self._engine_key = key
         return self._engine
