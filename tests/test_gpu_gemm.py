@@ -153,7 +153,8 @@ def test_gemm_embed_epilogue_single_value_stream(lib, cg):
 
 
 @pytest.mark.parametrize("cg", [3, 2], ids=["tile256x352", "tile256x176"])
-@pytest.mark.parametrize("B,T,D,K", [(3, 256, 264, 264), (3, 256, 1056, 1056), (2, 512, 1056, 2816), (6, 8192, 1056, 264)])
+@pytest.mark.parametrize("B,T,D,K", [(3, 256, 264, 264), (5, 160, 528, 704), (3, 256, 1056, 1056), (2, 512, 1056, 2816),
+                                     (6, 8192, 1056, 264)])
 def test_gemm_ln_residual_epilogue_single_value_stream(lib, cg, B, T, D, K):
     """EPI_LN_RES with format word 3: x (hi half only) += LayerNorm(A W^T) * gain + bias, one fp16 rounding per update; the lo
     half is neither read nor written."""
